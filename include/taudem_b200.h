@@ -1,0 +1,159 @@
+/* taudem_b200 — C ABI of the B200-native TauDEM flow-direction / contributing-area path.
+ *
+ * Three layers, all `extern "C"`, plain pointers and sizes only:
+ *
+ *  1. FILE level  — drop-in replacements for the five reference library
+ *     functions that the reference's mains call (same parameter lists, bool -> int):
+ *       td_flood      <- int flood(...)     reference src/flood.h,  src/flood.cpp:50
+ *       td_setdird8   <- int setdird8(...)  reference src/d8.h:7,   src/d8.cpp:181
+ *       td_setdir     <- int setdir(...)    reference src/tardemlib.h:70, src/dinf.cpp:109
+ *       td_aread8     <- int aread8(...)    reference src/aread8.h:3,   src/aread8.cpp:56
+ *       td_area       <- int area(...)      reference src/areadinf.h:2, src/areadinf.cpp:53
+ *     They read/write rasters with the tiffIO contract (src/tiffIO.cpp) and return 0 on
+ *     success, non-zero on error, like the reference.
+ *
+ *  2. HOST-GRID level — the same computations on caller-owned host arrays
+ *     (row-major, row 0 = north, `nx` columns, `ny` rows, dense).  Host<->device
+ *     copies happen inside the call.  This is what a binding that already holds
+ *     the rasters in memory (e.g. a GDAL- or numpy-based caller) uses.
+ *
+ *  3. DEVICE-STRIP level — kernels on device-resident row strips, the unit the
+ *     reference distributes over MPI ranks (src/linearpart.h:125-166).  A strip
+ *     buffer holds `ny + 2` rows of `pitch` elements: row 0 is the halo row
+ *     above, rows 1..ny are owned, row ny+1 is the halo row below
+ *     (topBorder/bottomBorder, src/linearpart.h:66-67).  `has_top/has_bot` say
+ *     whether a neighbouring strip exists (hasAccess, src/linearpart.h:178-190).
+ *     `stream` is a cudaStream_t passed as void*.
+ *
+ * No CPU fallback exists: every compute entry point fails (TD_ERR_CUDA) when no
+ * CUDA device is usable.
+ */
+#ifndef TAUDEM_B200_H
+#define TAUDEM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TD_OK 0
+#define TD_ERR_ARG 1      /* bad argument / size mismatch (reference: return 1)        */
+#define TD_ERR_IO 21      /* cannot open raster (reference: MPI_Abort(MCW,21))          */
+#define TD_ERR_DRIVER 22  /* output driver unavailable (reference: MPI_Abort(MCW,22))   */
+#define TD_ERR_MISMATCH 5 /* companion raster mismatch (reference: MPI_Abort(MCW,5))    */
+#define TD_ERR_CUDA 90    /* CUDA runtime failure / no device                           */
+#define TD_ERR_ALLOC 91   /* device or host allocation failure (reference: -999)        */
+
+/* ---- version / diagnostics -------------------------------------------------------- */
+const char* td_version(void);            /* "5.4.0-b200" (TDVERSION, src/commonLib.h:63)  */
+const char* td_last_error(void);         /* thread-local message for the last failure     */
+int td_device_count(void);               /* number of CUDA devices, 0 if none             */
+int td_set_device(int dev);
+/* Kernels launched by this library since the last reset (bench `gpu_launches`). */
+unsigned long long td_launch_count(void);
+void td_reset_launch_count(void);
+/* Seconds spent inside the device-resident compute part of the last host-grid or
+ * file-level call (the reference's "Compute time", e.g. src/aread8.cpp:175,307). */
+double td_last_compute_seconds(void);
+
+/* ---- 1. file level ---------------------------------------------------------------- */
+int td_flood(const char* demfile, const char* felfile, const char* sfdrfile, int usesfdr,
+             int verbose, int is_4Point, int use_mask, const char* maskfile);
+int td_setdird8(const char* demfile, const char* pointfile, const char* slopefile,
+                const char* flowfile, int useflowfile);
+int td_setdir(const char* demfile, const char* angfile, const char* slopefile,
+              const char* flowfile, int useflowfile);
+int td_aread8(const char* pfile, const char* afile, const char* datasrc, const char* lyrname,
+              int uselyrname, int lyrno, const char* wfile, int useOutlets, int usew,
+              int contcheck);
+int td_area(const char* angfile, const char* scafile, const char* datasrc, const char* lyrname,
+            int uselyrname, int lyrno, const char* wfile, int useOutlets, int usew,
+            int contcheck);
+/* reference src/commonLib.cpp:53-73 */
+int td_nameadd(char* full, const char* arg, const char* suff);
+
+/* raster file helpers (tiffIO contract) used by the CLI, tests and bindings */
+int td_raster_info(const char* path, int* nx, int* ny, double* nodata, int* has_nodata,
+                   double* dx, double* dy, int* is_geographic, int* bits, int* sample_format);
+/* dtype: 0 = int16, 1 = int32, 2 = float32 (SHORT_TYPE/LONG_TYPE/FLOAT_TYPE) */
+int td_raster_read(const char* path, int dtype, void* dest, int nx, int ny);
+int td_raster_cell_sizes(const char* path, double* dxc, double* dyc, int ny);
+/* like_path may be NULL (no georeferencing); compression: 1 none, 5 LZW, 8 Deflate */
+int td_raster_write(const char* path, int dtype, const void* src, int nx, int ny, double nodata,
+                    const char* like_path, double dx, double dy, int compression);
+
+/* ---- 2. host-grid level ------------------------------------------------------------ */
+/* dxc/dyc: per-row cell sizes (ny doubles each; tiffIO::getdxc/getdyc). */
+int td_flood_host(const float* dem, float* fel, const int16_t* depmask /*may be NULL*/,
+                  int nx, int ny, float dem_nodata, int is_4Point);
+int td_setdird8_host(const float* fel, int16_t* p, float* sd8, int nx, int ny,
+                     float fel_nodata, const double* dxc, const double* dyc);
+int td_setdir_host(const float* fel, float* ang, float* slp, int nx, int ny, float fel_nodata,
+                   const double* dxc, const double* dyc);
+int td_aread8_host(const int16_t* p, const float* w /*NULL unless usew*/, float* ad8, int nx,
+                   int ny, int16_t p_nodata, float w_nodata, int contcheck);
+int td_area_host(const float* ang, const float* w /*NULL unless usew*/, float* sca, int nx, int ny,
+                 float ang_nodata, float w_nodata, const double* dxc, const double* dyc,
+                 int contcheck);
+
+/* ---- 3. device-strip level ----------------------------------------------------------- */
+typedef struct td_strip {
+  int nx;       /* columns of the grid                                                  */
+  int ny;       /* rows owned by this strip                                             */
+  int pitch;    /* elements per stored row, multiple of 32, >= nx                       */
+  int has_top;  /* 1 if a strip exists above (row 0 holds its last row)                 */
+  int has_bot;  /* 1 if a strip exists below (row ny+1 holds its first row)             */
+} td_strip;
+
+typedef struct td_ctx td_ctx;   /* per-device scratch (frontier queues, counters) */
+td_ctx* td_ctx_create(void);
+void td_ctx_destroy(td_ctx*);
+int td_pitch_for(int nx);        /* smallest legal pitch */
+
+/* synthetic fractal DEM written straight into a strip (bench/test input generator) */
+int td_gen_dem_dev(float* dem, td_strip s, int row0_global, int total_ny, unsigned seed,
+                   float hurst, float tilt, void* stream);
+int td_gen_weights_dev(float* w, td_strip s, int row0_global, unsigned seed, void* stream);
+
+/* pit filling: init (src/flood.cpp:243-271) + relaxation to the fixed point (:292-479).
+ * td_flood_relax_dev runs tile-local relaxation rounds until no tile of this strip changes
+ * given the current halo rows; *changed_out (host) tells whether anything moved.          */
+int td_flood_init_dev(td_ctx*, const float* dem, const int16_t* depmask, float* planchon,
+                      td_strip s, float dem_nodata, int is_4Point, void* stream);
+int td_flood_relax_dev(td_ctx*, const float* dem, float* planchon, td_strip s, int is_4Point,
+                       int* changed_out, void* stream);
+
+/* D8: setPosDir+calcSlope stencil (src/d8.cpp:359-409,153-177); dxc/dyc are DEVICE arrays
+ * of ny doubles.  *nflat_out (host) = number of dir==0 cells in the strip.                */
+int td_d8_slopes_dev(td_ctx*, const float* fel, int16_t* p, float* sd8, td_strip s,
+                     float fel_nodata, const double* dxc, const double* dyc,
+                     long long* nflat_out, void* stream);
+/* Garbrecht-Martz flat resolution, all iterations (src/d8.cpp:302-317,459-680).
+ * fel is modified like the reference modifies elevDEM.  Single strip only.              */
+int td_d8_flats_dev(td_ctx*, float* fel, int16_t* p, td_strip s, const double* dxc,
+                    const double* dyc, long long* nflat_left, void* stream);
+
+/* D-infinity: setPosDirDinf/SET2/VSLOPE stencil (src/dinf.cpp:530-595,317-373,286-313) */
+int td_dinf_slopes_dev(td_ctx*, const float* fel, float* ang, float* slp, td_strip s,
+                       float fel_nodata, const double* dxc, const double* dyc,
+                       long long* nflat_out, void* stream);
+int td_dinf_flats_dev(td_ctx*, float* fel, float* ang, td_strip s, const double* dxc,
+                      const double* dyc, long long* nflat_left, void* stream);
+
+/* contributing area.  *_deps_dev = initNeighborD8up / initNeighborDinfup
+ * (src/commonLib.cpp:240-283, 92-136): fills the strip's dependency state inside ctx.
+ * *_sweep_dev = the evaluation wavefront (src/aread8.cpp:216-304, src/areadinf.cpp:173-265)
+ * run until this strip has no ready cell left.  For one strip that is the whole job.
+ * *_deps_dev also initialises the output raster to its nodata value (-1).                 */
+int td_aread8_deps_dev(td_ctx*, const int16_t* p, float* ad8, td_strip s, int16_t p_nodata, void* stream);
+int td_aread8_sweep_dev(td_ctx*, const float* w, float* ad8, td_strip s, float w_nodata, int usew,
+                        int contcheck, void* stream);
+int td_area_deps_dev(td_ctx*, const float* ang, float* sca, td_strip s, float ang_nodata,
+                     const double* dxc, const double* dyc, void* stream);
+int td_area_sweep_dev(td_ctx*, const float* ang, const float* w, float* sca, td_strip s, int usew,
+                      int contcheck, const double* dxc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAUDEM_B200_H */

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY: forwards to the oracle GDAL shim.
+#pragma once
+#include "gdal.h"

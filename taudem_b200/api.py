@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+File level: ``flood``, ``setdird8``, ``setdir``, ``aread8``, ``area`` take the same
+arguments, in the same order and with the same meaning, as the reference functions
+(src/flood.cpp:50, src/d8.cpp:181, src/dinf.cpp:109, src/aread8.cpp:56,
+src/areadinf.cpp:53) and return 0 on success like they do.
+
+Grid level: ``*_grid`` functions run the same device path on numpy arrays (row 0 =
+north).  dx/dy may be scalars (projected grids) or per-row arrays (geographic grids,
+tiffIO::getdxc/getdyc).
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+_DT = {np.dtype(np.int16): 0, np.dtype(np.int32): 1, np.dtype(np.float32): 2}
+
+FEL_NODATA = np.float32(-3.0e38)            # src/flood.cpp:136
+MISSINGFLOAT = np.float32(-3.4028234663852886e38)   # src/commonLib.h:80
+MISSINGSHORT = np.int16(-32768)             # src/commonLib.h:77
+
+
+def _b(s):
+    return (s or "").encode()
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _rows(v, ny):
+    a = np.asarray(v, dtype=np.float64)
+    if a.ndim == 0:
+        a = np.full(ny, float(a), dtype=np.float64)
+    if a.shape != (ny,):
+        raise ValueError("per-row cell sizes must have one value per row")
+    return np.ascontiguousarray(a)
+
+
+def _grid(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.ndim != 2:
+        raise ValueError("rasters are 2-D arrays")
+    return a
+
+
+# --------------------------------------------------------------------- file level
+def flood(demfile, felfile, sfdrfile="", usesfdr=0, verbose=False, is_4Point=False, use_mask=False, maskfile=""):
+    return lib().td_flood(_b(demfile), _b(felfile), _b(sfdrfile), int(usesfdr), int(verbose), int(is_4Point), int(use_mask), _b(maskfile))
+
+
+def setdird8(demfile, pointfile, slopefile, flowfile="", useflowfile=0):
+    return lib().td_setdird8(_b(demfile), _b(pointfile), _b(slopefile), _b(flowfile), int(useflowfile))
+
+
+def setdir(demfile, angfile, slopefile, flowfile="", useflowfile=0):
+    return lib().td_setdir(_b(demfile), _b(angfile), _b(slopefile), _b(flowfile), int(useflowfile))
+
+
+def aread8(pfile, afile, datasrc="", lyrname="", uselyrname=0, lyrno=0, wfile="", useOutlets=0, usew=0, contcheck=1):
+    return lib().td_aread8(_b(pfile), _b(afile), _b(datasrc), _b(lyrname), int(uselyrname), int(lyrno), _b(wfile), int(useOutlets), int(usew), int(contcheck))
+
+
+def area(angfile, scafile, datasrc="", lyrname="", uselyrname=0, lyrno=0, wfile="", useOutlets=0, usew=0, contcheck=1):
+    return lib().td_area(_b(angfile), _b(scafile), _b(datasrc), _b(lyrname), int(uselyrname), int(lyrno), _b(wfile), int(useOutlets), int(usew), int(contcheck))
+
+
+def nameadd(arg, suff):
+    buf = C.create_string_buffer(4096)
+    lib().td_nameadd(buf, _b(arg), _b(suff))
+    return buf.value.decode()
+
+
+# --------------------------------------------------------------------- raster files
+def raster_info(path):
+    nx, ny, hn, geo, bits, fmt = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    nd, dx, dy = C.c_double(), C.c_double(), C.c_double()
+    check(lib().td_raster_info(_b(path), C.byref(nx), C.byref(ny), C.byref(nd), C.byref(hn), C.byref(dx), C.byref(dy),
+                               C.byref(geo), C.byref(bits), C.byref(fmt)))
+    return dict(nx=nx.value, ny=ny.value, nodata=nd.value, has_nodata=bool(hn.value), dx=dx.value, dy=dy.value,
+                is_geographic=bool(geo.value), bits=bits.value, sample_format=fmt.value)
+
+
+def read_raster(path, dtype=np.float32):
+    info = raster_info(path)
+    out = np.empty((info["ny"], info["nx"]), dtype=dtype)
+    check(lib().td_raster_read(_b(path), _DT[np.dtype(dtype)], _ptr(out), info["nx"], info["ny"]))
+    return out
+
+
+def write_raster(path, arr, nodata, like=None, dx=30.0, dy=30.0, compression=1):
+    arr = np.ascontiguousarray(arr)
+    check(lib().td_raster_write(_b(path), _DT[arr.dtype], _ptr(arr), arr.shape[1], arr.shape[0], float(nodata),
+                                _b(like) if like else None, float(dx), float(dy), int(compression)))
+
+
+# --------------------------------------------------------------------- grid level
+def pitremove_grid(dem, nodata=-9999.0, depmask=None, is_4Point=False, out=None):
+    dem = _grid(dem, np.float32)
+    ny, nx = dem.shape
+    fel = out if out is not None else np.empty_like(dem)
+    m = None if depmask is None else _grid(depmask, np.int16)
+    check(lib().td_flood_host(_ptr(dem), _ptr(fel), _ptr(m), nx, ny, np.float32(nodata), int(is_4Point)))
+    return fel
+
+
+def d8flowdir_grid(fel, nodata=float(FEL_NODATA), dx=30.0, dy=30.0, out=None):
+    fel = _grid(fel, np.float32)
+    ny, nx = fel.shape
+    p, sd8 = out if out is not None else (np.empty((ny, nx), np.int16), np.empty((ny, nx), np.float32))
+    dxc, dyc = _rows(dx, ny), _rows(dy, ny)
+    check(lib().td_setdird8_host(_ptr(fel), _ptr(p), _ptr(sd8), nx, ny, np.float32(nodata), _ptr(dxc), _ptr(dyc)))
+    return p, sd8
+
+
+def dinfflowdir_grid(fel, nodata=float(FEL_NODATA), dx=30.0, dy=30.0, out=None):
+    fel = _grid(fel, np.float32)
+    ny, nx = fel.shape
+    ang, slp = out if out is not None else (np.empty((ny, nx), np.float32), np.empty((ny, nx), np.float32))
+    dxc, dyc = _rows(dx, ny), _rows(dy, ny)
+    check(lib().td_setdir_host(_ptr(fel), _ptr(ang), _ptr(slp), nx, ny, np.float32(nodata), _ptr(dxc), _ptr(dyc)))
+    return ang, slp
+
+
+def aread8_grid(p, nodata=int(MISSINGSHORT), weights=None, w_nodata=-9999.0, contcheck=True, out=None):
+    p = _grid(p, np.int16)
+    ny, nx = p.shape
+    ad8 = out if out is not None else np.empty((ny, nx), np.float32)
+    w = None if weights is None else _grid(weights, np.float32)
+    check(lib().td_aread8_host(_ptr(p), _ptr(w), _ptr(ad8), nx, ny, int(nodata), np.float32(w_nodata), int(contcheck)))
+    return ad8
+
+
+def areadinf_grid(ang, nodata=float(MISSINGFLOAT), weights=None, w_nodata=-9999.0, dx=30.0, dy=30.0, contcheck=True, out=None):
+    ang = _grid(ang, np.float32)
+    ny, nx = ang.shape
+    sca = out if out is not None else np.empty((ny, nx), np.float32)
+    w = None if weights is None else _grid(weights, np.float32)
+    dxc, dyc = _rows(dx, ny), _rows(dy, ny)
+    check(lib().td_area_host(_ptr(ang), _ptr(w), _ptr(sca), nx, ny, np.float32(nodata), np.float32(w_nodata), _ptr(dxc), _ptr(dyc), int(contcheck)))
+    return sca

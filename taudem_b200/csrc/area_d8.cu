@@ -1,0 +1,172 @@
+// D8 contributing area: dependency stencil + chain-following evaluation sweep.
+//
+// reference: initNeighborD8up src/commonLib.cpp:240-283 (in-degree per cell),
+//            aread8 main loop   src/aread8.cpp:216-304 (pull-gather in k order,
+//            decrement the downslope cell, enqueue when its count reaches zero).
+//
+// The reference's result is a deterministic gather — area(c) = ((w|1) + a_k1) + a_k2 ...
+// over the neighbours that drain into c, in k = 1..8 order, float32 — evaluated once
+// per cell in ANY topological order, so the GPU schedule below is bit-exact:
+//
+//   k_deps_d8  : 3x3 stencil over p -> node (u16: inflow mask | dir | flags) and
+//                cnt (u8: remaining inflow count).  5 B/cell written-read, streamed
+//                through TMA-staged shared-memory tiles.
+//   k_sweep_d8 : one thread per cell; threads on source cells (no inflow) evaluate
+//                their cell, decrement the downslope count with an acq_rel atomic
+//                and, when they were the last arrival, keep walking down the chain
+//                (no queue round trip).  Every non-source cell is evaluated by the
+//                thread whose decrement brought its count to zero.
+//   Cross-strip edges (multi-GPU): a decrement that targets a halo row is recorded
+//   in ctx.halo and shipped to the neighbour strip by the caller (src/aread8.cpp:282-297).
+#include "common.cuh"
+#include "ctx.h"
+
+namespace td {
+namespace {
+constexpr int TW = 128, TH = 32;
+
+constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
+
+__global__ void __launch_bounds__(256) k_deps_d8(const short* __restrict__ p, unsigned short* __restrict__ node,
+                                                 unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,
+                                                 short nodata) {
+  using G = TileGeom<short, TW, TH>;
+  __shared__ __align__(128) short tile[G::ELEMS];
+  __shared__ __align__(8) uint64_t bar;
+  const int c0 = blockIdx.x * TW, r0 = 1 + blockIdx.y * TH;
+  load_tile_tma<short, TW, TH>(tile, &bar, p, s, r0, c0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int pass = 0; pass < TH / 8; ++pass) {
+    const int tr = warp + 8 * pass;
+    const int r = r0 + tr, c = c0 + lane * 4;
+    if (r > s.ny || c >= s.pitch) continue;
+    const short* pm = tile + tr * G::SW + G::HP + lane * 4;
+    short nb[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const short* q = pm + j * G::SW;
+      const short4 v = *reinterpret_cast<const short4*>(q);
+      nb[j][0] = q[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = q[4];
+    }
+    unsigned short on4[4]; unsigned char oc4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cc = c + i;
+      const short d = nb[1][i + 1];
+      const bool valid = cc < s.nx && !nd_s(d, nodata) && d >= 0 && d <= 8;
+      unsigned mask = 0; bool con = false;
+#pragma unroll
+      for (int k = 1; k <= 8; ++k) {
+        const short dn = nb[1 + drow(k)][i + 1 + dcol(k)];
+        if (!s.on_grid(r + drow(k), cc + dcol(k)) || nd_s(dn, nodata)) con = true;
+        else if (dn - k == 4 || dn - k == -4) {
+          if (dn >= 0 && dn <= 8) mask |= 1u << (k - 1);
+          else con = true;   // counted by the evaluation loop but never evaluated -> nodata area
+        }
+      }
+      on4[i] = valid ? (unsigned short)(NODE_VALID | (con ? NODE_CON : 0u) | ((unsigned)d << 8) | mask) : (unsigned short)0;
+      oc4[i] = valid ? (unsigned char)__popc(mask) : (unsigned char)0xff;
+    }
+    const long long o = s.idx(r, c);
+    *reinterpret_cast<ushort4*>(node + o) = make_ushort4(on4[0], on4[1], on4[2], on4[3]);
+    *reinterpret_cast<uchar4*>(cnt + o) = make_uchar4(oc4[0], oc4[1], oc4[2], oc4[3]);
+    // the area partition starts as nodata (-1) everywhere (src/aread8.cpp:193)
+    *reinterpret_cast<float4*>(area + o) = make_float4(-1.f, -1.f, -1.f, -1.f);
+  }
+}
+
+__device__ __forceinline__ unsigned atom_dec_byte(unsigned* words, long long cell) {
+  unsigned* a = words + (cell >> 2);
+  const unsigned sh = (unsigned)(cell & 3) * 8u;
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
+  return (old >> sh) & 0xffu;
+}
+
+// SRC = 0: threads map to the owned cells of the strip and start on sources.
+// SRC = 1: threads map to a list of cells that are ready (count already zero).
+template <int SRC>
+__global__ void __launch_bounds__(256) k_sweep_d8(const unsigned short* __restrict__ node, unsigned* __restrict__ cntw,
+                                                  float* __restrict__ area, const float* __restrict__ w, Strip s,
+                                                  float w_nodata, int usew, int contcheck, int* __restrict__ halo,
+                                                  const long long* __restrict__ list, unsigned long long nlist) {
+  int r, c;
+  if (SRC == 0) {
+    // 64 columns x 4 rows per CTA
+    c = blockIdx.x * 64 + (threadIdx.x & 63);
+    r = 1 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r > s.ny || c >= s.nx) return;
+  } else {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlist) return;
+    const long long ci = list[t];
+    r = (int)(ci / s.pitch); c = (int)(ci - (long long)r * s.pitch);
+  }
+  long long ci = s.idx(r, c);
+  unsigned nd = node[ci];
+  if (!(nd & NODE_VALID)) return;
+  if (SRC == 0 && (nd & 0xffu)) return;          // not a source
+
+  for (;;) {
+    // ---- flow algebra (src/aread8.cpp:228-257)
+    float a;
+    if (usew) { const float wv = w[ci]; a = nd_f(wv, w_nodata) ? -1.0f : wv; }
+    else a = 1.0f;
+    bool con = (nd & NODE_CON) != 0;
+    unsigned m = nd & 0xffu;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      if (m & (1u << (k - 1))) {
+        const float an = __ldcg(area + ci + (long long)drow(k) * s.pitch + dcol(k));
+        if (nd_f(an, -1.0f)) con = true;
+        else a = a + an;
+      }
+    }
+    if (con && contcheck) a = -1.0f;
+    area[ci] = a;
+    // ---- decrement the downslope cell (src/aread8.cpp:261-272)
+    const int d = (int)((nd >> 8) & 0xfu);
+    if (d < 1 || d > 8) return;
+    const int rn = r + drow(d), cn = c + dcol(d);
+    if (!s.on_grid(rn, cn)) return;
+    const long long cin = s.idx(rn, cn);
+    if (rn == 0 || rn == s.ny + 1) {               // crosses into the neighbour strip
+      __threadfence();
+      atomicAdd(halo + (rn == 0 ? 0 : s.pitch) + cn, 1);
+      return;
+    }
+    const unsigned ndn = node[cin];
+    if (!(ndn & NODE_VALID)) return;
+    if (atom_dec_byte(cntw, cin) != 1u) return;     // someone else will arrive later
+    r = rn; c = cn; ci = cin; nd = ndn;
+  }
+}
+}  // namespace
+
+cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s, short nodata,
+                           cudaStream_t st) {
+  dim3 grid((s.pitch + TW - 1) / TW, (s.ny + TH - 1) / TH);
+  k_deps_d8<<<grid, 256, 0, st>>>(p, node, cnt, area, s, nodata);
+  TD_LAUNCHED();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sweep_d8(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
+                            float w_nodata, int usew, int contcheck, int* halo, cudaStream_t st) {
+  dim3 grid((s.nx + 63) / 64, (s.ny + 3) / 4);
+  k_sweep_d8<0><<<grid, 256, 0, st>>>(node, cntw, area, w, s, w_nodata, usew, contcheck, halo, nullptr, 0ull);
+  TD_LAUNCHED();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sweep_d8_list(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
+                                 float w_nodata, int usew, int contcheck, int* halo, const long long* list,
+                                 unsigned long long n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  k_sweep_d8<1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(node, cntw, area, w, s, w_nodata, usew, contcheck, halo, list, n);
+  TD_LAUNCHED();
+  return cudaGetLastError();
+}
+
+}  // namespace td

@@ -1,0 +1,218 @@
+// D-infinity contributing area: dependency stencil + evaluation sweep.
+//
+// reference: prop()              src/commonLib.cpp:76-91  (share of a cell's flow going to neighbour k)
+//            initNeighborDinfup  src/commonLib.cpp:92-136 (in-degree = #neighbours with prop > 0)
+//            area() main loop    src/areadinf.cpp:173-265 (k-ordered gather
+//                                areares = (float)(areares + p*area_n), + weight or dxc[row],
+//                                then decrement every neighbour that receives flow).
+// prop's table aref[] = {-t,0,t,PI/2,PI-t,PI,PI+t,3PI/2,2PI-t,2PI} with t = atan2(dy,dx)
+// is rebuilt on the device from t (host glibc atan2, per row) using only +,-: the same
+// doubles as the reference.  The per-cell value is a deterministic gather, so any
+// topological schedule reproduces it.
+#include "common.cuh"
+#include "ctx.h"
+
+namespace td {
+namespace {
+constexpr int TW = 128, TH = 32;
+constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
+
+__device__ __forceinline__ double aref(int i, double t) {
+  // i in 0..9
+  const double PI = TD_PI;
+  switch (i) {
+    case 0: return -t;
+    case 1: return 0.;
+    case 2: return t;
+    case 3: return (double)(0.5 * PI);
+    case 4: return PI - t;
+    case 5: return (double)PI;
+    case 6: return PI + t;
+    case 7: return (double)(1.5 * PI);
+    case 8: return 2. * PI - t;
+    default: return (double)(2. * PI);
+  }
+}
+
+// src/commonLib.cpp:76-91
+__device__ __forceinline__ double prop_dev(float a, int k, double t) {
+  const double PI = TD_PI;
+  double p = 0.;
+  if (k <= 0) k = k + 8;
+  if (k == 1 && a > PI) a = (float)(a - 2.0 * PI);
+  const double lo = aref(k - 1, t), hi = aref(k + 1, t);
+  if (a > lo && a < hi) {
+    const double mid = aref(k, t);
+    if (a > mid) p = (hi - a) / (hi - mid);
+    else p = (a - lo) / (mid - lo);
+  }
+  if (p < 1e-5) return -1.;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang, unsigned short* __restrict__ node,
+                                                   unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,
+                                                   float nodata, const double* __restrict__ theta) {
+  using G = TileGeom<float, TW, TH>;
+  __shared__ __align__(128) float tile[G::ELEMS];
+  __shared__ __align__(8) uint64_t bar;
+  const int c0 = blockIdx.x * TW, r0 = 1 + blockIdx.y * TH;
+  load_tile_tma<float, TW, TH>(tile, &bar, ang, s, r0, c0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int pass = 0; pass < TH / 8; ++pass) {
+    const int tr = warp + 8 * pass;
+    const int r = r0 + tr, c = c0 + lane * 4;
+    if (r > s.ny || c >= s.pitch) continue;
+    const float* pm = tile + tr * G::SW + G::HP + lane * 4;
+    float nb[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float* q = pm + j * G::SW;
+      const float4 v = *reinterpret_cast<const float4*>(q);
+      nb[j][0] = q[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = q[4];
+    }
+    // atan2(dy,dx) of the rows above / at / below (clamped to the strip's own rows)
+    double th[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) th[j] = theta[min(max(r - 2 + j, 0), s.ny - 1)];
+    unsigned short on4[4]; unsigned char oc4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cc = c + i;
+      const bool valid = cc < s.nx && !nd_f(nb[1][i + 1], nodata);
+      unsigned mask = 0; bool con = false;
+#pragma unroll
+      for (int k = 1; k <= 8; ++k) {
+        const float an = nb[1 + drow(k)][i + 1 + dcol(k)];
+        if (!s.on_grid(r + drow(k), cc + dcol(k)) || nd_f(an, nodata)) con = true;
+        else {
+          const float p = (float)prop_dev(an, (k + 4) % 8, th[1 + drow(k)]);   // float p as in initNeighborDinfup
+          if (p > 0.0) mask |= 1u << (k - 1);
+        }
+      }
+      on4[i] = valid ? (unsigned short)(NODE_VALID | (con ? NODE_CON : 0u) | mask) : (unsigned short)0;
+      oc4[i] = valid ? (unsigned char)__popc(mask) : (unsigned char)0xff;
+    }
+    const long long o = s.idx(r, c);
+    *reinterpret_cast<ushort4*>(node + o) = make_ushort4(on4[0], on4[1], on4[2], on4[3]);
+    *reinterpret_cast<uchar4*>(cnt + o) = make_uchar4(oc4[0], oc4[1], oc4[2], oc4[3]);
+    *reinterpret_cast<float4*>(area + o) = make_float4(-1.f, -1.f, -1.f, -1.f);   // src/areadinf.cpp:154
+  }
+}
+
+__device__ __forceinline__ unsigned atom_dec_byte(unsigned* words, long long cell) {
+  unsigned* a = words + (cell >> 2);
+  const unsigned sh = (unsigned)(cell & 3) * 8u;
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
+  return (old >> sh) & 0xffu;
+}
+
+constexpr int STK = 12;
+
+// counters[0] = overflow list length, counters[1] = overflow list overflowed (fatal)
+template <int SRC>
+__global__ void __launch_bounds__(256) k_sweep_dinf(const unsigned short* __restrict__ node, unsigned* __restrict__ cntw,
+                                                    const float* __restrict__ ang, float* __restrict__ area,
+                                                    const float* __restrict__ w, Strip s, int usew, int contcheck,
+                                                    const double* __restrict__ theta, const double* __restrict__ dxc,
+                                                    int* __restrict__ halo, const long long* __restrict__ list,
+                                                    unsigned long long nlist, long long* __restrict__ ovf,
+                                                    unsigned long long ovf_cap, unsigned long long* __restrict__ counters) {
+  int r, c;
+  if (SRC == 0) {
+    c = blockIdx.x * 64 + (threadIdx.x & 63);
+    r = 1 + blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (r > s.ny || c >= s.nx) return;
+  } else {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nlist) return;
+    const long long ci0 = list[t];
+    r = (int)(ci0 / s.pitch); c = (int)(ci0 - (long long)r * s.pitch);
+  }
+  long long ci = s.idx(r, c);
+  unsigned nd = node[ci];
+  if (!(nd & NODE_VALID)) return;
+  if (SRC == 0 && (nd & 0xffu)) return;
+
+  long long stack[STK];
+  int sp = 0;
+  for (;;) {
+    // ---- flow algebra (src/areadinf.cpp:187-218)
+    float areares = 0.f;
+    bool con = (nd & NODE_CON) != 0;
+    const unsigned m = nd & 0xffu;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      if (m & (1u << (k - 1))) {
+        const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
+        const double p = prop_dev(ang[ni], (k + 4) % 8, theta[min(max(r - 1 + drow(k), 0), s.ny - 1)]);
+        const float an = __ldcg(area + ni);
+        if (nd_f(an, -1.0f)) con = true;
+        else areares = (float)((double)areares + p * (double)an);
+      }
+    }
+    if (usew) areares = areares + w[ci];
+    else areares = (float)((double)areares + dxc[r - 1]);
+    area[ci] = (con && contcheck) ? -1.0f : areares;
+
+    // ---- decrement every neighbour that receives flow (src/areadinf.cpp:221-239)
+    const float a0 = ang[ci];
+    const double t0 = theta[r - 1];
+    long long next = -1; int nr = 0, nc = 0; unsigned nnd = 0;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      if (prop_dev(a0, k, t0) > 0.0) {
+        const int rn = r + drow(k), cn = c + dcol(k);
+        if (!s.on_grid(rn, cn)) continue;
+        const long long cin = s.idx(rn, cn);
+        if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
+        const unsigned ndn = node[cin];
+        if (!(ndn & NODE_VALID)) continue;
+        if (atom_dec_byte(cntw, cin) == 1u) {
+          if (next < 0) { next = cin; nr = rn; nc = cn; nnd = ndn; }
+          else if (sp < STK) stack[sp++] = cin;
+          else {
+            const unsigned long long slot = atomicAdd(counters, 1ull);
+            if (slot < ovf_cap) ovf[slot] = cin; else counters[1] = 1ull;
+          }
+        }
+      }
+    }
+    if (next >= 0) { ci = next; r = nr; c = nc; nd = nnd; }
+    else if (sp > 0) {
+      ci = stack[--sp];
+      r = (int)(ci / s.pitch); c = (int)(ci - (long long)r * s.pitch);
+      nd = node[ci];
+    } else return;
+  }
+}
+}  // namespace
+
+cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
+                             float nodata, const double* theta, cudaStream_t st) {
+  dim3 grid((s.pitch + TW - 1) / TW, (s.ny + TH - 1) / TH);
+  k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, s, nodata, theta);
+  TD_LAUNCHED();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sweep_dinf(const unsigned short* node, unsigned* cntw, const float* ang, float* area, const float* w,
+                              const Strip& s, int usew, int contcheck, const double* theta, const double* dxc, int* halo,
+                              const long long* list, unsigned long long nlist, long long* ovf, unsigned long long ovf_cap,
+                              unsigned long long* counters, cudaStream_t st) {
+  if (list == nullptr) {
+    dim3 grid((s.nx + 63) / 64, (s.ny + 3) / 4);
+    k_sweep_dinf<0><<<grid, 256, 0, st>>>(node, cntw, ang, area, w, s, usew, contcheck, theta, dxc, halo, nullptr, 0ull, ovf,
+                                         ovf_cap, counters);
+  } else {
+    if (nlist == 0) return cudaSuccess;
+    k_sweep_dinf<1><<<(unsigned)((nlist + 255) / 256), 256, 0, st>>>(node, cntw, ang, area, w, s, usew, contcheck, theta, dxc,
+                                                                   halo, list, nlist, ovf, ovf_cap, counters);
+  }
+  TD_LAUNCHED();
+  return cudaGetLastError();
+}
+
+}  // namespace td

@@ -1,0 +1,374 @@
+// C ABI of taudem_b200: device-strip level and host-grid level entry points
+// (declared in include/taudem_b200.h).  File-level entry points live in tools.cpp.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace td {
+unsigned long long g_launches = 0;
+static thread_local std::string g_err;
+static double g_compute_s = 0.0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return (e == cudaErrorMemoryAllocation) ? TD_ERR_ALLOC : TD_ERR_CUDA;
+}
+void set_compute_seconds(double s) { g_compute_s = s; }
+}  // namespace td
+
+using td::Strip;
+
+td_ctx::td_ctx() {
+  cudaMalloc(&d_ctr, 32 * sizeof(unsigned long long));
+  cudaMallocHost(&h_ctr, 32 * sizeof(unsigned long long));
+  if (d_ctr) cudaMemset(d_ctr, 0, 32 * sizeof(unsigned long long));
+}
+td_ctx::~td_ctx() {
+  node.release(); cnt.release(); lev.release(); mk.release(); listA.release(); listB.release(); listC.release();
+  tileflags.release(); halo.release();
+  if (d_ctr) cudaFree(d_ctr);
+  if (h_ctr) cudaFreeHost(h_ctr);
+}
+
+namespace {
+int check_strip(const td_strip& s) {
+  if (s.nx <= 0 || s.ny <= 0 || s.pitch < s.nx || (s.pitch % 32) != 0) { td::set_error("bad strip geometry (pitch must be a multiple of 32 and >= nx)"); return TD_ERR_ARG; }
+  return TD_OK;
+}
+int need_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) { td::set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e)); return TD_ERR_CUDA; }
+  return TD_OK;
+}
+td_ctx* default_ctx() {
+  static td_ctx* c = nullptr;
+  if (!c) c = new td_ctx();
+  return c;
+}
+}  // namespace
+
+extern "C" {
+
+const char* td_version(void) { return "5.4.0-b200"; }
+const char* td_last_error(void) { return td::g_err.c_str(); }
+int td_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int td_set_device(int dev) { TD_CUDA(cudaSetDevice(dev)); return TD_OK; }
+unsigned long long td_launch_count(void) { return td::g_launches; }
+void td_reset_launch_count(void) { td::g_launches = 0; }
+double td_last_compute_seconds(void) { return td::g_compute_s; }
+int td_pitch_for(int nx) { return (nx + 31) / 32 * 32; }
+
+td_ctx* td_ctx_create(void) {
+  if (need_device() != TD_OK) return nullptr;
+  td_ctx* c = new td_ctx();
+  if (!c->d_ctr || !c->h_ctr) { delete c; td::set_error("context allocation failed"); return nullptr; }
+  return c;
+}
+void td_ctx_destroy(td_ctx* c) { delete c; }
+
+// ------------------------------------------------------------------ device-strip level
+int td_gen_dem_dev(float* dem, td_strip s, int row0_global, int total_ny, unsigned seed, float hurst, float tilt, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  TD_CUDA(td::launch_gen_dem(dem, Strip(s), row0_global, total_ny, seed, hurst, tilt, (cudaStream_t)stream));
+  return TD_OK;
+}
+int td_gen_weights_dev(float* w, td_strip s, int row0_global, unsigned seed, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  TD_CUDA(td::launch_gen_w(w, Strip(s), row0_global, seed, (cudaStream_t)stream));
+  return TD_OK;
+}
+
+int td_flood_init_dev(td_ctx* ctx, const float* dem, const int16_t* depmask, float* planchon, td_strip s, float dem_nodata,
+                      int is_4Point, void* stream) {
+  (void)ctx;
+  if (int rc = check_strip(s)) return rc;
+  return td::fill_init(dem, depmask, planchon, Strip(s), dem_nodata, is_4Point, (cudaStream_t)stream);
+}
+int td_flood_relax_dev(td_ctx* ctx, const float* dem, float* planchon, td_strip s, int is_4Point, int* changed_out, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  int ch = 0;
+  int rc = td::fill_relax(ctx, dem, planchon, Strip(s), is_4Point, &ch, (cudaStream_t)stream);
+  if (changed_out) *changed_out = ch;
+  return rc;
+}
+
+int td_d8_slopes_dev(td_ctx* ctx, const float* fel, int16_t* p, float* sd8, td_strip s, float fel_nodata, const double* dxc,
+                     const double* dyc, long long* nflat_out, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  TD_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, sizeof(unsigned long long), st));
+  TD_CUDA(td::launch_d8_stencil(fel, p, sd8, dxc, dyc, Strip(s), fel_nodata, ctx->d_ctr + 8, st));
+  if (nflat_out) {
+    TD_CUDA(cudaMemcpyAsync(ctx->h_ctr + 8, ctx->d_ctr + 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaStreamSynchronize(st));
+    *nflat_out = (long long)ctx->h_ctr[8];
+  }
+  return TD_OK;
+}
+int td_d8_flats_dev(td_ctx* ctx, float* fel, int16_t* p, td_strip s, const double* dxc, const double* dyc, long long* nflat_left,
+                    void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  long long left = 0;
+  int rc = td::resolve_flats_d8(ctx, fel, p, Strip(s), dxc, dyc, &left, (cudaStream_t)stream);
+  if (nflat_left) *nflat_left = left;
+  return rc;
+}
+
+// per-row atan2 tables are evaluated on the host (glibc), like the reference's prop()/VSLOPE do
+static int upload_theta(td_ctx* ctx, const double* d_dxc, const double* d_dyc, int ny, td_ctx::Buf& buf, cudaStream_t st) {
+  std::vector<double> dx(ny), dy(ny), th(2 * (size_t)ny);
+  TD_CUDA(cudaMemcpyAsync(dx.data(), d_dxc, sizeof(double) * ny, cudaMemcpyDeviceToHost, st));
+  TD_CUDA(cudaMemcpyAsync(dy.data(), d_dyc, sizeof(double) * ny, cudaMemcpyDeviceToHost, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  for (int j = 0; j < ny; j++) { th[j] = atan2(dy[j], dx[j]); th[ny + j] = atan2(dx[j], dy[j]); }
+  TD_CUDA(buf.ensure(sizeof(double) * 2 * (size_t)ny));
+  TD_CUDA(cudaMemcpyAsync(buf.p, th.data(), sizeof(double) * 2 * (size_t)ny, cudaMemcpyHostToDevice, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  (void)ctx;
+  return TD_OK;
+}
+
+int td_dinf_slopes_dev(td_ctx* ctx, const float* fel, float* ang, float* slp, td_strip s, float fel_nodata, const double* dxc,
+                       const double* dyc, long long* nflat_out, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
+  const double* thA = ctx->theta.as<double>();
+  TD_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, sizeof(unsigned long long), st));
+  TD_CUDA(td::launch_dinf_stencil(fel, ang, slp, dxc, dyc, thA, thA + s.ny, Strip(s), fel_nodata, ctx->d_ctr + 8, st));
+  if (nflat_out) {
+    TD_CUDA(cudaMemcpyAsync(ctx->h_ctr + 8, ctx->d_ctr + 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaStreamSynchronize(st));
+    *nflat_out = (long long)ctx->h_ctr[8];
+  }
+  return TD_OK;
+}
+int td_dinf_flats_dev(td_ctx* ctx, float* fel, float* ang, td_strip s, const double* dxc, const double* dyc, long long* nflat_left,
+                      void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
+  const double* thA = ctx->theta.as<double>();
+  long long left = 0;
+  int rc = td::resolve_flats_dinf(ctx, fel, ang, Strip(s), dxc, dyc, thA, thA + s.ny, &left, st);
+  if (nflat_left) *nflat_left = left;
+  return rc;
+}
+
+static int ensure_dep_state(td_ctx* ctx, const Strip& s, cudaStream_t st) {
+  const size_t n = (size_t)s.cells();
+  TD_CUDA(ctx->node.ensure(n * 2));
+  TD_CUDA(ctx->cnt.ensure((n + 3) / 4 * 4));
+  TD_CUDA(ctx->halo.ensure(sizeof(int) * 2 * (size_t)s.pitch));
+  TD_CUDA(cudaMemsetAsync(ctx->halo.p, 0, sizeof(int) * 2 * (size_t)s.pitch, st));
+  return TD_OK;
+}
+
+int td_aread8_deps_dev(td_ctx* ctx, const int16_t* p, float* ad8, td_strip s, int16_t p_nodata, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = ensure_dep_state(ctx, Strip(s), st)) return rc;
+  TD_CUDA(td::launch_deps_d8(p, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), ad8, Strip(s), p_nodata, st));
+  return TD_OK;
+}
+int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, float w_nodata, int usew, int contcheck, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  TD_CUDA(td::launch_sweep_d8(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ad8, w, Strip(s), w_nodata, usew, contcheck,
+                              ctx->halo.as<int>(), (cudaStream_t)stream));
+  return TD_OK;
+}
+
+int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, float ang_nodata, const double* dxc, const double* dyc,
+                     void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = ensure_dep_state(ctx, Strip(s), st)) return rc;
+  if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
+  TD_CUDA(td::launch_deps_dinf(ang, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), sca, Strip(s), ang_nodata,
+                               ctx->theta.as<double>(), st));
+  return TD_OK;
+}
+int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca, td_strip s, int usew, int contcheck,
+                      const double* dxc, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Strip ss(s);
+  const unsigned long long cap = (unsigned long long)s.nx * s.ny / 8 + 4096;
+  TD_CUDA(ctx->listA.ensure(sizeof(long long) * cap));
+  TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap));
+  long long* cur = ctx->listA.as<long long>();
+  long long* nxt = ctx->listB.as<long long>();
+  unsigned long long* ctr = ctx->d_ctr + 16;
+  TD_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
+  TD_CUDA(td::launch_sweep_dinf(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ang, sca, w, ss, usew, contcheck,
+                                ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), nullptr, 0, cur, cap, ctr, st));
+  for (;;) {   // drain cells that overflowed a thread's private stack
+    TD_CUDA(cudaMemcpyAsync(ctx->h_ctr + 16, ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaStreamSynchronize(st));
+    const unsigned long long n = ctx->h_ctr[16];
+    if (ctx->h_ctr[17]) { td::set_error("areadinf: ready-cell overflow list exhausted"); return TD_ERR_ALLOC; }
+    if (n == 0) break;
+    TD_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
+    TD_CUDA(td::launch_sweep_dinf(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ang, sca, w, ss, usew, contcheck,
+                                  ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), cur, n, nxt, cap, ctr, st));
+    std::swap(cur, nxt);
+  }
+  return TD_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ host-grid level
+namespace {
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+  void start(cudaStream_t st) { cudaEventRecord(a, st); }
+  double stop(cudaStream_t st) { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms * 1e-3; }
+};
+// host dense (nx) <-> device strip rows 1..ny (pitch)
+template <typename T> cudaError_t h2d(T* dst, const T* src, const td_strip& s, cudaStream_t st) {
+  return cudaMemcpy2DAsync(dst + s.pitch, (size_t)s.pitch * sizeof(T), src, (size_t)s.nx * sizeof(T), (size_t)s.nx * sizeof(T), s.ny,
+                           cudaMemcpyHostToDevice, st);
+}
+template <typename T> cudaError_t d2h(T* dst, const T* src, const td_strip& s, cudaStream_t st) {
+  return cudaMemcpy2DAsync(dst, (size_t)s.nx * sizeof(T), src + s.pitch, (size_t)s.pitch * sizeof(T), (size_t)s.nx * sizeof(T), s.ny,
+                           cudaMemcpyDeviceToHost, st);
+}
+td_strip host_strip(int nx, int ny) { td_strip s; s.nx = nx; s.ny = ny; s.pitch = td_pitch_for(nx); s.has_top = 0; s.has_bot = 0; return s; }
+
+int upload_rows(td_ctx* ctx, const double* dxc, const double* dyc, int ny, const double** d_dxc, const double** d_dyc, cudaStream_t st) {
+  TD_CUDA(ctx->rows.ensure(sizeof(double) * 2 * (size_t)ny));
+  double* d = ctx->rows.as<double>();
+  TD_CUDA(cudaMemcpyAsync(d, dxc, sizeof(double) * ny, cudaMemcpyHostToDevice, st));
+  TD_CUDA(cudaMemcpyAsync(d + ny, dyc, sizeof(double) * ny, cudaMemcpyHostToDevice, st));
+  *d_dxc = d; *d_dyc = d + ny;
+  return TD_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int td_flood_host(const float* dem, float* fel, const int16_t* depmask, int nx, int ny, float dem_nodata, int is_4Point) {
+  if (int rc = need_device()) return rc;
+  if (!dem || !fel || nx <= 0 || ny <= 0) { td::set_error("td_flood_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 4));
+  float* d_dem = ctx->io[0].as<float>(); float* d_w = ctx->io[1].as<float>();
+  int16_t* d_mask = nullptr;
+  TD_CUDA(h2d(d_dem, dem, s, st));
+  if (depmask) { TD_CUDA(ctx->io[2].ensure(n * 2)); d_mask = ctx->io[2].as<int16_t>(); TD_CUDA(h2d(d_mask, depmask, s, st)); }
+  Timer t; t.start(st);
+  if (int rc = td_flood_init_dev(ctx, d_dem, d_mask, d_w, s, dem_nodata, is_4Point, st)) return rc;
+  int changed = 0;
+  if (int rc = td_flood_relax_dev(ctx, d_dem, d_w, s, is_4Point, &changed, st)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(fel, d_w, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+int td_setdird8_host(const float* fel, int16_t* p, float* sd8, int nx, int ny, float fel_nodata, const double* dxc, const double* dyc) {
+  if (int rc = need_device()) return rc;
+  if (!fel || !p || !sd8 || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_setdird8_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[2].ensure(n * 2));
+  float* d_fel = ctx->io[0].as<float>(); float* d_sl = ctx->io[1].as<float>(); int16_t* d_p = ctx->io[2].as<int16_t>();
+  const double *d_dx, *d_dy;
+  if (int rc = upload_rows(ctx, dxc, dyc, ny, &d_dx, &d_dy, st)) return rc;
+  TD_CUDA(h2d(d_fel, fel, s, st));
+  Timer t; t.start(st);
+  long long nflat = 0;
+  if (int rc = td_d8_slopes_dev(ctx, d_fel, d_p, d_sl, s, fel_nodata, d_dx, d_dy, &nflat, st)) return rc;
+  // the slope raster is final before flats are resolved (src/d8.cpp:282-288)
+  if (nflat > 0) { long long left = 0; if (int rc = td_d8_flats_dev(ctx, d_fel, d_p, s, d_dx, d_dy, &left, st)) return rc; }
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(p, d_p, s, st));
+  TD_CUDA(d2h(sd8, d_sl, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+int td_setdir_host(const float* fel, float* ang, float* slp, int nx, int ny, float fel_nodata, const double* dxc, const double* dyc) {
+  if (int rc = need_device()) return rc;
+  if (!fel || !ang || !slp || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_setdir_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[2].ensure(n * 4));
+  float* d_fel = ctx->io[0].as<float>(); float* d_sl = ctx->io[1].as<float>(); float* d_ang = ctx->io[2].as<float>();
+  const double *d_dx, *d_dy;
+  if (int rc = upload_rows(ctx, dxc, dyc, ny, &d_dx, &d_dy, st)) return rc;
+  TD_CUDA(h2d(d_fel, fel, s, st));
+  Timer t; t.start(st);
+  long long nflat = 0;
+  if (int rc = td_dinf_slopes_dev(ctx, d_fel, d_ang, d_sl, s, fel_nodata, d_dx, d_dy, &nflat, st)) return rc;
+  if (nflat > 0) { long long left = 0; if (int rc = td_dinf_flats_dev(ctx, d_fel, d_ang, s, d_dx, d_dy, &left, st)) return rc; }
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(ang, d_ang, s, st));
+  TD_CUDA(d2h(slp, d_sl, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+int td_aread8_host(const int16_t* p, const float* w, float* ad8, int nx, int ny, int16_t p_nodata, float w_nodata, int contcheck) {
+  if (int rc = need_device()) return rc;
+  if (!p || !ad8 || nx <= 0 || ny <= 0) { td::set_error("td_aread8_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 2)); TD_CUDA(ctx->io[1].ensure(n * 4));
+  int16_t* d_p = ctx->io[0].as<int16_t>(); float* d_a = ctx->io[1].as<float>(); float* d_w = nullptr;
+  TD_CUDA(h2d(d_p, p, s, st));
+  if (w) { TD_CUDA(ctx->io[2].ensure(n * 4)); d_w = ctx->io[2].as<float>(); TD_CUDA(h2d(d_w, w, s, st)); }
+  Timer t; t.start(st);
+  if (int rc = td_aread8_deps_dev(ctx, d_p, d_a, s, p_nodata, st)) return rc;
+  if (int rc = td_aread8_sweep_dev(ctx, d_w, d_a, s, w_nodata, w != nullptr, contcheck, st)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(ad8, d_a, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+int td_area_host(const float* ang, const float* w, float* sca, int nx, int ny, float ang_nodata, float w_nodata, const double* dxc,
+                 const double* dyc, int contcheck) {
+  (void)w_nodata;   // the reference adds the raw weight, nodata or not (src/areadinf.cpp:210)
+  if (int rc = need_device()) return rc;
+  if (!ang || !sca || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_area_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 4));
+  float* d_ang = ctx->io[0].as<float>(); float* d_a = ctx->io[1].as<float>(); float* d_w = nullptr;
+  const double *d_dx, *d_dy;
+  if (int rc = upload_rows(ctx, dxc, dyc, ny, &d_dx, &d_dy, st)) return rc;
+  TD_CUDA(h2d(d_ang, ang, s, st));
+  if (w) { TD_CUDA(ctx->io[2].ensure(n * 4)); d_w = ctx->io[2].as<float>(); TD_CUDA(h2d(d_w, w, s, st)); }
+  Timer t; t.start(st);
+  if (int rc = td_area_deps_dev(ctx, d_ang, d_a, s, ang_nodata, d_dx, d_dy, st)) return rc;
+  if (int rc = td_area_sweep_dev(ctx, d_ang, d_w, d_a, s, w != nullptr, contcheck, d_dx, st)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(sca, d_a, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+}  // extern "C"

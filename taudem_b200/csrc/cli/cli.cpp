@@ -1,0 +1,169 @@
+// Command line front ends: pitremove, d8flowdir, dinfflowdir, aread8, areadinf.
+// Same flags, same two invocation styles and the same "print usage and exit(0)" error
+// behaviour as the reference mains (src/PitRemovemn.cpp:48-172, src/D8FlowDirmn.cpp:49-146,
+// src/DinfFlowDirmn.cpp:54-147, src/aread8mn.cpp:49-193, src/areadinfmn.cpp:49-178);
+// one table-driven parser instead of five strcmp chains.  Build with -DTOOL_<name>.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../../include/taudem_b200.h"
+
+#define MAXLN 4096
+
+struct Opt {
+  const char* flag;
+  int kind;        // 0 = file name, 1 = switch, 2 = integer
+  char* sval;      // kind 0
+  int* ival;       // kind 1 (set to `set`) / kind 2 (parsed) / kind 0 (set to `set` when given, may be NULL)
+  int set;
+};
+
+static void usage(const char* prog);
+
+// argc == 2 -> "simple usage" (nothing parsed, names derived with nameadd);
+// argc  > 2 -> flags; unknown flag or missing value -> usage, exit(0).
+static void parse(int argc, char** argv, Opt* opts, int nopts) {
+  if (argc < 2) {
+    printf("Error: To run this program, use either the Simple Usage option or\n");
+    printf("the Usage with Specific file names option\n");
+    usage(argv[0]);
+  }
+  int i = argc > 2 ? 1 : 2;
+  while (argc > i) {
+    Opt* o = NULL;
+    for (int k = 0; k < nopts; k++) if (strcmp(argv[i], opts[k].flag) == 0) o = &opts[k];
+    if (!o) usage(argv[0]);
+    i++;
+    if (o->kind == 1) { *o->ival = o->set; continue; }
+    if (argc <= i) usage(argv[0]);
+    if (o->kind == 0) { strncpy(o->sval, argv[i], MAXLN - 1); o->sval[MAXLN - 1] = 0; if (o->ival) *o->ival = o->set; }
+    else sscanf(argv[i], "%d", o->ival);
+    i++;
+  }
+}
+
+#if defined(TOOL_pitremove)
+static void usage(const char* prog) {
+  printf("Simple use:\n %s <demfile>\n", prog);
+  printf("Simple use derives the output name by inserting 'fel' into the input file name;\n");
+  printf("a depression mask or 4 way filling cannot be requested this way.\n\n");
+  printf("General use with specific file names:\n %s -z <demfile> -fel <newfile> [-depmask <maskfile>] [ -4way] [-v] \n", prog);
+  printf("<demfile> is the name of the input elevation grid file.\n");
+  printf("<newfile> is the output elevation grid with pits filled.\n");
+  printf("<depmaskfile> is depression mask indicator grid.\n");
+  printf("-4way (optional) is flag to set 4 way depression filling.\n");
+  printf("-v (optional) is flag to set verbose (more detailed) output messages.\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char dem[MAXLN], fel[MAXLN], mask[MAXLN];
+  int verbose = 0, four = 0, use_mask = 0;
+  Opt opts[] = {{"-z", 0, dem, NULL, 0}, {"-fel", 0, fel, NULL, 0}, {"-v", 1, NULL, &verbose, 1},
+                {"-4way", 1, NULL, &four, 1}, {"-depmask", 0, mask, &use_mask, 1}};
+  parse(argc, argv, opts, 5);
+  if (argc == 2) { strncpy(dem, argv[1], MAXLN - 1); td_nameadd(fel, argv[1], "fel"); }
+  if (verbose) {
+    printf("On input demfile: %s\n", dem);
+    printf("On input newfile: %s\n", fel);
+    printf("%ssing mask file: %s\n", use_mask ? "U" : "Not U", use_mask ? mask : "N/A");
+    fflush(stdout);
+  }
+  int err = td_flood(dem, fel, "", 0, verbose, four, use_mask, mask);
+  if (err != 0) printf("PitRemove error %d\n", err);
+  return 0;
+}
+
+#elif defined(TOOL_d8flowdir)
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s -fel <demfile>\n", prog);
+  printf("-sd8 <slopefile> -p <angfile> [-sfdr <flowfile>]\n");
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("<demfile> is the pit filled or carved DEM input file.\n");
+  printf("<slopefile> is the slope output file.\n");
+  printf("<pointfile> is the output d8 flow direction file.\n");
+  printf("[-sfdr <flowfile>] is the optional user imposed stream flow direction file.\n");
+  printf("Suffixes appended to the base name in simple usage: fel (input), sd8, p (outputs)\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char dem[MAXLN], p[MAXLN], sd8[MAXLN], flow[MAXLN];
+  int useflow = 0;
+  Opt opts[] = {{"-fel", 0, dem, NULL, 0}, {"-sd8", 0, sd8, NULL, 0}, {"-p", 0, p, NULL, 0}, {"-sfdr", 0, flow, &useflow, 1}};
+  parse(argc, argv, opts, 4);
+  if (argc == 2) { td_nameadd(dem, argv[1], "fel"); td_nameadd(p, argv[1], "p"); td_nameadd(sd8, argv[1], "sd8"); }
+  int err = td_setdird8(dem, p, sd8, flow, useflow);
+  if (err != 0) printf("setdird8 error %d\n", err);
+  return 0;
+}
+
+#elif defined(TOOL_dinfflowdir)
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s -fel <demfile>\n", prog);
+  printf("-slp <slopefile> -ang <angfile> [-sfdr <flowfile>]\n");
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("<demfile> is the pit filled or carved DEM input file.\n");
+  printf("<slopefile> is the slope output file.\n");
+  printf("<angfile> is the output D-infinity flow direction file.\n");
+  printf("[-sfdr <flowfile>] is the optional user imposed stream flow direction file.\n");
+  printf("Suffixes appended to the base name in simple usage: fel (input), slp, ang (outputs)\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char dem[MAXLN], ang[MAXLN], slp[MAXLN], flow[MAXLN];
+  int useflow = 0;
+  Opt opts[] = {{"-fel", 0, dem, NULL, 0}, {"-slp", 0, slp, NULL, 0}, {"-ang", 0, ang, NULL, 0}, {"-sfdr", 0, flow, &useflow, 1}};
+  parse(argc, argv, opts, 4);
+  if (argc == 2) { td_nameadd(dem, argv[1], "fel"); td_nameadd(ang, argv[1], "ang"); td_nameadd(slp, argv[1], "slp"); }
+  int err = td_setdir(dem, ang, slp, flow, useflow);
+  if (err != 0) printf("Setdir error %d\n", err);
+  return 0;
+}
+
+#elif defined(TOOL_aread8) || defined(TOOL_areadinf)
+#if defined(TOOL_aread8)
+#define IN_FLAG "-p"
+#define OUT_FLAG "-ad8"
+#define IN_SUFF "p"
+#define OUT_SUFF "ad8"
+#define IN_DESC "<pfile> is the D8 flow direction input file."
+#define OUT_DESC "<afile> is the D8 area output file."
+#define CALL td_aread8
+#else
+#define IN_FLAG "-ang"
+#define OUT_FLAG "-sca"
+#define IN_SUFF "ang"
+#define OUT_SUFF "sca"
+#define IN_DESC "<angfile> is the D-infinity flow direction input file."
+#define OUT_DESC "<scafile> is the D-infinity specific catchment area output file."
+#define CALL td_area
+#endif
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s %s <infile>\n", prog, IN_FLAG);
+  printf("%s <outfile> [-o <outletfile>] [-lyrno <n>] [-lyrname <name>] [-wg <wfile>] [-nc]\n", OUT_FLAG);
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("%s\n%s\n", IN_DESC, OUT_DESC);
+  printf("[-o <outletfile>] is the optional outlet point input file.\n");
+  printf("[-wg <wfile>] is the optional weight grid input file.\n");
+  printf("The flag -nc overrides edge contamination checking\n");
+  printf("Suffixes appended to the base name in simple usage: %s (input), %s (output)\n", IN_SUFF, OUT_SUFF);
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char in[MAXLN], out[MAXLN], wfile[MAXLN], datasrc[MAXLN], lyrname[MAXLN];
+  int useOutlets = 0, uselyrname = 0, usew = 0, contcheck = 1, lyrno = 0;
+  Opt opts[] = {{IN_FLAG, 0, in, NULL, 0},        {OUT_FLAG, 0, out, NULL, 0},          {"-o", 0, datasrc, &useOutlets, 1},
+                {"-lyrno", 2, NULL, &lyrno, 0},   {"-lyrname", 0, lyrname, &uselyrname, 1}, {"-wg", 0, wfile, &usew, 1},
+                {"-nc", 1, NULL, &contcheck, 0}};
+  parse(argc, argv, opts, 7);
+  if (argc == 2) { td_nameadd(out, argv[1], OUT_SUFF); td_nameadd(in, argv[1], IN_SUFF); }
+  int err = CALL(in, out, datasrc, lyrname, uselyrname, lyrno, wfile, useOutlets, usew, contcheck);
+  if (err != 0) printf("area error %d\n", err);
+  return 0;
+}
+#else
+#error "define TOOL_<name>"
+#endif

@@ -1,0 +1,51 @@
+// D-infinity facet arithmetic shared by the stencil and the flat-resolution kernels.
+// reference: VSLOPE src/dinf.cpp:286-313, facet tables src/dinf.cpp:328-335.
+#pragma once
+#include "common.cuh"
+
+namespace td {
+
+// Facet K = 1..8: E1 is the cardinal neighbour, E2 the diagonal one.
+//   (row,col) offsets: I1/J1 for E1, I2/J2 for E2; D1/D2 = dx or dy by ID1/ID2.
+__host__ __device__ __forceinline__ constexpr int fI1(int K) { return (K == 2 || K == 3) ? -1 : (K == 6 || K == 7) ? 1 : 0; }
+__host__ __device__ __forceinline__ constexpr int fJ1(int K) { return (K == 1 || K == 8) ? 1 : (K == 4 || K == 5) ? -1 : 0; }
+__host__ __device__ __forceinline__ constexpr int fI2(int K) { return (K >= 1 && K <= 4) ? -1 : 1; }
+__host__ __device__ __forceinline__ constexpr int fJ2(int K) { return (K == 1 || K == 2 || K == 7 || K == 8) ? 1 : -1; }
+__host__ __device__ __forceinline__ constexpr bool fD1isDx(int K) { return K == 1 || K == 4 || K == 5 || K == 8; }
+__host__ __device__ __forceinline__ constexpr double fANGC(int K) { return (double)(K / 2); }            // 0,1,1,2,2,3,3,4
+__host__ __device__ __forceinline__ constexpr double fANGF(int K) { return (K & 1) ? 1.0 : -1.0; }       // 1,-1,1,-1,...
+
+// Result of one facet: slope S and how its angle A is obtained
+//   code 0: A = 0;  code 1: A = AD (atan2(D2,D1), host glibc value);  code 2: A = atan2(S2,S1)
+struct Facet { double S, S1, S2; int code; };
+
+// Branch selection of VSLOPE without evaluating atan2 unless the facet direction is
+// within 1e-9 (relative) of the facet diagonal; S2 = (E1-E2)/D2 is never -0, so
+// atan2(S2,S1) < 0  <=>  S2 < 0.
+__device__ __forceinline__ Facet vslope_dev(double E0, double E1, double E2, double D1, double D2, double DD) {
+  Facet f;
+  f.S1 = (E0 - E1) / D1;
+  f.S2 = (E1 - E2) / D2;
+  if (f.S2 < 0.) { f.S = f.S1; f.code = 0; return f; }
+  bool clip;
+  if (f.S1 <= 0.) clip = !(f.S1 == 0. && f.S2 == 0.);
+  else {
+    const double x = f.S2 * D1, y = f.S1 * D2;
+    if (x > y * (1. + 1e-9)) clip = true;
+    else if (x < y * (1. - 1e-9)) clip = false;
+    else clip = atan2(f.S2, f.S1) > atan2(D2, D1);
+  }
+  if (clip) { f.S = (E0 - E2) / DD; f.code = 1; return f; }
+  f.S = sqrt(f.S1 * f.S1 + f.S2 * f.S2);
+  f.code = (f.S1 == 0. && f.S2 == 0.) ? 0 : 2;
+  return f;
+}
+
+__device__ __forceinline__ double facet_angle(const Facet& f, double AD) {
+  return f.code == 0 ? 0. : f.code == 1 ? AD : atan2(f.S2, f.S1);
+}
+
+// angle written to the raster: (float)(ANGC[K]*(PI/2) + ANGF[K]*A)   (src/dinf.cpp:367)
+__device__ __forceinline__ float dinf_angle(int K, double A) { return (float)(fANGC(K) * (TD_PI / 2) + fANGF(K) * A); }
+
+}  // namespace td

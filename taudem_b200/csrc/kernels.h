@@ -1,0 +1,32 @@
+// Internal launcher prototypes (one per kernel family).
+#pragma once
+#include "ctx.h"
+
+namespace td {
+cudaError_t launch_d8_stencil(const float* elev, short* dir, float* slope, const double* dxc, const double* dyc,
+                              const Strip& s, float nodata, unsigned long long* nflat, cudaStream_t st);
+cudaError_t launch_dinf_stencil(const float* elev, float* ang, float* slp, const double* dxc, const double* dyc,
+                                const double* thA, const double* thB, const Strip& s, float nodata,
+                                unsigned long long* nflat, cudaStream_t st);
+int resolve_flats_d8(td_ctx* ctx, float* elev, short* dir, const Strip& s, const double* dxc, const double* dyc,
+                     long long* nleft, cudaStream_t st);
+int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, const double* dxc, const double* dyc,
+                       const double* thA, const double* thB, long long* nleft, cudaStream_t st);
+cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
+                           short nodata, cudaStream_t st);
+cudaError_t launch_sweep_d8(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
+                            float w_nodata, int usew, int contcheck, int* halo, cudaStream_t st);
+cudaError_t launch_sweep_d8_list(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
+                                 float w_nodata, int usew, int contcheck, int* halo, const long long* list,
+                                 unsigned long long n, cudaStream_t st);
+cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
+                             float nodata, const double* theta, cudaStream_t st);
+cudaError_t launch_sweep_dinf(const unsigned short* node, unsigned* cntw, const float* ang, float* area, const float* w,
+                              const Strip& s, int usew, int contcheck, const double* theta, const double* dxc, int* halo,
+                              const long long* list, unsigned long long nlist, long long* ovf, unsigned long long ovf_cap,
+                              unsigned long long* counters, cudaStream_t st);
+int fill_init(const float* dem, const short* mask, float* W, const Strip& s, float nodata, int four, cudaStream_t st);
+int fill_relax(td_ctx* ctx, const float* dem, float* W, const Strip& s, int four, int* changed, cudaStream_t st);
+cudaError_t launch_gen_dem(float* dem, const Strip& s, int row0, int total_ny, unsigned seed, float hurst, float tilt, cudaStream_t st);
+cudaError_t launch_gen_w(float* w, const Strip& s, int row0, unsigned seed, cudaStream_t st);
+}  // namespace td

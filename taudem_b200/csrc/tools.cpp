@@ -1,0 +1,331 @@
+// File-level entry points: the five reference library functions re-created behind the
+// C ABI (reference prototypes: src/flood.h, src/d8.h:7, src/tardemlib.h:70, src/aread8.h:3,
+// src/areadinf.h:2).  Each one reads its rasters with the tiffIO contract, runs the
+// device path through the host-grid level of this library and writes the outputs with
+// the reference's data types and nodata values (SURVEY.md 8(b) "File contract").
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/taudem_b200.h"
+#include "tiff_io.h"
+
+namespace td { void set_error(const std::string& msg); }
+
+namespace {
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct Input {
+  tdio::Raster r;
+  std::string path;
+  std::vector<double> dxc, dyc;
+  int nx = 0, ny = 0;
+  // mirrors tiffIO::tiffIO (src/tiffIO.cpp:54-185) including its console messages
+  int open(const char* p) {
+    path = p;
+    std::string err;
+    if (!r.open(p, &err)) {
+      printf("Error opening file %s.\n", p);
+      fflush(stdout);
+      td::set_error(err);
+      return TD_ERR_IO;
+    }
+    printf("Input file %s has %s coordinate system.\n", p, r.geo().is_geographic ? "geographic" : "projected");
+    nx = (int)r.width(); ny = (int)r.height();
+    r.cell_sizes(&dxc, &dyc);
+    return TD_OK;
+  }
+  template <typename T> int read(std::vector<T>* out, tdio::DType t) {
+    out->resize((size_t)nx * ny);
+    std::string err;
+    // stream by row blocks to bound the decode scratch
+    const long blk = std::max<long>(1, (64l << 20) / ((long)nx * 4));
+    for (long y = 0; y < ny; y += blk) {
+      const long n = std::min<long>(blk, ny - y);
+      if (!r.read(0, y, n, nx, out->data() + (size_t)y * nx, t, &err)) { td::set_error(err); printf("Error reading %s: %s\n", path.c_str(), err.c_str()); return TD_ERR_IO; }
+    }
+    return TD_OK;
+  }
+};
+
+// tiffIO copy-constructor + write (src/tiffIO.cpp:187-243, 263-428): same size and
+// georeferencing as `like`, given type and nodata, name by the reference's extension rule.
+template <typename T>
+int write_like(const char* name, const Input& like, tdio::DType t, double nodata, const std::vector<T>& data) {
+  const std::string path = tdio::output_path_rule(name);
+  const size_t dot = path.rfind('.');
+  const std::string ext = dot == std::string::npos ? "" : path.substr(dot);
+  if (ext != ".tif" && ext != ".tiff") {
+    printf("GDAL driver is not available\n");   // only the GTiff driver exists here (src/tiffIO.cpp:309-314)
+    td::set_error("only .tif/.tiff outputs are supported: " + path);
+    return TD_ERR_DRIVER;
+  }
+  const int cellbytes = t == tdio::DT_I16 ? 2 : 4;
+  const double fileGB = (double)cellbytes * like.nx * (double)like.ny / 1000000000.0;
+  if (fileGB > 4.0) printf("Setting BIGTIFF, File: %s, Anticipated size (GB):%.2f\n", path.c_str(), fileGB);
+  tdio::Writer w;
+  std::string err;
+  const char* comp_env = getenv("TAUDEM_B200_COMPRESS");   // "LZW" | "DEFLATE" | unset (= none)
+  int comp = 1;
+  if (comp_env && strcmp(comp_env, "LZW") == 0) comp = 5;
+  if (comp_env && strcmp(comp_env, "DEFLATE") == 0) comp = 8;
+  if (!w.create(path, like.nx, like.ny, t, nodata, like.r.geo(), comp, &err) || !w.write_rows(0, like.ny, data.data(), &err) || !w.close(&err)) {
+    printf("Error writing %s: %s\n", path.c_str(), err.c_str());
+    td::set_error(err);
+    return TD_ERR_IO;
+  }
+  return TD_OK;
+}
+
+void nodata_msgs(double nd, const char* what, double cast) {
+  // createpart.h:57-85 prints these two lines for every partition created from a file
+  printf("Nodata value input to create partition from file: %lf\n", nd);
+  printf("Nodata value recast to %s used in partition raster: %s\n", what, std::to_string(cast).c_str());
+}
+}  // namespace
+
+extern "C" {
+
+int td_nameadd(char* full, const char* arg, const char* suff) {
+  // suffix goes before the extension; the original extension is kept unless the suffix has its own
+  const char* ext = strrchr(arg, '.');
+  const char* extsuff = strrchr(suff, '.');
+  if (!ext) { sprintf(full, "%s%s", arg, suff); return (int)strlen(arg); }
+  const size_t nmain = strlen(arg) - strlen(ext);
+  memcpy(full, arg, nmain);
+  full[nmain] = 0;
+  strcat(full, suff);
+  if (!extsuff) strcat(full, ext);
+  return (int)nmain;
+}
+
+int td_raster_info(const char* path, int* nx, int* ny, double* nodata, int* has_nodata, double* dx, double* dy, int* is_geographic,
+                   int* bits, int* sample_format) {
+  tdio::Raster r; std::string err;
+  if (!r.open(path, &err)) { td::set_error(err); return TD_ERR_IO; }
+  if (nx) *nx = (int)r.width();
+  if (ny) *ny = (int)r.height();
+  if (nodata) *nodata = r.nodata();
+  if (has_nodata) *has_nodata = r.has_nodata();
+  if (dx) *dx = fabs(r.geo().gt[1]);
+  if (dy) *dy = fabs(r.geo().gt[5]);
+  if (is_geographic) *is_geographic = r.geo().is_geographic;
+  if (bits) *bits = r.bits();
+  if (sample_format) *sample_format = r.sample_format();
+  return TD_OK;
+}
+int td_raster_read(const char* path, int dtype, void* dest, int nx, int ny) {
+  tdio::Raster r; std::string err;
+  if (!r.open(path, &err)) { td::set_error(err); return TD_ERR_IO; }
+  if ((int)r.width() != nx || (int)r.height() != ny) { td::set_error("td_raster_read: size mismatch"); return TD_ERR_ARG; }
+  if (!r.read(0, 0, ny, nx, dest, (tdio::DType)dtype, &err)) { td::set_error(err); return TD_ERR_IO; }
+  return TD_OK;
+}
+int td_raster_cell_sizes(const char* path, double* dxc, double* dyc, int ny) {
+  tdio::Raster r; std::string err;
+  if (!r.open(path, &err)) { td::set_error(err); return TD_ERR_IO; }
+  if ((int)r.height() != ny) { td::set_error("td_raster_cell_sizes: size mismatch"); return TD_ERR_ARG; }
+  std::vector<double> x, y; r.cell_sizes(&x, &y);
+  memcpy(dxc, x.data(), sizeof(double) * ny); memcpy(dyc, y.data(), sizeof(double) * ny);
+  return TD_OK;
+}
+int td_raster_write(const char* path, int dtype, const void* src, int nx, int ny, double nodata, const char* like_path, double dx,
+                    double dy, int compression) {
+  tdio::GeoInfo geo; std::string err;
+  if (like_path) {
+    tdio::Raster r;
+    if (!r.open(like_path, &err)) { td::set_error(err); return TD_ERR_IO; }
+    geo = r.geo();
+  } else {
+    geo.gt[0] = 0; geo.gt[1] = dx; geo.gt[2] = 0; geo.gt[3] = dy * ny; geo.gt[4] = 0; geo.gt[5] = -dy;
+  }
+  tdio::Writer w;
+  if (!w.create(path, nx, ny, (tdio::DType)dtype, nodata, geo, compression, &err) || !w.write_rows(0, ny, src, &err) || !w.close(&err)) {
+    td::set_error(err); return TD_ERR_IO;
+  }
+  return TD_OK;
+}
+
+int td_flood(const char* demfile, const char* felfile, const char* sfdrfile, int usesfdr, int verbose, int is_4Point, int use_mask,
+             const char* maskfile) {
+  (void)sfdrfile; (void)usesfdr;     // not implemented by the reference either (src/PitRemovemn.cpp:143)
+  printf("PitRemove version %s\n", td_version());
+  fflush(stdout);
+  const double t0 = now();
+  Input dem;
+  if (int rc = dem.open(demfile)) return rc;
+  Input mask;
+  if (use_mask) {
+    if (int rc = mask.open(maskfile)) return rc;
+    if (!tdio::compare_rasters(dem.r, dem.path, mask.r, mask.path)) {
+      printf("Error using mask file.\n");
+      td::set_error("depression mask does not match the DEM");
+      return TD_ERR_ARG;
+    }
+  }
+  const double t1 = now();
+  std::vector<float> z; std::vector<int16_t> m;
+  nodata_msgs(dem.r.nodata(), "float", (float)dem.r.nodata());
+  if (int rc = dem.read(&z, tdio::DT_F32)) return rc;
+  if (use_mask) { nodata_msgs(mask.r.nodata(), "int16_t", (int16_t)mask.r.nodata()); if (int rc = mask.read(&m, tdio::DT_I16)) return rc; }
+  const double t2 = now();
+  if (verbose) {
+    printf("Data read\n");
+    printf("Midpoint of partition: 0, nxm: %d, nym: %d, value: %f\n", dem.nx / 2, dem.ny / 2, z[(size_t)(dem.ny / 2) * dem.nx + dem.nx / 2]);
+  }
+  std::vector<float> fel((size_t)dem.nx * dem.ny);
+  if (int rc = td_flood_host(z.data(), fel.data(), use_mask ? m.data() : nullptr, dem.nx, dem.ny, (float)dem.r.nodata(), is_4Point)) {
+    printf("PitRemove device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t3 = now();
+  const float felNodata = -3.0e38f;
+  if (int rc = write_like(felfile, dem, tdio::DT_F32, (double)felNodata, fel)) return rc;
+  const double t4 = now();
+  printf("Processes: 1\nHeader read time: %f\nData read time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1,
+         t3 - t2, t4 - t3, t4 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+}
+
+int td_setdird8(const char* demfile, const char* pointfile, const char* slopefile, const char* flowfile, int useflowfile) {
+  (void)flowfile; (void)useflowfile;   // -sfdr is accepted and functionally dead in the reference (src/d8.cpp:243-267)
+  printf("D8FlowDir version %s\n", td_version());
+  fflush(stdout);
+  const double t0 = now();
+  Input dem;
+  if (int rc = dem.open(demfile)) return rc;
+  const double t1 = now();
+  std::vector<float> z;
+  nodata_msgs(dem.r.nodata(), "float", (float)dem.r.nodata());
+  if (int rc = dem.read(&z, tdio::DT_F32)) return rc;
+  const double t2 = now();
+  std::vector<int16_t> p((size_t)dem.nx * dem.ny);
+  std::vector<float> sd8((size_t)dem.nx * dem.ny);
+  if (int rc = td_setdird8_host(z.data(), p.data(), sd8.data(), dem.nx, dem.ny, (float)dem.r.nodata(), dem.dxc.data(), dem.dyc.data())) {
+    printf("D8FlowDir device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t3 = now();
+  if (int rc = write_like(slopefile, dem, tdio::DT_F32, (double)-1.0f, sd8)) return rc;
+  const double t4 = now();
+  if (int rc = write_like(pointfile, dem, tdio::DT_I16, (double)(short)-32768, p)) return rc;
+  const double t5 = now();
+  printf("Processors: 1\nHeader read time: %f\nData read time: %f\nCompute Slope time: %f\nWrite Slope time: %f\nResolve Flat time: %f\nWrite Flat time: %f\nTotal time: %f\n",
+         t1 - t0, t2 - t1, t3 - t2, t4 - t3, 0.0, t5 - t4, t5 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+}
+
+int td_setdir(const char* demfile, const char* angfile, const char* slopefile, const char* flowfile, int useflowfile) {
+  (void)flowfile; (void)useflowfile;
+  printf("DinfFlowDir version %s\n", td_version());
+  fflush(stdout);
+  const double t0 = now();
+  Input dem;
+  if (int rc = dem.open(demfile)) return rc;
+  const double t1 = now();
+  std::vector<float> z;
+  nodata_msgs(dem.r.nodata(), "float", (float)dem.r.nodata());
+  if (int rc = dem.read(&z, tdio::DT_F32)) return rc;
+  const double t2 = now();
+  std::vector<float> ang((size_t)dem.nx * dem.ny), slp((size_t)dem.nx * dem.ny);
+  if (int rc = td_setdir_host(z.data(), ang.data(), slp.data(), dem.nx, dem.ny, (float)dem.r.nodata(), dem.dxc.data(), dem.dyc.data())) {
+    printf("DinfFlowDir device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t3 = now();
+  if (int rc = write_like(slopefile, dem, tdio::DT_F32, (double)-1.0f, slp)) return rc;
+  const double t4 = now();
+  const float missing = -3.402823466e+38F;   // MISSINGFLOAT (src/commonLib.h:80)
+  if (int rc = write_like(angfile, dem, tdio::DT_F32, (double)missing, ang)) return rc;
+  const double t5 = now();
+  printf("Processors: 1\nHeader read time: %f\nData read time: %f\nCompute Slope time: %f\nWrite Slope time: %f\nResolve Flat time: %f\nWrite Flat time: %f\nTotal time: %f\n",
+         t1 - t0, t2 - t1, t3 - t2, t4 - t3, 0.0, t5 - t4, t5 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+}
+
+static int outlets_unsupported(const char* tool) {
+  printf("%s: outlet (-o) evaluation is not available in this build.\n", tool);
+  td::set_error("outlets (-o) are not supported yet");
+  return TD_ERR_MISMATCH;
+}
+
+int td_aread8(const char* pfile, const char* afile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, const char* wfile,
+              int useOutlets, int usew, int contcheck) {
+  (void)datasrc; (void)lyrname; (void)uselyrname; (void)lyrno;
+  {  // src/aread8.cpp:62-71
+    FILE* fp = fopen(pfile, "r");
+    if (!fp) { fprintf(stderr, "Error: Input file %s does not exist.\n", pfile); td::set_error("input file does not exist"); return TD_ERR_IO; }
+    fclose(fp);
+  }
+  printf("AreaD8 version %s\n", td_version());
+  if (useOutlets) return outlets_unsupported("AreaD8");
+  const double t0 = now();
+  Input p;
+  if (int rc = p.open(pfile)) return rc;
+  std::vector<int16_t> dir;
+  nodata_msgs(p.r.nodata(), "int16_t", (int16_t)p.r.nodata());
+  if (int rc = p.read(&dir, tdio::DT_I16)) return rc;
+  Input w; std::vector<float> wg;
+  if (usew) {
+    if (int rc = w.open(wfile)) return rc;
+    if (!tdio::compare_rasters(p.r, p.path, w.r, w.path)) { printf("File sizes do not match\n%s\n", wfile); td::set_error("weight grid does not match"); return TD_ERR_MISMATCH; }
+    nodata_msgs(w.r.nodata(), "float", (float)w.r.nodata());
+    if (int rc = w.read(&wg, tdio::DT_F32)) return rc;
+  }
+  const double t1 = now();
+  std::vector<float> ad8((size_t)p.nx * p.ny);
+  if (int rc = td_aread8_host(dir.data(), usew ? wg.data() : nullptr, ad8.data(), p.nx, p.ny, (int16_t)p.r.nodata(),
+                              usew ? (float)w.r.nodata() : 0.f, contcheck)) {
+    printf("AreaD8 device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(afile, p, tdio::DT_F32, (double)-1.0f, ad8)) return rc;
+  const double t3 = now();
+  printf("Number of Processes: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+}
+
+int td_area(const char* angfile, const char* scafile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, const char* wfile,
+            int useOutlets, int usew, int contcheck) {
+  (void)datasrc; (void)lyrname; (void)uselyrname; (void)lyrno;
+  printf("AreaDinf version %s\n", td_version());
+  if (useOutlets) return outlets_unsupported("AreaDinf");
+  const double t0 = now();
+  Input a;
+  if (int rc = a.open(angfile)) return rc;
+  std::vector<float> ang;
+  nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
+  if (int rc = a.read(&ang, tdio::DT_F32)) return rc;
+  Input w; std::vector<float> wg;
+  if (usew) {
+    if (int rc = w.open(wfile)) return rc;
+    if (!tdio::compare_rasters(a.r, a.path, w.r, w.path)) { td::set_error("weight grid does not match"); return TD_ERR_ARG; }   // src/areadinf.cpp:132
+    nodata_msgs(w.r.nodata(), "float", (float)w.r.nodata());
+    if (int rc = w.read(&wg, tdio::DT_F32)) return rc;
+  }
+  const double t1 = now();
+  std::vector<float> sca((size_t)a.nx * a.ny);
+  if (int rc = td_area_host(ang.data(), usew ? wg.data() : nullptr, sca.data(), a.nx, a.ny, (float)a.r.nodata(),
+                            usew ? (float)w.r.nodata() : 0.f, a.dxc.data(), a.dyc.data(), contcheck)) {
+    printf("AreaDinf device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(scafile, a, tdio::DT_F32, (double)-1.0f, sca)) return rc;
+  const double t3 = now();
+  printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+}
+
+}  // extern "C"
