@@ -23,7 +23,7 @@ constexpr int SW = FW + 2;                 // shared W row stride (with ring)
 
 __global__ void __launch_bounds__(256) k_fill_init(const float* __restrict__ dem, const short* __restrict__ mask,
                                                    float* __restrict__ W, Strip s, float nodata, int step) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = 1 + blockIdx.y;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x, r = 1 + blockIdx.x;   // rows on grid.x (no 65535 limit)
   if (c >= s.nx) return;
   const long long ci = s.idx(r, c);
   const float z = dem[ci];
@@ -105,7 +105,7 @@ __global__ void k_fill_all_tiles(int* list, int* flag, int n) {
 }  // namespace
 
 int fill_init(const float* dem, const short* mask, float* W, const Strip& s, float nodata, int four, cudaStream_t st) {
-  dim3 grid((s.nx + 255) / 256, s.ny);
+  dim3 grid(s.ny, (s.nx + 255) / 256);
   k_fill_init<<<grid, 256, 0, st>>>(dem, mask, W, s, nodata, four ? 2 : 1);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());

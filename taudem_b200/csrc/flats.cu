@@ -58,7 +58,7 @@ __device__ __forceinline__ void append(long long* list, unsigned long long* ctr,
 template <class P>
 __global__ void k_collect(const typename P::DirT* __restrict__ dir, Strip s, long long* __restrict__ list,
                           unsigned long long* __restrict__ ctr) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = 1 + blockIdx.y;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x, r = 1 + blockIdx.x;   // rows on grid.x (no 65535 limit)
   const bool in = c < s.nx;
   const long long ci = s.idx(r, in ? c : 0);
   append(list, ctr, in && P::is_flat(dir[ci]), ci);
@@ -267,7 +267,7 @@ __global__ void k_set2_flat(const long long* __restrict__ list, unsigned long lo
 
 // src/d8.cpp:669-675: elevDEM := (float)elev2 on every cell (elev2 = 1 outside the flat set)
 __global__ void k_overwrite(float* __restrict__ elev, const int* __restrict__ lev, Strip s) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = 1 + blockIdx.y;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x, r = 1 + blockIdx.x;   // rows on grid.x (no 65535 limit)
   if (c >= s.nx) return;
   const long long ci = s.idx(r, c);
   const int l = lev[ci];
@@ -300,7 +300,7 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
   TD_CUDA(cudaMemsetAsync(dc, 0, 4 * sizeof(unsigned long long), st));
   TD_CUDA(ctx->listA.ensure(sizeof(long long) * (size_t)s.nx * s.ny));
   {
-    dim3 grid((s.nx + 255) / 256, s.ny);
+    dim3 grid(s.ny, (s.nx + 255) / 256);
     k_collect<P><<<grid, 256, 0, st>>>(dir, s, ctx->listA.as<long long>(), dc);
     TD_LAUNCHED();
   }
@@ -373,7 +373,7 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
     unsigned long long nn = 0;
     TD_CUDA(read_ctr(0, &nn));
     if (nn > 0) {
-      dim3 grid((s.nx + 255) / 256, s.ny);
+      dim3 grid(s.ny, (s.nx + 255) / 256);
       k_overwrite<<<grid, 256, 0, st>>>(elev, lev, s); TD_LAUNCHED();
     }
     k_reset<<<nblk(n), 256, 0, st>>>(cur, n, lev, mk); TD_LAUNCHED();

@@ -14,7 +14,7 @@ __host__ __device__ __forceinline__ unsigned hash3(unsigned x, unsigned y, unsig
 __host__ __device__ __forceinline__ float u01(unsigned h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 
 __global__ void k_gen_dem(float* __restrict__ dem, Strip s, int row0, int total_ny, unsigned seed, float hurst, float tilt) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = 1 + blockIdx.y;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x, r = 1 + blockIdx.x;   // rows on grid.x (no 65535 limit)
   if (c >= s.nx) return;
   const int y = row0 + r - 1;
   const int n = max(s.nx, total_ny);
@@ -41,20 +41,20 @@ __global__ void k_gen_dem(float* __restrict__ dem, Strip s, int row0, int total_
 }
 
 __global__ void k_gen_w(float* __restrict__ w, Strip s, int row0, unsigned seed) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = 1 + blockIdx.y;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x, r = 1 + blockIdx.x;   // rows on grid.x (no 65535 limit)
   if (c >= s.nx) return;
   w[s.idx(r, c)] = u01(hash3((unsigned)c, (unsigned)(row0 + r - 1), seed));
 }
 }  // namespace
 
 cudaError_t launch_gen_dem(float* dem, const Strip& s, int row0, int total_ny, unsigned seed, float hurst, float tilt, cudaStream_t st) {
-  dim3 grid((s.nx + 255) / 256, s.ny);
+  dim3 grid(s.ny, (s.nx + 255) / 256);
   k_gen_dem<<<grid, 256, 0, st>>>(dem, s, row0, total_ny, seed, hurst, tilt);
   TD_LAUNCHED();
   return cudaGetLastError();
 }
 cudaError_t launch_gen_w(float* w, const Strip& s, int row0, unsigned seed, cudaStream_t st) {
-  dim3 grid((s.nx + 255) / 256, s.ny);
+  dim3 grid(s.ny, (s.nx + 255) / 256);
   k_gen_w<<<grid, 256, 0, st>>>(w, s, row0, seed);
   TD_LAUNCHED();
   return cudaGetLastError();

@@ -1,0 +1,123 @@
+"""GPU parity: the CUDA path (through the C ABI, host-grid level) against
+(a) the committed golden outputs of the reference's own tools and
+(b) the reference tools run live (oracle/_ref) on larger seeded inputs.
+Bar: bit-exact fel, p, sd8, slp, ad8; <= 1e-5 relative (identical nodata masks) ang, sca.
+"""
+import numpy as np
+import pytest
+
+import taudem_b200 as td
+from taudem_b200 import synth
+from util import ANG_ND, FEL_ND, assert_bits, assert_float_parity, golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden(name):
+    g = load_golden(name)
+    dx, dy = float(g["dx"]), float(g["dy"])
+    assert_bits(td.pitremove_grid(g["dem"]), g["fel"], "fel")
+    assert_bits(td.pitremove_grid(g["dem"], is_4Point=True), g["fel4"], "fel -4way")
+    p, sd8 = td.d8flowdir_grid(g["fel"], dx=dx, dy=dy)
+    assert_bits(sd8, g["sd8"], "sd8")
+    assert_bits(p, g["p"], "p")
+    ang, slp = td.dinfflowdir_grid(g["fel"], dx=dx, dy=dy)
+    assert_bits(slp, g["slp"], "slp")
+    assert_float_parity(ang, g["ang"], "ang")
+    assert_bits(td.aread8_grid(g["p"]), g["ad8"], "ad8")
+    assert_bits(td.aread8_grid(g["p"], weights=g["w"]), g["ad8_w"], "ad8 -wg")
+    assert_bits(td.aread8_grid(g["p"], contcheck=False), g["ad8_nc"], "ad8 -nc")
+    assert_float_parity(td.areadinf_grid(g["ang"], dx=dx, dy=dy), g["sca"], "sca")
+    assert_float_parity(td.areadinf_grid(g["ang"], weights=g["w"], dx=dx, dy=dy), g["sca_w"], "sca -wg")
+    assert_float_parity(td.areadinf_grid(g["ang"], dx=dx, dy=dy, contcheck=False), g["sca_nc"], "sca -nc")
+
+
+CASES = [
+    ("rough768", lambda: synth.gen_dem(768, family="rough", seed=11), 30.0, 30.0),
+    ("hills_holes_1000x700", lambda: synth.punch_holes(synth.gen_dem(700, 1000, hurst=0.8, tilt=1.0, seed=5)), 25.0, 40.0),
+    ("tilted_odd", lambda: synth.gen_dem(333, 517, family="tilted", seed=2), 30.0, 30.0),
+]
+
+
+@pytest.mark.parametrize("name,make,dx,dy", CASES, ids=[c[0] for c in CASES])
+def test_live_reference(refrun, name, make, dx, dy):
+    dem = make()
+    w = synth.gen_weights(*dem.shape)
+    R = refrun.RefPipeline(dx=dx, dy=dy, np_ranks=4)
+    fel_r = R.pitremove(dem)
+    p_r, sd8_r = R.d8flowdir(fel_r)
+    ang_r, slp_r = R.dinfflowdir(fel_r)
+    # every stage on the reference's input for that stage ...
+    assert_bits(td.pitremove_grid(dem), fel_r, "fel")
+    p, sd8 = td.d8flowdir_grid(fel_r, dx=dx, dy=dy)
+    assert_bits(sd8, sd8_r, "sd8"); assert_bits(p, p_r, "p")
+    ang, slp = td.dinfflowdir_grid(fel_r, dx=dx, dy=dy)
+    assert_bits(slp, slp_r, "slp"); assert_float_parity(ang, ang_r, "ang")
+    assert_bits(td.aread8_grid(p_r), R.aread8(p_r), "ad8")
+    assert_bits(td.aread8_grid(p_r, weights=w, contcheck=False), R.aread8(p_r, weights=w, contcheck=False), "ad8 -wg -nc")
+    assert_float_parity(td.areadinf_grid(ang_r, dx=dx, dy=dy), R.areadinf(ang_r), "sca")
+    assert_float_parity(td.areadinf_grid(ang_r, weights=w, dx=dx, dy=dy), R.areadinf(ang_r, weights=w), "sca -wg")
+    # ... and end to end: D8 chain is bit-exact from the raw DEM
+    p2, _ = td.d8flowdir_grid(td.pitremove_grid(dem), dx=dx, dy=dy)
+    assert_bits(td.aread8_grid(p2), R.aread8(p_r), "ad8 end-to-end")
+
+
+def test_file_level_cli(refrun, tmp_path):
+    """The five executables on files, against the reference executables on the same files."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "taudem_b200", "bin")
+    dem = synth.punch_holes(synth.gen_dem(200, 260, hurst=0.8, tilt=1.0, seed=21))
+    R = refrun.RefPipeline(workdir=str(tmp_path / "ref"), dx=30.0, dy=30.0) if os.makedirs(tmp_path / "ref", exist_ok=True) is None else None
+    fel_r = R.pitremove(dem); p_r, sd8_r = R.d8flowdir(fel_r); ad8_r = R.aread8(p_r); ang_r, slp_r = R.dinfflowdir(fel_r); sca_r = R.areadinf(ang_r)
+    d = tmp_path
+    td.write_raster(str(d / "dem.tif"), dem, -9999.0, dx=30.0, dy=30.0)
+
+    def run(tool, *args):
+        r = subprocess.run([os.path.join(bindir, tool)] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0 and "error" not in r.stdout.lower(), r.stdout
+        return r.stdout
+
+    out = run("pitremove", "-z", d / "dem.tif", "-fel", d / "demfel.tif")
+    assert "PitRemove version" in out and "Compute time" in out
+    run("d8flowdir", d / "dem.tif")            # simple usage: demfel.tif -> demp.tif, demsd8.tif
+    run("aread8", d / "dem.tif")               # demp.tif -> demad8.tif
+    run("dinfflowdir", "-fel", d / "demfel.tif", "-ang", d / "demang.tif", "-slp", d / "demslp.tif")
+    run("areadinf", "-ang", d / "demang.tif", "-sca", d / "demsca.tif")
+    assert_bits(td.read_raster(str(d / "demfel.tif")), fel_r, "fel file")
+    assert_bits(td.read_raster(str(d / "demp.tif"), np.int16), p_r, "p file")
+    assert_bits(td.read_raster(str(d / "demsd8.tif")), sd8_r, "sd8 file")
+    assert_bits(td.read_raster(str(d / "demad8.tif")), ad8_r, "ad8 file")
+    assert_bits(td.read_raster(str(d / "demslp.tif")), slp_r, "slp file")
+    assert_float_parity(td.read_raster(str(d / "demang.tif")), ang_r, "ang file")
+    assert_float_parity(td.read_raster(str(d / "demsca.tif")), sca_r, "sca file")
+    # nodata tags round-trip like the reference's (SURVEY.md 8(b) file contract)
+    for f, nd in (("demfel.tif", -3.0e38), ("demp.tif", -32768), ("demad8.tif", -1.0), ("demang.tif", ANG_ND)):
+        assert np.float32(td.raster_info(str(d / f))["nodata"]) == np.float32(nd)
+
+
+def test_properties_large():
+    """Size-independent properties at a size the CPU reference cannot reach quickly (4096^2):
+    fill is idempotent and never lowers a cell; every resolved D8 direction points to a cell that
+    is not higher; D8 area (no contamination check) is conserved: the area leaving the grid equals
+    the number of cells."""
+    n = 4096
+    dem = synth.gen_dem(n, hurst=0.8, tilt=1.0, seed=77)
+    fel = td.pitremove_grid(dem)
+    assert (fel >= dem).all()
+    assert_bits(td.pitremove_grid(fel, nodata=-9999.0), fel, "fill idempotence")
+    p, sd8 = td.d8flowdir_grid(fel)
+    d1 = np.array([0, 1, 1, 0, -1, -1, -1, 0, 1]); d2 = np.array([0, 0, -1, -1, -1, 0, 1, 1, 1])
+    yy, xx = np.nonzero((p >= 1) & (p <= 8))
+    k = p[yy, xx]
+    assert (fel[yy + d2[k], xx + d1[k]] <= fel[yy, xx]).all()
+    assert (sd8[(p >= 1) & (p <= 8)] >= 0).all()
+    ad8 = td.aread8_grid(p, contcheck=False)
+    valid = (p >= 1) & (p <= 8)
+    ty, tx = yy + d2[k], xx + d1[k]
+    leaves = ~valid[ty, tx]                     # cells whose downslope neighbour is an edge/nodata cell
+    total = ad8[yy[leaves], xx[leaves]].astype(np.float64).sum()
+    assert abs(total - valid.sum()) <= 1e-3 * valid.sum(), (total, valid.sum())
+    assert ad8[valid].min() >= 1.0

@@ -1,0 +1,42 @@
+import glob
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FEL_ND = -3.0e38
+ANG_ND = -3.4028234663852886e38
+
+
+def golden_cases():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def bits_equal(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    if a.dtype != b.dtype or a.shape != b.shape:
+        return False
+    if a.dtype == np.float32:
+        return bool(np.array_equal(a.view(np.uint32), b.view(np.uint32)))
+    return bool(np.array_equal(a, b))
+
+
+def assert_bits(a, b, what):
+    if not bits_equal(a, b):
+        bad = np.argwhere(a != b) if a.shape == b.shape else []
+        raise AssertionError(f"{what}: {len(bad)} of {a.size} cells differ; first {[(tuple(i), a[tuple(i)], b[tuple(i)]) for i in bad[:5]]}")
+
+
+def assert_float_parity(a, b, what, rtol=1e-5):
+    """The north-star tolerance for D-infinity angle / sca floats: identical nodata/flat masks
+    (values <= -1) and 1e-5 relative elsewhere."""
+    ma, mb = a <= -1, b <= -1
+    assert np.array_equal(ma, mb), f"{what}: nodata masks differ in {(ma != mb).sum()} cells"
+    ok = ~ma
+    rel = np.abs(a[ok].astype(np.float64) - b[ok]) / np.maximum(np.abs(b[ok].astype(np.float64)), 1e-300)
+    assert rel.size == 0 or rel.max() <= rtol, f"{what}: max rel err {rel.max()}"
+    assert bits_equal(a[ma], b[ma]), f"{what}: nodata values differ"
