@@ -109,6 +109,8 @@ typedef struct td_ctx td_ctx;   /* per-device scratch (frontier queues, counters
 td_ctx* td_ctx_create(void);
 void td_ctx_destroy(td_ctx*);
 int td_pitch_for(int nx);        /* smallest legal pitch */
+/* diagnostics: device counter i of the context (27 = tile visits of the last sweep) */
+unsigned long long td_ctx_counter(td_ctx*, int i);
 
 /* synthetic fractal DEM written straight into a strip (bench/test input generator) */
 int td_gen_dem_dev(float* dem, td_strip s, int row0_global, int total_ny, unsigned seed,

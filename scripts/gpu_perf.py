@@ -17,6 +17,12 @@ def timed(fn):
     return r, a.elapsed_time(b) * 1e-3
 
 
+def stats(T):
+    c = [T.l.td_ctx_counter(T.ctx, 24 + i) for i in range(9)]
+    v = max(c[3], 1)
+    return f"visits {c[3]} per-visit cycles: wait {c[4]//v} load {c[5]//v} walk {c[6]//v} wb {c[7]//v} passes {c[8]/v:.2f}"
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     hurst = float(sys.argv[2]) if len(sys.argv) > 2 else 0.8
@@ -38,7 +44,7 @@ def main():
         ad8, t = timed(lambda: T.aread8(s, p)); print(f"aread8       {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {6*mc/t/1e3:8.1f} GB/s")
         ad8 = None
     ad8 = s.empty(torch.float32)
-    _, t1 = timed(lambda: T.aread8_deps(s, p, ad8)); _, t2 = timed(lambda: T.aread8_sweep(s, ad8)); print(f"  deps {t1*1e3:.2f} ms  sweep {t2*1e3:.2f} ms  max area {float(s.owned(ad8).max())}")
+    _, t1 = timed(lambda: T.aread8_deps(s, p, ad8)); _, t2 = timed(lambda: T.aread8_sweep(s, ad8)); print(f"  deps {t1*1e3:.2f} ms  sweep {t2*1e3:.2f} ms  max area {float(s.owned(ad8).max())}  {stats(T)} of {((n+63)//64)*((n+31)//32)} tiles")
     del ad8, p
     for rep in range(2):
         (ang, slp, nflat), t = timed(lambda: T.dinf_slopes(s, fel, dxc, dyc)); print(f"dinf stencil {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {12*mc/t/1e3:8.1f} GB/s  flats {nflat}")
@@ -50,7 +56,7 @@ def main():
         sca, t = timed(lambda: T.areadinf(s, ang, dxc, dyc)); print(f"areadinf     {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {8*mc/t/1e3:8.1f} GB/s")
         sca = None
     sca = s.empty(torch.float32)
-    _, t1 = timed(lambda: T.areadinf_deps(s, ang, sca, dxc, dyc)); _, t2 = timed(lambda: T.areadinf_sweep(s, ang, sca, dxc)); print(f"  deps {t1*1e3:.2f} ms  sweep {t2*1e3:.2f} ms  max sca {float(s.owned(sca).max())}")
+    _, t1 = timed(lambda: T.areadinf_deps(s, ang, sca, dxc, dyc)); _, t2 = timed(lambda: T.areadinf_sweep(s, ang, sca, dxc)); print(f"  deps {t1*1e3:.2f} ms  sweep {t2*1e3:.2f} ms  max sca {float(s.owned(sca).max())}  {stats(T)}")
     print("launches", td.launch_count(), "mem GB", torch.cuda.max_memory_allocated() / 1e9)
 
 

@@ -9,46 +9,13 @@
 // is rebuilt on the device from t (host glibc atan2, per row) using only +,-: the same
 // doubles as the reference.  The per-cell value is a deterministic gather, so any
 // topological schedule reproduces it.
-#include "common.cuh"
 #include "ctx.h"
+#include "dinf_common.cuh"
 
 namespace td {
 namespace {
 constexpr int TW = 128, TH = 32;
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
-
-__device__ __forceinline__ double aref(int i, double t) {
-  // i in 0..9
-  const double PI = TD_PI;
-  switch (i) {
-    case 0: return -t;
-    case 1: return 0.;
-    case 2: return t;
-    case 3: return (double)(0.5 * PI);
-    case 4: return PI - t;
-    case 5: return (double)PI;
-    case 6: return PI + t;
-    case 7: return (double)(1.5 * PI);
-    case 8: return 2. * PI - t;
-    default: return (double)(2. * PI);
-  }
-}
-
-// src/commonLib.cpp:76-91
-__device__ __forceinline__ double prop_dev(float a, int k, double t) {
-  const double PI = TD_PI;
-  double p = 0.;
-  if (k <= 0) k = k + 8;
-  if (k == 1 && a > PI) a = (float)(a - 2.0 * PI);
-  const double lo = aref(k - 1, t), hi = aref(k + 1, t);
-  if (a > lo && a < hi) {
-    const double mid = aref(k, t);
-    if (a > mid) p = (hi - a) / (hi - mid);
-    else p = (a - lo) / (mid - lo);
-  }
-  if (p < 1e-5) return -1.;
-  return p;
-}
 
 __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang, unsigned short* __restrict__ node,
                                                    unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,

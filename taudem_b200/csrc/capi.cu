@@ -1,6 +1,7 @@
 // C ABI of taudem_b200: device-strip level and host-grid level entry points
 // (declared in include/taudem_b200.h).  File-level entry points live in tools.cpp.
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -48,6 +49,12 @@ int need_device() {
   if (e != cudaSuccess || n == 0) { td::set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
+// TAUDEM_B200_SWEEP=chain selects the first-generation global chain-following sweep (kept for A/B
+// measurements); the default is the shared-memory tile dataflow (sweep_tiles.cu).
+bool chain_sweep() {
+  const char* e = getenv("TAUDEM_B200_SWEEP");
+  return e && strcmp(e, "chain") == 0;
+}
 td_ctx* default_ctx() {
   static td_ctx* c = nullptr;
   if (!c) c = new td_ctx();
@@ -65,6 +72,13 @@ unsigned long long td_launch_count(void) { return td::g_launches; }
 void td_reset_launch_count(void) { td::g_launches = 0; }
 double td_last_compute_seconds(void) { return td::g_compute_s; }
 int td_pitch_for(int nx) { return (nx + 31) / 32 * 32; }
+unsigned long long td_ctx_counter(td_ctx* ctx, int i) {
+  unsigned long long v = 0;
+  if (!ctx || i < 0 || i >= 32) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(&v, ctx->d_ctr + i, sizeof v, cudaMemcpyDeviceToHost);
+  return v;
+}
 
 td_ctx* td_ctx_create(void) {
   if (need_device() != TD_OK) return nullptr;
@@ -181,9 +195,13 @@ int td_aread8_deps_dev(td_ctx* ctx, const int16_t* p, float* ad8, td_strip s, in
 }
 int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, float w_nodata, int usew, int contcheck, void* stream) {
   if (int rc = check_strip(s)) return rc;
-  TD_CUDA(td::launch_sweep_d8(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ad8, w, Strip(s), w_nodata, usew, contcheck,
-                              ctx->halo.as<int>(), (cudaStream_t)stream));
-  return TD_OK;
+  if (chain_sweep()) {
+    TD_CUDA(td::launch_sweep_d8(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ad8, w, Strip(s), w_nodata, usew, contcheck,
+                                ctx->halo.as<int>(), (cudaStream_t)stream));
+    return TD_OK;
+  }
+  return td::sweep_tiles(ctx, false, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ad8, w, nullptr, Strip(s), w_nodata, usew,
+                         contcheck, nullptr, nullptr, ctx->halo.as<int>(), (cudaStream_t)stream);
 }
 
 int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, float ang_nodata, const double* dxc, const double* dyc,
@@ -201,6 +219,9 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   if (int rc = check_strip(s)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const Strip ss(s);
+  if (!chain_sweep())
+    return td::sweep_tiles(ctx, true, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), sca, w, ang, ss, 0.f, usew, contcheck,
+                           ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
   const unsigned long long cap = (unsigned long long)s.nx * s.ny / 8 + 4096;
   TD_CUDA(ctx->listA.ensure(sizeof(long long) * cap));
   TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap));

@@ -48,4 +48,38 @@ __device__ __forceinline__ double facet_angle(const Facet& f, double AD) {
 // angle written to the raster: (float)(ANGC[K]*(PI/2) + ANGF[K]*A)   (src/dinf.cpp:367)
 __device__ __forceinline__ float dinf_angle(int K, double A) { return (float)(fANGC(K) * (TD_PI / 2) + fANGF(K) * A); }
 
+// ---- prop(): share of a D-infinity cell's flow that goes to neighbour k (src/commonLib.cpp:76-91)
+__device__ __forceinline__ double aref(int i, double t) {
+  // i in 0..9
+  const double PI = TD_PI;
+  switch (i) {
+    case 0: return -t;
+    case 1: return 0.;
+    case 2: return t;
+    case 3: return (double)(0.5 * PI);
+    case 4: return PI - t;
+    case 5: return (double)PI;
+    case 6: return PI + t;
+    case 7: return (double)(1.5 * PI);
+    case 8: return 2. * PI - t;
+    default: return (double)(2. * PI);
+  }
+}
+
+// src/commonLib.cpp:76-91
+__device__ __forceinline__ double prop_dev(float a, int k, double t) {
+  const double PI = TD_PI;
+  double p = 0.;
+  if (k <= 0) k = k + 8;
+  if (k == 1 && a > PI) a = (float)(a - 2.0 * PI);
+  const double lo = aref(k - 1, t), hi = aref(k + 1, t);
+  if (a > lo && a < hi) {
+    const double mid = aref(k, t);
+    if (a > mid) p = (hi - a) / (hi - mid);
+    else p = (a - lo) / (mid - lo);
+  }
+  if (p < 1e-5) return -1.;
+  return p;
+}
+
 }  // namespace td

@@ -1,0 +1,388 @@
+// Contributing-area evaluation sweep as a tile-granular dataflow (D8 and D-infinity).
+//
+// reference: aread8 main loop src/aread8.cpp:216-304, area() main loop src/areadinf.cpp:173-265.
+// The value of a cell is a k-ordered gather over the neighbours that drain into it, evaluated
+// once when all of them are done; the schedule is free, so:
+//
+//  * the strip is cut into 64 x 32 tiles; persistent CTAs take tile ids from a device-side
+//    multi-producer/multi-consumer queue;
+//  * a CTA loads the tile's dependency counts, node words and areas (with a one-cell ring)
+//    into shared memory and runs the wavefront INSIDE shared memory: threads start on cells
+//    whose count is zero, evaluate them, decrement the downslope cell with a shared-memory
+//    atomic and keep following the chain while they are the last arrival (~100 cycles per hop
+//    instead of several L2 round trips);
+//  * flow that leaves the tile is delivered after the tile's areas are written back and
+//    fenced: one global atomic decrement per crossing; the delivery that brings a count to
+//    zero activates the owning tile (per-tile state: idle / queued / running / running+dirty,
+//    so a tile is never processed by two CTAs at once);
+//  * the kernel ends when no tile is queued or running.
+// Flow that crosses the strip boundary is recorded in ctx.halo for the neighbour strip
+// (src/aread8.cpp:282-297).
+#include "ctx.h"
+#include "dinf_common.cuh"
+
+namespace td {
+namespace {
+
+constexpr int TWX = 64, TWY = 32, TC = TWX * TWY;   // tile
+constexpr int RW = TWX + 2, RH = TWY + 2;           // ring
+constexpr int EXTCAP = 512;
+constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
+
+struct SweepArgs {
+  const unsigned short* node;
+  unsigned* cntw;
+  float* area;
+  const float* w;
+  const float* ang;
+  Strip s;
+  int usew, contcheck;
+  float w_nodata;
+  const double* theta;
+  const double* dxc;
+  int* halo;
+  int ntx, nty;
+  int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
+  unsigned char* visited;  // per tile: area interior has been written at least once
+  int* tq;                 // ring of tile ids + 1
+  unsigned qmask;
+  unsigned long long* ctr; // [0] head, [1] tail, [2] pending (queued + running tiles)
+};
+
+template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((const volatile T*)p); }
+
+__device__ void sched_push(const SweepArgs& a, int t) {
+  atomicAdd(a.ctr + 2, 1ull);
+  const unsigned long long slot = atomicAdd(a.ctr + 1, 1ull);
+  int* q = a.tq + (slot & a.qmask);
+  while (atomicCAS(q, 0, t + 1) != 0) {}
+}
+
+__device__ void sched_activate(const SweepArgs& a, int t) {
+  for (;;) {
+    const int st = ldv(a.state + t);
+    if (st == 1 || st == 3) return;
+    if (st == 0) { if (atomicCAS(a.state + t, 0, 1) == 0) { sched_push(a, t); return; } }
+    else if (atomicCAS(a.state + t, 2, 3) == 2) return;
+  }
+}
+
+// Ticket queue: one fetch-and-add per pop (a CAS loop on the head collapses under the
+// contention of ~900 persistent CTAs).  Ticket h is served by the h-th push; a consumer whose
+// ticket is never served leaves when no tile is queued or running any more.
+__device__ int sched_pop(const SweepArgs& a) {
+  const unsigned long long h = atomicAdd(a.ctr, 1ull);
+  int* q = a.tq + (h & a.qmask);
+  for (;;) {
+    const int v = ldv(q);
+    if (v != 0) {
+      atomicExch(q, 0);
+      atomicExch(a.state + (v - 1), 2);
+      atomicAdd(a.ctr + 3, 1ull);          // statistics: tile visits
+      __threadfence();
+      return v - 1;
+    }
+    if ((long long)ldv(a.ctr + 2) <= 0) return -1;
+    __nanosleep(64);
+  }
+}
+
+__device__ void sched_finish(const SweepArgs& a, int t) {
+  __threadfence();
+  if (atomicCAS(a.state + t, 2, 0) != 2) { atomicExch(a.state + t, 1); sched_push(a, t); }
+  atomicAdd(a.ctr + 2, ~0ull);   // pending -= 1
+}
+
+__global__ void k_sched_init(int* state, unsigned char* visited, int* tq, unsigned qcap, int ntiles, unsigned long long* ctr) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < qcap) tq[i] = (int)i < ntiles ? (int)i + 1 : 0;
+  if ((int)i < ntiles) { state[i] = 1; visited[i] = 0; }
+  if (i == 0) { ctr[0] = 0; ctr[1] = (unsigned long long)ntiles; ctr[2] = (unsigned long long)ntiles; ctr[3] = 0; ctr[4] = ctr[5] = ctr[6] = ctr[7] = ctr[8] = 0; }
+}
+
+template <bool DINF>
+__global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
+  // dynamic shared memory carve-up (doubles first)
+  extern __shared__ __align__(16) unsigned char dsm[];
+  double* sp1 = reinterpret_cast<double*>(dsm);                       // DINF: share of flow to sk1 / sk2 per ring cell
+  double* sp2 = sp1 + (DINF ? RH * RW : 0);
+  float* sarea = reinterpret_cast<float*>(sp2 + (DINF ? RH * RW : 0));
+  float* sw = sarea + RH * RW;
+  int* lc = reinterpret_cast<int*>(sw + TC);
+  unsigned short* snode = reinterpret_cast<unsigned short*>(lc + TC);
+  unsigned short* ext = snode + TC;
+  unsigned char* sk1 = reinterpret_cast<unsigned char*>(ext + EXTCAP);   // DINF: the (at most two) receiving directions
+  unsigned char* sk2 = sk1 + RH * RW;
+  __shared__ int next, cur_tile, self_dirty;
+  const Strip& s = a.s;
+  const int tid = threadIdx.x;
+
+  for (;;) {
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+    if (tid == 0) { tk0 = clock64(); cur_tile = sched_pop(a); next = 0; self_dirty = 0; tk1 = clock64(); }
+    __syncthreads();
+    const int t = cur_tile;
+    if (t < 0) return;
+    const int tx = t % a.ntx, ty = t / a.ntx;
+    const int c0 = tx * TWX, r0 = 1 + ty * TWY;
+
+    // ---- 1. dependency counts (4 cells per word, 2 words per thread), before anything else
+    unsigned g0[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int lb = 4 * (tid + 256 * j);
+      const int lr = lb / TWX, lx = lb % TWX;
+      const int r = r0 + lr, c = c0 + lx;
+      unsigned word = 0xffffffffu;
+      if (r <= s.ny && c < s.pitch) word = __ldcg(a.cntw + (s.idx(r, c) >> 2));
+      g0[j] = word;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const unsigned b = (word >> (8 * i)) & 0xffu; lc[lb + i] = b <= 8u ? (int)b : -1; }
+    }
+    __threadfence();
+    __syncthreads();
+    // ---- 2. node words, areas (+ring), angles (+ring), weights
+    const bool first = ldv(a.visited + t) == 0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int lb = 4 * (tid + 256 * j);
+      const int lr = lb / TWX, lx = lb % TWX;
+      const int r = r0 + lr, c = c0 + lx;
+      ushort4 nv = make_ushort4(0, 0, 0, 0);
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r <= s.ny && c < s.pitch) {
+        nv = *reinterpret_cast<const ushort4*>(a.node + s.idx(r, c));
+        if (a.usew) wv = *reinterpret_cast<const float4*>(a.w + s.idx(r, c));
+      }
+      *reinterpret_cast<ushort4*>(snode + lb) = nv;
+      sw[lb] = wv.x; sw[lb + 1] = wv.y; sw[lb + 2] = wv.z; sw[lb + 3] = wv.w;
+    }
+    for (int i = tid; i < RH * RW; i += 256) {
+      const int rr = i / RW, rc = i - rr * RW;
+      const int r = r0 - 1 + rr, c = c0 - 1 + rc;
+      const bool in = r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.nx;
+      const bool interior = rr >= 1 && rr <= TWY && rc >= 1 && rc <= TWX;
+      float v = -1.0f;
+      if (in && !(first && interior)) v = __ldcg(a.area + s.idx(r, c));
+      sarea[i] = v;
+    }
+    if (DINF) {
+      // prop() of every ring cell once, in parallel and off the wavefront's critical path:
+      // a cell sends flow to at most two (adjacent) neighbours (src/commonLib.cpp:76-91)
+      for (int i = tid; i < RH * RW; i += 256) {
+        const int rr = i / RW, rc = i - rr * RW;
+        const int r = r0 - 1 + rr, c = c0 - 1 + rc;
+        unsigned char k1 = 0, k2 = 0; double p1 = 0., p2 = 0.;
+        if (r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.nx) {
+          const float av = a.ang[s.idx(r, c)];
+          const double th = a.theta[min(max(r - 1, 0), s.ny - 1)];
+#pragma unroll
+          for (int k = 1; k <= 8; ++k) {
+            const double p = prop_dev(av, k, th);
+            if (p > 0.0) { if (k1 == 0) { k1 = (unsigned char)k; p1 = p; } else { k2 = (unsigned char)k; p2 = p; } }
+          }
+        }
+        sk1[i] = k1; sk2[i] = k2; sp1[i] = p1; sp2[i] = p2;
+      }
+    }
+    __syncthreads();
+
+    // ---- 3. the wavefront inside the tile
+    if (tid == 0) tk2 = clock64();
+    int npass = 0;
+    for (;;) {
+      ++npass;
+      unsigned ready = 0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (lc[4 * (tid + 256 * j) + i] == 0) ready |= 1u << (4 * j + i);
+      __syncthreads();                       // every scan finishes before any count is decremented
+      for (unsigned m = ready; m; m &= m - 1) {
+        const int bit = __ffs(m) - 1;
+        int l = 4 * (tid + 256 * (bit >> 2)) + (bit & 3);
+        for (;;) {                            // follow the chain while we are the last arrival
+          const int lr = l / TWX, lx = l % TWX;
+          const int ri = (lr + 1) * RW + lx + 1;
+          const unsigned nd = snode[l];
+          const unsigned msk = nd & 0xffu;
+          bool con = (nd & NODE_CON) != 0;
+          float val;
+          if (!DINF) {
+            // src/aread8.cpp:228-257
+            if (a.usew) { const float wv = sw[l]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
+            else val = 1.0f;
+#pragma unroll
+            for (int k = 1; k <= 8; ++k)
+              if (msk & (1u << (k - 1))) {
+                const float an = sarea[ri + drow(k) * RW + dcol(k)];
+                if (nd_f(an, -1.0f)) con = true; else val = val + an;
+              }
+          } else {
+            // src/areadinf.cpp:187-218
+            val = 0.f;
+#pragma unroll
+            for (int k = 1; k <= 8; ++k)
+              if (msk & (1u << (k - 1))) {
+                const int ni = ri + drow(k) * RW + dcol(k);
+                const int kk = k > 4 ? k - 4 : k + 4;            // the direction from that neighbour to this cell
+                const double p = sk1[ni] == kk ? sp1[ni] : sp2[ni];
+                const float an = sarea[ni];
+                if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
+              }
+            if (a.usew) val = val + sw[l];
+            else val = (float)((double)val + a.dxc[r0 + lr - 1]);
+          }
+          if (con && a.contcheck) val = -1.0f;
+          sarea[ri] = val;
+          lc[l] = -1;
+          __threadfence_block();     // the area is in shared memory before any count says so
+          // ---- decrement the downslope cell(s)
+          int cont = -1;
+          if (!DINF) {
+            const int d = (int)((nd >> 8) & 0xfu);
+            if (d >= 1 && d <= 8) {
+              const int nlr = lr + drow(d), nlx = lx + dcol(d);
+              if (nlr >= 0 && nlr < TWY && nlx >= 0 && nlx < TWX) {
+                const int l2 = nlr * TWX + nlx;
+                if (atomicSub(&lc[l2], 1) == 1) cont = l2;   // invalid / finished cells hold a negative count
+              } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
+                ext[atomicAdd(&next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int k = j == 0 ? sk1[ri] : sk2[ri];
+              if (k == 0) continue;
+              const int nlr = lr + drow(k), nlx = lx + dcol(k);
+              if (nlr >= 0 && nlr < TWY && nlx >= 0 && nlx < TWX) {
+                const int l2 = nlr * TWX + nlx;
+                // a second neighbour that becomes ready is picked up by the next scan
+                if (atomicSub(&lc[l2], 1) == 1 && cont < 0) cont = l2;
+              } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
+                ext[atomicAdd(&next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
+              }
+            }
+          }
+          if (cont < 0) break;
+          __threadfence_block();     // counts first, then the areas they announce
+          l = cont;
+        }
+      }
+      if (!__syncthreads_or(ready != 0)) break;
+    }
+
+    // ---- 4. write the areas back, then publish counts and deliver the crossings
+    if (tid == 0) tk3 = clock64();
+    for (int i = tid; i < TC; i += 256) {
+      const int lr = i / TWX, lx = i - lr * TWX;
+      const int r = r0 + lr, c = c0 + lx;
+      if (r <= s.ny && c < s.nx) a.area[s.idx(r, c)] = sarea[(lr + 1) * RW + lx + 1];
+    }
+    if (tid == 0) a.visited[t] = 1;
+    __threadfence();
+    __syncthreads();
+    __threadfence();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int lb = 4 * (tid + 256 * j);
+      const int lr = lb / TWX, lx = lb % TWX;
+      const int r = r0 + lr, c = c0 + lx;
+      if (!(r <= s.ny && c < s.pitch)) continue;
+      unsigned delta = 0; int dec[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = (int)((g0[j] >> (8 * i)) & 0xffu);
+        const int now = lc[lb + i];
+        int ci = 0;
+        if (b <= 8) ci = now < 0 ? 0xfe - b : now - b;     // evaluated -> 0xFE (done); else minus the local arrivals
+        dec[i] = ci;
+        delta += (unsigned)ci << (8 * i);
+      }
+      if (delta != 0) {
+        const unsigned old = atomicAdd(a.cntw + (s.idx(r, c) >> 2), delta);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (dec[i] < 0 && (int)((old >> (8 * i)) & 0xffu) + dec[i] == 0) self_dirty = 1;   // became ready meanwhile
+      }
+    }
+    const int ne = next;
+    for (int e = tid; e < ne; e += 256) {
+      const int code = ext[e];
+      const int rr = code / RW, rc = code - rr * RW;
+      const int r = r0 - 1 + rr, c = c0 - 1 + rc;
+      if (r == 0 || r == s.ny + 1) { atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1); continue; }
+      const long long ci = s.idx(r, c);
+      if (!(a.node[ci] & NODE_VALID)) continue;
+      const unsigned sh = (unsigned)(ci & 3) * 8u;
+      const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - (1u << sh));
+      if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TWY) * a.ntx + c / TWX);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (self_dirty) sched_activate(a, t);
+      sched_finish(a, t);
+      // statistics (cycles, summed over CTAs): queue wait, load, wavefront, write-back + deliveries; passes
+      const long long tk4 = clock64();
+      atomicAdd(a.ctr + 4, (unsigned long long)(tk1 - tk0));
+      atomicAdd(a.ctr + 5, (unsigned long long)(tk2 - tk1));
+      atomicAdd(a.ctr + 6, (unsigned long long)(tk3 - tk2));
+      atomicAdd(a.ctr + 7, (unsigned long long)(tk4 - tk3));
+      atomicAdd(a.ctr + 8, (unsigned long long)npass);
+    }
+    __syncthreads();
+  }
+}
+constexpr size_t smem_bytes(bool dinf) {
+  return (dinf ? 2 * RH * RW * sizeof(double) : 0) + (RH * RW + TC) * sizeof(float) + TC * sizeof(int) + (TC + EXTCAP) * sizeof(unsigned short) +
+         2 * RH * RW;
+}
+}  // namespace
+
+// Runs the evaluation wavefront over one strip until no tile has a ready cell left.
+int sweep_tiles(td_ctx* ctx, bool dinf, const unsigned short* node, unsigned* cntw, float* area, const float* w, const float* ang,
+                const Strip& s, float w_nodata, int usew, int contcheck, const double* theta, const double* dxc, int* halo,
+                cudaStream_t st) {
+  SweepArgs a;
+  a.node = node; a.cntw = cntw; a.area = area; a.w = w; a.ang = ang; a.s = s; a.usew = usew; a.contcheck = contcheck;
+  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+  a.ntx = (s.nx + TWX - 1) / TWX; a.nty = (s.ny + TWY - 1) / TWY;
+  const long long nt = (long long)a.ntx * a.nty;
+  if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
+  unsigned qcap = 1u << 14;   // always far more slots than persistent CTAs holding tickets
+  while (qcap < (unsigned long long)nt) qcap <<= 1;
+  TD_CUDA(ctx->tileflags.ensure((size_t)nt * 4 + (size_t)qcap * 4 + (size_t)nt));
+  a.state = ctx->tileflags.as<int>();
+  a.tq = a.state + nt;
+  a.visited = reinterpret_cast<unsigned char*>(a.tq + qcap);
+  a.qmask = qcap - 1;
+  a.ctr = ctx->d_ctr + 24;
+  k_sched_init<<<(qcap + 255) / 256, 256, 0, st>>>(a.state, a.visited, a.tq, qcap, (int)nt, a.ctr);
+  TD_LAUNCHED();
+  static int grid_d8 = 0, grid_dinf = 0;
+  int& grid = dinf ? grid_dinf : grid_d8;
+  if (!grid) {
+    int dev = 0, sms = 0, occ = 0;
+    TD_CUDA(cudaGetDevice(&dev));
+    TD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (dinf) {
+      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true)));
+      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<true>, 256, smem_bytes(true)));
+    } else {
+      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false)));
+      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<false>, 256, smem_bytes(false)));
+    }
+    if (occ < 1) { set_error("sweep kernel does not fit on an SM"); return TD_ERR_CUDA; }
+    grid = sms * occ;     // persistent: every CTA is resident, so queue waits cannot deadlock
+  }
+  const int g = (int)std::min<long long>(grid, nt);
+  if (dinf) k_sweep_tiles<true><<<g, 256, smem_bytes(true), st>>>(a);
+  else k_sweep_tiles<false><<<g, 256, smem_bytes(false), st>>>(a);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+}  // namespace td
