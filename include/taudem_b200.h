@@ -155,6 +155,22 @@ int td_area_deps_dev(td_ctx*, const float* ang, float* sca, td_strip s, float an
 int td_area_sweep_dev(td_ctx*, const float* ang, const float* w, float* sca, td_strip s, int usew,
                       int contcheck, const double* dxc, void* stream);
 
+/* Row-strip partitioned sweeps (one strip per GPU, src/aread8.cpp:280-304 / src/areadinf.cpp:241-265):
+ *   td_*_deps_dev (after the halo rows of p / ang were exchanged), td_sweep_begin_dev, then rounds of
+ *     td_*_sweep_run_dev      - evaluates until no cell of the strip is ready; halo_out (2*pitch ints,
+ *                               zeroed by the caller) counts the decrements that crossed into the strip
+ *                               above ([0,pitch)) and below ([pitch,2*pitch));
+ *     (caller) exchange the first/last area rows and the halo_out arrays with the neighbour ranks;
+ *     td_sweep_apply_halo_dev - applies the received decrements to the first (dec_top) / last (dec_bot)
+ *                               row and queues the tiles whose cells became ready;
+ *   until no rank sent a decrement (ringTerm, src/linearpart.h:344-384).                               */
+int td_sweep_begin_dev(td_ctx*, td_strip s, void* stream);
+int td_sweep_apply_halo_dev(td_ctx*, td_strip s, const int* dec_top, const int* dec_bot, void* stream);
+int td_aread8_sweep_run_dev(td_ctx*, const float* w, float* ad8, td_strip s, float w_nodata, int usew,
+                            int contcheck, int* halo_out, void* stream);
+int td_area_sweep_run_dev(td_ctx*, const float* ang, const float* w, float* sca, td_strip s, int usew,
+                          int contcheck, const double* dxc, int* halo_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

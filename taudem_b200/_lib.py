@@ -64,6 +64,10 @@ SIGNATURES = {
     "td_aread8_sweep_dev": (_I, [_P, _P, _P, Strip, _F, _I, _I, _P]),
     "td_area_deps_dev": (_I, [_P, _P, _P, Strip, _F, _P, _P, _P]),
     "td_area_sweep_dev": (_I, [_P, _P, _P, _P, Strip, _I, _I, _P, _P]),
+    "td_sweep_begin_dev": (_I, [_P, Strip, _P]),
+    "td_sweep_apply_halo_dev": (_I, [_P, Strip, _P, _P, _P]),
+    "td_aread8_sweep_run_dev": (_I, [_P, _P, _P, Strip, _F, _I, _I, _P, _P]),
+    "td_area_sweep_run_dev": (_I, [_P, _P, _P, _P, Strip, _I, _I, _P, _P, _P]),
 }
 
 

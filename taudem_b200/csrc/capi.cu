@@ -200,8 +200,9 @@ int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, flo
                                 ctx->halo.as<int>(), (cudaStream_t)stream));
     return TD_OK;
   }
-  return td::sweep_tiles(ctx, false, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ad8, w, nullptr, Strip(s), w_nodata, usew,
-                         contcheck, nullptr, nullptr, ctx->halo.as<int>(), (cudaStream_t)stream);
+  if (int rc = td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
+  return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(),
+                       (cudaStream_t)stream);
 }
 
 int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, float ang_nodata, const double* dxc, const double* dyc,
@@ -219,9 +220,10 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   if (int rc = check_strip(s)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const Strip ss(s);
-  if (!chain_sweep())
-    return td::sweep_tiles(ctx, true, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), sca, w, ang, ss, 0.f, usew, contcheck,
-                           ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
+  if (!chain_sweep()) {
+    if (int rc = td::sweep_begin(ctx, ss, st)) return rc;
+    return td::sweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
+  }
   const unsigned long long cap = (unsigned long long)s.nx * s.ny / 8 + 4096;
   TD_CUDA(ctx->listA.ensure(sizeof(long long) * cap));
   TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap));
@@ -243,6 +245,28 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
     std::swap(cur, nxt);
   }
   return TD_OK;
+}
+
+// ---- multi-strip sweeps: begin (queue all tiles) / run (until locally drained; crossings into the
+// neighbour strips are counted in halo_out[0..pitch) = row above, [pitch..2*pitch) = row below) /
+// apply (decrements received from the neighbours for my first / last row)
+int td_sweep_begin_dev(td_ctx* ctx, td_strip s, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream);
+}
+int td_sweep_apply_halo_dev(td_ctx* ctx, td_strip s, const int* dec_top, const int* dec_bot, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::sweep_apply_halo(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
+}
+int td_aread8_sweep_run_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, float w_nodata, int usew, int contcheck, int* halo_out,
+                            void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, halo_out, (cudaStream_t)stream);
+}
+int td_area_sweep_run_dev(td_ctx* ctx, const float* ang, const float* w, float* sca, td_strip s, int usew, int contcheck, const double* dxc,
+                          int* halo_out, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::sweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

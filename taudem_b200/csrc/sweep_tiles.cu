@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
             const int d = (int)((nd >> 8) & 0xfu);
             if (d >= 1 && d <= 8) {
               const int nlr = lr + drow(d), nlx = lx + dcol(d);
-              if (nlr >= 0 && nlr < TWY && nlx >= 0 && nlx < TWX) {
+              if (nlr >= 0 && nlr < TWY && nlx >= 0 && nlx < TWX && r0 + nlr <= s.ny) {   // owned cell of this tile
                 const int l2 = nlr * TWX + nlx;
                 if (atomicSub(&lc[l2], 1) == 1) cont = l2;   // invalid / finished cells hold a negative count
               } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
               const int k = j == 0 ? sk1[ri] : sk2[ri];
               if (k == 0) continue;
               const int nlr = lr + drow(k), nlx = lx + dcol(k);
-              if (nlr >= 0 && nlr < TWY && nlx >= 0 && nlx < TWX) {
+              if (nlr >= 0 && nlr < TWY && nlx >= 0 && nlx < TWX && r0 + nlr <= s.ny) {   // owned cell of this tile
                 const int l2 = nlr * TWX + nlx;
                 // a second neighbour that becomes ready is picked up by the next scan
                 if (atomicSub(&lc[l2], 1) == 1 && cont < 0) cont = l2;
@@ -341,13 +341,32 @@ constexpr size_t smem_bytes(bool dinf) {
 }
 }  // namespace
 
-// Runs the evaluation wavefront over one strip until no tile has a ready cell left.
-int sweep_tiles(td_ctx* ctx, bool dinf, const unsigned short* node, unsigned* cntw, float* area, const float* w, const float* ang,
-                const Strip& s, float w_nodata, int usew, int contcheck, const double* theta, const double* dxc, int* halo,
-                cudaStream_t st) {
-  SweepArgs a;
-  a.node = node; a.cntw = cntw; a.area = area; a.w = w; a.ang = ang; a.s = s; a.usew = usew; a.contcheck = contcheck;
-  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+namespace {
+// Applies the dependency decrements received from the neighbour strips (addBorders,
+// src/linearpart.h:314-328 and src/aread8.cpp:283-297): dec_top[c] arrivals for the cell (row 1, c),
+// dec_bot[c] for (row ny, c).  A count that reaches zero queues the cell's tile.
+__global__ void k_apply_halo(SweepArgs a, const int* __restrict__ dec_top, const int* __restrict__ dec_bot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.s.nx) return;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int* dec = side == 0 ? dec_top : dec_bot;
+    if (dec == nullptr) continue;
+    const int d = dec[c];
+    if (d <= 0) continue;
+    const int r = side == 0 ? 1 : a.s.ny;
+    const long long ci = a.s.idx(r, c);
+    if (!(a.node[ci] & NODE_VALID)) continue;
+    const unsigned sh = (unsigned)(ci & 3) * 8u;
+    const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - ((unsigned)d << sh));
+    if ((int)((old >> sh) & 0xffu) == d) sched_activate(a, ((r - 1) / TWY) * a.ntx + c / TWX);
+  }
+}
+
+__global__ void k_sched_reset(unsigned long long* ctr) { ctr[0] = ctr[1] = ctr[2] = 0; }
+
+int sweep_args(td_ctx* ctx, SweepArgs& a, const Strip& s) {
+  a.s = s;
   a.ntx = (s.nx + TWX - 1) / TWX; a.nty = (s.ny + TWY - 1) / TWY;
   const long long nt = (long long)a.ntx * a.nty;
   if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
@@ -359,8 +378,44 @@ int sweep_tiles(td_ctx* ctx, bool dinf, const unsigned short* node, unsigned* cn
   a.visited = reinterpret_cast<unsigned char*>(a.tq + qcap);
   a.qmask = qcap - 1;
   a.ctr = ctx->d_ctr + 24;
-  k_sched_init<<<(qcap + 255) / 256, 256, 0, st>>>(a.state, a.visited, a.tq, qcap, (int)nt, a.ctr);
+  a.node = ctx->node.as<unsigned short>();
+  a.cntw = ctx->cnt.as<unsigned>();
+  return TD_OK;
+}
+}  // namespace
+
+// Queues every tile of the strip (start of a sweep).
+int sweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
+  SweepArgs a;
+  if (int rc = sweep_args(ctx, a, s)) return rc;
+  const int nt = a.ntx * a.nty;
+  k_sched_init<<<(a.qmask + 1 + 255) / 256, 256, 0, st>>>(a.state, a.visited, a.tq, a.qmask + 1, nt, a.ctr);
   TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// Decrements that crossed the strip boundary (from the neighbours' halo records); queues the tiles
+// whose cells became ready.  Must be called between two sweep_run calls.
+int sweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st) {
+  SweepArgs a;
+  if (int rc = sweep_args(ctx, a, s)) return rc;
+  k_sched_reset<<<1, 1, 0, st>>>(a.ctr);   // tickets abandoned at the end of the previous run are void
+  TD_LAUNCHED();
+  k_apply_halo<<<(s.nx + 255) / 256, 256, 0, st>>>(a, dec_top, dec_bot);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// Runs the evaluation wavefront over the queued tiles until no tile of the strip has a ready cell left.
+int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
+              int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
+  SweepArgs a;
+  if (int rc = sweep_args(ctx, a, s)) return rc;
+  a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
+  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+  const long long nt = (long long)a.ntx * a.nty;
   static int grid_d8 = 0, grid_dinf = 0;
   int& grid = dinf ? grid_dinf : grid_d8;
   if (!grid) {

@@ -1,0 +1,263 @@
+"""Row-strip partitioned execution over several GPUs (one process per GPU).
+
+Mirrors the reference's only parallelisation (src/linearpart.h): the grid is cut into
+contiguous row strips, ``ny = total // size`` rows each with the remainder on the LAST rank
+(linearpart::init, :125-166); neighbouring strips exchange one halo row (share(), :195-219)
+and, for the contributing-area wavefront, the dependency decrements that crossed the strip
+boundary (addBorders(), :314-328); a global reduction decides termination (ringTerm(), :344-384).
+torch.distributed (NCCL send/recv + all_reduce on GPUs, gloo in the CPU tests) is the transport.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from ._lib import check, lib
+
+
+def partition(total_ny, world):
+    """[(row0, ny)] per rank, exactly like linearpart::init."""
+    ny = total_ny // world
+    out = []
+    for r in range(world):
+        n = ny + (total_ny % world if r == world - 1 else 0)
+        out.append((r * ny, n))
+    return out
+
+
+def _staged():
+    """gloo moves host memory only: device rows are staged through the host (used by the 2-rank
+    single-GPU test; the production transport is NCCL over NVLink)."""
+    return dist.get_backend() == "gloo"
+
+
+def _p2p(sends, recvs, group=None):
+    """sends: [(tensor, peer)], recvs: [(tensor, peer)] posted as one batch."""
+    if not sends and not recvs:
+        return
+    stage = _staged()
+    ops, back = [], []
+    for t, peer in sends:
+        ops.append(dist.P2POp(dist.isend, t.cpu() if (stage and t.is_cuda) else t, peer, group))
+    for t, peer in recvs:
+        if stage and t.is_cuda:
+            h = torch.empty(t.shape, dtype=t.dtype)
+            back.append((t, h))
+            ops.append(dist.P2POp(dist.irecv, h, peer, group))
+        else:
+            ops.append(dist.P2POp(dist.irecv, t, peer, group))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for t, h in back:
+        t.copy_(h)
+
+
+def all_reduce_scalar(value, op=None, device="cpu"):
+    t = torch.tensor([value], dtype=torch.int64, device="cpu" if _staged() else device)
+    dist.all_reduce(t, op=op or dist.ReduceOp.SUM)
+    return int(t.item())
+
+
+def exchange_rows(t, ny, rank, world, group=None):
+    """share(): my first owned row -> rank-1's bottom halo, my last owned row -> rank+1's top halo.
+    ``t`` has ny+2 rows (row 0 / ny+1 are the halos)."""
+    if world == 1:
+        return
+    row = lambda i: t[i].view(torch.uint8)      # rows travel as bytes (NCCL has no int16)
+    sends, recvs = [], []
+    if rank > 0:
+        sends.append((row(1), rank - 1)); recvs.append((row(0), rank - 1))
+    if rank < world - 1:
+        sends.append((row(ny), rank + 1)); recvs.append((row(ny + 1), rank + 1))
+    _p2p(sends, recvs, group)
+
+
+def exchange_counts(halo_out, pitch, rank, world, group=None):
+    """Sends the decrements recorded for the strip above / below, returns (dec_top, dec_bot): the
+    decrements the neighbours recorded for my first / last row (None at the grid edge)."""
+    dec_top = torch.zeros(pitch, dtype=torch.int32, device=halo_out.device) if rank > 0 else None
+    dec_bot = torch.zeros(pitch, dtype=torch.int32, device=halo_out.device) if rank < world - 1 else None
+    sends, recvs = [], []
+    if rank > 0:
+        sends.append((halo_out[:pitch], rank - 1)); recvs.append((dec_top, rank - 1))
+    if rank < world - 1:
+        sends.append((halo_out[pitch:], rank + 1)); recvs.append((dec_bot, rank + 1))
+    _p2p(sends, recvs, group)
+    return dec_top, dec_bot
+
+
+class DistTools:
+    """The strip of this rank plus the exchange rounds around the device-strip level C ABI."""
+
+    def __init__(self, nx, total_ny, rank, world, device="cuda"):
+        from .device import DeviceStrip, Tools
+        self.rank, self.world = rank, world
+        self.row0, self.ny = partition(total_ny, world)[rank]
+        self.s = DeviceStrip(nx, self.ny, has_top=rank > 0, has_bot=rank < world - 1, row0=self.row0, total_ny=total_ny, device=device)
+        self.T = Tools()
+        self.l = lib()
+        self.rounds = 0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def share(self, t):
+        exchange_rows(t, self.ny, self.rank, self.world)
+
+    def _sweep(self, run, out):
+        s = self.s
+        check(self.l.td_sweep_begin_dev(self.T.ctx, s.c, self._stream()))
+        halo = torch.zeros(2 * s.pitch, dtype=torch.int32, device=s.device)
+        self.rounds = 0
+        while True:
+            halo.zero_()
+            run(halo)
+            self.rounds += 1
+            if self.world == 1:
+                break
+            dec_top, dec_bot = exchange_counts(halo, s.pitch, self.rank, self.world)
+            self.share(out)                                   # the area rows the decrements announce
+            if all_reduce_scalar(int(halo.sum()), device=s.device) == 0:   # ringTerm: did anybody hand over work?
+                break
+            check(self.l.td_sweep_apply_halo_dev(self.T.ctx, s.c, None if dec_top is None else C.c_void_p(dec_top.data_ptr()),
+                                                 None if dec_bot is None else C.c_void_p(dec_bot.data_ptr()), self._stream()))
+        return out
+
+    def aread8(self, p, ad8=None, w=None, nodata=-32768, w_nodata=-9999.0, contcheck=True, shared=False):
+        s = self.s
+        ad8 = s.empty(torch.float32) if ad8 is None else ad8
+        if not shared:
+            self.share(p)
+        self.T.aread8_deps(s, p, ad8, nodata)
+        wp = None if w is None else C.c_void_p(w.data_ptr())
+        return self._sweep(lambda halo: check(self.l.td_aread8_sweep_run_dev(self.T.ctx, wp, C.c_void_p(ad8.data_ptr()), s.c, w_nodata, int(w is not None),
+                                                                              int(contcheck), C.c_void_p(halo.data_ptr()), self._stream())), ad8)
+
+    def areadinf(self, ang, dxc, dyc, sca=None, w=None, nodata=-3.4028234663852886e38, contcheck=True, shared=False):
+        s = self.s
+        sca = s.empty(torch.float32) if sca is None else sca
+        if not shared:
+            self.share(ang)
+        self.T.areadinf_deps(s, ang, sca, dxc, dyc, nodata)
+        wp = None if w is None else C.c_void_p(w.data_ptr())
+        return self._sweep(lambda halo: check(self.l.td_area_sweep_run_dev(self.T.ctx, C.c_void_p(ang.data_ptr()), wp, C.c_void_p(sca.data_ptr()), s.c,
+                                                                            int(w is not None), int(contcheck), C.c_void_p(dxc.data_ptr()),
+                                                                            C.c_void_p(halo.data_ptr()), self._stream())), sca)
+
+    def d8_slopes(self, fel, dxc, dyc, nodata=-3.0e38):
+        self.share(fel)
+        return self.T.d8_slopes(self.s, fel, dxc, dyc, nodata)
+
+    def dinf_slopes(self, fel, dxc, dyc, nodata=-3.0e38):
+        self.share(fel)
+        return self.T.dinf_slopes(self.s, fel, dxc, dyc, nodata)
+
+    def pitremove(self, dem, nodata=-9999.0, four_way=False):
+        """flood(): local relaxation to convergence, halo exchange, repeat until no strip changes
+        (src/flood.cpp:344-479 share()/ringTerm() structure)."""
+        s = self.s
+        self.share(dem)
+        w = self.T.flood_init(s, dem, nodata, four_way)
+        while True:
+            self.share(w)                                     # fresh halo rows from the neighbours
+            moved = int(self.T.flood_relax(s, dem, w, four_way))
+            if self.world > 1:
+                moved = all_reduce_scalar(moved, device=s.device)   # ringTerm: did any strip move?
+            if moved == 0:
+                break
+        return w
+
+
+def bench_main(args, rank, world, local):
+    """N > 1 arm of bench.py: strong scaling of the same DEM over row strips."""
+    import json
+    import os
+    import sys
+    import time
+
+    import bench as B
+    import taudem_b200 as td
+    from .device import Tools
+
+    dev = torch.device("cuda", local)
+    n = B.pick_size(torch, args.size)
+    cells = n * n
+    log = lambda *a: rank == 0 and print("[bench %.1fs]" % (time.time() - B.T0), *a, file=sys.stderr, flush=True)
+    # inputs: every rank prepares the full rasters with the single-strip tools (untimed; the distributed
+    # flat resolution is not implemented yet) and keeps its own strip
+    T0 = Tools()
+    s_full, dxc_f, dyc_f, p_full, ang_full, info = B.build_inputs(T0, n, torch)
+    D = DistTools(n, n, rank, world, device=dev)
+    s = D.s
+    p = s.empty(torch.int16); ang = s.empty(torch.float32)
+    p[1:s.ny + 1].copy_(p_full[1 + D.row0:1 + D.row0 + s.ny]); ang[1:s.ny + 1].copy_(ang_full[1 + D.row0:1 + D.row0 + s.ny])
+    del p_full, ang_full
+    T0.close(); torch.cuda.empty_cache()
+    dxc, dyc = s.rows(30.0), s.rows(30.0)
+    ad8, sca = s.empty(torch.float32), s.empty(torch.float32)
+    log("inputs ready", info)
+
+    def step():
+        D.aread8(p, ad8)
+        r1 = D.rounds
+        D.areadinf(ang, dxc, dyc, sca)
+        return r1, D.rounds
+
+    for _ in range(args.warmup):
+        rounds = step()
+    td.reset_launch_count()
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with B.ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            rounds = step()
+        e1.record()
+        torch.cuda.synchronize(); dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = torch.tensor([td.launch_count()], device=dev, dtype=torch.int64)
+    dist.all_reduce(launches)
+    mx = torch.stack([s.owned(ad8).max(), s.owned(sca).max()]).double()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = cells / 1e6 / (ms_per_step * 1e-3)
+
+    # end to end: pinned host strips in, pinned host strips out, copies inside the timed region
+    hp = torch.empty((s.ny, n), dtype=torch.int16, pin_memory=True); hp.copy_(s.owned(p))
+    ha = torch.empty((s.ny, n), dtype=torch.float32, pin_memory=True); ha.copy_(s.owned(ang))
+    o1 = torch.empty((s.ny, n), dtype=torch.float32, pin_memory=True); o2 = torch.empty((s.ny, n), dtype=torch.float32, pin_memory=True)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def e2e_step():
+        s.owned(p).copy_(hp, non_blocking=True); s.owned(ang).copy_(ha, non_blocking=True)
+        step()
+        o1.copy_(s.owned(ad8), non_blocking=True); o2.copy_(s.owned(sca), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_step()
+    dist.barrier(); t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    dist.barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev, dtype=torch.float64)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak, peak_src = B.peaks()
+        line = {"metric": B.METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"aread8 + areadinf on {n}x{n} float32 synthetic fractal DEM (hills: H={B.HURST}, tilt={B.TILT}, seed={B.SEED}, 30 m cells), contamination check on, no weights",
+                           "cells": cells, "partition": f"{world} row strips (linearpart: total//size rows, remainder on the last rank), NCCL send/recv halo + decrement exchange, all_reduce termination",
+                           "exchange_rounds": {"aread8": rounds[0], "areadinf": rounds[1]}, "l2": "inputs exceed the 126 MB L2; no explicit flush",
+                           "timed": "CUDA events per rank, max over ranks", "max_ad8": float(mx[0]), "max_sca": float(mx[1]), **info},
+                "clocks": clk.summary(),
+                "e2e": {"value": round(cells / 1e6 / float(te.item()), 2), "unit": "Mcells/s", "h2d_bytes_per_step": cells * 6, "d2h_bytes_per_step": cells * 8,
+                        "steps": e2e_steps, "ms_per_step": round(float(te.item()) * 1e3, 2), "api": "per-rank pinned host strips -> device strips -> DistTools.aread8/areadinf -> pinned host strips"},
+                "gpu_launches": int(launches.item()),
+                "roofline": {"bound": "hbm", "kernel": "k_sweep_tiles<dinf>", "achieved": round(8 * cells / (ms_per_step * 1e-3) / 1e9 / world, 2), "peak": peak, "unit": "GB/s",
+                             "frac": round(8 * cells / (ms_per_step * 1e-3) / 1e9 / world / peak, 5), "traffic": None, "peak_source": peak_src,
+                             "note": "per GPU, whole step time attributed to the dominant kernel (upper bound on its duration)"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
