@@ -25,6 +25,22 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
   __shared__ __align__(8) uint64_t bar;
   const int c0 = blockIdx.x * TW, r0 = 1 + blockIdx.y * TH;
   load_tile_tma<float, TW, TH>(tile, &bar, ang, s, r0, c0);
+  // outflow directions (k1 | k2 << 4) of every staged cell, one prop() interval search each
+  __shared__ double saref[(TH + 2) * 10];
+  __shared__ unsigned char sout[G::ELEMS];
+  for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) saref[i] = aref(i % 10, theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < G::ELEMS; i += 256) {
+    const int t = i / G::SW, sc = i - t * G::SW;
+    const int gr = r0 - 1 + t, gc = c0 - G::HP + sc;
+    unsigned char code = 0;
+    if (s.on_grid(gr, gc)) {
+      const float av = tile[i];
+      if (!nd_f(av, nodata)) { const Outflow o = dinf_outflow(av, saref + t * 10); code = (unsigned char)(o.k1 | (o.k2 << 4)); }
+    }
+    sout[i] = code;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int pass = 0; pass < TH / 8; ++pass) {
@@ -32,17 +48,16 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     const int r = r0 + tr, c = c0 + lane * 4;
     if (r > s.ny || c >= s.pitch) continue;
     const float* pm = tile + tr * G::SW + G::HP + lane * 4;
-    float nb[3][6];
+    const unsigned char* po = sout + tr * G::SW + G::HP + lane * 4;
+    float nb[3][6]; unsigned char ob[3][6];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const float* q = pm + j * G::SW;
       const float4 v = *reinterpret_cast<const float4*>(q);
       nb[j][0] = q[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = q[4];
-    }
-    // atan2(dy,dx) of the rows above / at / below (clamped to the strip's own rows)
-    double th[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) th[j] = theta[min(max(r - 2 + j, 0), s.ny - 1)];
+      for (int i = 0; i < 6; ++i) ob[j][i] = po[j * G::SW + i - 1];
+    }
     unsigned short on4[4]; unsigned char oc4[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -54,8 +69,10 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
         const float an = nb[1 + drow(k)][i + 1 + dcol(k)];
         if (!s.on_grid(r + drow(k), cc + dcol(k)) || nd_f(an, nodata)) con = true;
         else {
-          const float p = (float)prop_dev(an, (k + 4) % 8, th[1 + drow(k)]);   // float p as in initNeighborDinfup
-          if (p > 0.0) mask |= 1u << (k - 1);
+          // neighbour k drains to me when one of its receiving directions is (k+4)%8 (src/commonLib.cpp:105-134)
+          const int kk = k > 4 ? k - 4 : k + 4;
+          const unsigned code = ob[1 + drow(k)][i + 1 + dcol(k)];
+          if ((int)(code & 15u) == kk || (int)(code >> 4) == kk) mask |= 1u << (k - 1);
         }
       }
       on4[i] = valid ? (unsigned short)(NODE_VALID | (con ? NODE_CON : 0u) | mask) : (unsigned short)0;

@@ -82,4 +82,42 @@ __device__ __forceinline__ double prop_dev(float a, int k, double t) {
   return p;
 }
 
+// The outflow of a D-infinity cell in one step: the (at most two) receiving directions and their
+// shares, identical to evaluating prop(a, k) for k = 1..8 but with one interval search and two
+// divisions.  ar[0..9] is prop()'s aref[] table for the cell's row.  With j = #{i in 1..9 : ar[i] <= a}:
+//   1 <= j <= 8 : a lies in [ar[j], ar[j+1])  -> directions j and j+1 (direction 1 after j = 8, reached
+//                 through prop's "k == 1 && a > PI" wrap with the float-rounded a - 2*PI);
+//   j == 9 (a >= 2*PI) or j == 0 (a < 0)    -> direction 1 only.
+struct Outflow { int k1, k2; double p1, p2; };
+
+__device__ __forceinline__ double prop_dir1_wrapped(float a, const double* ar) {
+  const float a1 = (float)(a - 2.0 * TD_PI);
+  double p = 0.;
+  if (a1 > ar[0] && a1 < ar[2]) p = (a1 > ar[1]) ? (ar[2] - a1) / (ar[2] - ar[1]) : (a1 - ar[0]) / (ar[1] - ar[0]);
+  return p;
+}
+
+__device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) {
+  Outflow o; o.k1 = o.k2 = 0; o.p1 = o.p2 = 0.;
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i <= 9; ++i) j += (a >= ar[i]) ? 1 : 0;
+  double pA = 0., pB = 0.; int kA = 0, kB = 0;
+  if (j >= 1 && j <= 8) {
+    const double lo = ar[j - 1], mid = ar[j], hi = ar[j + 1];
+    kA = j;
+    pA = (a > mid) ? (hi - a) / (hi - mid) : (a - lo) / (mid - lo);
+    if (j < 8) { kB = j + 1; if (a > mid) pB = (a - mid) / (hi - mid); }
+    else { kB = 1; pB = prop_dir1_wrapped(a, ar); }
+  } else if (j == 9) {
+    kA = 1; pA = prop_dir1_wrapped(a, ar);
+  } else {
+    kA = 1;
+    if (a > ar[0]) pA = (a > ar[1]) ? (ar[2] - a) / (ar[2] - ar[1]) : (a - ar[0]) / (ar[1] - ar[0]);
+  }
+  if (!(pA < 1e-5)) { o.k1 = kA; o.p1 = pA; }
+  if (!(pB < 1e-5)) { if (o.k1 == 0) { o.k1 = kB; o.p1 = pB; } else { o.k2 = kB; o.p2 = pB; } }
+  return o;
+}
+
 }  // namespace td

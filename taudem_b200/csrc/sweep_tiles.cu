@@ -107,19 +107,22 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
   double* sp1 = reinterpret_cast<double*>(dsm);                       // DINF: share of flow to sk1 / sk2 per ring cell
   double* sp2 = sp1 + (DINF ? RH * RW : 0);
   float* sarea = reinterpret_cast<float*>(sp2 + (DINF ? RH * RW : 0));
-  float* sw = sarea + RH * RW;
-  int* lc = reinterpret_cast<int*>(sw + TC);
+  float* sang = sarea + RH * RW;                                      // DINF: angles of the ring
+  float* sw = sang + (DINF ? RH * RW : 0);                            // weights (only with -wg)
+  int* lc = reinterpret_cast<int*>(sw + (a.usew ? TC : 0));
   unsigned short* snode = reinterpret_cast<unsigned short*>(lc + TC);
   unsigned short* ext = snode + TC;
-  unsigned char* sk1 = reinterpret_cast<unsigned char*>(ext + EXTCAP);   // DINF: the (at most two) receiving directions
+  unsigned short* wq = ext + EXTCAP;                                  // ready cells (local index), 0xFFFF = not yet published
+  unsigned char* sk1 = reinterpret_cast<unsigned char*>(wq + TC);     // DINF: the (at most two) receiving directions
   unsigned char* sk2 = sk1 + RH * RW;
-  __shared__ int next, cur_tile, self_dirty;
+  __shared__ int next, cur_tile, self_dirty, wq_head, wq_tail, outstanding;
+  __shared__ double saref[DINF ? RH * 10 : 1];                     // prop()'s aref[] table of every ring row
   const Strip& s = a.s;
   const int tid = threadIdx.x;
 
   for (;;) {
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
-    if (tid == 0) { tk0 = clock64(); cur_tile = sched_pop(a); next = 0; self_dirty = 0; tk1 = clock64(); }
+    if (tid == 0) { tk0 = clock64(); cur_tile = sched_pop(a); next = 0; self_dirty = 0; wq_head = 0; wq_tail = 0; outstanding = 0; tk1 = clock64(); }
     __syncthreads();
     const int t = cur_tile;
     if (t < 0) return;
@@ -155,7 +158,8 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
         if (a.usew) wv = *reinterpret_cast<const float4*>(a.w + s.idx(r, c));
       }
       *reinterpret_cast<ushort4*>(snode + lb) = nv;
-      sw[lb] = wv.x; sw[lb + 1] = wv.y; sw[lb + 2] = wv.z; sw[lb + 3] = wv.w;
+      if (a.usew) { sw[lb] = wv.x; sw[lb + 1] = wv.y; sw[lb + 2] = wv.z; sw[lb + 3] = wv.w; }
+      *reinterpret_cast<ushort4*>(wq + lb) = make_ushort4(0xffff, 0xffff, 0xffff, 0xffff);
     }
     for (int i = tid; i < RH * RW; i += 256) {
       const int rr = i / RW, rc = i - rr * RW;
@@ -165,24 +169,19 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
       float v = -1.0f;
       if (in && !(first && interior)) v = __ldcg(a.area + s.idx(r, c));
       sarea[i] = v;
+      if (DINF) sang[i] = in ? a.ang[s.idx(r, c)] : TD_MISSINGFLOAT;
     }
     if (DINF) {
+      for (int i = tid; i < RH * 10; i += 256) saref[i] = aref(i % 10, a.theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]);
+      __syncthreads();
       // prop() of every ring cell once, in parallel and off the wavefront's critical path:
       // a cell sends flow to at most two (adjacent) neighbours (src/commonLib.cpp:76-91)
       for (int i = tid; i < RH * RW; i += 256) {
         const int rr = i / RW, rc = i - rr * RW;
         const int r = r0 - 1 + rr, c = c0 - 1 + rc;
-        unsigned char k1 = 0, k2 = 0; double p1 = 0., p2 = 0.;
-        if (r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.nx) {
-          const float av = a.ang[s.idx(r, c)];
-          const double th = a.theta[min(max(r - 1, 0), s.ny - 1)];
-#pragma unroll
-          for (int k = 1; k <= 8; ++k) {
-            const double p = prop_dev(av, k, th);
-            if (p > 0.0) { if (k1 == 0) { k1 = (unsigned char)k; p1 = p; } else { k2 = (unsigned char)k; p2 = p; } }
-          }
-        }
-        sk1[i] = k1; sk2[i] = k2; sp1[i] = p1; sp2[i] = p2;
+        Outflow o; o.k1 = o.k2 = 0; o.p1 = o.p2 = 0.;
+        if (r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.nx) o = dinf_outflow(sang[i], saref + rr * 10);
+        sk1[i] = (unsigned char)o.k1; sk2[i] = (unsigned char)o.k2; sp1[i] = o.p1; sp2[i] = o.p2;
       }
     }
     __syncthreads();
@@ -190,18 +189,43 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
     // ---- 3. the wavefront inside the tile
     if (tid == 0) tk2 = clock64();
     int npass = 0;
-    for (;;) {
-      ++npass;
+    {
+      // D-infinity: every thread publishes the ready cells among its own eight to the shared work queue
+      // (a cell can make two neighbours ready; idle threads take the second one at once).
+      // D8: a chain never forks, every thread simply walks the chains that start in its own cells
+      // (threads spinning on a queue only slow the walkers down).
+      int nready = 0;
       unsigned ready = 0;
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (lc[4 * (tid + 256 * j) + i] == 0) ready |= 1u << (4 * j + i);
-      __syncthreads();                       // every scan finishes before any count is decremented
-      for (unsigned m = ready; m; m &= m - 1) {
-        const int bit = __ffs(m) - 1;
-        int l = 4 * (tid + 256 * (bit >> 2)) + (bit & 3);
+        for (int i = 0; i < 4; ++i) {
+          const int l = 4 * (tid + 256 * j) + i;
+          if (lc[l] == 0) {
+            if (DINF) { wq[atomicAdd(&wq_tail, 1)] = (unsigned short)l; ++nready; }
+            else ready |= 1u << (4 * j + i);
+          }
+        }
+      if (nready) atomicAdd(&outstanding, nready);
+      __syncthreads();                       // all publications (and `outstanding`) are complete before any count moves
+      // work loop: take a ready cell, follow its chain; `outstanding` = live chains + queued cells
+      for (;;) {
+        int l = -1;
+        if (DINF) {
+          const int h = atomicAdd(&wq_head, 1);   // ticket order
+          for (;;) {
+            if (h < ldv(&wq_tail)) { unsigned short v; while ((v = ldv(wq + h)) == 0xffff) {} l = v; break; }
+            if (ldv(&outstanding) <= 0) break;
+            __nanosleep(100);
+          }
+        } else if (ready) {
+          const int bit = __ffs(ready) - 1;
+          ready &= ready - 1;
+          l = 4 * (tid + 256 * (bit >> 2)) + (bit & 3);
+        }
+        if (l < 0) break;
+        ++npass;
+        __threadfence_block();
         for (;;) {                            // follow the chain while we are the last arrival
           const int lr = l / TWX, lx = l % TWX;
           const int ri = (lr + 1) * RW + lx + 1;
@@ -259,8 +283,14 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
               const int nlr = lr + drow(k), nlx = lx + dcol(k);
               if (nlr >= 0 && nlr < TWY && nlx >= 0 && nlx < TWX && r0 + nlr <= s.ny) {   // owned cell of this tile
                 const int l2 = nlr * TWX + nlx;
-                // a second neighbour that becomes ready is picked up by the next scan
-                if (atomicSub(&lc[l2], 1) == 1 && cont < 0) cont = l2;
+                if (atomicSub(&lc[l2], 1) == 1) {
+                  if (cont < 0) cont = l2;
+                  else {                        // a second ready neighbour: hand it to an idle thread
+                    atomicAdd(&outstanding, 1);
+                    __threadfence_block();
+                    wq[atomicAdd(&wq_tail, 1)] = (unsigned short)l2;
+                  }
+                }
               } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
                 ext[atomicAdd(&next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
               }
@@ -270,8 +300,9 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
           __threadfence_block();     // counts first, then the areas they announce
           l = cont;
         }
+        if (DINF) atomicSub(&outstanding, 1);  // this chain has ended
       }
-      if (!__syncthreads_or(ready != 0)) break;
+      __syncthreads();
     }
 
     // ---- 4. write the areas back, then publish counts and deliver the crossings
@@ -335,9 +366,9 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
     __syncthreads();
   }
 }
-constexpr size_t smem_bytes(bool dinf) {
-  return (dinf ? 2 * RH * RW * sizeof(double) : 0) + (RH * RW + TC) * sizeof(float) + TC * sizeof(int) + (TC + EXTCAP) * sizeof(unsigned short) +
-         2 * RH * RW;
+size_t smem_bytes(bool dinf, bool usew) {
+  return (dinf ? 2 * RH * RW * sizeof(double) : 0) + (RH * RW + (dinf ? RH * RW : 0) + (usew ? TC : 0)) * sizeof(float) + TC * sizeof(int) +
+         (TC + EXTCAP + TC) * sizeof(unsigned short) + 2 * RH * RW;
 }
 }  // namespace
 
@@ -423,18 +454,18 @@ int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* 
     TD_CUDA(cudaGetDevice(&dev));
     TD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (dinf) {
-      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true)));
-      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<true>, 256, smem_bytes(true)));
+      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true, true)));
+      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<true>, 256, smem_bytes(true, false)));
     } else {
-      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false)));
-      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<false>, 256, smem_bytes(false)));
+      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false, true)));
+      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<false>, 256, smem_bytes(false, false)));
     }
     if (occ < 1) { set_error("sweep kernel does not fit on an SM"); return TD_ERR_CUDA; }
     grid = sms * occ;     // persistent: every CTA is resident, so queue waits cannot deadlock
   }
   const int g = (int)std::min<long long>(grid, nt);
-  if (dinf) k_sweep_tiles<true><<<g, 256, smem_bytes(true), st>>>(a);
-  else k_sweep_tiles<false><<<g, 256, smem_bytes(false), st>>>(a);
+  if (dinf) k_sweep_tiles<true><<<g, 256, smem_bytes(true, usew != 0), st>>>(a);
+  else k_sweep_tiles<false><<<g, 256, smem_bytes(false, usew != 0), st>>>(a);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;
