@@ -113,3 +113,26 @@ def test_reference_tools_reproduce_golden(refrun, name):
         assert_bits(R.aread8(p), g["ad8"], "ad8")
         ang, slp = R.dinfflowdir(fel); assert_bits(ang, g["ang"], "ang"); assert_bits(slp, g["slp"], "slp")
         assert_bits(R.areadinf(ang, weights=g["w"]), g["sca_w"], "sca_w")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_c_restatement_reproduces_golden(name):
+    """Pins the C restatement (oracle/port): bit-identical to the reference tools' outputs on every
+    golden case, for every tool, weights / -nc / -4way variants included."""
+    import port
+    if not port.available():
+        pytest.skip("oracle/port not built")
+    g = load_golden(name)
+    dx, dy = float(g["dx"]), float(g["dy"])
+    assert_bits(port.pitremove(g["dem"]), g["fel"], "fel")
+    assert_bits(port.pitremove(g["dem"], four_way=True), g["fel4"], "fel4")
+    p, sd8 = port.d8flowdir(g["fel"], dx=dx, dy=dy)
+    assert_bits(sd8, g["sd8"], "sd8"); assert_bits(p, g["p"], "p")
+    ang, slp = port.dinfflowdir(g["fel"], dx=dx, dy=dy)
+    assert_bits(slp, g["slp"], "slp"); assert_bits(ang, g["ang"], "ang")
+    assert_bits(port.aread8(g["p"]), g["ad8"], "ad8")
+    assert_bits(port.aread8(g["p"], weights=g["w"]), g["ad8_w"], "ad8_w")
+    assert_bits(port.aread8(g["p"], contcheck=False), g["ad8_nc"], "ad8_nc")
+    assert_bits(port.areadinf(g["ang"], dx=dx, dy=dy), g["sca"], "sca")
+    assert_bits(port.areadinf(g["ang"], weights=g["w"], dx=dx, dy=dy), g["sca_w"], "sca_w")
+    assert_bits(port.areadinf(g["ang"], dx=dx, dy=dy, contcheck=False), g["sca_nc"], "sca_nc")
