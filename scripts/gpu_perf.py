@@ -29,13 +29,24 @@ def main():
     tilt = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     T = Tools()
     s = DeviceStrip(n, n)
+    # box calibration: plain copy bandwidth + SM clock (timings differ between boxes of the pool)
+    a = torch.empty(1 << 28, dtype=torch.float32, device="cuda"); b = torch.empty_like(a)
+    best = min(timed(lambda: b.copy_(a))[1] for _ in range(5))
+    try:
+        import pynvml
+        pynvml.nvmlInit(); h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        clk = f"sm {pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)} MHz (max {pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)})"
+    except Exception as e:
+        clk = str(e)
+    print(f"calibration: copy {2 * a.numel() * 4 / best / 1e9:.0f} GB/s, {clk}")
+    del a, b
     mc = n * n / 1e6
     dxc, dyc = s.rows(30.0), s.rows(30.0)
     dem, t = timed(lambda: T.gen_dem(s, hurst=hurst, tilt=tilt)); print(f"gen_dem      {t*1e3:9.2f} ms")
     for rep in range(2):
         fel, t = timed(lambda: T.pitremove(s, dem)); print(f"pitremove    {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {8*mc/t/1e6*1e3/1e3:8.3f} GB/s")
     del dem
-    for rep in range(2):
+    for rep in range(4):
         (p, sd8, nflat), t = timed(lambda: T.d8_slopes(s, fel, dxc, dyc)); print(f"d8 stencil   {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {10*mc/t/1e3:8.1f} GB/s  flats {nflat}")
     felc = fel.clone()
     left, t = timed(lambda: T.d8_flats(s, felc, p, dxc, dyc)); print(f"d8 flats     {t*1e3:9.2f} ms  left {left}")
@@ -46,7 +57,7 @@ def main():
     ad8 = s.empty(torch.float32)
     _, t1 = timed(lambda: T.aread8_deps(s, p, ad8)); _, t2 = timed(lambda: T.aread8_sweep(s, ad8)); print(f"  deps {t1*1e3:.2f} ms  sweep {t2*1e3:.2f} ms  max area {float(s.owned(ad8).max())}  {stats(T)} of {((n+63)//64)*((n+31)//32)} tiles")
     del ad8, p
-    for rep in range(2):
+    for rep in range(4):
         (ang, slp, nflat), t = timed(lambda: T.dinf_slopes(s, fel, dxc, dyc)); print(f"dinf stencil {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {12*mc/t/1e3:8.1f} GB/s  flats {nflat}")
     del slp
     felc.copy_(fel)

@@ -190,6 +190,7 @@ int td_aread8_deps_dev(td_ctx* ctx, const int16_t* p, float* ad8, td_strip s, in
   if (int rc = check_strip(s)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = ensure_dep_state(ctx, Strip(s), st)) return rc;
+  ctx->sweep_dinf = 0;
   TD_CUDA(td::launch_deps_d8(p, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), ad8, Strip(s), p_nodata, st));
   return TD_OK;
 }
@@ -211,6 +212,7 @@ int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, floa
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = ensure_dep_state(ctx, Strip(s), st)) return rc;
   if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
+  ctx->sweep_dinf = 1;
   TD_CUDA(td::launch_deps_dinf(ang, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), sca, Strip(s), ang_nodata,
                                ctx->theta.as<double>(), st));
   return TD_OK;

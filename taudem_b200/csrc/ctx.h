@@ -34,6 +34,7 @@ struct td_ctx {
   Buf theta;     // per-row atan2(dy,dx) | atan2(dx,dy) tables (doubles)
   Buf rows;      // per-row dxc | dyc (host-grid level calls)
   Buf io[4];     // raster strips of host-grid level calls
+  int sweep_dinf = 0;                    // which dependency state node/cnt hold (tile height of the sweep)
   unsigned long long* d_ctr = nullptr;   // 32 device counters
   unsigned long long* h_ctr = nullptr;   // pinned host mirror
   td_ctx();

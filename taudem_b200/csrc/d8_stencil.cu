@@ -27,6 +27,56 @@ __device__ __forceinline__ void d8_try(float z, float zn, double f, int k, float
   if (sl > smax) { smax = sl; dir = k; }
 }
 
+// zz = neighbours in scan order 1,3,5,7,2,4,6,8 (rare path, kept out of line)
+__device__ __noinline__ void d8_literal(float z, const float* zz, double fE, double fN, double fD, int& dir, float& smax) {
+  dir = 0; smax = 0.f;
+  d8_try(z, zz[0], fE, 1, smax, dir); d8_try(z, zz[1], fN, 3, smax, dir);
+  d8_try(z, zz[2], fE, 5, smax, dir); d8_try(z, zz[3], fN, 7, smax, dir);
+  d8_try(z, zz[4], fD, 2, smax, dir); d8_try(z, zz[5], fD, 4, smax, dir);
+  d8_try(z, zz[6], fD, 6, smax, dir); d8_try(z, zz[7], fD, 8, smax, dir);
+}
+
+// One cell.  nbr = the 3x3 neighbourhood (row above / centre / below, columns i..i+2 of nb).
+// The reference scans k = 1,3,5,7,2,4,6,8 and keeps the first k with the strictly largest
+// slope_k = (float)(fact_k * (double)(z - z_k)).  fact takes only three values per row (E/W, N/S,
+// diagonals) and the rounding is monotone in the elevation drop, so the maximum of each group is
+// attained by the group's largest drop: three exact products instead of eight.  The winner is the
+// first k in scan order whose group slope equals the maximum and whose drop equals the group's
+// largest drop.  Two different drops can round to the same slope only when they are within an ulp or
+// two of each other; any such near-tie (relative gap < 2^-20) takes the literal eight-product path.
+__device__ __forceinline__ void d8_cell(const float (&nb)[3][6], int i, double fE, double fN, double fD, int& dir, float& smax) {
+  const float z = nb[1][i + 1];
+  const float e1 = z - nb[1][i + 2], e5 = z - nb[1][i], e3 = z - nb[0][i + 1], e7 = z - nb[2][i + 1];
+  const float e2 = z - nb[0][i + 2], e4 = z - nb[0][i], e6 = z - nb[2][i], e8 = z - nb[2][i + 2];
+  const float mE = fmaxf(e1, e5), mN = fmaxf(e3, e7), mD = fmaxf(fmaxf(e2, e4), fmaxf(e6, e8));
+  const float sE = (float)(fE * (double)mE), sN = (float)(fN * (double)mN), sD = (float)(fD * (double)mD);
+  const float S = fmaxf(fmaxf(sE, sN), sD);
+  dir = 0; smax = 0.f;
+  if (!(S > 0.f)) return;                       // flat: no positive slope
+  const bool eE = sE == S, eN = sN == S, eD = sD == S;
+  const float c = 0.99999905f;                  // 1 - 2^-20
+  const float lE = fminf(e1, e5), lN = fminf(e3, e7);
+  bool near = (eE && lE != mE && lE > mE * c) || (eN && lN != mN && lN > mN * c);
+  if (eD) {
+    const float t = mD * c;
+    near = near || (e2 != mD && e2 > t) || (e4 != mD && e4 > t) || (e6 != mD && e6 > t) || (e8 != mD && e8 > t);
+  }
+  if (near) {                                   // literal reference order, all eight products
+    const float zz[8] = {nb[1][i + 2], nb[0][i + 1], nb[1][i], nb[2][i + 1], nb[0][i + 2], nb[0][i], nb[2][i], nb[2][i + 2]};
+    d8_literal(z, zz, fE, fN, fD, dir, smax);
+    return;
+  }
+  smax = S;
+  if (eD && e8 == mD) dir = 8;                  // assigned in reverse scan order: the first in scan order wins
+  if (eD && e6 == mD) dir = 6;
+  if (eD && e4 == mD) dir = 4;
+  if (eD && e2 == mD) dir = 2;
+  if (eN && e7 == mN) dir = 7;
+  if (eE && e5 == mE) dir = 5;
+  if (eN && e3 == mN) dir = 3;
+  if (eE && e1 == mE) dir = 1;
+}
+
 __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ elev, short* __restrict__ dir,
                                                     float* __restrict__ slope, const double* __restrict__ dxc,
                                                     const double* __restrict__ dyc, Strip s, float nodata,
@@ -34,12 +84,19 @@ __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ el
   using G = TileGeom<float, TW, TH>;
   __shared__ __align__(128) float tile[G::ELEMS];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ double sfact[TH][3];               // 1/sqrt((d1 dx)^2 + (d2 dy)^2) per tile row: E/W, N/S, diagonal (src/d8.cpp:369-377)
   const int c0 = blockIdx.x * TW, r0 = 1 + blockIdx.y * TH;
-  load_tile_tma<float, TW, TH>(tile, &bar, elev, s, r0, c0);
+  if (threadIdx.x < TH && r0 + threadIdx.x <= s.ny) {
+    const double dx = dxc[r0 + threadIdx.x - 1], dy = dyc[r0 + threadIdx.x - 1];
+    sfact[threadIdx.x][0] = 1. / sqrt(dx * dx);
+    sfact[threadIdx.x][1] = 1. / sqrt(dy * dy);
+    sfact[threadIdx.x][2] = 1. / sqrt(dx * dx + dy * dy);
+  }
+  load_tile_tma<float, TW, TH>(tile, &bar, elev, s, r0, c0);   // contains the __syncthreads() that publishes sfact
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned myflat = 0;
-#pragma unroll
+#pragma unroll 1
   for (int pass = 0; pass < TH / 8; ++pass) {
     const int tr = warp + 8 * pass;
     const int r = r0 + tr, c = c0 + lane * 4;
@@ -52,31 +109,18 @@ __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ el
       const float4 v = *reinterpret_cast<const float4*>(p);
       nb[j][0] = p[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = p[4];
     }
-    const double dx = dxc[r - 1], dy = dyc[r - 1];
-    const double fE = 1. / sqrt(dx * dx), fN = 1. / sqrt(dy * dy), fD = 1. / sqrt(dx * dx + dy * dy);
-    bool ndv[3][6];
+    const double fE = sfact[tr][0], fN = sfact[tr][1], fD = sfact[tr][2];
+    // nodata per staged value, then per column, then per 3x3 window
+    bool colbad[6];
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-#pragma unroll
-      for (int i = 0; i < 6; ++i) ndv[j][i] = nd_f(nb[j][i], nodata);
-
+    for (int i = 0; i < 6; ++i) colbad[i] = nd_f(nb[0][i], nodata) || nd_f(nb[1][i], nodata) || nd_f(nb[2][i], nodata);
     short od[4]; float os[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int cc = c + i;
-      const float z = nb[1][i + 1];
-      bool bad = ndv[1][i + 1] || s.global_edge(r, cc) || cc >= s.nx;
-      bad = bad || ndv[0][i] || ndv[0][i + 1] || ndv[0][i + 2] || ndv[1][i] || ndv[1][i + 2] || ndv[2][i] ||
-            ndv[2][i + 1] || ndv[2][i + 2];
-      int d = 0; float smax = 0.f;
-      d8_try(z, nb[1][i + 2], fE, 1, smax, d);
-      d8_try(z, nb[0][i + 1], fN, 3, smax, d);
-      d8_try(z, nb[1][i], fE, 5, smax, d);
-      d8_try(z, nb[2][i + 1], fN, 7, smax, d);
-      d8_try(z, nb[0][i + 2], fD, 2, smax, d);
-      d8_try(z, nb[0][i], fD, 4, smax, d);
-      d8_try(z, nb[2][i], fD, 6, smax, d);
-      d8_try(z, nb[2][i + 2], fD, 8, smax, d);
+      const bool bad = colbad[i] || colbad[i + 1] || colbad[i + 2] || s.global_edge(r, cc) || cc >= s.nx;
+      int d; float smax;
+      d8_cell(nb, i, fE, fN, fD, d, smax);
       od[i] = bad ? TD_MISSINGSHORT : (short)d;
       os[i] = bad ? -1.0f : smax;
       if (!bad && d == 0) ++myflat;

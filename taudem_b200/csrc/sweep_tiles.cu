@@ -24,8 +24,9 @@
 namespace td {
 namespace {
 
-constexpr int TWX = 64, TWY = 32, TC = TWX * TWY;   // tile
-constexpr int RW = TWX + 2, RH = TWY + 2;           // ring
+constexpr int TWX = 64;                              // tile width; the height is a kernel template parameter
+constexpr int RW = TWX + 2;                          // ring width
+constexpr int TH_D8 = 32, TH_DINF = 16;              // D-infinity keeps two doubles per ring cell: smaller tiles, more CTAs per SM
 constexpr int EXTCAP = 512;
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 
@@ -41,7 +42,7 @@ struct SweepArgs {
   const double* theta;
   const double* dxc;
   int* halo;
-  int ntx, nty;
+  int ntx, nty, th;        // tiles across / down, tile height
   int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
   unsigned char* visited;  // per tile: area interior has been written at least once
   int* tq;                 // ring of tile ids + 1
@@ -100,8 +101,9 @@ __global__ void k_sched_init(int* state, unsigned char* visited, int* tq, unsign
   if (i == 0) { ctr[0] = 0; ctr[1] = (unsigned long long)ntiles; ctr[2] = (unsigned long long)ntiles; ctr[3] = 0; ctr[4] = ctr[5] = ctr[6] = ctr[7] = ctr[8] = 0; }
 }
 
-template <bool DINF>
+template <bool DINF, int TWY>
 __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
+  constexpr int TC = TWX * TWY, RH = TWY + 2, NWD = TC / 4 / 256;   // cells, ring rows, count words per thread
   // dynamic shared memory carve-up (doubles first)
   extern __shared__ __align__(16) unsigned char dsm[];
   double* sp1 = reinterpret_cast<double*>(dsm);                       // DINF: share of flow to sk1 / sk2 per ring cell
@@ -130,9 +132,9 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
     const int c0 = tx * TWX, r0 = 1 + ty * TWY;
 
     // ---- 1. dependency counts (4 cells per word, 2 words per thread), before anything else
-    unsigned g0[2];
+    unsigned g0[NWD];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < NWD; ++j) {
       const int lb = 4 * (tid + 256 * j);
       const int lr = lb / TWX, lx = lb % TWX;
       const int r = r0 + lr, c = c0 + lx;
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
     // ---- 2. node words, areas (+ring), angles (+ring), weights
     const bool first = ldv(a.visited + t) == 0;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < NWD; ++j) {
       const int lb = 4 * (tid + 256 * j);
       const int lr = lb / TWX, lx = lb % TWX;
       const int r = r0 + lr, c = c0 + lx;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
       int nready = 0;
       unsigned ready = 0;
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < NWD; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int l = 4 * (tid + 256 * j) + i;
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
     __syncthreads();
     __threadfence();
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < NWD; ++j) {
       const int lb = 4 * (tid + 256 * j);
       const int lr = lb / TWX, lx = lb % TWX;
       const int r = r0 + lr, c = c0 + lx;
@@ -367,8 +369,9 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
   }
 }
 size_t smem_bytes(bool dinf, bool usew) {
-  return (dinf ? 2 * RH * RW * sizeof(double) : 0) + (RH * RW + (dinf ? RH * RW : 0) + (usew ? TC : 0)) * sizeof(float) + TC * sizeof(int) +
-         (TC + EXTCAP + TC) * sizeof(unsigned short) + 2 * RH * RW;
+  const size_t th = dinf ? TH_DINF : TH_D8, tc = TWX * th, ring = (th + 2) * RW;
+  return (dinf ? 2 * ring * sizeof(double) : 0) + (ring + (dinf ? ring : 0) + (usew ? tc : 0)) * sizeof(float) + tc * sizeof(int) +
+         (tc + EXTCAP + tc) * sizeof(unsigned short) + 2 * ring;
 }
 }  // namespace
 
@@ -390,7 +393,7 @@ __global__ void k_apply_halo(SweepArgs a, const int* __restrict__ dec_top, const
     if (!(a.node[ci] & NODE_VALID)) continue;
     const unsigned sh = (unsigned)(ci & 3) * 8u;
     const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - ((unsigned)d << sh));
-    if ((int)((old >> sh) & 0xffu) == d) sched_activate(a, ((r - 1) / TWY) * a.ntx + c / TWX);
+    if ((int)((old >> sh) & 0xffu) == d) sched_activate(a, ((r - 1) / a.th) * a.ntx + c / TWX);
   }
 }
 
@@ -398,7 +401,8 @@ __global__ void k_sched_reset(unsigned long long* ctr) { ctr[0] = ctr[1] = ctr[2
 
 int sweep_args(td_ctx* ctx, SweepArgs& a, const Strip& s) {
   a.s = s;
-  a.ntx = (s.nx + TWX - 1) / TWX; a.nty = (s.ny + TWY - 1) / TWY;
+  a.th = ctx->sweep_dinf ? TH_DINF : TH_D8;
+  a.ntx = (s.nx + TWX - 1) / TWX; a.nty = (s.ny + a.th - 1) / a.th;
   const long long nt = (long long)a.ntx * a.nty;
   if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
   unsigned qcap = 1u << 14;   // always far more slots than persistent CTAs holding tickets
@@ -454,18 +458,18 @@ int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* 
     TD_CUDA(cudaGetDevice(&dev));
     TD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (dinf) {
-      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true, true)));
-      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<true>, 256, smem_bytes(true, false)));
+      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<true, TH_DINF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(true, true)));
+      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<true, TH_DINF>, 256, smem_bytes(true, false)));
     } else {
-      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false, true)));
-      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<false>, 256, smem_bytes(false, false)));
+      TD_CUDA(cudaFuncSetAttribute(k_sweep_tiles<false, TH_D8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(false, true)));
+      TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sweep_tiles<false, TH_D8>, 256, smem_bytes(false, false)));
     }
     if (occ < 1) { set_error("sweep kernel does not fit on an SM"); return TD_ERR_CUDA; }
     grid = sms * occ;     // persistent: every CTA is resident, so queue waits cannot deadlock
   }
   const int g = (int)std::min<long long>(grid, nt);
-  if (dinf) k_sweep_tiles<true><<<g, 256, smem_bytes(true, usew != 0), st>>>(a);
-  else k_sweep_tiles<false><<<g, 256, smem_bytes(false, usew != 0), st>>>(a);
+  if (dinf) k_sweep_tiles<true, TH_DINF><<<g, 256, smem_bytes(true, usew != 0), st>>>(a);
+  else k_sweep_tiles<false, TH_D8><<<g, 256, smem_bytes(false, usew != 0), st>>>(a);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;
