@@ -27,6 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 T0 = time.time()
 METRIC = "Mcells/s for aread8+areadinf on synthetic fractal DEM"
 HURST, TILT, SEED = 0.8, 1.0, 1234
+# dram__bytes_read+write per cell of the tile sweeps from the round-1 ncu capture (profiles/r01_ncu_summary.md)
+NCU_TRAFFIC_PER_CELL = {"aread8_sweep": 70.3, "areadinf_sweep": 132.0, "aread8_deps": 8.1, "areadinf_deps": 10.2}
 ALG_BYTES = {"aread8_deps": 2 + 0, "aread8_sweep": 2 + 4, "areadinf_deps": 4 + 0, "areadinf_sweep": 4 + 4}
 KERNEL = {"aread8_deps": "k_deps_d8", "aread8_sweep": "k_sweep_d8", "areadinf_deps": "k_deps_dinf", "areadinf_sweep": "k_sweep_dinf"}
 
@@ -180,7 +182,7 @@ def ours(args):
     dom = max(part_ms, key=part_ms.get)
     achieved = ALG_BYTES[dom] * cells / (part_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": KERNEL[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "frac": round(achieved / peak, 5), "traffic": round(NCU_TRAFFIC_PER_CELL[dom] * cells), "traffic_source": "ncu --set full capture at 8192^2 scaled per cell (profiles/r01_ncu_summary.md)", "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": ALG_BYTES[dom], "ms_per_launch": round(part_ms[dom], 3),
                 "per_kernel_ms": {KERNEL[k]: round(v, 3) for k, v in part_ms.items()},
                 "per_kernel_frac": {KERNEL[k]: round(ALG_BYTES[k] * cells / (v * 1e-3) / 1e9 / peak, 5) for k, v in part_ms.items()}}

@@ -58,10 +58,12 @@ def main():
     ldx, ldy = s.rows(30.0), s.rows(20.0)
     ok = True
     ok &= same("fel", D.pitremove(strip_of(dem, torch.float32)), fel)
-    p_d, sd8_d, _ = D.d8_slopes(strip_of(fel, torch.float32), ldx, ldy)
+    p_d, sd8_d = D.d8flowdir(strip_of(fel, torch.float32), ldx, ldy)
     ok &= same("sd8", sd8_d, sd8)
-    a_d, slp_d, _ = D.dinf_slopes(strip_of(fel, torch.float32), ldx, ldy)
+    ok &= same("p (flats resolved)", p_d, p)
+    a_d, slp_d = D.dinfflowdir(strip_of(fel, torch.float32), ldx, ldy)
     ok &= same("slp", slp_d, slp)
+    ok &= same("ang (flats resolved)", a_d, ang)
     ok &= same("ad8", D.aread8(strip_of(p, torch.int16)), ad8)
     ok &= same("ad8 -wg -nc", D.aread8(strip_of(p, torch.int16), w=strip_of(w, torch.float32), contcheck=False), ad8w)
     ok &= same("sca", D.areadinf(strip_of(ang, torch.float32), ldx, ldy), sca)

@@ -152,6 +152,69 @@ class DistTools:
         self.share(fel)
         return self.T.dinf_slopes(self.s, fel, dxc, dyc, nodata)
 
+    # ---- flow directions incl. flats.  The Garbrecht-Martz BFS is run REPLICATED this round: the strips
+    # of fel and of the positive-slope directions are all-gathered, every rank resolves the flats of the
+    # whole grid with the single-strip kernels and keeps its own rows (bit-identical by construction;
+    # a BFS with one halo exchange per level is the planned replacement).
+    def gather_full(self, t):
+        """All-gather of the owned rows of a strip tensor -> full-grid strip tensor (halo rows unused)."""
+        from .device import DeviceStrip
+        parts = partition(self.s.total_ny, self.world)
+        maxny = max(n for _, n in parts)
+        mine = torch.zeros((maxny, self.s.pitch), dtype=t.dtype, device=t.device)
+        mine[:self.ny].copy_(t[1:self.ny + 1])
+        if self.world == 1:
+            bufs = [mine]
+        elif _staged():
+            hm = mine.cpu().view(torch.uint8)                      # bytes: neither gloo nor NCCL moves int16
+            hb = [torch.empty_like(hm) for _ in range(self.world)]
+            dist.all_gather(hb, hm)
+            bufs = [b.view(mine.dtype).to(t.device) for b in hb]
+        else:
+            flat = torch.empty((self.world,) + tuple(mine.shape), dtype=mine.dtype, device=t.device)
+            dist.all_gather_into_tensor(flat.view(torch.uint8), mine.view(torch.uint8))
+            bufs = [flat[r] for r in range(self.world)]
+        sf = DeviceStrip(self.s.nx, self.s.total_ny, device=t.device)
+        full = sf.empty(t.dtype)
+        for (row0, n), b in zip(parts, bufs):
+            full[1 + row0:1 + row0 + n].copy_(b[:n])
+        return sf, full
+
+    def _flats(self, fel, d, dxc, dyc, nflat, dinf):
+        total = all_reduce_scalar(int(nflat), device=self.s.device) if self.world > 1 else int(nflat)
+        if total == 0:
+            return 0
+        sf, fel_full = self.gather_full(fel)
+        _, d_full = self.gather_full(d)
+        # per-row cell sizes of the whole grid
+        rows = torch.zeros(2, max(n for _, n in partition(self.s.total_ny, self.world)), dtype=torch.float64, device=self.s.device)
+        rows[0, :self.ny] = dxc; rows[1, :self.ny] = dyc
+        if self.world > 1:
+            allr = [torch.empty_like(rows) for _ in range(self.world)] if not _staged() else None
+            if _staged():
+                hb = [torch.empty(rows.shape, dtype=rows.dtype) for _ in range(self.world)]
+                dist.all_gather(hb, rows.cpu()); allr = [b.to(self.s.device) for b in hb]
+            else:
+                dist.all_gather(allr, rows)
+        else:
+            allr = [rows]
+        parts = partition(self.s.total_ny, self.world)
+        dxf = torch.cat([a[0, :n] for a, (_, n) in zip(allr, parts)]).contiguous()
+        dyf = torch.cat([a[1, :n] for a, (_, n) in zip(allr, parts)]).contiguous()
+        left = (self.T.dinf_flats if dinf else self.T.d8_flats)(sf, fel_full, d_full, dxf, dyf)
+        d[1:self.ny + 1].copy_(d_full[1 + self.row0:1 + self.row0 + self.ny])
+        return left
+
+    def d8flowdir(self, fel, dxc, dyc, nodata=-3.0e38):
+        p, sd8, nflat = self.d8_slopes(fel, dxc, dyc, nodata)
+        self._flats(fel, p, dxc, dyc, nflat, dinf=False)
+        return p, sd8
+
+    def dinfflowdir(self, fel, dxc, dyc, nodata=-3.0e38):
+        ang, slp, nflat = self.dinf_slopes(fel, dxc, dyc, nodata)
+        self._flats(fel, ang, dxc, dyc, nflat, dinf=True)
+        return ang, slp
+
     def pitremove(self, dem, nodata=-9999.0, four_way=False):
         """flood(): local relaxation to convergence, halo exchange, repeat until no strip changes
         (src/flood.cpp:344-479 share()/ringTerm() structure)."""
@@ -177,23 +240,25 @@ def bench_main(args, rank, world, local):
 
     import bench as B
     import taudem_b200 as td
-    from .device import Tools
-
     dev = torch.device("cuda", local)
     n = B.pick_size(torch, args.size)
     cells = n * n
     log = lambda *a: rank == 0 and print("[bench %.1fs]" % (time.time() - B.T0), *a, file=sys.stderr, flush=True)
-    # inputs: every rank prepares the full rasters with the single-strip tools (untimed; the distributed
-    # flat resolution is not implemented yet) and keeps its own strip
-    T0 = Tools()
-    s_full, dxc_f, dyc_f, p_full, ang_full, info = B.build_inputs(T0, n, torch)
+    # inputs (untimed): the distributed pipeline itself — generated DEM strip -> pitremove -> d8flowdir /
+    # dinfflowdir over the row strips (flat resolution replicated after an all-gather, see DistTools._flats)
+    t_setup = time.time()
     D = DistTools(n, n, rank, world, device=dev)
     s = D.s
-    p = s.empty(torch.int16); ang = s.empty(torch.float32)
-    p[1:s.ny + 1].copy_(p_full[1 + D.row0:1 + D.row0 + s.ny]); ang[1:s.ny + 1].copy_(ang_full[1 + D.row0:1 + D.row0 + s.ny])
-    del p_full, ang_full
-    T0.close(); torch.cuda.empty_cache()
     dxc, dyc = s.rows(30.0), s.rows(30.0)
+    dem = D.T.gen_dem(s, seed=B.SEED, hurst=B.HURST, tilt=B.TILT)
+    fel = D.pitremove(dem)
+    del dem
+    p, sd8 = D.d8flowdir(fel, dxc, dyc)
+    del sd8
+    ang, slp = D.dinfflowdir(fel, dxc, dyc)
+    del slp, fel
+    torch.cuda.synchronize(); torch.cuda.empty_cache()
+    info = {"setup_s": round(time.time() - t_setup, 2)}
     ad8, sca = s.empty(torch.float32), s.empty(torch.float32)
     log("inputs ready", info)
 

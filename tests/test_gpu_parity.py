@@ -161,4 +161,4 @@ def test_row_strip_partition_matches_single_strip(world):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(root, "scripts", "dist_check.py"), "1001", "1300"],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and "DIFFERENT" not in r.stdout and r.stdout.count("identical") == 7, r.stdout[-3000:]
+    assert r.returncode == 0 and "DIFFERENT" not in r.stdout and r.stdout.count("identical") == 9, r.stdout[-3000:]
