@@ -162,3 +162,59 @@ def test_row_strip_partition_matches_single_strip(world):
                         "--master-port", str(port), os.path.join(root, "scripts", "dist_check.py"), "1001", "1300"],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "DIFFERENT" not in r.stdout and r.stdout.count("identical") == 9, r.stdout[-3000:]
+
+
+def test_edge_shapes_against_c_restatement():
+    """Degenerate and awkward shapes, checked against the pinned C restatement (oracle/port): a single
+    row / column (everything is edge), 2-row and 3-row grids, widths that are not multiples of the
+    vector width or of the tile size, an all-nodata grid, a grid whose border is nodata, a constant grid."""
+    import port
+    if not port.available():
+        pytest.skip("oracle/port not built")
+    rng = np.random.default_rng(4)
+    shapes = [(1, 9), (9, 1), (2, 5), (3, 3), (3, 70), (33, 65), (64, 129), (31, 257)]
+    grids = [(rng.random(s) * 50).astype(np.float32) for s in shapes]
+    ring = (rng.random((40, 37)) * 30).astype(np.float32); ring[0, :] = ring[-1, :] = ring[:, 0] = ring[:, -1] = -9999.0
+    grids += [np.full((12, 19), -9999.0, np.float32), ring, np.full((20, 21), 7.0, np.float32)]
+    for dem in grids:
+        w = rng.random(dem.shape).astype(np.float32)
+        fel = td.pitremove_grid(dem)
+        assert_bits(fel, port.pitremove(dem), f"fel {dem.shape}")
+        p, sd8 = td.d8flowdir_grid(fel, dx=10.0, dy=12.0)
+        p_o, sd8_o = port.d8flowdir(fel, dx=10.0, dy=12.0)
+        assert_bits(p, p_o, f"p {dem.shape}"); assert_bits(sd8, sd8_o, f"sd8 {dem.shape}")
+        ang, slp = td.dinfflowdir_grid(fel, dx=10.0, dy=12.0)
+        ang_o, slp_o = port.dinfflowdir(fel, dx=10.0, dy=12.0)
+        assert_bits(slp, slp_o, f"slp {dem.shape}"); assert_float_parity(ang, ang_o, f"ang {dem.shape}")
+        assert_bits(td.aread8_grid(p_o, weights=w), port.aread8(p_o, weights=w), f"ad8 {dem.shape}")
+        assert_float_parity(td.areadinf_grid(ang_o, dx=10.0, dy=12.0), port.areadinf(ang_o, dx=10.0, dy=12.0), f"sca {dem.shape}")
+
+
+def test_odd_direction_codes_and_nodata_weights():
+    """aread8 quirks of the reference that a real p raster can contain: unresolved
+    flats (0), out-of-range codes, a nodata value other than -32768, nodata weights."""
+    import port
+    if not port.available():
+        pytest.skip("oracle/port not built")
+    rng = np.random.default_rng(8)
+    p = rng.integers(-3, 13, size=(70, 90)).astype(np.int16)
+    p[rng.random(p.shape) < 0.05] = -1
+    w = rng.random(p.shape).astype(np.float32); w[rng.random(p.shape) < 0.1] = -5.0
+    for cont in (True, False):
+        assert_bits(td.aread8_grid(p, nodata=-1, weights=w, w_nodata=-5.0, contcheck=cont),
+                    port.aread8(p, nodata=-1, weights=w, w_nodata=-5.0, contcheck=cont), f"ad8 contcheck={cont}")
+
+
+def test_large_vs_c_restatement():
+    """1500 x 1100 hills DEM end to end against the C restatement (seconds on one CPU core)."""
+    import port
+    if not port.available():
+        pytest.skip("oracle/port not built")
+    dem = synth.punch_holes(synth.gen_dem(1100, 1500, hurst=0.8, tilt=1.0, seed=31))
+    fel = td.pitremove_grid(dem); assert_bits(fel, port.pitremove(dem), "fel")
+    p, sd8 = td.d8flowdir_grid(fel); p_o, sd8_o = port.d8flowdir(fel)
+    assert_bits(p, p_o, "p"); assert_bits(sd8, sd8_o, "sd8")
+    assert_bits(td.aread8_grid(p), port.aread8(p_o), "ad8")
+    ang, slp = td.dinfflowdir_grid(fel); ang_o, slp_o = port.dinfflowdir(fel)
+    assert_bits(slp, slp_o, "slp"); assert_float_parity(ang, ang_o, "ang")
+    assert_float_parity(td.areadinf_grid(ang_o), port.areadinf(ang_o), "sca")
