@@ -27,13 +27,15 @@ __device__ __forceinline__ void d8_try(float z, float zn, double f, int k, float
   if (sl > smax) { smax = sl; dir = k; }
 }
 
-// zz = neighbours in scan order 1,3,5,7,2,4,6,8 (rare path, kept out of line)
-__device__ __noinline__ void d8_literal(float z, const float* zz, double fE, double fN, double fD, int& dir, float& smax) {
-  dir = 0; smax = 0.f;
-  d8_try(z, zz[0], fE, 1, smax, dir); d8_try(z, zz[1], fN, 3, smax, dir);
-  d8_try(z, zz[2], fE, 5, smax, dir); d8_try(z, zz[3], fN, 7, smax, dir);
-  d8_try(z, zz[4], fD, 2, smax, dir); d8_try(z, zz[5], fD, 4, smax, dir);
-  d8_try(z, zz[6], fD, 6, smax, dir); d8_try(z, zz[7], fD, 8, smax, dir);
+// Literal reference order with all eight products (rare path, out of line; q = centre cell in the staged tile)
+__device__ __noinline__ void d8_literal(const float* q, int sw, double fE, double fN, double fD, int* dir, float* smax) {
+  const float z = q[0];
+  int d = 0; float sm = 0.f;
+  d8_try(z, q[1], fE, 1, sm, d); d8_try(z, q[-sw], fN, 3, sm, d);
+  d8_try(z, q[-1], fE, 5, sm, d); d8_try(z, q[sw], fN, 7, sm, d);
+  d8_try(z, q[-sw + 1], fD, 2, sm, d); d8_try(z, q[-sw - 1], fD, 4, sm, d);
+  d8_try(z, q[sw - 1], fD, 6, sm, d); d8_try(z, q[sw + 1], fD, 8, sm, d);
+  *dir = d; *smax = sm;
 }
 
 // One cell.  nbr = the 3x3 neighbourhood (row above / centre / below, columns i..i+2 of nb).
@@ -44,37 +46,32 @@ __device__ __noinline__ void d8_literal(float z, const float* zz, double fE, dou
 // first k in scan order whose group slope equals the maximum and whose drop equals the group's
 // largest drop.  Two different drops can round to the same slope only when they are within an ulp or
 // two of each other; any such near-tie (relative gap < 2^-20) takes the literal eight-product path.
-__device__ __forceinline__ void d8_cell(const float (&nb)[3][6], int i, double fE, double fN, double fD, int& dir, float& smax) {
+__device__ __forceinline__ bool d8_cell(const float (&nb)[3][6], int i, double fE, double fN, double fD, int& dir, float& smax) {
   const float z = nb[1][i + 1];
   const float e1 = z - nb[1][i + 2], e5 = z - nb[1][i], e3 = z - nb[0][i + 1], e7 = z - nb[2][i + 1];
   const float e2 = z - nb[0][i + 2], e4 = z - nb[0][i], e6 = z - nb[2][i], e8 = z - nb[2][i + 2];
-  const float mE = fmaxf(e1, e5), mN = fmaxf(e3, e7), mD = fmaxf(fmaxf(e2, e4), fmaxf(e6, e8));
-  const float sE = (float)(fE * (double)mE), sN = (float)(fN * (double)mN), sD = (float)(fD * (double)mD);
+  const float m15 = fmaxf(e1, e5), m37 = fmaxf(e3, e7), m24 = fmaxf(e2, e4), m68 = fmaxf(e6, e8), mD = fmaxf(m24, m68);
+  const float sE = (float)(fE * (double)m15), sN = (float)(fN * (double)m37), sD = (float)(fD * (double)mD);
   const float S = fmaxf(fmaxf(sE, sN), sD);
-  dir = 0; smax = 0.f;
-  if (!(S > 0.f)) return;                       // flat: no positive slope
-  const bool eE = sE == S, eN = sN == S, eD = sD == S;
-  const float c = 0.99999905f;                  // 1 - 2^-20
+  // candidate of each group = its first member (scan order 1,3,5,7,2,4,6,8) with the largest drop,
+  // coded as (scan position << 4) | k so that an integer minimum picks the earliest one
+  int cE = (e1 >= e5) ? 0x01 : 0x25;
+  int cN = (e3 >= e7) ? 0x13 : 0x37;
+  const int c24 = (e2 >= e4) ? 0x42 : 0x54, c68 = (e6 >= e8) ? 0x66 : 0x78;
+  int cD = (m24 >= m68) ? c24 : c68;
+  cE = (sE == S) ? cE : 0xff; cN = (sN == S) ? cN : 0xff; cD = (sD == S) ? cD : 0xff;
+  const int best = min(cE, min(cN, cD));
+  const bool pos = S > 0.f;
+  dir = pos ? (best & 15) : 0;
+  smax = pos ? S : 0.f;
+  // a drop within 2^-20 (relative) below its group's largest drop could round to the same slope and, if it
+  // comes earlier in the scan, win: such cells (rare) take the literal path.  Bitwise logic: no branches.
+  const float c = 0.99999905f;
+  const float tE = m15 * c, tN = m37 * c, tD = mD * c;
   const float lE = fminf(e1, e5), lN = fminf(e3, e7);
-  bool near = (eE && lE != mE && lE > mE * c) || (eN && lN != mN && lN > mN * c);
-  if (eD) {
-    const float t = mD * c;
-    near = near || (e2 != mD && e2 > t) || (e4 != mD && e4 > t) || (e6 != mD && e6 > t) || (e8 != mD && e8 > t);
-  }
-  if (near) {                                   // literal reference order, all eight products
-    const float zz[8] = {nb[1][i + 2], nb[0][i + 1], nb[1][i], nb[2][i + 1], nb[0][i + 2], nb[0][i], nb[2][i], nb[2][i + 2]};
-    d8_literal(z, zz, fE, fN, fD, dir, smax);
-    return;
-  }
-  smax = S;
-  if (eD && e8 == mD) dir = 8;                  // assigned in reverse scan order: the first in scan order wins
-  if (eD && e6 == mD) dir = 6;
-  if (eD && e4 == mD) dir = 4;
-  if (eD && e2 == mD) dir = 2;
-  if (eN && e7 == mN) dir = 7;
-  if (eE && e5 == mE) dir = 5;
-  if (eN && e3 == mN) dir = 3;
-  if (eE && e1 == mE) dir = 1;
+  const bool near = pos & (((lE < m15) & (lE > tE)) | ((lN < m37) & (lN > tN)) | ((e2 < mD) & (e2 > tD)) | ((e4 < mD) & (e4 > tD)) |
+                           ((e6 < mD) & (e6 > tD)) | ((e8 < mD) & (e8 > tD)));
+  return near;
 }
 
 __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ elev, short* __restrict__ dir,
@@ -120,7 +117,7 @@ __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ el
       const int cc = c + i;
       const bool bad = colbad[i] || colbad[i + 1] || colbad[i + 2] || s.global_edge(r, cc) || cc >= s.nx;
       int d; float smax;
-      d8_cell(nb, i, fE, fN, fD, d, smax);
+      if (d8_cell(nb, i, fE, fN, fD, d, smax)) d8_literal(pm + G::SW + i, G::SW, fE, fN, fD, &d, &smax);
       od[i] = bad ? TD_MISSINGSHORT : (short)d;
       os[i] = bad ? -1.0f : smax;
       if (!bad && d == 0) ++myflat;
