@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_deps_d8(const short* __restrict__ p, un
   const int c0 = blockIdx.x * TW, r0 = 1 + blockIdx.y * TH;
   load_tile_tma<short, TW, TH>(tile, &bar, p, s, r0, c0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
+#pragma unroll 1
   for (int pass = 0; pass < TH / 8; ++pass) {
     const int tr = warp + 8 * pass;
     const int r = r0 + tr, c = c0 + lane * 4;
@@ -49,21 +49,26 @@ __global__ void __launch_bounds__(256) k_deps_d8(const short* __restrict__ p, un
       const short4 v = *reinterpret_cast<const short4*>(q);
       nb[j][0] = q[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = q[4];
     }
+    // branch-free: isNodata of an int16 raster is plain equality (|v - nd| < 1e-5 on integers),
+    // on-grid flags per neighbour row / column instead of eight Strip::on_grid() calls
+    const bool rowok[3] = {s.on_grid(r - 1, 0), true, s.on_grid(r + 1, 0)};
     unsigned short on4[4]; unsigned char oc4[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int cc = c + i;
-      const short d = nb[1][i + 1];
-      const bool valid = cc < s.nx && !nd_s(d, nodata) && d >= 0 && d <= 8;
-      unsigned mask = 0; bool con = false;
+      const int d = nb[1][i + 1];
+      const bool colok[3] = {cc - 1 >= 0, true, cc + 1 < s.nx};
+      const bool valid = (cc < s.nx) & (d != (int)nodata) & ((unsigned)d <= 8u);
+      unsigned mask = 0, con = 0;
 #pragma unroll
       for (int k = 1; k <= 8; ++k) {
-        const short dn = nb[1 + drow(k)][i + 1 + dcol(k)];
-        if (!s.on_grid(r + drow(k), cc + dcol(k)) || nd_s(dn, nodata)) con = true;
-        else if (dn - k == 4 || dn - k == -4) {
-          if (dn >= 0 && dn <= 8) mask |= 1u << (k - 1);
-          else con = true;   // counted by the evaluation loop but never evaluated -> nodata area
-        }
+        const int dn = nb[1 + drow(k)][i + 1 + dcol(k)];
+        const unsigned miss = (unsigned)(!(rowok[1 + drow(k)] & colok[1 + dcol(k)]) | (dn == (int)nodata));   // off-grid or nodata
+        const unsigned toward = (unsigned)((dn - k == 4) | (dn - k == -4));                                    // drains into this cell
+        const unsigned inrange = (unsigned)((unsigned)dn <= 8u);
+        mask |= ((~miss & 1u) & toward & inrange) << (k - 1);
+        // counted by the evaluation loop but never evaluated (code outside 0..8) -> its area stays nodata
+        con |= miss | (toward & (inrange ^ 1u));
       }
       on4[i] = valid ? (unsigned short)(NODE_VALID | (con ? NODE_CON : 0u) | ((unsigned)d << 8) | mask) : (unsigned short)0;
       oc4[i] = valid ? (unsigned char)__popc(mask) : (unsigned char)0xff;

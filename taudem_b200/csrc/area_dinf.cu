@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
+#pragma unroll 1
   for (int pass = 0; pass < TH / 8; ++pass) {
     const int tr = warp + 8 * pass;
     const int r = r0 + tr, c = c0 + lane * 4;
