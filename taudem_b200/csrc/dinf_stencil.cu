@@ -6,7 +6,9 @@
 // evaluated in double precision exactly as VSLOPE does; the first facet with the
 // strictly largest slope wins; angle = (float)(ANGC*PI/2 + ANGF*A), slope = (float)Smax;
 // no facet with S > 0 -> angle -1 (flat), slope 0.
-// A facet whose E1 and E2 are both >= E0 cannot produce S > 0 and is skipped.
+// The eight facets are first ranked with a float copy of the same formula; only the facets within 1e-3
+// of the best approximate slope (1-2 in practice) are evaluated in FP64, in increasing K with the
+// reference's strict '>' — the exact winner is always among them.
 // HBM traffic per cell: read fel 4 B, write ang 4 B + slp 4 B = 12 B (algorithmic);
 // the kernel is FP64-issue bound (4 + 8 divisions, up to 8 square roots per cell).
 #include "dinf_common.cuh"
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(256) k_dinf_stencil(const float* __restrict__ 
     const double dx = dxc[r - 1], dy = dyc[r - 1];
     const double DD = sqrt(dx * dx + dy * dy);
     const double adA = thA[r - 1], adB = thB[r - 1];   // atan2(dy,dx), atan2(dx,dy)
+    const float dxf = (float)dx, dyf = (float)dy, rdx = 1.0f / dxf, rdy = 1.0f / dyf, rdd = 1.0f / (float)DD;
     float oa[4], os[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -51,16 +54,34 @@ __global__ void __launch_bounds__(256) k_dinf_stencil(const float* __restrict__ 
       bool bad = nd_f(z, nodata) || s.global_edge(r, cc) || cc >= s.nx;
 #pragma unroll
       for (int k = 1; k <= 8; ++k) bad = bad || nd_f(nb[1 + drow(k)][i + 1 + dcol(k)], nodata);
-      double SMAX = 0.; int KD = 0; Facet best; best.S = 0.; best.S1 = best.S2 = 0.; best.code = 0;
-      if (!bad) {
-        const double E0 = (double)z;
+      // float pre-screen of the eight facets (same three-branch formula as VSLOPE, ~1e-6 relative): only the
+      // facets within 1e-3 of the best approximate slope can be the exact winner and get the FP64 treatment
+      float st[8], smaxf = 0.f;
 #pragma unroll
-        for (int K = 1; K <= 8; ++K) {
-          const float e1 = nb[1 + fI1(K)][i + 1 + fJ1(K)], e2 = nb[1 + fI2(K)][i + 1 + fJ2(K)];
-          if (!(e1 < z || e2 < z)) continue;   // S <= 0 for this facet, cannot win
-          const Facet f = vslope_dev(E0, (double)e1, (double)e2, fD1isDx(K) ? dx : dy, fD1isDx(K) ? dy : dx, DD);
-          if (f.S > SMAX) { SMAX = f.S; KD = K; best = f; }
-        }
+      for (int K = 1; K <= 8; ++K) {
+        const float e1 = nb[1 + fI1(K)][i + 1 + fJ1(K)], e2 = nb[1 + fI2(K)][i + 1 + fJ2(K)];
+        const float r1 = fD1isDx(K) ? rdx : rdy, r2 = fD1isDx(K) ? rdy : rdx;
+        const float d1f = fD1isDx(K) ? dxf : dyf, d2f = fD1isDx(K) ? dyf : dxf;
+        const float s1 = (z - e1) * r1, s2 = (e1 - e2) * r2;
+        const bool clip = (s1 <= 0.f) ? !(s1 == 0.f && s2 == 0.f) : (s2 * d1f > s1 * d2f);
+        const float S = (s2 < 0.f) ? s1 : (clip ? (z - e2) * rdd : sqrtf(s1 * s1 + s2 * s2));
+        st[K - 1] = S;
+        smaxf = fmaxf(smaxf, S);
+      }
+      unsigned cand = 0;
+      const float thr = smaxf * 0.999f;
+#pragma unroll
+      for (int K = 1; K <= 8; ++K) cand |= (st[K - 1] >= thr && st[K - 1] > 0.f) ? (1u << (K - 1)) : 0u;
+      if (bad) cand = 0;
+      double SMAX = 0.; int KD = 0; Facet best; best.S = 0.; best.S1 = best.S2 = 0.; best.code = 0;
+      const float* q0 = pm + G::SW + i;          // centre cell in the staged tile
+      const double E0 = (double)z;
+      for (unsigned m = cand; m; m &= m - 1) {     // increasing K, strict '>' : first facet with the largest exact slope
+        const int K = __ffs(m);
+        const bool d1x = fD1isDx(K);
+        const float e1 = q0[fI1(K) * G::SW + fJ1(K)], e2 = q0[fI2(K) * G::SW + fJ2(K)];
+        const Facet f = vslope_dev(E0, (double)e1, (double)e2, d1x ? dx : dy, d1x ? dy : dx, DD);
+        if (f.S > SMAX) { SMAX = f.S; KD = K; best = f; }
       }
       float a = -1.0f;
       if (KD > 0) a = dinf_angle(KD, facet_angle(best, fD1isDx(KD) ? adA : adB));
