@@ -30,7 +30,7 @@ HURST, TILT, SEED = 0.8, 1.0, 1234
 # dram__bytes_read+write per cell of the tile sweeps from the round-1 ncu capture (profiles/r01_ncu_summary.md)
 NCU_TRAFFIC_PER_CELL = {"aread8_sweep": 70.3, "areadinf_sweep": 132.0, "aread8_deps": 8.1, "areadinf_deps": 10.2}
 ALG_BYTES = {"aread8_deps": 2 + 0, "aread8_sweep": 2 + 4, "areadinf_deps": 4 + 0, "areadinf_sweep": 4 + 4}
-KERNEL = {"aread8_deps": "k_deps_d8", "aread8_sweep": "k_sweep_d8", "areadinf_deps": "k_deps_dinf", "areadinf_sweep": "k_sweep_dinf"}
+KERNEL = {"aread8_deps": "k_deps_d8", "aread8_sweep": "k_sweep_tiles<d8,64x32>", "areadinf_deps": "k_deps_dinf", "areadinf_sweep": "k_sweep_tiles<dinf,64x16>"}
 
 
 def peaks():
