@@ -145,7 +145,9 @@ int td_raster_write(const char* path, int dtype, const void* src, int nx, int ny
     geo.gt[0] = 0; geo.gt[1] = dx; geo.gt[2] = 0; geo.gt[3] = dy * ny; geo.gt[4] = 0; geo.gt[5] = -dy;
   }
   tdio::Writer w;
-  if (!w.create(path, nx, ny, (tdio::DType)dtype, nodata, geo, compression, &err) || !w.write_rows(0, ny, src, &err) || !w.close(&err)) {
+  const bool force_big = (compression & 0x100) != 0;     // bit 8: write BigTIFF regardless of size (tests)
+  compression &= 0xff;
+  if (!w.create(path, nx, ny, (tdio::DType)dtype, nodata, geo, compression, &err, force_big) || !w.write_rows(0, ny, src, &err) || !w.close(&err)) {
     td::set_error(err); return TD_ERR_IO;
   }
   return TD_OK;

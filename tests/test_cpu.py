@@ -71,6 +71,17 @@ def test_tiff_reads_pil_written_files(tmp_path):
         assert td.raster_info(f)["nodata"] == -9999.0 and not td.raster_info(f)["has_nodata"]   # tiffIO default
 
 
+def test_bigtiff_layout(tmp_path):
+    from PIL import Image
+    a = (np.random.default_rng(3).random((300, 257)) * 1000).astype(np.float32)
+    for comp in (1, 5):
+        f = str(tmp_path / f"big{comp}.tif")
+        td.write_raster(f, a, -1.0, compression=comp | 0x100)          # bit 8 forces the BigTIFF layout
+        assert open(f, 'rb').read(4) == b'II+\x00'
+        assert_bits(td.read_raster(f), a, 'bigtiff own reader')
+        assert np.array_equal(np.array(Image.open(f)), a), 'libtiff reads our BigTIFF'
+
+
 def test_bigtiff_and_geotags_passthrough(tmp_path):
     a = np.arange(50 * 40, dtype=np.float32).reshape(50, 40)
     f1, f2 = str(tmp_path / "a.tif"), str(tmp_path / "b.tif")
