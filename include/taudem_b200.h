@@ -171,6 +171,17 @@ int td_aread8_sweep_run_dev(td_ctx*, const float* w, float* ad8, td_strip s, flo
 int td_area_sweep_run_dev(td_ctx*, const float* ang, const float* w, float* sca, td_strip s, int usew,
                           int contcheck, const double* dxc, int* halo_out, void* stream);
 
+/* Peer mode (one process per GPU on one NVSwitch box): every rank exports the IPC handles of the buffers
+ * its neighbours write (counts, tile scheduler, halo areas, rank 0 also the global pending counter), opens
+ * its neighbours' (which: 0 = strip above, 1 = strip below, 2 = counter owner; NULL handles = none / self),
+ * then td_sweep_peer_begin_dev + a barrier + ONE td_*_sweep_run_dev per rank complete the whole sweep:
+ * tiles deliver into the neighbour GPU over NVLink (remote store + system-scope atomics) and queue its
+ * tiles directly.  td_sweep_peer_off_dev returns to the round-based mode.                                */
+int td_sweep_peer_export_dev(td_ctx*, td_strip s, int dinf, unsigned char* handles_5x64, int* meta_5, void* stream);
+int td_sweep_peer_connect_dev(td_ctx*, int which, const unsigned char* handles_5x64, const int* meta_5);
+int td_sweep_peer_begin_dev(td_ctx*, td_strip s, void* stream);
+void td_sweep_peer_off_dev(td_ctx*);
+
 #ifdef __cplusplus
 }
 #endif

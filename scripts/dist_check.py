@@ -49,6 +49,12 @@ def main():
     def same(name, mine, full):
         ok = torch.equal(mine[1:s.ny + 1, :nx].view(torch.int32 if mine.dtype == torch.float32 else mine.dtype),
                          full[rows, :nx].view(torch.int32 if full.dtype == torch.float32 else full.dtype))
+        if not ok:
+            a_ = mine[1:s.ny + 1, :nx]; b_ = full[rows, :nx]
+            bad = (a_ != b_)
+            idx = bad.nonzero()
+            print(f"   rank {rank}: {int(bad.sum())} cells differ; rows {int(idx[:,0].min())}..{int(idx[:,0].max())} of {s.ny}; "
+                  f"first {[(int(y), int(x), float(a_[y, x]), float(b_[y, x])) for y, x in idx[:4].tolist()]}", flush=True)
         from taudem_b200.dist import all_reduce_scalar
         flag = all_reduce_scalar(int(ok), op=dist.ReduceOp.MIN, device=s.device)
         if rank == 0:

@@ -67,6 +67,10 @@ SIGNATURES = {
     "td_sweep_begin_dev": (_I, [_P, Strip, _P]),
     "td_sweep_apply_halo_dev": (_I, [_P, Strip, _P, _P, _P]),
     "td_aread8_sweep_run_dev": (_I, [_P, _P, _P, Strip, _F, _I, _I, _P, _P]),
+    "td_sweep_peer_export_dev": (_I, [_P, Strip, _I, _P, _P, _P]),
+    "td_sweep_peer_connect_dev": (_I, [_P, _I, _P, _P]),
+    "td_sweep_peer_begin_dev": (_I, [_P, Strip, _P]),
+    "td_sweep_peer_off_dev": (None, [_P]),
     "td_area_sweep_run_dev": (_I, [_P, _P, _P, _P, Strip, _I, _I, _P, _P, _P]),
 }
 

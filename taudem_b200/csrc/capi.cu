@@ -271,6 +271,21 @@ int td_area_sweep_run_dev(td_ctx* ctx, const float* ang, const float* w, float* 
   return td::sweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
 }
 
+// ---- peer mode of the partitioned sweeps: neighbours' counts / tile queues / halo buffers mapped over
+// NVLink with CUDA IPC; the sweep kernel then delivers across GPUs itself and no exchange rounds exist.
+int td_sweep_peer_export_dev(td_ctx* ctx, td_strip s, int dinf, unsigned char* handles_5x64, int* meta_5, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::sweep_peer_export(ctx, Strip(s), dinf, handles_5x64, meta_5, (cudaStream_t)stream);
+}
+int td_sweep_peer_connect_dev(td_ctx* ctx, int which, const unsigned char* handles_5x64, const int* meta_5) {
+  return td::sweep_peer_connect(ctx, which, handles_5x64, meta_5);
+}
+int td_sweep_peer_begin_dev(td_ctx* ctx, td_strip s, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::sweep_peer_begin(ctx, Strip(s), (cudaStream_t)stream);
+}
+void td_sweep_peer_off_dev(td_ctx* ctx) { td::sweep_peer_off(ctx); }
+
 }  // extern "C"
 
 // ------------------------------------------------------------------ host-grid level

@@ -34,6 +34,13 @@ struct td_ctx {
   Buf theta;     // per-row atan2(dy,dx) | atan2(dx,dy) tables (doubles)
   Buf rows;      // per-row dxc | dyc (host-grid level calls)
   Buf io[4];     // raster strips of host-grid level calls
+  // peer mode of the sweeps (neighbour strips' buffers opened through CUDA IPC, see sweep_tiles.cu)
+  struct PeerInfo { void *cntw = nullptr, *tileflags = nullptr, *dctr = nullptr, *halo_in = nullptr; int qmask = 0, ntx = 0, ny = 0, th = 0, nt = 0, valid = 0; };
+  PeerInfo peer_up, peer_down;
+  void* peer_G = nullptr;                // global pending counter (rank 0's gbuf)
+  bool peer_G_opened = false;
+  Buf peer_halo, gbuf;
+  int peer_on = 0;
   int sweep_dinf = 0;                    // which dependency state node/cnt hold (tile height of the sweep)
   unsigned long long* d_ctr = nullptr;   // 32 device counters
   unsigned long long* h_ctr = nullptr;   // pinned host mirror

@@ -29,6 +29,10 @@ int sweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
 int sweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
 int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
+int sweep_peer_export(td_ctx* ctx, const Strip& s, int dinf, unsigned char* handles, int* meta, cudaStream_t st);
+int sweep_peer_connect(td_ctx* ctx, int which, const unsigned char* handles, const int* meta);
+int sweep_peer_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
+void sweep_peer_off(td_ctx* ctx);
 int fill_init(const float* dem, const short* mask, float* W, const Strip& s, float nodata, int four, cudaStream_t st);
 int fill_relax(td_ctx* ctx, const float* dem, float* W, const Strip& s, int four, int* changed, cudaStream_t st);
 cudaError_t launch_gen_dem(float* dem, const Strip& s, int row0, int total_ny, unsigned seed, float hurst, float tilt, cudaStream_t st);

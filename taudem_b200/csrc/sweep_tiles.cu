@@ -18,6 +18,8 @@
 //  * the kernel ends when no tile is queued or running.
 // Flow that crosses the strip boundary is recorded in ctx.halo for the neighbour strip
 // (src/aread8.cpp:282-297).
+#include <string.h>
+
 #include "ctx.h"
 #include "dinf_common.cuh"
 
@@ -29,6 +31,12 @@ constexpr int RW = TWX + 2;                          // ring width
 constexpr int TH_D8 = 32, TH_DINF = 16;              // D-infinity keeps two doubles per ring cell: smaller tiles, more CTAs per SM
 constexpr int EXTCAP = 512;
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
+
+// what a neighbouring strip exposes to this GPU (device pointers into the peer's memory)
+struct PeerStrip {
+  unsigned* cntw; int* state; int* tq; unsigned long long* ctr; float* halo_in;
+  unsigned qmask; int ntx, ny, th, valid;
+};
 
 struct SweepArgs {
   const unsigned short* node;
@@ -48,50 +56,100 @@ struct SweepArgs {
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;
   unsigned long long* ctr; // [0] head, [1] tail, [2] pending (queued + running tiles)
+  // peer mode (one strip per GPU, neighbours' buffers mapped over NVLink): no exchange rounds, a tile
+  // delivers into the neighbour GPU exactly as it delivers into a neighbour tile
+  int peer;
+  PeerStrip up, down;      // the strip above (rank-1) / below (rank+1)
+  unsigned long long* G;   // queued + running tiles of ALL strips (lives on rank 0)
+  const float* halo_in;    // areas of the neighbours' edge cells: [0,pitch) row above, [pitch,2 pitch) row below
 };
 
 template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((const volatile T*)p); }
 
+// In peer mode a neighbour GPU operates on this strip's counts and scheduler words with system-scope
+// atomics; the owner then uses system scope on the same words too (atomics of different scopes on one
+// address are not guaranteed to be atomic with respect to each other).
+#define A_ADD(ptr, v) (a.peer ? atomicAdd_system((ptr), (v)) : atomicAdd((ptr), (v)))
+#define A_CAS(ptr, c, v) (a.peer ? atomicCAS_system((ptr), (c), (v)) : atomicCAS((ptr), (c), (v)))
+#define A_EXCH(ptr, v) (a.peer ? atomicExch_system((ptr), (v)) : atomicExch((ptr), (v)))
+#define A_FENCE() do { if (a.peer) __threadfence_system(); else __threadfence(); } while (0)
+
+__device__ __forceinline__ void pending_add(const SweepArgs& a, unsigned long long v) {
+  if (a.peer) atomicAdd_system(a.G, v); else atomicAdd(a.ctr + 2, v);
+}
+__device__ __forceinline__ long long pending_now(const SweepArgs& a) { return (long long)ldv(a.peer ? a.G : a.ctr + 2); }
+
 __device__ void sched_push(const SweepArgs& a, int t) {
-  atomicAdd(a.ctr + 2, 1ull);
-  const unsigned long long slot = atomicAdd(a.ctr + 1, 1ull);
+  pending_add(a, 1ull);
+  const unsigned long long slot = A_ADD(a.ctr + 1, 1ull);
   int* q = a.tq + (slot & a.qmask);
-  while (atomicCAS(q, 0, t + 1) != 0) {}
+  while (A_CAS(q, 0, t + 1) != 0) {}
 }
 
 __device__ void sched_activate(const SweepArgs& a, int t) {
   for (;;) {
     const int st = ldv(a.state + t);
     if (st == 1 || st == 3) return;
-    if (st == 0) { if (atomicCAS(a.state + t, 0, 1) == 0) { sched_push(a, t); return; } }
-    else if (atomicCAS(a.state + t, 2, 3) == 2) return;
+    if (st == 0) { if (A_CAS(a.state + t, 0, 1) == 0) { sched_push(a, t); return; } }
+    else if (A_CAS(a.state + t, 2, 3) == 2) return;
   }
+}
+
+// the same protocol on a neighbour GPU's scheduler (system-scope atomics over NVLink)
+__device__ void sched_activate_peer(const SweepArgs& a, const PeerStrip& P, int t) {
+  for (;;) {
+    const int st = ldv(P.state + t);
+    if (st == 1 || st == 3) return;
+    if (st == 0) {
+      if (atomicCAS_system(P.state + t, 0, 1) == 0) {
+        atomicAdd_system(a.G, 1ull);
+        const unsigned long long slot = atomicAdd_system(P.ctr + 1, 1ull);
+        int* q = P.tq + (slot & P.qmask);
+        while (atomicCAS_system(q, 0, t + 1) != 0) {}
+        return;
+      }
+    } else if (atomicCAS_system(P.state + t, 2, 3) == 2) return;
+  }
+}
+
+// Flow into the strip above (up = true) / below: the source cell's area goes into the neighbour's halo
+// buffer, is fenced system-wide, then the neighbour's count is decremented; zero -> queue its tile.
+__device__ void deliver_peer(const SweepArgs& a, bool up, int c_src, float val, int c_dst) {
+  const PeerStrip& P = up ? a.up : a.down;
+  const int pitch = a.s.pitch;
+  P.halo_in[(up ? pitch : 0) + c_src] = val;        // I am the row BELOW the strip above / the row ABOVE the strip below
+  __threadfence_system();
+  const int r = up ? P.ny : 1;
+  const long long ci = (long long)r * pitch + c_dst;
+  const unsigned sh = (unsigned)(ci & 3) * 8u;
+  const unsigned old = atomicAdd_system(P.cntw + (ci >> 2), 0u - (1u << sh));
+  if (((old >> sh) & 0xffu) == 1u) sched_activate_peer(a, P, ((r - 1) / P.th) * P.ntx + c_dst / TWX);
 }
 
 // Ticket queue: one fetch-and-add per pop (a CAS loop on the head collapses under the
 // contention of ~900 persistent CTAs).  Ticket h is served by the h-th push; a consumer whose
 // ticket is never served leaves when no tile is queued or running any more.
 __device__ int sched_pop(const SweepArgs& a) {
-  const unsigned long long h = atomicAdd(a.ctr, 1ull);
+  const unsigned long long h = A_ADD(a.ctr, 1ull);
   int* q = a.tq + (h & a.qmask);
   for (;;) {
     const int v = ldv(q);
     if (v != 0) {
-      atomicExch(q, 0);
-      atomicExch(a.state + (v - 1), 2);
+      A_EXCH(q, 0);
+      A_EXCH(a.state + (v - 1), 2);
       atomicAdd(a.ctr + 3, 1ull);          // statistics: tile visits
-      __threadfence();
+      if (a.peer) __threadfence_system(); else __threadfence();
       return v - 1;
     }
-    if ((long long)ldv(a.ctr + 2) <= 0) return -1;
+    if (pending_now(a) <= 0) return -1;
     __nanosleep(64);
   }
 }
 
 __device__ void sched_finish(const SweepArgs& a, int t) {
-  __threadfence();
-  if (atomicCAS(a.state + t, 2, 0) != 2) { atomicExch(a.state + t, 1); sched_push(a, t); }
-  atomicAdd(a.ctr + 2, ~0ull);   // pending -= 1
+  if (a.peer) __threadfence_system(); else __threadfence();
+  if (A_CAS(a.state + t, 2, 0) != 2) { A_EXCH(a.state + t, 1); sched_push(a, t); }
+  pending_add(a, ~0ull);   // pending -= 1
 }
 
 __global__ void k_sched_init(int* state, unsigned char* visited, int* tq, unsigned qcap, int ntiles, unsigned long long* ctr) {
@@ -144,7 +202,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const unsigned b = (word >> (8 * i)) & 0xffu; lc[lb + i] = b <= 8u ? (int)b : -1; }
     }
-    __threadfence();
+    A_FENCE();
     __syncthreads();
     // ---- 2. node words, areas (+ring), angles (+ring), weights
     const bool first = ldv(a.visited + t) == 0;
@@ -167,9 +225,12 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
       const int rr = i / RW, rc = i - rr * RW;
       const int r = r0 - 1 + rr, c = c0 - 1 + rc;
       const bool in = r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.nx;
-      const bool interior = rr >= 1 && rr <= TWY && rc >= 1 && rc <= TWX;
+      const bool interior = rr >= 1 && rr <= TWY && rc >= 1 && rc <= TWX && r <= s.ny;   // owned cell of this tile (a halo row can fall inside a partial tile)
       float v = -1.0f;
-      if (in && !(first && interior)) v = __ldcg(a.area + s.idx(r, c));
+      if (in && !(first && interior)) {
+        if (a.peer && (r == 0 || r == s.ny + 1)) v = __ldcg(a.halo_in + (r == 0 ? 0 : s.pitch) + c);
+        else v = __ldcg(a.area + s.idx(r, c));
+      }
       sarea[i] = v;
       if (DINF) sang[i] = in ? a.ang[s.idx(r, c)] : TD_MISSINGFLOAT;
     }
@@ -274,7 +335,8 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
                 const int l2 = nlr * TWX + nlx;
                 if (atomicSub(&lc[l2], 1) == 1) cont = l2;   // invalid / finished cells hold a negative count
               } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
-                ext[atomicAdd(&next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
+                if (a.peer && (r0 + nlr == 0 || r0 + nlr == s.ny + 1)) deliver_peer(a, r0 + nlr == 0, c0 + lx, val, c0 + nlx);
+                else ext[atomicAdd(&next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
               }
             }
           } else {
@@ -294,7 +356,8 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
                   }
                 }
               } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
-                ext[atomicAdd(&next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
+                if (a.peer && (r0 + nlr == 0 || r0 + nlr == s.ny + 1)) deliver_peer(a, r0 + nlr == 0, c0 + lx, val, c0 + nlx);
+                else ext[atomicAdd(&next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
               }
             }
           }
@@ -315,9 +378,9 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
       if (r <= s.ny && c < s.nx) a.area[s.idx(r, c)] = sarea[(lr + 1) * RW + lx + 1];
     }
     if (tid == 0) a.visited[t] = 1;
-    __threadfence();
+    A_FENCE();
     __syncthreads();
-    __threadfence();
+    A_FENCE();
 #pragma unroll
     for (int j = 0; j < NWD; ++j) {
       const int lb = 4 * (tid + 256 * j);
@@ -335,7 +398,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
         delta += (unsigned)ci << (8 * i);
       }
       if (delta != 0) {
-        const unsigned old = atomicAdd(a.cntw + (s.idx(r, c) >> 2), delta);
+        const unsigned old = A_ADD(a.cntw + (s.idx(r, c) >> 2), delta);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (dec[i] < 0 && (int)((old >> (8 * i)) & 0xffu) + dec[i] == 0) self_dirty = 1;   // became ready meanwhile
@@ -350,7 +413,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
       const long long ci = s.idx(r, c);
       if (!(a.node[ci] & NODE_VALID)) continue;
       const unsigned sh = (unsigned)(ci & 3) * 8u;
-      const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - (1u << sh));
+      const unsigned old = A_ADD(a.cntw + (ci >> 2), 0u - (1u << sh));
       if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TWY) * a.ntx + c / TWX);
     }
     __syncthreads();
@@ -443,6 +506,81 @@ int sweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int*
   return TD_OK;
 }
 
+namespace {
+__global__ void k_add_G(unsigned long long* G, unsigned long long v) { atomicAdd_system(G, v); __threadfence_system(); }
+}
+
+// ---- peer mode plumbing (CUDA IPC).  export: make sure every buffer a neighbour touches exists at its
+// final size and hand out its IPC handle; connect: open a neighbour's (or rank 0's counter) handles.
+int sweep_peer_export(td_ctx* ctx, const Strip& s, int dinf, unsigned char* handles, int* meta, cudaStream_t st) {
+  SweepArgs a;
+  ctx->sweep_dinf = dinf ? 1 : 0;    // tile geometry of the sweep that is about to run
+  const size_t n = (size_t)s.cells();
+  TD_CUDA(ctx->node.ensure(n * 2));
+  TD_CUDA(ctx->cnt.ensure((n + 3) / 4 * 4));
+  if (int rc = sweep_args(ctx, a, s)) return rc;
+  TD_CUDA(ctx->peer_halo.ensure(sizeof(float) * 2 * (size_t)s.pitch));
+  TD_CUDA(ctx->gbuf.ensure(64));
+  TD_CUDA(cudaMemsetAsync(ctx->gbuf.p, 0, 64, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  void* ptrs[5] = {ctx->cnt.p, ctx->tileflags.p, ctx->d_ctr, ctx->peer_halo.p, ctx->gbuf.p};
+  for (int i = 0; i < 5; ++i) {
+    cudaIpcMemHandle_t h;
+    TD_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
+    memcpy(handles + 64 * i, &h, 64);
+  }
+  meta[0] = (int)a.qmask; meta[1] = a.ntx; meta[2] = s.ny; meta[3] = a.th; meta[4] = a.ntx * a.nty;
+  return TD_OK;
+}
+
+static void close_peer(td_ctx::PeerInfo& pi) {
+  if (pi.cntw) cudaIpcCloseMemHandle(pi.cntw);
+  if (pi.tileflags) cudaIpcCloseMemHandle(pi.tileflags);
+  if (pi.dctr) cudaIpcCloseMemHandle(pi.dctr);
+  if (pi.halo_in) cudaIpcCloseMemHandle(pi.halo_in);
+  pi = td_ctx::PeerInfo();
+}
+
+// which: 0 = strip above, 1 = strip below, 2 = owner of the global counter (handles == NULL: this rank)
+int sweep_peer_connect(td_ctx* ctx, int which, const unsigned char* handles, const int* meta) {
+  auto open = [](const unsigned char* h64, void** out) -> cudaError_t {
+    cudaIpcMemHandle_t h; memcpy(&h, h64, 64);
+    return cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+  };
+  if (which == 2) {
+    if (ctx->peer_G_opened && ctx->peer_G) cudaIpcCloseMemHandle(ctx->peer_G);
+    ctx->peer_G_opened = false;
+    if (!handles) { ctx->peer_G = ctx->gbuf.p; return TD_OK; }
+    TD_CUDA(open(handles + 64 * 4, &ctx->peer_G));
+    ctx->peer_G_opened = true;
+    return TD_OK;
+  }
+  td_ctx::PeerInfo& pi = which == 0 ? ctx->peer_up : ctx->peer_down;
+  close_peer(pi);
+  if (!handles) return TD_OK;
+  TD_CUDA(open(handles, &pi.cntw));
+  TD_CUDA(open(handles + 64, &pi.tileflags));
+  TD_CUDA(open(handles + 128, &pi.dctr));
+  TD_CUDA(open(handles + 192, &pi.halo_in));
+  pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4]; pi.valid = 1;
+  return TD_OK;
+}
+
+// start of a peer-mode sweep: queue all tiles, announce them in the global counter.  The caller must put a
+// barrier between this call and sweep_run on every rank (nobody may see G == 0 before everybody announced).
+int sweep_peer_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
+  ctx->peer_on = 1;
+  if (int rc = sweep_begin(ctx, s, st)) return rc;
+  SweepArgs a;
+  if (int rc = sweep_args(ctx, a, s)) return rc;
+  TD_CUDA(cudaMemsetAsync(ctx->peer_halo.p, 0, sizeof(float) * 2 * (size_t)s.pitch, st));
+  k_add_G<<<1, 1, 0, st>>>((unsigned long long*)ctx->peer_G, (unsigned long long)a.ntx * a.nty);
+  TD_LAUNCHED();
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+void sweep_peer_off(td_ctx* ctx) { ctx->peer_on = 0; }
+
 // Runs the evaluation wavefront over the queued tiles until no tile of the strip has a ready cell left.
 int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
@@ -450,6 +588,18 @@ int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* 
   if (int rc = sweep_args(ctx, a, s)) return rc;
   a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
   a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+  a.peer = ctx->peer_on;
+  if (a.peer) {
+    auto fill = [](const td_ctx::PeerInfo& pi, PeerStrip& P) {
+      P.valid = pi.valid;
+      P.cntw = (unsigned*)pi.cntw; P.state = (int*)pi.tileflags; P.tq = P.state + pi.nt; P.ctr = (unsigned long long*)pi.dctr + 24;
+      P.halo_in = (float*)pi.halo_in; P.qmask = (unsigned)pi.qmask; P.ntx = pi.ntx; P.ny = pi.ny; P.th = pi.th;
+    };
+    fill(ctx->peer_up, a.up); fill(ctx->peer_down, a.down);
+    a.G = (unsigned long long*)ctx->peer_G;
+    a.halo_in = ctx->peer_halo.as<float>();
+    if ((s.has_top && !a.up.valid) || (s.has_bot && !a.down.valid) || !a.G) { set_error("peer mode: neighbours are not connected"); return TD_ERR_ARG; }
+  } else { a.G = nullptr; a.halo_in = nullptr; a.up.valid = a.down.valid = 0; }
   const long long nt = (long long)a.ntx * a.nty;
   static int grid_d8 = 0, grid_dinf = 0;
   int& grid = dinf ? grid_dinf : grid_d8;

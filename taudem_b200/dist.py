@@ -89,8 +89,15 @@ def exchange_counts(halo_out, pitch, rank, world, group=None):
 class DistTools:
     """The strip of this rank plus the exchange rounds around the device-strip level C ABI."""
 
-    def __init__(self, nx, total_ny, rank, world, device="cuda"):
+    def __init__(self, nx, total_ny, rank, world, device="cuda", peer=None):
+        import os
         from .device import DeviceStrip, Tools
+        # peer mode: sweeps deliver across GPUs inside the kernel (CUDA IPC + NVLink atomics), no exchange
+        # rounds.  Needs one GPU per rank and the NCCL backend; TAUDEM_B200_PEER=0/1 overrides.
+        if peer is None:
+            peer = os.environ.get("TAUDEM_B200_PEER", "0") == "1"
+        self.peer = bool(peer) and world > 1
+        self._peer_cache = None
         self.rank, self.world = rank, world
         self.row0, self.ny = partition(total_ny, world)[rank]
         self.s = DeviceStrip(nx, self.ny, has_top=rank > 0, has_bot=rank < world - 1, row0=self.row0, total_ny=total_ny, device=device)
@@ -104,7 +111,45 @@ class DistTools:
     def share(self, t):
         exchange_rows(t, self.ny, self.rank, self.world)
 
+    def _peer_setup(self, dinf):
+        """Exports this rank's IPC handles, gathers everybody's, opens the neighbours' (cached while unchanged)."""
+        import numpy as np
+        s = self.s
+        handles = np.zeros(320, np.uint8); meta = np.zeros(5, np.int32)
+        check(self.l.td_sweep_peer_export_dev(self.T.ctx, s.c, int(dinf), handles.ctypes.data_as(C.c_void_p), meta.ctypes.data_as(C.c_void_p), self._stream()))
+        mine = torch.from_numpy(np.concatenate([handles, meta.view(np.uint8)])).to(s.device)
+        allp = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allp, mine)
+        packs = [p.cpu().numpy() for p in allp]
+        key = b"".join(p.tobytes() for p in packs)
+        if key == self._peer_cache:
+            return
+        def conn(which, r):
+            if r is None:
+                check(self.l.td_sweep_peer_connect_dev(self.T.ctx, which, None, None))
+            else:
+                h = np.ascontiguousarray(packs[r][:320]); m = np.ascontiguousarray(packs[r][320:]).view(np.int32)
+                check(self.l.td_sweep_peer_connect_dev(self.T.ctx, which, h.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)))
+        conn(0, self.rank - 1 if self.rank > 0 else None)
+        conn(1, self.rank + 1 if self.rank < self.world - 1 else None)
+        conn(2, None if self.rank == 0 else 0)
+        self._peer_cache = key
+
+    def _sweep_peer(self, run, out):
+        """One kernel per rank: tiles deliver into the neighbour GPUs over NVLink themselves."""
+        s = self.s
+        check(self.l.td_sweep_peer_begin_dev(self.T.ctx, s.c, self._stream()))
+        torch.cuda.synchronize(); dist.barrier()          # every rank has announced its tiles in the global counter
+        halo = torch.zeros(2 * s.pitch, dtype=torch.int32, device=s.device)
+        run(halo)
+        torch.cuda.synchronize(); dist.barrier()
+        self.l.td_sweep_peer_off_dev(self.T.ctx)
+        self.rounds = 1
+        return out
+
     def _sweep(self, run, out):
+        if self.peer:
+            return self._sweep_peer(run, out)
         s = self.s
         check(self.l.td_sweep_begin_dev(self.T.ctx, s.c, self._stream()))
         halo = torch.zeros(2 * s.pitch, dtype=torch.int32, device=s.device)
@@ -128,6 +173,8 @@ class DistTools:
         ad8 = s.empty(torch.float32) if ad8 is None else ad8
         if not shared:
             self.share(p)
+        if self.peer:
+            self._peer_setup(False)
         self.T.aread8_deps(s, p, ad8, nodata)
         wp = None if w is None else C.c_void_p(w.data_ptr())
         return self._sweep(lambda halo: check(self.l.td_aread8_sweep_run_dev(self.T.ctx, wp, C.c_void_p(ad8.data_ptr()), s.c, w_nodata, int(w is not None),
@@ -138,6 +185,8 @@ class DistTools:
         sca = s.empty(torch.float32) if sca is None else sca
         if not shared:
             self.share(ang)
+        if self.peer:
+            self._peer_setup(True)
         self.T.areadinf_deps(s, ang, sca, dxc, dyc, nodata)
         wp = None if w is None else C.c_void_p(w.data_ptr())
         return self._sweep(lambda halo: check(self.l.td_area_sweep_run_dev(self.T.ctx, C.c_void_p(ang.data_ptr()), wp, C.c_void_p(sca.data_ptr()), s.c,
