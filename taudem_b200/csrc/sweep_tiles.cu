@@ -156,7 +156,7 @@ __global__ void k_sched_init(int* state, unsigned char* visited, int* tq, unsign
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < qcap) tq[i] = (int)i < ntiles ? (int)i + 1 : 0;
   if ((int)i < ntiles) { state[i] = 1; visited[i] = 0; }
-  if (i == 0) { ctr[0] = 0; ctr[1] = (unsigned long long)ntiles; ctr[2] = (unsigned long long)ntiles; ctr[3] = 0; ctr[4] = ctr[5] = ctr[6] = ctr[7] = ctr[8] = 0; }
+  if (i == 0) { ctr[0] = 0; ctr[1] = (unsigned long long)ntiles; ctr[2] = (unsigned long long)ntiles; ctr[3] = 0; ctr[4] = ctr[5] = ctr[6] = ctr[7] = 0; }
 }
 
 template <bool DINF, int TWY>
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
       atomicAdd(a.ctr + 5, (unsigned long long)(tk2 - tk1));
       atomicAdd(a.ctr + 6, (unsigned long long)(tk3 - tk2));
       atomicAdd(a.ctr + 7, (unsigned long long)(tk4 - tk3));
-      atomicAdd(a.ctr + 8, (unsigned long long)npass);
+      (void)npass;
     }
     __syncthreads();
   }
@@ -556,6 +556,10 @@ int sweep_peer_connect(td_ctx* ctx, int which, const unsigned char* handles, con
     return TD_OK;
   }
   td_ctx::PeerInfo& pi = which == 0 ? ctx->peer_up : ctx->peer_down;
+  if (!handles && meta && pi.valid) {       // same buffers, new tile geometry (D8 <-> D-infinity sweep)
+    pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4];
+    return TD_OK;
+  }
   close_peer(pi);
   if (!handles) return TD_OK;
   TD_CUDA(open(handles, &pi.cntw));

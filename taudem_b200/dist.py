@@ -121,28 +121,38 @@ class DistTools:
         allp = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allp, mine)
         packs = [p.cpu().numpy() for p in allp]
-        key = b"".join(p.tobytes() for p in packs)
-        if key == self._peer_cache:
-            return
-        def conn(which, r):
+        hkey = b"".join(p[:320].tobytes() for p in packs)      # the IPC handles: re-opened only when a buffer moved
+        mkey = b"".join(p[320:].tobytes() for p in packs)      # tile geometry: cheap to refresh (D8 <-> D-infinity)
+        def conn(which, r, handles=True):
             if r is None:
                 check(self.l.td_sweep_peer_connect_dev(self.T.ctx, which, None, None))
             else:
                 h = np.ascontiguousarray(packs[r][:320]); m = np.ascontiguousarray(packs[r][320:]).view(np.int32)
-                check(self.l.td_sweep_peer_connect_dev(self.T.ctx, which, h.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)))
-        conn(0, self.rank - 1 if self.rank > 0 else None)
-        conn(1, self.rank + 1 if self.rank < self.world - 1 else None)
-        conn(2, None if self.rank == 0 else 0)
-        self._peer_cache = key
+                check(self.l.td_sweep_peer_connect_dev(self.T.ctx, which, h.ctypes.data_as(C.c_void_p) if handles else None, m.ctypes.data_as(C.c_void_p)))
+        up = self.rank - 1 if self.rank > 0 else None
+        down = self.rank + 1 if self.rank < self.world - 1 else None
+        if self._peer_cache is None or hkey != self._peer_cache[0]:
+            conn(0, up); conn(1, down); conn(2, None if self.rank == 0 else 0)
+        elif mkey != self._peer_cache[1]:
+            if up is not None: conn(0, up, handles=False)
+            if down is not None: conn(1, down, handles=False)
+        self._peer_cache = (hkey, mkey)
 
     def _sweep_peer(self, run, out):
         """One kernel per rank: tiles deliver into the neighbour GPUs over NVLink themselves."""
+        import os, sys, time
+        dbg = os.environ.get("TD_DEBUG") == "1"
         s = self.s
         check(self.l.td_sweep_peer_begin_dev(self.T.ctx, s.c, self._stream()))
         torch.cuda.synchronize(); dist.barrier()          # every rank has announced its tiles in the global counter
+        if dbg:
+            print(f"[peer r{self.rank} {time.time():.3f}] begin done, launching", file=sys.stderr, flush=True)
         halo = torch.zeros(2 * s.pitch, dtype=torch.int32, device=s.device)
         run(halo)
-        torch.cuda.synchronize(); dist.barrier()
+        torch.cuda.synchronize()
+        if dbg:
+            print(f"[peer r{self.rank} {time.time():.3f}] kernel finished", file=sys.stderr, flush=True)
+        dist.barrier()
         self.l.td_sweep_peer_off_dev(self.T.ctx)
         self.rounds = 1
         return out
