@@ -34,8 +34,8 @@ constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 
 // what a neighbouring strip exposes to this GPU (device pointers into the peer's memory)
 struct PeerStrip {
-  unsigned* cntw; int* state; int* tq; unsigned long long* ctr; float* halo_in;
-  unsigned qmask; int ntx, ny, th, valid;
+  unsigned* cntw = nullptr; int* state = nullptr; int* tq = nullptr; unsigned long long* ctr = nullptr; float* halo_in = nullptr;
+  unsigned qmask = 0; int ntx = 0, ny = 0, th = 0, valid = 0;
 };
 
 struct SweepArgs {
@@ -464,6 +464,9 @@ __global__ void k_sched_reset(unsigned long long* ctr) { ctr[0] = ctr[1] = ctr[2
 
 int sweep_args(td_ctx* ctx, SweepArgs& a, const Strip& s) {
   a.s = s;
+  // fields only the sweep kernel fills; the scheduler helpers (k_apply_halo) read a.peer / a.G
+  a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
+  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
   a.th = ctx->sweep_dinf ? TH_DINF : TH_D8;
   a.ntx = (s.nx + TWX - 1) / TWX; a.nty = (s.ny + a.th - 1) / a.th;
   const long long nt = (long long)a.ntx * a.nty;
