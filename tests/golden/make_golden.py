@@ -41,6 +41,13 @@ def main():
         out = dict(dem=dem, dx=np.float64(dx), dy=np.float64(dy), w=w, fel=fel, fel4=fel4, p=p, sd8=sd8, ang=ang, slp=slp,
                    ad8=R.aread8(p), ad8_w=R.aread8(p, weights=w), ad8_nc=R.aread8(p, contcheck=False),
                    sca=R.areadinf(ang), sca_w=R.areadinf(ang, weights=w), sca_nc=R.areadinf(ang, contcheck=False))
+        if name == "lake":
+            # depression mask (-depmask): the cells marked 1 are real depressions and keep their elevation
+            mask = np.zeros(dem.shape, np.int16)
+            mask[24:36, 28:42] = 1
+            out["depmask"] = mask
+            out["fel_mask"] = R.pitremove(dem, depmask=mask)
+            out["fel_mask4"] = R.pitremove(dem, depmask=mask, four_way=True)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         flats = int(((sd8 == 0) & (p != -32768)).sum())
         print(f"{name}: {dem.shape} filled {(fel != dem).sum()} flats {flats} ad8 max {out['ad8'].max()} sca nodata {(out['sca'] == -1).sum()}")

@@ -137,6 +137,9 @@ def test_c_restatement_reproduces_golden(name):
     dx, dy = float(g["dx"]), float(g["dy"])
     assert_bits(port.pitremove(g["dem"]), g["fel"], "fel")
     assert_bits(port.pitremove(g["dem"], four_way=True), g["fel4"], "fel4")
+    if "depmask" in g:
+        assert_bits(port.pitremove(g["dem"], depmask=g["depmask"]), g["fel_mask"], "fel -depmask")
+        assert_bits(port.pitremove(g["dem"], depmask=g["depmask"], four_way=True), g["fel_mask4"], "fel -depmask -4way")
     p, sd8 = port.d8flowdir(g["fel"], dx=dx, dy=dy)
     assert_bits(sd8, g["sd8"], "sd8"); assert_bits(p, g["p"], "p")
     ang, slp = port.dinfflowdir(g["fel"], dx=dx, dy=dy)

@@ -218,3 +218,16 @@ def test_large_vs_c_restatement():
     ang, slp = td.dinfflowdir_grid(fel); ang_o, slp_o = port.dinfflowdir(fel)
     assert_bits(slp, slp_o, "slp"); assert_float_parity(ang, ang_o, "ang")
     assert_float_parity(td.areadinf_grid(ang_o), port.areadinf(ang_o), "sca")
+
+
+def test_depression_mask():
+    """pitremove -depmask (src/flood.cpp:75-85, 250-251): masked cells are seeds and keep their elevation."""
+    g = load_golden("lake")
+    assert_bits(td.pitremove_grid(g["dem"], depmask=g["depmask"]), g["fel_mask"], "fel -depmask")
+    assert_bits(td.pitremove_grid(g["dem"], depmask=g["depmask"], is_4Point=True), g["fel_mask4"], "fel -depmask -4way")
+    # and a partial mask on a larger grid against the C restatement
+    import port
+    if port.available():
+        dem = synth.gen_dem(300, 420, family="rough", seed=3)
+        mask = (synth.gen_weights(300, 420, seed=17) > 0.97).astype(np.int16)
+        assert_bits(td.pitremove_grid(dem, depmask=mask), port.pitremove(dem, depmask=mask), "fel -depmask rough")
