@@ -10,7 +10,7 @@ import pytest
 
 import taudem_b200 as td
 from taudem_b200 import _lib, synth
-from util import assert_bits, golden_cases, load_golden
+from util import assert_bits, golden_cases, load_golden, write_geographic_dem
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -150,3 +150,30 @@ def test_c_restatement_reproduces_golden(name):
     assert_bits(port.areadinf(g["ang"], dx=dx, dy=dy), g["sca"], "sca")
     assert_bits(port.areadinf(g["ang"], weights=g["w"], dx=dx, dy=dy), g["sca_w"], "sca_w")
     assert_bits(port.areadinf(g["ang"], dx=dx, dy=dy, contcheck=False), g["sca_nc"], "sca_nc")
+
+
+def test_geographic_cell_sizes_match_reference(refrun, tmp_path):
+    """Geographic rasters: our per-row dxc/dyc (tiff_io cell_sizes) fed to the C restatement reproduce what
+    the reference tools compute from the same file (they derive the sizes themselves in tiffIO)."""
+    import port
+    if not port.available():
+        pytest.skip("oracle/port not built")
+    dem = synth.gen_dem(90, 120, hurst=0.8, tilt=1.0, seed=8)
+    f = str(tmp_path / "geo.tif")
+    write_geographic_dem(f, dem)
+    info = td.raster_info(f)
+    assert info["is_geographic"] and info["dx"] == 0.001
+    dxc, dyc = np.zeros(90), np.zeros(90)
+    assert td.lib().td_raster_cell_sizes(f.encode(), dxc.ctypes.data_as(ctypes.c_void_p), dyc.ctypes.data_as(ctypes.c_void_p), 90) == 0
+    assert 82.9 < dxc[0] < dxc[-1] < 83.2 and 111.0 < dyc[0] < 111.1     # metres at 41.9 N
+    out, _ = refrun.run_tool("d8flowdir", ["-fel", f, "-p", str(tmp_path / "p.tif"), "-sd8", str(tmp_path / "sd8.tif")])
+    assert "geographic coordinate system" in out
+    p_o, sd8_o = port.d8flowdir(dem, nodata=-9999.0, dx=dxc, dy=dyc)
+    assert_bits(td.read_raster(str(tmp_path / "p.tif"), np.int16), p_o, "p")
+    assert_bits(td.read_raster(str(tmp_path / "sd8.tif")), sd8_o, "sd8")
+    refrun.run_tool("dinfflowdir", ["-fel", f, "-ang", str(tmp_path / "ang.tif"), "-slp", str(tmp_path / "slp.tif")])
+    ang_r = td.read_raster(str(tmp_path / "ang.tif"))
+    ang_o, slp_o = port.dinfflowdir(dem, nodata=-9999.0, dx=dxc, dy=dyc)
+    assert_bits(ang_r, ang_o, "ang"); assert_bits(td.read_raster(str(tmp_path / "slp.tif")), slp_o, "slp")
+    refrun.run_tool("areadinf", ["-ang", str(tmp_path / "ang.tif"), "-sca", str(tmp_path / "sca.tif")])
+    assert_bits(td.read_raster(str(tmp_path / "sca.tif")), port.areadinf(ang_r, dx=dxc, dy=dyc), "sca")

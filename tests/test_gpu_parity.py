@@ -8,7 +8,7 @@ import pytest
 
 import taudem_b200 as td
 from taudem_b200 import synth
-from util import ANG_ND, FEL_ND, assert_bits, assert_float_parity, golden_cases, load_golden
+from util import ANG_ND, FEL_ND, assert_bits, assert_float_parity, golden_cases, load_golden, write_geographic_dem
 
 pytestmark = pytest.mark.gpu
 
@@ -231,3 +231,28 @@ def test_depression_mask():
         dem = synth.gen_dem(300, 420, family="rough", seed=3)
         mask = (synth.gen_weights(300, 420, seed=17) > 0.97).astype(np.int16)
         assert_bits(td.pitremove_grid(dem, depmask=mask), port.pitremove(dem, depmask=mask), "fel -depmask rough")
+
+
+def test_geographic_dem_file_level(refrun, tmp_path):
+    """A DEM in geographic coordinates through the file-level entry points: per-row cell sizes on the
+    ellipsoid (src/tiffIO.cpp:118-151) reach every kernel; rasters against the reference tools'."""
+    import os
+    dem = synth.punch_holes(synth.gen_dem(150, 210, hurst=0.8, tilt=1.0, seed=12))
+    d = str(tmp_path)
+    write_geographic_dem(os.path.join(d, "geo.tif"), dem)
+    os.makedirs(os.path.join(d, "ref"))
+    for tool, args in (("pitremove", ["-z", "geo.tif", "-fel", "{o}fel.tif"]), ("d8flowdir", ["-fel", "{o}fel.tif", "-p", "{o}p.tif", "-sd8", "{o}sd8.tif"]),
+                       ("dinfflowdir", ["-fel", "{o}fel.tif", "-ang", "{o}ang.tif", "-slp", "{o}slp.tif"]),
+                       ("aread8", ["-p", "{o}p.tif", "-ad8", "{o}ad8.tif"]), ("areadinf", ["-ang", "{o}ang.tif", "-sca", "{o}sca.tif"])):
+        refrun.run_tool(tool, [os.path.join(d, a.format(o="ref/")) if a.endswith(".tif") else a for a in args])
+    q = lambda n: os.path.join(d, n)
+    assert td.flood(q("geo.tif"), q("fel.tif")) == 0
+    assert td.setdird8(q("fel.tif"), q("p.tif"), q("sd8.tif")) == 0
+    assert td.setdir(q("fel.tif"), q("ang.tif"), q("slp.tif")) == 0
+    assert td.aread8(q("p.tif"), q("ad8.tif")) == 0
+    assert td.area(q("ang.tif"), q("sca.tif")) == 0
+    for n, dt, exact in (("fel", np.float32, True), ("p", np.int16, True), ("sd8", np.float32, True), ("slp", np.float32, True),
+                         ("ad8", np.float32, True), ("ang", np.float32, False), ("sca", np.float32, False)):
+        a, b = td.read_raster(q(n + ".tif"), dt), td.read_raster(q("ref/" + n + ".tif"), dt)
+        (assert_bits if exact else assert_float_parity)(a, b, n + " (geographic)")
+    assert td.raster_info(q("sca.tif"))["is_geographic"]        # GeoTIFF keys pass through to the outputs

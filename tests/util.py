@@ -40,3 +40,16 @@ def assert_float_parity(a, b, what, rtol=1e-5):
     rel = np.abs(a[ok].astype(np.float64) - b[ok]) / np.maximum(np.abs(b[ok].astype(np.float64)), 1e-300)
     assert rel.size == 0 or rel.max() <= rtol, f"{what}: max rel err {rel.max()}"
     assert bits_equal(a[ma], b[ma]), f"{what}: nodata values differ"
+
+
+def write_geographic_dem(path, dem, lon0=-111.8, lat0=41.9, cell=0.001, nodata=-9999.0):
+    """A GeoTIFF in geographic coordinates (GTModelTypeGeoKey = 2) written with libtiff (PIL): the reference
+    then derives per-row metric cell sizes on the WGS84 ellipsoid (src/tiffIO.cpp:118-151, 434-445)."""
+    from PIL import Image, TiffImagePlugin
+    info = TiffImagePlugin.ImageFileDirectory_v2()
+    info[33550] = (cell, cell, 0.0)
+    info[33922] = (0.0, 0.0, 0.0, lon0, lat0, 0.0)
+    info[34735] = (1, 1, 0, 2, 1024, 0, 1, 2, 1025, 0, 1, 1)
+    info.tagtype[33550] = 12; info.tagtype[33922] = 12; info.tagtype[34735] = 3
+    info[42113] = repr(float(nodata))
+    Image.fromarray(np.ascontiguousarray(dem, np.float32)).save(path, tiffinfo=info)
