@@ -1,12 +1,16 @@
 // Native TIFF / BigTIFF raster I/O (see tiff_io.h for the reference contract).
 #include "tiff_io.h"
 
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <atomic>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 namespace tdio {
 namespace {
@@ -23,9 +27,16 @@ void swap_elems(uint8_t* p, size_t n, int sz) {
   else if (sz == 8) { for (size_t i = 0; i < n; i++) { uint64_t v; memcpy(&v, p + 8 * i, 8); v = bswap64(v); memcpy(p + 8 * i, &v, 8); } }
 }
 
+// positional read on the descriptor: safe from several decoder threads at once
 bool pread_all(FILE* fp, uint64_t off, void* buf, size_t n) {
-  if (fseeko(fp, (off_t)off, SEEK_SET) != 0) return false;
-  return fread(buf, 1, n, fp) == n;
+  const int fd = fileno(fp);
+  char* c = (char*)buf;
+  while (n) {
+    const ssize_t k = pread(fd, c, n, (off_t)off);
+    if (k <= 0) return false;
+    c += k; off += (uint64_t)k; n -= (size_t)k;
+  }
+  return true;
 }
 
 double tag_double(const RawTag& t, size_t i) {
@@ -104,49 +115,59 @@ void convert_row(const uint8_t* src, int bits, int fmt, void* dst, DType type, l
 
 // ------------------------------------------------------------------ LZW
 bool lzw_decode(const uint8_t* in, size_t n, std::vector<uint8_t>* out, size_t expect) {
-  out->clear();
-  out->reserve(expect);
+  // TIFF flavour: MSB-first codes, ClearCode 256, EOI 257, "early change" of the code width.
+  out->resize(expect);
+  uint8_t* o = out->data();
+  size_t op = 0;
   struct Entry { int32_t prev; uint16_t len; uint8_t first, last; };
-  std::vector<Entry> tab(4096 + 2);
+  Entry tab[4096 + 2];
   for (int i = 0; i < 256; i++) tab[i] = {-1, 1, (uint8_t)i, (uint8_t)i};
   int next = 258, bits = 9, prev = -1;
   uint64_t acc = 0; int nacc = 0; size_t pos = 0;
-  std::vector<uint8_t> tmp;
-  while (out->size() < expect) {
-    while (nacc < bits && pos < n) { acc = (acc << 8) | in[pos++]; nacc += 8; }
+  while (op < expect) {
+    while (nacc <= 56 && pos < n) { acc = (acc << 8) | in[pos++]; nacc += 8; }
     if (nacc < bits) break;
-    int code = (int)((acc >> (nacc - bits)) & ((1u << bits) - 1));
+    const int code = (int)((acc >> (nacc - bits)) & ((1u << bits) - 1));
     nacc -= bits;
     if (code == 257) break;
     if (code == 256) { next = 258; bits = 9; prev = -1; continue; }
     if (prev < 0) {
       if (code >= 256) return false;
-      out->push_back((uint8_t)code);
+      o[op++] = (uint8_t)code;
       prev = code;
       continue;
     }
     int emit = code;
-    uint8_t extra = 0; bool has_extra = false;
+    bool kwk = false;
     if (code >= next) {            // KwKwK case
       if (code != next) return false;
-      emit = prev; extra = tab[prev].first; has_extra = true;
+      emit = prev; kwk = true;
     }
-    size_t len = tab[emit].len;
-    size_t base = out->size();
-    out->resize(base + len + (has_extra ? 1 : 0));
-    int c = emit;
-    for (size_t k = len; k-- > 0;) { (*out)[base + k] = tab[c].last; c = tab[c].prev; }
-    if (has_extra) (*out)[base + len] = extra;
+    const size_t len = tab[emit].len;
+    const size_t total = len + (kwk ? 1 : 0);
+    const uint8_t firstc = tab[emit].first;
+    if (op + total <= expect) {
+      int c = emit;
+      for (size_t k = len; k-- > 0;) { o[op + k] = tab[c].last; c = tab[c].prev; }
+      if (kwk) o[op + len] = firstc;
+      op += total;
+    } else {                       // last string runs past the expected size: keep the part that fits
+      uint8_t tmp[4100];
+      int c = emit;
+      for (size_t k = len; k-- > 0;) { tmp[k] = tab[c].last; c = tab[c].prev; }
+      if (kwk) tmp[len] = firstc;
+      const size_t fit = expect - op;
+      memcpy(o + op, tmp, fit);
+      op = expect;
+    }
     if (next < 4096) {
-      tab[next] = {prev, (uint16_t)(tab[prev].len + 1), tab[prev].first,
-                   has_extra ? extra : tab[emit].first};
+      tab[next] = {prev, (uint16_t)(tab[prev].len + 1), tab[prev].first, firstc};
       next++;
     }
     if (next == (1 << bits) - 1 && bits < 12) bits++;   // TIFF "early change"
     prev = code;
   }
-  if (out->size() > expect) out->resize(expect);
-  return out->size() == expect;
+  return op == expect;
 }
 
 void lzw_encode(const uint8_t* in, size_t n, std::vector<uint8_t>* out) {
@@ -384,10 +405,27 @@ bool Raster::read(long xstart, long ystart, long nrows, long ncols, void* dest, 
   if (dest_stride == 0) dest_stride = ncols;
   const int sb = bits_ / 8, db = dtype_bytes(type);
   const uint64_t blocks_across = tiled_ ? (width_ + block_w_ - 1) / block_w_ : 1;
-  std::vector<uint8_t> blk;
-  for (long by = ystart / block_h_; by <= (ystart + nrows - 1) / (long)block_h_; by++) {
-    for (uint64_t bx = (uint64_t)xstart / block_w_; bx <= (uint64_t)(xstart + ncols - 1) / block_w_; bx++) {
-      if (!load_block((uint64_t)by * blocks_across + bx, &blk, err)) return false;
+  // the blocks (strips / tiles) that intersect the window, decoded by a small pool of threads: every block
+  // writes a disjoint part of dest (LZW / Deflate decoding is the cost of reading real-world DEMs)
+  struct Job { long by; uint64_t bx; };
+  std::vector<Job> jobs;
+  for (long by = ystart / block_h_; by <= (ystart + nrows - 1) / (long)block_h_; by++)
+    for (uint64_t bx = (uint64_t)xstart / block_w_; bx <= (uint64_t)(xstart + ncols - 1) / block_w_; bx++) jobs.push_back({by, bx});
+  std::atomic<size_t> next(0);
+  std::atomic<bool> failed(false);
+  std::mutex emu;
+  auto work = [&]() {
+    std::vector<uint8_t> blk;
+    std::string e;
+    for (;;) {
+      const size_t j = next.fetch_add(1);
+      if (j >= jobs.size() || failed.load()) return;
+      const long by = jobs[j].by; const uint64_t bx = jobs[j].bx;
+      if (!load_block((uint64_t)by * blocks_across + bx, &blk, &e)) {
+        std::lock_guard<std::mutex> g(emu);
+        if (!failed.exchange(true)) *err = e;
+        return;
+      }
       const long r0 = std::max<long>(ystart, by * (long)block_h_);
       const long r1 = std::min<long>(ystart + nrows, (by + 1) * (long)block_h_);
       const long c0 = std::max<long>(xstart, (long)(bx * block_w_));
@@ -398,8 +436,16 @@ bool Raster::read(long xstart, long ystart, long nrows, long ncols, void* dest, 
         convert_row(src, bits_, sample_format_, dst, type, c1 - c0);
       }
     }
+  };
+  unsigned nthreads = compression_ == 1 ? 1u : std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  nthreads = (unsigned)std::min<size_t>(nthreads, jobs.size());
+  if (nthreads <= 1) work();
+  else {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
   }
-  return true;
+  return !failed.load();
 }
 
 // ------------------------------------------------------------------ Writer
