@@ -4,8 +4,8 @@
 // The value of a cell is a k-ordered gather over the neighbours that drain into it, evaluated
 // once when all of them are done; the schedule is free, so:
 //
-//  * the strip is cut into 64 x 32 tiles; persistent CTAs take tile ids from a device-side
-//    multi-producer/multi-consumer queue;
+//  * the strip is cut into 64 x 32 (D8) / 64 x 16 (D-infinity) tiles; persistent CTAs take tile ids
+//    from a device-side multi-producer/multi-consumer ticket queue;
 //  * a CTA loads the tile's dependency counts, node words and areas (with a one-cell ring)
 //    into shared memory and runs the wavefront INSIDE shared memory: threads start on cells
 //    whose count is zero, evaluate them, decrement the downslope cell with a shared-memory
@@ -16,8 +16,9 @@
 //    zero activates the owning tile (per-tile state: idle / queued / running / running+dirty,
 //    so a tile is never processed by two CTAs at once);
 //  * the kernel ends when no tile is queued or running.
-// Flow that crosses the strip boundary is recorded in ctx.halo for the neighbour strip
-// (src/aread8.cpp:282-297).
+// Flow that crosses the strip boundary (one strip per GPU) is either recorded in `halo` for the
+// host-driven exchange rounds (src/aread8.cpp:282-297) or, in peer mode, delivered straight into the
+// neighbour GPU's counts / halo buffer / tile queue over NVLink (deliver_peer, sched_activate_peer).
 #include <string.h>
 
 #include "ctx.h"
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(256) k_sweep_tiles(const SweepArgs a) {
     if (tid == 0) {
       if (self_dirty) sched_activate(a, t);
       sched_finish(a, t);
-      // statistics (cycles, summed over CTAs): queue wait, load, wavefront, write-back + deliveries; passes
+      // statistics (cycles, summed over CTAs): queue wait, load, wavefront, write-back + deliveries
       const long long tk4 = clock64();
       atomicAdd(a.ctr + 4, (unsigned long long)(tk1 - tk0));
       atomicAdd(a.ctr + 5, (unsigned long long)(tk2 - tk1));
