@@ -94,8 +94,14 @@ class DistTools:
         from .device import DeviceStrip, Tools
         # peer mode: sweeps deliver across GPUs inside the kernel (CUDA IPC + NVLink atomics), no exchange
         # rounds.  Needs one GPU per rank and the NCCL backend; TAUDEM_B200_PEER=0/1 overrides.
+        # Default: on for 2..4 NCCL ranks (validated bit-identical on 2 GPUs and by the 4-GPU 65536^2 bench), off
+        # for more ranks until it has been run there (the round-based exchange has been, on 8 GPUs).
         if peer is None:
-            peer = os.environ.get("TAUDEM_B200_PEER", "0") == "1"
+            env = os.environ.get("TAUDEM_B200_PEER")
+            if env is not None:
+                peer = env == "1"
+            else:
+                peer = dist.is_initialized() and dist.get_backend() == "nccl" and 2 <= world <= 4
         self.peer = bool(peer) and world > 1
         self._peer_cache = None
         self.rank, self.world = rank, world
@@ -371,7 +377,7 @@ def bench_main(args, rank, world, local):
         line = {"metric": B.METRIC, "value": round(value, 2), "unit": "Mcells/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"aread8 + areadinf on {n}x{n} float32 synthetic fractal DEM (hills: H={B.HURST}, tilt={B.TILT}, seed={B.SEED}, 30 m cells), contamination check on, no weights",
-                           "cells": cells, "partition": f"{world} row strips (linearpart: total//size rows, remainder on the last rank), NCCL send/recv halo + decrement exchange, all_reduce termination",
+                           "cells": cells, "partition": f"{world} row strips (linearpart: total//size rows, remainder on the last rank); " + ("peer mode: the sweep kernels deliver across GPUs over NVLink (CUDA IPC, system-scope atomics), no exchange rounds" if D.peer else "NCCL send/recv halo + decrement exchange rounds, all_reduce termination"),
                            "exchange_rounds": {"aread8": rounds[0], "areadinf": rounds[1]}, "l2": "inputs exceed the 126 MB L2; no explicit flush",
                            "timed": "CUDA events per rank, max over ranks", "max_ad8": float(mx[0]), "max_sca": float(mx[1]), **info},
                 "clocks": clk.summary(),
