@@ -1,0 +1,62 @@
+"""A/B of the single-strip sweep implementations (TAUDEM_B200_SWEEP = tiles | hybrid | walk | chain):
+bit-identity of ad8 / sca against the default tile dataflow and CUDA-event timings of the sweep alone.
+
+  python scripts/sweep_modes.py [n=4096] [modes=tiles,hybrid,walk] [reps=3]
+
+Every mode runs under the caller's own `timeout`; a mode that differs prints DIFFERENT and the script
+exits 1 at the end."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from taudem_b200.device import DeviceStrip, Tools
+
+
+def timed(fn):
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+    return r, a.elapsed_time(b)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    modes = (sys.argv[2] if len(sys.argv) > 2 else "tiles,hybrid,walk").split(",")
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+    T = Tools()
+    s = DeviceStrip(n, n)
+    dxc, dyc = s.rows(30.0), s.rows(30.0)
+    dem = T.gen_dem(s, hurst=0.8, tilt=1.0)
+    fel = T.pitremove(s, dem); del dem
+    p, sd8, _ = T.d8_slopes(s, fel, dxc, dyc); del sd8
+    felc = fel.clone(); T.d8_flats(s, felc, p, dxc, dyc)
+    ang, slp, _ = T.dinf_slopes(s, fel, dxc, dyc); del slp
+    felc.copy_(fel); T.dinf_flats(s, felc, ang, dxc, dyc); del felc, fel
+    ref, bad = {}, 0
+    for mode in modes:
+        os.environ["TAUDEM_B200_SWEEP"] = mode
+        for tool in ("aread8", "areadinf"):
+            out = s.empty(torch.float32)
+            best = 1e30
+            for _ in range(reps):
+                if tool == "aread8":
+                    T.aread8_deps(s, p, out); _, t = timed(lambda: T.aread8_sweep(s, out))
+                else:
+                    T.areadinf_deps(s, ang, out, dxc, dyc); _, t = timed(lambda: T.areadinf_sweep(s, ang, out, dxc))
+                best = min(best, t)
+            own = s.owned(out)
+            if tool not in ref: ref[tool] = own.clone(); verdict = "reference"
+            else:
+                same = torch.equal(own.view(torch.int32), ref[tool].view(torch.int32))
+                verdict = "identical" if same else f"DIFFERENT ({int((own.view(torch.int32) != ref[tool].view(torch.int32)).sum())} cells)"
+                bad += 0 if same else 1
+            print(f"{mode:7s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}", flush=True)
+            del out
+    os.environ.pop("TAUDEM_B200_SWEEP", None)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,11 +49,34 @@ int need_device() {
   if (e != cudaSuccess || n == 0) { td::set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
-// TAUDEM_B200_SWEEP=chain selects the first-generation global chain-following sweep (kept for A/B
-// measurements); the default is the shared-memory tile dataflow (sweep_tiles.cu).
-bool chain_sweep() {
+// TAUDEM_B200_SWEEP selects the single-strip sweep (A/B measurements); the default is the shared-memory
+// tile dataflow (sweep_tiles.cu):
+//   chain  : first-generation one-thread-per-cell chain following (area_d8.cu / area_dinf.cu)
+//   hybrid : one pass of the tile kernel over every tile, then warp-level chain walking from the cells that
+//            are ready but not evaluated (sweep_walk.cu)
+//   walk   : warp-level chain walking from the sources alone
+enum SweepMode { SWEEP_TILES, SWEEP_CHAIN, SWEEP_HYBRID, SWEEP_WALK };
+SweepMode sweep_mode() {
   const char* e = getenv("TAUDEM_B200_SWEEP");
-  return e && strcmp(e, "chain") == 0;
+  if (!e) return SWEEP_TILES;
+  if (strcmp(e, "chain") == 0) return SWEEP_CHAIN;
+  if (strcmp(e, "hybrid") == 0) return SWEEP_HYBRID;
+  if (strcmp(e, "walk") == 0) return SWEEP_WALK;
+  return SWEEP_TILES;
+}
+bool chain_sweep() { return sweep_mode() == SWEEP_CHAIN; }
+// hybrid / walk (see above); halo records cross-strip decrements exactly like the other sweeps
+int sweep_alt(td_ctx* ctx, SweepMode mode, bool dinf, float* area, const float* w, const float* ang, const td::Strip& s, float w_nodata,
+              int usew, int contcheck, const double* dxc, cudaStream_t st) {
+  const double* theta = dinf ? ctx->theta.as<double>() : nullptr;
+  if (mode == SWEEP_HYBRID) {
+    if (int rc = td::sweep_begin(ctx, s, st)) return rc;
+    ctx->sweep_once = 1;
+    const int rc = td::sweep_run(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st);
+    ctx->sweep_once = 0;
+    if (rc) return rc;
+  }
+  return td::sweep_walk(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st);
 }
 td_ctx* default_ctx() {
   static td_ctx* c = nullptr;
@@ -201,6 +224,9 @@ int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, flo
                                 ctx->halo.as<int>(), (cudaStream_t)stream));
     return TD_OK;
   }
+  const SweepMode mode = sweep_mode();
+  if (mode == SWEEP_HYBRID || mode == SWEEP_WALK)
+    return sweep_alt(ctx, mode, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, (cudaStream_t)stream);
   if (int rc = td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
   return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(),
                        (cudaStream_t)stream);
@@ -222,6 +248,8 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   if (int rc = check_strip(s)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const Strip ss(s);
+  const SweepMode mode = sweep_mode();
+  if (mode == SWEEP_HYBRID || mode == SWEEP_WALK) return sweep_alt(ctx, mode, true, sca, w, ang, ss, 0.f, usew, contcheck, dxc, st);
   if (!chain_sweep()) {
     if (int rc = td::sweep_begin(ctx, ss, st)) return rc;
     return td::sweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);

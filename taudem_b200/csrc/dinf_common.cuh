@@ -90,14 +90,22 @@ __device__ __forceinline__ double prop_dev(float a, int k, double t) {
 //   j == 9 (a >= 2*PI) or j == 0 (a < 0)    -> direction 1 only.
 struct Outflow { int k1, k2; double p1, p2; };
 
-__device__ __forceinline__ double prop_dir1_wrapped(float a, const double* ar) {
+// prop()'s table for one row without storing it: ArefRow{t}[i] == aref(i, t)
+struct ArefRow {
+  double t;
+  __device__ __forceinline__ double operator[](int i) const { return aref(i, t); }
+};
+
+template <typename AR>
+__device__ __forceinline__ double prop_dir1_wrapped(float a, const AR& ar) {
   const float a1 = (float)(a - 2.0 * TD_PI);
   double p = 0.;
   if (a1 > ar[0] && a1 < ar[2]) p = (a1 > ar[1]) ? (ar[2] - a1) / (ar[2] - ar[1]) : (a1 - ar[0]) / (ar[1] - ar[0]);
   return p;
 }
 
-__device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) {
+template <typename AR>
+__device__ __forceinline__ Outflow dinf_outflow_t(float a, const AR& ar) {
   Outflow o; o.k1 = o.k2 = 0; o.p1 = o.p2 = 0.;
   int j = 0;
 #pragma unroll
@@ -119,5 +127,7 @@ __device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) {
   if (!(pB < 1e-5)) { if (o.k1 == 0) { o.k1 = kB; o.p1 = pB; } else { o.k2 = kB; o.p2 = pB; } }
   return o;
 }
+__device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) { return dinf_outflow_t(a, ar); }
+__device__ __forceinline__ Outflow dinf_outflow(float a, double t) { return dinf_outflow_t(a, ArefRow{t}); }
 
 }  // namespace td

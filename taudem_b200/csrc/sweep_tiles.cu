@@ -63,6 +63,8 @@ struct SweepArgs {
   PeerStrip up, down;      // the strip above (rank-1) / below (rank+1)
   unsigned long long* G;   // queued + running tiles of ALL strips (lives on rank 0)
   const float* halo_in;    // areas of the neighbours' edge cells: [0,pitch) row above, [pitch,2 pitch) row below
+  int once;                // every tile is visited exactly once: nothing is re-activated (first phase of the hybrid sweep,
+                           // sweep_walk.cu finishes the cells that become ready after their tile's visit)
 };
 
 template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((const volatile T*)p); }
@@ -88,6 +90,7 @@ __device__ void sched_push(const SweepArgs& a, int t) {
 }
 
 __device__ void sched_activate(const SweepArgs& a, int t) {
+  if (a.once) return;
   for (;;) {
     const int st = ldv(a.state + t);
     if (st == 1 || st == 3) return;
@@ -466,7 +469,7 @@ __global__ void k_sched_reset(unsigned long long* ctr) { ctr[0] = ctr[1] = ctr[2
 int sweep_args(td_ctx* ctx, SweepArgs& a, const Strip& s) {
   a.s = s;
   // fields only the sweep kernel fills; the scheduler helpers (k_apply_halo) read a.peer / a.G
-  a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
+  a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip(); a.once = 0;
   a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
   a.th = ctx->sweep_dinf ? TH_DINF : TH_D8;
   a.ntx = (s.nx + TWX - 1) / TWX; a.nty = (s.ny + a.th - 1) / a.th;
@@ -597,6 +600,8 @@ int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* 
   a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
   a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
   a.peer = ctx->peer_on;
+  a.once = ctx->sweep_once;
+  if (a.peer && a.once) { set_error("the single-pass tile sweep does not run in peer mode"); return TD_ERR_ARG; }
   if (a.peer) {
     auto fill = [](const td_ctx::PeerInfo& pi, PeerStrip& P) {
       P.valid = pi.valid;

@@ -1,0 +1,279 @@
+// Contributing-area evaluation by chain walking in global memory, fed from a list of ready cells.
+//
+// reference: aread8 main loop src/aread8.cpp:216-304, area() main loop src/areadinf.cpp:173-265
+// (queue of cells whose dependency count is zero; evaluate, decrement the receivers, push those that
+// reach zero).  The gather is k-ordered float32, evaluated once per cell when all contributors are final,
+// so the result does not depend on who evaluates a cell (same argument as sweep_tiles.cu).
+//
+// Used in two ways (TAUDEM_B200_SWEEP, see capi.cu):
+//   hybrid : the tile kernel (sweep_tiles.cu) visits every tile exactly ONCE and evaluates what is
+//            ready inside it — the bulk of the grid, streamed through shared memory; what is left are the
+//            cells downstream of a tile crossing (a sparse channel network).  Those are finished here
+//            without re-loading tiles: k_ready_* collect the cells whose count is already zero, k_walk
+//            follows the chains from there.
+//   walk   : everything from the sources with k_walk alone (A/B reference for the bulk rate).
+//
+// k_walk: every lane of a warp owns one chain.  A lane evaluates its cell, releases the area, decrements
+// the receiver(s) with an acq_rel atomic and moves on when it was the last arrival.  Idle lanes refill
+// from the warp's own fork stack (D-infinity: a cell can make two receivers ready) and then from the
+// global ready list in batches (one fetch-add per warp).  No CTA-wide barrier and no inter-warp waiting:
+// a warp that holds one long river does not keep a whole CTA's worth of threads from other work.
+// A fork stack that overflows spills to a global list that the host drains with another launch.
+#include <algorithm>
+
+#include "ctx.h"
+#include "dinf_common.cuh"
+#include "kernels.h"
+
+namespace td {
+namespace {
+constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
+constexpr int WQ = 96;        // fork stack entries per warp
+
+struct WalkArgs {
+  const unsigned short* node;
+  unsigned* cntw;
+  float* area;
+  const float* w;
+  const float* ang;
+  Strip s;
+  int usew, contcheck;
+  float w_nodata;
+  const double* theta;
+  const double* dxc;
+  int* halo;
+  const long long* list;
+  unsigned long long nlist;
+  unsigned long long* ctr;    // [0] list ticket, [1] spill length, [2] spill list exhausted, [3] ready cells (collect)
+  long long* spill;
+  unsigned long long spill_cap;
+};
+
+__device__ __forceinline__ unsigned dec_count(unsigned* words, long long cell) {
+  unsigned* a = words + (cell >> 2);
+  const unsigned sh = (unsigned)(cell & 3) * 8u;
+  unsigned old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
+  return (old >> sh) & 0xffu;
+}
+
+// ---- ready cells: count byte == 0 on an owned, valid cell.  One thread per count word (4 cells).
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_ready(const unsigned* __restrict__ cntw, const unsigned short* __restrict__ node, Strip s,
+                                               unsigned long long* __restrict__ ctr, long long* __restrict__ list) {
+  const long long wpr = s.pitch >> 2;                                   // words per row
+  const long long wi = (long long)blockIdx.x * 256 + threadIdx.x;
+  int n = 0;
+  long long cells[4];
+  if (wi < wpr * s.ny) {
+    const int r = 1 + (int)(wi / wpr), c = (int)(wi - (long long)(r - 1) * wpr) * 4;
+    const long long ci = s.idx(r, c);
+    const unsigned word = cntw[ci >> 2];
+    if (((word - 0x01010101u) & ~word & 0x80808080u) != 0u) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (((word >> (8 * i)) & 0xffu) == 0u && c + i < s.nx && (node[ci + i] & NODE_VALID)) cells[n++] = ci + i;
+    }
+  }
+  // warp-aggregated reservation
+  const unsigned lane = threadIdx.x & 31u;
+  int incl = n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  unsigned long long base = 0;
+  if (lane == 31) base = atomicAdd(ctr + (FILL ? 0 : 3), (unsigned long long)total);
+  if (!FILL) return;
+  base = __shfl_sync(0xffffffffu, base, 31);
+  for (int i = 0; i < n; ++i) list[base + (unsigned long long)(incl - n + i)] = cells[i];
+}
+
+template <bool DINF>
+__global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
+  __shared__ long long wq[8][WQ];
+  __shared__ int wqn[8];
+  const Strip& s = a.s;
+  const unsigned lane = threadIdx.x & 31u;
+  const int wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  if (lane == 0) wqn[wid] = 0;
+  __syncwarp();
+  long long cur = -1;
+  bool list_done = a.nlist == 0;        // warp-uniform
+  for (;;) {
+    // ---- refill idle lanes: the warp's fork stack first, then a batch of the global ready list
+    unsigned idle = __ballot_sync(0xffffffffu, cur < 0);
+    if (idle) {
+      const int nl = wqn[wid];
+      const int rank = __popc(idle & lt);
+      if (cur < 0 && rank < nl) cur = wq[wid][nl - 1 - rank];
+      __syncwarp();
+      if (lane == 0) wqn[wid] = max(0, nl - __popc(idle));
+      __syncwarp();
+      idle = __ballot_sync(0xffffffffu, cur < 0);
+      if (idle && !list_done) {
+        const int need = __popc(idle);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.ctr, (unsigned long long)need);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned long long mine = base + (unsigned long long)__popc(idle & lt);
+        if (cur < 0 && mine < a.nlist) cur = a.list[mine];
+        if (base + (unsigned long long)need >= a.nlist) list_done = true;
+      }
+    }
+    if (__ballot_sync(0xffffffffu, cur >= 0) == 0u) break;   // stack empty and list exhausted
+
+    // ---- one hop per active lane
+    long long fork = -1;
+    if (cur >= 0) {
+      const long long ci = cur;
+      const int r = (int)(ci / s.pitch), c = (int)(ci - (long long)r * s.pitch);
+      const unsigned nd = a.node[ci];
+      const unsigned m = nd & 0xffu;
+      bool con = (nd & NODE_CON) != 0;
+      long long next = -1;
+      // contributors' areas (and angles): all loads issued before any is used
+      float an[8], aa[8];
+#pragma unroll
+      for (int k = 1; k <= 8; ++k) {
+        const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
+        const bool in = (m >> (k - 1)) & 1u;
+        an[k - 1] = in ? __ldcg(a.area + ni) : 0.f;
+        if (DINF) aa[k - 1] = in ? a.ang[ni] : 0.f;
+      }
+      float val;
+      if (!DINF) {
+        // src/aread8.cpp:228-257
+        if (a.usew) { const float wv = a.w[ci]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
+        else val = 1.0f;
+#pragma unroll
+        for (int k = 1; k <= 8; ++k)
+          if ((m >> (k - 1)) & 1u) { if (nd_f(an[k - 1], -1.0f)) con = true; else val = val + an[k - 1]; }
+        if (con && a.contcheck) val = -1.0f;
+        a.area[ci] = val;
+        // src/aread8.cpp:261-272
+        const int d = (int)((nd >> 8) & 0xfu);
+        if (d >= 1 && d <= 8) {
+          const int rn = r + drow(d), cn = c + dcol(d);
+          if (s.on_grid(rn, cn)) {
+            const long long cin = s.idx(rn, cn);
+            if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); }
+            else if ((a.node[cin] & NODE_VALID) && dec_count(a.cntw, cin) == 1u) next = cin;
+          }
+        }
+      } else {
+        // src/areadinf.cpp:187-218
+        const float a0 = a.ang[ci];
+        val = 0.f;
+#pragma unroll
+        for (int k = 1; k <= 8; ++k)
+          if ((m >> (k - 1)) & 1u) {
+            const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
+            const Outflow o = dinf_outflow(aa[k - 1], a.theta[min(max(r - 1 + drow(k), 0), s.ny - 1)]);
+            const double p = o.k1 == kk ? o.p1 : o.p2;
+            if (nd_f(an[k - 1], -1.0f)) con = true; else val = (float)((double)val + p * (double)an[k - 1]);
+          }
+        if (a.usew) val = val + a.w[ci];
+        else val = (float)((double)val + a.dxc[r - 1]);
+        if (con && a.contcheck) val = -1.0f;
+        a.area[ci] = val;
+        // src/areadinf.cpp:221-239: every neighbour that receives a share
+        const Outflow o = dinf_outflow(a0, a.theta[r - 1]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int k = j == 0 ? o.k1 : o.k2;
+          if (k == 0) continue;
+          const int rn = r + drow(k), cn = c + dcol(k);
+          if (!s.on_grid(rn, cn)) continue;
+          const long long cin = s.idx(rn, cn);
+          if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
+          if (!(a.node[cin] & NODE_VALID)) continue;
+          if (dec_count(a.cntw, cin) == 1u) { if (next < 0) next = cin; else fork = cin; }
+        }
+      }
+      cur = next;
+    }
+    if (DINF) {
+      // ---- second ready receivers go to the warp's fork stack (idle lanes take them in the next iteration)
+      const unsigned fm = __ballot_sync(0xffffffffu, fork >= 0);
+      if (fm) {
+        const int nl = wqn[wid];
+        const int slot = nl + __popc(fm & lt);
+        if (fork >= 0) {
+          if (slot < WQ) wq[wid][slot] = fork;
+          else {
+            const unsigned long long g = atomicAdd(a.ctr + 1, 1ull);
+            if (g < a.spill_cap) a.spill[g] = fork; else a.ctr[2] = 1ull;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) wqn[wid] = min(WQ, nl + __popc(fm));
+        __syncwarp();
+      }
+    }
+  }
+}
+
+template <bool DINF>
+int walk_grid(unsigned long long n) {
+  static int per_dev = 0;
+  if (!per_dev) {
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_walk<DINF>, 256, 0) != cudaSuccess || occ < 1)
+      return 0;
+    per_dev = sms * occ;
+  }
+  return (int)std::min<unsigned long long>((unsigned long long)per_dev, (n + 255) / 256);
+}
+}  // namespace
+
+// Finishes a sweep from the current dependency state: every cell whose count is zero is evaluated and the
+// chains are followed until nothing is ready any more.  With from_sources the state is the one the
+// dependency stencil left (mode "walk"); otherwise the one a single pass of the tile kernel left ("hybrid").
+int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
+  WalkArgs a;
+  a.node = ctx->node.as<unsigned short>(); a.cntw = ctx->cnt.as<unsigned>();
+  a.area = area; a.w = w; a.ang = ang; a.s = s; a.usew = usew; a.contcheck = contcheck; a.w_nodata = w_nodata;
+  a.theta = theta; a.dxc = dxc; a.halo = halo;
+  a.ctr = ctx->d_ctr + 16;
+  unsigned long long* hc = ctx->h_ctr + 16;
+  const long long words = (long long)(s.pitch >> 2) * s.ny;
+  const unsigned blocks = (unsigned)((words + 255) / 256);
+  TD_CUDA(cudaMemsetAsync(a.ctr, 0, 4 * sizeof(unsigned long long), st));
+  k_ready<false><<<blocks, 256, 0, st>>>(a.cntw, a.node, s, a.ctr, nullptr);
+  TD_LAUNCHED();
+  TD_CUDA(cudaMemcpyAsync(hc, a.ctr, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  unsigned long long n = hc[3];
+  if (n == 0) return TD_OK;
+  TD_CUDA(ctx->listA.ensure(sizeof(long long) * n));
+  k_ready<true><<<blocks, 256, 0, st>>>(a.cntw, a.node, s, a.ctr, ctx->listA.as<long long>());
+  TD_LAUNCHED();
+  const unsigned long long cap = (unsigned long long)s.nx * s.ny / 16 + 65536;
+  if (dinf) { TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap)); TD_CUDA(ctx->listC.ensure(sizeof(long long) * cap)); }
+  const long long* cur = ctx->listA.as<long long>();
+  long long* spill = dinf ? ctx->listB.as<long long>() : nullptr;
+  long long* other = dinf ? ctx->listC.as<long long>() : nullptr;
+  for (;;) {
+    TD_CUDA(cudaMemsetAsync(a.ctr, 0, 3 * sizeof(unsigned long long), st));
+    a.list = cur; a.nlist = n; a.spill = spill; a.spill_cap = dinf ? cap : 0;
+    const int grid = dinf ? walk_grid<true>(n) : walk_grid<false>(n);
+    if (grid < 1) { set_error("walk kernel does not fit on an SM"); return TD_ERR_CUDA; }
+    if (dinf) k_walk<true><<<grid, 256, 0, st>>>(a); else k_walk<false><<<grid, 256, 0, st>>>(a);
+    TD_LAUNCHED();
+    TD_CUDA(cudaGetLastError());
+    if (!dinf) break;                    // D8 chains never fork: nothing can spill
+    TD_CUDA(cudaMemcpyAsync(hc, a.ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaStreamSynchronize(st));
+    if (hc[2]) { set_error("areadinf: ready-cell spill list exhausted"); return TD_ERR_ALLOC; }
+    n = hc[1];
+    if (n == 0) break;
+    cur = spill; std::swap(spill, other);
+  }
+  return TD_OK;
+}
+
+}  // namespace td

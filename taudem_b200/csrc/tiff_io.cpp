@@ -549,17 +549,39 @@ bool Writer::create(const std::string& path, uint32_t width, uint32_t height, DT
   return true;
 }
 
-bool Writer::flush_strip(uint64_t strip, const uint8_t* raw, size_t nbytes, std::string* err) {
-  std::vector<uint8_t> comp;
-  if (compression_ == 5) lzw_encode(raw, nbytes, &comp);
+bool Writer::flush_batch(std::string* err) {
+  // compress the queued strips on a small thread pool, then append them in strip order
+  const size_t n = batch_.size();
+  if (n == 0) return true;
+  std::vector<std::vector<uint8_t>> comp(n);
+  std::atomic<size_t> next{0};
+  std::atomic<bool> failed{false};
+  auto work = [&]() {
+    for (size_t i; (i = next.fetch_add(1)) < n;) {
+      const std::vector<uint8_t>& raw = batch_[i].second;
+      if (compression_ == 5) lzw_encode(raw.data(), raw.size(), &comp[i]);
+      else {
+        uLongf dl = compressBound((uLong)raw.size()); comp[i].resize(dl);
+        if (compress2(comp[i].data(), &dl, raw.data(), (uLong)raw.size(), 6) != Z_OK) { failed = true; return; }
+        comp[i].resize(dl);
+      }
+    }
+  };
+  const unsigned nthreads = (unsigned)std::min<size_t>(n, std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())));
+  if (nthreads <= 1) work();
   else {
-    uLongf dl = compressBound((uLong)nbytes); comp.resize(dl);
-    if (compress2(comp.data(), &dl, raw, (uLong)nbytes, 6) != Z_OK) { *err = "deflate failed"; return false; }
-    comp.resize(dl);
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
   }
-  if (fseeko(fp_, (off_t)append_pos_, SEEK_SET) != 0 || fwrite(comp.data(), 1, comp.size(), fp_) != comp.size()) { *err = "write failed"; return false; }
-  offsets_[strip] = append_pos_; counts_[strip] = comp.size();
-  append_pos_ += comp.size();
+  if (failed.load()) { *err = "deflate failed"; return false; }
+  if (fseeko(fp_, (off_t)append_pos_, SEEK_SET) != 0) { *err = "write failed"; return false; }
+  for (size_t i = 0; i < n; i++) {
+    if (fwrite(comp[i].data(), 1, comp[i].size(), fp_) != comp[i].size()) { *err = "write failed"; return false; }
+    offsets_[batch_[i].first] = append_pos_; counts_[batch_[i].first] = comp[i].size();
+    append_pos_ += comp[i].size();
+  }
+  batch_.clear();
   if (!big_ && append_pos_ > 0xffffffffull) { *err = "raster too large for classic TIFF"; return false; }
   return true;
 }
@@ -593,8 +615,9 @@ bool Writer::write_rows(long ystart, long nrows, const void* src, std::string* e
     }
     memcpy(pending_.data() + (size_t)(y - srow0) * rowb, (const uint8_t*)src + (size_t)r * src_stride * cb, rowb);
     if (y == srow0 + srows - 1) {
-      if (!flush_strip((uint64_t)s, pending_.data(), pending_.size(), err)) return false;
-      pending_row0_ = -1;
+      batch_.emplace_back((uint64_t)s, std::move(pending_));
+      pending_.clear(); pending_row0_ = -1;
+      if (batch_.size() >= 64 && !flush_batch(err)) return false;
     }
   }
   return true;
@@ -603,6 +626,7 @@ bool Writer::write_rows(long ystart, long nrows, const void* src, std::string* e
 bool Writer::close(std::string* err) {
   if (!fp_) return true;
   bool ok = true;
+  if (compression_ != 1) { std::string e; if (!flush_batch(&e)) ok = false; }
   const int osz = big_ ? 8 : 4;
   std::vector<uint8_t> ob(offsets_.size() * osz), cbuf(counts_.size() * osz);
   for (size_t i = 0; i < offsets_.size(); i++) {

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace tdio {
@@ -109,7 +110,8 @@ class Writer {
   std::vector<uint64_t> offsets_, counts_;
   std::vector<uint8_t> pending_;  // partial strip buffer for compressed output
   long pending_row0_ = -1;
-  bool flush_strip(uint64_t strip, const uint8_t* raw, size_t nbytes, std::string* err);
+  std::vector<std::pair<uint64_t, std::vector<uint8_t>>> batch_;  // finished raw strips awaiting compression
+  bool flush_batch(std::string* err);
 };
 
 // The reference's output naming rule (tiffIO.cpp:268-306): known extensions

@@ -144,6 +144,29 @@ def test_tile_sweep_equals_chain_sweep():
     assert res["tiles"][0].max() > 1e5
 
 
+@pytest.mark.skipif(__import__("os").environ.get("TAUDEM_B200_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental sweep schedules (hybrid / walk): set TAUDEM_B200_TEST_EXPERIMENTAL=1")
+def test_experimental_sweep_schedules_equal_tile_sweep():
+    """TAUDEM_B200_SWEEP=hybrid (one tile pass + warp-level chain walking) and =walk (chain walking from the
+    sources) are further schedules of the same gather: bit-identical to the default, with and without weights."""
+    import os
+    dem = synth.punch_holes(synth.gen_dem(2100, 3000, hurst=0.8, tilt=1.0, seed=9))
+    w = synth.gen_weights(*dem.shape)
+    fel = td.pitremove_grid(dem)
+    p, _ = td.d8flowdir_grid(fel)
+    ang, _ = td.dinfflowdir_grid(fel)
+    res = {}
+    for mode in ("tiles", "hybrid", "walk"):
+        os.environ["TAUDEM_B200_SWEEP"] = mode
+        try:
+            res[mode] = (td.aread8_grid(p), td.aread8_grid(p, weights=w, contcheck=False), td.areadinf_grid(ang), td.areadinf_grid(ang, weights=w, contcheck=False))
+        finally:
+            os.environ.pop("TAUDEM_B200_SWEEP", None)
+    for mode in ("hybrid", "walk"):
+        for a, b, what in zip(res["tiles"], res[mode], ("ad8", "ad8 -wg -nc", "sca", "sca -wg -nc")):
+            assert_bits(a, b, f"{mode}: {what}")
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_row_strip_partition_matches_single_strip(world):
     """Rank-count invariance of the row-strip partition: `world` processes, each owning
