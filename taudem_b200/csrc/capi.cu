@@ -55,13 +55,15 @@ int need_device() {
 //   hybrid : one pass of the tile kernel over every tile, then warp-level chain walking from the cells that
 //            are ready but not evaluated (sweep_walk.cu)
 //   walk   : warp-level chain walking from the sources alone
-enum SweepMode { SWEEP_TILES, SWEEP_CHAIN, SWEEP_HYBRID, SWEEP_WALK };
+//   levels : TAUDEM_B200_LEVELS (default 24) streaming level passes, then warp-level chain walking
+enum SweepMode { SWEEP_TILES, SWEEP_CHAIN, SWEEP_HYBRID, SWEEP_WALK, SWEEP_LEVELS };
 SweepMode sweep_mode() {
   const char* e = getenv("TAUDEM_B200_SWEEP");
   if (!e) return SWEEP_TILES;
   if (strcmp(e, "chain") == 0) return SWEEP_CHAIN;
   if (strcmp(e, "hybrid") == 0) return SWEEP_HYBRID;
   if (strcmp(e, "walk") == 0) return SWEEP_WALK;
+  if (strcmp(e, "levels") == 0) return SWEEP_LEVELS;
   return SWEEP_TILES;
 }
 bool chain_sweep() { return sweep_mode() == SWEEP_CHAIN; }
@@ -75,6 +77,11 @@ int sweep_alt(td_ctx* ctx, SweepMode mode, bool dinf, float* area, const float* 
     const int rc = td::sweep_run(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st);
     ctx->sweep_once = 0;
     if (rc) return rc;
+  }
+  if (mode == SWEEP_LEVELS) {
+    const char* e = getenv("TAUDEM_B200_LEVELS");
+    const int passes = e ? std::max(0, std::min(atoi(e), 4096)) : 24;
+    if (int rc = td::sweep_levels(ctx, dinf, passes, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st)) return rc;
   }
   return td::sweep_walk(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st);
 }
@@ -225,7 +232,7 @@ int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, flo
     return TD_OK;
   }
   const SweepMode mode = sweep_mode();
-  if (mode == SWEEP_HYBRID || mode == SWEEP_WALK)
+  if (mode != SWEEP_TILES && mode != SWEEP_CHAIN)
     return sweep_alt(ctx, mode, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, (cudaStream_t)stream);
   if (int rc = td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
   return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(),
@@ -249,7 +256,7 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   cudaStream_t st = (cudaStream_t)stream;
   const Strip ss(s);
   const SweepMode mode = sweep_mode();
-  if (mode == SWEEP_HYBRID || mode == SWEEP_WALK) return sweep_alt(ctx, mode, true, sca, w, ang, ss, 0.f, usew, contcheck, dxc, st);
+  if (mode != SWEEP_TILES && mode != SWEEP_CHAIN) return sweep_alt(ctx, mode, true, sca, w, ang, ss, 0.f, usew, contcheck, dxc, st);
   if (!chain_sweep()) {
     if (int rc = td::sweep_begin(ctx, ss, st)) return rc;
     return td::sweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);

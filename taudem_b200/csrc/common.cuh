@@ -53,6 +53,7 @@ struct Strip {
 // are not copied (their smem contents are never used for decisions: callers
 // test coordinates with Strip::on_grid first).
 // ----------------------------------------------------------------------------
+#ifndef TD_EMU   // (tests/emu compiles the queue / count protocols for the CPU; no TMA there)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -111,6 +112,8 @@ __device__ __forceinline__ void load_tile_tma(T* tile, uint64_t* bar, const T* _
   }
   mbar_wait(bar, 0);
 }
+
+#endif  // TD_EMU
 
 // launch accounting (bench gpu_launches)
 extern unsigned long long g_launches;

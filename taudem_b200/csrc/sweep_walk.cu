@@ -1,24 +1,27 @@
-// Contributing-area evaluation by chain walking in global memory, fed from a list of ready cells.
+// Contributing-area evaluation without tiles: level passes + chain walking in global memory.
 //
 // reference: aread8 main loop src/aread8.cpp:216-304, area() main loop src/areadinf.cpp:173-265
 // (queue of cells whose dependency count is zero; evaluate, decrement the receivers, push those that
 // reach zero).  The gather is k-ordered float32, evaluated once per cell when all contributors are final,
-// so the result does not depend on who evaluates a cell (same argument as sweep_tiles.cu).
+// so the result does not depend on who evaluates a cell or when (same argument as sweep_tiles.cu).
 //
-// Used in two ways (TAUDEM_B200_SWEEP, see capi.cu):
-//   hybrid : the tile kernel (sweep_tiles.cu) visits every tile exactly ONCE and evaluates what is
-//            ready inside it — the bulk of the grid, streamed through shared memory; what is left are the
-//            cells downstream of a tile crossing (a sparse channel network).  Those are finished here
-//            without re-loading tiles: k_ready_* collect the cells whose count is already zero, k_walk
-//            follows the chains from there.
-//   walk   : everything from the sources with k_walk alone (A/B reference for the bulk rate).
-//
-// k_walk: every lane of a warp owns one chain.  A lane evaluates its cell, releases the area, decrements
-// the receiver(s) with an acq_rel atomic and moves on when it was the last arrival.  Idle lanes refill
-// from the warp's own fork stack (D-infinity: a cell can make two receivers ready) and then from the
-// global ready list in batches (one fetch-add per warp).  No CTA-wide barrier and no inter-warp waiting:
-// a warp that holds one long river does not keep a whole CTA's worth of threads from other work.
-// A fork stack that overflows spills to a global list that the host drains with another launch.
+// Building blocks (combined by TAUDEM_B200_SWEEP, see capi.cu):
+//   k_level : one streaming pass over the count array.  The thread that OWNS a cell evaluates it when its
+//             count is zero, decrements the receivers and marks the cell done (0xFE); receivers that reach
+//             zero are picked up by their owners in this or the next pass.  A pass costs one byte per cell
+//             plus the work of the cells it evaluates, fully coalesced, no queue, no waiting.  Topological
+//             levels thin out fast (8192^2 fractal DEM: 91 % of the D8 cells and 76 % of the D-infinity
+//             cells lie in the first 16 levels), so a few dozen passes do the bulk of the grid.
+//   k_ready : collects the cells whose count is zero but which are not evaluated yet into a list.
+//   k_walk  : finishes from such a list by chain walking.  Every lane of a warp owns one chain: it evaluates
+//             its cell, releases the area, decrements the receiver(s) with an acq_rel atomic and moves on
+//             when it was the last arrival.  Idle lanes refill from the warp's own fork stack (D-infinity:
+//             a cell can make two receivers ready) and then from the global ready list in batches (one
+//             fetch-add per warp).  No CTA-wide barrier and no inter-warp waiting: a warp that holds one
+//             long river does not keep other threads from their work.  A fork stack that overflows spills to
+//             a global list that the host drains with another launch.
+// Modes: "levels" = K passes of k_level, then k_ready + k_walk;  "hybrid" = one visit of every tile by the
+// tile kernel (sweep_tiles.cu, `once`), then k_ready + k_walk;  "walk" = k_ready + k_walk from the sources.
 #include <algorithm>
 
 #include "ctx.h"
@@ -28,7 +31,10 @@
 namespace td {
 namespace {
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
-constexpr int WQ = 96;        // fork stack entries per warp
+#ifndef TD_WALK_WQ
+#define TD_WALK_WQ 96
+#endif
+constexpr int WQ = TD_WALK_WQ;   // fork stack entries per warp
 
 struct WalkArgs {
   const unsigned short* node;
@@ -53,8 +59,136 @@ __device__ __forceinline__ unsigned dec_count(unsigned* words, long long cell) {
   unsigned* a = words + (cell >> 2);
   const unsigned sh = (unsigned)(cell & 3) * 8u;
   unsigned old;
+#ifdef TD_EMU
+  old = atomicAdd(a, 0u - (1u << sh));
+#else
   asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
+#endif
   return (old >> sh) & 0xffu;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+#ifdef TD_EMU
+  v = __ldcg(p);
+#else
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+#endif
+  return v;
+}
+
+// Evaluates cell (r, c) = ci whose contributors are all final, stores its area and decrements the
+// receivers.  Receivers whose count reached zero through this decrement are returned in ready[0..1]
+// (with their node words) — the caller decides whether it follows them.
+template <bool DINF>
+__device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r, int c, unsigned nd, long long* ready, unsigned* ready_nd) {
+  const Strip& s = a.s;
+  const unsigned m = nd & 0xffu;
+  bool con = (nd & NODE_CON) != 0;
+  int nready = 0;
+  // contributors' areas (and angles): all loads are issued before any is used
+  float an[8], aa[8];
+#pragma unroll
+  for (int k = 1; k <= 8; ++k) {
+    const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
+    const bool in = (m >> (k - 1)) & 1u;
+    an[k - 1] = in ? __ldcg(a.area + ni) : 0.f;
+    if (DINF) aa[k - 1] = in ? a.ang[ni] : 0.f;
+  }
+  float val;
+  if (!DINF) {
+    // src/aread8.cpp:228-257
+    const int d = (int)((nd >> 8) & 0xfu);
+    long long cin = -1; unsigned ndn = 0; int rn = 0, cn = 0;
+    if (d >= 1 && d <= 8) {
+      rn = r + drow(d); cn = c + dcol(d);
+      if (s.on_grid(rn, cn)) { cin = s.idx(rn, cn); if (rn != 0 && rn != s.ny + 1) ndn = a.node[cin]; }
+    }
+    if (a.usew) { const float wv = a.w[ci]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
+    else val = 1.0f;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k)
+      if ((m >> (k - 1)) & 1u) { if (nd_f(an[k - 1], -1.0f)) con = true; else val = val + an[k - 1]; }
+    if (con && a.contcheck) val = -1.0f;
+    a.area[ci] = val;
+    // src/aread8.cpp:261-272
+    if (cin >= 0) {
+      if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); }
+      else if ((ndn & NODE_VALID) && dec_count(a.cntw, cin) == 1u) { ready[0] = cin; ready_nd[0] = ndn; nready = 1; }
+    }
+  } else {
+    // src/areadinf.cpp:187-218
+    const float a0 = a.ang[ci];
+    val = 0.f;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k)
+      if ((m >> (k - 1)) & 1u) {
+        const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
+        const Outflow o = dinf_outflow(aa[k - 1], a.theta[min(max(r - 1 + drow(k), 0), s.ny - 1)]);
+        const double p = o.k1 == kk ? o.p1 : o.p2;
+        if (nd_f(an[k - 1], -1.0f)) con = true; else val = (float)((double)val + p * (double)an[k - 1]);
+      }
+    if (a.usew) val = val + a.w[ci];
+    else val = (float)((double)val + a.dxc[r - 1]);
+    if (con && a.contcheck) val = -1.0f;
+    a.area[ci] = val;
+    // src/areadinf.cpp:221-239: every neighbour that receives a share
+    const Outflow o = dinf_outflow(a0, a.theta[r - 1]);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = j == 0 ? o.k1 : o.k2;
+      if (k == 0) continue;
+      const int rn = r + drow(k), cn = c + dcol(k);
+      if (!s.on_grid(rn, cn)) continue;
+      const long long cin = s.idx(rn, cn);
+      if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
+      const unsigned ndn = a.node[cin];
+      if (!(ndn & NODE_VALID)) continue;
+      if (dec_count(a.cntw, cin) == 1u) {
+        if (nready == 0) { ready[0] = cin; ready_nd[0] = ndn; } else { ready[1] = cin; ready_nd[1] = ndn; }
+        ++nready;
+      }
+    }
+  }
+  return nready;
+}
+
+// ---- level pass: one thread per 16 cells of a row (four count words)
+template <bool DINF>
+__global__ void __launch_bounds__(256) k_level(const WalkArgs a) {
+  const Strip& s = a.s;
+  const long long gpr = s.pitch >> 4;                                   // 16-cell groups per row (pitch % 32 == 0)
+  const long long gi = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (gi >= gpr * s.ny) return;
+  const int r = 1 + (int)(gi / gpr), c0 = (int)(gi - (long long)(r - 1) * gpr) * 16;
+  const long long base = s.idx(r, c0);
+  const uint4 q = __ldcg(reinterpret_cast<const uint4*>(a.cntw + (base >> 2)));
+  const unsigned w4[4] = {q.x, q.y, q.z, q.w};
+  unsigned todo = 0;                                                     // bit b: cell base + b is ready
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (((w4[j] - 0x01010101u) & ~w4[j] & 0x80808080u) == 0u) continue;  // no zero byte in this word
+    const unsigned word = ld_acquire(a.cntw + ((base + 4 * j) >> 2));    // the contributors' areas are visible after this
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (((word >> (8 * i)) & 0xffu) == 0u && c0 + 4 * j + i < s.nx) todo |= 1u << (4 * j + i);
+  }
+  unsigned d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll 1
+  while (todo) {
+    const int b = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const unsigned nd = a.node[base + b];
+    if (!(nd & NODE_VALID)) continue;
+    long long ready[2]; unsigned rnd[2];
+    eval_cell<DINF>(a, base + b, r, c0 + b, nd, ready, rnd);            // receivers wait for their owners
+    const unsigned bit = 0xfeu << (8 * (b & 3));
+    if ((b >> 2) == 0) d0 |= bit; else if ((b >> 2) == 1) d1 |= bit; else if ((b >> 2) == 2) d2 |= bit; else d3 |= bit;
+  }
+  unsigned* cw = a.cntw + (base >> 2);                                   // 0 -> 0xFE (evaluated)
+  if (d0) atomicAdd(cw, d0);
+  if (d1) atomicAdd(cw + 1, d1);
+  if (d2) atomicAdd(cw + 2, d2);
+  if (d3) atomicAdd(cw + 3, d3);
 }
 
 // ---- ready cells: count byte == 0 on an owned, valid cell.  One thread per count word (4 cells).
@@ -100,6 +234,8 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
   if (lane == 0) wqn[wid] = 0;
   __syncwarp();
   long long cur = -1;
+  unsigned curnd = 0;
+  bool have_nd = false;
   bool list_done = a.nlist == 0;        // warp-uniform
   for (;;) {
     // ---- refill idle lanes: the warp's fork stack first, then a batch of the global ready list
@@ -107,7 +243,7 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
     if (idle) {
       const int nl = wqn[wid];
       const int rank = __popc(idle & lt);
-      if (cur < 0 && rank < nl) cur = wq[wid][nl - 1 - rank];
+      if (cur < 0 && rank < nl) { cur = wq[wid][nl - 1 - rank]; have_nd = false; }
       __syncwarp();
       if (lane == 0) wqn[wid] = max(0, nl - __popc(idle));
       __syncwarp();
@@ -118,7 +254,7 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
         if (lane == 0) base = atomicAdd(a.ctr, (unsigned long long)need);
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned long long mine = base + (unsigned long long)__popc(idle & lt);
-        if (cur < 0 && mine < a.nlist) cur = a.list[mine];
+        if (cur < 0 && mine < a.nlist) { cur = a.list[mine]; have_nd = false; }
         if (base + (unsigned long long)need >= a.nlist) list_done = true;
       }
     }
@@ -129,70 +265,11 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
     if (cur >= 0) {
       const long long ci = cur;
       const int r = (int)(ci / s.pitch), c = (int)(ci - (long long)r * s.pitch);
-      const unsigned nd = a.node[ci];
-      const unsigned m = nd & 0xffu;
-      bool con = (nd & NODE_CON) != 0;
-      long long next = -1;
-      // contributors' areas (and angles): all loads issued before any is used
-      float an[8], aa[8];
-#pragma unroll
-      for (int k = 1; k <= 8; ++k) {
-        const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
-        const bool in = (m >> (k - 1)) & 1u;
-        an[k - 1] = in ? __ldcg(a.area + ni) : 0.f;
-        if (DINF) aa[k - 1] = in ? a.ang[ni] : 0.f;
-      }
-      float val;
-      if (!DINF) {
-        // src/aread8.cpp:228-257
-        if (a.usew) { const float wv = a.w[ci]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
-        else val = 1.0f;
-#pragma unroll
-        for (int k = 1; k <= 8; ++k)
-          if ((m >> (k - 1)) & 1u) { if (nd_f(an[k - 1], -1.0f)) con = true; else val = val + an[k - 1]; }
-        if (con && a.contcheck) val = -1.0f;
-        a.area[ci] = val;
-        // src/aread8.cpp:261-272
-        const int d = (int)((nd >> 8) & 0xfu);
-        if (d >= 1 && d <= 8) {
-          const int rn = r + drow(d), cn = c + dcol(d);
-          if (s.on_grid(rn, cn)) {
-            const long long cin = s.idx(rn, cn);
-            if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); }
-            else if ((a.node[cin] & NODE_VALID) && dec_count(a.cntw, cin) == 1u) next = cin;
-          }
-        }
-      } else {
-        // src/areadinf.cpp:187-218
-        const float a0 = a.ang[ci];
-        val = 0.f;
-#pragma unroll
-        for (int k = 1; k <= 8; ++k)
-          if ((m >> (k - 1)) & 1u) {
-            const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
-            const Outflow o = dinf_outflow(aa[k - 1], a.theta[min(max(r - 1 + drow(k), 0), s.ny - 1)]);
-            const double p = o.k1 == kk ? o.p1 : o.p2;
-            if (nd_f(an[k - 1], -1.0f)) con = true; else val = (float)((double)val + p * (double)an[k - 1]);
-          }
-        if (a.usew) val = val + a.w[ci];
-        else val = (float)((double)val + a.dxc[r - 1]);
-        if (con && a.contcheck) val = -1.0f;
-        a.area[ci] = val;
-        // src/areadinf.cpp:221-239: every neighbour that receives a share
-        const Outflow o = dinf_outflow(a0, a.theta[r - 1]);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int k = j == 0 ? o.k1 : o.k2;
-          if (k == 0) continue;
-          const int rn = r + drow(k), cn = c + dcol(k);
-          if (!s.on_grid(rn, cn)) continue;
-          const long long cin = s.idx(rn, cn);
-          if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
-          if (!(a.node[cin] & NODE_VALID)) continue;
-          if (dec_count(a.cntw, cin) == 1u) { if (next < 0) next = cin; else fork = cin; }
-        }
-      }
-      cur = next;
+      const unsigned nd = have_nd ? curnd : (unsigned)a.node[ci];
+      long long ready[2]; unsigned rnd[2];
+      const int nr = eval_cell<DINF>(a, ci, r, c, nd, ready, rnd);
+      if (nr >= 1) { cur = ready[0]; curnd = rnd[0]; have_nd = true; } else cur = -1;
+      if (DINF && nr == 2) fork = ready[1];
     }
     if (DINF) {
       // ---- second ready receivers go to the warp's fork stack (idle lanes take them in the next iteration)
@@ -227,18 +304,38 @@ int walk_grid(unsigned long long n) {
   }
   return (int)std::min<unsigned long long>((unsigned long long)per_dev, (n + 255) / 256);
 }
-}  // namespace
 
-// Finishes a sweep from the current dependency state: every cell whose count is zero is evaluated and the
-// chains are followed until nothing is ready any more.  With from_sources the state is the one the
-// dependency stencil left (mode "walk"); otherwise the one a single pass of the tile kernel left ("hybrid").
-int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
-               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
-  WalkArgs a;
+void walk_args(td_ctx* ctx, WalkArgs& a, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
+               int contcheck, const double* theta, const double* dxc, int* halo) {
   a.node = ctx->node.as<unsigned short>(); a.cntw = ctx->cnt.as<unsigned>();
   a.area = area; a.w = w; a.ang = ang; a.s = s; a.usew = usew; a.contcheck = contcheck; a.w_nodata = w_nodata;
   a.theta = theta; a.dxc = dxc; a.halo = halo;
+  a.list = nullptr; a.nlist = 0; a.spill = nullptr; a.spill_cap = 0;
   a.ctr = ctx->d_ctr + 16;
+}
+}  // namespace
+
+// `passes` streaming level passes over the strip (see k_level).
+int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w, const float* ang, const Strip& s, float w_nodata,
+                 int usew, int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
+  WalkArgs a;
+  walk_args(ctx, a, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo);
+  const long long groups = (long long)(s.pitch >> 4) * s.ny;
+  const unsigned blocks = (unsigned)((groups + 255) / 256);
+  for (int p = 0; p < passes; ++p) {
+    if (dinf) k_level<true><<<blocks, 256, 0, st>>>(a); else k_level<false><<<blocks, 256, 0, st>>>(a);
+    TD_LAUNCHED();
+  }
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// Finishes a sweep from the current dependency state: every cell whose count is zero is evaluated and the
+// chains are followed until nothing is ready any more.
+int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
+  WalkArgs a;
+  walk_args(ctx, a, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo);
   unsigned long long* hc = ctx->h_ctr + 16;
   const long long words = (long long)(s.pitch >> 2) * s.ny;
   const unsigned blocks = (unsigned)((words + 255) / 256);
