@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -67,24 +68,26 @@ SweepMode sweep_mode() {
   return SWEEP_TILES;
 }
 bool chain_sweep() { return sweep_mode() == SWEEP_CHAIN; }
-// hybrid / walk (see above); halo records cross-strip decrements exactly like the other sweeps
+// hybrid / walk / levels (see above).  `first`: the bulk phase (tile pass / level passes) runs once per dependency
+// state; later calls (after sweep_apply_plain delivered the neighbours' decrements) only walk from the new ready cells.
 int sweep_alt(td_ctx* ctx, SweepMode mode, bool dinf, float* area, const float* w, const float* ang, const td::Strip& s, float w_nodata,
-              int usew, int contcheck, const double* dxc, cudaStream_t st) {
+              int usew, int contcheck, const double* dxc, int* halo, bool first, cudaStream_t st) {
   const double* theta = dinf ? ctx->theta.as<double>() : nullptr;
-  if (mode == SWEEP_HYBRID) {
+  if (first && mode == SWEEP_HYBRID) {
     if (int rc = td::sweep_begin(ctx, s, st)) return rc;
     ctx->sweep_once = 1;
-    const int rc = td::sweep_run(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st);
+    const int rc = td::sweep_run(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st);
     ctx->sweep_once = 0;
     if (rc) return rc;
   }
-  if (mode == SWEEP_LEVELS) {
+  if (first && mode == SWEEP_LEVELS) {
     const char* e = getenv("TAUDEM_B200_LEVELS");
     const int passes = e ? std::max(0, std::min(atoi(e), 4096)) : 24;
-    if (int rc = td::sweep_levels(ctx, dinf, passes, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st)) return rc;
+    if (int rc = td::sweep_levels(ctx, dinf, passes, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st)) return rc;
   }
-  return td::sweep_walk(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, ctx->halo.as<int>(), st);
+  return td::sweep_walk(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st);
 }
+bool alt_mode(SweepMode m) { return m == SWEEP_HYBRID || m == SWEEP_WALK || m == SWEEP_LEVELS; }
 td_ctx* default_ctx() {
   static td_ctx* c = nullptr;
   if (!c) c = new td_ctx();
@@ -232,8 +235,8 @@ int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, flo
     return TD_OK;
   }
   const SweepMode mode = sweep_mode();
-  if (mode != SWEEP_TILES && mode != SWEEP_CHAIN)
-    return sweep_alt(ctx, mode, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, (cudaStream_t)stream);
+  if (alt_mode(mode))
+    return sweep_alt(ctx, mode, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, ctx->halo.as<int>(), true, (cudaStream_t)stream);
   if (int rc = td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
   return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(),
                        (cudaStream_t)stream);
@@ -256,7 +259,7 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   cudaStream_t st = (cudaStream_t)stream;
   const Strip ss(s);
   const SweepMode mode = sweep_mode();
-  if (mode != SWEEP_TILES && mode != SWEEP_CHAIN) return sweep_alt(ctx, mode, true, sca, w, ang, ss, 0.f, usew, contcheck, dxc, st);
+  if (alt_mode(mode)) return sweep_alt(ctx, mode, true, sca, w, ang, ss, 0.f, usew, contcheck, dxc, ctx->halo.as<int>(), true, st);
   if (!chain_sweep()) {
     if (int rc = td::sweep_begin(ctx, ss, st)) return rc;
     return td::sweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
@@ -289,20 +292,30 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
 // apply (decrements received from the neighbours for my first / last row)
 int td_sweep_begin_dev(td_ctx* ctx, td_strip s, void* stream) {
   if (int rc = check_strip(s)) return rc;
+  if (alt_mode(sweep_mode())) { ctx->sweep_first = 1; return TD_OK; }
   return td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream);
 }
 int td_sweep_apply_halo_dev(td_ctx* ctx, td_strip s, const int* dec_top, const int* dec_bot, void* stream) {
   if (int rc = check_strip(s)) return rc;
+  if (alt_mode(sweep_mode())) return td::sweep_apply_plain(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
   return td::sweep_apply_halo(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
 }
 int td_aread8_sweep_run_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, float w_nodata, int usew, int contcheck, int* halo_out,
                             void* stream) {
   if (int rc = check_strip(s)) return rc;
+  if (alt_mode(sweep_mode())) {
+    const bool first = ctx->sweep_first != 0; ctx->sweep_first = 0;
+    return sweep_alt(ctx, sweep_mode(), false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, halo_out, first, (cudaStream_t)stream);
+  }
   return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, halo_out, (cudaStream_t)stream);
 }
 int td_area_sweep_run_dev(td_ctx* ctx, const float* ang, const float* w, float* sca, td_strip s, int usew, int contcheck, const double* dxc,
                           int* halo_out, void* stream) {
   if (int rc = check_strip(s)) return rc;
+  if (alt_mode(sweep_mode())) {
+    const bool first = ctx->sweep_first != 0; ctx->sweep_first = 0;
+    return sweep_alt(ctx, sweep_mode(), true, sca, w, ang, Strip(s), 0.f, usew, contcheck, dxc, halo_out, first, (cudaStream_t)stream);
+  }
   return td::sweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
 }
 

@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
       const unsigned nd = have_nd ? curnd : (unsigned)a.node[ci];
       long long ready[2]; unsigned rnd[2];
       const int nr = eval_cell<DINF>(a, ci, r, c, nd, ready, rnd);
+      atomicAdd(a.cntw + (ci >> 2), 0xfeu << ((unsigned)(ci & 3) * 8u));     // 0 -> 0xFE (evaluated), like k_level and the tile kernel
       if (nr >= 1) { cur = ready[0]; curnd = rnd[0]; have_nd = true; } else cur = -1;
       if (DINF && nr == 2) fork = ready[1];
     }
@@ -289,6 +290,25 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
         __syncwarp();
       }
     }
+  }
+}
+
+// Dependency decrements received from the neighbour strips (addBorders, src/linearpart.h:314-328 and
+// src/aread8.cpp:283-297): dec_top[c] arrivals for the cell (row 1, c), dec_bot[c] for (row ny, c).  Cells
+// that reach zero are found by the next k_ready scan.
+__global__ void k_apply_plain(unsigned* __restrict__ cntw, const unsigned short* __restrict__ node, Strip s,
+                              const int* __restrict__ dec_top, const int* __restrict__ dec_bot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= s.nx) return;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int* dec = side == 0 ? dec_top : dec_bot;
+    if (dec == nullptr) continue;
+    const int d = dec[c];
+    if (d <= 0) continue;
+    const long long ci = s.idx(side == 0 ? 1 : s.ny, c);
+    if (!(node[ci] & NODE_VALID)) continue;
+    atomicAdd(cntw + (ci >> 2), 0u - ((unsigned)d << ((unsigned)(ci & 3) * 8u)));
   }
 }
 
@@ -314,6 +334,13 @@ void walk_args(td_ctx* ctx, WalkArgs& a, float* area, const float* w, const floa
   a.ctr = ctx->d_ctr + 16;
 }
 }  // namespace
+
+int sweep_apply_plain(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st) {
+  k_apply_plain<<<(s.nx + 255) / 256, 256, 0, st>>>(ctx->cnt.as<unsigned>(), ctx->node.as<unsigned short>(), s, dec_top, dec_bot);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
 
 // `passes` streaming level passes over the strip (see k_level).
 int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w, const float* ang, const Strip& s, float w_nodata,

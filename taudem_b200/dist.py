@@ -102,6 +102,9 @@ class DistTools:
                 peer = env == "1"
             else:
                 peer = dist.is_initialized() and dist.get_backend() == "nccl" and 2 <= world <= 4
+        # the level / walk / hybrid sweeps (TAUDEM_B200_SWEEP) exchange through the rounds below; peer mode is the tile kernel's
+        if os.environ.get("TAUDEM_B200_SWEEP") in ("levels", "walk", "hybrid"):
+            peer = False
         self.peer = bool(peer) and world > 1
         self._peer_cache = None
         self.rank, self.world = rank, world

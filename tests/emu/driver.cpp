@@ -23,82 +23,140 @@ td_ctx::~td_ctx() {
 using td::Strip;
 using td::dcol;
 using td::drow;
+#include <algorithm>
 
-extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float* out, const float* wgt, int nx, int ny, float dir_nodata,
-                         int usew, int contcheck, float w_nodata, double dx, double dy, unsigned long long seed) {
-  emu::g_rng = seed * 2654435761ull + 1;
-  td_strip ts; ts.nx = nx; ts.ny = ny; ts.pitch = (nx + 31) / 32 * 32; ts.has_top = 0; ts.has_bot = 0;
-  const Strip s(ts);
+namespace {
+// one row strip with its own dependency state, like one rank of taudem_b200/dist.py
+struct StripState {
+  Strip s;
+  std::vector<unsigned short> node;
+  std::vector<unsigned char> cnt;
+  std::vector<float> area, w, ang;
+  std::vector<short> p;
+  std::vector<double> theta, dxc;
+  std::vector<int> halo;
+  td_ctx ctx;
+  int row0 = 0;
+};
+
+void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int nx, int total_ny, int row0, int ny, float dir_nodata,
+                 double dx, double dy) {
+  td_strip ts; ts.nx = nx; ts.ny = ny; ts.pitch = (nx + 31) / 32 * 32; ts.has_top = row0 > 0; ts.has_bot = row0 + ny < total_ny;
+  S.s = Strip(ts); S.row0 = row0;
+  const Strip& s = S.s;
   const size_t n = (size_t)s.cells();
-  std::vector<unsigned short> node(n, 0);
-  std::vector<unsigned char> cnt((n + 3) / 4 * 4, 0xff);
-  std::vector<float> area(n, -1.0f), w(n, 0.f), ang(n, 0.f);
-  std::vector<short> p(n, 0);
-  std::vector<double> theta(2 * (size_t)ny), dxc(ny, dx);
-  for (int j = 0; j < ny; ++j) { theta[j] = atan2(dy, dx); theta[ny + j] = atan2(dx, dy); }
-  for (int r = 1; r <= ny; ++r)
+  S.node.assign(n, 0); S.cnt.assign((n + 3) / 4 * 4, 0xff);
+  S.area.assign(n, -1.0f); S.w.assign(n, 0.f); S.ang.assign(n, 0.f); S.p.assign(n, 0);
+  S.theta.assign(2 * (size_t)ny, 0.); S.dxc.assign(ny, dx); S.halo.assign(2 * (size_t)s.pitch, 0);
+  for (int j = 0; j < ny; ++j) { S.theta[j] = atan2(dy, dx); S.theta[ny + j] = atan2(dx, dy); }
+  for (int r = 0; r <= ny + 1; ++r) {               // halo rows hold the neighbours' directions (DistTools.share)
+    const int gr = row0 + r - 1;
+    if (gr < 0 || gr >= total_ny) continue;
     for (int c = 0; c < nx; ++c) {
-      const size_t o = (size_t)s.idx(r, c), src = (size_t)(r - 1) * nx + c;
-      if (dinf) ang[o] = ((const float*)dir)[src]; else p[o] = ((const short*)dir)[src];
-      if (wgt) w[o] = wgt[src];
+      const size_t o = (size_t)s.idx(r, c), src = (size_t)gr * nx + c;
+      if (dinf) S.ang[o] = ((const float*)dir)[src]; else S.p[o] = ((const short*)dir)[src];
+      if (wgt) S.w[o] = wgt[src];
     }
+  }
   const unsigned VALID = 0x8000u, CON = 0x1000u;
   if (!dinf) {
     const short nd = (short)dir_nodata;
     for (int r = 1; r <= ny; ++r)
       for (int c = 0; c < nx; ++c) {
-        const int d = p[s.idx(r, c)];
+        const int d = S.p[s.idx(r, c)];
         if (d == nd || d < 0 || d > 8) continue;
         unsigned mask = 0; bool con = false;
         for (int k = 1; k <= 8; ++k) {
           const int rn = r + drow(k), cn = c + dcol(k);
           const bool on = s.on_grid(rn, cn);
-          const int dn = on ? p[s.idx(rn, cn)] : nd;
+          const int dn = on ? S.p[s.idx(rn, cn)] : nd;
           const bool miss = !on || dn == nd;
           const bool toward = (dn - k == 4) || (dn - k == -4);
           const bool inrange = dn >= 0 && dn <= 8;
           if (!miss && toward && inrange) mask |= 1u << (k - 1);
           if (miss || (toward && !inrange)) con = true;
         }
-        node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | ((unsigned)d << 8) | mask);
-        cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
+        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | ((unsigned)d << 8) | mask);
+        S.cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
       }
   } else {
     std::vector<unsigned char> code(n, 0);
-    for (int r = 1; r <= ny; ++r)
+    for (int r = 0; r <= ny + 1; ++r)
       for (int c = 0; c < nx; ++c) {
-        const float av = ang[s.idx(r, c)];
+        if (!s.on_grid(r, c)) continue;
+        const float av = S.ang[s.idx(r, c)];
         if (fabsf(av - dir_nodata) < 1e-5f) continue;
-        const td::Outflow o = td::dinf_outflow(av, theta[r - 1]);
+        const td::Outflow o = td::dinf_outflow(av, S.theta[std::min(std::max(r - 1, 0), ny - 1)]);
         code[s.idx(r, c)] = (unsigned char)(o.k1 | (o.k2 << 4));
       }
     for (int r = 1; r <= ny; ++r)
       for (int c = 0; c < nx; ++c) {
-        if (fabsf(ang[s.idx(r, c)] - dir_nodata) < 1e-5f) continue;
+        if (fabsf(S.ang[s.idx(r, c)] - dir_nodata) < 1e-5f) continue;
         unsigned mask = 0; bool con = false;
         for (int k = 1; k <= 8; ++k) {
           const int rn = r + drow(k), cn = c + dcol(k);
-          if (!s.on_grid(rn, cn) || fabsf(ang[s.idx(rn, cn)] - dir_nodata) < 1e-5f) { con = true; continue; }
+          if (!s.on_grid(rn, cn) || fabsf(S.ang[s.idx(rn, cn)] - dir_nodata) < 1e-5f) { con = true; continue; }
           const int kk = k > 4 ? k - 4 : k + 4;
           const unsigned cd = code[s.idx(rn, cn)];
           if ((int)(cd & 15u) == kk || (int)(cd >> 4) == kk) mask |= 1u << (k - 1);
         }
-        node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask);
-        cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
+        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask);
+        S.cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
       }
   }
-  td_ctx ctx;
-  ctx.node.p = node.data(); ctx.node.cap = node.size() * 2;
-  ctx.cnt.p = cnt.data(); ctx.cnt.cap = cnt.size();
-  std::vector<int> halo(2 * (size_t)s.pitch, 0);
-  int rc = 0;
-  if (mode == 1)
-    rc = td::sweep_levels(&ctx, dinf != 0, passes, area.data(), usew ? w.data() : nullptr, ang.data(), s, w_nodata, usew, contcheck,
-                          theta.data(), dxc.data(), halo.data(), nullptr);
-  if (!rc)
-    rc = td::sweep_walk(&ctx, dinf != 0, area.data(), usew ? w.data() : nullptr, ang.data(), s, w_nodata, usew, contcheck, theta.data(),
-                        dxc.data(), halo.data(), nullptr);
-  for (int r = 1; r <= ny; ++r)
-    for (int c = 0; c < nx; ++c) out[(size_t)(r - 1) * nx + c] = area[s.idx(r, c)];
-  return rc;
+  S.ctx.node.p = S.node.data(); S.ctx.node.cap = S.node.size() * 2;
+  S.ctx.cnt.p = S.cnt.data(); S.ctx.cnt.cap = S.cnt.size();
+}
+}  // namespace
+
+// mode 0: k_ready + k_walk from the sources; mode 1: `passes` level passes first.  nstrips > 1 emulates the
+// exchange rounds of taudem_b200/dist.py::DistTools._sweep (linearpart partition, halo counts, area rows).
+extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float* out, const float* wgt, int nx, int ny, float dir_nodata,
+                         int usew, int contcheck, float w_nodata, double dx, double dy, unsigned long long seed, int nstrips, int* rounds_out) {
+  emu::g_rng = seed * 2654435761ull + 1;
+  if (nstrips < 1 || ny / nstrips < 1) return 1;
+  std::vector<StripState> S(nstrips);
+  const int per = ny / nstrips;
+  for (int i = 0; i < nstrips; ++i)
+    build_strip(S[i], dinf, dir, usew ? wgt : nullptr, nx, ny, i * per, i == nstrips - 1 ? ny - i * per : per, dir_nodata, dx, dy);
+  bool first = true;
+  int rounds = 0;
+  for (;;) {
+    for (auto& T : S) {
+      std::fill(T.halo.begin(), T.halo.end(), 0);
+      int rc = 0;
+      if (first && mode == 1)
+        rc = td::sweep_levels(&T.ctx, dinf != 0, passes, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew,
+                              contcheck, T.theta.data(), T.dxc.data(), T.halo.data(), nullptr);
+      if (!rc)
+        rc = td::sweep_walk(&T.ctx, dinf != 0, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew, contcheck,
+                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr);
+      if (rc) return rc;
+    }
+    first = false;
+    ++rounds;
+    long long handed = 0;
+    for (auto& T : S) for (int v : T.halo) handed += v;
+    // DistTools.share(out): my last owned row -> the halo row 0 of the strip below, my first owned row -> halo row ny+1 of the strip above
+    for (int i = 0; i + 1 < nstrips; ++i) {
+      StripState &A = S[i], &B = S[i + 1];
+      for (int c = 0; c < nx; ++c) {
+        B.area[B.s.idx(0, c)] = A.area[A.s.idx(A.s.ny, c)];
+        A.area[A.s.idx(A.s.ny + 1, c)] = B.area[B.s.idx(1, c)];
+      }
+    }
+    if (handed == 0) break;
+    for (int i = 0; i < nstrips; ++i) {
+      const int pitch = S[i].s.pitch;
+      const int* dec_top = i > 0 ? S[i - 1].halo.data() + pitch : nullptr;            // what the strip above sent down
+      const int* dec_bot = i + 1 < nstrips ? S[i + 1].halo.data() : nullptr;           // what the strip below sent up
+      if (int rc = td::sweep_apply_plain(&S[i].ctx, S[i].s, dec_top, dec_bot, nullptr)) return rc;
+    }
+    if (rounds > 10000) return 2;
+  }
+  if (rounds_out) *rounds_out = rounds;
+  for (auto& T : S)
+    for (int r = 1; r <= T.s.ny; ++r)
+      for (int c = 0; c < nx; ++c) out[(size_t)(T.row0 + r - 1) * nx + c] = T.area[T.s.idx(r, c)];
+  return 0;
 }

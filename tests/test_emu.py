@@ -23,7 +23,7 @@ def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
     src = open(os.path.join(CSRC, "sweep_walk.cu")).read()
     # kernel<<<grid, block, smem, stream>>>(args);  ->  emu_launch(grid, block, [&]{ kernel(args); });
-    src, n = re.subn(r"(k_\w+<\w+>)<<<([^,]+),\s*([^,]+),[^>]*>>>\(([^;]*)\);",
+    src, n = re.subn(r"(k_\w+(?:<\w+>)?)<<<([^,]+),\s*([^,]+),[^>]*>>>\(([^;]*)\);",
                      r"emu_launch(dim3(\2), dim3(\3), [&] { \1(\4); });", src)
     assert n >= 6, n
     inc = os.path.join(BUILD, "sweep_walk_emu.inc")
@@ -37,7 +37,7 @@ def _build(tag="", defines=()):
                                *[f"-D{d}" for d in defines], "-o", so, os.path.join(EMU, "driver.cpp"), os.path.join(EMU, "emu.cpp")])
     lib = C.CDLL(so)
     lib.emu_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
-                              C.c_float, C.c_double, C.c_double, C.c_ulonglong]
+                              C.c_float, C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_void_p]
     return lib
 
 
@@ -57,14 +57,14 @@ def fields():
     return port, p, ang, w
 
 
-def _run(lib, dinf, mode, passes, direction, w, contcheck, seed):
+def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, rounds=None):
     ny, nx = direction.shape
     out = np.empty((ny, nx), np.float32)
     d = np.ascontiguousarray(direction)
     wp = None if w is None else np.ascontiguousarray(w, np.float32)
     nodata = -3.4028234663852886e38 if dinf else -32768.0
     rc = lib.emu_sweep(int(dinf), mode, passes, d.ctypes.data, out.ctypes.data, None if wp is None else wp.ctypes.data, nx, ny, nodata,
-                       int(w is not None), int(contcheck), -9999.0, 30.0, 30.0, seed)
+                       int(w is not None), int(contcheck), -9999.0, 30.0, 30.0, seed, nstrips, None if rounds is None else rounds.ctypes.data)
     assert rc == 0
     return out
 
@@ -91,3 +91,17 @@ def test_emulated_dinf_fork_stack_spills_to_the_global_list(fields):
     lib = _build("_wq2", ["TD_WALK_WQ=2"])
     for mode, passes, seed in ((0, 0, 7), (1, 3, 8)):
         assert_bits(_run(lib, True, mode, passes, ang, None, True, seed), port.areadinf(ang), f"sca, spilling, mode {mode}")
+
+
+@pytest.mark.parametrize("nstrips", [2, 3])
+def test_emulated_row_strips_with_exchange_rounds(emu, fields, nstrips):
+    """The multi-strip protocol of the level / walk sweeps (halo decrement counts, area rows, plain apply, re-collection
+    of the ready cells each round) reproduces the single-strip rasters."""
+    port, p, ang, w = fields
+    rounds = np.zeros(1, np.int32)
+    assert_bits(_run(emu, False, 1, 3, p, None, True, 11, nstrips, rounds), port.aread8(p), "ad8 strips")
+    assert rounds[0] > 1
+    assert_bits(_run(emu, False, 0, 0, p, w, False, 12, nstrips), port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc strips")
+    assert_bits(_run(emu, True, 1, 3, ang, None, True, 13, nstrips, rounds), port.areadinf(ang), "sca strips")
+    assert rounds[0] > 1
+    assert_bits(_run(emu, True, 0, 0, ang, w, False, 14, nstrips), port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc strips")
