@@ -135,6 +135,28 @@ int td_d8_slopes_dev(td_ctx*, const float* fel, int16_t* p, float* sd8, td_strip
 int td_d8_flats_dev(td_ctx*, float* fel, int16_t* p, td_strip s, const double* dxc,
                     const double* dyc, long long* nflat_left, void* stream);
 
+/* The same over row strips (one per process).  The callbacks stand where the reference's
+ * resolveflats calls linearpart::share() and MPI_Allreduce (src/d8.cpp:459-680,
+ * src/linearpart.h:195-219); they are invoked on the calling thread with the stream
+ * synchronised, the pointers are DEVICE pointers.  Return 0 on success.
+ *   share     : first / last owned row of a strip array (ny+2 rows of pitch cells,
+ *               elem_bytes per cell) -> bottom / top halo row of the strips above / below
+ *   collect   : the reverse: my halo row 0 -> the strip above, my halo row ny+1 -> the strip
+ *               below; recv_top / recv_bot (pitch cells, NULL at the grid edge) receive what
+ *               the strips above / below hold in their halo rows for my first / last row
+ *   allreduce_sum : element-wise sum of v[0..n) over all strips (host memory)
+ * fel, p / ang must have current halo rows on entry; nflat_left is the global count.     */
+typedef struct td_strip_comm {
+  void* user;
+  int (*share)(void* user, void* strip_array, int elem_bytes);
+  int (*collect)(void* user, const void* strip_array, int elem_bytes, void* recv_top, void* recv_bot);
+  int (*allreduce_sum)(void* user, unsigned long long* v, int n);
+} td_strip_comm;
+int td_d8_flats_strip_dev(td_ctx*, float* fel, int16_t* p, td_strip s, const double* dxc, const double* dyc,
+                          long long* nflat_left, const td_strip_comm* comm, void* stream);
+int td_dinf_flats_strip_dev(td_ctx*, float* fel, float* ang, td_strip s, const double* dxc, const double* dyc,
+                            long long* nflat_left, const td_strip_comm* comm, void* stream);
+
 /* D-infinity: setPosDirDinf/SET2/VSLOPE stencil (src/dinf.cpp:530-595,317-373,286-313) */
 int td_dinf_slopes_dev(td_ctx*, const float* fel, float* ang, float* slp, td_strip s,
                        float fel_nodata, const double* dxc, const double* dyc,

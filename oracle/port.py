@@ -20,6 +20,7 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(_SO)
         _lib.orc_flood.argtypes = [_P, _P, _P, _I, _I, _F, _I]
+        _lib.orc_set_skip_flats.argtypes = [_I]
         _lib.orc_d8.argtypes = [_P, _P, _P, _I, _I, _F, _P, _P]
         _lib.orc_dinf.argtypes = [_P, _P, _P, _I, _I, _F, _P, _P]
         _lib.orc_aread8.argtypes = [_P, _P, _P, _I, _I, C.c_int16, _F, _I, _I]
@@ -44,7 +45,9 @@ def pitremove(dem, nodata=-9999.0, four_way=False, depmask=None):
     return out
 
 
-def d8flowdir(fel, nodata=-3.0e38, dx=30.0, dy=30.0):
+def d8flowdir(fel, nodata=-3.0e38, dx=30.0, dy=30.0, flats=True):
+    """flats=False: stop after the positive-slope stencil (flat cells keep direction 0)."""
+    lib().orc_set_skip_flats(0 if flats else 1)
     fel = np.ascontiguousarray(fel, np.float32); ny, nx = fel.shape
     p, sd8 = np.empty((ny, nx), np.int16), np.empty((ny, nx), np.float32)
     dxc, dyc = _rows(dx, ny), _rows(dy, ny)
@@ -52,7 +55,9 @@ def d8flowdir(fel, nodata=-3.0e38, dx=30.0, dy=30.0):
     return p, sd8
 
 
-def dinfflowdir(fel, nodata=-3.0e38, dx=30.0, dy=30.0):
+def dinfflowdir(fel, nodata=-3.0e38, dx=30.0, dy=30.0, flats=True):
+    """flats=False: stop after the facet stencil (flat cells keep angle -1)."""
+    lib().orc_set_skip_flats(0 if flats else 1)
     fel = np.ascontiguousarray(fel, np.float32); ny, nx = fel.shape
     ang, slp = np.empty((ny, nx), np.float32), np.empty((ny, nx), np.float32)
     dxc, dyc = _rows(dx, ny), _rows(dy, ny)

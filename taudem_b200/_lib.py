@@ -58,6 +58,8 @@ SIGNATURES = {
     "td_flood_relax_dev": (_I, [_P, _P, _P, Strip, _I, _P, _P]),
     "td_d8_slopes_dev": (_I, [_P, _P, _P, _P, Strip, _F, _P, _P, _P, _P]),
     "td_d8_flats_dev": (_I, [_P, _P, _P, Strip, _P, _P, _P, _P]),
+    "td_d8_flats_strip_dev": (_I, [_P, _P, _P, Strip, _P, _P, _P, _P, _P]),
+    "td_dinf_flats_strip_dev": (_I, [_P, _P, _P, Strip, _P, _P, _P, _P, _P]),
     "td_dinf_slopes_dev": (_I, [_P, _P, _P, _P, Strip, _F, _P, _P, _P, _P]),
     "td_dinf_flats_dev": (_I, [_P, _P, _P, Strip, _P, _P, _P, _P]),
     "td_aread8_deps_dev": (_I, [_P, _P, _P, Strip, C.c_int16, _P]),

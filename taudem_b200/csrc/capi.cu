@@ -164,7 +164,15 @@ int td_d8_flats_dev(td_ctx* ctx, float* fel, int16_t* p, td_strip s, const doubl
                     void* stream) {
   if (int rc = check_strip(s)) return rc;
   long long left = 0;
-  int rc = td::resolve_flats_d8(ctx, fel, p, Strip(s), dxc, dyc, &left, (cudaStream_t)stream);
+  int rc = td::resolve_flats_d8(ctx, fel, p, Strip(s), dxc, dyc, &left, nullptr, (cudaStream_t)stream);
+  if (nflat_left) *nflat_left = left;
+  return rc;
+}
+int td_d8_flats_strip_dev(td_ctx* ctx, float* fel, int16_t* p, td_strip s, const double* dxc, const double* dyc, long long* nflat_left,
+                          const td_strip_comm* comm, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  long long left = 0;
+  int rc = td::resolve_flats_d8(ctx, fel, p, Strip(s), dxc, dyc, &left, comm, (cudaStream_t)stream);
   if (nflat_left) *nflat_left = left;
   return rc;
 }
@@ -205,7 +213,18 @@ int td_dinf_flats_dev(td_ctx* ctx, float* fel, float* ang, td_strip s, const dou
   if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
   const double* thA = ctx->theta.as<double>();
   long long left = 0;
-  int rc = td::resolve_flats_dinf(ctx, fel, ang, Strip(s), dxc, dyc, thA, thA + s.ny, &left, st);
+  int rc = td::resolve_flats_dinf(ctx, fel, ang, Strip(s), dxc, dyc, thA, thA + s.ny, &left, nullptr, st);
+  if (nflat_left) *nflat_left = left;
+  return rc;
+}
+int td_dinf_flats_strip_dev(td_ctx* ctx, float* fel, float* ang, td_strip s, const double* dxc, const double* dyc, long long* nflat_left,
+                            const td_strip_comm* comm, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
+  const double* thA = ctx->theta.as<double>();
+  long long left = 0;
+  int rc = td::resolve_flats_dinf(ctx, fel, ang, Strip(s), dxc, dyc, thA, thA + s.ny, &left, comm, st);
   if (nflat_left) *nflat_left = left;
   return rc;
 }

@@ -19,6 +19,13 @@
 // (float)elev2 before the next outer iteration — all exactly as the reference does.
 // Frontiers are int64 cell-index lists appended with warp-aggregated atomics; one
 // kernel launch per BFS level, total work O(|F|).
+//
+// Row strips (one per process, src/linearpart.h): every strip runs the same loop on its own flat cells; the
+// caller supplies three callbacks (td_strip_comm: share edge rows, collect halo rows, all-reduce) that stand
+// where the reference calls share()/MPI_Allreduce in resolveflats.  A BFS level may claim a cell of the
+// neighbour strip: the claim is made on the local halo copy of lev / mk, sent to the owner, merged there
+// (k_merge appends the cell to the owner's frontier) and the owner's edge row is shared back, so that the
+// levels — and with them T, U and every elev2 — are those of the undivided grid.
 #include <vector>
 
 #include "ctx.h"
@@ -118,7 +125,7 @@ __global__ void k_gather(const long long* __restrict__ list, unsigned long long 
 // equal-elevation, non-crossing link to the frontier cell stops at level t.
 template <class P>
 __global__ void k_expand_fall(const long long* __restrict__ fr, unsigned long long n, int t, const float* __restrict__ elev,
-                              const typename P::DirT* __restrict__ dir, int* __restrict__ lev, int pitch,
+                              const typename P::DirT* __restrict__ dir, int* __restrict__ lev, int pitch, int ny,
                               long long* __restrict__ out, unsigned long long* __restrict__ ctr) {
   const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = tid < n;
@@ -131,6 +138,7 @@ __global__ void k_expand_fall(const long long* __restrict__ fr, unsigned long lo
     if (in && lev[ci] == UNASSIGNED) {
       const int k = kk > 4 ? kk - 4 : kk + 4;  // direction from c back to the frontier cell
       if (elev[ci] - zn == 0 && !dont_cross<P>(dir, ci, pitch, k)) push = atomicCAS(lev + ci, UNASSIGNED, t) == UNASSIGNED;
+      if (ci < pitch || ci >= (long long)(ny + 1) * pitch) push = false;   // a cell of the neighbour strip: its owner appends it (k_merge)
     }
     append(out, ctr, push, ci);
   }
@@ -138,7 +146,7 @@ __global__ void k_expand_fall(const long long* __restrict__ fr, unsigned long lo
 
 // rise BFS: any flat neighbour of a cell marked in pass u-1 is marked in pass u (src/d8.cpp:611-618)
 __global__ void k_expand_rise(const long long* __restrict__ fr, unsigned long long n, int u, const int* __restrict__ lev,
-                              int* __restrict__ mk, int pitch, long long* __restrict__ out, unsigned long long* __restrict__ ctr) {
+                              int* __restrict__ mk, int pitch, int ny, long long* __restrict__ out, unsigned long long* __restrict__ ctr) {
   const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = tid < n;
   const long long ni = in ? fr[tid] : 0;
@@ -147,6 +155,7 @@ __global__ void k_expand_rise(const long long* __restrict__ fr, unsigned long lo
     bool push = false;
     const long long ci = ni + (long long)drow(kk) * pitch + dcol(kk);
     if (in && lev[ci] != 0 && mk[ci] == 0) push = atomicCAS(mk + ci, 0, u) == 0;
+    if (ci < pitch || ci >= (long long)(ny + 1) * pitch) push = false;     // neighbour strip's cell: see k_merge
     append(out, ctr, push, ci);
   }
 }
@@ -279,13 +288,38 @@ __global__ void k_reset(const long long* __restrict__ list, unsigned long long n
   if (t < n) { lev[list[t]] = 0; mk[list[t]] = 0; }
 }
 
+// Claims the neighbour strips made on their halo copies of my first / last row during BFS level t:
+// recv_top[c] / recv_bot[c] = the neighbour's lev (FALL) or mk (rise) value for (row 1, c) / (row ny, c).
+template <bool FALL>
+__global__ void k_merge(const int* __restrict__ recv_top, const int* __restrict__ recv_bot, Strip s, int t, int* __restrict__ lev,
+                        int* __restrict__ mk, long long* __restrict__ out, unsigned long long* __restrict__ ctr) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = c < s.nx;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int* recv = side == 0 ? recv_top : recv_bot;
+    const long long ci = s.idx(side == 0 ? 1 : s.ny, in ? c : 0);
+    bool push = false;
+    if (in && recv != nullptr && recv[c] == t) {
+      if (FALL) { if (lev[ci] == UNASSIGNED) { lev[ci] = t; push = true; } }
+      else if (lev[ci] != 0 && mk[ci] == 0) { mk[ci] = t; push = true; }
+    }
+    append(out, ctr, push, ci);
+  }
+}
+
 inline unsigned nblk(unsigned long long n) { return (unsigned)((n + 255) / 256); }
 
 struct Geo { const double *dxc, *dyc, *thA, *thB; };
 
 template <class P>
-int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& s, const Geo& g, long long* nleft, cudaStream_t st) {
-  if (s.has_top || s.has_bot) { set_error("flat resolution is implemented for a single strip"); return TD_ERR_ARG; }
+int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& s, const Geo& g, long long* nleft,
+                  const td_strip_comm* comm, cudaStream_t st) {
+  const bool multi = s.has_top || s.has_bot;
+  if (multi && (!comm || !comm->share || !comm->collect || !comm->allreduce_sum)) {
+    set_error("flat resolution over row strips needs the td_strip_comm callbacks"); return TD_ERR_ARG;
+  }
+  if (!multi) comm = nullptr;
   const size_t ncell = (size_t)s.cells();
   unsigned long long* dc = ctx->d_ctr;   // [0] list append, [1] frontier append
   auto read_ctr = [&](int i, unsigned long long* v) -> cudaError_t {
@@ -294,6 +328,29 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
     e = cudaStreamSynchronize(st);
     *v = ctx->h_ctr[i];
     return e;
+  };
+  // the three places where the reference's resolveflats talks to the other ranks
+  auto gsum = [&](unsigned long long v, unsigned long long* out) -> int {
+    *out = v;
+    if (comm && comm->allreduce_sum(comm->user, out, 1) != 0) { set_error("td_strip_comm.allreduce_sum failed"); return TD_ERR_ARG; }
+    return TD_OK;
+  };
+  auto share = [&](void* arr, int elem) -> int {
+    if (!comm) return TD_OK;
+    TD_CUDA(cudaStreamSynchronize(st));
+    if (comm->share(comm->user, arr, elem) != 0) { set_error("td_strip_comm.share failed"); return TD_ERR_ARG; }
+    return TD_OK;
+  };
+  int* recv_top = nullptr; int* recv_bot = nullptr;
+  if (multi) {
+    TD_CUDA(ctx->halo.ensure(sizeof(int) * 2 * (size_t)s.pitch));
+    if (s.has_top) recv_top = ctx->halo.as<int>();
+    if (s.has_bot) recv_bot = ctx->halo.as<int>() + s.pitch;
+  }
+  auto collect = [&](const void* arr) -> int {      // halo rows -> owners (recv_top / recv_bot)
+    TD_CUDA(cudaStreamSynchronize(st));
+    if (comm->collect(comm->user, arr, 4, recv_top, recv_bot) != 0) { set_error("td_strip_comm.collect failed"); return TD_ERR_ARG; }
+    return TD_OK;
   };
   // --- collect the flat cells (first call of the reference: src/d8.cpp:492-503)
   // worst case every cell is flat; size lists by a counting pass
@@ -304,14 +361,15 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
     k_collect<P><<<grid, 256, 0, st>>>(dir, s, ctx->listA.as<long long>(), dc);
     TD_LAUNCHED();
   }
-  unsigned long long n = 0;
+  unsigned long long n = 0, ntot = 0;      // flat cells of this strip / of the whole grid
   TD_CUDA(read_ctr(0, &n));
-  *nleft = (long long)n;
-  if (n == 0) return TD_OK;
+  if (int rc = gsum(n, &ntot)) return rc;
+  *nleft = (long long)ntot;
+  if (ntot == 0) return TD_OK;
   TD_CUDA(ctx->lev.ensure(ncell * 4));
   TD_CUDA(ctx->mk.ensure(ncell * 4));
-  TD_CUDA(ctx->listB.ensure(sizeof(long long) * n));
-  TD_CUDA(ctx->listC.ensure(sizeof(long long) * n));
+  TD_CUDA(ctx->listB.ensure(sizeof(long long) * (n + 1)));
+  TD_CUDA(ctx->listC.ensure(sizeof(long long) * (n + 1)));
   TD_CUDA(cudaMemsetAsync(ctx->lev.p, 0, ncell * 4, st));
   TD_CUDA(cudaMemsetAsync(ctx->mk.p, 0, ncell * 4, st));
   int* lev = ctx->lev.as<int>();
@@ -319,82 +377,112 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
   long long* cur = ctx->listA.as<long long>();
   long long* nxt = ctx->listB.as<long long>();
   long long* fr = ctx->listC.as<long long>();
+  const unsigned colblk = (unsigned)((s.nx + 255) / 256);
 
-  unsigned long long last = n + 1;
+  unsigned long long last = ntot + 1;
   // outer loop: src/d8.cpp:302-317
-  while (n > 0 && n < last) {
-    last = n;
-    k_mark<<<nblk(n), 256, 0, st>>>(cur, n, lev); TD_LAUNCHED();
-    k_classify<P><<<nblk(n), 256, 0, st>>>(cur, n, elev, dir, lev, mk, s.pitch); TD_LAUNCHED();
+  while (ntot > 0 && ntot < last) {
+    last = ntot;
+    if (n) { k_mark<<<nblk(n), 256, 0, st>>>(cur, n, lev); TD_LAUNCHED(); }
+    if (int rc = share(lev, 4)) return rc;                       // who is in the flat set on the other side of the boundary
+    if (n) { k_classify<P><<<nblk(n), 256, 0, st>>>(cur, n, elev, dir, lev, mk, s.pitch); TD_LAUNCHED(); }
+    if (int rc = share(lev, 4)) return rc;
+    if (int rc = share(mk, 4)) return rc;
     // ---- fall BFS
     TD_CUDA(cudaMemsetAsync(dc + 1, 0, sizeof(unsigned long long), st));
-    k_gather<<<nblk(n), 256, 0, st>>>(cur, n, lev, 1, fr, dc + 1); TD_LAUNCHED();
-    unsigned long long lo = 0, hi = 0;
+    if (n) { k_gather<<<nblk(n), 256, 0, st>>>(cur, n, lev, 1, fr, dc + 1); TD_LAUNCHED(); }
+    unsigned long long lo = 0, hi = 0, hitot = 0;
     TD_CUDA(read_ctr(1, &hi));
+    if (int rc = gsum(hi, &hitot)) return rc;
     int T = 1;
-    if (hi != n) {
+    if (hitot != ntot) {
       // pass 2: seeds (equal neighbour outside F) + expansion of level 1
-      k_gather<<<nblk(n), 256, 0, st>>>(cur, n, lev, 2, fr, dc + 1); TD_LAUNCHED();
+      if (n) { k_gather<<<nblk(n), 256, 0, st>>>(cur, n, lev, 2, fr, dc + 1); TD_LAUNCHED(); }
       int t = 2;
       for (;;) {
-        if (hi > lo) { k_expand_fall<P><<<nblk(hi - lo), 256, 0, st>>>(fr + lo, hi - lo, t, elev, dir, lev, s.pitch, fr, dc + 1); TD_LAUNCHED(); }
-        unsigned long long end = 0;
+        if (hi > lo) { k_expand_fall<P><<<nblk(hi - lo), 256, 0, st>>>(fr + lo, hi - lo, t, elev, dir, lev, s.pitch, s.ny, fr, dc + 1); TD_LAUNCHED(); }
+        if (multi) {
+          if (int rc = collect(lev)) return rc;
+          k_merge<true><<<colblk, 256, 0, st>>>(recv_top, recv_bot, s, t, lev, mk, fr, dc + 1); TD_LAUNCHED();
+          if (int rc = share(lev, 4)) return rc;
+        }
+        unsigned long long end = 0, nt = 0;
         TD_CUDA(read_ctr(1, &end));
         // level t occupies [hi', end): for t == 2 the seeds were appended before the expansion
-        const unsigned long long nt = end - hi;
+        if (int rc = gsum(end - hi, &nt)) return rc;
         if (nt == 0) { T = t; break; }
         lo = hi; hi = end; ++t;
       }
     }
     // ---- rise BFS
     TD_CUDA(cudaMemsetAsync(dc + 1, 0, sizeof(unsigned long long), st));
-    k_gather<<<nblk(n), 256, 0, st>>>(cur, n, mk, 1, fr, dc + 1); TD_LAUNCHED();
+    if (n) { k_gather<<<nblk(n), 256, 0, st>>>(cur, n, mk, 1, fr, dc + 1); TD_LAUNCHED(); }
     lo = 0; hi = 0;
     TD_CUDA(read_ctr(1, &hi));
+    if (int rc = gsum(hi, &hitot)) return rc;
     int U = 1;
-    if (hi > 0) {
+    if (hitot > 0) {
       int u = 2;
       for (;;) {
-        k_expand_rise<<<nblk(hi - lo), 256, 0, st>>>(fr + lo, hi - lo, u, lev, mk, s.pitch, fr, dc + 1); TD_LAUNCHED();
-        unsigned long long end = 0;
+        if (hi > lo) { k_expand_rise<<<nblk(hi - lo), 256, 0, st>>>(fr + lo, hi - lo, u, lev, mk, s.pitch, s.ny, fr, dc + 1); TD_LAUNCHED(); }
+        if (multi) {
+          if (int rc = collect(mk)) return rc;
+          k_merge<false><<<colblk, 256, 0, st>>>(recv_top, recv_bot, s, u, lev, mk, fr, dc + 1); TD_LAUNCHED();
+          if (int rc = share(mk, 4)) return rc;
+        }
+        unsigned long long end = 0, nu = 0;
         TD_CUDA(read_ctr(1, &end));
-        if (end == hi) { U = u; break; }
+        if (int rc = gsum(end - hi, &nu)) return rc;
+        if (nu == 0) { U = u; break; }
         lo = hi; hi = end; ++u;
       }
     }
     // ---- combine, set directions, collect what is still flat
-    k_combine<P><<<nblk(n), 256, 0, st>>>(cur, n, lev, mk, dir, T, U); TD_LAUNCHED();
+    if (n) { k_combine<P><<<nblk(n), 256, 0, st>>>(cur, n, lev, mk, dir, T, U); TD_LAUNCHED(); }
+    if (int rc = share(lev, 4)) return rc;                        // elev2 of the neighbours' edge cells
+    if (int rc = share(dir, (int)sizeof(typename P::DirT))) return rc;   // pits marked by k_combine
     TD_CUDA(cudaMemsetAsync(dc, 0, sizeof(unsigned long long), st));
-    if constexpr (sizeof(typename P::DirT) == 2)
-      k_setflow2<<<nblk(n), 256, 0, st>>>(cur, n, elev, lev, mk, (short*)dir, s, g.dxc, g.dyc, nxt, dc);
-    else
-      k_set2_flat<<<nblk(n), 256, 0, st>>>(cur, n, elev, lev, mk, (float*)dir, s, g.dxc, g.dyc, g.thA, g.thB, nxt, dc);
-    TD_LAUNCHED();
-    unsigned long long nn = 0;
-    TD_CUDA(read_ctr(0, &nn));
-    if (nn > 0) {
-      dim3 grid(s.ny, (s.nx + 255) / 256);
-      k_overwrite<<<grid, 256, 0, st>>>(elev, lev, s); TD_LAUNCHED();
+    if (n) {
+      if constexpr (sizeof(typename P::DirT) == 2)
+        k_setflow2<<<nblk(n), 256, 0, st>>>(cur, n, elev, lev, mk, (short*)dir, s, g.dxc, g.dyc, nxt, dc);
+      else
+        k_set2_flat<<<nblk(n), 256, 0, st>>>(cur, n, elev, lev, mk, (float*)dir, s, g.dxc, g.dyc, g.thA, g.thB, nxt, dc);
+      TD_LAUNCHED();
     }
-    k_reset<<<nblk(n), 256, 0, st>>>(cur, n, lev, mk); TD_LAUNCHED();
+    unsigned long long nn = 0, nntot = 0;
+    TD_CUDA(read_ctr(0, &nn));
+    if (int rc = gsum(nn, &nntot)) return rc;
+    if (int rc = share(dir, (int)sizeof(typename P::DirT))) return rc;   // the directions just set (dontCross of the next iteration)
+    if (nntot > 0) {
+      dim3 grid(s.ny, colblk);
+      k_overwrite<<<grid, 256, 0, st>>>(elev, lev, s); TD_LAUNCHED();
+      if (int rc = share(elev, 4)) return rc;
+    }
+    if (n) { k_reset<<<nblk(n), 256, 0, st>>>(cur, n, lev, mk); TD_LAUNCHED(); }
+    if (multi) {        // the halo copies of lev / mk are reset with their owners' cells
+      TD_CUDA(cudaMemsetAsync(lev, 0, sizeof(int) * (size_t)s.pitch, st));
+      TD_CUDA(cudaMemsetAsync(mk, 0, sizeof(int) * (size_t)s.pitch, st));
+      TD_CUDA(cudaMemsetAsync(lev + (size_t)(s.ny + 1) * s.pitch, 0, sizeof(int) * (size_t)s.pitch, st));
+      TD_CUDA(cudaMemsetAsync(mk + (size_t)(s.ny + 1) * s.pitch, 0, sizeof(int) * (size_t)s.pitch, st));
+    }
     std::swap(cur, nxt);
-    n = nn;
+    n = nn; ntot = nntot;
   }
   TD_CUDA(cudaGetLastError());
-  *nleft = (long long)n;
+  *nleft = (long long)ntot;
   return TD_OK;
 }
 }  // namespace
 
 int resolve_flats_d8(td_ctx* ctx, float* elev, short* dir, const Strip& s, const double* dxc, const double* dyc, long long* nleft,
-                     cudaStream_t st) {
+                     const td_strip_comm* comm, cudaStream_t st) {
   Geo g{dxc, dyc, nullptr, nullptr};
-  return resolve_flats<D8Pol>(ctx, elev, dir, s, g, nleft, st);
+  return resolve_flats<D8Pol>(ctx, elev, dir, s, g, nleft, comm, st);
 }
 int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, const double* dxc, const double* dyc, const double* thA,
-                       const double* thB, long long* nleft, cudaStream_t st) {
+                       const double* thB, long long* nleft, const td_strip_comm* comm, cudaStream_t st) {
   Geo g{dxc, dyc, thA, thB};
-  return resolve_flats<DinfPol>(ctx, elev, ang, s, g, nleft, st);
+  return resolve_flats<DinfPol>(ctx, elev, ang, s, g, nleft, comm, st);
 }
 
 }  // namespace td

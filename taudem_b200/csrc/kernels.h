@@ -9,9 +9,9 @@ cudaError_t launch_dinf_stencil(const float* elev, float* ang, float* slp, const
                                 const double* thA, const double* thB, const Strip& s, float nodata,
                                 unsigned long long* nflat, cudaStream_t st);
 int resolve_flats_d8(td_ctx* ctx, float* elev, short* dir, const Strip& s, const double* dxc, const double* dyc,
-                     long long* nleft, cudaStream_t st);
+                     long long* nleft, const td_strip_comm* comm, cudaStream_t st);
 int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, const double* dxc, const double* dyc,
-                       const double* thA, const double* thB, long long* nleft, cudaStream_t st);
+                       const double* thA, const double* thB, long long* nleft, const td_strip_comm* comm, cudaStream_t st);
 cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
                            short nodata, cudaStream_t st);
 cudaError_t launch_sweep_d8(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,

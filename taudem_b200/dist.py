@@ -220,10 +220,11 @@ class DistTools:
         self.share(fel)
         return self.T.dinf_slopes(self.s, fel, dxc, dyc, nodata)
 
-    # ---- flow directions incl. flats.  The Garbrecht-Martz BFS is run REPLICATED this round: the strips
-    # of fel and of the positive-slope directions are all-gathered, every rank resolves the flats of the
-    # whole grid with the single-strip kernels and keeps its own rows (bit-identical by construction;
-    # a BFS with one halo exchange per level is the planned replacement).
+    # ---- flow directions incl. flats.  Default: the Garbrecht-Martz BFS runs REPLICATED — the strips of fel and of
+    # the positive-slope directions are all-gathered, every rank resolves the flats of the whole grid with the
+    # single-strip kernels and keeps its own rows (bit-identical by construction).  TAUDEM_B200_FLATS=strips
+    # selects the partitioned BFS (_flats_strips: one exchange per level; its protocol is checked against the
+    # oracle on the CPU emulation, tests/test_emu.py; it becomes the default once it has run on GPUs).
     def gather_full(self, t):
         """All-gather of the owned rows of a strip tensor -> full-grid strip tensor (halo rows unused)."""
         from .device import DeviceStrip
@@ -248,10 +249,79 @@ class DistTools:
             full[1 + row0:1 + row0 + n].copy_(b[:n])
         return sf, full
 
+    def _flats_strips(self, fel, d, dxc, dyc, dinf):
+        """Flat resolution on the row strips themselves (TAUDEM_B200_FLATS=strips): every rank runs the BFS loop of
+        flats.cu on its own flat cells; the td_strip_comm callbacks below do what resolveflats does with
+        linearpart::share() and MPI_Allreduce — one collect + share + all-reduce per BFS level."""
+        import ctypes as C
+        s, dev = self.s, self.s.device
+        rank, world, ny = self.rank, self.world, self.ny
+
+        class _Dev:                                   # a device pointer as a byte tensor (CUDA array interface)
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+        def rows(ptr, elem, nrows):
+            return torch.as_tensor(_Dev(ptr, nrows * s.pitch * elem), device=dev).view(nrows, s.pitch * elem)
+
+        def share(user, ptr, elem):
+            try:
+                exchange_rows(rows(ptr, elem, ny + 2), ny, rank, world)
+                return 0
+            except Exception as e:                    # an exception must not unwind through the C frames
+                print("td_strip_comm.share:", e, flush=True)
+                return 1
+
+        def collect(user, ptr, elem, recv_top, recv_bot):
+            try:
+                t = rows(ptr, elem, ny + 2)
+                sends, recvs = [], []
+                if rank > 0:
+                    sends.append((t[0], rank - 1)); recvs.append((rows(recv_top, elem, 1)[0], rank - 1))
+                if rank < world - 1:
+                    sends.append((t[ny + 1], rank + 1)); recvs.append((rows(recv_bot, elem, 1)[0], rank + 1))
+                _p2p(sends, recvs)
+                return 0
+            except Exception as e:
+                print("td_strip_comm.collect:", e, flush=True)
+                return 1
+
+        def allreduce(user, v, n):
+            try:
+                t = torch.tensor([int(v[i]) for i in range(n)], dtype=torch.int64, device="cpu" if _staged() else dev)
+                dist.all_reduce(t)
+                for i, x in enumerate(t.tolist()):
+                    v[i] = x
+                return 0
+            except Exception as e:
+                print("td_strip_comm.allreduce_sum:", e, flush=True)
+                return 1
+
+        SHARE = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
+        COLLECT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
+        ALLRED = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong), C.c_int)
+
+        class Comm(C.Structure):
+            _fields_ = [("user", C.c_void_p), ("share", SHARE), ("collect", COLLECT), ("allreduce_sum", ALLRED)]
+
+        cbs = (SHARE(share), COLLECT(collect), ALLRED(allreduce))          # keep the thunks alive during the call
+        comm = Comm(None, *cbs)
+        felc = fel.clone()                                                  # the reference works on a copy of elevDEM too
+        self.share(d)                                                       # halo rows of the directions the stencil produced
+        left = C.c_longlong(0)
+        fn = self.l.td_dinf_flats_strip_dev if dinf else self.l.td_d8_flats_strip_dev
+        torch.cuda.synchronize()
+        check(fn(self.T.ctx, C.c_void_p(felc.data_ptr()), C.c_void_p(d.data_ptr()), s.c, C.c_void_p(dxc.data_ptr()), C.c_void_p(dyc.data_ptr()),
+                 C.byref(left), C.byref(comm) if world > 1 else None, self._stream()))
+        return int(left.value)
+
     def _flats(self, fel, d, dxc, dyc, nflat, dinf):
+        import os
         total = all_reduce_scalar(int(nflat), device=self.s.device) if self.world > 1 else int(nflat)
         if total == 0:
             return 0
+        if os.environ.get("TAUDEM_B200_FLATS") == "strips":
+            return self._flats_strips(fel, d, dxc, dyc, dinf)
         sf, fel_full = self.gather_full(fel)
         _, d_full = self.gather_full(d)
         # per-row cell sizes of the whole grid

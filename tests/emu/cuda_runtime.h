@@ -16,6 +16,7 @@
 #include <ucontext.h>
 
 #include <algorithm>
+#include <deque>
 #include <functional>
 #include <vector>
 
@@ -69,20 +70,22 @@ struct Block {
   ucontext_t sched;
   int cur = -1;
   int alive = 0;
-  // warp collectives: per warp, values deposited by the lanes of the current generation
-  struct Warp { unsigned long long val[32]; int arrived = 0; unsigned gen = 0; unsigned long long res[2][32]; unsigned ballot[2]; };
+  // warp collectives: one slot per participant mask (a *_sync with a partial mask involves only those lanes);
+  // the lanes of a generation deposit their values, the last arrival publishes res[] / ballot[] of that parity
+  struct Slot { unsigned mask = 0; unsigned long long val[32]; int arrived = 0; unsigned gen = 0; unsigned long long res[2][32]; unsigned ballot[2]; };
+  struct Warp { std::deque<Slot> slots; unsigned alive = 0xffffffffu; };
   std::vector<Warp> warps;
   int bar_arrived = 0; unsigned bar_gen = 0;
 };
-extern Block* g_blk;
-extern unsigned long long g_rng;
-extern std::function<void()> g_body;
+extern thread_local Block* g_blk;      // one emulated device per host thread (the multi-strip tests run one thread per strip)
+extern thread_local unsigned long long g_rng;
+extern thread_local std::function<void()> g_body;
 inline unsigned rnd() { g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull; return (unsigned)(g_rng >> 33); }
 void yield();                       // back to the scheduler (random next fiber)
 void run_block(dim3 grid, dim3 block, dim3 bid, const std::function<void()>& body);
 }  // namespace emu
 
-extern dim3 threadIdx, blockIdx, blockDim, gridDim;
+extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 template <typename F> inline void emu_launch(dim3 grid, dim3 block, F body) {
   for (unsigned by = 0; by < grid.y; ++by)
@@ -111,13 +114,14 @@ EMU_ATOMIC(int)
 EMU_ATOMIC(unsigned)
 EMU_ATOMIC(unsigned long long)
 
+unsigned __activemask();
 void __syncthreads();
 void __syncwarp(unsigned mask = 0xffffffffu);
 unsigned __ballot_sync(unsigned mask, int pred);
-unsigned long long emu_shfl(unsigned long long v, int src_lane_or_delta, int mode);   // mode 0 = idx, 1 = up
-template <typename T> inline T __shfl_sync(unsigned, T v, int lane) {
-  unsigned long long x = 0; memcpy(&x, &v, sizeof(T)); x = emu_shfl(x, lane, 0); T r; memcpy(&r, &x, sizeof(T)); return r;
+unsigned long long emu_shfl(unsigned mask, unsigned long long v, int src_lane_or_delta, int mode);   // mode 0 = idx, 1 = up
+template <typename T> inline T __shfl_sync(unsigned mask, T v, int lane) {
+  unsigned long long x = 0; memcpy(&x, &v, sizeof(T)); x = emu_shfl(mask, x, lane, 0); T r; memcpy(&r, &x, sizeof(T)); return r;
 }
-template <typename T> inline T __shfl_up_sync(unsigned, T v, int delta) {
-  unsigned long long x = 0; memcpy(&x, &v, sizeof(T)); x = emu_shfl(x, delta, 1); T r; memcpy(&r, &x, sizeof(T)); return r;
+template <typename T> inline T __shfl_up_sync(unsigned mask, T v, int delta) {
+  unsigned long long x = 0; memcpy(&x, &v, sizeof(T)); x = emu_shfl(mask, x, delta, 1); T r; memcpy(&r, &x, sizeof(T)); return r;
 }

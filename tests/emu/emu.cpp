@@ -1,17 +1,29 @@
 // TEST INFRASTRUCTURE ONLY — fiber scheduler and warp collectives of the CPU emulation (see cuda_runtime.h).
 #include "cuda_runtime.h"
 
-dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 namespace emu {
-Block* g_blk = nullptr;
-unsigned long long g_rng = 12345;
-std::function<void()> g_body;
+thread_local Block* g_blk = nullptr;
+thread_local unsigned long long g_rng = 12345;
+thread_local std::function<void()> g_body;
 
 namespace {
 struct Wait { const unsigned* ptr = nullptr; unsigned val = 0; };
-std::vector<Wait> g_wait;
-std::vector<int> g_exited;          // per warp: lanes that have returned
+thread_local std::vector<Wait> g_wait;
+thread_local std::vector<int> g_exited;          // per warp: lanes that have returned
+
+unsigned alive_mask(Block* b, int w) { return b->warps[w].alive; }
+
+void complete(Block* b, int w, Block::Slot& S) {
+  const unsigned g = S.gen & 1u;
+  unsigned bal = 0;
+  for (int l = 0; l < 32; ++l) {
+    S.res[g][l] = S.val[l];
+    if ((S.mask >> l & 1u) && !b->f[w * 32 + l].done && (S.val[l] & 1ull)) bal |= 1u << l;
+  }
+  S.ballot[g] = bal; S.arrived = 0; ++S.gen;
+}
 
 void trampoline() {
   Block* b = g_blk;
@@ -19,17 +31,12 @@ void trampoline() {
   g_body();
   b->f[me].done = true;
   --b->alive;
-  // a lane that returns no longer takes part in collectives: complete one that was waiting for it
+  // a lane that returns no longer takes part in collectives: complete those that were waiting for it
   const int w = me / 32;
-  ++g_exited[w];
-  Block::Warp& W = b->warps[w];
-  if (W.arrived > 0 && W.arrived == 32 - g_exited[w]) {
-    const unsigned g = W.gen & 1u;
-    unsigned bal = 0;
-    for (int l = 0; l < 32; ++l) W.res[g][l] = W.val[l];
-    for (int l = 0; l < 32; ++l) if (!b->f[w * 32 + l].done && (W.val[l] & 1ull)) bal |= 1u << l;
-    W.ballot[g] = bal; W.arrived = 0; ++W.gen;
-  }
+  b->warps[w].alive &= ~(1u << (me % 32));
+  const unsigned alive = alive_mask(b, w);
+  for (auto& S : b->warps[w].slots)
+    if (S.arrived > 0 && S.arrived == __builtin_popcount(S.mask & alive)) complete(b, w, S);
   swapcontext(&b->f[me].ctx, &b->sched);
 }
 
@@ -43,25 +50,21 @@ void wait_on(const unsigned* ptr, unsigned val) {
   g_wait[me].ptr = nullptr;
 }
 
-// deposits v, returns the generation parity whose res[] / ballot[] hold the result
-unsigned collective(unsigned long long v) {
+// deposits v among the lanes of `mask`; returns the slot and the generation parity that holds the result
+Block::Slot& collective(unsigned mask, unsigned long long v, unsigned* parity) {
   Block* b = g_blk;
   const int me = b->cur, w = me / 32, lane = me % 32;
   Block::Warp& W = b->warps[w];
-  const unsigned gen = W.gen, g = gen & 1u;
-  W.val[lane] = v;
-  ++W.arrived;
-  if (W.arrived == 32 - g_exited[w]) {
-    unsigned bal = 0;
-    for (int l = 0; l < 32; ++l) {
-      W.res[g][l] = W.val[l];
-      if (!b->f[w * 32 + l].done && (W.val[l] & 1ull)) bal |= 1u << l;
-    }
-    W.ballot[g] = bal; W.arrived = 0; ++W.gen;
-  } else {
-    wait_on(&W.gen, gen);
-  }
-  return g;
+  Block::Slot* S = nullptr;
+  for (auto& s : W.slots) if (s.mask == mask) { S = &s; break; }
+  if (!S) { W.slots.emplace_back(); S = &W.slots.back(); S->mask = mask; }
+  const unsigned gen = S->gen;
+  *parity = gen & 1u;
+  S->val[lane] = v;
+  ++S->arrived;
+  if (S->arrived == __builtin_popcount(mask & alive_mask(b, w))) complete(b, w, *S);
+  else wait_on(&S->gen, gen);
+  return *S;
 }
 }  // namespace
 
@@ -87,7 +90,7 @@ void run_block(dim3 grid, dim3 block, dim3 bid, const std::function<void()>& bod
   gridDim = grid; blockDim = block; blockIdx = bid;
   for (int i = 0; i < n; ++i) {
     Fiber& f = blk.f[i];
-    static std::vector<char*> pool;                 // fiber stacks are reused across blocks and launches
+    static thread_local std::vector<char*> pool;                 // fiber stacks are reused across blocks and launches
     while ((int)pool.size() <= i) pool.push_back((char*)malloc(STACK));
     f.tid = dim3(i % block.x, (i / block.x) % block.y, i / (block.x * block.y));
     getcontext(&f.ctx);
@@ -121,18 +124,22 @@ void __syncthreads() {
   if (++b->bar_arrived == live) { b->bar_arrived = 0; ++b->bar_gen; }
   else emu::wait_on(&b->bar_gen, gen);
 }
-void __syncwarp(unsigned) { emu::collective(0); }
-unsigned __ballot_sync(unsigned, int pred) {
+void __syncwarp(unsigned mask) { unsigned g; emu::collective(mask, 0, &g); }
+unsigned __activemask() {            // lanes of the warp that have not returned (kernels here do not diverge around collectives)
   emu::Block* b = emu::g_blk;
-  const int w = b->cur / 32;
-  const unsigned g = emu::collective(pred ? 1ull : 0ull);
-  return b->warps[w].ballot[g];
+  return emu::alive_mask(b, b->cur / 32);
 }
-unsigned long long emu_shfl(unsigned long long v, int x, int mode) {
+unsigned __ballot_sync(unsigned mask, int pred) {
+  unsigned g;
+  emu::Block::Slot& S = emu::collective(mask, pred ? 1ull : 0ull, &g);
+  return S.ballot[g];
+}
+unsigned long long emu_shfl(unsigned mask, unsigned long long v, int x, int mode) {
   emu::Block* b = emu::g_blk;
-  const int me = b->cur, w = me / 32, lane = me % 32;
-  const unsigned g = emu::collective(v);
+  const int lane = b->cur % 32;
+  unsigned g;
+  emu::Block::Slot& S = emu::collective(mask, v, &g);
   int src = mode == 0 ? (x & 31) : lane - x;
   if (src < 0) src = lane;
-  return b->warps[w].res[g][src];
+  return S.res[g][src];
 }

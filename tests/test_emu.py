@@ -19,25 +19,32 @@ CSRC = os.path.join(ROOT, "taudem_b200", "csrc")
 BUILD = os.path.join(EMU, "_build")
 
 
-def _build(tag="", defines=()):
-    os.makedirs(BUILD, exist_ok=True)
-    src = open(os.path.join(CSRC, "sweep_walk.cu")).read()
-    # kernel<<<grid, block, smem, stream>>>(args);  ->  emu_launch(grid, block, [&]{ kernel(args); });
+def _transform(name):
+    """kernel<<<grid, block, smem, stream>>>(args);  ->  emu_launch(grid, block, [&]{ kernel(args); });"""
+    src = open(os.path.join(CSRC, name + ".cu")).read()
     src, n = re.subn(r"(k_\w+(?:<\w+>)?)<<<([^,]+),\s*([^,]+),[^>]*>>>\(([^;]*)\);",
                      r"emu_launch(dim3(\2), dim3(\3), [&] { \1(\4); });", src)
-    assert n >= 6, n
-    inc = os.path.join(BUILD, "sweep_walk_emu.inc")
+    assert n >= 6 and "<<<" not in src, (name, n)
+    inc = os.path.join(BUILD, name + "_emu.inc")
     if not os.path.exists(inc) or open(inc).read() != src:
         open(inc, "w").write(src)
+    return inc
+
+
+def _build(tag="", defines=()):
+    os.makedirs(BUILD, exist_ok=True)
+    incs = [_transform("sweep_walk"), _transform("flats")]
     so = os.path.join(BUILD, f"libemu{tag}.so")
-    deps = [inc, os.path.join(EMU, "driver.cpp"), os.path.join(EMU, "emu.cpp"), os.path.join(EMU, "cuda_runtime.h"),
-            os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "dinf_common.cuh"), os.path.join(CSRC, "ctx.h")]
+    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "emu.cpp")]
+    deps = incs + srcs + [os.path.join(EMU, "cuda_runtime.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "dinf_common.cuh"),
+                          os.path.join(CSRC, "ctx.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I", EMU, "-I", BUILD, "-I", CSRC,
-                               *[f"-D{d}" for d in defines], "-o", so, os.path.join(EMU, "driver.cpp"), os.path.join(EMU, "emu.cpp")])
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ftls-model=initial-exec", "-ffp-contract=off", "-I", EMU, "-I", BUILD, "-I", CSRC,
+                               *[f"-D{d}" for d in defines], "-o", so, *srcs])
     lib = C.CDLL(so)
     lib.emu_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                               C.c_float, C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_void_p]
+    lib.emu_flats.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -105,3 +112,46 @@ def test_emulated_row_strips_with_exchange_rounds(emu, fields, nstrips):
     assert_bits(_run(emu, True, 1, 3, ang, None, True, 13, nstrips, rounds), port.areadinf(ang), "sca strips")
     assert rounds[0] > 1
     assert_bits(_run(emu, True, 0, 0, ang, w, False, 14, nstrips), port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc strips")
+
+
+# ---------------------------------------------------------------- flat resolution (taudem_b200/csrc/flats.cu)
+@pytest.fixture(scope="module")
+def terraces():
+    """A filled DEM with wide flats (quantised elevations: terraces with higher and lower rims) and nodata holes."""
+    from oracle import port
+    dem = synth.gen_dem(120, 150, hurst=0.8, tilt=1.0, seed=17)
+    q = (dem.max() - dem.min()) / 14
+    dem = (np.round(dem / q) * q).astype(np.float32)
+    dem = synth.punch_holes(dem, seed=3)
+    fel = port.pitremove(dem)
+    return port, fel
+
+
+def _flats(lib, dinf, fel, d0, nstrips, seed):
+    ny, nx = fel.shape
+    d = np.ascontiguousarray(d0).copy()
+    left = np.zeros(1, np.int64); coll = np.zeros(1, np.int64)
+    rc = lib.emu_flats(int(dinf), np.ascontiguousarray(fel, np.float32).ctypes.data, d.ctypes.data, nx, ny, 30.0, 30.0, nstrips, seed,
+                       left.ctypes.data, coll.ctypes.data)
+    assert rc == 0
+    return d, int(left[0]), int(coll[0])
+
+
+@pytest.mark.parametrize("nstrips", [1, 2, 3, 5])
+def test_emulated_flat_resolution_d8(emu, terraces, nstrips):
+    port, fel = terraces
+    p0, _ = port.d8flowdir(fel, flats=False)
+    p_ref, _ = port.d8flowdir(fel)
+    assert (p0 == 0).sum() > 2000, "the test DEM must have wide flats"
+    p, left, coll = _flats(emu, False, fel, p0, nstrips, 21 + nstrips)
+    assert_bits(p, p_ref, f"p, {nstrips} strips")
+    assert left == int((p_ref == 0).sum()) and (nstrips == 1 or coll > 10)
+
+
+@pytest.mark.parametrize("nstrips", [1, 2, 3, 5])
+def test_emulated_flat_resolution_dinf(emu, terraces, nstrips):
+    port, fel = terraces
+    a0, _ = port.dinfflowdir(fel, flats=False)
+    a_ref, _ = port.dinfflowdir(fel)
+    a, left, _ = _flats(emu, True, fel, a0, nstrips, 31 + nstrips)
+    assert_bits(a, a_ref, f"ang, {nstrips} strips")
