@@ -89,7 +89,11 @@ __device__ __forceinline__ unsigned atom_dec_byte(unsigned* words, long long cel
   unsigned* a = words + (cell >> 2);
   const unsigned sh = (unsigned)(cell & 3) * 8u;
   unsigned old;
+#ifdef TD_EMU
+  old = atomicAdd(a, 0u - (1u << sh));
+#else
   asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
+#endif
   return (old >> sh) & 0xffu;
 }
 

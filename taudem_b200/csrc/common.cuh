@@ -83,6 +83,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, ui
                : "memory");
 }
 
+#endif  // TD_EMU
+
 template <typename T, int TW, int TH>
 struct TileGeom {
   static constexpr int HP = 16 / (int)sizeof(T);
@@ -91,6 +93,7 @@ struct TileGeom {
   static constexpr int ELEMS = SW * ROWS;
 };
 
+#ifndef TD_EMU
 // Must be called by every thread of the CTA (contains __syncthreads()).  `bar` must be
 // a fresh (never used) mbarrier word in shared memory; the tile is loaded once per CTA.
 template <typename T, int TW, int TH>
@@ -113,6 +116,19 @@ __device__ __forceinline__ void load_tile_tma(T* tile, uint64_t* bar, const T* _
   mbar_wait(bar, 0);
 }
 
+#else   // TD_EMU: the same staging contract with plain copies
+template <typename T, int TW, int TH>
+__device__ __forceinline__ void load_tile_tma(T* tile, uint64_t*, const T* __restrict__ g, const Strip& s, int r0, int c0) {
+  using G = TileGeom<T, TW, TH>;
+  const int cs = max(c0 - G::HP, 0), ce = min(c0 + TW + G::HP, s.pitch);
+  const int gr_lo = max(r0 - 1, 0), gr_hi = min(r0 + TH, s.ny + 1);
+  __syncthreads();
+  for (int gr = gr_lo + (int)threadIdx.x; gr <= gr_hi; gr += (int)blockDim.x) {
+    const int t = gr - (r0 - 1);
+    for (int c = cs; c < ce; ++c) tile[t * G::SW + (c - (c0 - G::HP))] = g[(long long)gr * s.pitch + c];
+  }
+  __syncthreads();
+}
 #endif  // TD_EMU
 
 // launch accounting (bench gpu_launches)

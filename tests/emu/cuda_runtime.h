@@ -25,6 +25,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
@@ -39,6 +40,7 @@ inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return
 inline ushort4 make_ushort4(unsigned short a, unsigned short b, unsigned short c, unsigned short d) { return {a, b, c, d}; }
 inline uchar4 make_uchar4(unsigned char a, unsigned char b, unsigned char c, unsigned char d) { return {a, b, c, d}; }
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+inline short4 make_short4(short a, short b, short c, short d) { return {a, b, c, d}; }
 
 // ---- host runtime
 typedef int cudaError_t;
@@ -118,9 +120,12 @@ unsigned __activemask();
 void __syncthreads();
 void __syncwarp(unsigned mask = 0xffffffffu);
 unsigned __ballot_sync(unsigned mask, int pred);
-unsigned long long emu_shfl(unsigned mask, unsigned long long v, int src_lane_or_delta, int mode);   // mode 0 = idx, 1 = up
+unsigned long long emu_shfl(unsigned mask, unsigned long long v, int src_lane_or_delta, int mode);   // mode 0 = idx, 1 = up, 2 = xor
 template <typename T> inline T __shfl_sync(unsigned mask, T v, int lane) {
   unsigned long long x = 0; memcpy(&x, &v, sizeof(T)); x = emu_shfl(mask, x, lane, 0); T r; memcpy(&r, &x, sizeof(T)); return r;
+}
+template <typename T> inline T __shfl_xor_sync(unsigned mask, T v, int lanemask) {
+  unsigned long long x = 0; memcpy(&x, &v, sizeof(T)); x = emu_shfl(mask, x, lanemask, 2); T r; memcpy(&r, &x, sizeof(T)); return r;
 }
 template <typename T> inline T __shfl_up_sync(unsigned mask, T v, int delta) {
   unsigned long long x = 0; memcpy(&x, &v, sizeof(T)); x = emu_shfl(mask, x, delta, 1); T r; memcpy(&r, &x, sizeof(T)); return r;

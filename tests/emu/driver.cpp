@@ -160,3 +160,13 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
       for (int c = 0; c < nx; ++c) out[(size_t)(T.row0 + r - 1) * nx + c] = T.area[T.s.idx(r, c)];
   return 0;
 }
+
+// the plain-loop dependency state of a single strip (for comparison with the emulated k_deps_* kernels)
+extern "C" int emu_ref_deps(int dinf, const void* dir, unsigned short* node, unsigned char* cnt, int nx, int ny, float dir_nodata, double dx, double dy) {
+  StripState S;
+  build_strip(S, dinf, dir, nullptr, nx, ny, 0, ny, dir_nodata, dx, dy);
+  for (int r = 1; r <= ny; ++r)
+    for (int c = 0; c < nx; ++c) { node[(size_t)(r - 1) * nx + c] = S.node[S.s.idx(r, c)]; cnt[(size_t)(r - 1) * nx + c] = S.cnt[S.s.idx(r, c)]; }
+  S.ctx.node.p = S.ctx.cnt.p = nullptr;
+  return 0;
+}

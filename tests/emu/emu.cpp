@@ -139,7 +139,7 @@ unsigned long long emu_shfl(unsigned mask, unsigned long long v, int x, int mode
   const int lane = b->cur % 32;
   unsigned g;
   emu::Block::Slot& S = emu::collective(mask, v, &g);
-  int src = mode == 0 ? (x & 31) : lane - x;
+  int src = mode == 0 ? (x & 31) : mode == 2 ? (lane ^ x) & 31 : lane - x;
   if (src < 0) src = lane;
   return S.res[g][src];
 }

@@ -19,12 +19,15 @@ CSRC = os.path.join(ROOT, "taudem_b200", "csrc")
 BUILD = os.path.join(EMU, "_build")
 
 
-def _transform(name):
+STENCILS = ("d8_stencil", "dinf_stencil", "area_d8", "area_dinf")
+
+
+def _transform(name, min_launches=6):
     """kernel<<<grid, block, smem, stream>>>(args);  ->  emu_launch(grid, block, [&]{ kernel(args); });"""
     src = open(os.path.join(CSRC, name + ".cu")).read()
     src, n = re.subn(r"(k_\w+(?:<\w+>)?)<<<([^,]+),\s*([^,]+),[^>]*>>>\(([^;]*)\);",
                      r"emu_launch(dim3(\2), dim3(\3), [&] { \1(\4); });", src)
-    assert n >= 6 and "<<<" not in src, (name, n)
+    assert n >= min_launches and "<<<" not in src, (name, n)
     inc = os.path.join(BUILD, name + "_emu.inc")
     if not os.path.exists(inc) or open(inc).read() != src:
         open(inc, "w").write(src)
@@ -33,9 +36,18 @@ def _transform(name):
 
 def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
-    incs = [_transform("sweep_walk"), _transform("flats")]
+    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS]
     so = os.path.join(BUILD, f"libemu{tag}.so")
-    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "emu.cpp")]
+    objs = []
+    for i, n in enumerate(STENCILS):                       # one translation unit per kernel file (their helper names collide)
+        o = os.path.join(BUILD, f"stencil{i + 1}.o")
+        deps_o = [incs[2 + i], os.path.join(EMU, "stencil_driver.cpp"), os.path.join(EMU, "cuda_runtime.h"), os.path.join(CSRC, "common.cuh"),
+                  os.path.join(CSRC, "dinf_common.cuh")]
+        if not os.path.exists(o) or any(os.path.getmtime(d) > os.path.getmtime(o) for d in deps_o):
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-c", "-pthread", "-ftls-model=initial-exec", "-ffp-contract=off", "-I", EMU,
+                                   "-I", BUILD, "-I", CSRC, f"-DEMU_WHICH={i + 1}", "-o", o, os.path.join(EMU, "stencil_driver.cpp")])
+        objs.append(o)
+    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "emu.cpp")] + objs
     deps = incs + srcs + [os.path.join(EMU, "cuda_runtime.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "dinf_common.cuh"),
                           os.path.join(CSRC, "ctx.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
@@ -44,6 +56,12 @@ def _build(tag="", defines=()):
     lib = C.CDLL(so)
     lib.emu_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                               C.c_float, C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_void_p]
+    P = C.c_void_p
+    lib.emu_d8_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
+    lib.emu_dinf_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
+    lib.emu_deps_d8.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_short]
+    lib.emu_deps_dinf.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
+    lib.emu_ref_deps.argtypes = [C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     lib.emu_flats.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
     return lib
 
@@ -155,3 +173,65 @@ def test_emulated_flat_resolution_dinf(emu, terraces, nstrips):
     a_ref, _ = port.dinfflowdir(fel)
     a, left, _ = _flats(emu, True, fel, a0, nstrips, 31 + nstrips)
     assert_bits(a, a_ref, f"ang, {nstrips} strips")
+
+
+# ---------------------------------------------------------------- stencil and dependency kernels
+def test_emulated_slope_stencils_match_the_oracle(emu, terraces):
+    """k_d8_stencil / k_dinf_stencil (positive-slope pass): p, sd8, ang, slp bit for bit, and the flat count."""
+    port, fel = terraces
+    ny, nx = fel.shape
+    f = np.ascontiguousarray(fel, np.float32)
+    for dx, dy in ((30.0, 30.0), (10.0, 25.0)):
+        p = np.empty((ny, nx), np.int16); sd8 = np.empty((ny, nx), np.float32); nflat = np.zeros(1, np.uint64)
+        assert emu.emu_d8_stencil(f.ctypes.data, p.ctypes.data, sd8.ctypes.data, nx, ny, -3.0e38, dx, dy, nflat.ctypes.data) == 0
+        p_ref, sd8_ref = port.d8flowdir(fel, dx=dx, dy=dy, flats=False)
+        assert_bits(p, p_ref, f"p (stencil) {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 {dx}x{dy}")
+        assert int(nflat[0]) == int((p_ref == 0).sum())
+        ang = np.empty((ny, nx), np.float32); slp = np.empty((ny, nx), np.float32)
+        assert emu.emu_dinf_stencil(f.ctypes.data, ang.ctypes.data, slp.ctypes.data, nx, ny, -3.0e38, dx, dy, nflat.ctypes.data) == 0
+        ang_ref, slp_ref = port.dinfflowdir(fel, dx=dx, dy=dy, flats=False)
+        assert_bits(ang, ang_ref, f"ang (stencil) {dx}x{dy}"); assert_bits(slp, slp_ref, f"slp {dx}x{dy}")
+        assert int(nflat[0]) == int((ang_ref == -1.0).sum())
+
+
+def test_emulated_dependency_stencils(emu, fields):
+    """k_deps_d8 / k_deps_dinf against the plain-loop restatement the emulated sweeps are fed with."""
+    _, p, ang, _ = fields
+    ny, nx = p.shape
+    for dinf, d, nd in ((0, np.ascontiguousarray(p), -32768.0), (1, np.ascontiguousarray(ang), -3.4028234663852886e38)):
+        node = np.empty((ny, nx), np.uint16); cnt = np.empty((ny, nx), np.uint8); area = np.empty((ny, nx), np.float32)
+        rn = np.empty((ny, nx), np.uint16); rc = np.empty((ny, nx), np.uint8)
+        if dinf:
+            assert emu.emu_deps_dinf(d.ctypes.data, node.ctypes.data, cnt.ctypes.data, area.ctypes.data, nx, ny, nd, 30.0, 30.0) == 0
+        else:
+            assert emu.emu_deps_d8(d.ctypes.data, node.ctypes.data, cnt.ctypes.data, area.ctypes.data, nx, ny, int(nd)) == 0
+        assert emu.emu_ref_deps(dinf, d.ctypes.data, rn.ctypes.data, rc.ctypes.data, nx, ny, nd, 30.0, 30.0) == 0
+        assert np.array_equal(cnt, rc), f"counts dinf={dinf}: {int((cnt != rc).sum())} differ"
+        assert np.array_equal(node, rn), f"node words dinf={dinf}: {int((node != rn).sum())} differ"
+        assert np.all(area == -1.0)
+
+
+def test_emulated_d8_stencil_ties_and_near_ties(emu):
+    """Exact ties (quantised elevations) and drops that are adjacent floats whose slopes round to the same float32: the
+    scan-order rule of the reference (first k in 1,3,5,7,2,4,6,8 with the strictly largest rounded slope) must survive
+    the three-product shortcut.  (Without the literal fallback of d8_cell about 170 cells of the second grid differ.)"""
+    from oracle import port
+    rng = np.random.default_rng(5)
+    ny, nx = 96, 128
+    base = (1000.0 + rng.integers(0, 4, (ny, nx)) * 2.5).astype(np.float32)          # many exact ties
+    grids = [(base.view(np.int32) + rng.integers(-3, 4, (ny, nx)).astype(np.int32)).view(np.float32)]
+    # peaks near 1000 over a floor near 10 / 26: the drops lie in the top of a binade, where neighbouring float drops
+    # collapse onto one slope after the multiplication by 1/distance
+    rng = np.random.default_rng(7)
+    ny, nx = 192, 256
+    g = (10.0 + rng.integers(0, 2, (ny, nx)) * 16.0 + rng.integers(-4, 5, (ny, nx)) * 3.0e-5).astype(np.float32)
+    g[1::3, 1::3] = (np.float32(1000.0).view(np.int32) + rng.integers(-2, 3, g[1::3, 1::3].shape).astype(np.int32)).view(np.float32)
+    grids.append(g)
+    for fel in grids:
+        ny, nx = fel.shape
+        f = np.ascontiguousarray(fel)
+        for dx, dy in ((30.0, 30.0), (30.0, 30.000001), (12.5, 40.0), (7.0, 7.1)):
+            p = np.empty((ny, nx), np.int16); sd8 = np.empty((ny, nx), np.float32); nflat = np.zeros(1, np.uint64)
+            assert emu.emu_d8_stencil(f.ctypes.data, p.ctypes.data, sd8.ctypes.data, nx, ny, -3.0e38, dx, dy, nflat.ctypes.data) == 0
+            p_ref, sd8_ref = port.d8flowdir(fel, dx=dx, dy=dy, flats=False)
+            assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
