@@ -17,6 +17,9 @@ namespace {
 constexpr int TW = 128, TH = 32;
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 
+// bit 7 of every byte of the result = (that byte of w == that byte of t); all bytes of w ^ t must be < 0x80
+__device__ __forceinline__ unsigned eq_bytes7(unsigned w, unsigned t) { return ~((w ^ t) + 0x7f7f7f7fu) & 0x80808080u; }
+
 __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang, unsigned short* __restrict__ node,
                                                    unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,
                                                    float nodata, const double* __restrict__ theta) {
@@ -25,58 +28,64 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
   __shared__ __align__(8) uint64_t bar;
   const int c0 = blockIdx.x * TW, r0 = 1 + blockIdx.y * TH;
   load_tile_tma<float, TW, TH>(tile, &bar, ang, s, r0, c0);
-  // outflow directions (k1 | k2 << 4) of every staged cell, one prop() interval search each
+  // one byte per staged cell: k1 | 0x10 if there is a second receiver (always the next direction, k1 % 8 + 1) |
+  // 0x20 if the cell is off the grid or nodata; one prop() interval search each
   __shared__ double saref[(TH + 2) * 10];
-  __shared__ unsigned char sout[G::ELEMS];
+  __shared__ __align__(16) unsigned char sout[G::ELEMS];
   for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) saref[i] = aref(i % 10, theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]);
   __syncthreads();
   for (int i = threadIdx.x; i < G::ELEMS; i += 256) {
     const int t = i / G::SW, sc = i - t * G::SW;
     const int gr = r0 - 1 + t, gc = c0 - G::HP + sc;
-    unsigned char code = 0;
+    unsigned char code = 0x20;
     if (s.on_grid(gr, gc)) {
       const float av = tile[i];
-      if (!nd_f(av, nodata)) { const Outflow o = dinf_outflow(av, saref + t * 10); code = (unsigned char)(o.k1 | (o.k2 << 4)); }
+      if (!nd_f(av, nodata)) { const Outflow o = dinf_outflow(av, saref + t * 10); code = (unsigned char)(o.k1 | (o.k2 ? 0x10 : 0)); }
     }
     sout[i] = code;
   }
   __syncthreads();
+  // four adjacent cells per thread with byte-parallel arithmetic: neighbour k drains into me when one of its
+  // receiving directions is kk = (k+4)%8 (src/commonLib.cpp:105-134), i.e. k1 == kk, or k1 == kk-1 with a second receiver
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned* soutw = reinterpret_cast<const unsigned*>(sout);
+  constexpr int QW = G::SW / 4;
 #pragma unroll 1
   for (int pass = 0; pass < TH / 8; ++pass) {
     const int tr = warp + 8 * pass;
     const int r = r0 + tr, c = c0 + lane * 4;
     if (r > s.ny || c >= s.pitch) continue;
-    const float* pm = tile + tr * G::SW + G::HP + lane * 4;
-    const unsigned char* po = sout + tr * G::SW + G::HP + lane * 4;
-    float nb[3][6]; unsigned char ob[3][6];
+    unsigned W[3][3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float* q = pm + j * G::SW;
-      const float4 v = *reinterpret_cast<const float4*>(q);
-      nb[j][0] = q[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = q[4];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) ob[j][i] = po[j * G::SW + i - 1];
+      const unsigned* q = soutw + (tr + j) * QW + lane;      // word lane + 1 holds the cells c .. c+3 (HP = 4 columns of padding)
+      const unsigned wl = q[0], wc = q[1], wr = q[2];
+      W[j][0] = __funnelshift_l(wl, wc, 8);
+      W[j][1] = wc;
+      W[j][2] = __funnelshift_r(wc, wr, 8);
     }
+    unsigned mb = 0, all = 0;
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      const unsigned wk = W[1 + drow(k)][1 + dcol(k)];
+      const unsigned kk = k > 4 ? k - 4 : k + 4, prev = kk == 1 ? 8u : kk - 1u;
+      const unsigned z = eq_bytes7(wk & 0x0f0f0f0fu, kk * 0x01010101u) | eq_bytes7(wk & 0x1f1f1f1fu, (0x10u | prev) * 0x01010101u);
+      mb |= z >> (8 - k);
+      all |= wk;
+    }
+    const unsigned wc = W[1][1];
+    const unsigned vm = ((~wc >> 5) & 0x01010101u) * 0xffu;              // 0xff per cell of the flow field
+    unsigned x = mb - ((mb >> 1) & 0x55555555u);                          // per-byte population count
+    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+    x = (x + (x >> 4)) & 0x0f0f0f0fu;
+    const unsigned cw = (x & vm) | ~vm;                                   // count, or 0xff outside the field
+    const unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1)) & vm;  // VALID | CON (a neighbour off the grid or nodata)
+    const unsigned mw = mb & vm;
     unsigned short on4[4]; unsigned char oc4[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int cc = c + i;
-      const bool valid = cc < s.nx && !nd_f(nb[1][i + 1], nodata);
-      unsigned mask = 0; bool con = false;
-#pragma unroll
-      for (int k = 1; k <= 8; ++k) {
-        const float an = nb[1 + drow(k)][i + 1 + dcol(k)];
-        if (!s.on_grid(r + drow(k), cc + dcol(k)) || nd_f(an, nodata)) con = true;
-        else {
-          // neighbour k drains to me when one of its receiving directions is (k+4)%8 (src/commonLib.cpp:105-134)
-          const int kk = k > 4 ? k - 4 : k + 4;
-          const unsigned code = ob[1 + drow(k)][i + 1 + dcol(k)];
-          if ((int)(code & 15u) == kk || (int)(code >> 4) == kk) mask |= 1u << (k - 1);
-        }
-      }
-      on4[i] = valid ? (unsigned short)(NODE_VALID | (con ? NODE_CON : 0u) | mask) : (unsigned short)0;
-      oc4[i] = valid ? (unsigned char)__popc(mask) : (unsigned char)0xff;
+      on4[i] = (unsigned short)(((hb >> (8 * i)) & 0xffu) << 8 | ((mw >> (8 * i)) & 0xffu));
+      oc4[i] = (unsigned char)(cw >> (8 * i));
     }
     const long long o = s.idx(r, c);
     *reinterpret_cast<ushort4*>(node + o) = make_ushort4(on4[0], on4[1], on4[2], on4[3]);

@@ -38,40 +38,38 @@ __device__ __noinline__ void d8_literal(const float* q, int sw, double fE, doubl
   *dir = d; *smax = sm;
 }
 
-// One cell.  nbr = the 3x3 neighbourhood (row above / centre / below, columns i..i+2 of nb).
+// One cell.  nb = the staged neighbourhood (row above / centre / below, columns i..i+2 of nb).
 // The reference scans k = 1,3,5,7,2,4,6,8 and keeps the first k with the strictly largest
 // slope_k = (float)(fact_k * (double)(z - z_k)).  fact takes only three values per row (E/W, N/S,
 // diagonals) and the rounding is monotone in the elevation drop, so the maximum of each group is
-// attained by the group's largest drop: three exact products instead of eight.  The winner is the
-// first k in scan order whose group slope equals the maximum and whose drop equals the group's
-// largest drop.  Two different drops can round to the same slope only when they are within an ulp or
-// two of each other; any such near-tie (relative gap < 2^-20) takes the literal eight-product path.
+// attained by the group's largest drop: three exact products instead of eight.  Within a group the
+// winner is the first member (scan order) whose slope equals the group's: a drop more than 2^-20
+// (relative) below the largest one cannot round to the same slope, so the candidate is the first
+// member inside that band; if it is not the largest drop itself the cell is ambiguous (two nearly equal
+// drops, rare) and takes the literal eight-product path.  A group whose largest drop is <= 0 has no
+// member inside the band and can never win (S > 0 is required), so it never raises the flag.
 __device__ __forceinline__ bool d8_cell(const float (&nb)[3][6], int i, double fE, double fN, double fD, int& dir, float& smax) {
   const float z = nb[1][i + 1];
   const float e1 = z - nb[1][i + 2], e5 = z - nb[1][i], e3 = z - nb[0][i + 1], e7 = z - nb[2][i + 1];
   const float e2 = z - nb[0][i + 2], e4 = z - nb[0][i], e6 = z - nb[2][i], e8 = z - nb[2][i + 2];
-  const float m15 = fmaxf(e1, e5), m37 = fmaxf(e3, e7), m24 = fmaxf(e2, e4), m68 = fmaxf(e6, e8), mD = fmaxf(m24, m68);
+  const float m15 = fmaxf(e1, e5), m37 = fmaxf(e3, e7), mD = fmaxf(fmaxf(e2, e4), fmaxf(e6, e8));
   const float sE = (float)(fE * (double)m15), sN = (float)(fN * (double)m37), sD = (float)(fD * (double)mD);
   const float S = fmaxf(fmaxf(sE, sN), sD);
-  // candidate of each group = its first member (scan order 1,3,5,7,2,4,6,8) with the largest drop,
-  // coded as (scan position << 4) | k so that an integer minimum picks the earliest one
-  int cE = (e1 >= e5) ? 0x01 : 0x25;
-  int cN = (e3 >= e7) ? 0x13 : 0x37;
-  const int c24 = (e2 >= e4) ? 0x42 : 0x54, c68 = (e6 >= e8) ? 0x66 : 0x78;
-  int cD = (m24 >= m68) ? c24 : c68;
+  const float c = 0.99999905f;                       // 1 - 2^-20
+  const float tE = m15 * c, tN = m37 * c, tD = mD * c;
+  // candidates coded as (scan position << 4) | k so that an integer minimum picks the earliest one
+  const bool in1 = e1 > tE, in3 = e3 > tN, in2 = e2 > tD, in4 = e4 > tD, in6 = e6 > tD;
+  int cE = in1 ? 0x01 : 0x25;
+  int cN = in3 ? 0x13 : 0x37;
+  int cD = in2 ? 0x42 : (in4 ? 0x54 : (in6 ? 0x66 : 0x78));
+  const float eD = in2 ? e2 : (in4 ? e4 : (in6 ? e6 : mD));
+  const bool amb = (in1 & (e1 < m15)) | (in3 & (e3 < m37)) | (eD < mD);
   cE = (sE == S) ? cE : 0xff; cN = (sN == S) ? cN : 0xff; cD = (sD == S) ? cD : 0xff;
   const int best = min(cE, min(cN, cD));
   const bool pos = S > 0.f;
   dir = pos ? (best & 15) : 0;
   smax = pos ? S : 0.f;
-  // a drop within 2^-20 (relative) below its group's largest drop could round to the same slope and, if it
-  // comes earlier in the scan, win: such cells (rare) take the literal path.  Bitwise logic: no branches.
-  const float c = 0.99999905f;
-  const float tE = m15 * c, tN = m37 * c, tD = mD * c;
-  const float lE = fminf(e1, e5), lN = fminf(e3, e7);
-  const bool near = pos & (((lE < m15) & (lE > tE)) | ((lN < m37) & (lN > tN)) | ((e2 < mD) & (e2 > tD)) | ((e4 < mD) & (e4 > tD)) |
-                           ((e6 < mD) & (e6 > tD)) | ((e8 < mD) & (e8 > tD)));
-  return near;
+  return amb & pos;
 }
 
 __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ elev, short* __restrict__ dir,
@@ -107,15 +105,19 @@ __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ el
       nb[j][0] = p[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = p[4];
     }
     const double fE = sfact[tr][0], fN = sfact[tr][1], fD = sfact[tr][2];
-    // nodata per staged value, then per column, then per 3x3 window
-    bool colbad[6];
+    // nodata: distance of every staged value to the nodata value, minimum per column, then per 3x3 window
+    float colmin[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) colbad[i] = nd_f(nb[0][i], nodata) || nd_f(nb[1][i], nodata) || nd_f(nb[2][i], nodata);
+    for (int i = 0; i < 6; ++i) colmin[i] = fminf(fminf(fabsf(nb[0][i] - nodata), fabsf(nb[1][i] - nodata)), fabsf(nb[2][i] - nodata));
+    // cells on the edge of the whole grid or beyond the last column, as a 4-bit mask for this thread's cells
+    unsigned em = ((r == 1 && !s.has_top) || (r == s.ny && !s.has_bot)) ? 0xfu : 0u;
+    em |= (c == 0) ? 1u : 0u;
+    const int klast = s.nx - 1 - c;                                   // cell index of the last grid column within this thread
+    if (klast < 4) em |= (0xfu << max(klast, 0)) & 0xfu;
     short od[4]; float os[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int cc = c + i;
-      const bool bad = colbad[i] || colbad[i + 1] || colbad[i + 2] || s.global_edge(r, cc) || cc >= s.nx;
+      const bool bad = (fminf(fminf(colmin[i], colmin[i + 1]), colmin[i + 2]) < TD_MINEPS) || ((em >> i) & 1u);
       int d; float smax;
       if (d8_cell(nb, i, fE, fN, fD, d, smax)) d8_literal(pm + G::SW + i, G::SW, fE, fN, fD, &d, &smax);
       od[i] = bad ? TD_MISSINGSHORT : (short)d;

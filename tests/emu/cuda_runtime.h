@@ -103,6 +103,8 @@ template <typename T> inline T __ldcg(const T* p) { emu::yield(); return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline long long clock64() { return 0; }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) << (sh & 31) >> 32); }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31)); }
 using std::max;
 using std::min;
 inline int min(int a, unsigned b) { return a < (int)b ? a : (int)b; }

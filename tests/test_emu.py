@@ -198,7 +198,12 @@ def test_emulated_dependency_stencils(emu, fields):
     """k_deps_d8 / k_deps_dinf against the plain-loop restatement the emulated sweeps are fed with."""
     _, p, ang, _ = fields
     ny, nx = p.shape
-    for dinf, d, nd in ((0, np.ascontiguousarray(p), -32768.0), (1, np.ascontiguousarray(ang), -3.4028234663852886e38)):
+    rng = np.random.default_rng(3)
+    podd = p.copy()                                       # direction codes outside 0..8 (the generic path of k_deps_d8) and zeros
+    idx = rng.integers(0, p.size, 400)
+    podd.ravel()[idx] = rng.choice(np.array([0, 0, 9, 10, 12, -1, -3, 100, -32768], np.int16), 400)
+    for dinf, d, nd in ((0, np.ascontiguousarray(p), -32768.0), (0, np.ascontiguousarray(podd), -32768.0),
+                        (1, np.ascontiguousarray(ang), -3.4028234663852886e38)):
         node = np.empty((ny, nx), np.uint16); cnt = np.empty((ny, nx), np.uint8); area = np.empty((ny, nx), np.float32)
         rn = np.empty((ny, nx), np.uint16); rc = np.empty((ny, nx), np.uint8)
         if dinf:

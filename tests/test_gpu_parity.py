@@ -279,3 +279,24 @@ def test_geographic_dem_file_level(refrun, tmp_path):
         a, b = td.read_raster(q(n + ".tif"), dt), td.read_raster(q("ref/" + n + ".tif"), dt)
         (assert_bits if exact else assert_float_parity)(a, b, n + " (geographic)")
     assert td.raster_info(q("sca.tif"))["is_geographic"]        # GeoTIFF keys pass through to the outputs
+
+
+def test_d8_stencil_ties_and_near_ties():
+    """Exact ties and drops that are adjacent floats whose slopes round to the same float32 (the literal fallback of
+    d8_cell): p and sd8 of the positive-slope pass + flats against the C restatement.  Same grids as
+    tests/test_emu.py::test_emulated_d8_stencil_ties_and_near_ties."""
+    from oracle import port
+    rng = np.random.default_rng(5)
+    ny, nx = 96, 128
+    base = (1000.0 + rng.integers(0, 4, (ny, nx)) * 2.5).astype(np.float32)
+    grids = [(base.view(np.int32) + rng.integers(-3, 4, (ny, nx)).astype(np.int32)).view(np.float32)]
+    rng = np.random.default_rng(7)
+    ny, nx = 192, 256
+    g = (10.0 + rng.integers(0, 2, (ny, nx)) * 16.0 + rng.integers(-4, 5, (ny, nx)) * 3.0e-5).astype(np.float32)
+    g[1::3, 1::3] = (np.float32(1000.0).view(np.int32) + rng.integers(-2, 3, g[1::3, 1::3].shape).astype(np.int32)).view(np.float32)
+    grids.append(g)
+    for fel in grids:
+        for dx, dy in ((30.0, 30.0), (12.5, 40.0), (7.0, 7.1)):
+            p, sd8 = td.d8flowdir_grid(fel, dx=dx, dy=dy)
+            p_ref, sd8_ref = port.d8flowdir(fel, dx=dx, dy=dy)
+            assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
