@@ -5,6 +5,8 @@
 //            area() main loop    src/areadinf.cpp:173-265 (k-ordered gather
 //                                areares = (float)(areares + p*area_n), + weight or dxc[row],
 //                                then decrement every neighbour that receives flow).
+// node word of a D-infinity cell: bits 0-7 = which neighbours drain into it, bits 8-11 = its first receiving
+// direction k1 (0 = none), 0x2000 = it has a second receiver (always k1 % 8 + 1), 0x1000 = contaminated, 0x8000 = valid.
 // prop's table aref[] = {-t,0,t,PI/2,PI-t,PI,PI+t,3PI/2,2PI-t,2PI} with t = atan2(dy,dx)
 // is rebuilt on the device from t (host glibc atan2, per row) using only +,-: the same
 // doubles as the reference.  The per-cell value is a deterministic gather, so any
@@ -79,7 +81,8 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
     x = (x + (x >> 4)) & 0x0f0f0f0fu;
     const unsigned cw = (x & vm) | ~vm;                                   // count, or 0xff outside the field
-    const unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1)) & vm;  // VALID | CON (a neighbour off the grid or nodata)
+    // VALID | CON (a neighbour off the grid or nodata) | the cell's own receivers: k1 in bits 8-11, 0x2000 = a second one (k1 % 8 + 1)
+    const unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1) | (wc & 0x0f0f0f0fu) | ((wc & 0x10101010u) << 1)) & vm;
     const unsigned mw = mb & vm;
     unsigned short on4[4]; unsigned char oc4[4];
 #pragma unroll

@@ -76,6 +76,12 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   return v;
 }
 
+// prop(angle, kk) through the full interval search (one copy, out of line: it is the rare path of eval_cell)
+__device__ __noinline__ double share_full(float ang, double t, int kk) {
+  const Outflow o = dinf_outflow(ang, t);
+  return o.k1 == kk ? o.p1 : o.p2;
+}
+
 // Evaluates cell (r, c) = ci whose contributors are all final, stores its area and decrements the
 // receivers.  Receivers whose count reached zero through this decrement are returned in ready[0..1]
 // (with their node words) — the caller decides whether it follows them.
@@ -116,26 +122,42 @@ __device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r,
       else if ((ndn & NODE_VALID) && dec_count(a.cntw, cin) == 1u) { ready[0] = cin; ready_nd[0] = ndn; nready = 1; }
     }
   } else {
-    // src/areadinf.cpp:187-218
-    const float a0 = a.ang[ci];
+    // src/areadinf.cpp:187-218.  The share a contributor sends here is prop(angle, direction): for a contributor with
+    // two receivers in one of the sectors 1..7 the node word already says which sector (k1 = j, k1 + 1), so the share
+    // is one division, (hi - a)/(hi - mid) for its first receiver and (a - mid)/(hi - mid) for the second — exactly
+    // the expressions dinf_outflow evaluates; everything else (single receiver, the wrap sector, contributors in a
+    // halo row, whose node words belong to the neighbour strip) takes the full interval search.
+    unsigned short nn[8];
+#pragma unroll
+    for (int k = 1; k <= 8; ++k) {
+      const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
+      nn[k - 1] = ((m >> (k - 1)) & 1u) ? a.node[ni] : (unsigned short)0;
+    }
     val = 0.f;
 #pragma unroll
     for (int k = 1; k <= 8; ++k)
       if ((m >> (k - 1)) & 1u) {
         const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
-        const Outflow o = dinf_outflow(aa[k - 1], a.theta[min(max(r - 1 + drow(k), 0), s.ny - 1)]);
-        const double p = o.k1 == kk ? o.p1 : o.p2;
+        const int rn = r + drow(k);
+        const double t = a.theta[min(max(rn - 1, 0), s.ny - 1)];
+        const int k1n = (nn[k - 1] >> 8) & 0xf;
+        double p;
+        if ((nn[k - 1] & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
+          const double mid = aref(k1n, t), hi = aref(k1n + 1, t);
+          const float av = aa[k - 1];
+          p = (kk == k1n) ? (hi - av) / (hi - mid) : (av - mid) / (hi - mid);
+        } else p = share_full(aa[k - 1], t, kk);
         if (nd_f(an[k - 1], -1.0f)) con = true; else val = (float)((double)val + p * (double)an[k - 1]);
       }
     if (a.usew) val = val + a.w[ci];
     else val = (float)((double)val + a.dxc[r - 1]);
     if (con && a.contcheck) val = -1.0f;
     a.area[ci] = val;
-    // src/areadinf.cpp:221-239: every neighbour that receives a share
-    const Outflow o = dinf_outflow(a0, a.theta[r - 1]);
+    // src/areadinf.cpp:221-239: every neighbour that receives a share (the receivers are in the node word)
+    const int k1 = (int)((nd >> 8) & 0xfu);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int k = j == 0 ? o.k1 : o.k2;
+      const int k = j == 0 ? k1 : ((nd & 0x2000u) ? k1 % 8 + 1 : 0);
       if (k == 0) continue;
       const int rn = r + drow(k), cn = c + dcol(k);
       if (!s.on_grid(rn, cn)) continue;

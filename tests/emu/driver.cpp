@@ -100,8 +100,10 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
           const unsigned cd = code[s.idx(rn, cn)];
           if ((int)(cd & 15u) == kk || (int)(cd >> 4) == kk) mask |= 1u << (k - 1);
         }
-        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask);
+        const unsigned own = code[s.idx(r, c)];                        // receivers of the cell itself: k1, and whether there is a second one
+        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask | ((own & 15u) << 8) | ((own >> 4) ? 0x2000u : 0u));
         S.cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
+        if ((own >> 4) && (own >> 4) != (own & 15u) % 8 + 1) abort();  // the second receiver is always the next direction
       }
   }
   S.ctx.node.p = S.node.data(); S.ctx.node.cap = S.node.size() * 2;
