@@ -22,6 +22,8 @@
 //             a global list that the host drains with another launch.
 // Modes: "levels" = K passes of k_level, then k_ready + k_walk;  "hybrid" = one visit of every tile by the
 // tile kernel (sweep_tiles.cu, `once`), then k_ready + k_walk;  "walk" = k_ready + k_walk from the sources.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "ctx.h"
@@ -51,8 +53,9 @@ struct WalkArgs {
   const long long* list;
   unsigned long long nlist;
   unsigned long long* ctr;    // [0] list ticket, [1] spill length, [2] spill list exhausted, [3] ready cells (collect)
-  long long* spill;
+  long long* spill;            // D-infinity: forks that did not fit the warp's stack; D8: parked river heads (k_river)
   unsigned long long spill_cap;
+  int river_hops;              // D8: a lane that has followed one chain for this many cells parks it for k_river (0 = never)
 };
 
 __device__ __forceinline__ unsigned dec_count(unsigned* words, long long cell) {
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
   long long cur = -1;
   unsigned curnd = 0;
   bool have_nd = false;
+  int hops = 0;                         // cells of the current chain (D8 river parking)
   bool list_done = a.nlist == 0;        // warp-uniform
   for (;;) {
     // ---- refill idle lanes: the warp's fork stack first, then a batch of the global ready list
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
     if (idle) {
       const int nl = wqn[wid];
       const int rank = __popc(idle & lt);
-      if (cur < 0 && rank < nl) { cur = wq[wid][nl - 1 - rank]; have_nd = false; }
+      if (cur < 0 && rank < nl) { cur = wq[wid][nl - 1 - rank]; have_nd = false; hops = 0; }
       __syncwarp();
       if (lane == 0) wqn[wid] = max(0, nl - __popc(idle));
       __syncwarp();
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
         if (lane == 0) base = atomicAdd(a.ctr, (unsigned long long)need);
         base = __shfl_sync(0xffffffffu, base, 0);
         const unsigned long long mine = base + (unsigned long long)__popc(idle & lt);
-        if (cur < 0 && mine < a.nlist) { cur = a.list[mine]; have_nd = false; }
+        if (cur < 0 && mine < a.nlist) { cur = a.list[mine]; have_nd = false; hops = 0; }
         if (base + (unsigned long long)need >= a.nlist) list_done = true;
       }
     }
@@ -292,6 +296,12 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
       const int nr = eval_cell<DINF>(a, ci, r, c, nd, ready, rnd);
       atomicAdd(a.cntw + (ci >> 2), 0xfeu << ((unsigned)(ci & 3) * 8u));     // 0 -> 0xFE (evaluated), like k_level and the tile kernel
       if (nr >= 1) { cur = ready[0]; curnd = rnd[0]; have_nd = true; } else cur = -1;
+      if (!DINF && a.river_hops > 0 && cur >= 0 && ++hops >= a.river_hops) {
+        // a long chain: most likely a river.  Its next cell (ready, not evaluated) goes to the river list, where a
+        // whole warp follows it with look-ahead (k_river) once the short chains are done.
+        const unsigned long long g = atomicAdd(a.ctr + 1, 1ull);
+        if (g < a.spill_cap) { a.spill[g] = cur; cur = -1; } else atomicAdd(a.ctr + 1, ~0ull);   // list full: keep walking
+      }
       if (DINF && nr == 2) fork = ready[1];
     }
     if (DINF) {
@@ -311,6 +321,98 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
         if (lane == 0) wqn[wid] = min(WQ, nl + __popc(fm));
         __syncwarp();
       }
+    }
+  }
+}
+
+// D8 rivers.  A chain never forks and its path is static (the direction codes), so a warp can look ahead: it
+// follows the path from a ready head for up to 32 cells, as long as the next cell's only missing arrival is
+// the cell before it on the path (count byte == 1: every other contributor has released its area).  Those
+// cells are resolved together — contributors gathered by all lanes at once, then one k-ordered float fold per
+// cell handed from lane to lane by shuffle (the exact sequence of additions of src/aread8.cpp:228-257) — with
+// ONE memory round trip per cell (node word + count word of the next cell, issued together) instead of the
+// four dependent ones of a chain walker.  The warp then arrives at the first cell it could not resolve with
+// the usual release + decrement and goes on from there if it was the last arrival.
+__global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
+  const Strip& s = a.s;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = (int)(threadIdx.x & 31u);
+  for (;;) {
+    long long head = -1;
+    if (lane == 0) { const unsigned long long t = atomicAdd(a.ctr, 1ull); if (t < a.nlist) head = a.list[t]; }
+    head = __shfl_sync(FULL, head, 0);
+    if (head < 0) return;
+    int hr = (int)(head / s.pitch), hc = (int)(head - (long long)hr * s.pitch);
+    unsigned hnd = a.node[head];
+    for (;;) {
+      if (lane == 0) (void)ld_acquire(a.cntw + (head >> 2));   // what the head's contributors released ...
+      __syncwarp();                                            // ... is visible to every lane of the warp
+      // ---- 1. the path: the same loop in every lane (uniform loads), lane i keeps cell i
+      long long ci = head; int r = hr, c = hc; unsigned nd = hnd; int kp = 0;
+      long long my = -1; int mykp = 0; unsigned mynd = 0;
+      long long nxt = -1; int nxr = 0, nxc = 0; unsigned nxnd = 0; bool halo_exit = false;
+      int len = 0;
+      for (int i = 0; i < 32; ++i) {
+        if (lane == i) { my = ci; mynd = nd; mykp = kp; }
+        len = i + 1;
+        nxt = -1;
+        const int d = (int)((nd >> 8) & 0xfu);
+        if (d < 1 || d > 8) break;
+        const int rn = r + drow(d), cn = c + dcol(d);
+        if (!s.on_grid(rn, cn)) break;
+        if (rn == 0 || rn == s.ny + 1) { halo_exit = true; nxr = rn; nxc = cn; break; }
+        const long long cin = s.idx(rn, cn);
+        const unsigned ndn = a.node[cin];
+        unsigned cw = 0;                                  // the count word changes under us: one lane reads it for the warp
+        if (lane == 0) cw = ld_acquire(a.cntw + (cin >> 2));
+        cw = __shfl_sync(FULL, cw, 0);                    // (the shuffle also orders the other lanes' later loads behind the acquire)
+        if (!(ndn & NODE_VALID)) break;
+        nxt = cin; nxr = rn; nxc = cn; nxnd = ndn;
+        if (((cw >> ((unsigned)(cin & 3) * 8u)) & 0xffu) != 1u || i == 31) break;   // not resolvable ahead of time: arrive there
+        kp = d > 4 ? d - 4 : d + 4;                      // the direction from the next cell back to this one
+        ci = cin; r = rn; c = cn; nd = ndn;
+      }
+      // ---- 2. the areas of the contributors that are not on the path (all final)
+      const unsigned m = lane < len ? (mynd & 0xffu) : 0u;
+      float an[8];
+#pragma unroll
+      for (int k = 1; k <= 8; ++k) {
+        const bool in = ((m >> (k - 1)) & 1u) && k != mykp;
+        an[k - 1] = in ? __ldcg(a.area + my + (long long)drow(k) * s.pitch + dcol(k)) : 0.f;
+      }
+      float wv = 1.0f;
+      if (a.usew && lane < len) { const float x = a.w[my]; wv = nd_f(x, a.w_nodata) ? -1.0f : x; }
+      // ---- 3. the fold, one cell after the other (src/aread8.cpp:228-257)
+      float val = 0.f;
+      for (int i = 0; i < len; ++i) {
+        const float prev = __shfl_sync(FULL, val, (i + 31) & 31);
+        if (lane == i) {
+          bool con = (mynd & NODE_CON) != 0;
+          float v = wv;
+#pragma unroll
+          for (int k = 1; k <= 8; ++k)
+            if ((m >> (k - 1)) & 1u) {
+              const float x = k == mykp ? prev : an[k - 1];
+              if (nd_f(x, -1.0f)) con = true; else v = v + x;
+            }
+          if (con && a.contcheck) v = -1.0f;
+          val = v;
+        }
+      }
+      // ---- 4. results; the head had count 0, the others 1 (their missing arrival was the path)
+      if (lane < len) {
+        a.area[my] = val;
+        atomicAdd(a.cntw + (my >> 2), (lane == 0 ? 0xfeu : 0xfdu) << ((unsigned)(my & 3) * 8u));
+      }
+      // ---- 5. arrive at the next cell of the path (release of the last area, decrement)
+      long long newhead = -1;
+      if (lane == len - 1) {
+        if (halo_exit) { __threadfence(); atomicAdd(a.halo + (nxr == 0 ? 0 : s.pitch) + nxc, 1); }
+        else if (nxt >= 0 && dec_count(a.cntw, nxt) == 1u) newhead = nxt;
+      }
+      newhead = __shfl_sync(FULL, newhead, len - 1);
+      if (newhead < 0) break;
+      head = newhead; hr = nxr; hc = nxc; hnd = nxnd;
     }
   }
 }
@@ -352,7 +454,7 @@ void walk_args(td_ctx* ctx, WalkArgs& a, float* area, const float* w, const floa
   a.node = ctx->node.as<unsigned short>(); a.cntw = ctx->cnt.as<unsigned>();
   a.area = area; a.w = w; a.ang = ang; a.s = s; a.usew = usew; a.contcheck = contcheck; a.w_nodata = w_nodata;
   a.theta = theta; a.dxc = dxc; a.halo = halo;
-  a.list = nullptr; a.nlist = 0; a.spill = nullptr; a.spill_cap = 0;
+  a.list = nullptr; a.nlist = 0; a.spill = nullptr; a.spill_cap = 0; a.river_hops = 0;
   a.ctr = ctx->d_ctr + 16;
 }
 }  // namespace
@@ -399,24 +501,38 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   k_ready<true><<<blocks, 256, 0, st>>>(a.cntw, a.node, s, a.ctr, ctx->listA.as<long long>());
   TD_LAUNCHED();
   const unsigned long long cap = (unsigned long long)s.nx * s.ny / 16 + 65536;
-  if (dinf) { TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap)); TD_CUDA(ctx->listC.ensure(sizeof(long long) * cap)); }
+  // D8: TAUDEM_B200_RIVER = number of cells after which a chain is parked for k_river (0 / unset = off)
+  int river = 0;
+  if (!dinf) { const char* e = getenv("TAUDEM_B200_RIVER"); river = e ? std::max(0, atoi(e)) : 0; }
+  if (dinf || river) TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap));
+  if (dinf) TD_CUDA(ctx->listC.ensure(sizeof(long long) * cap));
   const long long* cur = ctx->listA.as<long long>();
-  long long* spill = dinf ? ctx->listB.as<long long>() : nullptr;
+  long long* spill = (dinf || river) ? ctx->listB.as<long long>() : nullptr;
   long long* other = dinf ? ctx->listC.as<long long>() : nullptr;
   for (;;) {
     TD_CUDA(cudaMemsetAsync(a.ctr, 0, 3 * sizeof(unsigned long long), st));
-    a.list = cur; a.nlist = n; a.spill = spill; a.spill_cap = dinf ? cap : 0;
+    a.list = cur; a.nlist = n; a.spill = spill; a.spill_cap = spill ? cap : 0; a.river_hops = river;
     const int grid = dinf ? walk_grid<true>(n) : walk_grid<false>(n);
     if (grid < 1) { set_error("walk kernel does not fit on an SM"); return TD_ERR_CUDA; }
     if (dinf) k_walk<true><<<grid, 256, 0, st>>>(a); else k_walk<false><<<grid, 256, 0, st>>>(a);
     TD_LAUNCHED();
     TD_CUDA(cudaGetLastError());
-    if (!dinf) break;                    // D8 chains never fork: nothing can spill
+    if (!dinf && !river) break;          // D8 chains never fork: nothing can spill
     TD_CUDA(cudaMemcpyAsync(hc, a.ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));
     if (hc[2]) { set_error("areadinf: ready-cell spill list exhausted"); return TD_ERR_ALLOC; }
     n = hc[1];
     if (n == 0) break;
+    if (!dinf) {
+      // the parked river heads: one warp each, with look-ahead; rivers that meet continue as one (last arrival)
+      TD_CUDA(cudaMemsetAsync(a.ctr, 0, 3 * sizeof(unsigned long long), st));
+      a.list = spill; a.nlist = n; a.spill = nullptr; a.spill_cap = 0;
+      const int rgrid = (int)std::min<unsigned long long>((unsigned long long)std::max(1, walk_grid<false>(1ull << 40)), (n + 7) / 8);
+      k_river<<<rgrid, 256, 0, st>>>(a);
+      TD_LAUNCHED();
+      TD_CUDA(cudaGetLastError());
+      break;
+    }
     cur = spill; std::swap(spill, other);
   }
   return TD_OK;

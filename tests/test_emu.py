@@ -240,3 +240,14 @@ def test_emulated_d8_stencil_ties_and_near_ties(emu):
             assert emu.emu_d8_stencil(f.ctypes.data, p.ctypes.data, sd8.ctypes.data, nx, ny, -3.0e38, dx, dy, nflat.ctypes.data) == 0
             p_ref, sd8_ref = port.d8flowdir(fel, dx=dx, dy=dy, flats=False)
             assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
+
+
+@pytest.mark.parametrize("hops", [1, 3, 20])
+def test_emulated_d8_rivers_with_lookahead(emu, fields, hops, monkeypatch):
+    """TAUDEM_B200_RIVER: chains longer than `hops` cells are parked by k_walk and finished by k_river (one warp per
+    river, look-ahead along the static path, lane-to-lane fold) — same rasters, single strip and row strips."""
+    port, p, _, w = fields
+    monkeypatch.setenv("TAUDEM_B200_RIVER", str(hops))
+    assert_bits(_run(emu, False, 0, 0, p, None, True, 41), port.aread8(p), f"ad8 rivers hops={hops}")
+    assert_bits(_run(emu, False, 1, 2, p, w, False, 42), port.aread8(p, weights=w, contcheck=False), f"ad8 -wg -nc rivers hops={hops}")
+    assert_bits(_run(emu, False, 1, 2, p, None, True, 43, 3), port.aread8(p), f"ad8 rivers hops={hops}, 3 strips")
