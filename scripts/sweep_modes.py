@@ -1,7 +1,10 @@
-"""A/B of the single-strip sweep implementations (TAUDEM_B200_SWEEP = tiles | hybrid | walk | chain):
-bit-identity of ad8 / sca against the default tile dataflow and CUDA-event timings of the sweep alone.
+"""A/B of the single-strip sweep implementations (TAUDEM_B200_SWEEP = tiles | levels | hybrid | walk | chain):
+bit-identity of ad8 / sca against the first mode listed and CUDA-event timings of the sweep alone.
 
-  python scripts/sweep_modes.py [n=4096] [modes=tiles,hybrid,walk] [reps=3]
+  python scripts/sweep_modes.py [n=4096] [modes=tiles,levels,levels:48,levels+river:64,hybrid,walk] [reps=3]
+
+A mode is NAME[:passes][+river:hops]: `levels:48` = 48 level passes (TAUDEM_B200_LEVELS), `+river:64` = D8 chains
+longer than 64 cells go to the look-ahead river kernel (TAUDEM_B200_RIVER).
 
 Every mode runs under the caller's own `timeout`; a mode that differs prints DIFFERENT and the script
 exits 1 at the end."""
@@ -23,7 +26,7 @@ def timed(fn):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    modes = (sys.argv[2] if len(sys.argv) > 2 else "tiles,hybrid,walk").split(",")
+    modes = (sys.argv[2] if len(sys.argv) > 2 else "tiles,levels,levels:48,levels+river:64,hybrid,walk").split(",")
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
     T = Tools()
     s = DeviceStrip(n, n)
@@ -36,7 +39,12 @@ def main():
     felc.copy_(fel); T.dinf_flats(s, felc, ang, dxc, dyc); del felc, fel
     ref, bad = {}, 0
     for mode in modes:
-        os.environ["TAUDEM_B200_SWEEP"] = mode
+        base, _, river = mode.partition("+river:")
+        name, _, passes = base.partition(":")
+        os.environ["TAUDEM_B200_SWEEP"] = name
+        for key, val in (("TAUDEM_B200_LEVELS", passes), ("TAUDEM_B200_RIVER", river)):
+            if val: os.environ[key] = val
+            else: os.environ.pop(key, None)
         for tool in ("aread8", "areadinf"):
             out = s.empty(torch.float32)
             best = 1e30
@@ -52,9 +60,9 @@ def main():
                 same = torch.equal(own.view(torch.int32), ref[tool].view(torch.int32))
                 verdict = "identical" if same else f"DIFFERENT ({int((own.view(torch.int32) != ref[tool].view(torch.int32)).sum())} cells)"
                 bad += 0 if same else 1
-            print(f"{mode:7s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}", flush=True)
+            print(f"{mode:18s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}", flush=True)
             del out
-    os.environ.pop("TAUDEM_B200_SWEEP", None)
+    for key in ("TAUDEM_B200_SWEEP", "TAUDEM_B200_LEVELS", "TAUDEM_B200_RIVER"): os.environ.pop(key, None)
     sys.exit(1 if bad else 0)
 
 
