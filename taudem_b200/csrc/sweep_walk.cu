@@ -296,11 +296,11 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
       const int nr = eval_cell<DINF>(a, ci, r, c, nd, ready, rnd);
       atomicAdd(a.cntw + (ci >> 2), 0xfeu << ((unsigned)(ci & 3) * 8u));     // 0 -> 0xFE (evaluated), like k_level and the tile kernel
       if (nr >= 1) { cur = ready[0]; curnd = rnd[0]; have_nd = true; } else cur = -1;
-      if (!DINF && a.river_hops > 0 && cur >= 0 && ++hops >= a.river_hops) {
+      if (a.river_hops > 0 && cur >= 0 && ++hops >= a.river_hops) {
         // a long chain: most likely a river.  Its next cell (ready, not evaluated) goes to the river list, where a
         // whole warp follows it with look-ahead (k_river) once the short chains are done.
         const unsigned long long g = atomicAdd(a.ctr + 1, 1ull);
-        if (g < a.spill_cap) { a.spill[g] = cur; cur = -1; } else atomicAdd(a.ctr + 1, ~0ull);   // list full: keep walking
+        if (g < a.spill_cap) { a.spill[g] = cur; cur = -1; hops = 0; } else atomicAdd(a.ctr + 1, ~0ull);   // list full: keep walking
       }
       if (DINF && nr == 2) fork = ready[1];
     }
@@ -325,14 +325,18 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
   }
 }
 
-// D8 rivers.  A chain never forks and its path is static (the direction codes), so a warp can look ahead: it
-// follows the path from a ready head for up to 32 cells, as long as the next cell's only missing arrival is
-// the cell before it on the path (count byte == 1: every other contributor has released its area).  Those
-// cells are resolved together — contributors gathered by all lanes at once, then one k-ordered float fold per
-// cell handed from lane to lane by shuffle (the exact sequence of additions of src/aread8.cpp:228-257) — with
-// ONE memory round trip per cell (node word + count word of the next cell, issued together) instead of the
-// four dependent ones of a chain walker.  The warp then arrives at the first cell it could not resolve with
-// the usual release + decrement and goes on from there if it was the last arrival.
+// Rivers.  A D8 chain never forks and its path is static (the direction codes); a D-infinity chain is the same
+// for as long as its cells have a single receiver — 87 % of the cells of the longest dependency chain of the
+// 8192^2 test field, three quarters of them in runs of eight or more (flat-resolved valley floors).  So a warp can
+// look ahead: it follows the path from a ready head for up to 32 cells, as long as the next cell's only missing
+// arrival is the cell before it on the path (count byte == 1: every other contributor has released its area).
+// Those cells are resolved together — contributors (and their shares) gathered by all lanes at once, then one
+// k-ordered fold per cell handed from lane to lane by shuffle (the exact sequence of operations of
+// src/aread8.cpp:228-257 / src/areadinf.cpp:187-218) — with ONE memory round trip per cell (node word + count
+// word of the next cell) instead of the four dependent ones of a chain walker.  The warp then arrives at the
+// receiver(s) of the last cell with the usual release + decrement and goes on from one that became ready; a
+// second one (D-infinity) goes to the spill list for the next launch.
+template <bool DINF>
 __global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
   const Strip& s = a.s;
   const unsigned FULL = 0xffffffffu;
@@ -342,22 +346,23 @@ __global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
     if (lane == 0) { const unsigned long long t = atomicAdd(a.ctr, 1ull); if (t < a.nlist) head = a.list[t]; }
     head = __shfl_sync(FULL, head, 0);
     if (head < 0) return;
-    int hr = (int)(head / s.pitch), hc = (int)(head - (long long)hr * s.pitch);
-    unsigned hnd = a.node[head];
     for (;;) {
+      const int hr = (int)(head / s.pitch), hc = (int)(head - (long long)hr * s.pitch);
+      const unsigned hnd = a.node[head];
       if (lane == 0) (void)ld_acquire(a.cntw + (head >> 2));   // what the head's contributors released ...
       __syncwarp();                                            // ... is visible to every lane of the warp
       // ---- 1. the path: the same loop in every lane (uniform loads), lane i keeps cell i
       long long ci = head; int r = hr, c = hc; unsigned nd = hnd; int kp = 0;
-      long long my = -1; int mykp = 0; unsigned mynd = 0;
-      long long nxt = -1; int nxr = 0, nxc = 0; unsigned nxnd = 0; bool halo_exit = false;
+      long long my = -1; int mykp = 0, myr = 0, myc = 0; unsigned mynd = 0;
+      long long nxt = -1; int nxr = 0, nxc = 0; bool halo_exit = false;
       int len = 0;
       for (int i = 0; i < 32; ++i) {
-        if (lane == i) { my = ci; mynd = nd; mykp = kp; }
+        if (lane == i) { my = ci; mynd = nd; mykp = kp; myr = r; myc = c; }
         len = i + 1;
         nxt = -1;
-        const int d = (int)((nd >> 8) & 0xfu);
+        const int d = (int)((nd >> 8) & 0xfu);               // D8: the direction; D-infinity: the first receiver
         if (d < 1 || d > 8) break;
+        if (DINF && (nd & 0x2000u)) break;                   // two receivers: the batch ends with this cell
         const int rn = r + drow(d), cn = c + dcol(d);
         if (!s.on_grid(rn, cn)) break;
         if (rn == 0 || rn == s.ny + 1) { halo_exit = true; nxr = rn; nxc = cn; break; }
@@ -367,34 +372,57 @@ __global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
         if (lane == 0) cw = ld_acquire(a.cntw + (cin >> 2));
         cw = __shfl_sync(FULL, cw, 0);                    // (the shuffle also orders the other lanes' later loads behind the acquire)
         if (!(ndn & NODE_VALID)) break;
-        nxt = cin; nxr = rn; nxc = cn; nxnd = ndn;
+        nxt = cin; nxr = rn; nxc = cn;
         if (((cw >> ((unsigned)(cin & 3) * 8u)) & 0xffu) != 1u || i == 31) break;   // not resolvable ahead of time: arrive there
         kp = d > 4 ? d - 4 : d + 4;                      // the direction from the next cell back to this one
         ci = cin; r = rn; c = cn; nd = ndn;
       }
-      // ---- 2. the areas of the contributors that are not on the path (all final)
+      // ---- 2. the contributors that are not on the path (all final): areas, and for D-infinity every contributor's share
       const unsigned m = lane < len ? (mynd & 0xffu) : 0u;
       float an[8];
+      double pk[DINF ? 8 : 1];
 #pragma unroll
       for (int k = 1; k <= 8; ++k) {
-        const bool in = ((m >> (k - 1)) & 1u) && k != mykp;
-        an[k - 1] = in ? __ldcg(a.area + my + (long long)drow(k) * s.pitch + dcol(k)) : 0.f;
+        const bool in = ((m >> (k - 1)) & 1u) != 0u;
+        const long long ni = my + (long long)drow(k) * s.pitch + dcol(k);
+        an[k - 1] = (in && k != mykp) ? __ldcg(a.area + ni) : 0.f;
+        if (DINF) {
+          double p = 0.;
+          if (in) {
+            const float av = a.ang[ni];
+            const unsigned nn = a.node[ni];
+            const int kk = k > 4 ? k - 4 : k + 4, rn = myr + drow(k), k1n = (int)((nn >> 8) & 0xfu);
+            const double t = a.theta[min(max(rn - 1, 0), s.ny - 1)];
+            if ((nn & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
+              const double mid = aref(k1n, t), hi = aref(k1n + 1, t);
+              p = (kk == k1n) ? (hi - av) / (hi - mid) : (av - mid) / (hi - mid);
+            } else p = share_full(av, t, kk);
+          }
+          pk[k - 1] = p;
+        }
       }
       float wv = 1.0f;
-      if (a.usew && lane < len) { const float x = a.w[my]; wv = nd_f(x, a.w_nodata) ? -1.0f : x; }
-      // ---- 3. the fold, one cell after the other (src/aread8.cpp:228-257)
+      double dxr = 0.;
+      if (lane < len) {
+        if (a.usew) { const float x = a.w[my]; wv = (!DINF && nd_f(x, a.w_nodata)) ? -1.0f : x; }
+        else if (DINF) dxr = a.dxc[myr - 1];
+      }
+      // ---- 3. the fold, one cell after the other
       float val = 0.f;
       for (int i = 0; i < len; ++i) {
         const float prev = __shfl_sync(FULL, val, (i + 31) & 31);
         if (lane == i) {
           bool con = (mynd & NODE_CON) != 0;
-          float v = wv;
+          float v = DINF ? 0.f : wv;
 #pragma unroll
           for (int k = 1; k <= 8; ++k)
             if ((m >> (k - 1)) & 1u) {
               const float x = k == mykp ? prev : an[k - 1];
-              if (nd_f(x, -1.0f)) con = true; else v = v + x;
+              if (nd_f(x, -1.0f)) con = true;
+              else if (DINF) v = (float)((double)v + pk[DINF ? k - 1 : 0] * (double)x);
+              else v = v + x;
             }
+          if (DINF) { if (a.usew) v = v + wv; else v = (float)((double)v + dxr); }
           if (con && a.contcheck) v = -1.0f;
           val = v;
         }
@@ -404,15 +432,35 @@ __global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
         a.area[my] = val;
         atomicAdd(a.cntw + (my >> 2), (lane == 0 ? 0xfeu : 0xfdu) << ((unsigned)(my & 3) * 8u));
       }
-      // ---- 5. arrive at the next cell of the path (release of the last area, decrement)
+      // ---- 5. the last cell of the batch arrives at its receiver(s): release of its area, decrement
       long long newhead = -1;
       if (lane == len - 1) {
-        if (halo_exit) { __threadfence(); atomicAdd(a.halo + (nxr == 0 ? 0 : s.pitch) + nxc, 1); }
-        else if (nxt >= 0 && dec_count(a.cntw, nxt) == 1u) newhead = nxt;
+        if (!DINF || !(mynd & 0x2000u)) {                    // one receiver: the cell the path search stopped at
+          if (halo_exit) { __threadfence(); atomicAdd(a.halo + (nxr == 0 ? 0 : s.pitch) + nxc, 1); }
+          else if (nxt >= 0 && dec_count(a.cntw, nxt) == 1u) newhead = nxt;
+        } else {                                             // src/areadinf.cpp:221-239
+          const int k1 = (int)((mynd >> 8) & 0xfu);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int k = j == 0 ? k1 : k1 % 8 + 1;
+            const int rn = myr + drow(k), cn = myc + dcol(k);
+            if (!s.on_grid(rn, cn)) continue;
+            const long long cin = s.idx(rn, cn);
+            if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
+            if (!(a.node[cin] & NODE_VALID)) continue;
+            if (dec_count(a.cntw, cin) == 1u) {
+              if (newhead < 0) newhead = cin;
+              else {
+                const unsigned long long g = atomicAdd(a.ctr + 1, 1ull);
+                if (g < a.spill_cap) a.spill[g] = cin; else a.ctr[2] = 1ull;
+              }
+            }
+          }
+        }
       }
       newhead = __shfl_sync(FULL, newhead, len - 1);
       if (newhead < 0) break;
-      head = newhead; hr = nxr; hc = nxc; hnd = nxnd;
+      head = newhead;
     }
   }
 }
@@ -501,38 +549,38 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   k_ready<true><<<blocks, 256, 0, st>>>(a.cntw, a.node, s, a.ctr, ctx->listA.as<long long>());
   TD_LAUNCHED();
   const unsigned long long cap = (unsigned long long)s.nx * s.ny / 16 + 65536;
-  // D8: TAUDEM_B200_RIVER = number of cells after which a chain is parked for k_river (0 / unset = off)
-  int river = 0;
-  if (!dinf) { const char* e = getenv("TAUDEM_B200_RIVER"); river = e ? std::max(0, atoi(e)) : 0; }
-  if (dinf || river) TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap));
-  if (dinf) TD_CUDA(ctx->listC.ensure(sizeof(long long) * cap));
+  // TAUDEM_B200_RIVER = number of cells after which a lane parks its chain for k_river (0 / unset = off)
+  const char* re = getenv("TAUDEM_B200_RIVER");
+  const int river = re ? std::max(0, atoi(re)) : 0;
+  const bool lists = dinf || river;
+  if (lists) { TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap)); TD_CUDA(ctx->listC.ensure(sizeof(long long) * cap)); }
   const long long* cur = ctx->listA.as<long long>();
-  long long* spill = (dinf || river) ? ctx->listB.as<long long>() : nullptr;
-  long long* other = dinf ? ctx->listC.as<long long>() : nullptr;
+  long long* spill = lists ? ctx->listB.as<long long>() : nullptr;
+  long long* other = lists ? ctx->listC.as<long long>() : nullptr;
+  bool first = true;
   for (;;) {
     TD_CUDA(cudaMemsetAsync(a.ctr, 0, 3 * sizeof(unsigned long long), st));
-    a.list = cur; a.nlist = n; a.spill = spill; a.spill_cap = spill ? cap : 0; a.river_hops = river;
-    const int grid = dinf ? walk_grid<true>(n) : walk_grid<false>(n);
-    if (grid < 1) { set_error("walk kernel does not fit on an SM"); return TD_ERR_CUDA; }
-    if (dinf) k_walk<true><<<grid, 256, 0, st>>>(a); else k_walk<false><<<grid, 256, 0, st>>>(a);
+    a.list = cur; a.nlist = n; a.spill = spill; a.spill_cap = lists ? cap : 0; a.river_hops = river;
+    if (first || !river) {
+      // chain walking, one chain per lane (the spill list receives overflowing forks and, with `river`, parked chains)
+      const int grid = dinf ? walk_grid<true>(n) : walk_grid<false>(n);
+      if (grid < 1) { set_error("walk kernel does not fit on an SM"); return TD_ERR_CUDA; }
+      if (dinf) k_walk<true><<<grid, 256, 0, st>>>(a); else k_walk<false><<<grid, 256, 0, st>>>(a);
+    } else {
+      // what was parked or spilled: one warp each, with look-ahead; rivers that meet continue as one (last arrival)
+      const int per_dev = dinf ? walk_grid<true>(1ull << 40) : walk_grid<false>(1ull << 40);
+      const int rgrid = (int)std::min<unsigned long long>((unsigned long long)std::max(1, per_dev), (n + 7) / 8);
+      if (dinf) k_river<true><<<rgrid, 256, 0, st>>>(a); else k_river<false><<<rgrid, 256, 0, st>>>(a);
+    }
     TD_LAUNCHED();
     TD_CUDA(cudaGetLastError());
-    if (!dinf && !river) break;          // D8 chains never fork: nothing can spill
+    first = false;
+    if (!lists) break;                   // D8 chains never fork: nothing can spill
     TD_CUDA(cudaMemcpyAsync(hc, a.ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));
-    if (hc[2]) { set_error("areadinf: ready-cell spill list exhausted"); return TD_ERR_ALLOC; }
+    if (hc[2]) { set_error("contributing area: ready-cell spill list exhausted"); return TD_ERR_ALLOC; }
     n = hc[1];
     if (n == 0) break;
-    if (!dinf) {
-      // the parked river heads: one warp each, with look-ahead; rivers that meet continue as one (last arrival)
-      TD_CUDA(cudaMemsetAsync(a.ctr, 0, 3 * sizeof(unsigned long long), st));
-      a.list = spill; a.nlist = n; a.spill = nullptr; a.spill_cap = 0;
-      const int rgrid = (int)std::min<unsigned long long>((unsigned long long)std::max(1, walk_grid<false>(1ull << 40)), (n + 7) / 8);
-      k_river<<<rgrid, 256, 0, st>>>(a);
-      TD_LAUNCHED();
-      TD_CUDA(cudaGetLastError());
-      break;
-    }
     cur = spill; std::swap(spill, other);
   }
   return TD_OK;

@@ -251,3 +251,14 @@ def test_emulated_d8_rivers_with_lookahead(emu, fields, hops, monkeypatch):
     assert_bits(_run(emu, False, 0, 0, p, None, True, 41), port.aread8(p), f"ad8 rivers hops={hops}")
     assert_bits(_run(emu, False, 1, 2, p, w, False, 42), port.aread8(p, weights=w, contcheck=False), f"ad8 -wg -nc rivers hops={hops}")
     assert_bits(_run(emu, False, 1, 2, p, None, True, 43, 3), port.aread8(p), f"ad8 rivers hops={hops}, 3 strips")
+
+
+@pytest.mark.parametrize("hops", [1, 4, 20])
+def test_emulated_dinf_rivers_with_lookahead(emu, fields, hops, monkeypatch):
+    """The same for D-infinity: the look-ahead runs through stretches of single-receiver cells; a two-receiver cell ends
+    a batch and its second ready receiver goes to the next launch."""
+    port, _, ang, w = fields
+    monkeypatch.setenv("TAUDEM_B200_RIVER", str(hops))
+    assert_bits(_run(emu, True, 0, 0, ang, None, True, 51), port.areadinf(ang), f"sca rivers hops={hops}")
+    assert_bits(_run(emu, True, 1, 2, ang, w, False, 52), port.areadinf(ang, weights=w, contcheck=False), f"sca -wg -nc rivers hops={hops}")
+    assert_bits(_run(emu, True, 1, 2, ang, None, True, 53, 3), port.areadinf(ang), f"sca rivers hops={hops}, 3 strips")
