@@ -60,7 +60,9 @@ def main():
                 same = torch.equal(own.view(torch.int32), ref[tool].view(torch.int32))
                 verdict = "identical" if same else f"DIFFERENT ({int((own.view(torch.int32) != ref[tool].view(torch.int32)).sum())} cells)"
                 bad += 0 if same else 1
-            print(f"{mode:18s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}", flush=True)
+            ph = [T.l.td_ctx_phase_ms(T.ctx, i) for i in range(4)]
+            phases = "" if not any(ph) else "  [levels %.1f ready %.1f walk %.1f river %.1f ms]" % tuple(ph)
+            print(f"{mode:18s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}{phases}", flush=True)
             del out
     for key in ("TAUDEM_B200_SWEEP", "TAUDEM_B200_LEVELS", "TAUDEM_B200_RIVER"): os.environ.pop(key, None)
     sys.exit(1 if bad else 0)

@@ -113,6 +113,8 @@ unsigned long long td_ctx_counter(td_ctx* ctx, int i) {
   return v;
 }
 
+double td_ctx_phase_ms(td_ctx* ctx, int i) { return (ctx && i >= 0 && i < 4) ? ctx->phase_ms[i] : 0.; }
+
 td_ctx* td_ctx_create(void) {
   if (need_device() != TD_OK) return nullptr;
   td_ctx* c = new td_ctx();

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "ctx.h"
 #include "dinf_common.cuh"
@@ -497,6 +498,19 @@ int walk_grid(unsigned long long n) {
   return (int)std::min<unsigned long long>((unsigned long long)per_dev, (n + 255) / 256);
 }
 
+// TAUDEM_B200_TIMING=1: wall-clock milliseconds per phase (with a stream synchronisation at every phase boundary)
+struct PhaseTimer {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+  PhaseTimer(cudaStream_t s) : st(s) { const char* e = getenv("TAUDEM_B200_TIMING"); on = e && atoi(e) > 0; if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); } }
+  void lap(double* acc) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    *acc += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+};
+
 void walk_args(td_ctx* ctx, WalkArgs& a, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
                int contcheck, const double* theta, const double* dxc, int* halo) {
   a.node = ctx->node.as<unsigned short>(); a.cntw = ctx->cnt.as<unsigned>();
@@ -521,11 +535,14 @@ int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w
   walk_args(ctx, a, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo);
   const long long groups = (long long)(s.pitch >> 4) * s.ny;
   const unsigned blocks = (unsigned)((groups + 255) / 256);
+  for (double& v : ctx->phase_ms) v = 0.;
+  PhaseTimer tm(st);
   for (int p = 0; p < passes; ++p) {
     if (dinf) k_level<true><<<blocks, 256, 0, st>>>(a); else k_level<false><<<blocks, 256, 0, st>>>(a);
     TD_LAUNCHED();
   }
   TD_CUDA(cudaGetLastError());
+  tm.lap(&ctx->phase_ms[0]);
   return TD_OK;
 }
 
@@ -538,6 +555,7 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   unsigned long long* hc = ctx->h_ctr + 16;
   const long long words = (long long)(s.pitch >> 2) * s.ny;
   const unsigned blocks = (unsigned)((words + 255) / 256);
+  PhaseTimer tm(st);
   TD_CUDA(cudaMemsetAsync(a.ctr, 0, 4 * sizeof(unsigned long long), st));
   k_ready<false><<<blocks, 256, 0, st>>>(a.cntw, a.node, s, a.ctr, nullptr);
   TD_LAUNCHED();
@@ -548,6 +566,7 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   TD_CUDA(ctx->listA.ensure(sizeof(long long) * n));
   k_ready<true><<<blocks, 256, 0, st>>>(a.cntw, a.node, s, a.ctr, ctx->listA.as<long long>());
   TD_LAUNCHED();
+  tm.lap(&ctx->phase_ms[1]);
   const unsigned long long cap = (unsigned long long)s.nx * s.ny / 16 + 65536;
   // TAUDEM_B200_RIVER = number of cells after which a lane parks its chain for k_river (0 / unset = off)
   const char* re = getenv("TAUDEM_B200_RIVER");
@@ -574,6 +593,7 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
     }
     TD_LAUNCHED();
     TD_CUDA(cudaGetLastError());
+    tm.lap(&ctx->phase_ms[(first || !river) ? 2 : 3]);
     first = false;
     if (!lists) break;                   // D8 chains never fork: nothing can spill
     TD_CUDA(cudaMemcpyAsync(hc, a.ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
