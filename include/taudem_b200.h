@@ -95,6 +95,22 @@ int td_aread8_host(const int16_t* p, const float* w /*NULL unless usew*/, float*
 int td_area_host(const float* ang, const float* w /*NULL unless usew*/, float* sca, int nx, int ny,
                  float ang_nodata, float w_nodata, const double* dxc, const double* dyc,
                  int contcheck);
+/* The same with outlets (-o; the outlet branches of initNeighborD8up / initNeighborDinfup,
+ * src/commonLib.cpp:285-385, 137-237): only the cells upstream of the outlet cells (column, row; points
+ * off the grid are ignored) are evaluated, everything else keeps the nodata value -1.  nout < 0: no
+ * outlets, the whole grid.                                                                            */
+int td_aread8_outlets_host(const int16_t* p, const float* w, float* ad8, int nx, int ny,
+                           int16_t p_nodata, float w_nodata, int contcheck,
+                           const int* outlet_cols, const int* outlet_rows, int nout);
+int td_area_outlets_host(const float* ang, const float* w, float* sca, int nx, int ny,
+                         float ang_nodata, float w_nodata, const double* dxc, const double* dyc,
+                         int contcheck, const int* outlet_cols, const int* outlet_rows, int nout);
+
+/* Outlet points of a data source (src/ReadOutlets.cpp:49-189 reads them through OGR): ESRI shapefile
+ * (.shp, Point / PointZ / PointM) or GeoJSON Point features; a directory is a data source whose layers are
+ * its .shp files.  Writes up to cap points, *n = number of points in the layer.  No GPU needed.        */
+int td_outlets_read(const char* datasrc, const char* lyrname, int uselyrname, int lyrno,
+                    double* x, double* y, int cap, int* n);
 
 /* ---- 3. device-strip level ----------------------------------------------------------- */
 typedef struct td_strip {
@@ -166,6 +182,10 @@ int td_dinf_slopes_dev(td_ctx*, const float* fel, float* ang, float* slp, td_str
                        long long* nflat_out, void* stream);
 int td_dinf_flats_dev(td_ctx*, float* fel, float* ang, td_strip s, const double* dxc,
                       const double* dyc, long long* nflat_left, void* stream);
+
+/* -o: restricts the dependency state built by *_deps_dev to the cells upstream of the outlets (host
+ * arrays of grid coordinates, row 0 = first owned row); call between *_deps_dev and *_sweep_dev.       */
+int td_sweep_restrict_dev(td_ctx*, td_strip s, const int* cols, const int* rows, int nout, void* stream);
 
 /* contributing area.  *_deps_dev = initNeighborD8up / initNeighborDinfup
  * (src/commonLib.cpp:240-283, 92-136): fills the strip's dependency state inside ctx.

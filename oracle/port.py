@@ -21,6 +21,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.orc_flood.argtypes = [_P, _P, _P, _I, _I, _F, _I]
         _lib.orc_set_skip_flats.argtypes = [_I]
+        _lib.orc_set_outlets.argtypes = [_P, _P, _I]
         _lib.orc_d8.argtypes = [_P, _P, _P, _I, _I, _F, _P, _P]
         _lib.orc_dinf.argtypes = [_P, _P, _P, _I, _I, _F, _P, _P]
         _lib.orc_aread8.argtypes = [_P, _P, _P, _I, _I, C.c_int16, _F, _I, _I]
@@ -65,7 +66,31 @@ def dinfflowdir(fel, nodata=-3.0e38, dx=30.0, dy=30.0, flats=True):
     return ang, slp
 
 
-def aread8(p, nodata=-32768, weights=None, w_nodata=-9999.0, contcheck=True):
+class _Outlets:
+    """outlets = (cols, rows) grid cells: only the cells upstream of them are evaluated (-o)."""
+    def __init__(self, outlets):
+        self.o = outlets
+    def __enter__(self):
+        if self.o is None:
+            lib().orc_set_outlets(None, None, -1)
+        else:
+            self.c = np.ascontiguousarray(self.o[0], np.int32); self.r = np.ascontiguousarray(self.o[1], np.int32)
+            lib().orc_set_outlets(_p(self.c), _p(self.r), len(self.c))
+    def __exit__(self, *a):
+        lib().orc_set_outlets(None, None, -1)
+
+
+def aread8(p, nodata=-32768, weights=None, w_nodata=-9999.0, contcheck=True, outlets=None):
+    with _Outlets(outlets):
+        return _aread8(p, nodata, weights, w_nodata, contcheck)
+
+
+def areadinf(ang, nodata=-3.4028234663852886e38, weights=None, dx=30.0, dy=30.0, contcheck=True, outlets=None):
+    with _Outlets(outlets):
+        return _areadinf(ang, nodata, weights, dx, dy, contcheck)
+
+
+def _aread8(p, nodata=-32768, weights=None, w_nodata=-9999.0, contcheck=True):
     p = np.ascontiguousarray(p, np.int16); ny, nx = p.shape
     out = np.empty((ny, nx), np.float32)
     w = None if weights is None else np.ascontiguousarray(weights, np.float32)
@@ -73,7 +98,7 @@ def aread8(p, nodata=-32768, weights=None, w_nodata=-9999.0, contcheck=True):
     return out
 
 
-def areadinf(ang, nodata=-3.4028234663852886e38, weights=None, dx=30.0, dy=30.0, contcheck=True):
+def _areadinf(ang, nodata=-3.4028234663852886e38, weights=None, dx=30.0, dy=30.0, contcheck=True):
     ang = np.ascontiguousarray(ang, np.float32); ny, nx = ang.shape
     out = np.empty((ny, nx), np.float32)
     w = None if weights is None else np.ascontiguousarray(weights, np.float32)

@@ -334,12 +334,38 @@ int orc_dinf(const float* fel, float* ang, float* slp, int nx, int ny, float nod
 /* ------------------------------------------------------------------------------------------------
  * aread8: initNeighborD8up (src/commonLib.cpp:240-283) + the evaluation loop (src/aread8.cpp:216-304).
  * ---------------------------------------------------------------------------------------------- */
+/* -o outlets (grid cells; n < 0 = none).  Set before orc_aread8 / orc_areadinf. */
+static int g_nout = -1;
+static const int32_t *g_ocol = NULL, *g_orow = NULL;
+void orc_set_outlets(const int32_t* cols, const int32_t* rows, int n) { g_ocol = cols; g_orow = rows; g_nout = n; }
+
 int orc_aread8(const int16_t* p, const float* w, float* ad8, int nx, int ny, int16_t pnd, float wnd, int usew, int contcheck) {
   const size_t n = (size_t)nx * ny;
   int16_t* nb = (int16_t*)malloc(n * 2);
   int32_t* q = (int32_t*)malloc(n * 4);
   size_t qh = 0, qt = 0;
   for (size_t c = 0; c < n; c++) ad8[c] = -1.0f;
+  if (g_nout >= 0) {
+    /* outlets: src/commonLib.cpp:285-385 — counts only upstream of the outlets, everything else stays nodata */
+    int32_t* tb = (int32_t*)malloc(n * 4 * 9);
+    size_t th = 0, tt = 0;
+    for (size_t c = 0; c < n; c++) nb[c] = MISSINGSHORT;
+    for (int o = 0; o < g_nout; o++) if (INSIDE(g_ocol[o], g_orow[o])) tb[tt++] = (int32_t)IDX(g_ocol[o], g_orow[o]);
+    while (th < tt) {
+      const size_t c = tb[th++];
+      const int i = c % nx, j = c / nx;
+      if (nb[c] != MISSINGSHORT) continue;
+      nb[c] = 0;
+      for (int k = 1; k <= 8; k++) {
+        const int in = i + d1[k], jn = j + d2[k];
+        if (!INSIDE(in, jn) || nds(p[IDX(in, jn)], pnd)) continue;
+        const int16_t d = p[IDX(in, jn)];
+        if (d >= 0 && d <= 8 && (d - k == 4 || d - k == -4)) { tb[tt++] = (int32_t)IDX(in, jn); nb[c]++; }
+      }
+      if (nb[c] == 0) q[qt++] = (int32_t)c;
+    }
+    free(tb);
+  } else
   for (int j = 0; j < ny; j++)
     for (int i = 0; i < nx; i++) {
       const size_t c = IDX(i, j);
@@ -369,7 +395,7 @@ int orc_aread8(const int16_t* p, const float* w, float* ad8, int nx, int ny, int
     const int k = p[c];
     if (k >= 1 && k <= 8) {
       const int in = i + d1[k], jn = j + d2[k];
-      if (INSIDE(in, jn)) { nb[IDX(in, jn)]--; if (nb[IDX(in, jn)] == 0) q[qt++] = (int32_t)IDX(in, jn); }
+      if (INSIDE(in, jn) && nb[IDX(in, jn)] != MISSINGSHORT) { nb[IDX(in, jn)]--; if (nb[IDX(in, jn)] == 0) q[qt++] = (int32_t)IDX(in, jn); }
     }
   }
   free(nb); free(q);
@@ -398,6 +424,27 @@ int orc_areadinf(const float* ang, const float* w, float* sca, int nx, int ny, f
   int32_t* q = (int32_t*)malloc(n * 4);
   size_t qh = 0, qt = 0;
   for (size_t c = 0; c < n; c++) sca[c] = -1.0f;
+  if (g_nout >= 0) {
+    /* outlets: src/commonLib.cpp:137-237 */
+    int32_t* tb = (int32_t*)malloc(n * 4 * 9);
+    size_t th = 0, tt = 0;
+    for (size_t c = 0; c < n; c++) nb[c] = MISSINGSHORT;
+    for (int o = 0; o < g_nout; o++) if (INSIDE(g_ocol[o], g_orow[o])) tb[tt++] = (int32_t)IDX(g_ocol[o], g_orow[o]);
+    while (th < tt) {
+      const size_t c = tb[th++];
+      const int i = c % nx, j = c / nx;
+      if (nb[c] != MISSINGSHORT) continue;
+      nb[c] = 0;
+      for (int k = 1; k <= 8; k++) {
+        const int in = i + d1[k], jn = j + d2[k];
+        if (!INSIDE(in, jn) || ndf(ang[IDX(in, jn)], and_)) continue;
+        const float pf = (float)prop(ang[IDX(in, jn)], (k + 4) % 8, dxc[jn], dyc[jn]);
+        if (pf > 0.0) { tb[tt++] = (int32_t)IDX(in, jn); nb[c]++; }
+      }
+      if (nb[c] == 0) q[qt++] = (int32_t)c;
+    }
+    free(tb);
+  } else
   for (int j = 0; j < ny; j++)
     for (int i = 0; i < nx; i++) {
       const size_t c = IDX(i, j);
@@ -427,7 +474,7 @@ int orc_areadinf(const float* ang, const float* w, float* sca, int nx, int ny, f
     for (int k = 1; k <= 8; k++)
       if (prop(ang[c], k, dxc[j], dyc[j]) > 0.0) {
         const int in = i + d1[k], jn = j + d2[k];
-        if (INSIDE(in, jn)) { nb[IDX(in, jn)]--; if (nb[IDX(in, jn)] == 0) q[qt++] = (int32_t)IDX(in, jn); }
+        if (INSIDE(in, jn) && nb[IDX(in, jn)] != MISSINGSHORT) { nb[IDX(in, jn)]--; if (nb[IDX(in, jn)] == 0) q[qt++] = (int32_t)IDX(in, jn); }
       }
   }
   free(nb); free(q);

@@ -76,9 +76,12 @@ class RefPipeline:
         _, self.times["dinfflowdir"] = run_tool("dinfflowdir", ["-fel", self.path("felin.tif"), "-ang", self.path("ang.tif"), "-slp", self.path("slp.tif")], self.np_ranks)
         return self.get("ang.tif", np.float32), self.get("slp.tif", np.float32)
 
-    def aread8(self, p, nodata=-32768, weights=None, w_nodata=-9999.0, contcheck=True):
+    def aread8(self, p, nodata=-32768, weights=None, w_nodata=-9999.0, contcheck=True, outlets=None):
+        """outlets: path of a point shapefile (-o)."""
         self.put("pin.tif", p.astype(np.int16), nodata)
         args = ["-p", self.path("pin.tif"), "-ad8", self.path("ad8.tif")]
+        if outlets is not None:
+            args += ["-o", outlets]
         if weights is not None:
             self.put("w.tif", weights, w_nodata)
             args += ["-wg", self.path("w.tif")]
@@ -87,9 +90,11 @@ class RefPipeline:
         _, self.times["aread8"] = run_tool("aread8", args, self.np_ranks)
         return self.get("ad8.tif", np.float32)
 
-    def areadinf(self, ang, nodata=-3.4028234663852886e38, weights=None, w_nodata=-9999.0, contcheck=True):
+    def areadinf(self, ang, nodata=-3.4028234663852886e38, weights=None, w_nodata=-9999.0, contcheck=True, outlets=None):
         self.put("angin.tif", ang, nodata)
         args = ["-ang", self.path("angin.tif"), "-sca", self.path("sca.tif")]
+        if outlets is not None:
+            args += ["-o", outlets]
         if weights is not None:
             self.put("w.tif", weights, w_nodata)
             args += ["-wg", self.path("w.tif")]

@@ -110,30 +110,65 @@ int OSRIsProjected(OGRSpatialReferenceH h) { return !(h && *(const char*)h == 'G
 double OSRGetLinearUnits(OGRSpatialReferenceH, char** n) { if (n) *n = (char*)"unknown"; return 1.0; }
 const char* OSRGetAttrValue(OGRSpatialReferenceH, const char*, int) { return NULL; }
 
-// OGR (outlets, -o): not part of the oracle's coverage; every open fails cleanly.
+// OGR (outlets, -o): a point shapefile is a data source with one layer named after the file; no attribute table
+// (readoutlets then numbers the outlets itself, src/ReadOutlets.cpp:178-180).  Own little .shp parser: main header
+// 100 bytes (shape type at byte 32, little endian), records = 8-byte big-endian header + content starting with
+// the shape type and x, y as little-endian doubles.
+struct ShimLayer { std::string name; int type = 0; std::vector<double> x, y; size_t next = 0; };
+struct ShimFeature { double x, y; };
 void OGRRegisterAll(void) {}
-OGRDataSourceH OGROpen(const char*, int, OGRSFDriverH*) { return NULL; }
-OGRLayerH OGR_DS_GetLayer(OGRDataSourceH, int) { return NULL; }
-OGRLayerH OGR_DS_GetLayerByName(OGRDataSourceH, const char*) { return NULL; }
-int OGR_DS_GetLayerCount(OGRDataSourceH) { return 0; }
-void OGR_DS_Destroy(OGRDataSourceH) {}
-const char* OGR_L_GetName(OGRLayerH) { return ""; }
-OGRwkbGeometryType OGR_L_GetGeomType(OGRLayerH) { return wkbUnknown; }
+OGRDataSourceH OGROpen(const char* path, int, OGRSFDriverH*) {
+  FILE* fp = fopen(path, "rb");
+  if (!fp) return NULL;
+  std::vector<unsigned char> b;
+  unsigned char tmp[4096]; size_t n;
+  while ((n = fread(tmp, 1, sizeof tmp, fp)) > 0) b.insert(b.end(), tmp, tmp + n);
+  fclose(fp);
+  if (b.size() < 100 || !(b[0] == 0 && b[1] == 0 && b[2] == 0x27 && b[3] == 0x0a)) return NULL;
+  ShimLayer* L = new ShimLayer;
+  std::string p = path;
+  const size_t sl = p.find_last_of('/'), dot = p.rfind('.');
+  L->name = p.substr(sl == std::string::npos ? 0 : sl + 1, dot - (sl == std::string::npos ? 0 : sl + 1));
+  memcpy(&L->type, &b[32], 4);
+  for (size_t pos = 100; pos + 8 <= b.size();) {
+    const size_t len = 2 * (((size_t)b[pos + 4] << 24) | ((size_t)b[pos + 5] << 16) | ((size_t)b[pos + 6] << 8) | b[pos + 7]);
+    if (pos + 8 + len > b.size()) break;
+    int st; memcpy(&st, &b[pos + 8], 4);
+    if (len >= 20 && (st == 1 || st == 11 || st == 21)) { double x, y; memcpy(&x, &b[pos + 12], 8); memcpy(&y, &b[pos + 20], 8); L->x.push_back(x); L->y.push_back(y); }
+    pos += 8 + len;
+  }
+  return (OGRDataSourceH)L;
+}
+OGRLayerH OGR_DS_GetLayer(OGRDataSourceH ds, int i) { return i == 0 ? (OGRLayerH)ds : NULL; }
+OGRLayerH OGR_DS_GetLayerByName(OGRDataSourceH ds, const char* nm) { return (ds && nm && ((ShimLayer*)ds)->name == nm) ? (OGRLayerH)ds : NULL; }
+int OGR_DS_GetLayerCount(OGRDataSourceH ds) { return ds ? 1 : 0; }
+void OGR_DS_Destroy(OGRDataSourceH ds) { delete (ShimLayer*)ds; }
+const char* OGR_L_GetName(OGRLayerH l) { return l ? ((ShimLayer*)l)->name.c_str() : ""; }
+OGRwkbGeometryType OGR_L_GetGeomType(OGRLayerH l) {
+  const int t = l ? ((ShimLayer*)l)->type : 0;
+  return (t == 1 || t == 11 || t == 21) ? wkbPoint : wkbUnknown;
+}
 OGRSpatialReferenceH OGR_L_GetSpatialRef(OGRLayerH) { return NULL; }
-GIntBig OGR_L_GetFeatureCount(OGRLayerH, int) { return 0; }
+GIntBig OGR_L_GetFeatureCount(OGRLayerH l, int) { return l ? (GIntBig)((ShimLayer*)l)->x.size() : 0; }
 OGRFeatureDefnH OGR_L_GetLayerDefn(OGRLayerH) { return NULL; }
-void OGR_L_ResetReading(OGRLayerH) {}
-OGRFeatureH OGR_L_GetNextFeature(OGRLayerH) { return NULL; }
+void OGR_L_ResetReading(OGRLayerH l) { if (l) ((ShimLayer*)l)->next = 0; }
+OGRFeatureH OGR_L_GetNextFeature(OGRLayerH l) {
+  ShimLayer* L = (ShimLayer*)l;
+  if (!L || L->next >= L->x.size()) return NULL;
+  ShimFeature* f = new ShimFeature{L->x[L->next], L->y[L->next]};
+  ++L->next;
+  return (OGRFeatureH)f;
+}
 OGRFeatureH OGR_L_GetFeature(OGRLayerH, GIntBig) { return NULL; }
-OGRGeometryH OGR_F_GetGeometryRef(OGRFeatureH) { return NULL; }
+OGRGeometryH OGR_F_GetGeometryRef(OGRFeatureH f) { return (OGRGeometryH)f; }
 int OGR_F_GetFieldIndex(OGRFeatureH, const char*) { return -1; }
 int OGR_F_GetFieldAsInteger(OGRFeatureH, int) { return 0; }
 GIntBig OGR_F_GetFieldAsInteger64(OGRFeatureH, int) { return 0; }
 double OGR_F_GetFieldAsDouble(OGRFeatureH, int) { return 0; }
 const char* OGR_F_GetFieldAsString(OGRFeatureH, int) { return ""; }
-void OGR_F_Destroy(OGRFeatureH) {}
+void OGR_F_Destroy(OGRFeatureH f) { delete (ShimFeature*)f; }
 OGRFieldDefnH OGR_FD_GetFieldDefn(OGRFeatureDefnH, int) { return NULL; }
 OGRFieldType OGR_Fld_GetType(OGRFieldDefnH) { return OFTInteger; }
-double OGR_G_GetX(OGRGeometryH, int) { return 0; }
-double OGR_G_GetY(OGRGeometryH, int) { return 0; }
+double OGR_G_GetX(OGRGeometryH g, int) { return g ? ((ShimFeature*)g)->x : 0; }
+double OGR_G_GetY(OGRGeometryH g, int) { return g ? ((ShimFeature*)g)->y : 0; }
 }

@@ -48,6 +48,10 @@ SIGNATURES = {
     "td_setdir_host": (_I, [_P, _P, _P, _I, _I, _F, _P, _P]),
     "td_aread8_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _F, _I]),
     "td_area_host": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _I]),
+    "td_aread8_outlets_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _F, _I, _P, _P, _I]),
+    "td_area_outlets_host": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _I, _P, _P, _I]),
+    "td_sweep_restrict_dev": (_I, [_P, Strip, _P, _P, _I, _P]),
+    "td_outlets_read": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _I, _P]),
     "td_ctx_create": (_P, []),
     "td_ctx_destroy": (None, [_P]),
     "td_pitch_for": (_I, [_I]),

@@ -124,20 +124,42 @@ def dinfflowdir_grid(fel, nodata=float(FEL_NODATA), dx=30.0, dy=30.0, out=None):
     return ang, slp
 
 
-def aread8_grid(p, nodata=int(MISSINGSHORT), weights=None, w_nodata=-9999.0, contcheck=True, out=None):
+def _outlet_args(outlets):
+    """outlets = (cols, rows) of the outlet cells -> (cols array, rows array, n); None -> no outlets (n = -1)."""
+    if outlets is None:
+        return None, None, -1
+    c = np.ascontiguousarray(outlets[0], np.int32); r = np.ascontiguousarray(outlets[1], np.int32)
+    assert c.shape == r.shape and c.ndim == 1
+    return c, r, len(c)
+
+
+def read_outlets(datasrc, lyrname="", uselyrname=0, lyrno=0):
+    """Outlet points (x, y) of a shapefile / GeoJSON data source (readoutlets, src/ReadOutlets.cpp)."""
+    n = C.c_int(0)
+    check(lib().td_outlets_read(_b(datasrc), _b(lyrname), int(uselyrname), int(lyrno), None, None, 0, C.byref(n)))
+    x = np.empty(max(n.value, 1), np.float64); y = np.empty(max(n.value, 1), np.float64)
+    check(lib().td_outlets_read(_b(datasrc), _b(lyrname), int(uselyrname), int(lyrno), _ptr(x), _ptr(y), n.value, C.byref(n)))
+    return x[:n.value], y[:n.value]
+
+
+def aread8_grid(p, nodata=int(MISSINGSHORT), weights=None, w_nodata=-9999.0, contcheck=True, out=None, outlets=None):
     p = _grid(p, np.int16)
     ny, nx = p.shape
     ad8 = out if out is not None else np.empty((ny, nx), np.float32)
     w = None if weights is None else _grid(weights, np.float32)
-    check(lib().td_aread8_host(_ptr(p), _ptr(w), _ptr(ad8), nx, ny, int(nodata), np.float32(w_nodata), int(contcheck)))
+    oc, orow, nout = _outlet_args(outlets)
+    check(lib().td_aread8_outlets_host(_ptr(p), _ptr(w), _ptr(ad8), nx, ny, int(nodata), np.float32(w_nodata), int(contcheck),
+                                       _ptr(oc), _ptr(orow), nout))
     return ad8
 
 
-def areadinf_grid(ang, nodata=float(MISSINGFLOAT), weights=None, w_nodata=-9999.0, dx=30.0, dy=30.0, contcheck=True, out=None):
+def areadinf_grid(ang, nodata=float(MISSINGFLOAT), weights=None, w_nodata=-9999.0, dx=30.0, dy=30.0, contcheck=True, out=None, outlets=None):
     ang = _grid(ang, np.float32)
     ny, nx = ang.shape
     sca = out if out is not None else np.empty((ny, nx), np.float32)
     w = None if weights is None else _grid(weights, np.float32)
     dxc, dyc = _rows(dx, ny), _rows(dy, ny)
-    check(lib().td_area_host(_ptr(ang), _ptr(w), _ptr(sca), nx, ny, np.float32(nodata), np.float32(w_nodata), _ptr(dxc), _ptr(dyc), int(contcheck)))
+    oc, orow, nout = _outlet_args(outlets)
+    check(lib().td_area_outlets_host(_ptr(ang), _ptr(w), _ptr(sca), nx, ny, np.float32(nodata), np.float32(w_nodata), _ptr(dxc), _ptr(dyc),
+                                     int(contcheck), _ptr(oc), _ptr(orow), nout))
     return sca

@@ -308,6 +308,14 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   return TD_OK;
 }
 
+// aread8 / areadinf -o: between *_deps_dev and *_sweep_dev, restricts the dependency state to the cells upstream of the
+// outlets (grid coordinates, row 0 = the strip's first owned row; host arrays).  Single strip.
+int td_sweep_restrict_dev(td_ctx* ctx, td_strip s, const int* cols, const int* rows, int nout, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  if (nout < 0 || (nout > 0 && (!cols || !rows))) { td::set_error("td_sweep_restrict_dev: bad arguments"); return TD_ERR_ARG; }
+  return td::sweep_restrict_upstream(ctx, Strip(s), cols, rows, nout, (cudaStream_t)stream);
+}
+
 // ---- multi-strip sweeps: begin (queue all tiles) / run (until locally drained; crossings into the
 // neighbour strips are counted in halo_out[0..pitch) = row above, [pitch..2*pitch) = row below) /
 // apply (decrements received from the neighbours for my first / last row)
@@ -459,6 +467,12 @@ int td_setdir_host(const float* fel, float* ang, float* slp, int nx, int ny, flo
 }
 
 int td_aread8_host(const int16_t* p, const float* w, float* ad8, int nx, int ny, int16_t p_nodata, float w_nodata, int contcheck) {
+  return td_aread8_outlets_host(p, w, ad8, nx, ny, p_nodata, w_nodata, contcheck, nullptr, nullptr, -1);
+}
+
+// nout < 0: no outlets (the whole grid); nout >= 0: only the cells upstream of the outlets (src/aread8.cpp -o)
+int td_aread8_outlets_host(const int16_t* p, const float* w, float* ad8, int nx, int ny, int16_t p_nodata, float w_nodata, int contcheck,
+                           const int* outlet_cols, const int* outlet_rows, int nout) {
   if (int rc = need_device()) return rc;
   if (!p || !ad8 || nx <= 0 || ny <= 0) { td::set_error("td_aread8_host: bad arguments"); return TD_ERR_ARG; }
   td_ctx* ctx = default_ctx();
@@ -471,6 +485,7 @@ int td_aread8_host(const int16_t* p, const float* w, float* ad8, int nx, int ny,
   if (w) { TD_CUDA(ctx->io[2].ensure(n * 4)); d_w = ctx->io[2].as<float>(); TD_CUDA(h2d(d_w, w, s, st)); }
   Timer t; t.start(st);
   if (int rc = td_aread8_deps_dev(ctx, d_p, d_a, s, p_nodata, st)) return rc;
+  if (nout >= 0) { if (int rc = td_sweep_restrict_dev(ctx, s, outlet_cols, outlet_rows, nout, st)) return rc; }
   if (int rc = td_aread8_sweep_dev(ctx, d_w, d_a, s, w_nodata, w != nullptr, contcheck, st)) return rc;
   td::set_compute_seconds(t.stop(st));
   TD_CUDA(d2h(ad8, d_a, s, st));
@@ -480,6 +495,11 @@ int td_aread8_host(const int16_t* p, const float* w, float* ad8, int nx, int ny,
 
 int td_area_host(const float* ang, const float* w, float* sca, int nx, int ny, float ang_nodata, float w_nodata, const double* dxc,
                  const double* dyc, int contcheck) {
+  return td_area_outlets_host(ang, w, sca, nx, ny, ang_nodata, w_nodata, dxc, dyc, contcheck, nullptr, nullptr, -1);
+}
+
+int td_area_outlets_host(const float* ang, const float* w, float* sca, int nx, int ny, float ang_nodata, float w_nodata, const double* dxc,
+                         const double* dyc, int contcheck, const int* outlet_cols, const int* outlet_rows, int nout) {
   (void)w_nodata;   // the reference adds the raw weight, nodata or not (src/areadinf.cpp:210)
   if (int rc = need_device()) return rc;
   if (!ang || !sca || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_area_host: bad arguments"); return TD_ERR_ARG; }
@@ -495,6 +515,7 @@ int td_area_host(const float* ang, const float* w, float* sca, int nx, int ny, f
   if (w) { TD_CUDA(ctx->io[2].ensure(n * 4)); d_w = ctx->io[2].as<float>(); TD_CUDA(h2d(d_w, w, s, st)); }
   Timer t; t.start(st);
   if (int rc = td_area_deps_dev(ctx, d_ang, d_a, s, ang_nodata, d_dx, d_dy, st)) return rc;
+  if (nout >= 0) { if (int rc = td_sweep_restrict_dev(ctx, s, outlet_cols, outlet_rows, nout, st)) return rc; }
   if (int rc = td_area_sweep_dev(ctx, d_ang, d_w, d_a, s, w != nullptr, contcheck, d_dx, st)) return rc;
   td::set_compute_seconds(t.stop(st));
   TD_CUDA(d2h(sca, d_a, s, st));

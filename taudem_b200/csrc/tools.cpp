@@ -253,25 +253,36 @@ int td_setdir(const char* demfile, const char* angfile, const char* slopefile, c
   return TD_OK;
 }
 
-static int outlets_unsupported(const char* tool) {
-  printf("%s: outlet (-o) evaluation is not available in this build.\n", tool);
-  td::set_error("outlets (-o) are not supported yet");
-  return TD_ERR_MISMATCH;
+// readoutlets + geoToGlobalXY (src/aread8.cpp:112-120,179-188, src/tiffIO.cpp:580-588): outlet points -> grid cells
+static int outlet_cells(const char* datasrc, const char* lyrname, int uselyrname, int lyrno, const Input& in, std::vector<int>* cols,
+                        std::vector<int>* rows) {
+  int n = 0;
+  if (int rc = td_outlets_read(datasrc, lyrname, uselyrname, lyrno, nullptr, nullptr, 0, &n)) { printf("Read outlets error: %s\n", td_last_error()); return rc; }
+  std::vector<double> x(n > 0 ? n : 1), y(n > 0 ? n : 1);
+  if (int rc = td_outlets_read(datasrc, lyrname, uselyrname, lyrno, x.data(), y.data(), n, &n)) return rc;
+  const tdio::GeoInfo& g = in.r.geo();
+  const double xleft = g.gt[0], ytop = g.gt[3], dlon = std::fabs(g.gt[1]), dlat = std::fabs(g.gt[5]);
+  cols->resize(n); rows->resize(n);
+  for (int i = 0; i < n; ++i) {
+    (*cols)[i] = (int)((x[i] - xleft) / dlon);
+    (*rows)[i] = (int)((ytop - y[i]) / dlat);
+  }
+  return TD_OK;
 }
 
 int td_aread8(const char* pfile, const char* afile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, const char* wfile,
               int useOutlets, int usew, int contcheck) {
-  (void)datasrc; (void)lyrname; (void)uselyrname; (void)lyrno;
   {  // src/aread8.cpp:62-71
     FILE* fp = fopen(pfile, "r");
     if (!fp) { fprintf(stderr, "Error: Input file %s does not exist.\n", pfile); td::set_error("input file does not exist"); return TD_ERR_IO; }
     fclose(fp);
   }
   printf("AreaD8 version %s\n", td_version());
-  if (useOutlets) return outlets_unsupported("AreaD8");
   const double t0 = now();
   Input p;
   if (int rc = p.open(pfile)) return rc;
+  std::vector<int> ocols, orows;
+  if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, p, &ocols, &orows)) return rc; }
   std::vector<int16_t> dir;
   nodata_msgs(p.r.nodata(), "int16_t", (int16_t)p.r.nodata());
   if (int rc = p.read(&dir, tdio::DT_I16)) return rc;
@@ -284,8 +295,9 @@ int td_aread8(const char* pfile, const char* afile, const char* datasrc, const c
   }
   const double t1 = now();
   std::vector<float> ad8((size_t)p.nx * p.ny);
-  if (int rc = td_aread8_host(dir.data(), usew ? wg.data() : nullptr, ad8.data(), p.nx, p.ny, (int16_t)p.r.nodata(),
-                              usew ? (float)w.r.nodata() : 0.f, contcheck)) {
+  if (int rc = td_aread8_outlets_host(dir.data(), usew ? wg.data() : nullptr, ad8.data(), p.nx, p.ny, (int16_t)p.r.nodata(),
+                                      usew ? (float)w.r.nodata() : 0.f, contcheck, ocols.data(), orows.data(),
+                                      useOutlets == 1 ? (int)ocols.size() : -1)) {
     printf("AreaD8 device error: %s\n", td_last_error());
     return rc;
   }
@@ -299,12 +311,12 @@ int td_aread8(const char* pfile, const char* afile, const char* datasrc, const c
 
 int td_area(const char* angfile, const char* scafile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, const char* wfile,
             int useOutlets, int usew, int contcheck) {
-  (void)datasrc; (void)lyrname; (void)uselyrname; (void)lyrno;
   printf("AreaDinf version %s\n", td_version());
-  if (useOutlets) return outlets_unsupported("AreaDinf");
   const double t0 = now();
   Input a;
   if (int rc = a.open(angfile)) return rc;
+  std::vector<int> ocols, orows;
+  if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, a, &ocols, &orows)) return rc; }
   std::vector<float> ang;
   nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
   if (int rc = a.read(&ang, tdio::DT_F32)) return rc;
@@ -317,8 +329,9 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
   }
   const double t1 = now();
   std::vector<float> sca((size_t)a.nx * a.ny);
-  if (int rc = td_area_host(ang.data(), usew ? wg.data() : nullptr, sca.data(), a.nx, a.ny, (float)a.r.nodata(),
-                            usew ? (float)w.r.nodata() : 0.f, a.dxc.data(), a.dyc.data(), contcheck)) {
+  if (int rc = td_area_outlets_host(ang.data(), usew ? wg.data() : nullptr, sca.data(), a.nx, a.ny, (float)a.r.nodata(),
+                                    usew ? (float)w.r.nodata() : 0.f, a.dxc.data(), a.dyc.data(), contcheck, ocols.data(), orows.data(),
+                                    useOutlets == 1 ? (int)ocols.size() : -1)) {
     printf("AreaDinf device error: %s\n", td_last_error());
     return rc;
   }

@@ -112,6 +112,7 @@ inline int min(int a, unsigned b) { return a < (int)b ? a : (int)b; }
 #define EMU_ATOMIC(T)                                                                       \
   inline T atomicAdd(T* p, T v) { emu::yield(); T o = *p; *p = (T)(o + v); return o; }       \
   inline T atomicSub(T* p, T v) { emu::yield(); T o = *p; *p = (T)(o - v); return o; }       \
+  inline T atomicOr(T* p, T v) { emu::yield(); T o = *p; *p = (T)(o | v); return o; }         \
   inline T atomicExch(T* p, T v) { emu::yield(); T o = *p; *p = v; return o; }               \
   inline T atomicCAS(T* p, T c, T v) { emu::yield(); T o = *p; if (o == c) *p = v; return o; }
 EMU_ATOMIC(int)

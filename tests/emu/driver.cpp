@@ -4,7 +4,8 @@
 // description of k_deps_d8 / k_deps_dinf (taudem_b200/csrc/area_d8.cu, area_dinf.cu).
 #include <string>
 
-#include "sweep_walk_emu.inc"   // the transformed kernel source (written by tests/test_emu.py)
+#include "sweep_walk_emu.inc"   // the transformed kernel sources (written by tests/test_emu.py)
+#include "outlets_emu.inc"
 
 namespace td {
 unsigned long long g_launches = 0;
@@ -114,13 +115,18 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
 // mode 0: k_ready + k_walk from the sources; mode 1: `passes` level passes first.  nstrips > 1 emulates the
 // exchange rounds of taudem_b200/dist.py::DistTools._sweep (linearpart partition, halo counts, area rows).
 extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float* out, const float* wgt, int nx, int ny, float dir_nodata,
-                         int usew, int contcheck, float w_nodata, double dx, double dy, unsigned long long seed, int nstrips, int* rounds_out) {
+                         int usew, int contcheck, float w_nodata, double dx, double dy, unsigned long long seed, int nstrips, int* rounds_out,
+                         const int* outlet_cols, const int* outlet_rows, int nout) {
   emu::g_rng = seed * 2654435761ull + 1;
   if (nstrips < 1 || ny / nstrips < 1) return 1;
   std::vector<StripState> S(nstrips);
   const int per = ny / nstrips;
   for (int i = 0; i < nstrips; ++i)
     build_strip(S[i], dinf, dir, usew ? wgt : nullptr, nx, ny, i * per, i == nstrips - 1 ? ny - i * per : per, dir_nodata, dx, dy);
+  if (nout >= 0) {          // -o: only the cells upstream of the outlets (single strip)
+    if (nstrips != 1) return 3;
+    if (int rc = td::sweep_restrict_upstream(&S[0].ctx, S[0].s, outlet_cols, outlet_rows, nout, nullptr)) return rc;
+  }
   bool first = true;
   int rounds = 0;
   for (;;) {

@@ -177,3 +177,57 @@ def test_geographic_cell_sizes_match_reference(refrun, tmp_path):
     assert_bits(ang_r, ang_o, "ang"); assert_bits(td.read_raster(str(tmp_path / "slp.tif")), slp_o, "slp")
     refrun.run_tool("areadinf", ["-ang", str(tmp_path / "ang.tif"), "-sca", str(tmp_path / "sca.tif")])
     assert_bits(td.read_raster(str(tmp_path / "sca.tif")), port.areadinf(ang_r, dx=dxc, dy=dyc), "sca")
+
+
+def test_outlet_readers(tmp_path):
+    """td_outlets_read: shapefile Point / PointZ / PointM, GeoJSON points, directory data sources, layer selection."""
+    from util import write_point_geojson, write_point_shapefile
+    xs = [500012.5, 500100.25, 499000.0]; ys = [4100000.75, 4099950.0, 4101000.125]
+    for st in (1, 11, 21):
+        f = str(tmp_path / f"out{st}.shp")
+        write_point_shapefile(f, xs, ys, st)
+        x, y = td.read_outlets(f)
+        assert list(x) == xs and list(y) == ys
+    g = str(tmp_path / "outlets.geojson")
+    write_point_geojson(g, xs, ys)
+    x, y = td.read_outlets(g)
+    assert list(x) == xs and list(y) == ys
+    # a directory is a data source whose layers are its shapefiles (by name, or by number in alphabetical order)
+    x, y = td.read_outlets(str(tmp_path), lyrname="out11", uselyrname=1)
+    assert list(x) == xs
+    x, y = td.read_outlets(str(tmp_path), lyrno=2)                                # out1, out11, out21
+    assert list(x) == xs
+    with pytest.raises(td.TaudemError):
+        td.read_outlets(str(tmp_path), lyrname="nope", uselyrname=1)
+    with pytest.raises(td.TaudemError):
+        td.read_outlets(str(tmp_path / "missing.shp"))
+    with pytest.raises(td.TaudemError):
+        td.read_outlets(str(tmp_path / "out1.shp"), lyrno=1)                        # a file has one layer
+    open(tmp_path / "poly.geojson", "w").write('{"type":"FeatureCollection","features":[{"type":"Feature","geometry":{"type":"LineString","coordinates":[[0,0],[1,1]]}}]}')
+    with pytest.raises(td.TaudemError):
+        td.read_outlets(str(tmp_path / "poly.geojson"))
+
+
+def test_outlets_reference_pins_the_restatement(refrun, tmp_path):
+    """aread8 / areadinf -o: the reference tools (OGR through the shim's point-shapefile reader) against the C
+    restatement's outlet branch, nested and disjoint basins, one point off the grid, 1 and 3 ranks."""
+    from oracle import port
+    from util import write_point_shapefile
+    dem = synth.punch_holes(synth.gen_dem(150, 190, hurst=0.8, tilt=1.0, seed=5))
+    fel = port.pitremove(dem); p, _ = port.d8flowdir(fel); ang, _ = port.dinfflowdir(fel)
+    ny, nx = p.shape
+    order = np.argsort(port.aread8(p).ravel())
+    cells = [int(order[-1]), int(order[-40]), int(order[-300]), int(order[len(order) // 2])]
+    cols = [c % nx for c in cells]; rows = [c // nx for c in cells]
+    dx = dy = 30.0
+    xs = [(c + 0.3) * dx for c in cols] + [-100.0]; ys = [dy * ny - (r + 0.6) * dy for r in rows] + [50.0]   # RefPipeline rasters: origin (0, dy*ny)
+    shp = str(tmp_path / "outlets.shp")
+    write_point_shapefile(shp, xs, ys)
+    # geoToGlobalXY (src/tiffIO.cpp:580-588); the fifth point is left of the grid (column -3) and is ignored
+    ocols = [int((x - 0.0) / dx) for x in xs]; orows = [int((dy * ny - y) / dy) for y in ys]
+    assert ocols[:4] == cols and orows[:4] == rows and ocols[4] == -3
+    for ranks in (1, 3):
+        R = refrun.RefPipeline(workdir=str(tmp_path), dx=dx, dy=dy, np_ranks=ranks)
+        assert_bits(R.aread8(p, outlets=shp), port.aread8(p, outlets=(ocols, orows)), f"ad8 -o, {ranks} ranks")
+        assert_bits(R.areadinf(ang, outlets=shp), port.areadinf(ang, outlets=(ocols, orows)), f"sca -o, {ranks} ranks")
+    assert 100 < int((port.aread8(p, outlets=(ocols, orows)) != -1).sum()) < p.size

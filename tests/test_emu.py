@@ -36,7 +36,7 @@ def _transform(name, min_launches=6):
 
 def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
-    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS]
+    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2)]
     so = os.path.join(BUILD, f"libemu{tag}.so")
     objs = []
     for i, n in enumerate(STENCILS):                       # one translation unit per kernel file (their helper names collide)
@@ -55,7 +55,7 @@ def _build(tag="", defines=()):
                                *[f"-D{d}" for d in defines], "-o", so, *srcs])
     lib = C.CDLL(so)
     lib.emu_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
-                              C.c_float, C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_void_p]
+                              C.c_float, C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     P = C.c_void_p
     lib.emu_d8_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
     lib.emu_dinf_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
@@ -82,14 +82,17 @@ def fields():
     return port, p, ang, w
 
 
-def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, rounds=None):
+def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, rounds=None, outlets=None):
     ny, nx = direction.shape
     out = np.empty((ny, nx), np.float32)
     d = np.ascontiguousarray(direction)
     wp = None if w is None else np.ascontiguousarray(w, np.float32)
     nodata = -3.4028234663852886e38 if dinf else -32768.0
+    oc = None if outlets is None else np.ascontiguousarray(outlets[0], np.int32)
+    orow = None if outlets is None else np.ascontiguousarray(outlets[1], np.int32)
     rc = lib.emu_sweep(int(dinf), mode, passes, d.ctypes.data, out.ctypes.data, None if wp is None else wp.ctypes.data, nx, ny, nodata,
-                       int(w is not None), int(contcheck), -9999.0, 30.0, 30.0, seed, nstrips, None if rounds is None else rounds.ctypes.data)
+                       int(w is not None), int(contcheck), -9999.0, 30.0, 30.0, seed, nstrips, None if rounds is None else rounds.ctypes.data,
+                       None if oc is None else oc.ctypes.data, None if orow is None else orow.ctypes.data, -1 if oc is None else len(oc))
     assert rc == 0
     return out
 
@@ -113,9 +116,13 @@ def test_emulated_dinf_sweeps_match_the_oracle(emu, fields, mode, passes):
 def test_emulated_dinf_fork_stack_spills_to_the_global_list(fields):
     """With a two-entry fork stack per warp nearly every fork spills: the host loop must drain the spill lists."""
     port, _, ang, _ = fields
-    lib = _build("_wq2", ["TD_WALK_WQ=2"])
+    lib = _build("_wq2", ["TD_WALK_WQ=2", "TD_UP_UQ=4"])
     for mode, passes, seed in ((0, 0, 7), (1, 3, 8)):
         assert_bits(_run(lib, True, mode, passes, ang, None, True, seed), port.areadinf(ang), f"sca, spilling, mode {mode}")
+    # the outlet flood with a four-entry stack per warp: nearly every discovered contributor spills
+    full = port.areadinf(ang)
+    c = int(np.argsort(full.ravel())[-1]); outs = ([c % ang.shape[1]], [c // ang.shape[1]])
+    assert_bits(_run(lib, True, 0, 0, ang, None, True, 9, outlets=outs), port.areadinf(ang, outlets=outs), "sca -o, spilling flood")
 
 
 @pytest.mark.parametrize("nstrips", [2, 3])
@@ -262,3 +269,20 @@ def test_emulated_dinf_rivers_with_lookahead(emu, fields, hops, monkeypatch):
     assert_bits(_run(emu, True, 0, 0, ang, None, True, 51), port.areadinf(ang), f"sca rivers hops={hops}")
     assert_bits(_run(emu, True, 1, 2, ang, w, False, 52), port.areadinf(ang, weights=w, contcheck=False), f"sca -wg -nc rivers hops={hops}")
     assert_bits(_run(emu, True, 1, 2, ang, None, True, 53, 3), port.areadinf(ang), f"sca rivers hops={hops}, 3 strips")
+
+
+def test_emulated_outlets_restrict_the_sweep(emu, fields):
+    """-o: k_upstream floods the contributor links from the outlet cells, k_restrict removes every other cell from the
+    flow field; the sweep then evaluates exactly what the reference's outlet branch evaluates."""
+    port, p, ang, w = fields
+    full = port.aread8(p)
+    order = np.argsort(full.ravel())
+    ny, nx = p.shape
+    cells = [int(order[-1]), int(order[-40]), int(order[-300]), int(order[len(order) // 2])]      # nested and disjoint basins, a small one
+    outs = ([c % nx for c in cells] + [-5, nx + 3], [c // nx for c in cells] + [2, 1])              # two points off the grid are ignored
+    ref = port.aread8(p, outlets=outs)
+    assert 100 < int((ref != -1).sum()) < p.size
+    assert_bits(_run(emu, False, 1, 3, p, None, True, 61, outlets=outs), ref, "ad8 -o")
+    assert_bits(_run(emu, False, 0, 0, p, w, False, 62, outlets=outs), port.aread8(p, weights=w, contcheck=False, outlets=outs), "ad8 -o -wg -nc")
+    assert_bits(_run(emu, True, 1, 3, ang, None, True, 63, outlets=outs), port.areadinf(ang, outlets=outs), "sca -o")
+    assert_bits(_run(emu, False, 0, 0, p, None, True, 64, outlets=([], [])), np.full(p.shape, -1.0, np.float32), "ad8 -o without points")

@@ -300,3 +300,39 @@ def test_d8_stencil_ties_and_near_ties():
             p, sd8 = td.d8flowdir_grid(fel, dx=dx, dy=dy)
             p_ref, sd8_ref = port.d8flowdir(fel, dx=dx, dy=dy)
             assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
+
+
+def test_outlets_grid_and_file_level(refrun, tmp_path):
+    """aread8 / areadinf -o: the cells upstream of the outlets only.  Grid level against the C restatement (which the
+    CPU suite pins on the reference tools), file level (our executables with a point shapefile) against the reference
+    executables on the same files."""
+    import os
+    import subprocess
+    from oracle import port
+    from util import write_point_shapefile
+    dem = synth.punch_holes(synth.gen_dem(300, 420, hurst=0.8, tilt=1.0, seed=15))
+    fel = td.pitremove_grid(dem); p, _ = td.d8flowdir_grid(fel); ang, _ = td.dinfflowdir_grid(fel)
+    w = synth.gen_weights(*dem.shape)
+    ny, nx = p.shape
+    order = np.argsort(td.aread8_grid(p).ravel())
+    cells = [int(order[-1]), int(order[-60]), int(order[-900]), int(order[len(order) // 2])]
+    cols = [c % nx for c in cells] + [-4]; rows = [c // nx for c in cells] + [7]
+    outs = (cols, rows)
+    assert_bits(td.aread8_grid(p, outlets=outs), port.aread8(p, outlets=outs), "ad8 -o")
+    assert_bits(td.aread8_grid(p, weights=w, contcheck=False, outlets=outs), port.aread8(p, weights=w, contcheck=False, outlets=outs), "ad8 -o -wg -nc")
+    assert_bits(td.areadinf_grid(ang, outlets=outs), port.areadinf(ang, outlets=outs), "sca -o")
+    assert_bits(td.aread8_grid(p, outlets=([], [])), np.full(p.shape, -1.0, np.float32), "ad8 -o, no points")
+    # file level
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dx = dy = 30.0
+    xs = [(c + 0.5) * dx for c in cols]; ys = [dy * ny - (r + 0.5) * dy for r in rows]
+    shp = str(tmp_path / "outlets.shp")
+    write_point_shapefile(shp, xs, ys)
+    R = refrun.RefPipeline(workdir=str(tmp_path), dx=dx, dy=dy)
+    ad8_ref = R.aread8(p, outlets=shp); sca_ref = R.areadinf(ang, outlets=shp)
+    for tool, inflag, infile, outflag, ref in (("aread8", "-p", "pin.tif", "-ad8", ad8_ref), ("areadinf", "-ang", "angin.tif", "-sca", sca_ref)):
+        out = str(tmp_path / f"ours_{tool}.tif")
+        r = subprocess.run([os.path.join(root, "taudem_b200", "bin", tool), inflag, str(tmp_path / infile), outflag, out, "-o", shp],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout
+        assert_bits(td.read_raster(out), ref, f"{tool} -o (files)")

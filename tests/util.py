@@ -53,3 +53,27 @@ def write_geographic_dem(path, dem, lon0=-111.8, lat0=41.9, cell=0.001, nodata=-
     info.tagtype[33550] = 12; info.tagtype[33922] = 12; info.tagtype[34735] = 3
     info[42113] = repr(float(nodata))
     Image.fromarray(np.ascontiguousarray(dem, np.float32)).save(path, tiffinfo=info)
+
+
+def write_point_shapefile(path, xs, ys, shape_type=1):
+    """Minimal ESRI shapefile (.shp + .shx) with Point (1), PointZ (11) or PointM (21) records."""
+    import struct
+    recs = b""
+    offsets = []
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        content = struct.pack("<idd", shape_type, float(x), float(y))
+        if shape_type == 11: content += struct.pack("<dd", 0.0, 0.0)
+        if shape_type == 21: content += struct.pack("<d", 0.0)
+        offsets.append((50 + len(recs) // 2, len(content) // 2))
+        recs += struct.pack(">ii", i + 1, len(content) // 2) + content
+    bbox = (min(xs), min(ys), max(xs), max(ys)) if len(xs) else (0.0, 0.0, 0.0, 0.0)
+    def header(nwords):
+        return struct.pack(">iiiiiii", 9994, 0, 0, 0, 0, 0, nwords) + struct.pack("<ii", 1000, shape_type) + struct.pack("<dddddddd", *bbox, 0, 0, 0, 0)
+    open(path, "wb").write(header(50 + len(recs) // 2) + recs)
+    open(path[:-4] + ".shx", "wb").write(header(50 + 4 * len(offsets)) + b"".join(struct.pack(">ii", o, l) for o, l in offsets))
+
+
+def write_point_geojson(path, xs, ys):
+    import json
+    feats = [{"type": "Feature", "properties": {"id": i + 1}, "geometry": {"type": "Point", "coordinates": [float(x), float(y)]}} for i, (x, y) in enumerate(zip(xs, ys))]
+    json.dump({"type": "FeatureCollection", "features": feats}, open(path, "w"))
