@@ -82,7 +82,7 @@ def fields():
     return port, p, ang, w
 
 
-def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, rounds=None, outlets=None):
+def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, rounds=None, outlets=None, dx=30.0, dy=30.0):
     ny, nx = direction.shape
     out = np.empty((ny, nx), np.float32)
     d = np.ascontiguousarray(direction)
@@ -91,7 +91,7 @@ def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, roun
     oc = None if outlets is None else np.ascontiguousarray(outlets[0], np.int32)
     orow = None if outlets is None else np.ascontiguousarray(outlets[1], np.int32)
     rc = lib.emu_sweep(int(dinf), mode, passes, d.ctypes.data, out.ctypes.data, None if wp is None else wp.ctypes.data, nx, ny, nodata,
-                       int(w is not None), int(contcheck), -9999.0, 30.0, 30.0, seed, nstrips, None if rounds is None else rounds.ctypes.data,
+                       int(w is not None), int(contcheck), -9999.0, dx, dy, seed, nstrips, None if rounds is None else rounds.ctypes.data,
                        None if oc is None else oc.ctypes.data, None if orow is None else orow.ctypes.data, -1 if oc is None else len(oc))
     assert rc == 0
     return out
@@ -152,11 +152,11 @@ def terraces():
     return port, fel
 
 
-def _flats(lib, dinf, fel, d0, nstrips, seed):
+def _flats(lib, dinf, fel, d0, nstrips, seed, dx=30.0, dy=30.0):
     ny, nx = fel.shape
     d = np.ascontiguousarray(d0).copy()
     left = np.zeros(1, np.int64); coll = np.zeros(1, np.int64)
-    rc = lib.emu_flats(int(dinf), np.ascontiguousarray(fel, np.float32).ctypes.data, d.ctypes.data, nx, ny, 30.0, 30.0, nstrips, seed,
+    rc = lib.emu_flats(int(dinf), np.ascontiguousarray(fel, np.float32).ctypes.data, d.ctypes.data, nx, ny, dx, dy, nstrips, seed,
                        left.ctypes.data, coll.ctypes.data)
     assert rc == 0
     return d, int(left[0]), int(coll[0])
@@ -286,3 +286,56 @@ def test_emulated_outlets_restrict_the_sweep(emu, fields):
     assert_bits(_run(emu, False, 0, 0, p, w, False, 62, outlets=outs), port.aread8(p, weights=w, contcheck=False, outlets=outs), "ad8 -o -wg -nc")
     assert_bits(_run(emu, True, 1, 3, ang, None, True, 63, outlets=outs), port.areadinf(ang, outlets=outs), "sca -o")
     assert_bits(_run(emu, False, 0, 0, p, None, True, 64, outlets=([], [])), np.full(p.shape, -1.0, np.float32), "ad8 -o without points")
+
+
+@pytest.mark.parametrize("rows_per_strip", [1, 2, 3])
+def test_emulated_thin_strips(emu, rows_per_strip):
+    """Strip heights of one to three rows (SURVEY.md extra parity cases): flat resolution and both sweeps over row strips
+    whose first and last row coincide or touch."""
+    from oracle import port
+    ny, nx = 18, 70
+    dem = synth.gen_dem(ny, nx, hurst=0.8, tilt=1.0, seed=23)
+    q = (dem.max() - dem.min()) / 6
+    dem = (np.round(dem / q) * q).astype(np.float32)
+    fel = port.pitremove(dem)
+    n = ny // rows_per_strip
+    p0, _ = port.d8flowdir(fel, flats=False); p_ref, _ = port.d8flowdir(fel)
+    assert (p0 == 0).sum() > 50
+    p, _, _ = _flats(emu, False, fel, p0, n, 71)
+    assert_bits(p, p_ref, f"p, {n} strips of {rows_per_strip} rows")
+    a0, _ = port.dinfflowdir(fel, flats=False); a_ref, _ = port.dinfflowdir(fel)
+    a, _, _ = _flats(emu, True, fel, a0, n, 72)
+    assert_bits(a, a_ref, f"ang, {n} strips of {rows_per_strip} rows")
+    assert_bits(_run(emu, False, 1, 2, p_ref, None, True, 73, n), port.aread8(p_ref), "ad8 thin strips")
+    assert_bits(_run(emu, True, 1, 2, a_ref, None, True, 74, n), port.areadinf(a_ref), "sca thin strips")
+
+
+@pytest.mark.parametrize("name", ["tiny", "plateau", "lake", "hills_holes", "rough"])
+def test_emulated_pipeline_reproduces_the_reference_golden_vectors(emu, name):
+    """fel (golden) -> emulated k_d8_stencil / k_dinf_stencil -> emulated flat resolution (1 and 2 strips) -> emulated
+    dependency state, level passes, walkers and rivers: p, sd8, ang, slp, ad8, sca of the REFERENCE-generated golden
+    vectors (tests/golden/make_golden.py), bit for bit."""
+    from util import load_golden
+    g = load_golden(name)
+    fel = np.ascontiguousarray(g["fel"], np.float32)
+    ny, nx = fel.shape
+    dx, dy = float(g["dx"]), float(g["dy"])
+    f = fel
+    p = np.empty((ny, nx), np.int16); sd8 = np.empty((ny, nx), np.float32); nflat = np.zeros(1, np.uint64)
+    assert emu.emu_d8_stencil(f.ctypes.data, p.ctypes.data, sd8.ctypes.data, nx, ny, -3.0e38, dx, dy, nflat.ctypes.data) == 0
+    assert_bits(sd8, g["sd8"], "sd8")
+    ang = np.empty((ny, nx), np.float32); slp = np.empty((ny, nx), np.float32)
+    assert emu.emu_dinf_stencil(f.ctypes.data, ang.ctypes.data, slp.ctypes.data, nx, ny, -3.0e38, dx, dy, nflat.ctypes.data) == 0
+    assert_bits(slp, g["slp"], "slp")
+    for strips in ((1, 2) if ny >= 8 else (1,)):
+        pr, _, _ = _flats(emu, False, fel, p, strips, 81, dx, dy)
+        assert_bits(pr, g["p"], f"p ({strips} strips)")
+        ar, _, _ = _flats(emu, True, fel, ang, strips, 82, dx, dy)
+        assert_bits(ar, g["ang"], f"ang ({strips} strips)")
+    w = np.ascontiguousarray(g["w"], np.float32)
+    assert_bits(_run(emu, False, 1, 3, g["p"], None, True, 83, dx=dx, dy=dy), g["ad8"], "ad8")
+    assert_bits(_run(emu, False, 0, 0, g["p"], w, True, 84, dx=dx, dy=dy), g["ad8_w"], "ad8 -wg")
+    assert_bits(_run(emu, False, 1, 3, g["p"], None, False, 85, dx=dx, dy=dy), g["ad8_nc"], "ad8 -nc")
+    assert_bits(_run(emu, True, 1, 3, g["ang"], None, True, 86, dx=dx, dy=dy), g["sca"], "sca")
+    assert_bits(_run(emu, True, 0, 0, g["ang"], w, True, 87, dx=dx, dy=dy), g["sca_w"], "sca -wg")
+    assert_bits(_run(emu, True, 1, 3, g["ang"], None, False, 88, dx=dx, dy=dy), g["sca_nc"], "sca -nc")
