@@ -119,6 +119,29 @@ def pick_size(torch, want):
     return 65536 if free > 120e9 else 16384
 
 
+def apply_sweep_spec(spec):
+    """NAME[:passes][+river:cells] -> the environment variables the library reads (capi.cu, sweep_walk.cu)."""
+    if not spec:
+        return
+    base, _, river = spec.partition("+river:")
+    name, _, passes = base.partition(":")
+    os.environ["TAUDEM_B200_SWEEP"] = name
+    for key, val in (("TAUDEM_B200_LEVELS", passes), ("TAUDEM_B200_RIVER", river)):
+        if val:
+            os.environ[key] = val
+        else:
+            os.environ.pop(key, None)
+
+
+def sweep_name():
+    m = os.environ.get("TAUDEM_B200_SWEEP", "") or "tiles"
+    if m == "levels":
+        m += ":" + os.environ.get("TAUDEM_B200_LEVELS", "24")
+    if os.environ.get("TAUDEM_B200_RIVER"):
+        m += "+river:" + os.environ["TAUDEM_B200_RIVER"]
+    return m
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -181,11 +204,29 @@ def ours(args):
     peak, peak_src = peaks()
     dom = max(part_ms, key=part_ms.get)
     achieved = ALG_BYTES[dom] * cells / (part_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": KERNEL[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 5), "traffic": round(NCU_TRAFFIC_PER_CELL[dom] * cells), "traffic_source": "ncu --set full capture at 8192^2 scaled per cell (profiles/r01_ncu_summary.md)", "peak_source": peak_src,
+    tiles = sweep_name() == "tiles"
+    kname = dict(KERNEL)
+    phases = None
+    if not tiles:
+        # level / walk schedules: the sweep is several kernels; one extra untimed step with phase timers says which one dominates
+        names = ("k_level", "k_ready", "k_walk", "k_river")
+        os.environ["TAUDEM_B200_TIMING"] = "1"
+        phases = {}
+        for tool, run in (("aread8", lambda: (T.aread8_deps(s, p, ad8), T.aread8_sweep(s, ad8))),
+                          ("areadinf", lambda: (T.areadinf_deps(s, ang, sca, dxc, dyc), T.areadinf_sweep(s, ang, sca, dxc)))):
+            run(); torch.cuda.synchronize()
+            phases[tool] = {names[i]: round(T.l.td_ctx_phase_ms(T.ctx, i), 3) for i in range(4)}
+        os.environ.pop("TAUDEM_B200_TIMING", None)
+        for tool in ("aread8", "areadinf"):
+            top = max(phases[tool], key=phases[tool].get)
+            kname[tool + "_sweep"] = f"{top}<{'d8' if tool == 'aread8' else 'dinf'}> (+ the other phases of sweep_walk.cu)"
+    roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": round(NCU_TRAFFIC_PER_CELL[dom] * cells) if tiles or dom.endswith("deps") else None,
+                "traffic_source": "ncu --set full capture at 8192^2 scaled per cell (profiles/r01_ncu_summary.md)" if tiles or dom.endswith("deps") else "not captured for this schedule yet",
+                "peak_source": peak_src, "sweep": sweep_name(), "sweep_phases_ms": phases,
                 "algorithmic_bytes_per_cell": ALG_BYTES[dom], "ms_per_launch": round(part_ms[dom], 3),
-                "per_kernel_ms": {KERNEL[k]: round(v, 3) for k, v in part_ms.items()},
-                "per_kernel_frac": {KERNEL[k]: round(ALG_BYTES[k] * cells / (v * 1e-3) / 1e9 / peak, 5) for k, v in part_ms.items()}}
+                "per_kernel_ms": {kname[k]: round(v, 3) for k, v in part_ms.items()},
+                "per_kernel_frac": {kname[k]: round(ALG_BYTES[k] * cells / (v * 1e-3) / 1e9 / peak, 5) for k, v in part_ms.items()}}
 
     # ---- end to end through the host-grid C ABI with pinned host buffers
     T.close(); del ad8, sca
@@ -220,7 +261,7 @@ def ours(args):
             "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": f"aread8 + areadinf on {n}x{n} float32 synthetic fractal DEM (hills: H={HURST}, tilt={TILT}, seed={SEED}, 30 m cells), contamination check on, no weights",
                                              "cells": cells, "l2": "inputs (>= 1.5 GiB) exceed the 126 MB L2; no explicit flush", "timed": "CUDA events on the launching stream, wall %.3f s for %d steps" % (wall, args.steps),
-                                             "max_ad8": max_ad8, "max_sca": max_sca, **info},
+                                             "max_ad8": max_ad8, "max_sca": max_sca, "sweep": sweep_name(), **info},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
 
@@ -302,7 +343,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=6144)
     ap.add_argument("--cpu-ranks", type=int, default=48, help="MPI ranks of the CPU reference (48 measured 1.9x faster than 16 on the 128-core bench host)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", default=os.environ.get("TAUDEM_B200_SWEEP_SPEC", ""),
+                    help="sweep schedule: tiles (default) | levels[:passes][+river:cells] | hybrid | walk  (sets TAUDEM_B200_SWEEP / _LEVELS / _RIVER)")
     args = ap.parse_args()
+    apply_sweep_spec(args.sweep)
     if args.impl == "reference":
         reference(args)
     else:
