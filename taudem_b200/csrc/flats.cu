@@ -23,8 +23,8 @@
 // Row strips (one per process, src/linearpart.h): every strip runs the same loop on its own flat cells; the
 // caller supplies three callbacks (td_strip_comm: share edge rows, collect halo rows, all-reduce) that stand
 // where the reference calls share()/MPI_Allreduce in resolveflats.  A BFS level may claim a cell of the
-// neighbour strip: the claim is made on the local halo copy of lev / mk, sent to the owner, merged there
-// (k_merge appends the cell to the owner's frontier) and the owner's edge row is shared back, so that the
+// neighbour strip: the claim is made on the local halo copy of lev / mk, sent to the owner and merged there
+// (k_merge appends the cell to the owner's frontier; a claim on a cell the owner has already assigned is ignored), so that the
 // levels — and with them T, U and every elev2 — are those of the undivided grid.
 #include <vector>
 
@@ -402,9 +402,9 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
       for (;;) {
         if (hi > lo) { k_expand_fall<P><<<nblk(hi - lo), 256, 0, st>>>(fr + lo, hi - lo, t, elev, dir, lev, s.pitch, s.ny, fr, dc + 1); TD_LAUNCHED(); }
         if (multi) {
+          // (the halo copies are not refreshed per level: a stale "unassigned" only produces a claim the owner ignores)
           if (int rc = collect(lev)) return rc;
           k_merge<true><<<colblk, 256, 0, st>>>(recv_top, recv_bot, s, t, lev, mk, fr, dc + 1); TD_LAUNCHED();
-          if (int rc = share(lev, 4)) return rc;
         }
         unsigned long long end = 0, nt = 0;
         TD_CUDA(read_ctr(1, &end));
@@ -428,7 +428,6 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
         if (multi) {
           if (int rc = collect(mk)) return rc;
           k_merge<false><<<colblk, 256, 0, st>>>(recv_top, recv_bot, s, u, lev, mk, fr, dc + 1); TD_LAUNCHED();
-          if (int rc = share(mk, 4)) return rc;
         }
         unsigned long long end = 0, nu = 0;
         TD_CUDA(read_ctr(1, &end));
@@ -440,6 +439,7 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
     // ---- combine, set directions, collect what is still flat
     if (n) { k_combine<P><<<nblk(n), 256, 0, st>>>(cur, n, lev, mk, dir, T, U); TD_LAUNCHED(); }
     if (int rc = share(lev, 4)) return rc;                        // elev2 of the neighbours' edge cells
+    if (int rc = share(mk, 4)) return rc;                         // and whether they rise (k_setflow2 / k_set2_flat read both)
     if (int rc = share(dir, (int)sizeof(typename P::DirT))) return rc;   // pits marked by k_combine
     TD_CUDA(cudaMemsetAsync(dc, 0, sizeof(unsigned long long), st));
     if (n) {
