@@ -23,7 +23,7 @@ fi
 # 1. the default path (three stencils were rewritten): the parity tests proper
 step tests_gpu 1200 python -m pytest tests -x -q -m gpu
 # 2. the opt-in schedules against the default, bit for bit
-TAUDEM_B200_TEST_EXPERIMENTAL=1 step tests_experimental 600 python -m pytest tests/test_gpu_parity.py -x -q -k experimental
+TAUDEM_B200_TEST_EXPERIMENTAL=1 step tests_experimental 600 python -m pytest tests/test_gpu_parity.py -q -k 'experimental or outlets'
 # 3. timings: every schedule at two sizes (identical / DIFFERENT is printed per mode)
 step modes_4096 600 python scripts/sweep_modes.py 4096 tiles,levels:8,levels:24,levels:64,levels:24+river:64,hybrid,walk,walk+river:64 2
 step modes_16384 900 python scripts/sweep_modes.py 16384 tiles,levels:24,levels:48,levels:24+river:64,levels:48+river:32,hybrid 2
