@@ -67,7 +67,11 @@ struct SweepArgs {
                            // sweep_walk.cu finishes the cells that become ready after their tile's visit)
 };
 
+#ifdef TD_EMU   // the CPU emulation switches threads at every volatile load (spin loops must let the writer run)
+template <typename T> __device__ __forceinline__ T ldv(const T* p) { emu::yield(); return *((const volatile T*)p); }
+#else
 template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((const volatile T*)p); }
+#endif
 
 // In peer mode a neighbour GPU operates on this strip's counts and scheduler words with system-scope
 // atomics; the owner then uses system scope on the same words too (atomics of different scopes on one

@@ -58,7 +58,14 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 3; return cudaSuccess; }   // "3 SMs"
 template <typename F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 2; return cudaSuccess; }
+inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaIpcMemLazyEnablePeerAccess = 1 };
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+struct cudaIpcMemHandle_t { char reserved[64]; };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return 1; }       // no peers on the emulation
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return 1; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 // ---- fibers
 namespace emu {
@@ -118,6 +125,9 @@ inline int min(int a, unsigned b) { return a < (int)b ? a : (int)b; }
 EMU_ATOMIC(int)
 EMU_ATOMIC(unsigned)
 EMU_ATOMIC(unsigned long long)
+#define atomicAdd_system atomicAdd
+#define atomicCAS_system atomicCAS
+#define atomicExch_system atomicExch
 
 unsigned __activemask();
 void __syncthreads();

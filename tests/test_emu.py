@@ -25,7 +25,8 @@ STENCILS = ("d8_stencil", "dinf_stencil", "area_d8", "area_dinf")
 def _transform(name, min_launches=6):
     """kernel<<<grid, block, smem, stream>>>(args);  ->  emu_launch(grid, block, [&]{ kernel(args); });"""
     src = open(os.path.join(CSRC, name + ".cu")).read()
-    src, n = re.subn(r"(k_\w+(?:<\w+>)?)<<<([^,]+),\s*([^,]+),[^>]*>>>\(([^;]*)\);",
+    src = src.replace("extern __shared__ __align__(16) unsigned char dsm[];", "static __align__(16) unsigned char dsm[256 * 1024];")
+    src, n = re.subn(r"(k_\w+(?:<[\w, ]+>)?)<<<([^,]+),\s*([^,]+),[^>]*>>>\(([^;]*)\);",
                      r"emu_launch(dim3(\2), dim3(\3), [&] { \1(\4); });", src)
     assert n >= min_launches and "<<<" not in src, (name, n)
     inc = os.path.join(BUILD, name + "_emu.inc")
@@ -36,7 +37,7 @@ def _transform(name, min_launches=6):
 
 def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
-    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2)]
+    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("sweep_tiles", 5)]
     so = os.path.join(BUILD, f"libemu{tag}.so")
     objs = []
     for i, n in enumerate(STENCILS):                       # one translation unit per kernel file (their helper names collide)
@@ -47,7 +48,7 @@ def _build(tag="", defines=()):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-c", "-pthread", "-ftls-model=initial-exec", "-ffp-contract=off", "-I", EMU,
                                    "-I", BUILD, "-I", CSRC, f"-DEMU_WHICH={i + 1}", "-o", o, os.path.join(EMU, "stencil_driver.cpp")])
         objs.append(o)
-    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "emu.cpp")] + objs
+    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "tiles_driver.cpp", "emu.cpp")] + objs
     deps = incs + srcs + [os.path.join(EMU, "cuda_runtime.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "dinf_common.cuh"),
                           os.path.join(CSRC, "ctx.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
@@ -62,6 +63,7 @@ def _build(tag="", defines=()):
     lib.emu_deps_d8.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_short]
     lib.emu_deps_dinf.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     lib.emu_ref_deps.argtypes = [C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
+    lib.emu_tiles.argtypes = [C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_ulonglong, P]
     lib.emu_flats.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
     return lib
 
@@ -339,3 +341,31 @@ def test_emulated_pipeline_reproduces_the_reference_golden_vectors(emu, name):
     assert_bits(_run(emu, True, 1, 3, g["ang"], None, True, 86, dx=dx, dy=dy), g["sca"], "sca")
     assert_bits(_run(emu, True, 0, 0, g["ang"], w, True, 87, dx=dx, dy=dy), g["sca_w"], "sca -wg")
     assert_bits(_run(emu, True, 1, 3, g["ang"], None, False, 88, dx=dx, dy=dy), g["sca_nc"], "sca -nc")
+
+
+# ---------------------------------------------------------------- the tile dataflow sweep (taudem_b200/csrc/sweep_tiles.cu)
+def _tiles(lib, dinf, hybrid, direction, w, contcheck, seed):
+    ny, nx = direction.shape
+    out = np.empty((ny, nx), np.float32)
+    d = np.ascontiguousarray(direction)
+    wp = None if w is None else np.ascontiguousarray(w, np.float32)
+    visits = np.zeros(1, np.uint64)
+    nodata = -3.4028234663852886e38 if dinf else -32768.0
+    rc = lib.emu_tiles(int(dinf), int(hybrid), d.ctypes.data, out.ctypes.data, None if wp is None else wp.ctypes.data, nx, ny, nodata,
+                       int(w is not None), int(contcheck), -9999.0, 30.0, 30.0, seed, visits.ctypes.data)
+    assert rc == 0
+    return out, int(visits[0])
+
+
+@pytest.mark.parametrize("hybrid", [0, 1])
+def test_emulated_tile_sweep(emu, fields, hybrid):
+    """The default sweep — persistent CTAs, ticket queue, four-state tile protocol, in-tile wavefront with its work queue
+    — and the `once` variant followed by the walkers ("hybrid"), under randomised thread interleavings."""
+    port, p, ang, w = fields
+    ntiles_d8 = -(-p.shape[1] // 64) * -(-p.shape[0] // 32)
+    a, visits = _tiles(emu, False, hybrid, p, None, True, 91)
+    assert_bits(a, port.aread8(p), f"ad8 tiles hybrid={hybrid}")
+    assert (visits == ntiles_d8) if hybrid else (visits > ntiles_d8)
+    assert_bits(_tiles(emu, False, hybrid, p, w, False, 92)[0], port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc tiles")
+    assert_bits(_tiles(emu, True, hybrid, ang, None, True, 93)[0], port.areadinf(ang), f"sca tiles hybrid={hybrid}")
+    assert_bits(_tiles(emu, True, hybrid, ang, w, False, 94)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc tiles")
