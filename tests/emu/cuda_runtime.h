@@ -8,6 +8,7 @@
 // checks protocol logic and arithmetic (bit-exact: plain IEEE float/double, no contraction), not the
 // PTX memory model.  `__shared__` variables are function-local statics (one block at a time).
 #pragma once
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -131,6 +132,7 @@ EMU_ATOMIC(unsigned long long)
 
 unsigned __activemask();
 void __syncthreads();
+int __syncthreads_or(int pred);
 void __syncwarp(unsigned mask = 0xffffffffu);
 unsigned __ballot_sync(unsigned mask, int pred);
 unsigned long long emu_shfl(unsigned mask, unsigned long long v, int src_lane_or_delta, int mode);   // mode 0 = idx, 1 = up, 2 = xor

@@ -124,6 +124,17 @@ void __syncthreads() {
   if (++b->bar_arrived == live) { b->bar_arrived = 0; ++b->bar_gen; }
   else emu::wait_on(&b->bar_gen, gen);
 }
+// barrier + OR of the predicates: accumulate, barrier, read, barrier, reset, barrier
+int __syncthreads_or(int pred) {
+  static thread_local int acc = 0;
+  if (pred) acc = 1;
+  __syncthreads();
+  const int r = acc;
+  __syncthreads();
+  acc = 0;
+  __syncthreads();
+  return r;
+}
 void __syncwarp(unsigned mask) { unsigned g; emu::collective(mask, 0, &g); }
 unsigned __activemask() {            // lanes of the warp that have not returned (kernels here do not diverge around collectives)
   emu::Block* b = emu::g_blk;

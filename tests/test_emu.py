@@ -37,7 +37,7 @@ def _transform(name, min_launches=6):
 
 def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
-    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("sweep_tiles", 5)]
+    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("sweep_tiles", 5), _transform("fill", 3)]
     so = os.path.join(BUILD, f"libemu{tag}.so")
     objs = []
     for i, n in enumerate(STENCILS):                       # one translation unit per kernel file (their helper names collide)
@@ -64,6 +64,7 @@ def _build(tag="", defines=()):
     lib.emu_deps_dinf.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     lib.emu_ref_deps.argtypes = [C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     lib.emu_tiles.argtypes = [C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_ulonglong, P]
+    lib.emu_fill.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_ulonglong]
     lib.emu_flats.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
     return lib
 
@@ -369,3 +370,22 @@ def test_emulated_tile_sweep(emu, fields, hybrid):
     assert_bits(_tiles(emu, False, hybrid, p, w, False, 92)[0], port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc tiles")
     assert_bits(_tiles(emu, True, hybrid, ang, None, True, 93)[0], port.areadinf(ang), f"sca tiles hybrid={hybrid}")
     assert_bits(_tiles(emu, True, hybrid, ang, w, False, 94)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc tiles")
+
+
+def test_emulated_pitremove(emu):
+    """k_fill_init + k_fill_relax (tile-local Planchon-Darboux relaxation, active-tile lists): fel of the reference-generated
+    golden vectors, 8- and 4-way, and the depression mask case."""
+    from util import load_golden
+    for name in ("tiny", "plateau", "lake", "hills_holes", "rough"):
+        g = load_golden(name)
+        dem = np.ascontiguousarray(g["dem"], np.float32); ny, nx = dem.shape
+        for four, key in ((0, "fel"), (1, "fel4")):
+            out = np.empty_like(dem)
+            assert emu.emu_fill(dem.ctypes.data, out.ctypes.data, None, nx, ny, -9999.0, four, 5) == 0
+            assert_bits(out, g[key], f"{name} {key}")
+        if "depmask" in g:
+            m = np.ascontiguousarray(g["depmask"], np.int16)
+            for four, key in ((0, "fel_mask"), (1, "fel_mask4")):
+                out = np.empty_like(dem)
+                assert emu.emu_fill(dem.ctypes.data, out.ctypes.data, m.ctypes.data, nx, ny, -9999.0, four, 6) == 0
+                assert_bits(out, g[key], f"{name} {key}")
