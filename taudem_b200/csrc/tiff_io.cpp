@@ -358,11 +358,16 @@ bool Raster::load_block(uint64_t idx, std::vector<uint8_t>* out, std::string* er
     uint64_t rows = std::min<uint64_t>(block_h_, height_ - row0);
     expect = (size_t)rows * width_ * sb;
   }
-  std::vector<uint8_t> comp(counts_[idx]);
-  if (!pread_all(fp_, offsets_[idx], comp.data(), comp.size())) { *err = "short read of raster block"; return false; }
+  std::vector<uint8_t> comp;
+  if (compression_ == 1) {                      // stored: straight into the block buffer
+    if (counts_[idx] < expect) { *err = "raster block too short"; return false; }
+    out->resize(counts_[idx]);
+    if (!pread_all(fp_, offsets_[idx], out->data(), out->size())) { *err = "short read of raster block"; return false; }
+  } else {
+    comp.resize(counts_[idx]);
+    if (!pread_all(fp_, offsets_[idx], comp.data(), comp.size())) { *err = "short read of raster block"; return false; }
+  }
   if (compression_ == 1) {
-    out->assign(comp.begin(), comp.end());
-    if (out->size() < expect) { *err = "raster block too short"; return false; }
   } else if (compression_ == 5) {
     if (!lzw_decode(comp.data(), comp.size(), out, expect)) { *err = "LZW decode failed"; return false; }
   } else {
@@ -414,6 +419,11 @@ bool Raster::read(long xstart, long ystart, long nrows, long ncols, void* dest, 
   std::atomic<size_t> next(0);
   std::atomic<bool> failed(false);
   std::mutex emu;
+  // stored strips of the file's own sample type, whole rows: the file bytes ARE the destination bytes
+  const bool direct = compression_ == 1 && !tiled_ && predictor_ == 1 && !(swap_ && sb > 1) && xstart == 0 && ncols == (long)width_ &&
+                      dest_stride == ncols &&
+                      ((type == DT_F32 && bits_ == 32 && sample_format_ == 3) || (type == DT_I16 && bits_ == 16 && sample_format_ == 2) ||
+                       (type == DT_I32 && bits_ == 32 && sample_format_ == 2));
   auto work = [&]() {
     std::vector<uint8_t> blk;
     std::string e;
@@ -421,6 +431,19 @@ bool Raster::read(long xstart, long ystart, long nrows, long ncols, void* dest, 
       const size_t j = next.fetch_add(1);
       if (j >= jobs.size() || failed.load()) return;
       const long by = jobs[j].by; const uint64_t bx = jobs[j].bx;
+      if (direct) {
+        const long r0 = std::max<long>(ystart, by * (long)block_h_), r1 = std::min<long>(ystart + nrows, (by + 1) * (long)block_h_);
+        const size_t rowb = (size_t)width_ * sb;
+        const uint64_t off = offsets_[(size_t)by] + (uint64_t)(r0 - by * (long)block_h_) * rowb;
+        const size_t want = (size_t)(r1 - r0) * rowb;
+        if ((uint64_t)(r1 - by * (long)block_h_) * rowb > counts_[(size_t)by] ||
+            !pread_all(fp_, off, (uint8_t*)dest + (size_t)(r0 - ystart) * rowb, want)) {
+          std::lock_guard<std::mutex> g(emu);
+          if (!failed.exchange(true)) *err = "short read of raster block";
+          return;
+        }
+        continue;
+      }
       if (!load_block((uint64_t)by * blocks_across + bx, &blk, &e)) {
         std::lock_guard<std::mutex> g(emu);
         if (!failed.exchange(true)) *err = e;
@@ -437,7 +460,7 @@ bool Raster::read(long xstart, long ystart, long nrows, long ncols, void* dest, 
       }
     }
   };
-  unsigned nthreads = compression_ == 1 ? 1u : std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+  unsigned nthreads = std::min<unsigned>(compression_ == 1 ? 8u : 16u, std::max(1u, std::thread::hardware_concurrency()));
   nthreads = (unsigned)std::min<size_t>(nthreads, jobs.size());
   if (nthreads <= 1) work();
   else {
@@ -567,7 +590,7 @@ bool Writer::flush_batch(std::string* err) {
       }
     }
   };
-  const unsigned nthreads = (unsigned)std::min<size_t>(n, std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency())));
+  const unsigned nthreads = (unsigned)std::min<size_t>(n, std::min<unsigned>(32u, std::max(1u, std::thread::hardware_concurrency())));
   if (nthreads <= 1) work();
   else {
     std::vector<std::thread> pool;
