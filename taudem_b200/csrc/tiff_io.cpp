@@ -171,32 +171,38 @@ bool lzw_decode(const uint8_t* in, size_t n, std::vector<uint8_t>* out, size_t e
 }
 
 void lzw_encode(const uint8_t* in, size_t n, std::vector<uint8_t>* out) {
-  out->clear();
+  // TIFF flavour (see lzw_decode).  The string table is an open-addressing hash of (prefix code << 8 | byte) with a
+  // generation stamp per slot, so that the frequent table resets of barely compressible data (float rasters) cost nothing.
+  out->resize(n + n / 2 + 16);                   // 12-bit codes for 8-bit symbols: at most 1.5 bytes per byte (+ clear / EOI)
+  uint8_t* o = out->data();
+  size_t op = 0;
   uint64_t acc = 0; int nacc = 0;
   auto put = [&](int code, int bits) {
     acc = (acc << bits) | (uint32_t)code; nacc += bits;
-    while (nacc >= 8) { out->push_back((uint8_t)(acc >> (nacc - 8))); nacc -= 8; }
+    while (nacc >= 8) { o[op++] = (uint8_t)(acc >> (nacc - 8)); nacc -= 8; }
   };
-  const int HSIZE = 9001;
-  std::vector<int32_t> hkey(HSIZE), hval(HSIZE);
-  auto reset = [&]() { std::fill(hkey.begin(), hkey.end(), -1); };
-  reset();
+  constexpr int HBITS = 14, HSIZE = 1 << HBITS;
+  struct Slot { uint32_t key; uint16_t val, gen; };
+  std::vector<Slot> tab(HSIZE, Slot{0, 0, 0});
+  uint16_t gen = 1;
+  auto reset = [&]() { if (++gen == 0) { std::fill(tab.begin(), tab.end(), Slot{0, 0, 0}); gen = 1; } };
   int next = 258, bits = 9;
   put(256, bits);
-  if (n == 0) { put(257, bits); if (nacc) out->push_back((uint8_t)(acc << (8 - nacc))); return; }
+  if (n == 0) { put(257, bits); if (nacc) o[op++] = (uint8_t)(acc << (8 - nacc)); out->resize(op); return; }
   int cur = in[0];
   for (size_t i = 1; i < n; i++) {
-    int c = in[i];
-    int32_t key = (cur << 8) | c;
-    int h = (int)(((uint32_t)key * 2654435761u) % HSIZE);
+    const int c = in[i];
+    const uint32_t key = ((uint32_t)cur << 8) | (uint32_t)c;
+    uint32_t h = (key * 2654435761u) >> (32 - HBITS);
     bool found = false;
-    while (hkey[h] != -1) {
-      if (hkey[h] == key) { cur = hval[h]; found = true; break; }
-      if (++h == HSIZE) h = 0;
+    while (tab[h].gen == gen) {
+      if (tab[h].key == key) { cur = tab[h].val; found = true; break; }
+      h = (h + 1) & (HSIZE - 1);
     }
     if (found) continue;
     put(cur, bits);
-    hkey[h] = key; hval[h] = next++;
+    tab[h] = Slot{key, (uint16_t)next, gen};
+    next++;
     if (next == (1 << bits) - 1 + 1 && bits < 12) bits++;   // writer lags reader by one entry
     if (next >= 4094) { put(256, bits); reset(); next = 258; bits = 9; }
     cur = c;
@@ -205,7 +211,8 @@ void lzw_encode(const uint8_t* in, size_t n, std::vector<uint8_t>* out) {
   next++;
   if (next == (1 << bits) - 1 + 1 && bits < 12) bits++;
   put(257, bits);
-  if (nacc) out->push_back((uint8_t)((acc << (8 - nacc)) & 0xff));
+  if (nacc) o[op++] = (uint8_t)((acc << (8 - nacc)) & 0xff);
+  out->resize(op);
 }
 
 // ------------------------------------------------------------------ Raster
