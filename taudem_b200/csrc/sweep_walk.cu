@@ -380,6 +380,9 @@ __global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
       }
       // ---- 2. the contributors that are not on the path (all final): areas, and for D-infinity every contributor's share
       const unsigned m = lane < len ? (mynd & 0xffu) : 0u;
+      // every lane acquires on its own cell's count word — the location its side contributors released their areas on
+      // (lane 0 read these words for the path search; its acquire does not formally order the other lanes' loads)
+      if (lane < len) (void)ld_acquire(a.cntw + (my >> 2));
       float an[8];
       double pk[DINF ? 8 : 1];
 #pragma unroll
