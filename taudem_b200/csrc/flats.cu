@@ -26,6 +26,9 @@
 // neighbour strip: the claim is made on the local halo copy of lev / mk, sent to the owner and merged there
 // (k_merge appends the cell to the owner's frontier; a claim on a cell the owner has already assigned is ignored), so that the
 // levels — and with them T, U and every elev2 — are those of the undivided grid.
+#include <stdlib.h>
+
+#include <algorithm>
 #include <vector>
 
 #include "ctx.h"
@@ -157,6 +160,47 @@ __global__ void k_expand_rise(const long long* __restrict__ fr, unsigned long lo
     if (in && lev[ci] != 0 && mk[ci] == 0) push = atomicCAS(mk + ci, 0, u) == 0;
     if (ci < pitch || ci >= (long long)(ny + 1) * pitch) push = false;     // neighbour strip's cell: see k_merge
     append(out, ctr, push, ci);
+  }
+}
+
+// One BFS level without a host round trip (single strip, TAUDEM_B200_FLATS_BATCH): a fixed grid strides over the
+// frontier of level t-1 = fr[bounds[t-2], bounds[t-1]) — the bounds live in device memory — and the last block to
+// finish records where level t ends, bounds[t] = *ctr.  The host enqueues a batch of levels and reads the bounds
+// back once; levels past the last non-empty one find an empty frontier and do nothing.
+template <class P, bool FALL>
+__global__ void __launch_bounds__(256) k_bfs_level(const long long* __restrict__ fr, unsigned long long* __restrict__ bounds, int t,
+                                                   const float* __restrict__ elev, const typename P::DirT* __restrict__ dir,
+                                                   int* __restrict__ lev, int* __restrict__ mk, int pitch, int ny, long long* __restrict__ out,
+                                                   unsigned long long* __restrict__ ctr, unsigned* __restrict__ blkdone) {
+  const unsigned long long lo = bounds[t - 2], hi = bounds[t - 1];
+  const unsigned long long n = hi - lo;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * 256; base < n; base += (unsigned long long)gridDim.x * 256) {
+    const unsigned long long i = base + threadIdx.x;
+    const bool in = i < n;
+    const long long ni = in ? fr[lo + i] : 0;
+    const float zn = (FALL && in) ? elev[ni] : 0.f;
+#pragma unroll
+    for (int kk = 1; kk <= 8; ++kk) {
+      bool push = false;
+      const long long ci = ni + (long long)drow(kk) * pitch + dcol(kk);
+      if (FALL) {
+        if (in && lev[ci] == UNASSIGNED) {
+          const int k = kk > 4 ? kk - 4 : kk + 4;
+          if (elev[ci] - zn == 0 && !dont_cross<P>(dir, ci, pitch, k)) push = atomicCAS(lev + ci, UNASSIGNED, t) == UNASSIGNED;
+        }
+      } else if (in && lev[ci] != 0 && mk[ci] == 0) push = atomicCAS(mk + ci, 0, t) == 0;
+      if (ci < pitch || ci >= (long long)(ny + 1) * pitch) push = false;
+      append(out, ctr, push, ci);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(blkdone, 1u) == gridDim.x - 1) {          // the last block: every append of this level is done
+      __threadfence();
+      bounds[t] = *reinterpret_cast<volatile unsigned long long*>(ctr);
+      *blkdone = 0;
+    }
   }
 }
 
@@ -379,6 +423,44 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
   long long* fr = ctx->listC.as<long long>();
   const unsigned colblk = (unsigned)((s.nx + 255) / 256);
 
+  // TAUDEM_B200_FLATS_BATCH = K > 0 (single strip): K BFS levels per host round trip (k_bfs_level) instead of one
+  int batch = 0;
+  if (!multi) { const char* e = getenv("TAUDEM_B200_FLATS_BATCH"); batch = e ? std::max(0, std::min(atoi(e), 4096)) : 0; }
+  constexpr unsigned long long MAXLEV = 1ull << 22;
+  unsigned long long* bounds = nullptr; unsigned* blkdone = nullptr;
+  int bgrid = 1;
+  if (batch > 0) {
+    TD_CUDA(ctx->tileflags.ensure(sizeof(unsigned long long) * (MAXLEV + 2)));
+    bounds = ctx->tileflags.as<unsigned long long>();
+    blkdone = reinterpret_cast<unsigned*>(bounds + MAXLEV + 1);
+    TD_CUDA(cudaMemsetAsync(blkdone, 0, sizeof(unsigned long long), st));
+    int dev = 0, sms = 1;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    bgrid = std::max(1, sms * 4);
+  }
+  std::vector<unsigned long long> hb;
+  // runs BFS levels 2, 3, ... in batches from the frontier fr[0, hi1) of level 1; *passes = first level that assigns nothing
+  auto bfs_batched = [&](bool fall, unsigned long long hi1, int* passes) -> int {
+    const unsigned long long b01[2] = {0ull, hi1};
+    TD_CUDA(cudaMemcpyAsync(bounds, b01, sizeof b01, cudaMemcpyHostToDevice, st));
+    unsigned long long prev = hi1;
+    for (int t0 = 2;; t0 += batch) {
+      if ((unsigned long long)(t0 + batch) >= MAXLEV) { set_error("flat resolution: too many BFS levels for the batched mode"); return TD_ERR_ALLOC; }
+      for (int t = t0; t < t0 + batch; ++t) {
+        if (fall) k_bfs_level<P, true><<<bgrid, 256, 0, st>>>(fr, bounds, t, elev, dir, lev, mk, s.pitch, s.ny, fr, dc + 1, blkdone);
+        else k_bfs_level<P, false><<<bgrid, 256, 0, st>>>(fr, bounds, t, elev, dir, lev, mk, s.pitch, s.ny, fr, dc + 1, blkdone);
+        TD_LAUNCHED();
+      }
+      hb.resize(batch);
+      TD_CUDA(cudaMemcpyAsync(hb.data(), bounds + t0, sizeof(unsigned long long) * batch, cudaMemcpyDeviceToHost, st));
+      TD_CUDA(cudaStreamSynchronize(st));
+      for (int j = 0; j < batch; ++j) {
+        if (hb[j] == prev) { *passes = t0 + j; return TD_OK; }
+        prev = hb[j];
+      }
+    }
+  };
+
   unsigned long long last = ntot + 1;
   // outer loop: src/d8.cpp:302-317
   while (ntot > 0 && ntot < last) {
@@ -399,6 +481,9 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
       // pass 2: seeds (equal neighbour outside F) + expansion of level 1
       if (n) { k_gather<<<nblk(n), 256, 0, st>>>(cur, n, lev, 2, fr, dc + 1); TD_LAUNCHED(); }
       int t = 2;
+      if (batch > 0) {
+        if (int rc = bfs_batched(true, hi, &T)) return rc;
+      } else
       for (;;) {
         if (hi > lo) { k_expand_fall<P><<<nblk(hi - lo), 256, 0, st>>>(fr + lo, hi - lo, t, elev, dir, lev, s.pitch, s.ny, fr, dc + 1); TD_LAUNCHED(); }
         if (multi) {
@@ -423,6 +508,9 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
     int U = 1;
     if (hitot > 0) {
       int u = 2;
+      if (batch > 0) {
+        if (int rc = bfs_batched(false, hi, &U)) return rc;
+      } else
       for (;;) {
         if (hi > lo) { k_expand_rise<<<nblk(hi - lo), 256, 0, st>>>(fr + lo, hi - lo, u, lev, mk, s.pitch, s.ny, fr, dc + 1); TD_LAUNCHED(); }
         if (multi) {

@@ -389,3 +389,21 @@ def test_emulated_pitremove(emu):
                 out = np.empty_like(dem)
                 assert emu.emu_fill(dem.ctypes.data, out.ctypes.data, m.ctypes.data, nx, ny, -9999.0, four, 6) == 0
                 assert_bits(out, g[key], f"{name} {key}")
+
+
+@pytest.mark.parametrize("batch", [1, 3, 64])
+def test_emulated_flat_resolution_batched_levels(emu, terraces, batch, monkeypatch):
+    """TAUDEM_B200_FLATS_BATCH: several BFS levels per host round trip (k_bfs_level: device-resident level bounds, the last
+    block of a level records where it ends) — same directions, D8 and D-infinity, and the golden plateau / lake cases."""
+    from util import load_golden
+    port, fel = terraces
+    monkeypatch.setenv("TAUDEM_B200_FLATS_BATCH", str(batch))
+    p0, _ = port.d8flowdir(fel, flats=False); p_ref, _ = port.d8flowdir(fel)
+    assert_bits(_flats(emu, False, fel, p0, 1, 101)[0], p_ref, f"p, batch {batch}")
+    a0, _ = port.dinfflowdir(fel, flats=False); a_ref, _ = port.dinfflowdir(fel)
+    assert_bits(_flats(emu, True, fel, a0, 1, 102)[0], a_ref, f"ang, batch {batch}")
+    for name in ("plateau", "lake"):
+        g = load_golden(name)
+        f = np.ascontiguousarray(g["fel"], np.float32)
+        q0, _ = port.d8flowdir(f, dx=float(g["dx"]), dy=float(g["dy"]), flats=False)
+        assert_bits(_flats(emu, False, f, q0, 1, 103, float(g["dx"]), float(g["dy"]))[0], g["p"], f"{name} p, batch {batch}")
