@@ -32,6 +32,7 @@ TAUDEM_B200_TIMING=1 step modes_16384_phases 600 python scripts/sweep_modes.py 1
 step perf_16384 600 python scripts/gpu_perf.py 16384
 step bench_16384_levels 900 python bench.py --size 16384 --steps 3 --warmup 3 --no-cpu --sweep levels:24+river:64
 step bench_16384_tiles 900 python bench.py --size 16384 --steps 3 --warmup 3 --no-cpu
+TAUDEM_B200_FLATS_BATCH=64 step tests_flats_batch 600 python -m pytest tests/test_gpu_parity.py -q -k "golden or live_reference or depression"
 TAUDEM_B200_FLATS_BATCH=64 step perf_16384_flats_batch 600 python scripts/gpu_perf.py 16384
 # 5. row strips on one GPU (gloo, host-staged): level sweeps + strip flats
 TAUDEM_B200_SWEEP=levels TAUDEM_B200_FLATS=strips TD_BACKEND=gloo step strips_gloo 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 \
