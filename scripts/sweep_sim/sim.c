@@ -215,3 +215,35 @@ long sim_local(int nx, int ny, const int32_t* d1, const int32_t* d2, const uint8
   free(cnt); free(q);
   return tail;
 }
+
+/* Model of the streaming level passes (k_level): a pass visits the rows in bands of `band` rows (what runs
+ * concurrently on the GPU); a cell is evaluated in a pass if it is ready when its band starts.  dir = +1 forward
+ * raster order, -1 reverse, 0 alternate per pass.  done_after[p] = cells evaluated after pass p+1. */
+int sim_levelpasses(int nx, int ny, const int32_t* d1, const int32_t* d2, const uint8_t* cnt0, int band, int passes, int dir,
+                    int64_t* done_after, uint8_t* done_out) {
+  const long n = (long)nx * ny;
+  uint8_t* cnt = (uint8_t*)malloc(n); memcpy(cnt, cnt0, n);
+  uint8_t* done = (uint8_t*)calloc(n, 1);
+  int32_t* ready = (int32_t*)malloc(sizeof(int32_t) * (size_t)nx * band);
+  long total = 0;
+  const int nb = (ny + band - 1) / band;
+  for (int p = 0; p < passes; ++p) {
+    const int rev = dir < 0 || (dir == 0 && (p & 1));
+    for (int bi = 0; bi < nb; ++bi) {
+      const int b = rev ? nb - 1 - bi : bi;
+      const int r0 = b * band, r1 = r0 + band < ny ? r0 + band : ny;
+      long nr = 0;
+      for (long c = (long)r0 * nx; c < (long)r1 * nx; ++c) if (!done[c] && cnt[c] == 0) ready[nr++] = (int32_t)c;
+      for (long i = 0; i < nr; ++i) {
+        const long c = ready[i];
+        done[c] = 1; ++total;
+        if (d1[c] >= 0) --cnt[d1[c]];
+        if (d2 && d2[c] >= 0) --cnt[d2[c]];
+      }
+    }
+    done_after[p] = total;
+  }
+  if (done_out) memcpy(done_out, done, n);
+  free(cnt); free(done); free(ready);
+  return 0;
+}

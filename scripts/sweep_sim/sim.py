@@ -97,3 +97,15 @@ def local_cells(d1, d2, cnt, twx, twy):
     loc = np.zeros(d1.size, np.uint8)
     l.sim_local(nx, ny, d1.ctypes.data, None if d2 is None else d2.ctypes.data, cnt.ctypes.data, twx, twy, loc.ctypes.data)
     return loc.reshape(ny, nx)
+
+
+def level_passes(d1, d2, cnt, band, passes, direction=1):
+    """Model of k_level: `passes` streaming passes, rows visited in bands of `band` rows (direction +1 forward, -1 reverse,
+    0 alternating).  Returns (cells evaluated after each pass, done mask)."""
+    ny, nx = d1.shape
+    l = lib()
+    l.sim_levelpasses.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    out = np.zeros(passes, np.int64); done = np.zeros(d1.size, np.uint8)
+    l.sim_levelpasses(nx, ny, d1.ctypes.data, None if d2 is None else d2.ctypes.data, cnt.ctypes.data, band, passes, direction,
+                      out.ctypes.data, done.ctypes.data)
+    return out, done.reshape(ny, nx)
