@@ -186,6 +186,12 @@ int td_dinf_flats_dev(td_ctx*, float* fel, float* ang, td_strip s, const double*
 /* -o: restricts the dependency state built by *_deps_dev to the cells upstream of the outlets (host
  * arrays of grid coordinates, row 0 = first owned row); call between *_deps_dev and *_sweep_dev.       */
 int td_sweep_restrict_dev(td_ctx*, td_strip s, const int* cols, const int* rows, int nout, void* stream);
+/* Row strips: one round (outlet seeds with nout >= 0 in the first round; in_top / in_bot = the neighbour strips'
+ * requests for my first / last row, device arrays of pitch ints or NULL; req_out = my requests to them, device,
+ * 2 x pitch ints: [0,pitch) to the strip above, [pitch,2 pitch) below).  Exchange req_out like the sweeps' halo
+ * counts and repeat until no strip requests anything, then call once more with finish = 1.              */
+int td_sweep_restrict_round_dev(td_ctx*, td_strip s, const int* cols, const int* rows, int nout,
+                                const int* in_top, const int* in_bot, int* req_out, int finish, void* stream);
 
 /* contributing area.  *_deps_dev = initNeighborD8up / initNeighborDinfup
  * (src/commonLib.cpp:240-283, 92-136): fills the strip's dependency state inside ctx.

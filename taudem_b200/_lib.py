@@ -51,6 +51,7 @@ SIGNATURES = {
     "td_aread8_outlets_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _F, _I, _P, _P, _I]),
     "td_area_outlets_host": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _I, _P, _P, _I]),
     "td_sweep_restrict_dev": (_I, [_P, Strip, _P, _P, _I, _P]),
+    "td_sweep_restrict_round_dev": (_I, [_P, Strip, _P, _P, _I, _P, _P, _P, _I, _P]),
     "td_outlets_read": (_I, [C.c_char_p, C.c_char_p, _I, _I, _P, _P, _I, _P]),
     "td_ctx_create": (_P, []),
     "td_ctx_destroy": (None, [_P]),

@@ -316,6 +316,17 @@ int td_sweep_restrict_dev(td_ctx* ctx, td_strip s, const int* cols, const int* r
   return td::sweep_restrict_upstream(ctx, Strip(s), cols, rows, nout, (cudaStream_t)stream);
 }
 
+// The same over row strips, in rounds like the sweeps: seeds = the outlets of this strip (first round) + the requests the
+// neighbour strips recorded for my first / last row (in_top / in_bot, device, pitch ints, NULL = none); req_out (device,
+// 2 x pitch ints) receives my requests to them; repeat until nobody requests anything, then one call with finish = 1
+// (src/commonLib.cpp:300-375 does this exchange with bufferAbove / bufferBelow and transferPack).
+int td_sweep_restrict_round_dev(td_ctx* ctx, td_strip s, const int* cols, const int* rows, int nout, const int* in_top, const int* in_bot,
+                                int* req_out, int finish, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  if ((nout > 0 && (!cols || !rows)) || !req_out) { td::set_error("td_sweep_restrict_round_dev: bad arguments"); return TD_ERR_ARG; }
+  return td::sweep_restrict_round(ctx, Strip(s), cols, rows, nout, in_top, in_bot, req_out, finish, (cudaStream_t)stream);
+}
+
 // ---- multi-strip sweeps: begin (queue all tiles) / run (until locally drained; crossings into the
 // neighbour strips are counted in halo_out[0..pitch) = row above, [pitch..2*pitch) = row below) /
 // apply (decrements received from the neighbours for my first / last row)

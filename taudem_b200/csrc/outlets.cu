@@ -31,6 +31,7 @@ struct UpArgs {
   unsigned long long* ctr;    // [0] list ticket, [1] spill length, [2] spill list exhausted
   long long* spill;
   unsigned long long spill_cap;
+  int* req;                   // row strips: req[c] = 1 asks the strip above to continue at (its last row, c), req[pitch + c] the strip below
 };
 
 __global__ void __launch_bounds__(256) k_upstream(const UpArgs a) {
@@ -72,6 +73,8 @@ __global__ void __launch_bounds__(256) k_upstream(const UpArgs a) {
         for (int k = 1; k <= 8; ++k)
           if ((nd >> (k - 1)) & 1u) {
             const long long ni = cur + (long long)drow(k) * s.pitch + dcol(k);
+            if (ni < s.pitch) { a.req[ni] = 1; continue; }                                              // a cell of the strip above
+            if (ni >= (long long)(s.ny + 1) * s.pitch) { a.req[s.pitch + (int)(ni - (long long)(s.ny + 1) * s.pitch)] = 1; continue; }
             const int slot = atomicAdd(&wqn[wid], 1);
             if (slot < UQ) wq[wid][slot] = ni;
             else {
@@ -108,25 +111,49 @@ __global__ void __launch_bounds__(256) k_restrict(unsigned short* __restrict__ n
 }
 }  // namespace
 
-// cols / rows: the outlets' grid coordinates (row 0 = first owned row of the strip), host memory; points outside the
-// strip are ignored like the reference ignores points outside the partition.  Single strip only.
-int sweep_restrict_upstream(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, cudaStream_t st) {
-  if (s.has_top || s.has_bot) { set_error("outlets (-o) are implemented for a single strip"); return TD_ERR_ARG; }
+namespace {
+// requests received from the neighbour strips -> cells of my first / last row appended to the seed list
+__global__ void k_requests(const int* __restrict__ in_top, const int* __restrict__ in_bot, Strip s, long long* __restrict__ list,
+                           unsigned long long* __restrict__ ctr) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= s.nx) return;
+  if (in_top && in_top[c] > 0) list[atomicAdd(ctr, 1ull)] = s.idx(1, c);
+  if (in_bot && in_bot[c] > 0) list[atomicAdd(ctr, 1ull)] = s.idx(s.ny, c);
+}
+}  // namespace
+
+// One round of the outlet restriction on a strip.  Seeds: the outlets (cols / rows: grid coordinates, row 0 = first owned
+// row of the strip, host memory; points outside the strip are ignored like the reference ignores points outside the
+// partition; nout < 0 = none this round) and the requests of the neighbour strips (in_top / in_bot: device arrays of
+// pitch ints, what the strip above / below wrote into its req_out for my first / last row; NULL = none).  req_out
+// (device, 2 x pitch ints, zeroed here) receives this strip's requests to its neighbours.  finish != 0: nobody has
+// requests left — everything that was not reached is removed from the flow field (k_restrict).
+int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, const int* in_top, const int* in_bot,
+                         int* req_out, int finish, cudaStream_t st) {
   std::vector<long long> cells;
   for (int i = 0; i < nout; ++i)
     if (cols[i] >= 0 && cols[i] < s.nx && rows[i] >= 0 && rows[i] < s.ny) cells.push_back(s.idx(rows[i] + 1, cols[i]));
   unsigned long long n = cells.size();
   const unsigned long long cap = (unsigned long long)s.nx * s.ny / 16 + 65536;
-  TD_CUDA(ctx->listA.ensure(sizeof(long long) * std::max<unsigned long long>(n, 1)));
+  TD_CUDA(ctx->listA.ensure(sizeof(long long) * (n + 2 * (unsigned long long)s.nx + 1)));
   TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap));
   TD_CUDA(ctx->listC.ensure(sizeof(long long) * cap));
   if (n) TD_CUDA(cudaMemcpyAsync(ctx->listA.p, cells.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
   UpArgs a;
-  a.node = ctx->node.as<unsigned short>(); a.s = s; a.ctr = ctx->d_ctr + 16; a.spill_cap = cap;
+  a.node = ctx->node.as<unsigned short>(); a.s = s; a.ctr = ctx->d_ctr + 16; a.spill_cap = cap; a.req = req_out;
+  unsigned long long* hc = ctx->h_ctr + 16;
+  if (req_out) TD_CUDA(cudaMemsetAsync(req_out, 0, sizeof(int) * 2 * (size_t)s.pitch, st));
+  if (in_top || in_bot) {
+    TD_CUDA(cudaMemcpyAsync(a.ctr + 3, &n, sizeof n, cudaMemcpyHostToDevice, st));
+    k_requests<<<(s.nx + 255) / 256, 256, 0, st>>>(in_top, in_bot, s, ctx->listA.as<long long>(), a.ctr + 3);
+    TD_LAUNCHED();
+    TD_CUDA(cudaMemcpyAsync(hc + 3, a.ctr + 3, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaStreamSynchronize(st));
+    n = hc[3];
+  }
   const long long* cur = ctx->listA.as<long long>();
   long long* spill = ctx->listB.as<long long>();
   long long* other = ctx->listC.as<long long>();
-  unsigned long long* hc = ctx->h_ctr + 16;
   int dev = 0, sms = 1;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   while (n > 0) {
@@ -142,11 +169,20 @@ int sweep_restrict_upstream(td_ctx* ctx, const Strip& s, const int* cols, const 
     n = hc[1];
     cur = spill; std::swap(spill, other);
   }
-  const long long words = (long long)(s.pitch >> 2) * s.ny;
-  k_restrict<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(a.node, ctx->cnt.as<unsigned char>(), s);
-  TD_LAUNCHED();
+  if (finish) {
+    const long long words = (long long)(s.pitch >> 2) * s.ny;
+    k_restrict<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(a.node, ctx->cnt.as<unsigned char>(), s);
+    TD_LAUNCHED();
+  }
   TD_CUDA(cudaGetLastError());
   return TD_OK;
+}
+
+// the whole restriction on a single strip
+int sweep_restrict_upstream(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, cudaStream_t st) {
+  if (s.has_top || s.has_bot) { set_error("sweep_restrict_upstream: row strips go through sweep_restrict_round"); return TD_ERR_ARG; }
+  TD_CUDA(ctx->halo.ensure(sizeof(int) * 2 * (size_t)s.pitch));
+  return sweep_restrict_round(ctx, s, cols, rows, nout, nullptr, nullptr, ctx->halo.as<int>(), 1, st);
 }
 
 }  // namespace td

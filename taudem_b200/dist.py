@@ -187,7 +187,29 @@ class DistTools:
                                                  None if dec_bot is None else C.c_void_p(dec_bot.data_ptr()), self._stream()))
         return out
 
-    def aread8(self, p, ad8=None, w=None, nodata=-32768, w_nodata=-9999.0, contcheck=True, shared=False):
+    def _restrict(self, outlets):
+        """-o over row strips: the upstream flood of the outlets in rounds (requests for the neighbours' edge rows travel like
+        the sweeps' halo counts; the outlet branch of initNeighborD8up / initNeighborDinfup, src/commonLib.cpp:300-375)."""
+        import numpy as np
+        s = self.s
+        cols = np.ascontiguousarray(outlets[0], np.int32)
+        rows = np.ascontiguousarray(np.asarray(outlets[1], np.int64) - self.row0, np.int32)    # row 0 = my first owned row
+        req = torch.zeros(2 * s.pitch, dtype=torch.int32, device=s.device)
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        in_top = in_bot = None
+        nout = len(cols)
+        while True:
+            check(self.l.td_sweep_restrict_round_dev(self.T.ctx, s.c, cols.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.c_void_p), nout,
+                                                     ptr(in_top), ptr(in_bot), ptr(req), 0, self._stream()))
+            nout = -1
+            if self.world == 1:
+                break
+            in_top, in_bot = exchange_counts(req, s.pitch, self.rank, self.world)
+            if all_reduce_scalar(int(req.sum()), device=s.device) == 0:
+                break
+        check(self.l.td_sweep_restrict_round_dev(self.T.ctx, s.c, None, None, -1, None, None, ptr(req), 1, self._stream()))
+
+    def aread8(self, p, ad8=None, w=None, nodata=-32768, w_nodata=-9999.0, contcheck=True, shared=False, outlets=None):
         s = self.s
         ad8 = s.empty(torch.float32) if ad8 is None else ad8
         if not shared:
@@ -195,11 +217,13 @@ class DistTools:
         if self.peer:
             self._peer_setup(False)
         self.T.aread8_deps(s, p, ad8, nodata)
+        if outlets is not None:
+            self._restrict(outlets)
         wp = None if w is None else C.c_void_p(w.data_ptr())
         return self._sweep(lambda halo: check(self.l.td_aread8_sweep_run_dev(self.T.ctx, wp, C.c_void_p(ad8.data_ptr()), s.c, w_nodata, int(w is not None),
                                                                               int(contcheck), C.c_void_p(halo.data_ptr()), self._stream())), ad8)
 
-    def areadinf(self, ang, dxc, dyc, sca=None, w=None, nodata=-3.4028234663852886e38, contcheck=True, shared=False):
+    def areadinf(self, ang, dxc, dyc, sca=None, w=None, nodata=-3.4028234663852886e38, contcheck=True, shared=False, outlets=None):
         s = self.s
         sca = s.empty(torch.float32) if sca is None else sca
         if not shared:
@@ -207,6 +231,8 @@ class DistTools:
         if self.peer:
             self._peer_setup(True)
         self.T.areadinf_deps(s, ang, sca, dxc, dyc, nodata)
+        if outlets is not None:
+            self._restrict(outlets)
         wp = None if w is None else C.c_void_p(w.data_ptr())
         return self._sweep(lambda halo: check(self.l.td_area_sweep_run_dev(self.T.ctx, C.c_void_p(ang.data_ptr()), wp, C.c_void_p(sca.data_ptr()), s.c,
                                                                             int(w is not None), int(contcheck), C.c_void_p(dxc.data_ptr()),

@@ -123,9 +123,33 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   const int per = ny / nstrips;
   for (int i = 0; i < nstrips; ++i)
     build_strip(S[i], dinf, dir, usew ? wgt : nullptr, nx, ny, i * per, i == nstrips - 1 ? ny - i * per : per, dir_nodata, dx, dy);
-  if (nout >= 0) {          // -o: only the cells upstream of the outlets (single strip)
-    if (nstrips != 1) return 3;
-    if (int rc = td::sweep_restrict_upstream(&S[0].ctx, S[0].s, outlet_cols, outlet_rows, nout, nullptr)) return rc;
+  if (nout >= 0) {          // -o: only the cells upstream of the outlets; row strips exchange requests like DistTools._restrict
+    std::vector<std::vector<int>> req(nstrips), inreq(nstrips);
+    std::vector<int> lrows(nout > 0 ? nout : 1);
+    bool firstround = true;
+    for (;;) {
+      long long asked = 0;
+      for (int i = 0; i < nstrips; ++i) {
+        StripState& T = S[i];
+        const int pitch = T.s.pitch;
+        req[i].assign(2 * (size_t)pitch, 0);
+        for (int o = 0; o < nout; ++o) lrows[o] = outlet_rows[o] - T.row0;
+        const int* in_top = (!firstround && i > 0) ? inreq[i].data() : nullptr;
+        const int* in_bot = (!firstround && i + 1 < nstrips) ? inreq[i].data() + pitch : nullptr;
+        if (int rc = td::sweep_restrict_round(&T.ctx, T.s, outlet_cols, lrows.data(), firstround ? nout : -1, in_top, in_bot, req[i].data(), 0, nullptr)) return rc;
+      }
+      firstround = false;
+      for (int i = 0; i < nstrips; ++i) {            // exchange_counts: what the strip above sent down / the strip below sent up
+        const int pitch = S[i].s.pitch;
+        inreq[i].assign(2 * (size_t)pitch, 0);
+        if (i > 0) for (int c = 0; c < pitch; ++c) inreq[i][c] = req[i - 1][pitch + c];
+        if (i + 1 < nstrips) for (int c = 0; c < pitch; ++c) inreq[i][pitch + c] = req[i + 1][c];
+        for (int v : req[i]) asked += v;
+      }
+      if (asked == 0) break;
+    }
+    for (int i = 0; i < nstrips; ++i)
+      if (int rc = td::sweep_restrict_round(&S[i].ctx, S[i].s, nullptr, nullptr, -1, nullptr, nullptr, req[i].data(), 1, nullptr)) return rc;
   }
   bool first = true;
   int rounds = 0;

@@ -289,6 +289,10 @@ def test_emulated_outlets_restrict_the_sweep(emu, fields):
     assert_bits(_run(emu, False, 0, 0, p, w, False, 62, outlets=outs), port.aread8(p, weights=w, contcheck=False, outlets=outs), "ad8 -o -wg -nc")
     assert_bits(_run(emu, True, 1, 3, ang, None, True, 63, outlets=outs), port.areadinf(ang, outlets=outs), "sca -o")
     assert_bits(_run(emu, False, 0, 0, p, None, True, 64, outlets=([], [])), np.full(p.shape, -1.0, np.float32), "ad8 -o without points")
+    # row strips: the flood crosses the strip boundaries in rounds of requests
+    for n in (2, 5):
+        assert_bits(_run(emu, False, 1, 3, p, None, True, 65, n, outlets=outs), ref, f"ad8 -o, {n} strips")
+        assert_bits(_run(emu, True, 1, 3, ang, None, True, 66, n, outlets=outs), port.areadinf(ang, outlets=outs), f"sca -o, {n} strips")
 
 
 @pytest.mark.parametrize("rows_per_strip", [1, 2, 3])
