@@ -6,7 +6,7 @@
 // evaluated in double precision exactly as VSLOPE does; the first facet with the
 // strictly largest slope wins; angle = (float)(ANGC*PI/2 + ANGF*A), slope = (float)Smax;
 // no facet with S > 0 -> angle -1 (flat), slope 0.
-// The eight facets are first ranked with a float copy of the same formula; only the facets within 1e-3
+// The eight facets are first ranked with a float copy of the same formula (squared slopes, no root); only the facets within 1e-3
 // of the best approximate slope (1-2 in practice) are evaluated in FP64, in increasing K with the
 // reference's strict '>' — the exact winner is always among them.
 // HBM traffic per cell: read fel 4 B, write ang 4 B + slp 4 B = 12 B (algorithmic);
@@ -64,12 +64,14 @@ __global__ void __launch_bounds__(256) k_dinf_stencil(const float* __restrict__ 
         const float d1f = fD1isDx(K) ? dxf : dyf, d2f = fD1isDx(K) ? dyf : dxf;
         const float s1 = (z - e1) * r1, s2 = (e1 - e2) * r2;
         const bool clip = (s1 <= 0.f) ? !(s1 == 0.f && s2 == 0.f) : (s2 * d1f > s1 * d2f);
-        const float S = (s2 < 0.f) ? s1 : (clip ? (z - e2) * rdd : sqrtf(s1 * s1 + s2 * s2));
-        st[K - 1] = S;
-        smaxf = fmaxf(smaxf, S);
+        // squared slope (0 for a non-positive one): the ranking needs no square root
+        const float lin = (s2 < 0.f) ? s1 : (z - e2) * rdd;
+        const float Q = (s2 < 0.f || clip) ? (lin > 0.f ? lin * lin : 0.f) : s1 * s1 + s2 * s2;
+        st[K - 1] = Q;
+        smaxf = fmaxf(smaxf, Q);
       }
       unsigned cand = 0;
-      const float thr = smaxf * 0.999f;
+      const float thr = smaxf * 0.998f;            // (0.999)^2
 #pragma unroll
       for (int K = 1; K <= 8; ++K) cand |= (st[K - 1] >= thr && st[K - 1] > 0.f) ? (1u << (K - 1)) : 0u;
       if (bad) cand = 0;
