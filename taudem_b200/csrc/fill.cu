@@ -21,22 +21,62 @@ constexpr int FW = 64, FH = 32;
 constexpr int SW = FW + 2;                 // shared W row stride (with ring)
 #define TD_FELNODATA (-3.0e38f)
 
+// Initialisation (src/flood.cpp:243-271): nodata stays nodata, cells of the depression mask, cells on the edge of the
+// grid and cells with a nodata neighbour (8 or 4 neighbours) keep their elevation, everything else starts "under water"
+// (FLT_MAX).  A 3x3 stencil in the style of the flow-direction stencils: TMA-staged 32 x 128 tile, four cells per thread,
+// nodata through fmin chains over |z - nodata|, one float4 store.  8 B/cell (+2 with a mask).
+constexpr int IW = 128, IH = 32;
 __global__ void __launch_bounds__(256) k_fill_init(const float* __restrict__ dem, const short* __restrict__ mask,
                                                    float* __restrict__ W, Strip s, float nodata, int step) {
-  const int c = blockIdx.y * blockDim.x + threadIdx.x, r = 1 + blockIdx.x;   // rows on grid.x (no 65535 limit)
-  if (c >= s.nx) return;
-  const long long ci = s.idx(r, c);
-  const float z = dem[ci];
-  float out;
-  if (nd_f(z, nodata)) out = TD_FELNODATA;
-  else if (mask != nullptr && mask[ci] == 1) out = z;
-  else if (s.global_edge(r, c)) out = z;
-  else {
-    bool con = false;
-    for (int k = 1; k <= 8; k += step) con = con || nd_f(dem[ci + (long long)drow(k) * s.pitch + dcol(k)], nodata);
-    out = con ? z : FLT_MAX;
+  using G = TileGeom<float, IW, IH>;
+  __shared__ __align__(128) float tile[G::ELEMS];
+  __shared__ __align__(8) uint64_t bar;
+  const int c0 = blockIdx.x * IW, r0 = 1 + blockIdx.y * IH;
+  load_tile_tma<float, IW, IH>(tile, &bar, dem, s, r0, c0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int pass = 0; pass < IH / 8; ++pass) {
+    const int tr = warp + 8 * pass;
+    const int r = r0 + tr, c = c0 + lane * 4;
+    if (r > s.ny || c >= s.pitch) continue;
+    const float* pm = tile + tr * G::SW + G::HP + lane * 4;   // row above, column c
+    float nb[3][6], a[3][6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float* p = pm + j * G::SW;
+      const float4 v = *reinterpret_cast<const float4*>(p);
+      nb[j][0] = p[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = p[4];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        // a neighbour off the grid does not count (the cell is an edge cell anyway): huge distance
+        const bool on = s.on_grid(r - 1 + j, c - 1 + i);
+        a[j][i] = on ? fabsf(nb[j][i] - nodata) : FLT_MAX;
+      }
+    }
+    unsigned em = ((r == 1 && !s.has_top) || (r == s.ny && !s.has_bot)) ? 0xfu : 0u;     // cells on the edge of the whole grid
+    em |= (c == 0) ? 1u : 0u;
+    const int klast = s.nx - 1 - c;
+    if (klast < 4) em |= (0xfu << max(klast, 0)) & 0xfu;
+    short4 mk = make_short4(0, 0, 0, 0);
+    if (mask != nullptr) mk = *reinterpret_cast<const short4*>(mask + s.idx(r, c));
+    const short m4[4] = {mk.x, mk.y, mk.z, mk.w};
+    float out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float z = nb[1][i + 1];
+      float dmin;
+      if (step == 1)
+        dmin = fminf(fminf(fminf(a[0][i], a[0][i + 1]), fminf(a[0][i + 2], a[1][i])), fminf(fminf(a[1][i + 2], a[2][i]), fminf(a[2][i + 1], a[2][i + 2])));
+      else
+        dmin = fminf(fminf(a[0][i + 1], a[2][i + 1]), fminf(a[1][i], a[1][i + 2]));
+      const bool keep = (m4[i] == 1) || ((em >> i) & 1u) || dmin < TD_MINEPS;
+      float v = keep ? z : FLT_MAX;
+      if (a[1][i + 1] < TD_MINEPS) v = TD_FELNODATA;
+      if (c + i >= s.nx) v = TD_FELNODATA;                       // padding columns
+      out[i] = v;
+    }
+    *reinterpret_cast<float4*>(W + s.idx(r, c)) = make_float4(out[0], out[1], out[2], out[3]);
   }
-  W[ci] = out;
 }
 
 // flag[t] = last round for which tile t has been queued
@@ -105,7 +145,7 @@ __global__ void k_fill_all_tiles(int* list, int* flag, int n) {
 }  // namespace
 
 int fill_init(const float* dem, const short* mask, float* W, const Strip& s, float nodata, int four, cudaStream_t st) {
-  dim3 grid(s.ny, (s.nx + 255) / 256);
+  dim3 grid((s.pitch + IW - 1) / IW, (s.ny + IH - 1) / IH);
   k_fill_init<<<grid, 256, 0, st>>>(dem, mask, W, s, nodata, four ? 2 : 1);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
