@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     unsigned char code = 0x20;
     if (s.on_grid(gr, gc)) {
       const float av = tile[i];
-      if (!nd_f(av, nodata)) { const Outflow o = dinf_outflow(av, saref + t * 10); code = (unsigned char)(o.k1 | (o.k2 ? 0x10 : 0)); }
+      if (!nd_f(av, nodata)) code = (unsigned char)dinf_receivers(av, saref + t * 10);
     }
     sout[i] = code;
   }

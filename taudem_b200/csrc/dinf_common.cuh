@@ -127,6 +127,36 @@ __device__ __forceinline__ Outflow dinf_outflow_t(float a, const AR& ar) {
   if (!(pB < 1e-5)) { if (o.k1 == 0) { o.k1 = kB; o.p1 = pB; } else { o.k2 = kB; o.p2 = pB; } }
   return o;
 }
+// p >= 1e-5 for p = num / den (den > 0) without the division: p is only compared with the threshold, and the rounded
+// quotient can differ from num / den by half an ulp, so anything outside a 2^-40 band around 1e-5 * den is decided by
+// one multiplication; inside the band (practically never) the division itself decides.
+__device__ __forceinline__ bool share_counts(double num, double den) {
+  const double t = 1e-5 * den;
+  if (num > t * (1. + 0x1p-40)) return true;
+  if (num < t * (1. - 0x1p-40)) return false;
+  return !(num / den < 1e-5);
+}
+
+// Only the receivers of a cell, coded as k1 | 0x10 if there is a second one (k1 % 8 + 1) — what the dependency stencil
+// needs — without evaluating the shares: same interval search as dinf_outflow, two multiplications instead of two
+// divisions in the sectors 1..7; the wrap sector and angles outside [0, 2 PI) go through dinf_outflow itself.
+template <typename AR>
+__device__ __forceinline__ unsigned dinf_receivers(float a, const AR& ar) {
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i <= 9; ++i) j += (a >= ar[i]) ? 1 : 0;
+  if (j >= 1 && j <= 7) {
+    const double lo = ar[j - 1], mid = ar[j], hi = ar[j + 1];
+    const bool up = a > mid;
+    const bool cA = up ? share_counts(hi - a, hi - mid) : share_counts(a - lo, mid - lo);     // pA >= 1e-5
+    const bool cB = up && share_counts(a - mid, hi - mid);                                      // pB >= 1e-5 (pB = 0 unless a > mid)
+    if (cA) return (unsigned)j | (cB ? 0x10u : 0u);
+    return cB ? (unsigned)(j + 1) : 0u;
+  }
+  const Outflow o = dinf_outflow_t(a, ar);
+  return (unsigned)o.k1 | (o.k2 ? 0x10u : 0u);
+}
+
 __device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) { return dinf_outflow_t(a, ar); }
 __device__ __forceinline__ Outflow dinf_outflow(float a, double t) { return dinf_outflow_t(a, ArefRow{t}); }
 
