@@ -22,10 +22,12 @@
 //             a global list that the host drains with another launch.
 // Modes: "levels" = K passes of k_level, then k_ready + k_walk;  "hybrid" = one visit of every tile by the
 // tile kernel (sweep_tiles.cu, `once`), then k_ready + k_walk;  "walk" = k_ready + k_walk from the sources.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
 #include <chrono>
+#include <vector>
 
 #include "ctx.h"
 #include "dinf_common.cuh"
@@ -56,7 +58,8 @@ struct WalkArgs {
   unsigned long long* ctr;    // [0] list ticket, [1] spill length, [2] spill list exhausted, [3] ready cells (collect)
   long long* spill;            // D-infinity: forks that did not fit the warp's stack; D8: parked river heads (k_river)
   unsigned long long spill_cap;
-  int river_hops;              // D8: a lane that has followed one chain for this many cells parks it for k_river (0 = never)
+  int river_hops;              // a lane that has followed one chain for this many cells parks it for k_river (0 = never)
+  unsigned long long* pass_cells;   // k_level diagnostics (TAUDEM_B200_TIMING=2): cells evaluated by this pass, or NULL
 };
 
 __device__ __forceinline__ unsigned dec_count(unsigned* words, long long cell) {
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(256) k_level(const WalkArgs a) {
     for (int i = 0; i < 4; ++i)
       if (((word >> (8 * i)) & 0xffu) == 0u && c0 + 4 * j + i < s.nx) todo |= 1u << (4 * j + i);
   }
+  if (a.pass_cells && todo) atomicAdd(a.pass_cells, (unsigned long long)__popc(todo));
   unsigned d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll 1
   while (todo) {
@@ -519,7 +523,7 @@ void walk_args(td_ctx* ctx, WalkArgs& a, float* area, const float* w, const floa
   a.node = ctx->node.as<unsigned short>(); a.cntw = ctx->cnt.as<unsigned>();
   a.area = area; a.w = w; a.ang = ang; a.s = s; a.usew = usew; a.contcheck = contcheck; a.w_nodata = w_nodata;
   a.theta = theta; a.dxc = dxc; a.halo = halo;
-  a.list = nullptr; a.nlist = 0; a.spill = nullptr; a.spill_cap = 0; a.river_hops = 0;
+  a.list = nullptr; a.nlist = 0; a.spill = nullptr; a.spill_cap = 0; a.river_hops = 0; a.pass_cells = nullptr;
   a.ctr = ctx->d_ctr + 16;
 }
 }  // namespace
@@ -540,12 +544,25 @@ int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w
   const unsigned blocks = (unsigned)((groups + 255) / 256);
   for (double& v : ctx->phase_ms) v = 0.;
   PhaseTimer tm(st);
+  const char* te = getenv("TAUDEM_B200_TIMING");
+  const bool diag = te && atoi(te) >= 2 && passes > 0;          // per-pass cell counts on stderr (for choosing TAUDEM_B200_LEVELS)
+  if (diag) { TD_CUDA(ctx->rows.ensure(sizeof(unsigned long long) * (size_t)passes)); TD_CUDA(cudaMemsetAsync(ctx->rows.p, 0, sizeof(unsigned long long) * (size_t)passes, st)); }
   for (int p = 0; p < passes; ++p) {
+    a.pass_cells = diag ? ctx->rows.as<unsigned long long>() + p : nullptr;
     if (dinf) k_level<true><<<blocks, 256, 0, st>>>(a); else k_level<false><<<blocks, 256, 0, st>>>(a);
     TD_LAUNCHED();
   }
   TD_CUDA(cudaGetLastError());
   tm.lap(&ctx->phase_ms[0]);
+  if (diag) {
+    std::vector<unsigned long long> pc((size_t)passes);
+    TD_CUDA(cudaMemcpyAsync(pc.data(), ctx->rows.p, sizeof(unsigned long long) * (size_t)passes, cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaStreamSynchronize(st));
+    unsigned long long sum = 0;
+    fprintf(stderr, "[k_level %s] cells evaluated per pass:", dinf ? "dinf" : "d8");
+    for (int p = 0; p < passes; ++p) { sum += pc[p]; fprintf(stderr, " %llu", pc[p]); }
+    fprintf(stderr, "  total %llu of %lld\n", sum, (long long)s.nx * s.ny);
+  }
   return TD_OK;
 }
 
