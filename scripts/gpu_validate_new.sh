@@ -5,6 +5,7 @@
 #   gpurun --timeout 1800 -- 'bash scripts/gpu_validate_new.sh perf'    timings of every schedule, phases, stencils, bench lines
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_validate_new.sh extra'   batched flats, row strips on one GPU (gloo)
 #   gpurun --gpus 2 --timeout 900 -- 'bash scripts/gpu_validate_new.sh dist'   strip flats + level sweeps over NCCL
+#   gpurun --gpus 8 --timeout 900 -- 'bash scripts/gpu_validate_new.sh dist8'  peer mode and level sweeps on 8 strips
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
@@ -12,6 +13,13 @@ step() { local name=$1; shift; echo "=== $name"; ( time timeout "$@" ) > "gpurun
 summary() { grep -h "DIFFERENT\|identical\|passed\|failed\|Error\|error" gpurun_out/*.log | sort | uniq -c | sort -rn | head -40; }
 
 case "${1:-core}" in
+dist8)
+  # gpurun --gpus 8 --timeout 900 -- 'bash scripts/gpu_validate_new.sh dist8': peer mode and level sweeps on 8 strips
+  TAUDEM_B200_PEER=1 TD_BACKEND=nccl step dist8_tiles_peer 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=8 \
+    --master-addr 127.0.0.1 --master-port 29513 scripts/dist_check.py 6000 5000
+  TAUDEM_B200_SWEEP=levels TAUDEM_B200_FLATS=strips TD_BACKEND=nccl step dist8_levels_strips 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node=8 \
+    --master-addr 127.0.0.1 --master-port 29514 scripts/dist_check.py 6000 5000
+  ;;
 dist)
   for mode in "" levels; do
     for flats in "" strips; do
