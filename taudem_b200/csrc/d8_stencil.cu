@@ -129,8 +129,17 @@ __global__ void __launch_bounds__(256) k_d8_stencil(const float* __restrict__ el
     *reinterpret_cast<float4*>(slope + o) = make_float4(os[0], os[1], os[2], os[3]);
   }
   // flat count: warp reduce, one atomic per warp that saw flats
+  // flat count: warp reduce, then one atomic per CTA (a million CTAs at 65536^2 all add to the same word)
+  __shared__ unsigned wflat[8];
   for (int o = 16; o; o >>= 1) myflat += __shfl_xor_sync(0xffffffffu, myflat, o);
-  if (lane == 0 && myflat) atomicAdd(nflat, (unsigned long long)myflat);
+  if (lane == 0) wflat[warp] = myflat;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += wflat[i];
+    if (t) atomicAdd(nflat, (unsigned long long)t);
+  }
 }
 }  // namespace
 

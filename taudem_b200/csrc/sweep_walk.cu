@@ -239,17 +239,24 @@ __global__ void __launch_bounds__(256) k_ready(const unsigned* __restrict__ cntw
         if (((word >> (8 * i)) & 0xffu) == 0u && c + i < s.nx && (node[ci + i] & NODE_VALID)) cells[n++] = ci + i;
     }
   }
-  // warp-aggregated reservation
+  // block-aggregated reservation: one atomic per CTA (a single address takes every reservation of the grid)
+  __shared__ int wtot[8];
+  __shared__ unsigned long long bbase;
   const unsigned lane = threadIdx.x & 31u;
+  const int wid = threadIdx.x >> 5;
   int incl = n;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += v; }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 31) wtot[wid] = incl;
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { if (i < wid) before += wtot[i]; total += wtot[i]; }
   if (total == 0) return;
-  unsigned long long base = 0;
-  if (lane == 31) base = atomicAdd(ctr + (FILL ? 0 : 3), (unsigned long long)total);
+  if (threadIdx.x == 0) bbase = atomicAdd(ctr + (FILL ? 0 : 3), (unsigned long long)total);
   if (!FILL) return;
-  base = __shfl_sync(0xffffffffu, base, 31);
+  __syncthreads();
+  const unsigned long long base = bbase + (unsigned long long)before;
   for (int i = 0; i < n; ++i) list[base + (unsigned long long)(incl - n + i)] = cells[i];
 }
 
