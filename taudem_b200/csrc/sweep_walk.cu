@@ -93,7 +93,8 @@ __device__ __noinline__ double share_full(float ang, double t, int kk) {
 // receivers.  Receivers whose count reached zero through this decrement are returned in ready[0..1]
 // (with their node words) — the caller decides whether it follows them.
 template <bool DINF>
-__device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r, int c, unsigned nd, long long* ready, unsigned* ready_nd) {
+__device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r, int c, unsigned nd, long long* ready, unsigned* ready_nd,
+                                         int* ready_r, int* ready_c) {
   const Strip& s = a.s;
   const unsigned m = nd & 0xffu;
   bool con = (nd & NODE_CON) != 0;
@@ -126,7 +127,7 @@ __device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r,
     // src/aread8.cpp:261-272
     if (cin >= 0) {
       if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); }
-      else if ((ndn & NODE_VALID) && dec_count(a.cntw, cin) == 1u) { ready[0] = cin; ready_nd[0] = ndn; nready = 1; }
+      else if ((ndn & NODE_VALID) && dec_count(a.cntw, cin) == 1u) { ready[0] = cin; ready_nd[0] = ndn; ready_r[0] = rn; ready_c[0] = cn; nready = 1; }
     }
   } else {
     // src/areadinf.cpp:187-218.  The share a contributor sends here is prop(angle, direction): for a contributor with
@@ -173,7 +174,8 @@ __device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r,
       const unsigned ndn = a.node[cin];
       if (!(ndn & NODE_VALID)) continue;
       if (dec_count(a.cntw, cin) == 1u) {
-        if (nready == 0) { ready[0] = cin; ready_nd[0] = ndn; } else { ready[1] = cin; ready_nd[1] = ndn; }
+        if (nready == 0) { ready[0] = cin; ready_nd[0] = ndn; ready_r[0] = rn; ready_c[0] = cn; }
+        else { ready[1] = cin; ready_nd[1] = ndn; ready_r[1] = rn; ready_c[1] = cn; }
         ++nready;
       }
     }
@@ -209,8 +211,8 @@ __global__ void __launch_bounds__(256) k_level(const WalkArgs a) {
     todo &= todo - 1;
     const unsigned nd = a.node[base + b];
     if (!(nd & NODE_VALID)) continue;
-    long long ready[2]; unsigned rnd[2];
-    eval_cell<DINF>(a, base + b, r, c0 + b, nd, ready, rnd);            // receivers wait for their owners
+    long long ready[2]; unsigned rnd[2]; int rr[2], rc[2];
+    eval_cell<DINF>(a, base + b, r, c0 + b, nd, ready, rnd, rr, rc);    // receivers wait for their owners
     const unsigned bit = 0xfeu << (8 * (b & 3));
     if ((b >> 2) == 0) d0 |= bit; else if ((b >> 2) == 1) d1 |= bit; else if ((b >> 2) == 2) d2 |= bit; else d3 |= bit;
   }
@@ -273,7 +275,8 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
   long long cur = -1;
   unsigned curnd = 0;
   bool have_nd = false;
-  int hops = 0;                         // cells of the current chain (D8 river parking)
+  int hops = 0;                         // cells of the current chain (river parking)
+  int curr = 0, curc = 0;               // row / column of `cur` when have_nd (a 64-bit division per hop otherwise)
   bool list_done = a.nlist == 0;        // warp-uniform
   for (;;) {
     // ---- refill idle lanes: the warp's fork stack first, then a batch of the global ready list
@@ -302,12 +305,14 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
     long long fork = -1;
     if (cur >= 0) {
       const long long ci = cur;
-      const int r = (int)(ci / s.pitch), c = (int)(ci - (long long)r * s.pitch);
+      int r, c;
+      if (have_nd) { r = curr; c = curc; }
+      else { r = (int)(ci / s.pitch); c = (int)(ci - (long long)r * s.pitch); }
       const unsigned nd = have_nd ? curnd : (unsigned)a.node[ci];
-      long long ready[2]; unsigned rnd[2];
-      const int nr = eval_cell<DINF>(a, ci, r, c, nd, ready, rnd);
+      long long ready[2]; unsigned rnd[2]; int rr[2], rc[2];
+      const int nr = eval_cell<DINF>(a, ci, r, c, nd, ready, rnd, rr, rc);
       atomicAdd(a.cntw + (ci >> 2), 0xfeu << ((unsigned)(ci & 3) * 8u));     // 0 -> 0xFE (evaluated), like k_level and the tile kernel
-      if (nr >= 1) { cur = ready[0]; curnd = rnd[0]; have_nd = true; } else cur = -1;
+      if (nr >= 1) { cur = ready[0]; curnd = rnd[0]; curr = rr[0]; curc = rc[0]; have_nd = true; } else cur = -1;
       if (a.river_hops > 0 && cur >= 0 && ++hops >= a.river_hops) {
         // a long chain: most likely a river.  Its next cell (ready, not evaluated) goes to the river list, where a
         // whole warp follows it with look-ahead (k_river) once the short chains are done.
