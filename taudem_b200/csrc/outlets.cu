@@ -92,10 +92,8 @@ __global__ void __launch_bounds__(256) k_upstream(const UpArgs a) {
 
 // one thread per four cells of a row
 __global__ void __launch_bounds__(256) k_restrict(unsigned short* __restrict__ node, unsigned char* __restrict__ cnt, Strip s) {
-  const long long wpr = s.pitch >> 2;
-  const long long wi = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (wi >= wpr * s.ny) return;
-  const int r = 1 + (int)(wi / wpr), c = (int)(wi - (long long)(r - 1) * wpr) * 4;
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;   // rows on grid.x
+  if (c >= s.pitch) return;
   const long long o = s.idx(r, c);
   ushort4 nd = *reinterpret_cast<ushort4*>(node + o);
   uchar4 cn = *reinterpret_cast<uchar4*>(cnt + o);
@@ -170,8 +168,8 @@ int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int
     cur = spill; std::swap(spill, other);
   }
   if (finish) {
-    const long long words = (long long)(s.pitch >> 2) * s.ny;
-    k_restrict<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(a.node, ctx->cnt.as<unsigned char>(), s);
+    const dim3 rgrid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
+    k_restrict<<<rgrid, 256, 0, st>>>(a.node, ctx->cnt.as<unsigned char>(), s);
     TD_LAUNCHED();
   }
   TD_CUDA(cudaGetLastError());

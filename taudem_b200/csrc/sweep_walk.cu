@@ -187,10 +187,9 @@ __device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r,
 template <bool DINF>
 __global__ void __launch_bounds__(256) k_level(const WalkArgs a) {
   const Strip& s = a.s;
-  const long long gpr = s.pitch >> 4;                                   // 16-cell groups per row (pitch % 32 == 0)
-  const long long gi = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (gi >= gpr * s.ny) return;
-  const int r = 1 + (int)(gi / gpr), c0 = (int)(gi - (long long)(r - 1) * gpr) * 16;
+  // rows on grid.x (no 65535 limit), 16-cell groups of the row on grid.y x threads (pitch % 32 == 0): no division
+  const int r = 1 + (int)blockIdx.x, c0 = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 16;
+  if (c0 >= s.pitch) return;
   const long long base = s.idx(r, c0);
   const uint4 q = __ldcg(reinterpret_cast<const uint4*>(a.cntw + (base >> 2)));
   const unsigned w4[4] = {q.x, q.y, q.z, q.w};
@@ -227,12 +226,10 @@ __global__ void __launch_bounds__(256) k_level(const WalkArgs a) {
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_ready(const unsigned* __restrict__ cntw, const unsigned short* __restrict__ node, Strip s,
                                                unsigned long long* __restrict__ ctr, long long* __restrict__ list) {
-  const long long wpr = s.pitch >> 2;                                   // words per row
-  const long long wi = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;   // rows on grid.x, words of the row on grid.y x threads
   int n = 0;
   long long cells[4];
-  if (wi < wpr * s.ny) {
-    const int r = 1 + (int)(wi / wpr), c = (int)(wi - (long long)(r - 1) * wpr) * 4;
+  if (c < s.pitch) {
     const long long ci = s.idx(r, c);
     const unsigned word = cntw[ci >> 2];
     if (((word - 0x01010101u) & ~word & 0x80808080u) != 0u) {
@@ -552,8 +549,7 @@ int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w
                  int usew, int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
   WalkArgs a;
   walk_args(ctx, a, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo);
-  const long long groups = (long long)(s.pitch >> 4) * s.ny;
-  const unsigned blocks = (unsigned)((groups + 255) / 256);
+  const dim3 blocks((unsigned)s.ny, (unsigned)(((s.pitch >> 4) + 255) / 256));
   for (double& v : ctx->phase_ms) v = 0.;
   PhaseTimer tm(st);
   const char* te = getenv("TAUDEM_B200_TIMING");
@@ -585,8 +581,7 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   WalkArgs a;
   walk_args(ctx, a, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo);
   unsigned long long* hc = ctx->h_ctr + 16;
-  const long long words = (long long)(s.pitch >> 2) * s.ny;
-  const unsigned blocks = (unsigned)((words + 255) / 256);
+  const dim3 blocks((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
   PhaseTimer tm(st);
   TD_CUDA(cudaMemsetAsync(a.ctr, 0, 4 * sizeof(unsigned long long), st));
   k_ready<false><<<blocks, 256, 0, st>>>(a.cntw, a.node, s, a.ctr, nullptr);
