@@ -70,14 +70,21 @@ inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 // ---- fibers
 namespace emu {
+// context of a fiber: on x86-64 just the saved stack pointer (callee-saved registers live on the fiber's stack; no signal
+// mask system calls like swapcontext makes), elsewhere a ucontext
+#if defined(__x86_64__)
+struct Context { void* sp = nullptr; };
+#else
+struct Context { ucontext_t uc; };
+#endif
 struct Fiber {
-  ucontext_t ctx;
+  Context ctx;
   bool done = false;
   dim3 tid;
 };
 struct Block {
   std::vector<Fiber> f;
-  ucontext_t sched;
+  Context sched;
   int cur = -1;
   int alive = 0;
   // warp collectives: one slot per participant mask (a *_sync with a partial mask involves only those lanes);

@@ -3,6 +3,48 @@
 
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+// ---- context switch
+#if defined(__x86_64__)
+extern "C" void emu_switch_sp(void** from_sp, void* const* to_sp);
+asm(R"(
+.text
+.globl emu_switch_sp
+.type emu_switch_sp,@function
+emu_switch_sp:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq (%rsi), %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch_sp,.-emu_switch_sp
+)");
+static inline void ctx_switch(emu::Context* from, emu::Context* to) { emu_switch_sp(&from->sp, &to->sp); }
+static inline void ctx_make(emu::Context* c, char* stack, size_t size, void (*fn)()) {
+  // after the six pops and the ret of emu_switch_sp the fiber starts in fn with a call-like stack alignment
+  uintptr_t top = ((uintptr_t)stack + size) & ~(uintptr_t)15;
+  void** sp = (void**)top;
+  *--sp = nullptr;             // fake return address of fn (it never returns)
+  *--sp = (void*)fn;
+  for (int i = 0; i < 6; ++i) *--sp = nullptr;
+  c->sp = sp;
+}
+#else
+static inline void ctx_switch(emu::Context* from, emu::Context* to) { swapcontext(&from->uc, &to->uc); }
+static inline void ctx_make(emu::Context* c, char* stack, size_t size, void (*fn)()) {
+  getcontext(&c->uc); c->uc.uc_stack.ss_sp = stack; c->uc.uc_stack.ss_size = size; c->uc.uc_link = nullptr; makecontext(&c->uc, fn, 0);
+}
+#endif
+
 namespace emu {
 thread_local Block* g_blk = nullptr;
 thread_local unsigned long long g_rng = 12345;
@@ -37,7 +79,7 @@ void trampoline() {
   const unsigned alive = alive_mask(b, w);
   for (auto& S : b->warps[w].slots)
     if (S.arrived > 0 && S.arrived == __builtin_popcount(S.mask & alive)) complete(b, w, S);
-  swapcontext(&b->f[me].ctx, &b->sched);
+  ctx_switch(&b->f[me].ctx, &b->sched);
 }
 
 void wait_on(const unsigned* ptr, unsigned val) {
@@ -45,7 +87,7 @@ void wait_on(const unsigned* ptr, unsigned val) {
   const int me = b->cur;
   while (*ptr == val) {
     g_wait[me].ptr = ptr; g_wait[me].val = val;
-    swapcontext(&b->f[me].ctx, &b->sched);
+    ctx_switch(&b->f[me].ctx, &b->sched);
   }
   g_wait[me].ptr = nullptr;
 }
@@ -72,7 +114,7 @@ void yield() {
   Block* b = g_blk;
   if (!b || b->cur < 0) return;
   const int me = b->cur;
-  swapcontext(&b->f[me].ctx, &b->sched);
+  ctx_switch(&b->f[me].ctx, &b->sched);
 }
 
 void run_block(dim3 grid, dim3 block, dim3 bid, const std::function<void()>& body) {
@@ -93,23 +135,20 @@ void run_block(dim3 grid, dim3 block, dim3 bid, const std::function<void()>& bod
     static thread_local std::vector<char*> pool;                 // fiber stacks are reused across blocks and launches
     while ((int)pool.size() <= i) pool.push_back((char*)malloc(STACK));
     f.tid = dim3(i % block.x, (i / block.x) % block.y, i / (block.x * block.y));
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = pool[i];
-    f.ctx.uc_stack.ss_size = STACK;
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, trampoline, 0);
+    ctx_make(&f.ctx, pool[i], STACK, trampoline);
   }
-  std::vector<int> runnable;
   while (blk.alive > 0) {
-    runnable.clear();
-    for (int i = 0; i < n; ++i)
-      if (!blk.f[i].done && (g_wait[i].ptr == nullptr || *g_wait[i].ptr != g_wait[i].val)) runnable.push_back(i);
-    if (runnable.empty()) { fprintf(stderr, "emu: deadlock (%d threads alive, none runnable)\n", blk.alive); abort(); }
-    // run a random runnable fiber; stay on it for a random number of scheduling points to get long and short interleavings
-    const int pick = runnable[rnd() % runnable.size()];
+    // a random runnable fiber: random start, linear probe (most fibers are runnable most of the time)
+    int pick = -1;
+    const int start = (int)(rnd() % (unsigned)n);
+    for (int k = 0; k < n; ++k) {
+      const int i = start + k < n ? start + k : start + k - n;
+      if (!blk.f[i].done && (g_wait[i].ptr == nullptr || *g_wait[i].ptr != g_wait[i].val)) { pick = i; break; }
+    }
+    if (pick < 0) { fprintf(stderr, "emu: deadlock (%d threads alive, none runnable)\n", blk.alive); abort(); }
     blk.cur = pick;
     threadIdx = blk.f[pick].tid;
-    swapcontext(&blk.sched, &blk.f[pick].ctx);
+    ctx_switch(&blk.sched, &blk.f[pick].ctx);
   }
   blk.cur = -1;
   g_blk = nullptr;
