@@ -411,3 +411,20 @@ def test_emulated_flat_resolution_batched_levels(emu, terraces, batch, monkeypat
         f = np.ascontiguousarray(g["fel"], np.float32)
         q0, _ = port.d8flowdir(f, dx=float(g["dx"]), dy=float(g["dy"]), flats=False)
         assert_bits(_flats(emu, False, f, q0, 1, 103, float(g["dx"]), float(g["dy"]))[0], g["p"], f"{name} p, batch {batch}")
+
+
+def test_emulated_sweeps_on_a_larger_grid(emu, monkeypatch):
+    """500 x 700 cells (352 D8 tiles / 704 D-infinity tiles, rivers of several hundred cells): the default tile dataflow, level
+    passes + walkers + rivers, single strip and four strips."""
+    from oracle import port
+    dem = synth.punch_holes(synth.gen_dem(500, 700, hurst=0.8, tilt=1.0, seed=31))
+    fel = port.pitremove(dem); p, _ = port.d8flowdir(fel); ang, _ = port.dinfflowdir(fel)
+    ad8 = port.aread8(p); sca = port.areadinf(ang)
+    assert ad8.max() > 1.0e4
+    assert_bits(_tiles(emu, False, 0, p, None, True, 201)[0], ad8, "ad8 tiles")
+    assert_bits(_tiles(emu, True, 0, ang, None, True, 202)[0], sca, "sca tiles")
+    monkeypatch.setenv("TAUDEM_B200_RIVER", "16")
+    assert_bits(_run(emu, False, 1, 6, p, None, True, 203), ad8, "ad8 levels + rivers")
+    assert_bits(_run(emu, True, 1, 6, ang, None, True, 204), sca, "sca levels + rivers")
+    assert_bits(_run(emu, False, 1, 6, p, None, True, 205, 4), ad8, "ad8 levels + rivers, 4 strips")
+    assert_bits(_run(emu, True, 1, 6, ang, None, True, 206, 4), sca, "sca levels + rivers, 4 strips")
