@@ -21,13 +21,13 @@ for seed in range(first, first + count):
     w=synth.gen_weights(ny,nx,seed=seed)
     ad8=port.aread8(p); sca=port.areadinf(ang); ad8w=port.aread8(p,weights=w,contcheck=False); scaw=port.areadinf(ang,weights=w,contcheck=False)
     strips=int(rng.integers(1,4))
-    os.environ["TAUDEM_B200_RIVER"]=str(int(rng.choice([0,1,2,5,16])))
+    os.environ["TAUDEM_B200_RIVER"]=str(int(rng.choice([0,1,2,5,16]))); os.environ["TAUDEM_B200_RIVER_DINF"]=str(int(rng.choice([0,1,3,16])))
     passes=int(rng.integers(0,6))
     checks=[('ad8',test_emu._run(lib,False,1,passes,p,None,True,seed,strips),ad8),
             ('sca',test_emu._run(lib,True,1,passes,ang,None,True,seed+1,strips),sca),
             ('ad8w',test_emu._run(lib,False,0,0,p,w,False,seed+2,strips),ad8w),
             ('scaw',test_emu._run(lib,True,0,0,ang,w,False,seed+3,strips),scaw)]
-    os.environ.pop("TAUDEM_B200_RIVER")
+    os.environ.pop("TAUDEM_B200_RIVER"); os.environ.pop("TAUDEM_B200_RIVER_DINF")
     checks+= [('tiles ad8',test_emu._tiles(lib,False,int(rng.integers(0,2)),p,None,True,seed+4)[0],ad8),
               ('tiles sca',test_emu._tiles(lib,True,int(rng.integers(0,2)),ang,None,True,seed+5)[0],sca)]
     # flats over strips

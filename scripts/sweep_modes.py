@@ -4,7 +4,8 @@ bit-identity of ad8 / sca against the first mode listed and CUDA-event timings o
   python scripts/sweep_modes.py [n=4096] [modes=tiles,levels,levels:48,levels+river:64,hybrid,walk] [reps=3]
 
 A mode is NAME[:passes][+river:hops]: `levels:48` = 48 level passes (TAUDEM_B200_LEVELS), `+river:64` = D8 chains
-longer than 64 cells go to the look-ahead river kernel (TAUDEM_B200_RIVER).
+longer than 64 cells go to the look-ahead river kernel (TAUDEM_B200_RIVER; with RIVER_DINF=1 in the environment also
+TAUDEM_B200_RIVER_DINF for areadinf, where the look-ahead rarely pays: braided strands).
 
 Every mode runs under the caller's own `timeout`; a mode that differs prints DIFFERENT and the script
 exits 1 at the end."""
@@ -42,7 +43,7 @@ def main():
         base, _, river = mode.partition("+river:")
         name, _, passes = base.partition(":")
         os.environ["TAUDEM_B200_SWEEP"] = name
-        for key, val in (("TAUDEM_B200_LEVELS", passes), ("TAUDEM_B200_RIVER", river)):
+        for key, val in (("TAUDEM_B200_LEVELS", passes), ("TAUDEM_B200_RIVER", river), ("TAUDEM_B200_RIVER_DINF", river if os.environ.get("RIVER_DINF") else "")):
             if val: os.environ[key] = val
             else: os.environ.pop(key, None)
         for tool in ("aread8", "areadinf"):
@@ -64,7 +65,7 @@ def main():
             phases = "" if not any(ph) else "  [levels %.1f ready %.1f walk %.1f river %.1f ms]" % tuple(ph)
             print(f"{mode:18s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}{phases}", flush=True)
             del out
-    for key in ("TAUDEM_B200_SWEEP", "TAUDEM_B200_LEVELS", "TAUDEM_B200_RIVER"): os.environ.pop(key, None)
+    for key in ("TAUDEM_B200_SWEEP", "TAUDEM_B200_LEVELS", "TAUDEM_B200_RIVER", "TAUDEM_B200_RIVER_DINF"): os.environ.pop(key, None)
     sys.exit(1 if bad else 0)
 
 

@@ -60,6 +60,7 @@ struct WalkArgs {
   unsigned long long spill_cap;
   int river_hops;              // a lane that has followed one chain for this many cells parks it for k_river (0 = never)
   unsigned long long* pass_cells;   // k_level diagnostics (TAUDEM_B200_TIMING=2): cells evaluated by this pass, or NULL
+  int diag;                         // k_river diagnostics: ctr[4] += batches, ctr[5] += cells resolved in batches
 };
 
 __device__ __forceinline__ unsigned dec_count(unsigned* words, long long cell) {
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
         kp = d > 4 ? d - 4 : d + 4;                      // the direction from the next cell back to this one
         ci = cin; r = rn; c = cn; nd = ndn;
       }
+      if (a.diag && lane == 0) { atomicAdd(a.ctr + 4, 1ull); atomicAdd(a.ctr + 5, (unsigned long long)len); }
       // ---- 2. the contributors that are not on the path (all final): areas, and for D-infinity every contributor's share
       const unsigned m = lane < len ? (mynd & 0xffu) : 0u;
       // every lane acquires on its own cell's count word — the location its side contributors released their areas on
@@ -532,7 +534,7 @@ void walk_args(td_ctx* ctx, WalkArgs& a, float* area, const float* w, const floa
   a.node = ctx->node.as<unsigned short>(); a.cntw = ctx->cnt.as<unsigned>();
   a.area = area; a.w = w; a.ang = ang; a.s = s; a.usew = usew; a.contcheck = contcheck; a.w_nodata = w_nodata;
   a.theta = theta; a.dxc = dxc; a.halo = halo;
-  a.list = nullptr; a.nlist = 0; a.spill = nullptr; a.spill_cap = 0; a.river_hops = 0; a.pass_cells = nullptr;
+  a.list = nullptr; a.nlist = 0; a.spill = nullptr; a.spill_cap = 0; a.river_hops = 0; a.pass_cells = nullptr; a.diag = 0;
   a.ctr = ctx->d_ctr + 16;
 }
 }  // namespace
@@ -595,9 +597,14 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   TD_LAUNCHED();
   tm.lap(&ctx->phase_ms[1]);
   const unsigned long long cap = (unsigned long long)s.nx * s.ny / 16 + 65536;
-  // TAUDEM_B200_RIVER = number of cells after which a lane parks its chain for k_river (0 / unset = off)
-  const char* re = getenv("TAUDEM_B200_RIVER");
+  // TAUDEM_B200_RIVER (aread8) / TAUDEM_B200_RIVER_DINF (areadinf) = number of cells after which a lane parks its chain for
+  // k_river (0 / unset = off).  Separate switches: on the 1024^2 test field the look-ahead resolves 27 cells per batch for D8
+  // and 2.2 for D-infinity (braided strands feed each other, so the next cell is rarely resolvable ahead of time).
+  const char* re = getenv(dinf ? "TAUDEM_B200_RIVER_DINF" : "TAUDEM_B200_RIVER");
   const int river = re ? std::max(0, atoi(re)) : 0;
+  const char* te = getenv("TAUDEM_B200_TIMING");
+  a.diag = (te && atoi(te) >= 2) ? 1 : 0;
+  unsigned long long rbatches = 0, rcells = 0;
   const bool lists = dinf || river;
   if (lists) { TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap)); TD_CUDA(ctx->listC.ensure(sizeof(long long) * cap)); }
   const long long* cur = ctx->listA.as<long long>();
@@ -605,7 +612,7 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   long long* other = lists ? ctx->listC.as<long long>() : nullptr;
   bool first = true;
   for (;;) {
-    TD_CUDA(cudaMemsetAsync(a.ctr, 0, 3 * sizeof(unsigned long long), st));
+    TD_CUDA(cudaMemsetAsync(a.ctr, 0, 6 * sizeof(unsigned long long), st));
     a.list = cur; a.nlist = n; a.spill = spill; a.spill_cap = lists ? cap : 0; a.river_hops = river;
     if (first || !river) {
       // chain walking, one chain per lane (the spill list receives overflowing forks and, with `river`, parked chains)
@@ -623,13 +630,15 @@ int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
     tm.lap(&ctx->phase_ms[(first || !river) ? 2 : 3]);
     first = false;
     if (!lists) break;                   // D8 chains never fork: nothing can spill
-    TD_CUDA(cudaMemcpyAsync(hc, a.ctr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    TD_CUDA(cudaMemcpyAsync(hc, a.ctr, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));
     if (hc[2]) { set_error("contributing area: ready-cell spill list exhausted"); return TD_ERR_ALLOC; }
+    rbatches += hc[4]; rcells += hc[5];
     n = hc[1];
     if (n == 0) break;
     cur = spill; std::swap(spill, other);
   }
+  if (a.diag && rbatches) fprintf(stderr, "[k_river %s] %llu cells in %llu look-ahead batches (%.2f per batch)\n", dinf ? "dinf" : "d8", rcells, rbatches, (double)rcells / (double)rbatches);
   return TD_OK;
 }
 

@@ -268,7 +268,7 @@ def test_emulated_dinf_rivers_with_lookahead(emu, fields, hops, monkeypatch):
     """The same for D-infinity: the look-ahead runs through stretches of single-receiver cells; a two-receiver cell ends
     a batch and its second ready receiver goes to the next launch."""
     port, _, ang, w = fields
-    monkeypatch.setenv("TAUDEM_B200_RIVER", str(hops))
+    monkeypatch.setenv("TAUDEM_B200_RIVER_DINF", str(hops))
     assert_bits(_run(emu, True, 0, 0, ang, None, True, 51), port.areadinf(ang), f"sca rivers hops={hops}")
     assert_bits(_run(emu, True, 1, 2, ang, w, False, 52), port.areadinf(ang, weights=w, contcheck=False), f"sca -wg -nc rivers hops={hops}")
     assert_bits(_run(emu, True, 1, 2, ang, None, True, 53, 3), port.areadinf(ang), f"sca rivers hops={hops}, 3 strips")
@@ -423,7 +423,7 @@ def test_emulated_sweeps_on_a_larger_grid(emu, monkeypatch):
     assert ad8.max() > 1.0e4
     assert_bits(_tiles(emu, False, 0, p, None, True, 201)[0], ad8, "ad8 tiles")
     assert_bits(_tiles(emu, True, 0, ang, None, True, 202)[0], sca, "sca tiles")
-    monkeypatch.setenv("TAUDEM_B200_RIVER", "16")
+    monkeypatch.setenv("TAUDEM_B200_RIVER", "16"); monkeypatch.setenv("TAUDEM_B200_RIVER_DINF", "16")
     assert_bits(_run(emu, False, 1, 6, p, None, True, 203), ad8, "ad8 levels + rivers")
     assert_bits(_run(emu, True, 1, 6, ang, None, True, 204), sca, "sca levels + rivers")
     assert_bits(_run(emu, False, 1, 6, p, None, True, 205, 4), ad8, "ad8 levels + rivers, 4 strips")
