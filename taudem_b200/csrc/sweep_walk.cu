@@ -142,6 +142,19 @@ __device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r,
       const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
       nn[k - 1] = ((m >> (k - 1)) & 1u) ? a.node[ni] : (unsigned short)0;
     }
+    // the receivers (from the node word) and their node words, requested together with the contributors' data
+    const int k1 = (int)((nd >> 8) & 0xfu);
+    int rk[2]; long long rci[2]; unsigned rnd2[2]; int rrn[2], rcn[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = j == 0 ? k1 : ((nd & 0x2000u) ? k1 % 8 + 1 : 0);
+      rk[j] = 0; rci[j] = -1; rnd2[j] = 0; rrn[j] = rcn[j] = 0;
+      if (k == 0) continue;
+      const int rn = r + drow(k), cn = c + dcol(k);
+      if (!s.on_grid(rn, cn)) continue;
+      rk[j] = k; rrn[j] = rn; rcn[j] = cn; rci[j] = s.idx(rn, cn);
+      if (rn != 0 && rn != s.ny + 1) rnd2[j] = a.node[rci[j]];
+    }
     val = 0.f;
 #pragma unroll
     for (int k = 1; k <= 8; ++k)
@@ -162,17 +175,14 @@ __device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r,
     else val = (float)((double)val + a.dxc[r - 1]);
     if (con && a.contcheck) val = -1.0f;
     a.area[ci] = val;
-    // src/areadinf.cpp:221-239: every neighbour that receives a share (the receivers are in the node word)
-    const int k1 = (int)((nd >> 8) & 0xfu);
+    // src/areadinf.cpp:221-239: every neighbour that receives a share
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int k = j == 0 ? k1 : ((nd & 0x2000u) ? k1 % 8 + 1 : 0);
-      if (k == 0) continue;
-      const int rn = r + drow(k), cn = c + dcol(k);
-      if (!s.on_grid(rn, cn)) continue;
-      const long long cin = s.idx(rn, cn);
+      if (rk[j] == 0) continue;
+      const int rn = rrn[j], cn = rcn[j];
+      const long long cin = rci[j];
       if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
-      const unsigned ndn = a.node[cin];
+      const unsigned ndn = rnd2[j];
       if (!(ndn & NODE_VALID)) continue;
       if (dec_count(a.cntw, cin) == 1u) {
         if (nready == 0) { ready[0] = cin; ready_nd[0] = ndn; ready_r[0] = rn; ready_c[0] = cn; }
