@@ -38,6 +38,7 @@ core)
   ;;
 perf)
   step modes_16384 900 python scripts/sweep_modes.py 16384 tiles,levels:24,levels:48,levels:24+river:64,levels:48+river:32,hybrid 2
+  RIVER_DINF=1 step modes_16384_river_dinf 600 python scripts/sweep_modes.py 16384 levels:24,levels:24+river:64 2
   TAUDEM_B200_TIMING=2 step modes_16384_phases 600 python scripts/sweep_modes.py 16384 levels:64,levels:24+river:64 1
   step perf_16384 600 python scripts/gpu_perf.py 16384
   step bench_16384_levels 900 python bench.py --size 16384 --steps 3 --warmup 3 --no-cpu --sweep levels:24+river:64
