@@ -37,7 +37,7 @@ core)
   step modes_4096 600 python scripts/sweep_modes.py 4096 tiles,levels:8,levels:24,levels:64,levels:24+river:64,hybrid,walk,walk+river:64 2
   ;;
 perf)
-  step modes_16384 900 python scripts/sweep_modes.py 16384 tiles,levels:24,levels:48,levels:24+river:64,levels:48+river:32,hybrid 2
+  step modes_16384 900 python scripts/sweep_modes.py 16384 tiles,levels:24,levels:48,levels:auto,levels:24+river:64,levels:auto+river:64,hybrid 2
   RIVER_DINF=1 step modes_16384_river_dinf 600 python scripts/sweep_modes.py 16384 levels:24,levels:24+river:64 2
   TAUDEM_B200_TIMING=2 step modes_16384_phases 600 python scripts/sweep_modes.py 16384 levels:64,levels:24+river:64 1
   step perf_16384 600 python scripts/gpu_perf.py 16384

@@ -3,7 +3,7 @@ bit-identity of ad8 / sca against the first mode listed and CUDA-event timings o
 
   python scripts/sweep_modes.py [n=4096] [modes=tiles,levels,levels:48,levels+river:64,hybrid,walk] [reps=3]
 
-A mode is NAME[:passes][+river:hops]: `levels:48` = 48 level passes (TAUDEM_B200_LEVELS), `+river:64` = D8 chains
+A mode is NAME[:passes][+river:hops]: `levels:48` = 48 level passes (TAUDEM_B200_LEVELS; `levels:auto` = until a pass stops paying), `+river:64` = D8 chains
 longer than 64 cells go to the look-ahead river kernel (TAUDEM_B200_RIVER; with RIVER_DINF=1 in the environment also
 TAUDEM_B200_RIVER_DINF for areadinf, where the look-ahead rarely pays: braided strands).
 

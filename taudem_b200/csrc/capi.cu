@@ -56,7 +56,7 @@ int need_device() {
 //   hybrid : one pass of the tile kernel over every tile, then warp-level chain walking from the cells that
 //            are ready but not evaluated (sweep_walk.cu)
 //   walk   : warp-level chain walking from the sources alone
-//   levels : TAUDEM_B200_LEVELS (default 24) streaming level passes, then warp-level chain walking
+//   levels : TAUDEM_B200_LEVELS (a number, default 24, or "auto") streaming level passes, then warp-level chain walking
 enum SweepMode { SWEEP_TILES, SWEEP_CHAIN, SWEEP_HYBRID, SWEEP_WALK, SWEEP_LEVELS };
 SweepMode sweep_mode() {
   const char* e = getenv("TAUDEM_B200_SWEEP");
@@ -81,8 +81,8 @@ int sweep_alt(td_ctx* ctx, SweepMode mode, bool dinf, float* area, const float* 
     if (rc) return rc;
   }
   if (first && mode == SWEEP_LEVELS) {
-    const char* e = getenv("TAUDEM_B200_LEVELS");
-    const int passes = e ? std::max(0, std::min(atoi(e), 4096)) : 24;
+    const char* e = getenv("TAUDEM_B200_LEVELS");                      // a number of passes, or "auto" (stop when a pass no longer pays)
+    const int passes = !e ? 24 : (strcmp(e, "auto") == 0 ? -1 : std::max(0, std::min(atoi(e), 4096)));
     if (int rc = td::sweep_levels(ctx, dinf, passes, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st)) return rc;
   }
   return td::sweep_walk(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st);

@@ -200,9 +200,10 @@ __global__ void __launch_bounds__(256) k_level(const WalkArgs a) {
   const Strip& s = a.s;
   // rows on grid.x (no 65535 limit), 16-cell groups of the row on grid.y x threads (pitch % 32 == 0): no division
   const int r = 1 + (int)blockIdx.x, c0 = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 16;
-  if (c0 >= s.pitch) return;
-  const long long base = s.idx(r, c0);
-  const uint4 q = __ldcg(reinterpret_cast<const uint4*>(a.cntw + (base >> 2)));
+  const bool inrow = c0 < s.pitch;
+  const long long base = s.idx(r, inrow ? c0 : 0);
+  uint4 q = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  if (inrow) q = __ldcg(reinterpret_cast<const uint4*>(a.cntw + (base >> 2)));
   const unsigned w4[4] = {q.x, q.y, q.z, q.w};
   unsigned todo = 0;                                                     // bit b: cell base + b is ready
 #pragma unroll
@@ -213,7 +214,15 @@ __global__ void __launch_bounds__(256) k_level(const WalkArgs a) {
     for (int i = 0; i < 4; ++i)
       if (((word >> (8 * i)) & 0xffu) == 0u && c0 + 4 * j + i < s.nx) todo |= 1u << (4 * j + i);
   }
-  if (a.pass_cells && todo) atomicAdd(a.pass_cells, (unsigned long long)__popc(todo));
+  if (a.pass_cells && (blockIdx.x & 15u) == 0u) {
+    // every 16th row reports how many cells it evaluates (one atomic per CTA): enough to steer the number of passes
+    __shared__ unsigned bsum;
+    if (threadIdx.x == 0) bsum = 0;
+    __syncthreads();
+    if (todo) atomicAdd(&bsum, (unsigned)__popc(todo));
+    __syncthreads();
+    if (threadIdx.x == 0 && bsum) atomicAdd(a.pass_cells, (unsigned long long)bsum);
+  }
   unsigned d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll 1
   while (todo) {
@@ -564,24 +573,36 @@ int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w
   const dim3 blocks((unsigned)s.ny, (unsigned)(((s.pitch >> 4) + 255) / 256));
   for (double& v : ctx->phase_ms) v = 0.;
   PhaseTimer tm(st);
+  // passes < 0: as many passes as pay — a pass costs a scan of the whole count array, so stop when the (sampled: every
+  // 16th row) number of cells it evaluated falls below 0.4 % of the strip; the walkers finish such remainders faster
+  const bool autostop = passes < 0;
+  const int maxp = autostop ? 96 : passes;
   const char* te = getenv("TAUDEM_B200_TIMING");
-  const bool diag = te && atoi(te) >= 2 && passes > 0;          // per-pass cell counts on stderr (for choosing TAUDEM_B200_LEVELS)
-  if (diag) { TD_CUDA(ctx->rows.ensure(sizeof(unsigned long long) * (size_t)passes)); TD_CUDA(cudaMemsetAsync(ctx->rows.p, 0, sizeof(unsigned long long) * (size_t)passes, st)); }
-  for (int p = 0; p < passes; ++p) {
-    a.pass_cells = diag ? ctx->rows.as<unsigned long long>() + p : nullptr;
+  const bool diag = te && atoi(te) >= 2 && maxp > 0;             // per-pass cell counts on stderr
+  if (diag || autostop) { TD_CUDA(ctx->rows.ensure(sizeof(unsigned long long) * (size_t)maxp)); TD_CUDA(cudaMemsetAsync(ctx->rows.p, 0, sizeof(unsigned long long) * (size_t)maxp, st)); }
+  const double sampled = (double)((s.ny + 15) / 16) * s.nx;
+  int done = 0;
+  for (int p = 0; p < maxp; ++p) {
+    a.pass_cells = (diag || autostop) ? ctx->rows.as<unsigned long long>() + p : nullptr;
     if (dinf) k_level<true><<<blocks, 256, 0, st>>>(a); else k_level<false><<<blocks, 256, 0, st>>>(a);
     TD_LAUNCHED();
+    ++done;
+    if (autostop) {
+      unsigned long long* h = ctx->h_ctr + 20;
+      TD_CUDA(cudaMemcpyAsync(h, ctx->rows.as<unsigned long long>() + p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      TD_CUDA(cudaStreamSynchronize(st));
+      if ((double)*h < 0.004 * sampled) break;
+    }
   }
   TD_CUDA(cudaGetLastError());
   tm.lap(&ctx->phase_ms[0]);
   if (diag) {
-    std::vector<unsigned long long> pc((size_t)passes);
-    TD_CUDA(cudaMemcpyAsync(pc.data(), ctx->rows.p, sizeof(unsigned long long) * (size_t)passes, cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned long long> pc((size_t)done);
+    TD_CUDA(cudaMemcpyAsync(pc.data(), ctx->rows.p, sizeof(unsigned long long) * (size_t)done, cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));
-    unsigned long long sum = 0;
-    fprintf(stderr, "[k_level %s] cells evaluated per pass:", dinf ? "dinf" : "d8");
-    for (int p = 0; p < passes; ++p) { sum += pc[p]; fprintf(stderr, " %llu", pc[p]); }
-    fprintf(stderr, "  total %llu of %lld\n", sum, (long long)s.nx * s.ny);
+    fprintf(stderr, "[k_level %s] %d passes; cells evaluated per pass in every 16th row (of %.0f):", dinf ? "dinf" : "d8", done, sampled);
+    for (int p = 0; p < done; ++p) fprintf(stderr, " %llu", pc[p]);
+    fprintf(stderr, "\n");
   }
   return TD_OK;
 }

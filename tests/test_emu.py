@@ -100,7 +100,7 @@ def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, roun
     return out
 
 
-@pytest.mark.parametrize("mode,passes", [(0, 0), (1, 1), (1, 4), (1, 40)])
+@pytest.mark.parametrize("mode,passes", [(0, 0), (1, 1), (1, 4), (1, 40), (1, -1)])
 def test_emulated_d8_sweeps_match_the_oracle(emu, fields, mode, passes):
     port, p, _, w = fields
     for seed in (1, 2):
@@ -108,7 +108,7 @@ def test_emulated_d8_sweeps_match_the_oracle(emu, fields, mode, passes):
     assert_bits(_run(emu, False, mode, passes, p, w, False, 3), port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc")
 
 
-@pytest.mark.parametrize("mode,passes", [(0, 0), (1, 1), (1, 4), (1, 40)])
+@pytest.mark.parametrize("mode,passes", [(0, 0), (1, 1), (1, 4), (1, 40), (1, -1)])
 def test_emulated_dinf_sweeps_match_the_oracle(emu, fields, mode, passes):
     port, _, ang, w = fields
     for seed in (1, 2):
