@@ -74,6 +74,26 @@ __device__ __forceinline__ unsigned dec_count(unsigned* words, long long cell) {
 #endif
   return (old >> sh) & 0xffu;
 }
+// the same decrement without ordering, and the fence that supplies it: "fence; relaxed atomics; fence" releases the area
+// once for both receivers of a D-infinity cell and lets the two atomics travel together
+__device__ __forceinline__ unsigned dec_count_relaxed(unsigned* words, long long cell) {
+  unsigned* a = words + (cell >> 2);
+  const unsigned sh = (unsigned)(cell & 3) * 8u;
+  unsigned old;
+#ifdef TD_EMU
+  old = atomicAdd(a, 0u - (1u << sh));
+#else
+  asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
+#endif
+  return (old >> sh) & 0xffu;
+}
+__device__ __forceinline__ void fence_acq_rel() {
+#ifdef TD_EMU
+  __threadfence();
+#else
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
 #ifdef TD_EMU
@@ -175,21 +195,27 @@ __device__ __forceinline__ int eval_cell(const WalkArgs& a, long long ci, int r,
     else val = (float)((double)val + a.dxc[r - 1]);
     if (con && a.contcheck) val = -1.0f;
     a.area[ci] = val;
-    // src/areadinf.cpp:221-239: every neighbour that receives a share
+    // src/areadinf.cpp:221-239: every neighbour that receives a share.  One release fence, then both decrements (issued
+    // back to back, their round trips overlap), one acquire fence if a receiver became ready.
+    unsigned oldc[2] = {0u, 0u};
+    const bool any = rk[0] != 0 || rk[1] != 0;
+    if (any) fence_acq_rel();
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       if (rk[j] == 0) continue;
       const int rn = rrn[j], cn = rcn[j];
-      const long long cin = rci[j];
-      if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
-      const unsigned ndn = rnd2[j];
-      if (!(ndn & NODE_VALID)) continue;
-      if (dec_count(a.cntw, cin) == 1u) {
-        if (nready == 0) { ready[0] = cin; ready_nd[0] = ndn; ready_r[0] = rn; ready_c[0] = cn; }
-        else { ready[1] = cin; ready_nd[1] = ndn; ready_r[1] = rn; ready_c[1] = cn; }
+      if (rn == 0 || rn == s.ny + 1) { atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
+      if (!(rnd2[j] & NODE_VALID)) continue;
+      oldc[j] = dec_count_relaxed(a.cntw, rci[j]);
+    }
+    if (oldc[0] == 1u || oldc[1] == 1u) fence_acq_rel();
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (oldc[j] == 1u) {
+        if (nready == 0) { ready[0] = rci[j]; ready_nd[0] = rnd2[j]; ready_r[0] = rrn[j]; ready_c[0] = rcn[j]; }
+        else { ready[1] = rci[j]; ready_nd[1] = rnd2[j]; ready_r[1] = rrn[j]; ready_c[1] = rcn[j]; }
         ++nready;
       }
-    }
   }
   return nready;
 }
