@@ -22,7 +22,7 @@ for seed in range(first, first + count):
     ad8=port.aread8(p); sca=port.areadinf(ang); ad8w=port.aread8(p,weights=w,contcheck=False); scaw=port.areadinf(ang,weights=w,contcheck=False)
     strips=int(rng.integers(1,4))
     os.environ["TAUDEM_B200_RIVER"]=str(int(rng.choice([0,1,2,5,16]))); os.environ["TAUDEM_B200_RIVER_DINF"]=str(int(rng.choice([0,1,3,16])))
-    passes=int(rng.integers(0,6))
+    passes=int(rng.choice([-1,0,1,2,3,5,9]))
     checks=[('ad8',test_emu._run(lib,False,1,passes,p,None,True,seed,strips),ad8),
             ('sca',test_emu._run(lib,True,1,passes,ang,None,True,seed+1,strips),sca),
             ('ad8w',test_emu._run(lib,False,0,0,p,w,False,seed+2,strips),ad8w),
