@@ -428,3 +428,12 @@ def test_emulated_sweeps_on_a_larger_grid(emu, monkeypatch):
     assert_bits(_run(emu, True, 1, 6, ang, None, True, 204), sca, "sca levels + rivers")
     assert_bits(_run(emu, False, 1, 6, p, None, True, 205, 4), ad8, "ad8 levels + rivers, 4 strips")
     assert_bits(_run(emu, True, 1, 6, ang, None, True, 206, 4), sca, "sca levels + rivers, 4 strips")
+
+
+def test_emulated_random_configurations(emu):
+    """A short deterministic slice of scripts/emu_stress.py: random grid sizes, flats, holes, strip counts, level passes (incl.
+    auto), river thresholds, tile / hybrid sweeps and strip flats against the oracle."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "emu_stress.py"), "777", "14", "120"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and " bad 0 " in r.stdout, r.stdout[-2000:]
