@@ -504,22 +504,30 @@ __global__ void __launch_bounds__(256) k_river(const WalkArgs a) {
           else if (nxt >= 0 && dec_count(a.cntw, nxt) == 1u) newhead = nxt;
         } else {                                             // src/areadinf.cpp:221-239
           const int k1 = (int)((mynd >> 8) & 0xfu);
+          long long cin2[2] = {-1, -1};
+          unsigned old2[2] = {0u, 0u};
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int k = j == 0 ? k1 : k1 % 8 + 1;
             const int rn = myr + drow(k), cn = myc + dcol(k);
             if (!s.on_grid(rn, cn)) continue;
-            const long long cin = s.idx(rn, cn);
             if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(a.halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
-            if (!(a.node[cin] & NODE_VALID)) continue;
-            if (dec_count(a.cntw, cin) == 1u) {
-              if (newhead < 0) newhead = cin;
+            const long long cin = s.idx(rn, cn);
+            if (a.node[cin] & NODE_VALID) cin2[j] = cin;
+          }
+          fence_acq_rel();                                   // release the area once, both decrements travel together
+#pragma unroll
+          for (int j = 0; j < 2; ++j) if (cin2[j] >= 0) old2[j] = dec_count_relaxed(a.cntw, cin2[j]);
+          if (old2[0] == 1u || old2[1] == 1u) fence_acq_rel();
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (old2[j] == 1u) {
+              if (newhead < 0) newhead = cin2[j];
               else {
                 const unsigned long long g = atomicAdd(a.ctr + 1, 1ull);
-                if (g < a.spill_cap) a.spill[g] = cin; else a.ctr[2] = 1ull;
+                if (g < a.spill_cap) a.spill[g] = cin2[j]; else a.ctr[2] = 1ull;
               }
             }
-          }
         }
       }
       newhead = __shfl_sync(FULL, newhead, len - 1);
