@@ -1,0 +1,9 @@
+#!/bin/bash
+# gpurun with retries on "no box free" (exit 3): scripts/gpurun_retry.sh <timeout> '<command>' [--gpus N]
+T=$1; CMD=$2; shift 2
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun "$@" --timeout "$T" -- "$CMD"; rc=$?
+  [ $rc -ne 3 ] && exit $rc
+  sleep 90
+done
+exit 3

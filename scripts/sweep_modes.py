@@ -61,9 +61,14 @@ def main():
                 same = torch.equal(own.view(torch.int32), ref[tool].view(torch.int32))
                 verdict = "identical" if same else f"DIFFERENT ({int((own.view(torch.int32) != ref[tool].view(torch.int32)).sum())} cells)"
                 bad += 0 if same else 1
+            st = ""
+            if os.environ.get("TAUDEM_B200_TIMING") and name in ("warp", "tiles"):
+                c = [T.l.td_ctx_counter(T.ctx, 24 + i) for i in range(8)]
+                v = max(c[3], 1)
+                st = f"  [visits {c[3]} cycles/visit: wait {c[4]//v} load {c[5]//v} walk {c[6]//v} wb {c[7]//v}]"
             ph = [T.l.td_ctx_phase_ms(T.ctx, i) for i in range(4)]
             phases = "" if not any(ph) else "  [levels %.1f ready %.1f walk %.1f river %.1f ms]" % tuple(ph)
-            print(f"{mode:18s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}{phases}", flush=True)
+            print(f"{mode:18s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}{phases}{st}", flush=True)
             del out
     for key in ("TAUDEM_B200_SWEEP", "TAUDEM_B200_LEVELS", "TAUDEM_B200_RIVER", "TAUDEM_B200_RIVER_DINF"): os.environ.pop(key, None)
     sys.exit(1 if bad else 0)

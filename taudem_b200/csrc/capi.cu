@@ -57,7 +57,7 @@ int need_device() {
 //            are ready but not evaluated (sweep_walk.cu)
 //   walk   : warp-level chain walking from the sources alone
 //   levels : TAUDEM_B200_LEVELS (a number, default 24, or "auto") streaming level passes, then warp-level chain walking
-enum SweepMode { SWEEP_TILES, SWEEP_CHAIN, SWEEP_HYBRID, SWEEP_WALK, SWEEP_LEVELS };
+enum SweepMode { SWEEP_TILES, SWEEP_CHAIN, SWEEP_HYBRID, SWEEP_WALK, SWEEP_LEVELS, SWEEP_WARP };
 SweepMode sweep_mode() {
   const char* e = getenv("TAUDEM_B200_SWEEP");
   if (!e) return SWEEP_TILES;
@@ -65,6 +65,7 @@ SweepMode sweep_mode() {
   if (strcmp(e, "hybrid") == 0) return SWEEP_HYBRID;
   if (strcmp(e, "walk") == 0) return SWEEP_WALK;
   if (strcmp(e, "levels") == 0) return SWEEP_LEVELS;
+  if (strcmp(e, "warp") == 0) return SWEEP_WARP;
   return SWEEP_TILES;
 }
 bool chain_sweep() { return sweep_mode() == SWEEP_CHAIN; }
@@ -258,6 +259,10 @@ int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, flo
   const SweepMode mode = sweep_mode();
   if (alt_mode(mode))
     return sweep_alt(ctx, mode, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, ctx->halo.as<int>(), true, (cudaStream_t)stream);
+  if (mode == SWEEP_WARP) {
+    if (int rc = td::wsweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
+    return td::wsweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(), (cudaStream_t)stream);
+  }
   if (int rc = td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
   return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(),
                        (cudaStream_t)stream);
@@ -281,6 +286,10 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   const Strip ss(s);
   const SweepMode mode = sweep_mode();
   if (alt_mode(mode)) return sweep_alt(ctx, mode, true, sca, w, ang, ss, 0.f, usew, contcheck, dxc, ctx->halo.as<int>(), true, st);
+  if (mode == SWEEP_WARP) {
+    if (int rc = td::wsweep_begin(ctx, ss, st)) return rc;
+    return td::wsweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
+  }
   if (!chain_sweep()) {
     if (int rc = td::sweep_begin(ctx, ss, st)) return rc;
     return td::sweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
@@ -333,11 +342,13 @@ int td_sweep_restrict_round_dev(td_ctx* ctx, td_strip s, const int* cols, const 
 int td_sweep_begin_dev(td_ctx* ctx, td_strip s, void* stream) {
   if (int rc = check_strip(s)) return rc;
   if (alt_mode(sweep_mode())) { ctx->sweep_first = 1; return TD_OK; }
+  if (sweep_mode() == SWEEP_WARP) return td::wsweep_begin(ctx, Strip(s), (cudaStream_t)stream);
   return td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream);
 }
 int td_sweep_apply_halo_dev(td_ctx* ctx, td_strip s, const int* dec_top, const int* dec_bot, void* stream) {
   if (int rc = check_strip(s)) return rc;
   if (alt_mode(sweep_mode())) return td::sweep_apply_plain(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
+  if (sweep_mode() == SWEEP_WARP) return td::wsweep_apply_halo(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
   return td::sweep_apply_halo(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
 }
 int td_aread8_sweep_run_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, float w_nodata, int usew, int contcheck, int* halo_out,
@@ -347,6 +358,8 @@ int td_aread8_sweep_run_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s,
     const bool first = ctx->sweep_first != 0; ctx->sweep_first = 0;
     return sweep_alt(ctx, sweep_mode(), false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, halo_out, first, (cudaStream_t)stream);
   }
+  if (sweep_mode() == SWEEP_WARP)
+    return td::wsweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, halo_out, (cudaStream_t)stream);
   return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, halo_out, (cudaStream_t)stream);
 }
 int td_area_sweep_run_dev(td_ctx* ctx, const float* ang, const float* w, float* sca, td_strip s, int usew, int contcheck, const double* dxc,
@@ -356,6 +369,8 @@ int td_area_sweep_run_dev(td_ctx* ctx, const float* ang, const float* w, float* 
     const bool first = ctx->sweep_first != 0; ctx->sweep_first = 0;
     return sweep_alt(ctx, sweep_mode(), true, sca, w, ang, Strip(s), 0.f, usew, contcheck, dxc, halo_out, first, (cudaStream_t)stream);
   }
+  if (sweep_mode() == SWEEP_WARP)
+    return td::wsweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
   return td::sweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
 }
 

@@ -44,6 +44,7 @@ struct td_ctx {
   int sweep_dinf = 0;                    // which dependency state node/cnt hold (tile height of the sweep)
   int sweep_once = 0;                    // tile sweep: visit every tile once, no re-activation (hybrid mode)
   double phase_ms[4] = {0, 0, 0, 0};     // TAUDEM_B200_TIMING=1: level passes / ready-list collection / chain walking / rivers of the last sweep
+  int wgrid_d8 = 0, wgrid_dinf = 0;     // persistent grid of the warp-per-tile sweep kernels on this context's device
   int sweep_first = 1;                   // level / hybrid modes: the bulk phase has not run yet for the current dependency state
   unsigned long long* d_ctr = nullptr;   // 32 device counters
   unsigned long long* h_ctr = nullptr;   // pinned host mirror

@@ -29,6 +29,10 @@ int sweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
 int sweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
 int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
+int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
+int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
+int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
 int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w, const float* ang, const Strip& s, float w_nodata,
                  int usew, int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
 int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, const int* in_top, const int* in_bot,

@@ -1,0 +1,468 @@
+// Contributing-area evaluation sweep: tile dataflow with one WARP per tile visit (D8 and D-infinity).
+//
+// reference: aread8 main loop src/aread8.cpp:216-304, area() main loop src/areadinf.cpp:173-265 — a queue of cells
+// whose dependency count is zero; evaluate (k-ordered float32 gather over the neighbours that drain into the cell),
+// decrement the receivers, push those that reach zero.  The value of a cell does not depend on the schedule
+// (SURVEY.md A.6), so the schedule here is the GPU's:
+//
+//  * the strip is cut into 32 x 32 tiles; tile ids wait in a device-side multi-producer / multi-consumer ticket queue;
+//  * every warp of a grid of persistent CTAs is an independent worker: it pops a tile, stages the tile's dependency
+//    counts (1 KB) and areas with a one-cell ring (4.6 KB) in its own slice of shared memory and runs the wavefront
+//    there — each lane follows one chain (evaluate, shared-memory atomic decrement of the receiver(s), go on when it
+//    was the last arrival), second receivers of D-infinity cells go to a warp-local queue that idle lanes drain;
+//    no CTA-wide barrier exists anywhere, a warp that holds a long chain delays nobody;
+//  * what a visit costs is proportional to what it evaluates: only evaluated areas and changed count words are
+//    written back (one fence), flow that leaves the tile is one global atomic per crossing, and the arrival that
+//    zeroes a count activates the owning tile (per-tile state idle / queued / running / running + dirty, so that a
+//    tile is never processed by two warps at once);
+//  * the kernel ends when no tile is queued or running.
+// Flow that crosses the strip boundary (one strip per GPU) is recorded in `halo` for the exchange rounds of the
+// row-strip driver (src/aread8.cpp:282-297, linearpart::addBorders).
+#include <string.h>
+
+#include <algorithm>
+
+#include "ctx.h"
+#include "dinf_common.cuh"
+#include "kernels.h"
+
+namespace td {
+namespace {
+
+constexpr int TS = 32;                                // tile edge (cells)
+constexpr int TC = TS * TS;                           // cells per tile
+constexpr int RW = TS + 2;                            // ring width / height
+constexpr int EXTCAP = 256;                           // crossings of one visit: <= 124 perimeter cells x 2 receivers
+constexpr int WARPS = 8;                              // workers per CTA
+constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
+constexpr unsigned FULL = 0xffffffffu;
+
+// one worker's shared memory
+struct __align__(16) WarpMem {
+  float area[RW * RW];          // areas of the tile and its ring (-1 = nodata / not final)
+  unsigned cnt[TC / 4];         // dependency counts, four cells per word: 0..8, 0xFE = evaluated, 0xFF = not a node
+  unsigned short wq[TC];        // ready cells (every cell enters at most once)
+  unsigned short ext[EXTCAP];   // receivers outside the tile (ring index)
+  unsigned evmask[TS];          // per tile row: cells evaluated by this visit
+  int qtail, next, dirty, pad;
+};
+
+struct WArgs {
+  const unsigned short* node;
+  unsigned* cntw;
+  float* area;
+  const float* w;
+  const float* ang;
+  Strip s;
+  int usew, contcheck;
+  float w_nodata;
+  const double* theta;
+  const double* dxc;
+  int* halo;
+  int ntx, nty;
+  int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
+  int* tq;                 // ring of tile ids + 1
+  unsigned qmask;
+  unsigned long long* ctr; // [0] head, [1] tail, [2] pending (queued + running tiles), [3] visits, [4..7] cycle statistics
+  int stats;
+};
+
+#ifdef TD_EMU
+template <typename T> __device__ __forceinline__ T ldv(const T* p) { emu::yield(); return *((const volatile T*)p); }
+#else
+template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((const volatile T*)p); }
+#endif
+
+// ---- scheduler (the protocol of the first-generation tile kernel, one lane per worker)
+__device__ void sched_push(const WArgs& a, int t) {
+  atomicAdd(a.ctr + 2, 1ull);
+  const unsigned long long slot = atomicAdd(a.ctr + 1, 1ull);
+  int* q = a.tq + (slot & a.qmask);
+  while (atomicCAS(q, 0, t + 1) != 0) {}
+}
+__device__ void sched_activate(const WArgs& a, int t) {
+  for (;;) {
+    const int st = ldv(a.state + t);
+    if (st == 1 || st == 3) return;
+    if (st == 0) { if (atomicCAS(a.state + t, 0, 1) == 0) { sched_push(a, t); return; } }
+    else if (atomicCAS(a.state + t, 2, 3) == 2) return;
+  }
+}
+// Ticket h is served by the h-th push; a worker whose ticket is never served leaves when no tile is queued or running.
+__device__ int sched_pop(const WArgs& a) {
+  const unsigned long long h = atomicAdd(a.ctr, 1ull);
+  int* q = a.tq + (h & a.qmask);
+  unsigned ns = 32;
+  for (;;) {
+    const int v = ldv(q);
+    if (v != 0) {
+      atomicExch(q, 0);
+      atomicExch(a.state + (v - 1), 2);
+      __threadfence();
+      return v - 1;
+    }
+    if ((long long)ldv(a.ctr + 2) <= 0) return -1;
+    __nanosleep(ns);
+    if (ns < 1024) ns <<= 1;
+  }
+}
+__device__ void sched_finish(const WArgs& a, int t) {
+  __threadfence();
+  if (atomicCAS(a.state + t, 2, 0) != 2) { atomicExch(a.state + t, 1); sched_push(a, t); }
+  atomicAdd(a.ctr + 2, ~0ull);   // pending -= 1
+}
+
+__global__ void k_wsched_init(int* state, int* tq, unsigned qcap, int ntiles, unsigned long long* ctr) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < qcap) tq[i] = (int)i < ntiles ? (int)i + 1 : 0;
+  if ((int)i < ntiles) state[i] = 1;
+  if (i == 0) { ctr[0] = 0; ctr[1] = (unsigned long long)ntiles; ctr[2] = (unsigned long long)ntiles; ctr[3] = ctr[4] = ctr[5] = ctr[6] = ctr[7] = 0; }
+}
+
+// prop(angle, kk) through the full interval search (the rare path of the D-infinity gather)
+__device__ __noinline__ double wshare_full(float ang, double t, int kk) {
+  const Outflow o = dinf_outflow(ang, t);
+  return o.k1 == kk ? o.p1 : o.p2;
+}
+
+// bit 7 of every byte of the result is set exactly where that byte of w is zero (no borrow between bytes)
+__device__ __forceinline__ unsigned zero_bytes(unsigned w) { return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; }
+
+template <bool DINF>
+__global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const Strip& s = a.s;
+  const int lane = (int)(threadIdx.x & 31u), wid = (int)(threadIdx.x >> 5);
+  const unsigned lt = (1u << lane) - 1u;
+  WarpMem& M = *reinterpret_cast<WarpMem*>(dsm + (size_t)wid * sizeof(WarpMem));
+
+  for (;;) {
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+    int t = -1;
+    if (lane == 0) { if (a.stats) tk0 = clock64(); t = sched_pop(a); if (a.stats) tk1 = clock64(); }
+    t = __shfl_sync(FULL, t, 0);
+    if (t < 0) return;
+    const int ty = t / a.ntx, tx = t - ty * a.ntx;
+    const int c0 = tx * TS, r0 = 1 + ty * TS;
+
+    // ---- 1. dependency counts: lane = tile row (32 bytes each), before anything else
+    unsigned g0[8];
+    {
+      const int r = r0 + lane;
+      uint4 qa = make_uint4(FULL, FULL, FULL, FULL), qb = qa;
+      if (r <= s.ny) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.cntw + (s.idx(r, c0) >> 2));
+        qa = __ldcg(src); qb = __ldcg(src + 1);
+      }
+      g0[0] = qa.x; g0[1] = qa.y; g0[2] = qa.z; g0[3] = qa.w; g0[4] = qb.x; g0[5] = qb.y; g0[6] = qb.z; g0[7] = qb.w;
+      uint4* dst = reinterpret_cast<uint4*>(M.cnt + lane * 8);
+      dst[0] = qa; dst[1] = qb;
+      M.evmask[lane] = 0u;
+    }
+    if (lane == 0) { M.qtail = 0; M.next = 0; M.dirty = 0; }
+    __threadfence();          // the counts first, then the areas they announce (loaded by other lanes: barrier in between)
+    __syncwarp();
+    // ---- 2. areas of the tile and its ring: lane = column (lanes 0 / 1 also take the two extra ring columns)
+#pragma unroll 2
+    for (int rr = 0; rr < RW; ++rr) {
+      const int r = r0 - 1 + rr;
+      const bool rowin = r >= 0 && r <= s.ny + 1;
+      {
+        const int c = c0 - 1 + lane;
+        float v = -1.0f;
+        if (rowin && c >= 0 && c < s.nx) v = __ldcg(a.area + s.idx(r, c));
+        M.area[rr * RW + lane] = v;
+      }
+      if (lane < 2) {
+        const int c = c0 + 31 + lane;
+        float v = -1.0f;
+        if (rowin && c < s.nx) v = __ldcg(a.area + s.idx(r, c));
+        M.area[rr * RW + 32 + lane] = v;
+      }
+    }
+    __syncwarp();
+    // ---- 3. cells that are ready (count 0): lane = tile row
+    {
+      int n = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) n += __popc(zero_bytes(g0[j]));
+      int incl = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+      int pos = incl - n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        unsigned z = zero_bytes(g0[j]);
+        while (z) {
+          const int b = (__ffs(z) - 1) >> 3;
+          z &= z - 1;
+          M.wq[pos++] = (unsigned short)(lane * TS + 4 * j + b);
+        }
+      }
+      const int total = __shfl_sync(FULL, incl, 31);
+      if (lane == 0) M.qtail = total;
+    }
+    __syncwarp();
+    if (a.stats && lane == 0) tk2 = clock64();
+
+    // ---- 4. the wavefront inside the tile: one chain per lane, refilled from the warp's queue
+    int qhead = 0;                 // warp-uniform
+    int cur = -1;
+    for (;;) {
+      const unsigned idle = __ballot_sync(FULL, cur < 0);
+      if (idle) {
+        const int avail = ldv(&M.qtail) - qhead;
+        const int take = min(__popc(idle), avail);
+        const int rank = __popc(idle & lt);
+        if (cur < 0 && rank < take) cur = M.wq[qhead + rank];
+        qhead += take;
+      }
+      if (__ballot_sync(FULL, cur >= 0) == 0u) break;
+      if (cur >= 0) {
+        const int l = cur;
+        const int lr = l >> 5, lx = l & 31;
+        const int ri = (lr + 1) * RW + lx + 1;
+        const int r = r0 + lr, c = c0 + lx;
+        const long long ci = s.idx(r, c);
+        const unsigned nd = a.node[ci];
+        const unsigned msk = nd & 0xffu;
+        bool con = (nd & NODE_CON) != 0;
+        float val;
+        int cont = -1;
+        if (!DINF) {
+          // src/aread8.cpp:228-257
+          if (a.usew) { const float wv = a.w[ci]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
+          else val = 1.0f;
+#pragma unroll
+          for (int k = 1; k <= 8; ++k)
+            if (msk & (1u << (k - 1))) {
+              const float an = M.area[ri + drow(k) * RW + dcol(k)];
+              if (nd_f(an, -1.0f)) con = true; else val = val + an;
+            }
+        } else {
+          // src/areadinf.cpp:187-218.  The share a contributor sends here is prop(its angle, direction to me): for a
+          // contributor with two receivers in one of the sectors 1..7 its node word says which sector (k1, k1 + 1), so
+          // the share is one division — exactly the expressions dinf_outflow evaluates; everything else (single
+          // receiver, the wrap sector, contributors in a halo row, whose node words belong to the neighbour strip)
+          // takes the full interval search.
+          float aa[8]; unsigned short nn[8];
+#pragma unroll
+          for (int k = 1; k <= 8; ++k) {
+            const bool in = (msk >> (k - 1)) & 1u;
+            const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
+            aa[k - 1] = in ? a.ang[ni] : 0.f;
+            nn[k - 1] = in ? a.node[ni] : (unsigned short)0;
+          }
+          val = 0.f;
+#pragma unroll
+          for (int k = 1; k <= 8; ++k)
+            if (msk & (1u << (k - 1))) {
+              const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
+              const int rn = r + drow(k);
+              const double th = a.theta[min(max(rn - 1, 0), s.ny - 1)];
+              const int k1n = (nn[k - 1] >> 8) & 0xf;
+              double p;
+              if ((nn[k - 1] & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
+                const double mid = aref(k1n, th), hi = aref(k1n + 1, th);
+                const float av = aa[k - 1];
+                p = (kk == k1n) ? (hi - av) / (hi - mid) : (av - mid) / (hi - mid);
+              } else p = wshare_full(aa[k - 1], th, kk);
+              const float an = M.area[ri + drow(k) * RW + dcol(k)];
+              if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
+            }
+          if (a.usew) val = val + a.w[ci];
+          else val = (float)((double)val + a.dxc[r - 1]);
+        }
+        if (con && a.contcheck) val = -1.0f;
+        M.area[ri] = val;
+        atomicAdd(&M.cnt[l >> 2], 0xfeu << ((unsigned)(l & 3) * 8u));     // 0 -> 0xFE (evaluated)
+        atomicOr(&M.evmask[lr], 1u << lx);
+        __threadfence_block();     // the area is in shared memory before any count says so
+        // ---- the receivers: src/aread8.cpp:261-272, src/areadinf.cpp:221-239
+#pragma unroll
+        for (int j = 0; j < (DINF ? 2 : 1); ++j) {
+          int k;
+          if (!DINF) k = (int)((nd >> 8) & 0xfu);
+          else { const int k1 = (int)((nd >> 8) & 0xfu); k = j == 0 ? k1 : ((nd & 0x2000u) ? k1 % 8 + 1 : 0); }
+          if (k < 1 || k > 8) continue;
+          const int nlr = lr + drow(k), nlx = lx + dcol(k);
+          if (nlr >= 0 && nlr < TS && nlx >= 0 && nlx < TS && r0 + nlr <= s.ny) {       // a cell of this tile
+            const int l2 = nlr * TS + nlx;
+            const unsigned sh = (unsigned)(l2 & 3) * 8u;
+            const unsigned old = atomicSub(&M.cnt[l2 >> 2], 1u << sh);
+            if (((old >> sh) & 0xffu) == 1u) {
+              if (cont < 0) cont = l2;
+              else M.wq[atomicAdd(&M.qtail, 1)] = (unsigned short)l2;   // a second ready receiver: an idle lane takes it
+            }
+          } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
+            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
+          }
+        }
+        cur = cont;
+      }
+      __syncwarp();              // counts first, then the areas they announce (next iteration)
+    }
+    if (a.stats && lane == 0) tk3 = clock64();
+
+    // ---- 5. write back what this visit evaluated, then publish counts and deliver the crossings
+#pragma unroll 4
+    for (int lr = 0; lr < TS; ++lr)
+      if ((M.evmask[lr] >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RW + lane + 1];
+    __threadfence();
+    __syncwarp();
+    __threadfence();          // release by the lanes that publish: the other lanes' area stores are ordered before their atomics
+    {
+      const int r = r0 + lane;
+      bool dirty = false;
+      if (r <= s.ny) {
+        unsigned* gw = a.cntw + (s.idx(r, c0) >> 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned was = g0[j], now = M.cnt[lane * 8 + j];
+          if (was == now) continue;
+          unsigned delta = 0; int dec[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int b = (int)((was >> (8 * i)) & 0xffu), n = (int)((now >> (8 * i)) & 0xffu);
+            const int ci = b <= 8 ? n - b : 0;                  // evaluated: 0xFE - b; else minus the local arrivals
+            dec[i] = ci;
+            delta += (unsigned)ci << (8 * i);
+          }
+          if (delta != 0) {
+            const unsigned old = atomicAdd(gw + j, delta);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (dec[i] < 0 && (int)((old >> (8 * i)) & 0xffu) + dec[i] == 0) dirty = true;   // became ready meanwhile
+          }
+        }
+      }
+      if (dirty) M.dirty = 1;
+    }
+    __syncwarp();
+    const int ne = M.next;
+    for (int e = lane; e < ne; e += 32) {
+      const int code = M.ext[e];
+      const int rr = code / RW, rc = code - rr * RW;
+      const int r = r0 - 1 + rr, c = c0 - 1 + rc;
+      if (r == 0 || r == s.ny + 1) { atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1); continue; }
+      const long long ci = s.idx(r, c);
+      if (!(a.node[ci] & NODE_VALID)) continue;
+      const unsigned sh = (unsigned)(ci & 3) * 8u;
+      const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - (1u << sh));
+      if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (M.dirty) sched_activate(a, t);
+      sched_finish(a, t);
+      if (a.stats) {
+        const long long tk4 = clock64();
+        atomicAdd(a.ctr + 3, 1ull);
+        atomicAdd(a.ctr + 4, (unsigned long long)(tk1 - tk0));
+        atomicAdd(a.ctr + 5, (unsigned long long)(tk2 - tk1));
+        atomicAdd(a.ctr + 6, (unsigned long long)(tk3 - tk2));
+        atomicAdd(a.ctr + 7, (unsigned long long)(tk4 - tk3));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Applies the dependency decrements received from the neighbour strips (addBorders, src/linearpart.h:314-328 and
+// src/aread8.cpp:283-297): dec_top[c] arrivals for the cell (row 1, c), dec_bot[c] for (row ny, c).  A count that
+// reaches zero queues the cell's tile.
+__global__ void k_wapply_halo(WArgs a, const int* __restrict__ dec_top, const int* __restrict__ dec_bot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.s.nx) return;
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int* dec = side == 0 ? dec_top : dec_bot;
+    if (dec == nullptr) continue;
+    const int d = dec[c];
+    if (d <= 0) continue;
+    const int r = side == 0 ? 1 : a.s.ny;
+    const long long ci = a.s.idx(r, c);
+    if (!(a.node[ci] & NODE_VALID)) continue;
+    const unsigned sh = (unsigned)(ci & 3) * 8u;
+    const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - ((unsigned)d << sh));
+    if ((int)((old >> sh) & 0xffu) == d) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
+  }
+}
+
+__global__ void k_wsched_reset(unsigned long long* ctr) { ctr[0] = ctr[1] = ctr[2] = 0; }
+
+int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
+  a.s = s;
+  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
+  a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + TS - 1) / TS;
+  a.stats = 0;
+  const long long nt = (long long)a.ntx * a.nty;
+  if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
+  unsigned qcap = 1u << 14;   // always far more slots than workers holding tickets
+  while (qcap < (unsigned long long)nt) qcap <<= 1;
+  TD_CUDA(ctx->tileflags.ensure((size_t)nt * 4 + (size_t)qcap * 4));
+  a.state = ctx->tileflags.as<int>();
+  a.tq = a.state + nt;
+  a.qmask = qcap - 1;
+  a.ctr = ctx->d_ctr + 24;
+  a.node = ctx->node.as<unsigned short>();
+  a.cntw = ctx->cnt.as<unsigned>();
+  return TD_OK;
+}
+}  // namespace
+
+// Queues every tile of the strip (start of a sweep).
+int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
+  WArgs a;
+  if (int rc = wargs(ctx, a, s)) return rc;
+  const int nt = a.ntx * a.nty;
+  k_wsched_init<<<(a.qmask + 1 + 255) / 256, 256, 0, st>>>(a.state, a.tq, a.qmask + 1, nt, a.ctr);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// Decrements that crossed the strip boundary (from the neighbours' halo records); queues the tiles whose cells became
+// ready.  Must be called between two wsweep_run calls.
+int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st) {
+  WArgs a;
+  if (int rc = wargs(ctx, a, s)) return rc;
+  k_wsched_reset<<<1, 1, 0, st>>>(a.ctr);   // tickets abandoned at the end of the previous run are void
+  TD_LAUNCHED();
+  k_wapply_halo<<<(s.nx + 255) / 256, 256, 0, st>>>(a, dec_top, dec_bot);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+// Runs the evaluation wavefront over the queued tiles until no tile of the strip has a ready cell left.
+int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
+  WArgs a;
+  if (int rc = wargs(ctx, a, s)) return rc;
+  a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
+  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+  const char* te = getenv("TAUDEM_B200_TIMING");
+  a.stats = (te && atoi(te) > 0) ? 1 : 0;
+  const size_t smem = sizeof(WarpMem) * WARPS;
+  const void* kern = dinf ? (const void*)k_sweep_warp<true> : (const void*)k_sweep_warp<false>;
+  int& per_dev = dinf ? ctx->wgrid_dinf : ctx->wgrid_d8;
+  if (!per_dev) {
+    int dev = 0, sms = 0, occ = 0;
+    TD_CUDA(cudaGetDevice(&dev));
+    TD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+    if (occ < 1) { set_error("sweep kernel does not fit on an SM"); return TD_ERR_CUDA; }
+    per_dev = sms * occ;     // persistent: every CTA is resident, so queue waits cannot deadlock
+  }
+  const long long nt = (long long)a.ntx * a.nty;
+  const int g = (int)std::min<long long>(per_dev, (nt + WARPS - 1) / WARPS);
+  if (dinf) k_sweep_warp<true><<<g, WARPS * 32, smem, st>>>(a);
+  else k_sweep_warp<false><<<g, WARPS * 32, smem, st>>>(a);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+
+}  // namespace td

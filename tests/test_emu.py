@@ -37,7 +37,7 @@ def _transform(name, min_launches=6):
 
 def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
-    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("sweep_tiles", 5), _transform("fill", 3)]
+    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("sweep_tiles", 5), _transform("fill", 3), _transform("sweep_warp", 4)]
     so = os.path.join(BUILD, f"libemu{tag}.so")
     objs = []
     for i, n in enumerate(STENCILS):                       # one translation unit per kernel file (their helper names collide)
@@ -48,7 +48,7 @@ def _build(tag="", defines=()):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-c", "-pthread", "-ftls-model=initial-exec", "-ffp-contract=off", "-I", EMU,
                                    "-I", BUILD, "-I", CSRC, f"-DEMU_WHICH={i + 1}", "-o", o, os.path.join(EMU, "stencil_driver.cpp")])
         objs.append(o)
-    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "tiles_driver.cpp", "emu.cpp")] + objs
+    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "tiles_driver.cpp", "warp_driver.cpp", "emu.cpp")] + objs
     deps = incs + srcs + [os.path.join(EMU, "cuda_runtime.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "dinf_common.cuh"),
                           os.path.join(CSRC, "ctx.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
@@ -64,6 +64,7 @@ def _build(tag="", defines=()):
     lib.emu_deps_dinf.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     lib.emu_ref_deps.argtypes = [C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     lib.emu_tiles.argtypes = [C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_ulonglong, P]
+    lib.emu_wtiles.argtypes = [C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_ulonglong, P]
     lib.emu_fill.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_ulonglong]
     lib.emu_flats.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
     return lib
@@ -374,6 +375,50 @@ def test_emulated_tile_sweep(emu, fields, hybrid):
     assert_bits(_tiles(emu, False, hybrid, p, w, False, 92)[0], port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc tiles")
     assert_bits(_tiles(emu, True, hybrid, ang, None, True, 93)[0], port.areadinf(ang), f"sca tiles hybrid={hybrid}")
     assert_bits(_tiles(emu, True, hybrid, ang, w, False, 94)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc tiles")
+
+
+def _wtiles(lib, dinf, direction, w, contcheck, seed, dx=30.0, dy=30.0):
+    ny, nx = direction.shape
+    out = np.empty((ny, nx), np.float32)
+    d = np.ascontiguousarray(direction)
+    wp = None if w is None else np.ascontiguousarray(w, np.float32)
+    visits = np.zeros(1, np.uint64)
+    nodata = -3.4028234663852886e38 if dinf else -32768.0
+    os.environ["TAUDEM_B200_TIMING"] = "1"        # the visit counter is a statistic
+    try:
+        rc = lib.emu_wtiles(int(dinf), d.ctypes.data, out.ctypes.data, None if wp is None else wp.ctypes.data, nx, ny, nodata,
+                            int(w is not None), int(contcheck), -9999.0, dx, dy, seed, visits.ctypes.data)
+    finally:
+        os.environ.pop("TAUDEM_B200_TIMING", None)
+    assert rc == 0, rc
+    return out, int(visits[0])
+
+
+def test_emulated_warp_tile_sweep(emu, fields):
+    """The warp-per-tile dataflow sweep (sweep_warp.cu): every warp of the persistent CTA is an independent worker on
+    32 x 32 tiles; randomised interleavings of the eight workers; D8 / D-infinity, weights, no contamination check."""
+    port, p, ang, w = fields
+    ntiles = -(-p.shape[1] // 32) * -(-p.shape[0] // 32)
+    for seed in (101, 102, 103):
+        a, visits = _wtiles(emu, False, p, None, True, seed)
+        assert_bits(a, port.aread8(p), f"ad8 warp tiles seed {seed}")
+        assert visits > ntiles
+        assert_bits(_wtiles(emu, True, ang, None, True, seed)[0], port.areadinf(ang), f"sca warp tiles seed {seed}")
+    assert_bits(_wtiles(emu, False, p, w, False, 104)[0], port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc warp tiles")
+    assert_bits(_wtiles(emu, True, ang, w, False, 105)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc warp tiles")
+
+
+def test_emulated_warp_tile_sweep_golden(emu):
+    """... and on the reference-generated golden vectors (nodata holes, dx != dy, plateau, lake, 5 x 7 grid)."""
+    from util import golden_cases, load_golden
+    for name in golden_cases():
+        g = load_golden(name)
+        dx, dy = float(g["dx"]), float(g["dy"])
+        assert_bits(_wtiles(emu, False, g["p"], None, True, 111)[0], g["ad8"], f"{name} ad8")
+        assert_bits(_wtiles(emu, False, g["p"], g["w"], True, 112)[0], g["ad8_w"], f"{name} ad8 -wg")
+        assert_bits(_wtiles(emu, True, g["ang"], None, True, 113, dx, dy)[0], g["sca"], f"{name} sca")
+        assert_bits(_wtiles(emu, True, g["ang"], g["w"], True, 114, dx, dy)[0], g["sca_w"], f"{name} sca -wg")
+        assert_bits(_wtiles(emu, True, g["ang"], None, False, 115, dx, dy)[0], g["sca_nc"], f"{name} sca -nc")
 
 
 def test_emulated_pitremove(emu):
