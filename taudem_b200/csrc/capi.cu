@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "rowfact.cuh"
 
 namespace td {
 unsigned long long g_launches = 0;
@@ -155,7 +156,9 @@ int td_d8_slopes_dev(td_ctx* ctx, const float* fel, int16_t* p, float* sd8, td_s
   if (int rc = check_strip(s)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   TD_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, sizeof(unsigned long long), st));
-  TD_CUDA(td::launch_d8_stencil(fel, p, sd8, dxc, dyc, Strip(s), fel_nodata, ctx->d_ctr + 8, st));
+  TD_CUDA(ctx->rowfact.ensure(sizeof(td::RowFact) * (size_t)s.ny));
+  td::launch_row_factors(dxc, dyc, nullptr, nullptr, ctx->rowfact.as<td::RowFact>(), s.ny, st);
+  if (int rc = td::launch_d8_stencil(fel, p, sd8, ctx->rowfact.as<td::RowFact>(), Strip(s), fel_nodata, ctx->d_ctr + 8, st)) return rc;
   if (nflat_out) {
     TD_CUDA(cudaMemcpyAsync(ctx->h_ctr + 8, ctx->d_ctr + 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));
@@ -201,7 +204,9 @@ int td_dinf_slopes_dev(td_ctx* ctx, const float* fel, float* ang, float* slp, td
   if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
   const double* thA = ctx->theta.as<double>();
   TD_CUDA(cudaMemsetAsync(ctx->d_ctr + 8, 0, sizeof(unsigned long long), st));
-  TD_CUDA(td::launch_dinf_stencil(fel, ang, slp, dxc, dyc, thA, thA + s.ny, Strip(s), fel_nodata, ctx->d_ctr + 8, st));
+  TD_CUDA(ctx->rowfact.ensure(sizeof(td::RowFact) * (size_t)s.ny));
+  td::launch_row_factors(dxc, dyc, thA, thA + s.ny, ctx->rowfact.as<td::RowFact>(), s.ny, st);
+  if (int rc = td::launch_dinf_stencil(fel, ang, slp, ctx->rowfact.as<td::RowFact>(), Strip(s), fel_nodata, ctx->d_ctr + 8, st)) return rc;
   if (nflat_out) {
     TD_CUDA(cudaMemcpyAsync(ctx->h_ctr + 8, ctx->d_ctr + 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     TD_CUDA(cudaStreamSynchronize(st));

@@ -33,6 +33,7 @@ struct td_ctx {
   Buf halo;      // cross-strip dependency decrements: 2 x pitch ints
   Buf theta;     // per-row atan2(dy,dx) | atan2(dx,dy) tables (doubles)
   Buf rows;      // per-row dxc | dyc (host-grid level calls)
+  Buf rowfact;   // per-row constants of the flow-direction stencils (rowfact.cuh)
   Buf io[4];     // raster strips of host-grid level calls
   // peer mode of the sweeps (neighbour strips' buffers opened through CUDA IPC, see sweep_tiles.cu)
   struct PeerInfo { void *cntw = nullptr, *tileflags = nullptr, *dctr = nullptr, *halo_in = nullptr; int qmask = 0, ntx = 0, ny = 0, th = 0, nt = 0, valid = 0; };

@@ -3,11 +3,11 @@
 #include "ctx.h"
 
 namespace td {
-cudaError_t launch_d8_stencil(const float* elev, short* dir, float* slope, const double* dxc, const double* dyc,
-                              const Strip& s, float nodata, unsigned long long* nflat, cudaStream_t st);
-cudaError_t launch_dinf_stencil(const float* elev, float* ang, float* slp, const double* dxc, const double* dyc,
-                                const double* thA, const double* thB, const Strip& s, float nodata,
-                                unsigned long long* nflat, cudaStream_t st);
+struct RowFact;
+int launch_d8_stencil(const float* elev, short* dir, float* slope, const RowFact* rowf, const Strip& s, float nodata,
+                      unsigned long long* nflat, cudaStream_t st);
+int launch_dinf_stencil(const float* elev, float* ang, float* slp, const RowFact* rowf, const Strip& s, float nodata,
+                        unsigned long long* nflat, cudaStream_t st);
 int resolve_flats_d8(td_ctx* ctx, float* elev, short* dir, const Strip& s, const double* dxc, const double* dyc,
                      long long* nleft, const td_strip_comm* comm, cudaStream_t st);
 int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, const double* dxc, const double* dyc,

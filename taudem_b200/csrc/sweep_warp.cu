@@ -7,7 +7,7 @@
 //
 //  * the strip is cut into 32 x 32 tiles; tile ids wait in a device-side multi-producer / multi-consumer ticket queue;
 //  * every warp of a grid of persistent CTAs is an independent worker: it pops a tile, stages the tile's dependency
-//    counts (1 KB) and areas with a one-cell ring (4.6 KB) in its own slice of shared memory and runs the wavefront
+//    counts, node words, areas (and angles) with a one-cell ring in its own slice of shared memory (cp.async, one round trip) and runs the wavefront
 //    there — each lane follows one chain (evaluate, shared-memory atomic decrement of the receiver(s), go on when it
 //    was the last arrival), second receivers of D-infinity cells go to a warp-local queue that idle lanes drain;
 //    no CTA-wide barrier exists anywhere, a warp that holds a long chain delays nobody;
@@ -31,21 +31,27 @@ namespace {
 
 constexpr int TS = 32;                                // tile edge (cells)
 constexpr int TC = TS * TS;                           // cells per tile
-constexpr int RW = TS + 2;                            // ring width / height
+constexpr int RH = TS + 2;                            // ring rows
+constexpr int RS = TS + 8;                            // ring row stride: columns c0-4 .. c0+35 (16-byte aligned rows), cell lx at lx + 4
 constexpr int EXTCAP = 256;                           // crossings of one visit: <= 124 perimeter cells x 2 receivers
-constexpr int WARPS = 8;                              // workers per CTA
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 constexpr unsigned FULL = 0xffffffffu;
 
-// one worker's shared memory
+// one worker's shared memory: everything a visit touches while it runs the wavefront
+template <bool DINF>
 struct __align__(16) WarpMem {
-  float area[RW * RW];          // areas of the tile and its ring (-1 = nodata / not final)
-  unsigned cnt[TC / 4];         // dependency counts, four cells per word: 0..8, 0xFE = evaluated, 0xFF = not a node
-  unsigned short wq[TC];        // ready cells (every cell enters at most once)
-  unsigned short ext[EXTCAP];   // receivers outside the tile (ring index)
-  unsigned evmask[TS];          // per tile row: cells evaluated by this visit
+  float area[RH * RS];                    // areas of the tile and its ring (-1 = nodata / not final)
+  float ang[DINF ? RH * RS : 4];          // D-infinity: angles of the same cells
+  unsigned short node[RH * RS];           // node words of the same cells (D8 uses the interior only)
+  unsigned cnt[TC / 4];                   // dependency counts, four cells per word: 0..8, 0xFE = evaluated, 0xFF = not a node
+  double theta[DINF ? RH + 2 : 2];        // D-infinity: prop()'s row angle for every ring row
+  double dxr[DINF ? TS : 2];              // D-infinity: cell size of every tile row
+  unsigned short wq[TC];                  // ready cells (every cell enters at most once)
+  unsigned short ext[EXTCAP];             // receivers outside the tile (ring index)
+  unsigned evmask[TS];                    // per tile row: cells evaluated by this visit
   int qtail, next, dirty, pad;
 };
+template <bool DINF> constexpr int workers_per_cta() { return DINF ? 12 : 16; }
 
 struct WArgs {
   const unsigned short* node;
@@ -71,6 +77,16 @@ struct WArgs {
 template <typename T> __device__ __forceinline__ T ldv(const T* p) { emu::yield(); return *((const volatile T*)p); }
 #else
 template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((const volatile T*)p); }
+#endif
+
+#ifndef TD_EMU
+__device__ __forceinline__ void cp16(void* smem, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp8(void* smem, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+__device__ __forceinline__ void cp16(void* smem, const void* g) { emu::yield(); memcpy(smem, g, 16); }
+__device__ __forceinline__ void cp8(void* smem, const void* g) { memcpy(smem, g, 8); }
+__device__ __forceinline__ void cp_wait_all() {}
 #endif
 
 // ---- scheduler (the protocol of the first-generation tile kernel, one lane per worker)
@@ -129,12 +145,13 @@ __device__ __noinline__ double wshare_full(float ang, double t, int kk) {
 __device__ __forceinline__ unsigned zero_bytes(unsigned w) { return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; }
 
 template <bool DINF>
-__global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
+__global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(const WArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
+  using Mem = WarpMem<DINF>;
   const Strip& s = a.s;
   const int lane = (int)(threadIdx.x & 31u), wid = (int)(threadIdx.x >> 5);
   const unsigned lt = (1u << lane) - 1u;
-  WarpMem& M = *reinterpret_cast<WarpMem*>(dsm + (size_t)wid * sizeof(WarpMem));
+  Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
 
   for (;;) {
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
@@ -162,25 +179,32 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
     if (lane == 0) { M.qtail = 0; M.next = 0; M.dirty = 0; }
     __threadfence();          // the counts first, then the areas they announce (loaded by other lanes: barrier in between)
     __syncwarp();
-    // ---- 2. areas of the tile and its ring: lane = column (lanes 0 / 1 also take the two extra ring columns)
-#pragma unroll 2
-    for (int rr = 0; rr < RW; ++rr) {
-      const int r = r0 - 1 + rr;
-      const bool rowin = r >= 0 && r <= s.ny + 1;
-      {
-        const int c = c0 - 1 + lane;
-        float v = -1.0f;
-        if (rowin && c >= 0 && c < s.nx) v = __ldcg(a.area + s.idx(r, c));
-        M.area[rr * RW + lane] = v;
-      }
-      if (lane < 2) {
-        const int c = c0 + 31 + lane;
-        float v = -1.0f;
-        if (rowin && c < s.nx) v = __ldcg(a.area + s.idx(r, c));
-        M.area[rr * RW + 32 + lane] = v;
+    // ---- 2. areas (+ node words, angles) of the tile and its ring: asynchronous 16-byte copies straight into shared memory,
+    //         all in flight at once (one round trip); what lies off the strip is filled in directly
+#pragma unroll
+    for (int j = 0; j < (RH * (RS / 4) + 31) / 32; ++j) {
+      const int i = lane + 32 * j;
+      if (i < RH * (RS / 4)) {
+        const int rr = i / (RS / 4), q = i - rr * (RS / 4);
+        const int r = r0 - 1 + rr, c = c0 - 4 + 4 * q;
+        const int so = rr * RS + 4 * q;
+        if (r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.pitch) {
+          const long long g = s.idx(r, c);
+          cp16(M.area + so, a.area + g);
+          if (DINF) cp16(M.ang + so, a.ang + g);
+          if (DINF || (rr >= 1 && rr <= TS && q >= 1 && q <= TS / 4)) cp8(M.node + so, a.node + g);
+        } else {
+          *reinterpret_cast<float4*>(M.area + so) = make_float4(-1.f, -1.f, -1.f, -1.f);
+          if (DINF) *reinterpret_cast<float4*>(M.ang + so) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<uint2*>(M.node + so) = make_uint2(0u, 0u);
+        }
       }
     }
-    __syncwarp();
+    if (DINF) {
+      // prop()'s row angle of every ring row (clamped to the strip's rows like the dependency stencil does), cell sizes of the tile rows
+      for (int i = lane; i < RH; i += 32) M.theta[i] = a.theta[min(max(r0 - 2 + i, 0), s.ny - 1)];
+      M.dxr[lane] = a.dxc[min(r0 + lane, s.ny) - 1];
+    }
     // ---- 3. cells that are ready (count 0): lane = tile row
     {
       int n = 0;
@@ -202,6 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
       const int total = __shfl_sync(FULL, incl, 31);
       if (lane == 0) M.qtail = total;
     }
+    cp_wait_all();
     __syncwarp();
     if (a.stats && lane == 0) tk2 = clock64();
 
@@ -221,22 +246,20 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
       if (cur >= 0) {
         const int l = cur;
         const int lr = l >> 5, lx = l & 31;
-        const int ri = (lr + 1) * RW + lx + 1;
-        const int r = r0 + lr, c = c0 + lx;
-        const long long ci = s.idx(r, c);
-        const unsigned nd = a.node[ci];
+        const int ri = (lr + 1) * RS + lx + 4;
+        const unsigned nd = M.node[ri];
         const unsigned msk = nd & 0xffu;
         bool con = (nd & NODE_CON) != 0;
         float val;
         int cont = -1;
         if (!DINF) {
           // src/aread8.cpp:228-257
-          if (a.usew) { const float wv = a.w[ci]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
+          if (a.usew) { const float wv = a.w[s.idx(r0 + lr, c0 + lx)]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
           else val = 1.0f;
 #pragma unroll
           for (int k = 1; k <= 8; ++k)
             if (msk & (1u << (k - 1))) {
-              const float an = M.area[ri + drow(k) * RW + dcol(k)];
+              const float an = M.area[ri + drow(k) * RS + dcol(k)];
               if (nd_f(an, -1.0f)) con = true; else val = val + an;
             }
         } else {
@@ -245,33 +268,28 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
           // the share is one division — exactly the expressions dinf_outflow evaluates; everything else (single
           // receiver, the wrap sector, contributors in a halo row, whose node words belong to the neighbour strip)
           // takes the full interval search.
-          float aa[8]; unsigned short nn[8];
-#pragma unroll
-          for (int k = 1; k <= 8; ++k) {
-            const bool in = (msk >> (k - 1)) & 1u;
-            const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
-            aa[k - 1] = in ? a.ang[ni] : 0.f;
-            nn[k - 1] = in ? a.node[ni] : (unsigned short)0;
-          }
+          const int r = r0 + lr;
           val = 0.f;
 #pragma unroll
           for (int k = 1; k <= 8; ++k)
             if (msk & (1u << (k - 1))) {
+              const int ni = ri + drow(k) * RS + dcol(k);
               const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
               const int rn = r + drow(k);
-              const double th = a.theta[min(max(rn - 1, 0), s.ny - 1)];
-              const int k1n = (nn[k - 1] >> 8) & 0xf;
+              const double th = M.theta[lr + 1 + drow(k)];
+              const unsigned nn = M.node[ni];
+              const float av = M.ang[ni];
+              const int k1n = (nn >> 8) & 0xf;
               double p;
-              if ((nn[k - 1] & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
+              if ((nn & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
                 const double mid = aref(k1n, th), hi = aref(k1n + 1, th);
-                const float av = aa[k - 1];
                 p = (kk == k1n) ? (hi - av) / (hi - mid) : (av - mid) / (hi - mid);
-              } else p = wshare_full(aa[k - 1], th, kk);
-              const float an = M.area[ri + drow(k) * RW + dcol(k)];
+              } else p = wshare_full(av, th, kk);
+              const float an = M.area[ni];
               if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
             }
-          if (a.usew) val = val + a.w[ci];
-          else val = (float)((double)val + a.dxc[r - 1]);
+          if (a.usew) val = val + a.w[s.idx(r, c0 + lx)];
+          else val = (float)((double)val + M.dxr[lr]);
         }
         if (con && a.contcheck) val = -1.0f;
         M.area[ri] = val;
@@ -295,7 +313,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
               else M.wq[atomicAdd(&M.qtail, 1)] = (unsigned short)l2;   // a second ready receiver: an idle lane takes it
             }
           } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
-            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)((nlr + 1) * RW + nlx + 1);
+            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)((nlr + 1) * RS + nlx + 4);
           }
         }
         cur = cont;
@@ -305,9 +323,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
     if (a.stats && lane == 0) tk3 = clock64();
 
     // ---- 5. write back what this visit evaluated, then publish counts and deliver the crossings
-#pragma unroll 4
+#pragma unroll
     for (int lr = 0; lr < TS; ++lr)
-      if ((M.evmask[lr] >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RW + lane + 1];
+      if ((M.evmask[lr] >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RS + lane + 4];
     __threadfence();
     __syncwarp();
     __threadfence();          // release by the lanes that publish: the other lanes' area stores are ordered before their atomics
@@ -342,11 +360,12 @@ __global__ void __launch_bounds__(WARPS * 32) k_sweep_warp(const WArgs a) {
     const int ne = M.next;
     for (int e = lane; e < ne; e += 32) {
       const int code = M.ext[e];
-      const int rr = code / RW, rc = code - rr * RW;
-      const int r = r0 - 1 + rr, c = c0 - 1 + rc;
+      const int rr = code / RS, rc = code - rr * RS;
+      const int r = r0 - 1 + rr, c = c0 - 4 + rc;
       if (r == 0 || r == s.ny + 1) { atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1); continue; }
       const long long ci = s.idx(r, c);
-      if (!(a.node[ci] & NODE_VALID)) continue;
+      const unsigned ndr = DINF ? (unsigned)M.node[code] : (unsigned)a.node[ci];
+      if (!(ndr & NODE_VALID)) continue;
       const unsigned sh = (unsigned)(ci & 3) * 8u;
       const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - (1u << sh));
       if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
@@ -444,7 +463,8 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
   const char* te = getenv("TAUDEM_B200_TIMING");
   a.stats = (te && atoi(te) > 0) ? 1 : 0;
-  const size_t smem = sizeof(WarpMem) * WARPS;
+  const int warps = dinf ? workers_per_cta<true>() : workers_per_cta<false>();
+  const size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
   const void* kern = dinf ? (const void*)k_sweep_warp<true> : (const void*)k_sweep_warp<false>;
   int& per_dev = dinf ? ctx->wgrid_dinf : ctx->wgrid_d8;
   if (!per_dev) {
@@ -452,14 +472,14 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
     TD_CUDA(cudaGetDevice(&dev));
     TD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     TD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+    TD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
     if (occ < 1) { set_error("sweep kernel does not fit on an SM"); return TD_ERR_CUDA; }
     per_dev = sms * occ;     // persistent: every CTA is resident, so queue waits cannot deadlock
   }
   const long long nt = (long long)a.ntx * a.nty;
-  const int g = (int)std::min<long long>(per_dev, (nt + WARPS - 1) / WARPS);
-  if (dinf) k_sweep_warp<true><<<g, WARPS * 32, smem, st>>>(a);
-  else k_sweep_warp<false><<<g, WARPS * 32, smem, st>>>(a);
+  const int g = (int)std::min<long long>(per_dev, (nt + warps - 1) / warps);
+  if (dinf) k_sweep_warp<true><<<g, warps * 32, smem, st>>>(a);
+  else k_sweep_warp<false><<<g, warps * 32, smem, st>>>(a);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;

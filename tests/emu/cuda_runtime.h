@@ -33,6 +33,8 @@
 
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3() {} dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+inline uint2 make_uint2(unsigned a, unsigned b) { return {a, b}; }
 struct ushort4 { unsigned short x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
 struct float4 { float x, y, z, w; };
@@ -118,6 +120,7 @@ template <typename T> inline T __ldcg(const T* p) { emu::yield(); return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline long long clock64() { return 0; }
+inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) << (sh & 31) >> 32); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31)); }
 using std::max;

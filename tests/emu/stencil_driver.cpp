@@ -3,6 +3,7 @@
 // the rasters with the oracle and the dependency state with the plain-loop restatement in driver.cpp.
 #if EMU_WHICH == 1
 #include "d8_stencil_emu.inc"
+#include "rowfact_emu.inc"
 #elif EMU_WHICH == 2
 #include "dinf_stencil_emu.inc"
 #elif EMU_WHICH == 3
@@ -41,7 +42,9 @@ extern "C" int emu_d8_stencil(const float* fel, short* p, float* sd8, int nx, in
   auto e = g.in(fel);
   std::vector<short> d((size_t)g.s.cells(), 0); std::vector<float> sl((size_t)g.s.cells(), 0.f);
   *nflat = 0;
-  td::launch_d8_stencil(e.data(), d.data(), sl.data(), g.dxc.data(), g.dyc.data(), g.s, nodata, nflat, nullptr);
+  std::vector<td::RowFact> rf(ny);
+  td::launch_row_factors(g.dxc.data(), g.dyc.data(), nullptr, nullptr, rf.data(), ny, nullptr);
+  if (td::launch_d8_stencil(e.data(), d.data(), sl.data(), rf.data(), g.s, nodata, nflat, nullptr)) return 1;
   g.out(d, p); g.out(sl, sd8);
   return 0;
 }
@@ -51,7 +54,9 @@ extern "C" int emu_dinf_stencil(const float* fel, float* ang, float* slp, int nx
   auto e = g.in(fel);
   std::vector<float> a((size_t)g.s.cells(), 0.f), sl((size_t)g.s.cells(), 0.f);
   *nflat = 0;
-  td::launch_dinf_stencil(e.data(), a.data(), sl.data(), g.dxc.data(), g.dyc.data(), g.th.data(), g.th.data() + ny, g.s, nodata, nflat, nullptr);
+  std::vector<td::RowFact> rf(ny);
+  td::launch_row_factors(g.dxc.data(), g.dyc.data(), g.th.data(), g.th.data() + ny, rf.data(), ny, nullptr);
+  if (td::launch_dinf_stencil(e.data(), a.data(), sl.data(), rf.data(), g.s, nodata, nflat, nullptr)) return 1;
   g.out(a, ang); g.out(sl, slp);
   return 0;
 }

@@ -26,6 +26,7 @@ def _transform(name, min_launches=6):
     """kernel<<<grid, block, smem, stream>>>(args);  ->  emu_launch(grid, block, [&]{ kernel(args); });"""
     src = open(os.path.join(CSRC, name + ".cu")).read()
     src = src.replace("extern __shared__ __align__(16) unsigned char dsm[];", "static __align__(16) unsigned char dsm[256 * 1024];")
+    src = src.replace("extern __shared__ __align__(128) unsigned char dsm128[];", "static __align__(128) unsigned char dsm128[256 * 1024];")
     src, n = re.subn(r"(k_\w+(?:<[\w, ]+>)?)<<<([^,]+),\s*([^,]+),[^>]*>>>\(([^;]*)\);",
                      r"emu_launch(dim3(\2), dim3(\3), [&] { \1(\4); });", src)
     assert n >= min_launches and "<<<" not in src, (name, n)
@@ -37,13 +38,14 @@ def _transform(name, min_launches=6):
 
 def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
+    _transform("rowfact", 1)
     incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("sweep_tiles", 5), _transform("fill", 3), _transform("sweep_warp", 4)]
     so = os.path.join(BUILD, f"libemu{tag}.so")
     objs = []
     for i, n in enumerate(STENCILS):                       # one translation unit per kernel file (their helper names collide)
         o = os.path.join(BUILD, f"stencil{i + 1}.o")
         deps_o = [incs[2 + i], os.path.join(EMU, "stencil_driver.cpp"), os.path.join(EMU, "cuda_runtime.h"), os.path.join(CSRC, "common.cuh"),
-                  os.path.join(CSRC, "dinf_common.cuh")]
+                  os.path.join(CSRC, "dinf_common.cuh"), os.path.join(CSRC, "tile_pipe.cuh"), os.path.join(CSRC, "rowfact.cuh"), os.path.join(BUILD, "rowfact_emu.inc")]
         if not os.path.exists(o) or any(os.path.getmtime(d) > os.path.getmtime(o) for d in deps_o):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-c", "-pthread", "-ftls-model=initial-exec", "-ffp-contract=off", "-I", EMU,
                                    "-I", BUILD, "-I", CSRC, f"-DEMU_WHICH={i + 1}", "-o", o, os.path.join(EMU, "stencil_driver.cpp")])
