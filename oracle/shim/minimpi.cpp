@@ -1,6 +1,10 @@
 // TEST INFRASTRUCTURE ONLY.  fork()+socketpair implementation of oracle/shim/mpi.h.
 #include "mpi.h"
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <errno.h>
+#include <sched.h>
 #include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -64,6 +68,18 @@ int MPI_Init(int*, char***) {
     if (pid < 0) die("fork");
     if (pid == 0) { g_rank = r; g_children.clear(); break; }
     g_children.push_back(pid);
+  }
+  // MINIMPI_PIN=1: rank r runs on the r-th CPU of the process's affinity mask (stable timings between hosts: no rank migration)
+  if (const char* pin = getenv("MINIMPI_PIN")) {
+    if (atoi(pin) > 0) {
+      cpu_set_t have, want;
+      if (sched_getaffinity(0, sizeof have, &have) == 0) {
+        const int n = CPU_COUNT(&have);
+        int k = n > 0 ? g_rank % n : 0;
+        for (int c = 0; c < CPU_SETSIZE; c++)
+          if (CPU_ISSET(c, &have) && k-- == 0) { CPU_ZERO(&want); CPU_SET(c, &want); sched_setaffinity(0, sizeof want, &want); break; }
+      }
+    }
   }
   g_fd.assign(g_size, -1);
   for (int a = 0; a < g_size; a++)

@@ -35,7 +35,7 @@ td_ctx::td_ctx() {
 }
 td_ctx::~td_ctx() {
   node.release(); cnt.release(); lev.release(); mk.release(); listA.release(); listB.release(); listC.release();
-  tileflags.release(); halo.release();
+  tileflags.release(); wsched.release(); rowfact.release(); halo.release();
   if (d_ctr) cudaFree(d_ctr);
   if (h_ctr) cudaFreeHost(h_ctr);
 }
@@ -193,7 +193,10 @@ static int upload_theta(td_ctx* ctx, const double* d_dxc, const double* d_dyc, i
   TD_CUDA(buf.ensure(sizeof(double) * 2 * (size_t)ny));
   TD_CUDA(cudaMemcpyAsync(buf.p, th.data(), sizeof(double) * 2 * (size_t)ny, cudaMemcpyHostToDevice, st));
   TD_CUDA(cudaStreamSynchronize(st));
-  (void)ctx;
+  // one prop() table for the whole strip when every row has the same angle (projected rasters)
+  bool uni = true;
+  for (int j = 1; j < ny && uni; j++) uni = th[j] == th[0];
+  td::make_prop_row(th[0], uni, &ctx->prop);
   return TD_OK;
 }
 

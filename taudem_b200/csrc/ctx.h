@@ -8,6 +8,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "dinf_common.cuh"
 
 struct td_ctx {
   // growable device buffers
@@ -30,6 +31,7 @@ struct td_ctx {
   Buf lev, mk;   // i32 per strip cell: Garbrecht-Martz levels / rise marks
   Buf listA, listB, listC;   // int64 cell-index lists (flat cells, BFS frontiers, ready queues)
   Buf tileflags; // fill: active-tile flags (2 x ntiles bytes)
+  Buf wsched;    // warp sweep: scheduler words (head / tail / pending), one 128-byte line each
   Buf halo;      // cross-strip dependency decrements: 2 x pitch ints
   Buf theta;     // per-row atan2(dy,dx) | atan2(dx,dy) tables (doubles)
   Buf rows;      // per-row dxc | dyc (host-grid level calls)
@@ -45,6 +47,7 @@ struct td_ctx {
   int sweep_dinf = 0;                    // which dependency state node/cnt hold (tile height of the sweep)
   int sweep_once = 0;                    // tile sweep: visit every tile once, no re-activation (hybrid mode)
   double phase_ms[4] = {0, 0, 0, 0};     // TAUDEM_B200_TIMING=1: level passes / ready-list collection / chain walking / rivers of the last sweep
+  td::PropRow prop;                      // prop() table of the strip whose theta table is loaded (uniform = 0: rows differ)
   int wgrid_d8 = 0, wgrid_dinf = 0;     // persistent grid of the warp-per-tile sweep kernels on this context's device
   int sweep_first = 1;                   // level / hybrid modes: the bulk phase has not run yet for the current dependency state
   unsigned long long* d_ctr = nullptr;   // 32 device counters

@@ -1,6 +1,8 @@
 // D-infinity facet arithmetic shared by the stencil and the flat-resolution kernels.
 // reference: VSLOPE src/dinf.cpp:286-313, facet tables src/dinf.cpp:328-335.
 #pragma once
+#include <string.h>
+
 #include "common.cuh"
 
 namespace td {
@@ -155,6 +157,31 @@ __device__ __forceinline__ unsigned dinf_receivers(float a, const AR& ar) {
   }
   const Outflow o = dinf_outflow_t(a, ar);
   return (unsigned)o.k1 | (o.k2 ? 0x10u : 0u);
+}
+
+// prop()'s table of a row with the sector widths and their reciprocals (strips whose rows all have the same cell size
+// keep ONE of these; the sweeps then get every share with a division by a table constant, rowfact.cuh's div_const)
+struct PropRow {
+  double ar[10];      // aref[]
+  double den[9];      // ar[j + 1] - ar[j]
+  double rden[9];     // RN(1 / den[j])
+  int safe;           // every den satisfies the precondition of the reciprocal division
+  int uniform;        // the strip has one table (else: per-row angles, plain divisions)
+};
+
+// host: the table for row angle t = atan2(dy, dx) (src/commonLib.cpp:78 builds aref[] with these expressions)
+inline void make_prop_row(double t, bool uniform, PropRow* P) {
+  const double PI = TD_PI;
+  const double ar[10] = {-t, 0., t, (double)(0.5 * PI), PI - t, (double)PI, PI + t, (double)(1.5 * PI), 2. * PI - t, (double)(2. * PI)};
+  P->safe = 1; P->uniform = uniform ? 1 : 0;
+  for (int i = 0; i < 10; i++) P->ar[i] = ar[i];
+  for (int i = 0; i < 9; i++) {
+    P->den[i] = ar[i + 1] - ar[i];
+    P->rden[i] = 1. / P->den[i];
+    unsigned long long b; memcpy(&b, &P->den[i], 8);
+    const unsigned long long ex = (b >> 52) & 0x7ffull, mant = b & 0xfffffffffffffull;
+    if ((b >> 63) != 0 || ex <= 64 || ex >= 1983 || mant == 0xfffffffffffffull) P->safe = 0;
+  }
 }
 
 __device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) { return dinf_outflow_t(a, ar); }

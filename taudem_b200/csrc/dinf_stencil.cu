@@ -49,6 +49,32 @@ __device__ __forceinline__ Facet vslope_row(double E0, double E1, double E2, dou
   return f;
 }
 
+// facet geometry as arithmetic on a run-time K: offsets of E1 / E2 in the staged tile, which cell size is D1
+__device__ __forceinline__ void facet_geom(int K, int sw, int& o1, int& o2, bool& d1x) {
+  const int i1 = (K == 2 || K == 3) ? -1 : (K == 6 || K == 7) ? 1 : 0;
+  const int j1 = (K == 1 || K == 8) ? 1 : (K == 4 || K == 5) ? -1 : 0;
+  const int i2 = K <= 4 ? -1 : 1;
+  const int j2 = (K == 1 || K == 2 || K == 7 || K == 8) ? 1 : -1;
+  o1 = i1 * sw + j1; o2 = i2 * sw + j2;
+  d1x = (K == 1 || K == 4 || K == 5 || K == 8);
+}
+
+// several facets within the float error of the best one: the exact slopes decide (increasing K, strict '>'); rare, out of line
+__device__ __noinline__ int exact_pick(const float* q0, int sw, unsigned cand, const RowFact* rfp) {
+  const RowFact rf = *rfp;
+  const double E0 = (double)q0[0];
+  double SMAX = 0.; int KD = 0;
+  for (unsigned m = cand; m; m &= m - 1) {
+    const int K = __ffs(m);
+    int o1, o2; bool d1x;
+    facet_geom(K, sw, o1, o2, d1x);
+    const Facet f = vslope_row(E0, (double)q0[o1], (double)q0[o2], d1x ? rf.dx : rf.dy, d1x ? rf.dy : rf.dx, rf.dd,
+                               d1x ? rf.rdx : rf.rdy, d1x ? rf.rdy : rf.rdx, rf.rdd, rf.safe != 0);
+    if (f.S > SMAX) { SMAX = f.S; KD = K; }
+  }
+  return KD;
+}
+
 __global__ void __launch_bounds__(256) k_dinf_stencil(const TD_GRID_CONSTANT TileMap tm, float* __restrict__ ang, float* __restrict__ slp,
                                                       const RowFact* __restrict__ rowf, Strip s, float nodata,
                                                       unsigned long long* __restrict__ nflat) {
@@ -67,81 +93,80 @@ __global__ void __launch_bounds__(256) k_dinf_stencil(const TD_GRID_CONSTANT Til
       const int r = r0 + tr, c = c0 + lane * 4;
       if (r > s.ny || c >= s.pitch) continue;
       const float* pm = tile + tr * G::SW + G::HP + lane * 4;
-      float nb[3][6];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float* q = pm + j * G::SW;
-        const float4 v = *reinterpret_cast<const float4*>(q);
-        nb[j][0] = q[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = q[4];
-      }
-      const RowFact rf = rowf[r - 1];
-      float colmin[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) colmin[i] = fminf(fminf(fabsf(nb[0][i] - nodata), fabsf(nb[1][i] - nodata)), fabsf(nb[2][i] - nodata));
+      const RowFact* rfp = rowf + (r - 1);
+      const float rdxf = rfp->rdxf, rdyf = rfp->rdyf, rddf = rfp->rddf, dxf = rfp->dxf, dyf = rfp->dyf;
       unsigned em = ((r == 1 && !s.has_top) || (r == s.ny && !s.has_bot)) ? 0xfu : 0u;
       em |= (c == 0) ? 1u : 0u;
       const int klast = s.nx - 1 - c;
       if (klast < 4) em |= (0xfu << max(klast, 0)) & 0xfu;
       float oa[4], os[4];
-#pragma unroll
+      // one cell at a time, the code once (an unrolled body of this size does not fit the instruction cache)
+#pragma unroll 1
       for (int i = 0; i < 4; ++i) {
-        const float z = nb[1][i + 1];
-        const bool bad = (fminf(fminf(colmin[i], colmin[i + 1]), colmin[i + 2]) < TD_MINEPS) || ((em >> i) & 1u);
-        // ---- 1. float ranking of the eight facets (squared slopes, 0 for a non-positive one)
+        const float* q0 = pm + G::SW + i;          // centre cell in the staged tile
+        float nb[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int x = 0; x < 3; ++x) nb[j][x] = q0[(j - 1) * G::SW + (x - 1)];
+        const float z = nb[1][1];
+        float dmin = fabsf(z - nodata);
+#pragma unroll
+        for (int k = 1; k <= 8; ++k) dmin = fminf(dmin, fabsf(nb[1 + drow(k)][1 + dcol(k)] - nodata));
+        const bool bad = dmin < TD_MINEPS || ((em >> i) & 1u);
+        // ---- 1. float ranking of the eight facets (squared slopes, 0 for a non-positive one) and the facts that are exact in float
         float st[8], smaxf = 0.f;
+        unsigned s2neg = 0, clipsafe = 0;
 #pragma unroll
         for (int K = 1; K <= 8; ++K) {
-          const float e1 = nb[1 + fI1(K)][i + 1 + fJ1(K)], e2 = nb[1 + fI2(K)][i + 1 + fJ2(K)];
-          const float r1 = fD1isDx(K) ? rf.rdxf : rf.rdyf, r2 = fD1isDx(K) ? rf.rdyf : rf.rdxf;
-          const float d1f = fD1isDx(K) ? rf.dxf : rf.dyf, d2f = fD1isDx(K) ? rf.dyf : rf.dxf;
+          const float e1 = nb[1 + fI1(K)][1 + fJ1(K)], e2 = nb[1 + fI2(K)][1 + fJ2(K)];
+          const float r1 = fD1isDx(K) ? rdxf : rdyf, r2 = fD1isDx(K) ? rdyf : rdxf;
+          const float d1f = fD1isDx(K) ? dxf : dyf, d2f = fD1isDx(K) ? dyf : dxf;
           const float s1 = (z - e1) * r1, s2 = (e1 - e2) * r2;
-          const bool clip = (s1 <= 0.f) ? !(s1 == 0.f && s2 == 0.f) : (s2 * d1f > s1 * d2f);
-          const float lin = (s2 < 0.f) ? s1 : (z - e2) * rf.rddf;
-          const float Q = (s2 < 0.f || clip) ? (lin > 0.f ? lin * lin : 0.f) : s1 * s1 + s2 * s2;
+          const bool neg = e1 < e2;                                      // S2 < 0, exactly
+          const float x = s2 * d1f, y = s1 * d2f;
+          const bool clip = (z <= e1) ? !(z == e1 && e1 == e2) : (x > y);
+          const bool csafe = !neg && ((z <= e1) ? !(z == e1 && e1 == e2) : (x > y * 1.0001f));   // clipped beyond doubt
+          const float lin = neg ? s1 : (z - e2) * rddf;
+          const float Q = (neg || clip) ? (lin > 0.f ? lin * lin : 0.f) : s1 * s1 + s2 * s2;
           st[K - 1] = Q;
           smaxf = fmaxf(smaxf, Q);
+          s2neg |= neg ? (1u << (K - 1)) : 0u;
+          clipsafe |= csafe ? (1u << (K - 1)) : 0u;
         }
         unsigned cand = 0;
         const float thr = smaxf * 0.99996f;
 #pragma unroll
         for (int K = 1; K <= 8; ++K) cand |= (st[K - 1] >= thr && st[K - 1] > 0.f) ? (1u << (K - 1)) : 0u;
         if (bad) cand = 0;
-        const float* q0 = pm + G::SW + i;          // centre cell in the staged tile
-        const double E0 = (double)z;
-        int KD = cand ? __ffs(cand) : 0;
-        if (cand & (cand - 1u)) {
-          // several facets within the float error of the best one: the exact slopes decide (increasing K, strict '>')
-          double SMAX = 0.; KD = 0;
-          for (unsigned m = cand; m; m &= m - 1) {
-            const int K = __ffs(m);
-            const bool d1x = fD1isDx(K);
-            const float e1 = q0[fI1(K) * G::SW + fJ1(K)], e2 = q0[fI2(K) * G::SW + fJ2(K)];
-            const Facet f = vslope_row(E0, (double)e1, (double)e2, d1x ? rf.dx : rf.dy, d1x ? rf.dy : rf.dx, rf.dd,
-                                       d1x ? rf.rdx : rf.rdy, d1x ? rf.rdy : rf.rdx, rf.rdd, rf.safe != 0);
-            if (f.S > SMAX) { SMAX = f.S; KD = K; }
-          }
+        // two facets that share E1 and both have S2 < 0 have the same slope S1 bit for bit, two that share E2 and are both
+        // clipped have the same slope (E0 - E2) / DD: the lower K wins such a tie (strict '>'), no FP64 needed to say so
+        {
+          const unsigned A = cand & s2neg, B = cand & clipsafe;
+          unsigned drop = ((A & 0x2au) << 1) & A;                         // pairs (2,3) (4,5) (6,7) share E1
+          if ((A & 0x81u) == 0x81u) drop |= 0x80u;                        // pair (1,8)
+          drop |= ((B & 0x55u) << 1) & B;                                 // pairs (1,2) (3,4) (5,6) (7,8) share E2
+          cand &= ~drop;
         }
+        int KD = cand ? __ffs(cand) : 0;
+        if (cand & (cand - 1u)) KD = exact_pick(q0, G::SW, cand, rfp);
         // ---- 2. the winner, once and uniformly
         float a = -1.0f, sl = 0.f;
         {
           const int K = KD ? KD : 1;
-          // facet geometry as arithmetic on K (no table): E1 offset, E2 offset, which cell size is D1
-          const int i1 = (K == 2 || K == 3) ? -1 : (K == 6 || K == 7) ? 1 : 0;
-          const int j1 = (K == 1 || K == 8) ? 1 : (K == 4 || K == 5) ? -1 : 0;
-          const int i2 = K <= 4 ? -1 : 1;
-          const int j2 = (K == 1 || K == 2 || K == 7 || K == 8) ? 1 : -1;
-          const bool d1x = (K == 1 || K == 4 || K == 5 || K == 8);
-          const float e1 = q0[i1 * G::SW + j1], e2 = q0[i2 * G::SW + j2];
-          const Facet f = vslope_row(E0, (double)e1, (double)e2, d1x ? rf.dx : rf.dy, d1x ? rf.dy : rf.dx, rf.dd,
-                                     d1x ? rf.rdx : rf.rdy, d1x ? rf.rdy : rf.rdx, rf.rdd, rf.safe != 0);
+          int o1, o2; bool d1x;
+          facet_geom(K, G::SW, o1, o2, d1x);
+          const double dx = rfp->dx, dy = rfp->dy, rdx = rfp->rdx, rdy = rfp->rdy;
+          const Facet f = vslope_row((double)z, (double)q0[o1], (double)q0[o2], d1x ? dx : dy, d1x ? dy : dx, rfp->dd,
+                                     d1x ? rdx : rdy, d1x ? rdy : rdx, rfp->rdd, rfp->safe != 0);
           if (KD > 0 && f.S > 0.) {
-            const double A = f.code == 0 ? 0. : f.code == 1 ? (d1x ? rf.adA : rf.adB) : atan2(f.S2, f.S1);
+            const double A = f.code == 0 ? 0. : f.code == 1 ? (d1x ? rfp->adA : rfp->adB) : atan2(f.S2, f.S1);
             a = dinf_angle(K, A);
             sl = (float)f.S;
           } else KD = 0;
         }
-        oa[i] = bad ? TD_MISSINGFLOAT : a;
-        os[i] = bad ? -1.0f : sl;
+        const float va = bad ? TD_MISSINGFLOAT : a, vs = bad ? -1.0f : sl;
+        if (i == 0) { oa[0] = va; os[0] = vs; } else if (i == 1) { oa[1] = va; os[1] = vs; } else if (i == 2) { oa[2] = va; os[2] = vs; } else { oa[3] = va; os[3] = vs; }
         if (!bad && KD == 0) ++myflat;
       }
       const long long o = s.idx(r, c);

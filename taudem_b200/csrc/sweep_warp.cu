@@ -25,6 +25,7 @@
 #include "ctx.h"
 #include "dinf_common.cuh"
 #include "kernels.h"
+#include "rowfact.cuh"
 
 namespace td {
 namespace {
@@ -33,9 +34,14 @@ constexpr int TS = 32;                                // tile edge (cells)
 constexpr int TC = TS * TS;                           // cells per tile
 constexpr int RH = TS + 2;                            // ring rows
 constexpr int RS = TS + 8;                            // ring row stride: columns c0-4 .. c0+35 (16-byte aligned rows), cell lx at lx + 4
+#ifndef TD_WSTK
+#define TD_WSTK 128
+#endif
+constexpr int STKCAP = TD_WSTK;                       // fork stack entries per worker
 constexpr int EXTCAP = 256;                           // crossings of one visit: <= 124 perimeter cells x 2 receivers
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int C_HEAD = 0, C_TAIL = 16, C_PEND = 32;   // indices into WArgs::ctr (8-byte words): head ticket, tail ticket, queued + running tiles
 
 // one worker's shared memory: everything a visit touches while it runs the wavefront
 template <bool DINF>
@@ -46,12 +52,12 @@ struct __align__(16) WarpMem {
   unsigned cnt[TC / 4];                   // dependency counts, four cells per word: 0..8, 0xFE = evaluated, 0xFF = not a node
   double theta[DINF ? RH + 2 : 2];        // D-infinity: prop()'s row angle for every ring row
   double dxr[DINF ? TS : 2];              // D-infinity: cell size of every tile row
-  unsigned short wq[TC];                  // ready cells (every cell enters at most once)
+  unsigned short stk[DINF ? STKCAP : 4];  // D-infinity: second receivers that became ready (what does not fit is found again by a rescan of the counts)
   unsigned short ext[EXTCAP];             // receivers outside the tile (ring index)
   unsigned evmask[TS];                    // per tile row: cells evaluated by this visit
-  int qtail, next, dirty, pad;
+  int sp, next, dirty, pad;
 };
-template <bool DINF> constexpr int workers_per_cta() { return DINF ? 12 : 16; }
+template <bool DINF> constexpr int workers_per_cta() { return DINF ? 14 : 22; }
 
 struct WArgs {
   const unsigned short* node;
@@ -69,7 +75,9 @@ struct WArgs {
   int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;
-  unsigned long long* ctr; // [0] head, [1] tail, [2] pending (queued + running tiles), [3] visits, [4..7] cycle statistics
+  PropRow prop;            // D-infinity: the strip's prop() table (prop.uniform) — else per-row angles from `theta`
+  unsigned long long* ctr; // scheduler words, one 128-byte line each (C_HEAD ...): every worker hammers them
+  unsigned long long* stat;// [3] visits, [4..7] cycle statistics (TAUDEM_B200_TIMING)
   int stats;
 };
 
@@ -91,24 +99,25 @@ __device__ __forceinline__ void cp_wait_all() {}
 
 // ---- scheduler (the protocol of the first-generation tile kernel, one lane per worker)
 __device__ void sched_push(const WArgs& a, int t) {
-  atomicAdd(a.ctr + 2, 1ull);
-  const unsigned long long slot = atomicAdd(a.ctr + 1, 1ull);
+  atomicAdd(a.ctr + C_PEND, 1ull);
+  const unsigned long long slot = atomicAdd(a.ctr + C_TAIL, 1ull);
   int* q = a.tq + (slot & a.qmask);
   while (atomicCAS(q, 0, t + 1) != 0) {}
 }
 __device__ void sched_activate(const WArgs& a, int t) {
   for (;;) {
-    const int st = ldv(a.state + t);
+    const int st = atomicCAS(a.state + t, 0, 1);            // idle -> queued (the common case: one round trip)
+    if (st == 0) { sched_push(a, t); return; }
     if (st == 1 || st == 3) return;
-    if (st == 0) { if (atomicCAS(a.state + t, 0, 1) == 0) { sched_push(a, t); return; } }
-    else if (atomicCAS(a.state + t, 2, 3) == 2) return;
+    if (atomicCAS(a.state + t, 2, 3) == 2) return;         // running -> running + re-activated
   }
 }
 // Ticket h is served by the h-th push; a worker whose ticket is never served leaves when no tile is queued or running.
+// A waiting worker polls its own slot (a word nobody else polls); the shared "pending" word only every 16th time.
 __device__ int sched_pop(const WArgs& a) {
-  const unsigned long long h = atomicAdd(a.ctr, 1ull);
+  const unsigned long long h = atomicAdd(a.ctr + C_HEAD, 1ull);
   int* q = a.tq + (h & a.qmask);
-  unsigned ns = 32;
+  unsigned ns = 64, n = 0;
   for (;;) {
     const int v = ldv(q);
     if (v != 0) {
@@ -117,22 +126,25 @@ __device__ int sched_pop(const WArgs& a) {
       __threadfence();
       return v - 1;
     }
-    if ((long long)ldv(a.ctr + 2) <= 0) return -1;
+    if ((++n & 15u) == 0u && (long long)ldv(a.ctr + C_PEND) <= 0) return -1;
     __nanosleep(ns);
-    if (ns < 1024) ns <<= 1;
+    if (ns < 2048) ns <<= 1;
   }
 }
 __device__ void sched_finish(const WArgs& a, int t) {
   __threadfence();
   if (atomicCAS(a.state + t, 2, 0) != 2) { atomicExch(a.state + t, 1); sched_push(a, t); }
-  atomicAdd(a.ctr + 2, ~0ull);   // pending -= 1
+  atomicAdd(a.ctr + C_PEND, ~0ull);   // pending -= 1
 }
 
-__global__ void k_wsched_init(int* state, int* tq, unsigned qcap, int ntiles, unsigned long long* ctr) {
+__global__ void k_wsched_init(int* state, int* tq, unsigned qcap, int ntiles, unsigned long long* ctr, unsigned long long* stat) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < qcap) tq[i] = (int)i < ntiles ? (int)i + 1 : 0;
   if ((int)i < ntiles) state[i] = 1;
-  if (i == 0) { ctr[0] = 0; ctr[1] = (unsigned long long)ntiles; ctr[2] = (unsigned long long)ntiles; ctr[3] = ctr[4] = ctr[5] = ctr[6] = ctr[7] = 0; }
+  if (i == 0) {
+    ctr[C_HEAD] = 0; ctr[C_TAIL] = (unsigned long long)ntiles; ctr[C_PEND] = (unsigned long long)ntiles;
+    stat[3] = stat[4] = stat[5] = stat[6] = stat[7] = 0;
+  }
 }
 
 // prop(angle, kk) through the full interval search (the rare path of the D-infinity gather)
@@ -141,8 +153,40 @@ __device__ __noinline__ double wshare_full(float ang, double t, int kk) {
   return o.k1 == kk ? o.p1 : o.p2;
 }
 
+// The share prop(av, kk) of a contributor (angle av, node word nn) for its receiver in direction kk, from the strip's
+// table: the contributor's first receiver k1 (node word) tells the sector of av with one comparison, every branch of
+// prop() / dinf_outflow is then numerator / (sector width), a division by a table constant (div_const).  Angles outside
+// the table's reach return through the interval search.
+__device__ __forceinline__ double wshare_tab(const PropRow& P, float av, unsigned nn, int kk) {
+  const int k1 = (int)((nn >> 8) & 0xfu);
+  const double a = (double)av;
+  if (k1 >= 1 && k1 <= 8 && av >= 0.f) {
+    int j = k1 - 1 + (a >= P.ar[k1] ? 1 : 0);
+    if (k1 == 1 && a >= P.ar[8]) j = a >= P.ar[9] ? 9 : 8;
+    double num; int d;
+    bool ok = true;
+    if (kk == j && j >= 1 && j <= 8) {
+      if (a > P.ar[j]) { num = P.ar[j + 1] - a; d = j; } else { num = a - P.ar[j - 1]; d = j - 1; }
+    } else if (kk == j + 1 && j >= 1 && j <= 7) { num = a - P.ar[j]; d = j; }
+    else if (kk == 1 && j >= 8) {
+      // src/commonLib.cpp:82: direction 1 reached through the wrap, with the float-rounded a - 2 PI
+      const float a1 = (float)(a - 2.0 * TD_PI);
+      const double b = (double)a1;
+      ok = a1 > P.ar[0] && a1 < P.ar[2];
+      if (a1 > P.ar[1]) { num = P.ar[2] - b; d = 1; } else { num = b - P.ar[0]; d = 0; }
+    } else { ok = false; num = 0.; d = 0; }
+    if (ok) return P.safe ? div_const(num, P.den[d], P.rden[d]) : num / P.den[d];
+  }
+  return wshare_full(av, P.ar[2], kk);
+}
+
 // bit 7 of every byte of the result is set exactly where that byte of w is zero (no borrow between bytes)
 __device__ __forceinline__ unsigned zero_bytes(unsigned w) { return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; }
+// bit i of the result: byte i of w is zero
+__device__ __forceinline__ unsigned zero_nibble(unsigned w) {
+  const unsigned z = zero_bytes(w);
+  return ((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u);
+}
 
 template <bool DINF>
 __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(const WArgs a) {
@@ -152,6 +196,11 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
   const int lane = (int)(threadIdx.x & 31u), wid = (int)(threadIdx.x >> 5);
   const unsigned lt = (1u << lane) - 1u;
   Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
+  __shared__ PropRow sprop;
+  if (DINF) {
+    if (threadIdx.x == 0) sprop = a.prop;
+    __syncthreads();
+  }
 
   for (;;) {
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
@@ -176,7 +225,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       dst[0] = qa; dst[1] = qb;
       M.evmask[lane] = 0u;
     }
-    if (lane == 0) { M.qtail = 0; M.next = 0; M.dirty = 0; }
+    if (lane == 0) { M.sp = 0; M.next = 0; M.dirty = 0; }
     __threadfence();          // the counts first, then the areas they announce (loaded by other lanes: barrier in between)
     __syncwarp();
     // ---- 2. areas (+ node words, angles) of the tile and its ring: asynchronous 16-byte copies straight into shared memory,
@@ -192,7 +241,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
           const long long g = s.idx(r, c);
           cp16(M.area + so, a.area + g);
           if (DINF) cp16(M.ang + so, a.ang + g);
-          if (DINF || (rr >= 1 && rr <= TS && q >= 1 && q <= TS / 4)) cp8(M.node + so, a.node + g);
+          cp8(M.node + so, a.node + g);
         } else {
           *reinterpret_cast<float4*>(M.area + so) = make_float4(-1.f, -1.f, -1.f, -1.f);
           if (DINF) *reinterpret_cast<float4*>(M.ang + so) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -205,44 +254,40 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       for (int i = lane; i < RH; i += 32) M.theta[i] = a.theta[min(max(r0 - 2 + i, 0), s.ny - 1)];
       M.dxr[lane] = a.dxc[min(r0 + lane, s.ny) - 1];
     }
-    // ---- 3. cells that are ready (count 0): lane = tile row
-    {
-      int n = 0;
+    // ---- 3. cells that are ready (count 0): every lane keeps the ready cells of its own tile row as a bit mask
+    unsigned rdy = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) n += __popc(zero_bytes(g0[j]));
-      int incl = n;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-      int pos = incl - n;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        unsigned z = zero_bytes(g0[j]);
-        while (z) {
-          const int b = (__ffs(z) - 1) >> 3;
-          z &= z - 1;
-          M.wq[pos++] = (unsigned short)(lane * TS + 4 * j + b);
-        }
-      }
-      const int total = __shfl_sync(FULL, incl, 31);
-      if (lane == 0) M.qtail = total;
-    }
+    for (int j = 0; j < 8; ++j) rdy |= zero_nibble(g0[j]) << (4 * j);
     cp_wait_all();
     __syncwarp();
     if (a.stats && lane == 0) tk2 = clock64();
 
-    // ---- 4. the wavefront inside the tile: one chain per lane, refilled from the warp's queue
-    int qhead = 0;                 // warp-uniform
+    // ---- 4. the wavefront inside the tile: one chain per lane; an idle lane goes on with the next ready cell of its own
+    //         row, then (D-infinity) with a cell from the warp's fork stack
     int cur = -1;
     for (;;) {
-      const unsigned idle = __ballot_sync(FULL, cur < 0);
-      if (idle) {
-        const int avail = ldv(&M.qtail) - qhead;
-        const int take = min(__popc(idle), avail);
-        const int rank = __popc(idle & lt);
-        if (cur < 0 && rank < take) cur = M.wq[qhead + rank];
-        qhead += take;
+      if (cur < 0 && rdy) { const int b = __ffs(rdy) - 1; rdy &= rdy - 1; cur = lane * TS + b; }
+      if (DINF) {
+        const unsigned idle = __ballot_sync(FULL, cur < 0);
+        if (idle) {
+          const int n = min(ldv(&M.sp), STKCAP);
+          if (n > 0) {
+            const int take = min(__popc(idle), n);
+            const int rank = __popc(idle & lt);
+            if (cur < 0 && rank < take) cur = M.stk[n - 1 - rank];
+            __syncwarp();
+            if (lane == 0) M.sp = n - take;
+          }
+        }
       }
-      if (__ballot_sync(FULL, cur >= 0) == 0u) break;
+      if (__ballot_sync(FULL, cur >= 0) == 0u) {
+        if (!DINF) break;
+        // forks that did not fit the stack are still ready (count 0) in shared memory: look once more
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rdy |= zero_nibble(M.cnt[lane * 8 + j]) << (4 * j);
+        if (__ballot_sync(FULL, rdy != 0u) == 0u) break;
+        continue;
+      }
       if (cur >= 0) {
         const int l = cur;
         const int lr = l >> 5, lx = l & 31;
@@ -270,24 +315,28 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
           // takes the full interval search.
           const int r = r0 + lr;
           val = 0.f;
-#pragma unroll
-          for (int k = 1; k <= 8; ++k)
-            if (msk & (1u << (k - 1))) {
-              const int ni = ri + drow(k) * RS + dcol(k);
-              const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
-              const int rn = r + drow(k);
-              const double th = M.theta[lr + 1 + drow(k)];
-              const unsigned nn = M.node[ni];
-              const float av = M.ang[ni];
+#pragma unroll 1
+          for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
+            const int k = __ffs(m);
+            const int dr = drow(k), dc = dcol(k);
+            const int ni = ri + dr * RS + dc;
+            const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
+            const int rn = r + dr;
+            const unsigned nn = M.node[ni];
+            const float av = M.ang[ni];
+            const float an = M.area[ni];
+            double p;
+            if (sprop.uniform && rn >= 1 && rn <= s.ny) p = wshare_tab(sprop, av, nn, kk);
+            else {
+              const double th = M.theta[lr + 1 + dr];
               const int k1n = (nn >> 8) & 0xf;
-              double p;
               if ((nn & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
                 const double mid = aref(k1n, th), hi = aref(k1n + 1, th);
                 p = (kk == k1n) ? (hi - av) / (hi - mid) : (av - mid) / (hi - mid);
               } else p = wshare_full(av, th, kk);
-              const float an = M.area[ni];
-              if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
             }
+            if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
+          }
           if (a.usew) val = val + a.w[s.idx(r, c0 + lx)];
           else val = (float)((double)val + M.dxr[lr]);
         }
@@ -310,7 +359,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
             const unsigned old = atomicSub(&M.cnt[l2 >> 2], 1u << sh);
             if (((old >> sh) & 0xffu) == 1u) {
               if (cont < 0) cont = l2;
-              else M.wq[atomicAdd(&M.qtail, 1)] = (unsigned short)l2;   // a second ready receiver: an idle lane takes it
+              else { const int slot = atomicAdd(&M.sp, 1); if (slot < STKCAP) M.stk[slot] = (unsigned short)l2; }   // a second ready receiver: an idle lane takes it
             }
           } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
             M.ext[atomicAdd(&M.next, 1)] = (unsigned short)((nlr + 1) * RS + nlx + 4);
@@ -364,7 +413,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       const int r = r0 - 1 + rr, c = c0 - 4 + rc;
       if (r == 0 || r == s.ny + 1) { atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1); continue; }
       const long long ci = s.idx(r, c);
-      const unsigned ndr = DINF ? (unsigned)M.node[code] : (unsigned)a.node[ci];
+      const unsigned ndr = (unsigned)M.node[code];
       if (!(ndr & NODE_VALID)) continue;
       const unsigned sh = (unsigned)(ci & 3) * 8u;
       const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - (1u << sh));
@@ -376,11 +425,11 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       sched_finish(a, t);
       if (a.stats) {
         const long long tk4 = clock64();
-        atomicAdd(a.ctr + 3, 1ull);
-        atomicAdd(a.ctr + 4, (unsigned long long)(tk1 - tk0));
-        atomicAdd(a.ctr + 5, (unsigned long long)(tk2 - tk1));
-        atomicAdd(a.ctr + 6, (unsigned long long)(tk3 - tk2));
-        atomicAdd(a.ctr + 7, (unsigned long long)(tk4 - tk3));
+        atomicAdd(a.stat + 3, 1ull);
+        atomicAdd(a.stat + 4, (unsigned long long)(tk1 - tk0));
+        atomicAdd(a.stat + 5, (unsigned long long)(tk2 - tk1));
+        atomicAdd(a.stat + 6, (unsigned long long)(tk3 - tk2));
+        atomicAdd(a.stat + 7, (unsigned long long)(tk4 - tk3));
       }
     }
     __syncwarp();
@@ -408,7 +457,7 @@ __global__ void k_wapply_halo(WArgs a, const int* __restrict__ dec_top, const in
   }
 }
 
-__global__ void k_wsched_reset(unsigned long long* ctr) { ctr[0] = ctr[1] = ctr[2] = 0; }
+__global__ void k_wsched_reset(unsigned long long* ctr) { ctr[C_HEAD] = ctr[C_TAIL] = ctr[C_PEND] = 0; }
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
@@ -423,7 +472,9 @@ int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.state = ctx->tileflags.as<int>();
   a.tq = a.state + nt;
   a.qmask = qcap - 1;
-  a.ctr = ctx->d_ctr + 24;
+  TD_CUDA(ctx->wsched.ensure(64 * sizeof(unsigned long long)));
+  a.ctr = ctx->wsched.as<unsigned long long>();
+  a.stat = ctx->d_ctr + 24;
   a.node = ctx->node.as<unsigned short>();
   a.cntw = ctx->cnt.as<unsigned>();
   return TD_OK;
@@ -435,7 +486,7 @@ int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   const int nt = a.ntx * a.nty;
-  k_wsched_init<<<(a.qmask + 1 + 255) / 256, 256, 0, st>>>(a.state, a.tq, a.qmask + 1, nt, a.ctr);
+  k_wsched_init<<<(a.qmask + 1 + 255) / 256, 256, 0, st>>>(a.state, a.tq, a.qmask + 1, nt, a.ctr, a.stat);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;
@@ -461,6 +512,8 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   if (int rc = wargs(ctx, a, s)) return rc;
   a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
   a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+  a.prop = ctx->prop;
+  if (!dinf) a.prop.uniform = 0;
   const char* te = getenv("TAUDEM_B200_TIMING");
   a.stats = (te && atoi(te) > 0) ? 1 : 0;
   const int warps = dinf ? workers_per_cta<true>() : workers_per_cta<false>();

@@ -449,6 +449,11 @@ def bench_main(args, rank, world, local):
     dist.all_reduce(launches)
     mx = torch.stack([s.owned(ad8).max(), s.owned(sca).max()]).double()
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    # 64-bit hashes of the raw bits of the whole rasters: the strips' position-weighted sums add up (mod 2^64)
+    to_i64 = lambda h: h - (1 << 64) if h >= (1 << 63) else h
+    hs = torch.tensor([to_i64(B.raster_hash(torch, s.owned(ad8), D.row0, n)), to_i64(B.raster_hash(torch, s.owned(sca), D.row0, n))], device=dev, dtype=torch.int64)
+    dist.all_reduce(hs)
+    hashes = ["%016x" % (int(v) & ((1 << 64) - 1)) for v in hs.tolist()]
     ms_per_step = float(ms.item()) / args.steps
     value = cells / 1e6 / (ms_per_step * 1e-3)
 
@@ -478,7 +483,8 @@ def bench_main(args, rank, world, local):
                 "config": {"workload": f"aread8 + areadinf on {n}x{n} float32 synthetic fractal DEM (hills: H={B.HURST}, tilt={B.TILT}, seed={B.SEED}, 30 m cells), contamination check on, no weights",
                            "cells": cells, "partition": f"{world} row strips (linearpart: total//size rows, remainder on the last rank); " + ("peer mode: the sweep kernels deliver across GPUs over NVLink (CUDA IPC, system-scope atomics), no exchange rounds" if D.peer else "NCCL send/recv halo + decrement exchange rounds, all_reduce termination"),
                            "exchange_rounds": {"aread8": rounds[0], "areadinf": rounds[1]}, "l2": "inputs exceed the 126 MB L2; no explicit flush",
-                           "timed": "CUDA events per rank, max over ranks", "max_ad8": float(mx[0]), "max_sca": float(mx[1]), **info},
+                           "timed": "CUDA events per rank, max over ranks", "max_ad8": float(mx[0]), "max_sca": float(mx[1]),
+                           "hash_ad8": hashes[0], "hash_sca": hashes[1], **info},
                 "clocks": clk.summary(),
                 "e2e": {"value": round(cells / 1e6 / float(te.item()), 2), "unit": "Mcells/s", "h2d_bytes_per_step": cells * 6, "d2h_bytes_per_step": cells * 8,
                         "steps": e2e_steps, "ms_per_step": round(float(te.item()) * 1e3, 2), "api": "per-rank pinned host strips -> device strips -> DistTools.aread8/areadinf -> pinned host strips"},

@@ -18,7 +18,7 @@ td_ctx::td_ctx() { d_ctr = (unsigned long long*)calloc(32, 8); h_ctr = (unsigned
 td_ctx::~td_ctx() {
   free(d_ctr); free(h_ctr);
   node.p = cnt.p = nullptr;       // owned by the caller below
-  listA.release(); listB.release(); listC.release(); lev.release(); mk.release(); halo.release(); tileflags.release();
+  listA.release(); listB.release(); listC.release(); lev.release(); mk.release(); halo.release(); tileflags.release(); wsched.release(); rowfact.release();
 }
 
 using td::Strip;

@@ -31,6 +31,7 @@ extern "C" int emu_wtiles(int dinf, const void* dir, float* out, const float* wg
   td_ctx ctx;
   ctx.node.p = node.data(); ctx.node.cap = node.size() * 2;
   ctx.cnt.p = cnt.data(); ctx.cnt.cap = cnt.size();
+  td::make_prop_row(theta[0], true, &ctx.prop);
   std::vector<int> halo(2 * (size_t)s.pitch, 0);
   int rc = td::wsweep_begin(&ctx, s, nullptr);
   if (!rc) rc = td::wsweep_run(&ctx, dinf != 0, area.data(), usew ? w.data() : nullptr, ang.data(), s, w_nodata, usew, contcheck, theta.data(),

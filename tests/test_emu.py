@@ -410,6 +410,14 @@ def test_emulated_warp_tile_sweep(emu, fields):
     assert_bits(_wtiles(emu, True, ang, w, False, 105)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc warp tiles")
 
 
+def test_emulated_warp_tile_sweep_fork_stack_overflow(fields):
+    """A two-entry fork stack drops nearly every second receiver: the rescan of the shared-memory counts must find them."""
+    port, _, ang, w = fields
+    lib = _build("_wstk2", defines=("TD_WSTK=2",))
+    assert_bits(_wtiles(lib, True, ang, None, True, 121)[0], port.areadinf(ang), "sca, fork stack of 2")
+    assert_bits(_wtiles(lib, True, ang, w, False, 122)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc, fork stack of 2")
+
+
 def test_emulated_warp_tile_sweep_golden(emu):
     """... and on the reference-generated golden vectors (nodata holes, dx != dy, plateau, lake, 5 x 7 grid)."""
     from util import golden_cases, load_golden
