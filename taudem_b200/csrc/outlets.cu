@@ -7,8 +7,11 @@
 // counts for the whole strip; k_upstream floods the contributor links from the outlets (one cell per lane, the
 // warp's stack holds the discovered contributors, overflow spills to a list the host drains with another launch —
 // the structure of k_walk) and k_restrict turns everything that was not reached into "not a cell of the flow
-// field" (node 0, count 0xFF), after which the ordinary sweep runs.  An outlet on a cell without a valid flow
-// direction is ignored (the reference evaluates it with a warning; src/aread8.cpp:274-276).
+// field" (node 0, count 0xFF), after which the ordinary sweep runs.  An outlet on a cell WITHOUT a valid flow direction
+// (nodata direction: every D8 edge cell) is handled like the reference does (src/commonLib.cpp:319-343 never looks at
+// the outlet's own direction; src/aread8.cpp:274-276 evaluates it with a warning): the cell becomes a node of the flow
+// field with the contributors its neighbours' directions give it and no receiver, its contributors are flooded, and the
+// sweep evaluates it (contaminated if a neighbour is off the grid or has no direction).
 #include <algorithm>
 #include <vector>
 
@@ -32,6 +35,8 @@ struct UpArgs {
   long long* spill;
   unsigned long long spill_cap;
   int* req;                   // row strips: req[c] = 1 asks the strip above to continue at (its last row, c), req[pitch + c] the strip below
+  unsigned char* cnt;         // dependency counts (written for outlets on cells without a flow direction)
+  int adopt;                  // this launch's list holds outlet cells: cells without a valid direction are adopted as nodes
 };
 
 __global__ void __launch_bounds__(256) k_upstream(const UpArgs a) {
@@ -67,7 +72,26 @@ __global__ void __launch_bounds__(256) k_upstream(const UpArgs a) {
     if (cur >= 0) {
       unsigned* word = reinterpret_cast<unsigned*>(a.node) + (cur >> 1);
       const unsigned sh = (unsigned)(cur & 1) * 16u;
-      const unsigned nd = (atomicOr(word, IN_SET << sh) >> sh) & 0xffffu;
+      unsigned nd = (atomicOr(word, IN_SET << sh) >> sh) & 0xffffu;
+      if (a.adopt && !(nd & UP_VALID) && !(nd & IN_SET)) {
+        // an outlet on a cell without a flow direction: which neighbours drain into it (their first / second receiver
+        // points here), is any of them missing (off the grid / no direction -> the cell is contaminated)
+        const int r = (int)(cur / s.pitch), c = (int)(cur - (long long)r * s.pitch);
+        unsigned mask = 0, con = 0;
+#pragma unroll
+        for (int k = 1; k <= 8; ++k) {
+          const int rn = r + drow(k), cn = c + dcol(k);
+          unsigned nn = 0;
+          if (s.on_grid(rn, cn) && rn >= 1 && rn <= s.ny) nn = a.node[s.idx(rn, cn)];
+          if (!(nn & UP_VALID)) { con = 1; continue; }
+          const int back = k > 4 ? k - 4 : k + 4;
+          const int k1 = (int)((nn >> 8) & 0xfu), k2 = (nn & 0x2000u) ? k1 % 8 + 1 : 0;
+          if (k1 == back || k2 == back) mask |= 1u << (k - 1);
+        }
+        nd = UP_VALID | (con ? 0x1000u : 0u) | mask;            // receiver field 0: nothing downstream of it is decremented
+        atomicOr(word, nd << sh);
+        a.cnt[cur] = (unsigned char)__popc(mask);
+      }
       if ((nd & UP_VALID) && !(nd & IN_SET)) {
 #pragma unroll
         for (int k = 1; k <= 8; ++k)
@@ -139,6 +163,7 @@ int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int
   if (n) TD_CUDA(cudaMemcpyAsync(ctx->listA.p, cells.data(), sizeof(long long) * n, cudaMemcpyHostToDevice, st));
   UpArgs a;
   a.node = ctx->node.as<unsigned short>(); a.s = s; a.ctr = ctx->d_ctr + 16; a.spill_cap = cap; a.req = req_out;
+  a.cnt = ctx->cnt.as<unsigned char>(); a.adopt = 1;
   unsigned long long* hc = ctx->h_ctr + 16;
   if (req_out) TD_CUDA(cudaMemsetAsync(req_out, 0, sizeof(int) * 2 * (size_t)s.pitch, st));
   if (in_top || in_bot) {
@@ -166,6 +191,7 @@ int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int
     if (hc[2]) { set_error("outlets: spill list exhausted"); return TD_ERR_ALLOC; }
     n = hc[1];
     cur = spill; std::swap(spill, other);
+    a.adopt = 0;
   }
   if (finish) {
     const dim3 rgrid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));

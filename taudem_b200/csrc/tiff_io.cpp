@@ -1,6 +1,7 @@
 // Native TIFF / BigTIFF raster I/O (see tiff_io.h for the reference contract).
 #include "tiff_io.h"
 
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -238,6 +239,10 @@ bool Raster::open(const std::string& path, std::string* err) {
   if (big_) { uint64_t v; if (!pread_all(fp_, ifd_off, &v, 8)) { *err = "bad IFD"; return false; } nent = swap_ ? bswap64(v) : v; ifd_off += 8; }
   else { uint16_t v; if (!pread_all(fp_, ifd_off, &v, 2)) { *err = "bad IFD"; return false; } nent = swap_ ? bswap16(v) : v; ifd_off += 2; }
   const int esz = big_ ? 20 : 12;
+  // nothing in the file's own tables is trusted: every table must lie inside the file
+  uint64_t fsize = 0;
+  { struct stat sb; if (fstat(fileno(fp_), &sb) != 0) { *err = "cannot stat file"; return false; } fsize = (uint64_t)sb.st_size; }
+  if (nent == 0 || nent > 65536 || ifd_off > fsize || nent * esz > fsize - ifd_off) { *err = "bad IFD (entry table outside the file)"; return false; }
   std::vector<uint8_t> ents(nent * esz);
   if (!pread_all(fp_, ifd_off, ents.data(), ents.size())) { *err = "bad IFD"; return false; }
 
@@ -250,7 +255,9 @@ bool Raster::open(const std::string& path, std::string* err) {
     if (big_) { memcpy(&count, p + 4, 8); if (swap_) count = bswap64(count); }
     else { uint32_t c; memcpy(&c, p + 4, 4); if (swap_) c = bswap32(c); count = c; }
     if (type == 0 || type > 18 || kTypeSize[type] == 0) continue;
+    if (count > fsize) { *err = "bad tag (count exceeds the file size)"; return false; }
     const uint64_t nbytes = count * kTypeSize[type];
+    if (nbytes > fsize) { *err = "bad tag (data exceeds the file size)"; return false; }
     RawTag rt; rt.type = type; rt.count = count; rt.data.resize(nbytes);
     const int inl = big_ ? 8 : 4;
     const uint8_t* vp = p + (big_ ? 12 : 8);
@@ -259,7 +266,7 @@ bool Raster::open(const std::string& path, std::string* err) {
       uint64_t off;
       if (big_) { memcpy(&off, vp, 8); if (swap_) off = bswap64(off); }
       else { uint32_t o; memcpy(&o, vp, 4); if (swap_) o = bswap32(o); off = o; }
-      if (!pread_all(fp_, off, rt.data.data(), nbytes)) { *err = "bad tag data"; return false; }
+      if (off > fsize || nbytes > fsize - off || !pread_all(fp_, off, rt.data.data(), nbytes)) { *err = "bad tag data"; return false; }
     }
     if (swap_) swap_elems(rt.data.data(), (type == 5 || type == 10) ? count * 2 : count,
                           (type == 5 || type == 10) ? 4 : kTypeSize[type]);
@@ -276,7 +283,9 @@ bool Raster::open(const std::string& path, std::string* err) {
   if (!(compression_ == 1 || compression_ == 5 || compression_ == 8 || compression_ == 32946)) { *err = "unsupported compression " + std::to_string(compression_); return false; }
   if (tags.count(322)) {
     tiled_ = true; block_w_ = (uint32_t)geti(322, 0); block_h_ = (uint32_t)geti(323, 0);
+    if (!tags.count(324) || !tags.count(325)) { *err = "no tile offsets / byte counts"; return false; }
     const RawTag &o = tags[324], &c = tags[325];
+    if (c.count < o.count) { *err = "fewer tile byte counts than tile offsets"; return false; }
     for (uint64_t i = 0; i < o.count; i++) { offsets_.push_back(tag_u64(o, i)); counts_.push_back(tag_u64(c, i)); }
   } else {
     tiled_ = false; block_w_ = width_;
@@ -285,10 +294,27 @@ bool Raster::open(const std::string& path, std::string* err) {
     if (!tags.count(273)) { *err = "no strip offsets"; return false; }
     const RawTag& o = tags[273];
     for (uint64_t i = 0; i < o.count; i++) offsets_.push_back(tag_u64(o, i));
-    if (tags.count(279)) { const RawTag& c = tags[279]; for (uint64_t i = 0; i < c.count; i++) counts_.push_back(tag_u64(c, i)); }
+    if (tags.count(279)) {
+      const RawTag& c = tags[279];
+      if (c.count < o.count) { *err = "fewer strip byte counts than strip offsets"; return false; }
+      for (uint64_t i = 0; i < o.count; i++) counts_.push_back(tag_u64(c, i));
+    }
     else for (uint64_t i = 0; i < o.count; i++) counts_.push_back((uint64_t)block_h_ * width_ * (bits_ / 8));
   }
   if (block_w_ == 0 || block_h_ == 0) { *err = "bad block size"; return false; }
+  {
+    // every block the raster needs must exist and lie inside the file (extra blocks are ignored)
+    const uint64_t bx = ((uint64_t)width_ + block_w_ - 1) / block_w_, by = ((uint64_t)height_ + block_h_ - 1) / block_h_;
+    const uint64_t need = tiled_ ? bx * by : by;
+    if (offsets_.size() < need || counts_.size() < need) { *err = "block tables are shorter than the raster needs"; return false; }
+    for (uint64_t i = 0; i < need; i++)
+      if (offsets_[i] > fsize || counts_[i] > fsize - offsets_[i]) { *err = "block " + std::to_string(i) + " lies outside the file"; return false; }
+    offsets_.resize(need); counts_.resize(need);
+    if ((uint64_t)block_w_ * block_h_ * (bits_ / 8) > (1ull << 32)) { *err = "unreasonable block size"; return false; }
+  }
+  if (predictor_ == 2 && bits_ == 64) { *err = "horizontal predictor with 64-bit samples is not supported"; return false; }
+  if (predictor_ == 3 && !(sample_format_ == 3 && (bits_ == 32 || bits_ == 64))) { *err = "floating point predictor on a non-float raster"; return false; }
+  if (!(predictor_ == 1 || predictor_ == 2 || predictor_ == 3)) { *err = "unsupported predictor " + std::to_string(predictor_); return false; }
 
   // nodata (GDAL_NODATA, ASCII)
   if (tags.count(42113)) {
@@ -441,9 +467,9 @@ bool Raster::read(long xstart, long ystart, long nrows, long ncols, void* dest, 
       if (direct) {
         const long r0 = std::max<long>(ystart, by * (long)block_h_), r1 = std::min<long>(ystart + nrows, (by + 1) * (long)block_h_);
         const size_t rowb = (size_t)width_ * sb;
-        const uint64_t off = offsets_[(size_t)by] + (uint64_t)(r0 - by * (long)block_h_) * rowb;
+        const uint64_t off = ((size_t)by < offsets_.size() ? offsets_[(size_t)by] : 0) + (uint64_t)(r0 - by * (long)block_h_) * rowb;
         const size_t want = (size_t)(r1 - r0) * rowb;
-        if ((uint64_t)(r1 - by * (long)block_h_) * rowb > counts_[(size_t)by] ||
+        if ((size_t)by >= offsets_.size() || (uint64_t)(r1 - by * (long)block_h_) * rowb > counts_[(size_t)by] ||
             !pread_all(fp_, off, (uint8_t*)dest + (size_t)(r0 - ystart) * rowb, want)) {
           std::lock_guard<std::mutex> g(emu);
           if (!failed.exchange(true)) *err = "short read of raster block";

@@ -105,7 +105,7 @@ int td_nameadd(char* full, const char* arg, const char* suff) {
 }
 
 int td_raster_info(const char* path, int* nx, int* ny, double* nodata, int* has_nodata, double* dx, double* dy, int* is_geographic,
-                   int* bits, int* sample_format) {
+                   int* bits, int* sample_format) try {
   tdio::Raster r; std::string err;
   if (!r.open(path, &err)) { td::set_error(err); return TD_ERR_IO; }
   if (nx) *nx = (int)r.width();
@@ -118,24 +118,36 @@ int td_raster_info(const char* path, int* nx, int* ny, double* nodata, int* has_
   if (bits) *bits = r.bits();
   if (sample_format) *sample_format = r.sample_format();
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
-int td_raster_read(const char* path, int dtype, void* dest, int nx, int ny) {
+int td_raster_read(const char* path, int dtype, void* dest, int nx, int ny) try {
   tdio::Raster r; std::string err;
   if (!r.open(path, &err)) { td::set_error(err); return TD_ERR_IO; }
   if ((int)r.width() != nx || (int)r.height() != ny) { td::set_error("td_raster_read: size mismatch"); return TD_ERR_ARG; }
   if (!r.read(0, 0, ny, nx, dest, (tdio::DType)dtype, &err)) { td::set_error(err); return TD_ERR_IO; }
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
-int td_raster_cell_sizes(const char* path, double* dxc, double* dyc, int ny) {
+int td_raster_cell_sizes(const char* path, double* dxc, double* dyc, int ny) try {
   tdio::Raster r; std::string err;
   if (!r.open(path, &err)) { td::set_error(err); return TD_ERR_IO; }
   if ((int)r.height() != ny) { td::set_error("td_raster_cell_sizes: size mismatch"); return TD_ERR_ARG; }
   std::vector<double> x, y; r.cell_sizes(&x, &y);
   memcpy(dxc, x.data(), sizeof(double) * ny); memcpy(dyc, y.data(), sizeof(double) * ny);
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
 int td_raster_write(const char* path, int dtype, const void* src, int nx, int ny, double nodata, const char* like_path, double dx,
-                    double dy, int compression) {
+                    double dy, int compression) try {
   tdio::GeoInfo geo; std::string err;
   if (like_path) {
     tdio::Raster r;
@@ -151,10 +163,14 @@ int td_raster_write(const char* path, int dtype, const void* src, int nx, int ny
     td::set_error(err); return TD_ERR_IO;
   }
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
 
 int td_flood(const char* demfile, const char* felfile, const char* sfdrfile, int usesfdr, int verbose, int is_4Point, int use_mask,
-             const char* maskfile) {
+             const char* maskfile) try {
   (void)sfdrfile; (void)usesfdr;     // not implemented by the reference either (src/PitRemovemn.cpp:143)
   printf("PitRemove version %s\n", td_version());
   fflush(stdout);
@@ -193,9 +209,13 @@ int td_flood(const char* demfile, const char* felfile, const char* sfdrfile, int
          t3 - t2, t4 - t3, t4 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
 
-int td_setdird8(const char* demfile, const char* pointfile, const char* slopefile, const char* flowfile, int useflowfile) {
+int td_setdird8(const char* demfile, const char* pointfile, const char* slopefile, const char* flowfile, int useflowfile) try {
   (void)flowfile; (void)useflowfile;   // -sfdr is accepted and functionally dead in the reference (src/d8.cpp:243-267)
   printf("D8FlowDir version %s\n", td_version());
   fflush(stdout);
@@ -222,9 +242,13 @@ int td_setdird8(const char* demfile, const char* pointfile, const char* slopefil
          t1 - t0, t2 - t1, t3 - t2, t4 - t3, 0.0, t5 - t4, t5 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
 
-int td_setdir(const char* demfile, const char* angfile, const char* slopefile, const char* flowfile, int useflowfile) {
+int td_setdir(const char* demfile, const char* angfile, const char* slopefile, const char* flowfile, int useflowfile) try {
   (void)flowfile; (void)useflowfile;
   printf("DinfFlowDir version %s\n", td_version());
   fflush(stdout);
@@ -251,6 +275,10 @@ int td_setdir(const char* demfile, const char* angfile, const char* slopefile, c
          t1 - t0, t2 - t1, t3 - t2, t4 - t3, 0.0, t5 - t4, t5 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
 
 // readoutlets + geoToGlobalXY (src/aread8.cpp:112-120,179-188, src/tiffIO.cpp:580-588): outlet points -> grid cells
@@ -271,7 +299,7 @@ static int outlet_cells(const char* datasrc, const char* lyrname, int uselyrname
 }
 
 int td_aread8(const char* pfile, const char* afile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, const char* wfile,
-              int useOutlets, int usew, int contcheck) {
+              int useOutlets, int usew, int contcheck) try {
   {  // src/aread8.cpp:62-71
     FILE* fp = fopen(pfile, "r");
     if (!fp) { fprintf(stderr, "Error: Input file %s does not exist.\n", pfile); td::set_error("input file does not exist"); return TD_ERR_IO; }
@@ -307,10 +335,14 @@ int td_aread8(const char* pfile, const char* afile, const char* datasrc, const c
   printf("Number of Processes: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
 
 int td_area(const char* angfile, const char* scafile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, const char* wfile,
-            int useOutlets, int usew, int contcheck) {
+            int useOutlets, int usew, int contcheck) try {
   printf("AreaDinf version %s\n", td_version());
   const double t0 = now();
   Input a;
@@ -341,6 +373,10 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
   printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());
   return TD_OK;
+} catch (const std::exception& e) {
+  // a malformed file (or an allocation failure) must not unwind through the C ABI
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
 }
 
 }  // extern "C"

@@ -91,6 +91,44 @@ def test_bigtiff_and_geotags_passthrough(tmp_path):
     assert (i1["dx"], i1["dy"]) == (i2["dx"], i2["dy"]) == (0.001, 0.002)
 
 
+def test_malformed_tiffs_are_rejected_not_trusted(tmp_path):
+    """The parser trusts nothing in the file's own tables: truncated files, byte-count tables shorter than the
+    offset tables, blocks that point outside the file and absurd counts return TD_ERR_IO through the C ABI."""
+    import struct
+    good = str(tmp_path / "good.tif")
+    arr = (np.arange(40 * 30, dtype=np.float32).reshape(30, 40))
+    td.write_raster(good, arr, -9999.0)
+    raw = bytearray(open(good, "rb").read())
+    assert np.array_equal(td.read_raster(good), arr)
+
+    def variant(name, mutate):
+        b = bytearray(raw)
+        mutate(b)
+        path = str(tmp_path / name)
+        open(path, "wb").write(bytes(b))
+        return path
+
+    ifd = struct.unpack("<I", raw[4:8])[0]
+    nent = struct.unpack("<H", raw[ifd:ifd + 2])[0]
+    ents = {struct.unpack("<H", raw[ifd + 2 + 12 * i: ifd + 4 + 12 * i])[0]: ifd + 2 + 12 * i for i in range(nent)}
+    cases = [
+        variant("truncated.tif", lambda b: b.__delitem__(slice(len(b) // 2, None))),
+        variant("ifd_outside.tif", lambda b: b.__setitem__(slice(4, 8), struct.pack("<I", len(b) + 1000))),
+        variant("huge_entry_count.tif", lambda b: b.__setitem__(slice(ifd, ifd + 2), struct.pack("<H", 65535))),
+        variant("huge_tag_count.tif", lambda b: b.__setitem__(slice(ents[273] + 4, ents[273] + 8), struct.pack("<I", 0x7fffffff))),
+        variant("offset_outside.tif", lambda b: b.__setitem__(slice(ents[273] + 8, ents[273] + 12), struct.pack("<I", 0x7ffffff0))
+                if struct.unpack("<I", raw[ents[273] + 4: ents[273] + 8])[0] == 1 else None),
+        variant("zero_width.tif", lambda b: b.__setitem__(slice(ents[256] + 8, ents[256] + 12), struct.pack("<I", 0))),
+    ]
+    for path in cases:
+        if open(path, "rb").read() == bytes(raw):
+            continue
+        with pytest.raises(td.TaudemError):
+            td.read_raster(path)
+        with pytest.raises(td.TaudemError):
+            td.raster_info(path)
+
+
 def test_cli_usage_and_simple_mode_errors():
     bindir = os.path.join(ROOT, "taudem_b200", "bin")
     for tool in ("pitremove", "d8flowdir", "dinfflowdir", "aread8", "areadinf"):
@@ -231,3 +269,16 @@ def test_outlets_reference_pins_the_restatement(refrun, tmp_path):
         assert_bits(R.aread8(p, outlets=shp), port.aread8(p, outlets=(ocols, orows)), f"ad8 -o, {ranks} ranks")
         assert_bits(R.areadinf(ang, outlets=shp), port.areadinf(ang, outlets=(ocols, orows)), f"sca -o, {ranks} ranks")
     assert 100 < int((port.aread8(p, outlets=(ocols, orows)) != -1).sum()) < p.size
+    # an outlet on a grid-edge cell (no flow direction of its own) that interior cells drain into: the reference evaluates it and its
+    # upstream cells (with a warning), and so does the restatement
+    d1 = np.array([0, 1, 1, 0, -1, -1, -1, 0, 1]); d2 = np.array([0, 0, -1, -1, -1, 0, 1, 1, 1])
+    edge = [(r, c) for r in range(ny) for c in (0, nx - 1) for k in range(1, 9)
+            if 0 <= r - d2[k] < ny and 0 <= c - d1[k] < nx and p[r - d2[k], c - d1[k]] == k and not (1 <= p[r, c] <= 8)]
+    er, ec = edge[len(edge) // 2]
+    shp2 = str(tmp_path / "edge_outlet.shp")
+    write_point_shapefile(shp2, [(ec + 0.5) * dx], [dy * ny - (er + 0.5) * dy])
+    R = refrun.RefPipeline(workdir=str(tmp_path), dx=dx, dy=dy, np_ranks=1)
+    for cc in (True, False):
+        ref = R.aread8(p, outlets=shp2, contcheck=cc)
+        assert_bits(ref, port.aread8(p, outlets=([ec], [er]), contcheck=cc), f"ad8 -o on an edge cell, contcheck={cc}")
+    assert int((ref != -1).sum()) > 1

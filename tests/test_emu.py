@@ -292,6 +292,18 @@ def test_emulated_outlets_restrict_the_sweep(emu, fields):
     assert_bits(_run(emu, False, 0, 0, p, w, False, 62, outlets=outs), port.aread8(p, weights=w, contcheck=False, outlets=outs), "ad8 -o -wg -nc")
     assert_bits(_run(emu, True, 1, 3, ang, None, True, 63, outlets=outs), port.areadinf(ang, outlets=outs), "sca -o")
     assert_bits(_run(emu, False, 0, 0, p, None, True, 64, outlets=([], [])), np.full(p.shape, -1.0, np.float32), "ad8 -o without points")
+    # an outlet on a cell WITHOUT a flow direction (a grid-edge cell that interior cells drain into): the reference floods
+    # its contributors and evaluates it (contaminated here: it has off-grid neighbours) — not "ignored"
+    d1 = np.array([0, 1, 1, 0, -1, -1, -1, 0, 1]); d2 = np.array([0, 0, -1, -1, -1, 0, 1, 1, 1])
+    edge = [(r, c) for r in range(ny) for c in (0, nx - 1) for k in range(1, 9)
+            if 0 <= r - d2[k] < ny and 0 <= c - d1[k] < nx and p[r - d2[k], c - d1[k]] == k and not (1 <= p[r, c] <= 8)]
+    assert edge, "the test field has no interior cell draining into an edge cell"
+    er, ec = edge[len(edge) // 2]
+    eo = ([ec], [er])
+    ref_e = port.aread8(p, contcheck=False, outlets=eo)
+    assert int((ref_e != -1).sum()) > 1, "the oracle evaluates the outlet and its upstream cells"
+    assert_bits(_run(emu, False, 0, 0, p, None, False, 67, outlets=eo), ref_e, "ad8 -o -nc, outlet on an edge cell")
+    assert_bits(_run(emu, False, 0, 0, p, None, True, 68, outlets=eo), port.aread8(p, outlets=eo), "ad8 -o, outlet on an edge cell")
     # row strips: the flood crosses the strip boundaries in rounds of requests
     for n in (2, 5):
         assert_bits(_run(emu, False, 1, 3, p, None, True, 65, n, outlets=outs), ref, f"ad8 -o, {n} strips")
