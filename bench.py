@@ -157,22 +157,8 @@ def pick_size(torch, want):
     return 65536 if free > 120e9 else 16384
 
 
-def apply_sweep_spec(spec):
-    """NAME[:passes][+river:cells] -> the environment variables the library reads (capi.cu, sweep_walk.cu)."""
-    if not spec:
-        return
-    base, _, river = spec.partition("+river:")
-    name, _, passes = base.partition(":")
-    os.environ["TAUDEM_B200_SWEEP"] = name
-    for key, val in (("TAUDEM_B200_LEVELS", passes), ("TAUDEM_B200_RIVER", river)):
-        if val:
-            os.environ[key] = val
-        else:
-            os.environ.pop(key, None)
-
-
 def sweep_name():
-    return os.environ.get("TAUDEM_B200_SWEEP", "") or "warp"
+    return "warp-per-tile dataflow (sweep_warp.cu)"
 
 
 def run_size(args, torch, td, T, n, steps, warmup, e2e_steps, log, local):
@@ -418,10 +404,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-same-config", action="store_true", help="skip the additional 16384^2 measurement (the reference arm's configuration)")
     ap.add_argument("--prep", default="", help="write the REF_SIZE direction rasters into this directory and exit (input preparation of the reference arm)")
-    ap.add_argument("--sweep", default=os.environ.get("TAUDEM_B200_SWEEP_SPEC", ""),
-                    help="sweep schedule override for A/B runs (sets TAUDEM_B200_SWEEP)")
     args = ap.parse_args()
-    apply_sweep_spec(args.sweep)
     if args.prep:
         prep(args)
     elif args.impl == "reference":

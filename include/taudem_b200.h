@@ -129,7 +129,7 @@ int td_pitch_for(int nx);        /* smallest legal pitch */
 unsigned long long td_ctx_counter(td_ctx*, int i);
 /* TAUDEM_B200_TIMING=1: milliseconds the last level / walk sweep spent in phase i
  * (0 level passes, 1 ready-list collection, 2 chain walking, 3 rivers); 0 otherwise. */
-double td_ctx_phase_ms(td_ctx*, int i);
+unsigned long long td_ctx_sweep_hist(td_ctx*, int i);   /* TAUDEM_B200_TIMING statistics of the last sweep by visit size, see capi.cu */
 
 /* synthetic fractal DEM written straight into a strip (bench/test input generator) */
 int td_gen_dem_dev(float* dem, td_strip s, int row0_global, int total_ny, unsigned seed,

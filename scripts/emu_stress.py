@@ -1,5 +1,5 @@
-"""Randomised stress of the emulated kernels (tests/emu): random grid sizes, flats, nodata holes, strip counts, level passes,
-river parking thresholds, tile / hybrid sweeps and strip flats against the oracle.  python scripts/emu_stress.py [first_seed] [n_seeds] [seconds]"""
+"""Randomised stress of the emulated kernels (tests/emu): random grid sizes, flats, nodata holes, strip counts, the warp-per-tile
+sweep (single strip and exchange rounds) and strip flats against the oracle.  python scripts/emu_stress.py [first_seed] [n_seeds] [seconds]"""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -21,15 +21,12 @@ for seed in range(first, first + count):
     w=synth.gen_weights(ny,nx,seed=seed)
     ad8=port.aread8(p); sca=port.areadinf(ang); ad8w=port.aread8(p,weights=w,contcheck=False); scaw=port.areadinf(ang,weights=w,contcheck=False)
     strips=int(rng.integers(1,4))
-    os.environ["TAUDEM_B200_RIVER"]=str(int(rng.choice([0,1,2,5,16]))); os.environ["TAUDEM_B200_RIVER_DINF"]=str(int(rng.choice([0,1,3,16])))
-    passes=int(rng.choice([-1,0,1,2,3,5,9]))
-    checks=[('ad8',test_emu._run(lib,False,1,passes,p,None,True,seed,strips),ad8),
-            ('sca',test_emu._run(lib,True,1,passes,ang,None,True,seed+1,strips),sca),
+    checks=[('ad8',test_emu._run(lib,False,0,0,p,None,True,seed,strips),ad8),
+            ('sca',test_emu._run(lib,True,0,0,ang,None,True,seed+1,strips),sca),
             ('ad8w',test_emu._run(lib,False,0,0,p,w,False,seed+2,strips),ad8w),
-            ('scaw',test_emu._run(lib,True,0,0,ang,w,False,seed+3,strips),scaw)]
-    os.environ.pop("TAUDEM_B200_RIVER"); os.environ.pop("TAUDEM_B200_RIVER_DINF")
-    checks+= [('tiles ad8',test_emu._tiles(lib,False,int(rng.integers(0,2)),p,None,True,seed+4)[0],ad8),
-              ('tiles sca',test_emu._tiles(lib,True,int(rng.integers(0,2)),ang,None,True,seed+5)[0],sca)]
+            ('scaw',test_emu._run(lib,True,0,0,ang,w,False,seed+3,strips),scaw),
+            ('ad8 1 strip',test_emu._run(lib,False,0,0,p,None,True,seed+4),ad8),
+            ('sca 1 strip',test_emu._run(lib,True,0,0,ang,None,True,seed+5),sca)]
     # flats over strips
     p0,_=port.d8flowdir(fel,flats=False); a0,_=port.dinfflowdir(fel,flats=False)
     fs=int(rng.integers(1,5))

@@ -18,9 +18,9 @@ def timed(fn):
 
 
 def stats(T):
-    c = [T.l.td_ctx_counter(T.ctx, 24 + i) for i in range(9)]
+    c = [T.l.td_ctx_counter(T.ctx, 24 + i) for i in range(8)]
     v = max(c[3], 1)
-    return f"visits {c[3]} per-visit cycles: wait {c[4]//v} load {c[5]//v} walk {c[6]//v} wb {c[7]//v} passes {c[8]/v:.2f}"
+    return f"visits {c[3]} per-visit cycles: wait {c[4]//v} load {c[5]//v} wavefront {c[6]//v} write-back {c[7]//v}" if c[3] else "(TAUDEM_B200_TIMING=1 for per-visit statistics)"
 
 
 def main():
@@ -55,7 +55,7 @@ def main():
         ad8, t = timed(lambda: T.aread8(s, p)); print(f"aread8       {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {6*mc/t/1e3:8.1f} GB/s")
         ad8 = None
     ad8 = s.empty(torch.float32)
-    _, t1 = timed(lambda: T.aread8_deps(s, p, ad8)); _, t2 = timed(lambda: T.aread8_sweep(s, ad8)); print(f"  deps {t1*1e3:.2f} ms  sweep {t2*1e3:.2f} ms  max area {float(s.owned(ad8).max())}  {stats(T)} of {((n+63)//64)*((n+31)//32)} tiles")
+    _, t1 = timed(lambda: T.aread8_deps(s, p, ad8)); _, t2 = timed(lambda: T.aread8_sweep(s, ad8)); print(f"  deps {t1*1e3:.2f} ms  sweep {t2*1e3:.2f} ms  max area {float(s.owned(ad8).max())}  {stats(T)} of {((n+31)//32)**2} tiles")
     del ad8, p
     for rep in range(4):
         (ang, slp, nflat), t = timed(lambda: T.dinf_slopes(s, fel, dxc, dyc)); print(f"dinf stencil {t*1e3:9.2f} ms  {mc/t:10.1f} Mcells/s  {12*mc/t/1e3:8.1f} GB/s  flats {nflat}")

@@ -66,6 +66,10 @@ def main():
                 c = [T.l.td_ctx_counter(T.ctx, 24 + i) for i in range(8)]
                 v = max(c[3], 1)
                 st = f"  [visits {c[3]} cycles/visit: wait {c[4]//v} load {c[5]//v} walk {c[6]//v} wb {c[7]//v}]"
+                if name == "warp":
+                    hh = [T.l.td_ctx_sweep_hist(T.ctx, i) for i in range(20)]
+                    st += "\n      by cells/visit (<8,<32,<128,more): " + "  ".join(
+                        f"[{hh[4*b]} visits, {hh[4*b+1]/max(hh[4*b],1):.0f} cells, {hh[4*b+2]/max(hh[4*b],1):.0f} iters, {hh[4*b+3]/max(hh[4*b],1):.0f} cyc]" for b in range(4))
             ph = [T.l.td_ctx_phase_ms(T.ctx, i) for i in range(4)]
             phases = "" if not any(ph) else "  [levels %.1f ready %.1f walk %.1f river %.1f ms]" % tuple(ph)
             print(f"{mode:18s} {tool:9s} sweep {best:9.2f} ms  {n * n / best / 1e3:9.1f} Mcells/s  max {float(own.max()):.6g}  {verdict}{phases}{st}", flush=True)

@@ -1,4 +1,4 @@
-// D8 contributing area: dependency stencil + chain-following evaluation sweep.
+// D8 contributing area: the dependency stencil (the evaluation sweep is sweep_warp.cu).
 //
 // reference: initNeighborD8up src/commonLib.cpp:240-283 (in-degree per cell),
 //            aread8 main loop   src/aread8.cpp:216-304 (pull-gather in k order,
@@ -11,13 +11,7 @@
 //   k_deps_d8  : 3x3 stencil over p -> node (u16: inflow mask | dir | flags) and
 //                cnt (u8: remaining inflow count).  5 B/cell written-read, streamed
 //                through TMA-staged shared-memory tiles.
-//   k_sweep_d8 : one thread per cell; threads on source cells (no inflow) evaluate
-//                their cell, decrement the downslope count with an acq_rel atomic
-//                and, when they were the last arrival, keep walking down the chain
-//                (no queue round trip).  Every non-source cell is evaluated by the
-//                thread whose decrement brought its count to zero.
-//   Cross-strip edges (multi-GPU): a decrement that targets a halo row is recorded
-//   in ctx.halo and shipped to the neighbour strip by the caller (src/aread8.cpp:282-297).
+//   the sweep  : sweep_warp.cu (tile dataflow, one warp per tile visit).
 #include "common.cuh"
 #include "ctx.h"
 
@@ -157,76 +151,6 @@ __global__ void __launch_bounds__(256) k_deps_d8(const short* __restrict__ p, un
   }
 }
 
-__device__ __forceinline__ unsigned atom_dec_byte(unsigned* words, long long cell) {
-  unsigned* a = words + (cell >> 2);
-  const unsigned sh = (unsigned)(cell & 3) * 8u;
-  unsigned old;
-#ifdef TD_EMU
-  old = atomicAdd(a, 0u - (1u << sh));
-#else
-  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
-#endif
-  return (old >> sh) & 0xffu;
-}
-
-// SRC = 0: threads map to the owned cells of the strip and start on sources.
-// SRC = 1: threads map to a list of cells that are ready (count already zero).
-template <int SRC>
-__global__ void __launch_bounds__(256) k_sweep_d8(const unsigned short* __restrict__ node, unsigned* __restrict__ cntw,
-                                                  float* __restrict__ area, const float* __restrict__ w, Strip s,
-                                                  float w_nodata, int usew, int contcheck, int* __restrict__ halo,
-                                                  const long long* __restrict__ list, unsigned long long nlist) {
-  int r, c;
-  if (SRC == 0) {
-    // 64 columns x 4 rows per CTA
-    c = blockIdx.x * 64 + (threadIdx.x & 63);
-    r = 1 + blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r > s.ny || c >= s.nx) return;
-  } else {
-    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nlist) return;
-    const long long ci = list[t];
-    r = (int)(ci / s.pitch); c = (int)(ci - (long long)r * s.pitch);
-  }
-  long long ci = s.idx(r, c);
-  unsigned nd = node[ci];
-  if (!(nd & NODE_VALID)) return;
-  if (SRC == 0 && (nd & 0xffu)) return;          // not a source
-
-  for (;;) {
-    // ---- flow algebra (src/aread8.cpp:228-257)
-    float a;
-    if (usew) { const float wv = w[ci]; a = nd_f(wv, w_nodata) ? -1.0f : wv; }
-    else a = 1.0f;
-    bool con = (nd & NODE_CON) != 0;
-    unsigned m = nd & 0xffu;
-#pragma unroll
-    for (int k = 1; k <= 8; ++k) {
-      if (m & (1u << (k - 1))) {
-        const float an = __ldcg(area + ci + (long long)drow(k) * s.pitch + dcol(k));
-        if (nd_f(an, -1.0f)) con = true;
-        else a = a + an;
-      }
-    }
-    if (con && contcheck) a = -1.0f;
-    area[ci] = a;
-    // ---- decrement the downslope cell (src/aread8.cpp:261-272)
-    const int d = (int)((nd >> 8) & 0xfu);
-    if (d < 1 || d > 8) return;
-    const int rn = r + drow(d), cn = c + dcol(d);
-    if (!s.on_grid(rn, cn)) return;
-    const long long cin = s.idx(rn, cn);
-    if (rn == 0 || rn == s.ny + 1) {               // crosses into the neighbour strip
-      __threadfence();
-      atomicAdd(halo + (rn == 0 ? 0 : s.pitch) + cn, 1);
-      return;
-    }
-    const unsigned ndn = node[cin];
-    if (!(ndn & NODE_VALID)) return;
-    if (atom_dec_byte(cntw, cin) != 1u) return;     // someone else will arrive later
-    r = rn; c = cn; ci = cin; nd = ndn;
-  }
-}
 }  // namespace
 
 cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s, short nodata,
@@ -237,21 +161,6 @@ cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* 
   return cudaGetLastError();
 }
 
-cudaError_t launch_sweep_d8(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
-                            float w_nodata, int usew, int contcheck, int* halo, cudaStream_t st) {
-  dim3 grid((s.nx + 63) / 64, (s.ny + 3) / 4);
-  k_sweep_d8<0><<<grid, 256, 0, st>>>(node, cntw, area, w, s, w_nodata, usew, contcheck, halo, nullptr, 0ull);
-  TD_LAUNCHED();
-  return cudaGetLastError();
-}
 
-cudaError_t launch_sweep_d8_list(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
-                                 float w_nodata, int usew, int contcheck, int* halo, const long long* list,
-                                 unsigned long long n, cudaStream_t st) {
-  if (n == 0) return cudaSuccess;
-  k_sweep_d8<1><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(node, cntw, area, w, s, w_nodata, usew, contcheck, halo, list, n);
-  TD_LAUNCHED();
-  return cudaGetLastError();
-}
 
 }  // namespace td

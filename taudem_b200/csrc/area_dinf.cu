@@ -1,4 +1,4 @@
-// D-infinity contributing area: dependency stencil + evaluation sweep.
+// D-infinity contributing area: the dependency stencil (the evaluation sweep is sweep_warp.cu).
 //
 // reference: prop()              src/commonLib.cpp:76-91  (share of a cell's flow going to neighbour k)
 //            initNeighborDinfup  src/commonLib.cpp:92-136 (in-degree = #neighbours with prop > 0)
@@ -17,7 +17,6 @@
 namespace td {
 namespace {
 constexpr int TW = 128, TH = 32;
-constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 
 // bit 7 of every byte of the result = (that byte of w == that byte of t); all bytes of w ^ t must be < 0x80
 __device__ __forceinline__ unsigned eq_bytes7(unsigned w, unsigned t) { return ~((w ^ t) + 0x7f7f7f7fu) & 0x80808080u; }
@@ -97,97 +96,6 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
   }
 }
 
-__device__ __forceinline__ unsigned atom_dec_byte(unsigned* words, long long cell) {
-  unsigned* a = words + (cell >> 2);
-  const unsigned sh = (unsigned)(cell & 3) * 8u;
-  unsigned old;
-#ifdef TD_EMU
-  old = atomicAdd(a, 0u - (1u << sh));
-#else
-  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(a), "r"(0u - (1u << sh)) : "memory");
-#endif
-  return (old >> sh) & 0xffu;
-}
-
-constexpr int STK = 12;
-
-// counters[0] = overflow list length, counters[1] = overflow list overflowed (fatal)
-template <int SRC>
-__global__ void __launch_bounds__(256) k_sweep_dinf(const unsigned short* __restrict__ node, unsigned* __restrict__ cntw,
-                                                    const float* __restrict__ ang, float* __restrict__ area,
-                                                    const float* __restrict__ w, Strip s, int usew, int contcheck,
-                                                    const double* __restrict__ theta, const double* __restrict__ dxc,
-                                                    int* __restrict__ halo, const long long* __restrict__ list,
-                                                    unsigned long long nlist, long long* __restrict__ ovf,
-                                                    unsigned long long ovf_cap, unsigned long long* __restrict__ counters) {
-  int r, c;
-  if (SRC == 0) {
-    c = blockIdx.x * 64 + (threadIdx.x & 63);
-    r = 1 + blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (r > s.ny || c >= s.nx) return;
-  } else {
-    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nlist) return;
-    const long long ci0 = list[t];
-    r = (int)(ci0 / s.pitch); c = (int)(ci0 - (long long)r * s.pitch);
-  }
-  long long ci = s.idx(r, c);
-  unsigned nd = node[ci];
-  if (!(nd & NODE_VALID)) return;
-  if (SRC == 0 && (nd & 0xffu)) return;
-
-  long long stack[STK];
-  int sp = 0;
-  for (;;) {
-    // ---- flow algebra (src/areadinf.cpp:187-218)
-    float areares = 0.f;
-    bool con = (nd & NODE_CON) != 0;
-    const unsigned m = nd & 0xffu;
-#pragma unroll
-    for (int k = 1; k <= 8; ++k) {
-      if (m & (1u << (k - 1))) {
-        const long long ni = ci + (long long)drow(k) * s.pitch + dcol(k);
-        const double p = prop_dev(ang[ni], (k + 4) % 8, theta[min(max(r - 1 + drow(k), 0), s.ny - 1)]);
-        const float an = __ldcg(area + ni);
-        if (nd_f(an, -1.0f)) con = true;
-        else areares = (float)((double)areares + p * (double)an);
-      }
-    }
-    if (usew) areares = areares + w[ci];
-    else areares = (float)((double)areares + dxc[r - 1]);
-    area[ci] = (con && contcheck) ? -1.0f : areares;
-
-    // ---- decrement every neighbour that receives flow (src/areadinf.cpp:221-239)
-    const float a0 = ang[ci];
-    const double t0 = theta[r - 1];
-    long long next = -1; int nr = 0, nc = 0; unsigned nnd = 0;
-#pragma unroll
-    for (int k = 1; k <= 8; ++k) {
-      if (prop_dev(a0, k, t0) > 0.0) {
-        const int rn = r + drow(k), cn = c + dcol(k);
-        if (!s.on_grid(rn, cn)) continue;
-        const long long cin = s.idx(rn, cn);
-        if (rn == 0 || rn == s.ny + 1) { __threadfence(); atomicAdd(halo + (rn == 0 ? 0 : s.pitch) + cn, 1); continue; }
-        const unsigned ndn = node[cin];
-        if (!(ndn & NODE_VALID)) continue;
-        if (atom_dec_byte(cntw, cin) == 1u) {
-          if (next < 0) { next = cin; nr = rn; nc = cn; nnd = ndn; }
-          else if (sp < STK) stack[sp++] = cin;
-          else {
-            const unsigned long long slot = atomicAdd(counters, 1ull);
-            if (slot < ovf_cap) ovf[slot] = cin; else counters[1] = 1ull;
-          }
-        }
-      }
-    }
-    if (next >= 0) { ci = next; r = nr; c = nc; nd = nnd; }
-    else if (sp > 0) {
-      ci = stack[--sp];
-      r = (int)(ci / s.pitch); c = (int)(ci - (long long)r * s.pitch);
-      nd = node[ci];
-    } else return;
-  }
-}
 }  // namespace
 
 cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
@@ -198,21 +106,5 @@ cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned ch
   return cudaGetLastError();
 }
 
-cudaError_t launch_sweep_dinf(const unsigned short* node, unsigned* cntw, const float* ang, float* area, const float* w,
-                              const Strip& s, int usew, int contcheck, const double* theta, const double* dxc, int* halo,
-                              const long long* list, unsigned long long nlist, long long* ovf, unsigned long long ovf_cap,
-                              unsigned long long* counters, cudaStream_t st) {
-  if (list == nullptr) {
-    dim3 grid((s.nx + 63) / 64, (s.ny + 3) / 4);
-    k_sweep_dinf<0><<<grid, 256, 0, st>>>(node, cntw, ang, area, w, s, usew, contcheck, theta, dxc, halo, nullptr, 0ull, ovf,
-                                         ovf_cap, counters);
-  } else {
-    if (nlist == 0) return cudaSuccess;
-    k_sweep_dinf<1><<<(unsigned)((nlist + 255) / 256), 256, 0, st>>>(node, cntw, ang, area, w, s, usew, contcheck, theta, dxc,
-                                                                   halo, list, nlist, ovf, ovf_cap, counters);
-  }
-  TD_LAUNCHED();
-  return cudaGetLastError();
-}
 
 }  // namespace td

@@ -51,45 +51,6 @@ int need_device() {
   if (e != cudaSuccess || n == 0) { td::set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
-// TAUDEM_B200_SWEEP selects the single-strip sweep (A/B measurements); the default is the shared-memory
-// tile dataflow (sweep_tiles.cu):
-//   chain  : first-generation one-thread-per-cell chain following (area_d8.cu / area_dinf.cu)
-//   hybrid : one pass of the tile kernel over every tile, then warp-level chain walking from the cells that
-//            are ready but not evaluated (sweep_walk.cu)
-//   walk   : warp-level chain walking from the sources alone
-//   levels : TAUDEM_B200_LEVELS (a number, default 24, or "auto") streaming level passes, then warp-level chain walking
-enum SweepMode { SWEEP_TILES, SWEEP_CHAIN, SWEEP_HYBRID, SWEEP_WALK, SWEEP_LEVELS, SWEEP_WARP };
-SweepMode sweep_mode() {
-  const char* e = getenv("TAUDEM_B200_SWEEP");
-  if (!e) return SWEEP_TILES;
-  if (strcmp(e, "chain") == 0) return SWEEP_CHAIN;
-  if (strcmp(e, "hybrid") == 0) return SWEEP_HYBRID;
-  if (strcmp(e, "walk") == 0) return SWEEP_WALK;
-  if (strcmp(e, "levels") == 0) return SWEEP_LEVELS;
-  if (strcmp(e, "warp") == 0) return SWEEP_WARP;
-  return SWEEP_TILES;
-}
-bool chain_sweep() { return sweep_mode() == SWEEP_CHAIN; }
-// hybrid / walk / levels (see above).  `first`: the bulk phase (tile pass / level passes) runs once per dependency
-// state; later calls (after sweep_apply_plain delivered the neighbours' decrements) only walk from the new ready cells.
-int sweep_alt(td_ctx* ctx, SweepMode mode, bool dinf, float* area, const float* w, const float* ang, const td::Strip& s, float w_nodata,
-              int usew, int contcheck, const double* dxc, int* halo, bool first, cudaStream_t st) {
-  const double* theta = dinf ? ctx->theta.as<double>() : nullptr;
-  if (first && mode == SWEEP_HYBRID) {
-    if (int rc = td::sweep_begin(ctx, s, st)) return rc;
-    ctx->sweep_once = 1;
-    const int rc = td::sweep_run(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st);
-    ctx->sweep_once = 0;
-    if (rc) return rc;
-  }
-  if (first && mode == SWEEP_LEVELS) {
-    const char* e = getenv("TAUDEM_B200_LEVELS");                      // a number of passes, or "auto" (stop when a pass no longer pays)
-    const int passes = !e ? 24 : (strcmp(e, "auto") == 0 ? -1 : std::max(0, std::min(atoi(e), 4096)));
-    if (int rc = td::sweep_levels(ctx, dinf, passes, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st)) return rc;
-  }
-  return td::sweep_walk(ctx, dinf, area, w, ang, s, w_nodata, usew, contcheck, theta, dxc, halo, st);
-}
-bool alt_mode(SweepMode m) { return m == SWEEP_HYBRID || m == SWEEP_WALK || m == SWEEP_LEVELS; }
 td_ctx* default_ctx() {
   static td_ctx* c = nullptr;
   if (!c) c = new td_ctx();
@@ -115,7 +76,16 @@ unsigned long long td_ctx_counter(td_ctx* ctx, int i) {
   return v;
 }
 
-double td_ctx_phase_ms(td_ctx* ctx, int i) { return (ctx && i >= 0 && i < 4) ? ctx->phase_ms[i] : 0.; }
+// statistics of the last warp sweep (TAUDEM_B200_TIMING): i = 4 * bin + {0 visits, 1 cells, 2 wavefront iterations, 3 wavefront cycles},
+// bins by cells evaluated per visit (< 8, < 32, < 128, more)
+unsigned long long td_ctx_sweep_hist(td_ctx* ctx, int i) {
+  unsigned long long v = 0;
+  if (!ctx || i < 0 || i >= 20 || !ctx->wsched.p) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(&v, ctx->wsched.as<unsigned long long>() + 40 + i, sizeof v, cudaMemcpyDeviceToHost);
+  return v;
+}
+
 
 td_ctx* td_ctx_create(void) {
   if (need_device() != TD_OK) return nullptr;
@@ -259,21 +229,8 @@ int td_aread8_deps_dev(td_ctx* ctx, const int16_t* p, float* ad8, td_strip s, in
 }
 int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, float w_nodata, int usew, int contcheck, void* stream) {
   if (int rc = check_strip(s)) return rc;
-  if (chain_sweep()) {
-    TD_CUDA(td::launch_sweep_d8(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ad8, w, Strip(s), w_nodata, usew, contcheck,
-                                ctx->halo.as<int>(), (cudaStream_t)stream));
-    return TD_OK;
-  }
-  const SweepMode mode = sweep_mode();
-  if (alt_mode(mode))
-    return sweep_alt(ctx, mode, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, ctx->halo.as<int>(), true, (cudaStream_t)stream);
-  if (mode == SWEEP_WARP) {
-    if (int rc = td::wsweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
-    return td::wsweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(), (cudaStream_t)stream);
-  }
-  if (int rc = td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
-  return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(),
-                       (cudaStream_t)stream);
+  if (int rc = td::wsweep_begin(ctx, Strip(s), (cudaStream_t)stream)) return rc;
+  return td::wsweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(), (cudaStream_t)stream);
 }
 
 int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, float ang_nodata, const double* dxc, const double* dyc,
@@ -292,37 +249,8 @@ int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca,
   if (int rc = check_strip(s)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const Strip ss(s);
-  const SweepMode mode = sweep_mode();
-  if (alt_mode(mode)) return sweep_alt(ctx, mode, true, sca, w, ang, ss, 0.f, usew, contcheck, dxc, ctx->halo.as<int>(), true, st);
-  if (mode == SWEEP_WARP) {
-    if (int rc = td::wsweep_begin(ctx, ss, st)) return rc;
-    return td::wsweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
-  }
-  if (!chain_sweep()) {
-    if (int rc = td::sweep_begin(ctx, ss, st)) return rc;
-    return td::sweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
-  }
-  const unsigned long long cap = (unsigned long long)s.nx * s.ny / 8 + 4096;
-  TD_CUDA(ctx->listA.ensure(sizeof(long long) * cap));
-  TD_CUDA(ctx->listB.ensure(sizeof(long long) * cap));
-  long long* cur = ctx->listA.as<long long>();
-  long long* nxt = ctx->listB.as<long long>();
-  unsigned long long* ctr = ctx->d_ctr + 16;
-  TD_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
-  TD_CUDA(td::launch_sweep_dinf(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ang, sca, w, ss, usew, contcheck,
-                                ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), nullptr, 0, cur, cap, ctr, st));
-  for (;;) {   // drain cells that overflowed a thread's private stack
-    TD_CUDA(cudaMemcpyAsync(ctx->h_ctr + 16, ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    TD_CUDA(cudaStreamSynchronize(st));
-    const unsigned long long n = ctx->h_ctr[16];
-    if (ctx->h_ctr[17]) { td::set_error("areadinf: ready-cell overflow list exhausted"); return TD_ERR_ALLOC; }
-    if (n == 0) break;
-    TD_CUDA(cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), st));
-    TD_CUDA(td::launch_sweep_dinf(ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned>(), ang, sca, w, ss, usew, contcheck,
-                                  ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), cur, n, nxt, cap, ctr, st));
-    std::swap(cur, nxt);
-  }
-  return TD_OK;
+  if (int rc = td::wsweep_begin(ctx, ss, st)) return rc;
+  return td::wsweep_run(ctx, true, sca, w, ang, ss, 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, ctx->halo.as<int>(), st);
 }
 
 // aread8 / areadinf -o: between *_deps_dev and *_sweep_dev, restricts the dependency state to the cells upstream of the
@@ -349,37 +277,21 @@ int td_sweep_restrict_round_dev(td_ctx* ctx, td_strip s, const int* cols, const 
 // apply (decrements received from the neighbours for my first / last row)
 int td_sweep_begin_dev(td_ctx* ctx, td_strip s, void* stream) {
   if (int rc = check_strip(s)) return rc;
-  if (alt_mode(sweep_mode())) { ctx->sweep_first = 1; return TD_OK; }
-  if (sweep_mode() == SWEEP_WARP) return td::wsweep_begin(ctx, Strip(s), (cudaStream_t)stream);
-  return td::sweep_begin(ctx, Strip(s), (cudaStream_t)stream);
+  return td::wsweep_begin(ctx, Strip(s), (cudaStream_t)stream);
 }
 int td_sweep_apply_halo_dev(td_ctx* ctx, td_strip s, const int* dec_top, const int* dec_bot, void* stream) {
   if (int rc = check_strip(s)) return rc;
-  if (alt_mode(sweep_mode())) return td::sweep_apply_plain(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
-  if (sweep_mode() == SWEEP_WARP) return td::wsweep_apply_halo(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
-  return td::sweep_apply_halo(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
+  return td::wsweep_apply_halo(ctx, Strip(s), dec_top, dec_bot, (cudaStream_t)stream);
 }
 int td_aread8_sweep_run_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, float w_nodata, int usew, int contcheck, int* halo_out,
                             void* stream) {
   if (int rc = check_strip(s)) return rc;
-  if (alt_mode(sweep_mode())) {
-    const bool first = ctx->sweep_first != 0; ctx->sweep_first = 0;
-    return sweep_alt(ctx, sweep_mode(), false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, halo_out, first, (cudaStream_t)stream);
-  }
-  if (sweep_mode() == SWEEP_WARP)
-    return td::wsweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, halo_out, (cudaStream_t)stream);
-  return td::sweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, halo_out, (cudaStream_t)stream);
+  return td::wsweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, halo_out, (cudaStream_t)stream);
 }
 int td_area_sweep_run_dev(td_ctx* ctx, const float* ang, const float* w, float* sca, td_strip s, int usew, int contcheck, const double* dxc,
                           int* halo_out, void* stream) {
   if (int rc = check_strip(s)) return rc;
-  if (alt_mode(sweep_mode())) {
-    const bool first = ctx->sweep_first != 0; ctx->sweep_first = 0;
-    return sweep_alt(ctx, sweep_mode(), true, sca, w, ang, Strip(s), 0.f, usew, contcheck, dxc, halo_out, first, (cudaStream_t)stream);
-  }
-  if (sweep_mode() == SWEEP_WARP)
-    return td::wsweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
-  return td::sweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
+  return td::wsweep_run(ctx, true, sca, w, ang, Strip(s), 0.f, usew, contcheck, ctx->theta.as<double>(), dxc, halo_out, (cudaStream_t)stream);
 }
 
 // ---- peer mode of the partitioned sweeps: neighbours' counts / tile queues / halo buffers mapped over

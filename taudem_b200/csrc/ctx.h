@@ -37,7 +37,7 @@ struct td_ctx {
   Buf rows;      // per-row dxc | dyc (host-grid level calls)
   Buf rowfact;   // per-row constants of the flow-direction stencils (rowfact.cuh)
   Buf io[4];     // raster strips of host-grid level calls
-  // peer mode of the sweeps (neighbour strips' buffers opened through CUDA IPC, see sweep_tiles.cu)
+  // peer mode of the sweeps (neighbour strips' buffers opened through CUDA IPC, see sweep_warp.cu)
   struct PeerInfo { void *cntw = nullptr, *tileflags = nullptr, *dctr = nullptr, *halo_in = nullptr; int qmask = 0, ntx = 0, ny = 0, th = 0, nt = 0, valid = 0; };
   PeerInfo peer_up, peer_down;
   void* peer_G = nullptr;                // global pending counter (rank 0's gbuf)
@@ -45,11 +45,8 @@ struct td_ctx {
   Buf peer_halo, gbuf;
   int peer_on = 0;
   int sweep_dinf = 0;                    // which dependency state node/cnt hold (tile height of the sweep)
-  int sweep_once = 0;                    // tile sweep: visit every tile once, no re-activation (hybrid mode)
-  double phase_ms[4] = {0, 0, 0, 0};     // TAUDEM_B200_TIMING=1: level passes / ready-list collection / chain walking / rivers of the last sweep
   td::PropRow prop;                      // prop() table of the strip whose theta table is loaded (uniform = 0: rows differ)
   int wgrid_d8 = 0, wgrid_dinf = 0;     // persistent grid of the warp-per-tile sweep kernels on this context's device
-  int sweep_first = 1;                   // level / hybrid modes: the bulk phase has not run yet for the current dependency state
   unsigned long long* d_ctr = nullptr;   // 32 device counters
   unsigned long long* h_ctr = nullptr;   // pinned host mirror
   td_ctx();

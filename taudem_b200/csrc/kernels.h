@@ -14,33 +14,15 @@ int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, con
                        const double* thA, const double* thB, long long* nleft, const td_strip_comm* comm, cudaStream_t st);
 cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
                            short nodata, cudaStream_t st);
-cudaError_t launch_sweep_d8(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
-                            float w_nodata, int usew, int contcheck, int* halo, cudaStream_t st);
-cudaError_t launch_sweep_d8_list(const unsigned short* node, unsigned* cntw, float* area, const float* w, const Strip& s,
-                                 float w_nodata, int usew, int contcheck, int* halo, const long long* list,
-                                 unsigned long long n, cudaStream_t st);
 cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
                              float nodata, const double* theta, cudaStream_t st);
-cudaError_t launch_sweep_dinf(const unsigned short* node, unsigned* cntw, const float* ang, float* area, const float* w,
-                              const Strip& s, int usew, int contcheck, const double* theta, const double* dxc, int* halo,
-                              const long long* list, unsigned long long nlist, long long* ovf, unsigned long long ovf_cap,
-                              unsigned long long* counters, cudaStream_t st);
-int sweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
-int sweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
-int sweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
-              int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
 int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
 int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
                int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
-int sweep_levels(td_ctx* ctx, bool dinf, int passes, float* area, const float* w, const float* ang, const Strip& s, float w_nodata,
-                 int usew, int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
 int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, const int* in_top, const int* in_bot,
                          int* req_out, int finish, cudaStream_t st);
 int sweep_restrict_upstream(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, cudaStream_t st);
-int sweep_apply_plain(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
-int sweep_walk(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
-               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st);
 int sweep_peer_export(td_ctx* ctx, const Strip& s, int dinf, unsigned char* handles, int* meta, cudaStream_t st);
 int sweep_peer_connect(td_ctx* ctx, int which, const unsigned char* handles, const int* meta);
 int sweep_peer_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);

@@ -52,12 +52,19 @@ struct __align__(16) WarpMem {
   unsigned cnt[TC / 4];                   // dependency counts, four cells per word: 0..8, 0xFE = evaluated, 0xFF = not a node
   double theta[DINF ? RH + 2 : 2];        // D-infinity: prop()'s row angle for every ring row
   double dxr[DINF ? TS : 2];              // D-infinity: cell size of every tile row
-  unsigned short stk[DINF ? STKCAP : 4];  // D-infinity: second receivers that became ready (what does not fit is found again by a rescan of the counts)
+  unsigned short stk[DINF ? STKCAP : TC]; // D-infinity: second receivers that became ready (what does not fit is found again by a rescan of
+                                          // the counts); D8: the queue of the cells that are ready when the visit starts (any lane takes any)
   unsigned short ext[EXTCAP];             // receivers outside the tile (ring index)
   unsigned evmask[TS];                    // per tile row: cells evaluated by this visit
   int sp, next, dirty, pad;
 };
-template <bool DINF> constexpr int workers_per_cta() { return DINF ? 14 : 22; }
+template <bool DINF> constexpr int workers_per_cta() { return DINF ? 14 : 18; }
+
+// what a neighbouring strip exposes to this GPU (device pointers into the peer's memory)
+struct PeerStrip {
+  unsigned* cntw = nullptr; int* state = nullptr; int* tq = nullptr; unsigned long long* ctr = nullptr; float* halo_in = nullptr;
+  unsigned qmask = 0; int ntx = 0, ny = 0, valid = 0;
+};
 
 struct WArgs {
   const unsigned short* node;
@@ -79,6 +86,13 @@ struct WArgs {
   unsigned long long* ctr; // scheduler words, one 128-byte line each (C_HEAD ...): every worker hammers them
   unsigned long long* stat;// [3] visits, [4..7] cycle statistics (TAUDEM_B200_TIMING)
   int stats;
+  // peer mode (one strip per GPU, the neighbours' buffers mapped over NVLink with CUDA IPC): no exchange rounds — a tile
+  // delivers into the neighbour GPU exactly as it delivers into a neighbour tile.  Every GPU only WRITES remote memory
+  // (the neighbour's halo-area buffer, counts, tile states, queue); everything it reads is its own.
+  int peer;
+  PeerStrip up, down;      // the strip above (rank - 1) / below (rank + 1)
+  unsigned long long* G;   // queued + running tiles of ALL strips (lives on rank 0)
+  const float* halo_in;    // areas of the neighbours' edge cells: [0, pitch) row above, [pitch, 2 pitch) row below
 };
 
 #ifdef TD_EMU
@@ -98,43 +112,107 @@ __device__ __forceinline__ void cp_wait_all() {}
 #endif
 
 // ---- scheduler (the protocol of the first-generation tile kernel, one lane per worker)
+// In peer mode a neighbour GPU operates on this strip's scheduler words and on the counts of its edge rows with
+// system-scope atomics over NVLink; the owner then uses system scope on the same words (atomics of different scopes on one
+// address are not guaranteed to be atomic with respect to each other).
+#define W_ADD(ptr, v) (a.peer ? atomicAdd_system((ptr), (v)) : atomicAdd((ptr), (v)))
+#define W_CAS(ptr, c, v) (a.peer ? atomicCAS_system((ptr), (c), (v)) : atomicCAS((ptr), (c), (v)))
+#define W_EXCH(ptr, v) (a.peer ? atomicExch_system((ptr), (v)) : atomicExch((ptr), (v)))
+
+__device__ __forceinline__ void pending_add(const WArgs& a, unsigned long long v) {
+  if (a.peer) atomicAdd_system(a.G, v); else atomicAdd(a.ctr + C_PEND, v);
+}
 __device__ void sched_push(const WArgs& a, int t) {
-  atomicAdd(a.ctr + C_PEND, 1ull);
-  const unsigned long long slot = atomicAdd(a.ctr + C_TAIL, 1ull);
+  pending_add(a, 1ull);
+  const unsigned long long slot = W_ADD(a.ctr + C_TAIL, 1ull);
   int* q = a.tq + (slot & a.qmask);
-  while (atomicCAS(q, 0, t + 1) != 0) {}
+  while (W_CAS(q, 0, t + 1) != 0) {}
 }
 __device__ void sched_activate(const WArgs& a, int t) {
   for (;;) {
-    const int st = atomicCAS(a.state + t, 0, 1);            // idle -> queued (the common case: one round trip)
+    const int st = W_CAS(a.state + t, 0, 1);                // idle -> queued (the common case: one round trip)
     if (st == 0) { sched_push(a, t); return; }
     if (st == 1 || st == 3) return;
-    if (atomicCAS(a.state + t, 2, 3) == 2) return;         // running -> running + re-activated
+    if (W_CAS(a.state + t, 2, 3) == 2) return;             // running -> running + re-activated
   }
 }
+// the same protocol on a neighbour GPU's scheduler (system-scope atomics over NVLink)
+__device__ void sched_activate_peer(const WArgs& a, const PeerStrip& P, int t) {
+  for (;;) {
+    const int st = atomicCAS_system(P.state + t, 0, 1);
+    if (st == 0) {
+      atomicAdd_system(a.G, 1ull);
+      const unsigned long long slot = atomicAdd_system(P.ctr + C_TAIL, 1ull);
+      int* q = P.tq + (slot & P.qmask);
+      while (atomicCAS_system(q, 0, t + 1) != 0) {}
+      return;
+    }
+    if (st == 1 || st == 3) return;
+    if (atomicCAS_system(P.state + t, 2, 3) == 2) return;
+  }
+}
+// Flow into the strip above (up) / below: the source cell's area goes into the neighbour's halo buffer, is fenced
+// system-wide, then the neighbour's count is decremented; zero -> queue its tile (src/aread8.cpp:282-297 without rounds).
+__device__ void deliver_peer(const WArgs& a, bool up, int c_src, float val, int c_dst) {
+  const PeerStrip& P = up ? a.up : a.down;
+  const int pitch = a.s.pitch;
+  P.halo_in[(up ? pitch : 0) + c_src] = val;        // I am the row BELOW the strip above / the row ABOVE the strip below
+  __threadfence_system();
+  const int r = up ? P.ny : 1;
+  const long long ci = (long long)r * pitch + c_dst;
+  const unsigned sh = (unsigned)(ci & 3) * 8u;
+  const unsigned old = atomicAdd_system(P.cntw + (ci >> 2), 0u - (1u << sh));
+  if (((old >> sh) & 0xffu) == 1u) sched_activate_peer(a, P, ((r - 1) / TS) * P.ntx + c_dst / TS);
+}
+// relaxed gpu-scope load of a scheduler word (a volatile load is a system-scope load: far more expensive to poll with)
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+#ifdef TD_EMU
+  emu::yield(); return *((const volatile int*)p);
+#else
+  int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+#endif
+}
+__device__ __forceinline__ long long ld_relaxed(const unsigned long long* p) {
+#ifdef TD_EMU
+  emu::yield(); return (long long)*((const volatile unsigned long long*)p);
+#else
+  long long v; asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+#endif
+}
+// waits about `cycles` SM cycles without touching memory (nanosleep alone returns after a few tens of nanoseconds
+// whatever it is asked for: measured 68 ns per poll with requests of 2 us — thousands of idle workers then hammer the L2)
+__device__ __forceinline__ void idle_wait(unsigned cycles) {
+#ifdef TD_EMU
+  (void)cycles; emu::yield();
+#else
+  const long long t0 = clock64();
+  do { __nanosleep(cycles >> 1); } while (clock64() - t0 < (long long)cycles);
+#endif
+}
 // Ticket h is served by the h-th push; a worker whose ticket is never served leaves when no tile is queued or running.
-// A waiting worker polls its own slot (a word nobody else polls); the shared "pending" word only every 16th time.
+// A waiting worker polls its own slot (a word nobody else polls) with an exponential back-off of 0.25 .. 2 us; the shared
+// "pending" word only every 8th time.
 __device__ int sched_pop(const WArgs& a) {
   const unsigned long long h = atomicAdd(a.ctr + C_HEAD, 1ull);
   int* q = a.tq + (h & a.qmask);
-  unsigned ns = 64, n = 0;
+  unsigned wait = 512, n = 0;
   for (;;) {
-    const int v = ldv(q);
+    const int v = ld_relaxed(q);
     if (v != 0) {
-      atomicExch(q, 0);
-      atomicExch(a.state + (v - 1), 2);
+      W_EXCH(q, 0);
+      W_EXCH(a.state + (v - 1), 2);
       __threadfence();
       return v - 1;
     }
-    if ((++n & 15u) == 0u && (long long)ldv(a.ctr + C_PEND) <= 0) return -1;
-    __nanosleep(ns);
-    if (ns < 2048) ns <<= 1;
+    if ((++n & 7u) == 0u && ld_relaxed(a.peer ? a.G : a.ctr + C_PEND) <= 0) return -1;
+    idle_wait(wait);
+    if (wait < 4096) wait <<= 1;
   }
 }
 __device__ void sched_finish(const WArgs& a, int t) {
   __threadfence();
-  if (atomicCAS(a.state + t, 2, 0) != 2) { atomicExch(a.state + t, 1); sched_push(a, t); }
-  atomicAdd(a.ctr + C_PEND, ~0ull);   // pending -= 1
+  if (W_CAS(a.state + t, 2, 0) != 2) { W_EXCH(a.state + t, 1); sched_push(a, t); }
+  pending_add(a, ~0ull);   // pending -= 1
 }
 
 __global__ void k_wsched_init(int* state, int* tq, unsigned qcap, int ntiles, unsigned long long* ctr, unsigned long long* stat) {
@@ -144,6 +222,7 @@ __global__ void k_wsched_init(int* state, int* tq, unsigned qcap, int ntiles, un
   if (i == 0) {
     ctr[C_HEAD] = 0; ctr[C_TAIL] = (unsigned long long)ntiles; ctr[C_PEND] = (unsigned long long)ntiles;
     stat[3] = stat[4] = stat[5] = stat[6] = stat[7] = 0;
+    for (int j = 40; j < 60; ++j) ctr[j] = 0;
   }
 }
 
@@ -154,30 +233,20 @@ __device__ __noinline__ double wshare_full(float ang, double t, int kk) {
 }
 
 // The share prop(av, kk) of a contributor (angle av, node word nn) for its receiver in direction kk, from the strip's
-// table: the contributor's first receiver k1 (node word) tells the sector of av with one comparison, every branch of
-// prop() / dinf_outflow is then numerator / (sector width), a division by a table constant (div_const).  Angles outside
-// the table's reach return through the interval search.
+// table.  The contributor's first receiver k1 (node word) is the sector j of its angle or the sector after it — one
+// comparison; kk is then j (share (ar[j+1] - a) / den[j] above the sector's lower edge, (a - ar[j-1]) / den[j-1] on it) or
+// j + 1 (share (a - ar[j]) / den[j]): prop()'s / dinf_outflow's expressions with the division by a table constant
+// (div_const).  Direction 1 reached through the end of the table (the float-rounded a - 2 PI of src/commonLib.cpp:82)
+// and angles outside [0, 2 PI) go through the interval search (rare, out of line).
 __device__ __forceinline__ double wshare_tab(const PropRow& P, float av, unsigned nn, int kk) {
   const int k1 = (int)((nn >> 8) & 0xfu);
   const double a = (double)av;
-  if (k1 >= 1 && k1 <= 8 && av >= 0.f) {
-    int j = k1 - 1 + (a >= P.ar[k1] ? 1 : 0);
-    if (k1 == 1 && a >= P.ar[8]) j = a >= P.ar[9] ? 9 : 8;
-    double num; int d;
-    bool ok = true;
-    if (kk == j && j >= 1 && j <= 8) {
-      if (a > P.ar[j]) { num = P.ar[j + 1] - a; d = j; } else { num = a - P.ar[j - 1]; d = j - 1; }
-    } else if (kk == j + 1 && j >= 1 && j <= 7) { num = a - P.ar[j]; d = j; }
-    else if (kk == 1 && j >= 8) {
-      // src/commonLib.cpp:82: direction 1 reached through the wrap, with the float-rounded a - 2 PI
-      const float a1 = (float)(a - 2.0 * TD_PI);
-      const double b = (double)a1;
-      ok = a1 > P.ar[0] && a1 < P.ar[2];
-      if (a1 > P.ar[1]) { num = P.ar[2] - b; d = 1; } else { num = b - P.ar[0]; d = 0; }
-    } else { ok = false; num = 0.; d = 0; }
-    if (ok) return P.safe ? div_const(num, P.den[d], P.rden[d]) : num / P.den[d];
-  }
-  return wshare_full(av, P.ar[2], kk);
+  const int j = k1 - 1 + (a >= P.ar[k1 & 7 ? k1 : 8] ? 1 : 0);
+  if ((k1 == 1 && a >= P.ar[8]) || (j == 8 && kk == 1) || av < 0.f || k1 < 1 || k1 > 8) return wshare_full(av, P.ar[2], kk);
+  const bool isA = kk == j, up = a > P.ar[j];
+  const int d = (isA && !up) ? j - 1 : j;
+  const double num = (isA && up) ? P.ar[j + 1] - a : a - P.ar[d];
+  return P.safe ? div_const(num, P.den[d], P.rden[d]) : num / P.den[d];
 }
 
 // bit 7 of every byte of the result is set exactly where that byte of w is zero (no borrow between bytes)
@@ -239,7 +308,8 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
         const int so = rr * RS + 4 * q;
         if (r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.pitch) {
           const long long g = s.idx(r, c);
-          cp16(M.area + so, a.area + g);
+          if (a.peer && (r == 0 || r == s.ny + 1)) cp16(M.area + so, a.halo_in + (r == 0 ? 0 : s.pitch) + c);
+          else cp16(M.area + so, a.area + g);
           if (DINF) cp16(M.ang + so, a.ang + g);
           cp8(M.node + so, a.node + g);
         } else {
@@ -258,6 +328,18 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
     unsigned rdy = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) rdy |= zero_nibble(g0[j]) << (4 * j);
+    int qn = 0;                    // D8: length of the ready queue (warp-uniform)
+    if (!DINF) {
+      // chains never fork: every ready cell of the visit is known now; a shared queue keeps all lanes busy
+      const int n = __popc(rdy);
+      int incl = n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+      int pos = incl - n;
+      for (unsigned m = rdy; m; m &= m - 1u) M.stk[pos++] = (unsigned short)(lane * TS + __ffs(m) - 1);
+      qn = __shfl_sync(FULL, incl, 31);
+      rdy = 0;
+    }
     cp_wait_all();
     __syncwarp();
     if (a.stats && lane == 0) tk2 = clock64();
@@ -265,8 +347,20 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
     // ---- 4. the wavefront inside the tile: one chain per lane; an idle lane goes on with the next ready cell of its own
     //         row, then (D-infinity) with a cell from the warp's fork stack
     int cur = -1;
+    int iters = 0, qh = 0;
     for (;;) {
+      ++iters;
+
       if (cur < 0 && rdy) { const int b = __ffs(rdy) - 1; rdy &= rdy - 1; cur = lane * TS + b; }
+      if (!DINF) {
+        const unsigned idle = __ballot_sync(FULL, cur < 0);
+        if (idle && qh < qn) {
+          const int take = min(__popc(idle), qn - qh);
+          const int rank = __popc(idle & lt);
+          if (cur < 0 && rank < take) cur = M.stk[qh + rank];
+          qh += take;
+        }
+      }
       if (DINF) {
         const unsigned idle = __ballot_sync(FULL, cur < 0);
         if (idle) {
@@ -362,13 +456,14 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
               else { const int slot = atomicAdd(&M.sp, 1); if (slot < STKCAP) M.stk[slot] = (unsigned short)l2; }   // a second ready receiver: an idle lane takes it
             }
           } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
-            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)((nlr + 1) * RS + nlx + 4);
+            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)(((nlr + 1) * RS + nlx + 4) | (lx << 11));   // receiver (ring index) | source column
           }
         }
         cur = cont;
       }
       __syncwarp();              // counts first, then the areas they announce (next iteration)
     }
+
     if (a.stats && lane == 0) tk3 = clock64();
 
     // ---- 5. write back what this visit evaluated, then publish counts and deliver the crossings
@@ -396,7 +491,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
             delta += (unsigned)ci << (8 * i);
           }
           if (delta != 0) {
-            const unsigned old = atomicAdd(gw + j, delta);
+            const unsigned old = W_ADD(gw + j, delta);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               if (dec[i] < 0 && (int)((old >> (8 * i)) & 0xffu) + dec[i] == 0) dirty = true;   // became ready meanwhile
@@ -408,15 +503,21 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
     __syncwarp();
     const int ne = M.next;
     for (int e = lane; e < ne; e += 32) {
-      const int code = M.ext[e];
+      const int code = M.ext[e] & 0x7ff, lxs = M.ext[e] >> 11;
       const int rr = code / RS, rc = code - rr * RS;
       const int r = r0 - 1 + rr, c = c0 - 4 + rc;
-      if (r == 0 || r == s.ny + 1) { atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1); continue; }
+      if (r == 0 || r == s.ny + 1) {
+        if (a.peer) {      // the source is a cell of my first / last row: its area is still in shared memory
+          const int lrs = r == 0 ? 0 : s.ny - r0;
+          deliver_peer(a, r == 0, c0 + lxs, M.area[(lrs + 1) * RS + lxs + 4], c);
+        } else atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1);
+        continue;
+      }
       const long long ci = s.idx(r, c);
       const unsigned ndr = (unsigned)M.node[code];
       if (!(ndr & NODE_VALID)) continue;
       const unsigned sh = (unsigned)(ci & 3) * 8u;
-      const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - (1u << sh));
+      const unsigned old = W_ADD(a.cntw + (ci >> 2), 0u - (1u << sh));
       if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
     }
     __syncwarp();
@@ -430,6 +531,13 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
         atomicAdd(a.stat + 5, (unsigned long long)(tk2 - tk1));
         atomicAdd(a.stat + 6, (unsigned long long)(tk3 - tk2));
         atomicAdd(a.stat + 7, (unsigned long long)(tk4 - tk3));
+        // by size of the visit (cells evaluated: < 8, < 32, < 128, more): visits, cells, wavefront iterations, wavefront cycles
+        int ncell = 0;
+        for (int i = 0; i < TS; ++i) ncell += __popc(M.evmask[i]);
+        const int bin = ncell < 8 ? 0 : ncell < 32 ? 1 : ncell < 128 ? 2 : 3;
+        unsigned long long* h = a.ctr + 40 + 4 * bin;
+        atomicAdd(h, 1ull); atomicAdd(h + 1, (unsigned long long)ncell); atomicAdd(h + 2, (unsigned long long)iters);
+        atomicAdd(h + 3, (unsigned long long)(tk3 - tk2));
       }
     }
     __syncwarp();
@@ -457,13 +565,14 @@ __global__ void k_wapply_halo(WArgs a, const int* __restrict__ dec_top, const in
   }
 }
 
-__global__ void k_wsched_reset(unsigned long long* ctr) { ctr[C_HEAD] = ctr[C_TAIL] = ctr[C_PEND] = 0; }
+__global__ void k_wsched_reset(unsigned long long* ctr) { if (threadIdx.x == 0) ctr[C_HEAD] = ctr[C_TAIL] = ctr[C_PEND] = 0; }
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
   a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
   a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + TS - 1) / TS;
   a.stats = 0;
+  a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
   const long long nt = (long long)a.ntx * a.nty;
   if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
   unsigned qcap = 1u << 14;   // always far more slots than workers holding tickets
@@ -497,7 +606,7 @@ int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
 int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
-  k_wsched_reset<<<1, 1, 0, st>>>(a.ctr);   // tickets abandoned at the end of the previous run are void
+  k_wsched_reset<<<1, 32, 0, st>>>(a.ctr);   // tickets abandoned at the end of the previous run are void
   TD_LAUNCHED();
   k_wapply_halo<<<(s.nx + 255) / 256, 256, 0, st>>>(a, dec_top, dec_bot);
   TD_LAUNCHED();
@@ -514,6 +623,18 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
   a.prop = ctx->prop;
   if (!dinf) a.prop.uniform = 0;
+  a.peer = ctx->peer_on;
+  if (a.peer) {
+    auto fill = [](const td_ctx::PeerInfo& pi, PeerStrip& P) {
+      P.valid = pi.valid;
+      P.cntw = (unsigned*)pi.cntw; P.state = (int*)pi.tileflags; P.tq = P.state + pi.nt; P.ctr = (unsigned long long*)pi.dctr;
+      P.halo_in = (float*)pi.halo_in; P.qmask = (unsigned)pi.qmask; P.ntx = pi.ntx; P.ny = pi.ny;
+    };
+    fill(ctx->peer_up, a.up); fill(ctx->peer_down, a.down);
+    a.G = (unsigned long long*)ctx->peer_G;
+    a.halo_in = ctx->peer_halo.as<float>();
+    if ((s.has_top && !a.up.valid) || (s.has_bot && !a.down.valid) || !a.G) { set_error("peer mode: neighbours are not connected"); return TD_ERR_ARG; }
+  }
   const char* te = getenv("TAUDEM_B200_TIMING");
   a.stats = (te && atoi(te) > 0) ? 1 : 0;
   const int warps = dinf ? workers_per_cta<true>() : workers_per_cta<false>();
@@ -537,5 +658,83 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   TD_CUDA(cudaGetLastError());
   return TD_OK;
 }
+
+namespace {
+__global__ void k_add_G(unsigned long long* G, unsigned long long v) { if (threadIdx.x == 0) { atomicAdd_system(G, v); __threadfence_system(); } }
+void close_peer(td_ctx::PeerInfo& pi) {
+  if (pi.cntw) cudaIpcCloseMemHandle(pi.cntw);
+  if (pi.tileflags) cudaIpcCloseMemHandle(pi.tileflags);
+  if (pi.dctr) cudaIpcCloseMemHandle(pi.dctr);
+  if (pi.halo_in) cudaIpcCloseMemHandle(pi.halo_in);
+  pi = td_ctx::PeerInfo();
+}
+}  // namespace
+
+// ---- peer mode plumbing (CUDA IPC).  export: make sure every buffer a neighbour touches exists at its final size and
+// hand out its IPC handle; connect: open a neighbour's (or rank 0's counter) handles.
+int sweep_peer_export(td_ctx* ctx, const Strip& s, int dinf, unsigned char* handles, int* meta, cudaStream_t st) {
+  WArgs a;
+  ctx->sweep_dinf = dinf ? 1 : 0;
+  const size_t n = (size_t)s.cells();
+  TD_CUDA(ctx->node.ensure(n * 2));
+  TD_CUDA(ctx->cnt.ensure((n + 3) / 4 * 4));
+  if (int rc = wargs(ctx, a, s)) return rc;
+  TD_CUDA(ctx->peer_halo.ensure(sizeof(float) * 2 * (size_t)s.pitch));
+  TD_CUDA(ctx->gbuf.ensure(64));
+  TD_CUDA(cudaMemsetAsync(ctx->gbuf.p, 0, 64, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  void* ptrs[5] = {ctx->cnt.p, ctx->tileflags.p, ctx->wsched.p, ctx->peer_halo.p, ctx->gbuf.p};
+  for (int i = 0; i < 5; ++i) {
+    cudaIpcMemHandle_t h;
+    TD_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
+    memcpy(handles + 64 * i, &h, 64);
+  }
+  meta[0] = (int)a.qmask; meta[1] = a.ntx; meta[2] = s.ny; meta[3] = TS; meta[4] = a.ntx * a.nty;
+  return TD_OK;
+}
+
+// which: 0 = strip above, 1 = strip below, 2 = owner of the global counter (handles == NULL: this rank)
+int sweep_peer_connect(td_ctx* ctx, int which, const unsigned char* handles, const int* meta) {
+  auto open = [](const unsigned char* h64, void** out) -> cudaError_t {
+    cudaIpcMemHandle_t h; memcpy(&h, h64, 64);
+    return cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+  };
+  if (which == 2) {
+    if (ctx->peer_G_opened && ctx->peer_G) cudaIpcCloseMemHandle(ctx->peer_G);
+    ctx->peer_G_opened = false;
+    if (!handles) { ctx->peer_G = ctx->gbuf.p; return TD_OK; }
+    TD_CUDA(open(handles + 64 * 4, &ctx->peer_G));
+    ctx->peer_G_opened = true;
+    return TD_OK;
+  }
+  td_ctx::PeerInfo& pi = which == 0 ? ctx->peer_up : ctx->peer_down;
+  if (!handles && meta && pi.valid) {       // same buffers, new geometry
+    pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4];
+    return TD_OK;
+  }
+  close_peer(pi);
+  if (!handles) return TD_OK;
+  TD_CUDA(open(handles, &pi.cntw));
+  TD_CUDA(open(handles + 64, &pi.tileflags));
+  TD_CUDA(open(handles + 128, &pi.dctr));
+  TD_CUDA(open(handles + 192, &pi.halo_in));
+  pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4]; pi.valid = 1;
+  return TD_OK;
+}
+
+// start of a peer-mode sweep: queue all tiles, announce them in the global counter.  The caller must put a barrier
+// between this call and wsweep_run on every rank (nobody may see G == 0 before everybody announced).
+int sweep_peer_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
+  ctx->peer_on = 1;
+  if (int rc = wsweep_begin(ctx, s, st)) return rc;
+  WArgs a;
+  if (int rc = wargs(ctx, a, s)) return rc;
+  TD_CUDA(cudaMemsetAsync(ctx->peer_halo.p, 0, sizeof(float) * 2 * (size_t)s.pitch, st));
+  k_add_G<<<1, 32, 0, st>>>((unsigned long long*)ctx->peer_G, (unsigned long long)a.ntx * a.nty);
+  TD_LAUNCHED();
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+void sweep_peer_off(td_ctx* ctx) { ctx->peer_on = 0; }
 
 }  // namespace td

@@ -94,17 +94,13 @@ class DistTools:
         from .device import DeviceStrip, Tools
         # peer mode: sweeps deliver across GPUs inside the kernel (CUDA IPC + NVLink atomics), no exchange
         # rounds.  Needs one GPU per rank and the NCCL backend; TAUDEM_B200_PEER=0/1 overrides.
-        # Default: on for 2..4 NCCL ranks (validated bit-identical on 2 GPUs and by the 4-GPU 65536^2 bench), off
-        # for more ranks until it has been run there (the round-based exchange has been, on 8 GPUs).
+        # Default: on for NCCL ranks (one GPU each); the round-based exchange remains for gloo / shared-GPU tests.
         if peer is None:
             env = os.environ.get("TAUDEM_B200_PEER")
             if env is not None:
                 peer = env == "1"
             else:
-                peer = dist.is_initialized() and dist.get_backend() == "nccl" and 2 <= world <= 4
-        # the level / walk / hybrid sweeps (TAUDEM_B200_SWEEP) exchange through the rounds below; peer mode is the tile kernel's
-        if os.environ.get("TAUDEM_B200_SWEEP") in ("levels", "walk", "hybrid"):
-            peer = False
+                peer = dist.is_initialized() and dist.get_backend() == "nccl" and world >= 2
         self.peer = bool(peer) and world > 1
         self._peer_cache = None
         self.rank, self.world = rank, world

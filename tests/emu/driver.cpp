@@ -1,10 +1,12 @@
-// TEST INFRASTRUCTURE ONLY — runs the level / ready / walk kernels of taudem_b200/csrc/sweep_walk.cu on the
-// CPU emulation (cuda_runtime.h, emu.cpp) from a flow-direction grid; tests/test_emu.py compares the result
-// with the oracle.  The dependency state (node words, counts) is rebuilt here in plain loops following the
+// TEST INFRASTRUCTURE ONLY — runs the warp-per-tile dataflow sweep (taudem_b200/csrc/sweep_warp.cu: the warps of a
+// persistent CTA are independent workers — ticket queue, four-state tile protocol, warp-local wavefront with shared-memory
+// counts — interleaved at random at every atomic / volatile load / fence) and the outlet restriction (outlets.cu) on the
+// CPU emulation (cuda_runtime.h, emu.cpp) from a flow-direction grid, on one or several row strips with the exchange
+// rounds of taudem_b200/dist.py; tests/test_emu.py compares the result with the oracle.  The dependency state (node words, counts) is rebuilt here in plain loops following the
 // description of k_deps_d8 / k_deps_dinf (taudem_b200/csrc/area_d8.cu, area_dinf.cu).
 #include <string>
 
-#include "sweep_walk_emu.inc"   // the transformed kernel sources (written by tests/test_emu.py)
+#include "sweep_warp_emu.inc"   // the transformed kernel sources (written by tests/test_emu.py)
 #include "outlets_emu.inc"
 
 namespace td {
@@ -153,15 +155,13 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   }
   bool first = true;
   int rounds = 0;
+  for (auto& T : S) td::make_prop_row(T.theta[0], true, &T.ctx.prop);
   for (;;) {
     for (auto& T : S) {
       std::fill(T.halo.begin(), T.halo.end(), 0);
-      int rc = 0;
-      if (first && mode == 1)
-        rc = td::sweep_levels(&T.ctx, dinf != 0, passes, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew,
-                              contcheck, T.theta.data(), T.dxc.data(), T.halo.data(), nullptr);
+      int rc = first ? td::wsweep_begin(&T.ctx, T.s, nullptr) : 0;
       if (!rc)
-        rc = td::sweep_walk(&T.ctx, dinf != 0, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew, contcheck,
+        rc = td::wsweep_run(&T.ctx, dinf != 0, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew, contcheck,
                             T.theta.data(), T.dxc.data(), T.halo.data(), nullptr);
       if (rc) return rc;
     }
@@ -182,11 +182,14 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
       const int pitch = S[i].s.pitch;
       const int* dec_top = i > 0 ? S[i - 1].halo.data() + pitch : nullptr;            // what the strip above sent down
       const int* dec_bot = i + 1 < nstrips ? S[i + 1].halo.data() : nullptr;           // what the strip below sent up
-      if (int rc = td::sweep_apply_plain(&S[i].ctx, S[i].s, dec_top, dec_bot, nullptr)) return rc;
+      if (int rc = td::wsweep_apply_halo(&S[i].ctx, S[i].s, dec_top, dec_bot, nullptr)) return rc;
     }
     if (rounds > 10000) return 2;
   }
   if (rounds_out) *rounds_out = rounds;
+  for (auto& T : S)       // every cell of the flow field must have been evaluated (count byte 0xFE) or removed (0xFF)
+    for (int r = 1; r <= T.s.ny; ++r)
+      for (int c = 0; c < nx; ++c) if (T.cnt[T.s.idx(r, c)] <= 8) return 77;
   for (auto& T : S)
     for (int r = 1; r <= T.s.ny; ++r)
       for (int c = 0; c < nx; ++c) out[(size_t)(T.row0 + r - 1) * nx + c] = T.area[T.s.idx(r, c)];

@@ -1,7 +1,7 @@
-"""The queue / count protocols of the level + walk sweep kernels (taudem_b200/csrc/sweep_walk.cu), executed on a
-CPU emulation of the CUDA thread model (tests/emu: fibers, warp collectives, randomised interleavings) and
-compared bit for bit with the oracle.  This checks protocol logic and arithmetic, not the GPU memory model —
-the GPU parity tests do that (TAUDEM_B200_SWEEP=levels|walk|hybrid in tests/test_gpu_parity.py)."""
+"""The kernels of taudem_b200/csrc (the warp-per-tile dataflow sweep with its scheduler / count protocols, the stencils,
+the flat resolution, pit removal, the outlet restriction), executed on a CPU emulation of the CUDA thread model
+(tests/emu: fibers, warp collectives, randomised interleavings) and compared bit for bit with the oracle.  This checks
+protocol logic and arithmetic, not the GPU memory model — the GPU parity tests (tests/test_gpu_parity.py) do that."""
 import ctypes as C
 import os
 import re
@@ -39,7 +39,7 @@ def _transform(name, min_launches=6):
 def _build(tag="", defines=()):
     os.makedirs(BUILD, exist_ok=True)
     _transform("rowfact", 1)
-    incs = [_transform("sweep_walk"), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("sweep_tiles", 5), _transform("fill", 3), _transform("sweep_warp", 4)]
+    incs = [_transform("sweep_warp", 4), _transform("flats")] + [_transform(n, 1) for n in STENCILS] + [_transform("outlets", 2), _transform("fill", 3)]
     so = os.path.join(BUILD, f"libemu{tag}.so")
     objs = []
     for i, n in enumerate(STENCILS):                       # one translation unit per kernel file (their helper names collide)
@@ -50,7 +50,7 @@ def _build(tag="", defines=()):
             subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-c", "-pthread", "-ftls-model=initial-exec", "-ffp-contract=off", "-I", EMU,
                                    "-I", BUILD, "-I", CSRC, f"-DEMU_WHICH={i + 1}", "-o", o, os.path.join(EMU, "stencil_driver.cpp")])
         objs.append(o)
-    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "tiles_driver.cpp", "warp_driver.cpp", "emu.cpp")] + objs
+    srcs = [os.path.join(EMU, f) for f in ("driver.cpp", "flats_driver.cpp", "fill_driver.cpp", "emu.cpp")] + objs
     deps = incs + srcs + [os.path.join(EMU, "cuda_runtime.h"), os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "dinf_common.cuh"),
                           os.path.join(CSRC, "ctx.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
@@ -65,8 +65,6 @@ def _build(tag="", defines=()):
     lib.emu_deps_d8.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_short]
     lib.emu_deps_dinf.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
     lib.emu_ref_deps.argtypes = [C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double]
-    lib.emu_tiles.argtypes = [C.c_int, C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_ulonglong, P]
-    lib.emu_wtiles.argtypes = [C.c_int, P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, C.c_ulonglong, P]
     lib.emu_fill.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_ulonglong]
     lib.emu_flats.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_ulonglong, C.c_void_p, C.c_void_p]
     return lib
@@ -103,29 +101,30 @@ def _run(lib, dinf, mode, passes, direction, w, contcheck, seed, nstrips=1, roun
     return out
 
 
-@pytest.mark.parametrize("mode,passes", [(0, 0), (1, 1), (1, 4), (1, 40), (1, -1)])
-def test_emulated_d8_sweeps_match_the_oracle(emu, fields, mode, passes):
+def test_emulated_d8_sweep_matches_the_oracle(emu, fields):
+    """The warp-per-tile dataflow sweep (sweep_warp.cu): every warp of the persistent CTA is an independent worker on 32 x 32
+    tiles (ticket queue, four-state tile protocol, shared ready queue); randomised interleavings of the workers."""
     port, p, _, w = fields
-    for seed in (1, 2):
-        assert_bits(_run(emu, False, mode, passes, p, None, True, seed), port.aread8(p), f"ad8 mode {mode}/{passes} seed {seed}")
-    assert_bits(_run(emu, False, mode, passes, p, w, False, 3), port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc")
+    for seed in (1, 2, 3):
+        assert_bits(_run(emu, False, 0, 0, p, None, True, seed), port.aread8(p), f"ad8 seed {seed}")
+    assert_bits(_run(emu, False, 0, 0, p, w, False, 4), port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc")
 
 
-@pytest.mark.parametrize("mode,passes", [(0, 0), (1, 1), (1, 4), (1, 40), (1, -1)])
-def test_emulated_dinf_sweeps_match_the_oracle(emu, fields, mode, passes):
+def test_emulated_dinf_sweep_matches_the_oracle(emu, fields):
+    """... D-infinity: row ready masks, fork stack, shares from the strip's prop() table with reciprocal divisions."""
     port, _, ang, w = fields
-    for seed in (1, 2):
-        assert_bits(_run(emu, True, mode, passes, ang, None, True, seed), port.areadinf(ang), f"sca mode {mode}/{passes} seed {seed}")
-    assert_bits(_run(emu, True, mode, passes, ang, w, False, 3), port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc")
+    for seed in (1, 2, 3):
+        assert_bits(_run(emu, True, 0, 0, ang, None, True, seed), port.areadinf(ang), f"sca seed {seed}")
+    assert_bits(_run(emu, True, 0, 0, ang, w, False, 4), port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc")
 
 
-def test_emulated_dinf_fork_stack_spills_to_the_global_list(fields):
-    """With a two-entry fork stack per warp nearly every fork spills: the host loop must drain the spill lists."""
-    port, _, ang, _ = fields
-    lib = _build("_wq2", ["TD_WALK_WQ=2", "TD_UP_UQ=4"])
-    for mode, passes, seed in ((0, 0, 7), (1, 3, 8)):
-        assert_bits(_run(lib, True, mode, passes, ang, None, True, seed), port.areadinf(ang), f"sca, spilling, mode {mode}")
-    # the outlet flood with a four-entry stack per warp: nearly every discovered contributor spills
+def test_emulated_small_stacks_spill(fields):
+    """A two-entry fork stack drops nearly every second receiver (the rescan of the shared-memory counts must find them);
+    the outlet flood with a four-entry stack per warp spills nearly every discovered contributor to the host-drained list."""
+    port, _, ang, w = fields
+    lib = _build("_wstk2", ["TD_WSTK=2", "TD_UP_UQ=4"])
+    assert_bits(_run(lib, True, 0, 0, ang, None, True, 7), port.areadinf(ang), "sca, fork stack of 2")
+    assert_bits(_run(lib, True, 0, 0, ang, w, False, 8), port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc, fork stack of 2")
     full = port.areadinf(ang)
     c = int(np.argsort(full.ravel())[-1]); outs = ([c % ang.shape[1]], [c // ang.shape[1]])
     assert_bits(_run(lib, True, 0, 0, ang, None, True, 9, outlets=outs), port.areadinf(ang, outlets=outs), "sca -o, spilling flood")
@@ -133,8 +132,8 @@ def test_emulated_dinf_fork_stack_spills_to_the_global_list(fields):
 
 @pytest.mark.parametrize("nstrips", [2, 3])
 def test_emulated_row_strips_with_exchange_rounds(emu, fields, nstrips):
-    """The multi-strip protocol of the level / walk sweeps (halo decrement counts, area rows, plain apply, re-collection
-    of the ready cells each round) reproduces the single-strip rasters."""
+    """The row-strip protocol of the sweep (halo decrement counts, area rows, k_wapply_halo re-activating the tiles whose
+    cells became ready, one kernel per round) reproduces the single-strip rasters."""
     port, p, ang, w = fields
     rounds = np.zeros(1, np.int32)
     assert_bits(_run(emu, False, 1, 3, p, None, True, 11, nstrips, rounds), port.aread8(p), "ad8 strips")
@@ -255,28 +254,6 @@ def test_emulated_d8_stencil_ties_and_near_ties(emu):
             assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
 
 
-@pytest.mark.parametrize("hops", [1, 3, 20])
-def test_emulated_d8_rivers_with_lookahead(emu, fields, hops, monkeypatch):
-    """TAUDEM_B200_RIVER: chains longer than `hops` cells are parked by k_walk and finished by k_river (one warp per
-    river, look-ahead along the static path, lane-to-lane fold) — same rasters, single strip and row strips."""
-    port, p, _, w = fields
-    monkeypatch.setenv("TAUDEM_B200_RIVER", str(hops))
-    assert_bits(_run(emu, False, 0, 0, p, None, True, 41), port.aread8(p), f"ad8 rivers hops={hops}")
-    assert_bits(_run(emu, False, 1, 2, p, w, False, 42), port.aread8(p, weights=w, contcheck=False), f"ad8 -wg -nc rivers hops={hops}")
-    assert_bits(_run(emu, False, 1, 2, p, None, True, 43, 3), port.aread8(p), f"ad8 rivers hops={hops}, 3 strips")
-
-
-@pytest.mark.parametrize("hops", [1, 4, 20])
-def test_emulated_dinf_rivers_with_lookahead(emu, fields, hops, monkeypatch):
-    """The same for D-infinity: the look-ahead runs through stretches of single-receiver cells; a two-receiver cell ends
-    a batch and its second ready receiver goes to the next launch."""
-    port, _, ang, w = fields
-    monkeypatch.setenv("TAUDEM_B200_RIVER_DINF", str(hops))
-    assert_bits(_run(emu, True, 0, 0, ang, None, True, 51), port.areadinf(ang), f"sca rivers hops={hops}")
-    assert_bits(_run(emu, True, 1, 2, ang, w, False, 52), port.areadinf(ang, weights=w, contcheck=False), f"sca -wg -nc rivers hops={hops}")
-    assert_bits(_run(emu, True, 1, 2, ang, None, True, 53, 3), port.areadinf(ang), f"sca rivers hops={hops}, 3 strips")
-
-
 def test_emulated_outlets_restrict_the_sweep(emu, fields):
     """-o: k_upstream floods the contributor links from the outlet cells, k_restrict removes every other cell from the
     flow field; the sweep then evaluates exactly what the reference's outlet branch evaluates."""
@@ -363,84 +340,17 @@ def test_emulated_pipeline_reproduces_the_reference_golden_vectors(emu, name):
     assert_bits(_run(emu, True, 1, 3, g["ang"], None, False, 88, dx=dx, dy=dy), g["sca_nc"], "sca -nc")
 
 
-# ---------------------------------------------------------------- the tile dataflow sweep (taudem_b200/csrc/sweep_tiles.cu)
-def _tiles(lib, dinf, hybrid, direction, w, contcheck, seed):
-    ny, nx = direction.shape
-    out = np.empty((ny, nx), np.float32)
-    d = np.ascontiguousarray(direction)
-    wp = None if w is None else np.ascontiguousarray(w, np.float32)
-    visits = np.zeros(1, np.uint64)
-    nodata = -3.4028234663852886e38 if dinf else -32768.0
-    rc = lib.emu_tiles(int(dinf), int(hybrid), d.ctypes.data, out.ctypes.data, None if wp is None else wp.ctypes.data, nx, ny, nodata,
-                       int(w is not None), int(contcheck), -9999.0, 30.0, 30.0, seed, visits.ctypes.data)
-    assert rc == 0
-    return out, int(visits[0])
-
-
-@pytest.mark.parametrize("hybrid", [0, 1])
-def test_emulated_tile_sweep(emu, fields, hybrid):
-    """The default sweep — persistent CTAs, ticket queue, four-state tile protocol, in-tile wavefront with its work queue
-    — and the `once` variant followed by the walkers ("hybrid"), under randomised thread interleavings."""
-    port, p, ang, w = fields
-    ntiles_d8 = -(-p.shape[1] // 64) * -(-p.shape[0] // 32)
-    a, visits = _tiles(emu, False, hybrid, p, None, True, 91)
-    assert_bits(a, port.aread8(p), f"ad8 tiles hybrid={hybrid}")
-    assert (visits == ntiles_d8) if hybrid else (visits > ntiles_d8)
-    assert_bits(_tiles(emu, False, hybrid, p, w, False, 92)[0], port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc tiles")
-    assert_bits(_tiles(emu, True, hybrid, ang, None, True, 93)[0], port.areadinf(ang), f"sca tiles hybrid={hybrid}")
-    assert_bits(_tiles(emu, True, hybrid, ang, w, False, 94)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc tiles")
-
-
-def _wtiles(lib, dinf, direction, w, contcheck, seed, dx=30.0, dy=30.0):
-    ny, nx = direction.shape
-    out = np.empty((ny, nx), np.float32)
-    d = np.ascontiguousarray(direction)
-    wp = None if w is None else np.ascontiguousarray(w, np.float32)
-    visits = np.zeros(1, np.uint64)
-    nodata = -3.4028234663852886e38 if dinf else -32768.0
-    os.environ["TAUDEM_B200_TIMING"] = "1"        # the visit counter is a statistic
-    try:
-        rc = lib.emu_wtiles(int(dinf), d.ctypes.data, out.ctypes.data, None if wp is None else wp.ctypes.data, nx, ny, nodata,
-                            int(w is not None), int(contcheck), -9999.0, dx, dy, seed, visits.ctypes.data)
-    finally:
-        os.environ.pop("TAUDEM_B200_TIMING", None)
-    assert rc == 0, rc
-    return out, int(visits[0])
-
-
-def test_emulated_warp_tile_sweep(emu, fields):
-    """The warp-per-tile dataflow sweep (sweep_warp.cu): every warp of the persistent CTA is an independent worker on
-    32 x 32 tiles; randomised interleavings of the eight workers; D8 / D-infinity, weights, no contamination check."""
-    port, p, ang, w = fields
-    ntiles = -(-p.shape[1] // 32) * -(-p.shape[0] // 32)
-    for seed in (101, 102, 103):
-        a, visits = _wtiles(emu, False, p, None, True, seed)
-        assert_bits(a, port.aread8(p), f"ad8 warp tiles seed {seed}")
-        assert visits > ntiles
-        assert_bits(_wtiles(emu, True, ang, None, True, seed)[0], port.areadinf(ang), f"sca warp tiles seed {seed}")
-    assert_bits(_wtiles(emu, False, p, w, False, 104)[0], port.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc warp tiles")
-    assert_bits(_wtiles(emu, True, ang, w, False, 105)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc warp tiles")
-
-
-def test_emulated_warp_tile_sweep_fork_stack_overflow(fields):
-    """A two-entry fork stack drops nearly every second receiver: the rescan of the shared-memory counts must find them."""
-    port, _, ang, w = fields
-    lib = _build("_wstk2", defines=("TD_WSTK=2",))
-    assert_bits(_wtiles(lib, True, ang, None, True, 121)[0], port.areadinf(ang), "sca, fork stack of 2")
-    assert_bits(_wtiles(lib, True, ang, w, False, 122)[0], port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc, fork stack of 2")
-
-
-def test_emulated_warp_tile_sweep_golden(emu):
-    """... and on the reference-generated golden vectors (nodata holes, dx != dy, plateau, lake, 5 x 7 grid)."""
+def test_emulated_sweep_on_the_reference_golden_vectors(emu):
+    """The sweep on the reference-generated golden vectors (nodata holes, dx != dy, plateau, lake, 5 x 7 grid)."""
     from util import golden_cases, load_golden
     for name in golden_cases():
         g = load_golden(name)
         dx, dy = float(g["dx"]), float(g["dy"])
-        assert_bits(_wtiles(emu, False, g["p"], None, True, 111)[0], g["ad8"], f"{name} ad8")
-        assert_bits(_wtiles(emu, False, g["p"], g["w"], True, 112)[0], g["ad8_w"], f"{name} ad8 -wg")
-        assert_bits(_wtiles(emu, True, g["ang"], None, True, 113, dx, dy)[0], g["sca"], f"{name} sca")
-        assert_bits(_wtiles(emu, True, g["ang"], g["w"], True, 114, dx, dy)[0], g["sca_w"], f"{name} sca -wg")
-        assert_bits(_wtiles(emu, True, g["ang"], None, False, 115, dx, dy)[0], g["sca_nc"], f"{name} sca -nc")
+        assert_bits(_run(emu, False, 0, 0, g["p"], None, True, 111, dx=dx, dy=dy), g["ad8"], f"{name} ad8")
+        assert_bits(_run(emu, False, 0, 0, g["p"], g["w"], True, 112, dx=dx, dy=dy), g["ad8_w"], f"{name} ad8 -wg")
+        assert_bits(_run(emu, True, 0, 0, g["ang"], None, True, 113, dx=dx, dy=dy), g["sca"], f"{name} sca")
+        assert_bits(_run(emu, True, 0, 0, g["ang"], g["w"], True, 114, dx=dx, dy=dy), g["sca_w"], f"{name} sca -wg")
+        assert_bits(_run(emu, True, 0, 0, g["ang"], None, False, 115, dx=dx, dy=dy), g["sca_nc"], f"{name} sca -nc")
 
 
 def test_emulated_pitremove(emu):
@@ -480,26 +390,22 @@ def test_emulated_flat_resolution_batched_levels(emu, terraces, batch, monkeypat
         assert_bits(_flats(emu, False, f, q0, 1, 103, float(g["dx"]), float(g["dy"]))[0], g["p"], f"{name} p, batch {batch}")
 
 
-def test_emulated_sweeps_on_a_larger_grid(emu, monkeypatch):
-    """500 x 700 cells (352 D8 tiles / 704 D-infinity tiles, rivers of several hundred cells): the default tile dataflow, level
-    passes + walkers + rivers, single strip and four strips."""
+def test_emulated_sweeps_on_a_larger_grid(emu):
+    """500 x 700 cells (352 tiles, rivers of several hundred cells): single strip and four strips."""
     from oracle import port
     dem = synth.punch_holes(synth.gen_dem(500, 700, hurst=0.8, tilt=1.0, seed=31))
     fel = port.pitremove(dem); p, _ = port.d8flowdir(fel); ang, _ = port.dinfflowdir(fel)
     ad8 = port.aread8(p); sca = port.areadinf(ang)
     assert ad8.max() > 1.0e4
-    assert_bits(_tiles(emu, False, 0, p, None, True, 201)[0], ad8, "ad8 tiles")
-    assert_bits(_tiles(emu, True, 0, ang, None, True, 202)[0], sca, "sca tiles")
-    monkeypatch.setenv("TAUDEM_B200_RIVER", "16"); monkeypatch.setenv("TAUDEM_B200_RIVER_DINF", "16")
-    assert_bits(_run(emu, False, 1, 6, p, None, True, 203), ad8, "ad8 levels + rivers")
-    assert_bits(_run(emu, True, 1, 6, ang, None, True, 204), sca, "sca levels + rivers")
-    assert_bits(_run(emu, False, 1, 6, p, None, True, 205, 4), ad8, "ad8 levels + rivers, 4 strips")
-    assert_bits(_run(emu, True, 1, 6, ang, None, True, 206, 4), sca, "sca levels + rivers, 4 strips")
+    assert_bits(_run(emu, False, 0, 0, p, None, True, 203), ad8, "ad8")
+    assert_bits(_run(emu, True, 0, 0, ang, None, True, 204), sca, "sca")
+    assert_bits(_run(emu, False, 0, 0, p, None, True, 205, 4), ad8, "ad8, 4 strips")
+    assert_bits(_run(emu, True, 0, 0, ang, None, True, 206, 4), sca, "sca, 4 strips")
 
 
 def test_emulated_random_configurations(emu):
-    """A short deterministic slice of scripts/emu_stress.py: random grid sizes, flats, holes, strip counts, level passes (incl.
-    auto), river thresholds, tile / hybrid sweeps and strip flats against the oracle."""
+    """A short deterministic slice of scripts/emu_stress.py: random grid sizes, flats, holes, strip counts, sweeps and strip
+    flats against the oracle."""
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "emu_stress.py"), "777", "14", "120"], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=600)

@@ -123,48 +123,21 @@ def test_properties_large():
     assert ad8[valid].min() >= 1.0
 
 
-def test_tile_sweep_equals_chain_sweep():
-    """The shared-memory tile dataflow and the first-generation global chain-following sweep are two
-    schedules of the same gather: bit-identical rasters at a size with many tile crossings."""
-    import os
+def test_sweep_with_many_tile_crossings_matches_the_reference(refrun):
+    """2100 x 3000 cells (6 200 tiles of the dataflow sweep, rivers that cross hundreds of tiles, thousands of tile
+    re-activations): ad8 bit for bit, sca within the tolerance, with and without weights, against the reference tools."""
     dem = synth.punch_holes(synth.gen_dem(2100, 3000, hurst=0.8, tilt=1.0, seed=9))
     w = synth.gen_weights(*dem.shape)
     fel = td.pitremove_grid(dem)
     p, _ = td.d8flowdir_grid(fel)
     ang, _ = td.dinfflowdir_grid(fel)
-    res = {}
-    for mode in ("tiles", "chain"):
-        os.environ["TAUDEM_B200_SWEEP"] = mode
-        try:
-            res[mode] = (td.aread8_grid(p), td.aread8_grid(p, weights=w, contcheck=False), td.areadinf_grid(ang), td.areadinf_grid(ang, weights=w, contcheck=False))
-        finally:
-            os.environ.pop("TAUDEM_B200_SWEEP", None)
-    for a, b, what in zip(res["tiles"], res["chain"], ("ad8", "ad8 -wg -nc", "sca", "sca -wg -nc")):
-        assert_bits(a, b, what)
-    assert res["tiles"][0].max() > 1e5
-
-
-@pytest.mark.skipif(__import__("os").environ.get("TAUDEM_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental sweep schedules (hybrid / walk): set TAUDEM_B200_TEST_EXPERIMENTAL=1")
-def test_experimental_sweep_schedules_equal_tile_sweep():
-    """TAUDEM_B200_SWEEP=hybrid (one tile pass + warp-level chain walking) and =walk (chain walking from the
-    sources) are further schedules of the same gather: bit-identical to the default, with and without weights."""
-    import os
-    dem = synth.punch_holes(synth.gen_dem(2100, 3000, hurst=0.8, tilt=1.0, seed=9))
-    w = synth.gen_weights(*dem.shape)
-    fel = td.pitremove_grid(dem)
-    p, _ = td.d8flowdir_grid(fel)
-    ang, _ = td.dinfflowdir_grid(fel)
-    res = {}
-    for mode in ("tiles", "hybrid", "walk"):
-        os.environ["TAUDEM_B200_SWEEP"] = mode
-        try:
-            res[mode] = (td.aread8_grid(p), td.aread8_grid(p, weights=w, contcheck=False), td.areadinf_grid(ang), td.areadinf_grid(ang, weights=w, contcheck=False))
-        finally:
-            os.environ.pop("TAUDEM_B200_SWEEP", None)
-    for mode in ("hybrid", "walk"):
-        for a, b, what in zip(res["tiles"], res[mode], ("ad8", "ad8 -wg -nc", "sca", "sca -wg -nc")):
-            assert_bits(a, b, f"{mode}: {what}")
+    R = refrun.RefPipeline(np_ranks=8)
+    ad8 = td.aread8_grid(p)
+    assert_bits(ad8, R.aread8(p), "ad8")
+    assert_bits(td.aread8_grid(p, weights=w, contcheck=False), R.aread8(p, weights=w, contcheck=False), "ad8 -wg -nc")
+    assert_float_parity(td.areadinf_grid(ang), R.areadinf(ang), "sca")
+    assert_float_parity(td.areadinf_grid(ang, weights=w, contcheck=False), R.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc")
+    assert ad8.max() > 1e5
 
 
 @pytest.mark.parametrize("world", [2, 3])
