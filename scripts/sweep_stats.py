@@ -3,7 +3,8 @@
   TAUDEM_B200_TIMING=1 python scripts/sweep_stats.py [n=16384] [reps=2]
 
 With TAUDEM_B200_TIMING=1 the kernel records, per tile visit, the cycles lane 0 spent waiting for a ticket, loading,
-running the wavefront and writing back, and a histogram of the visits by the number of cells they evaluated."""
+running the wavefront and writing back, the cells evaluated and the wavefront iterations.
+TAUDEM_B200_WORKERS=<n> (fewer workers per SM) and TAUDEM_B200_POLL=1 (plain nanosleep polling) are experiment knobs of the kernel."""
 import os
 import sys
 
@@ -42,9 +43,7 @@ def main():
             c = [T.l.td_ctx_counter(T.ctx, 24 + i) for i in range(8)]
             v = max(c[3], 1)
             line += f"\n    visits {c[3]} ({c[3] / ((n + 31) // 32) ** 2:.2f} per tile); cycles per visit: wait {c[4]//v} load {c[5]//v} wavefront {c[6]//v} write-back {c[7]//v}"
-            hh = [T.l.td_ctx_sweep_hist(T.ctx, i) for i in range(16)]
-            line += "\n    by cells per visit (<8, <32, <128, more): " + "  ".join(
-                f"[{hh[4*b]} visits, {hh[4*b+1]/max(hh[4*b],1):.0f} cells, {hh[4*b+2]/max(hh[4*b],1):.0f} iterations, {hh[4*b+3]/max(hh[4*b],1):.0f} cycles]" for b in range(4))
+            line += f"; cells/visit {c[1] / v:.0f}, wavefront iterations/visit {c[2] / v:.1f}, cycles/iteration {c[6] / max(c[2], 1):.0f}"
         print(line, flush=True)
         del out
 

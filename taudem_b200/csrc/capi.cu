@@ -165,8 +165,9 @@ static int upload_theta(td_ctx* ctx, const double* d_dxc, const double* d_dyc, i
   TD_CUDA(cudaStreamSynchronize(st));
   // one prop() table for the whole strip when every row has the same angle (projected rasters)
   bool uni = true;
-  for (int j = 1; j < ny && uni; j++) uni = th[j] == th[0];
+  for (int j = 1; j < ny && uni; j++) uni = th[j] == th[0] && dx[j] == dx[0];
   td::make_prop_row(th[0], uni, &ctx->prop);
+  ctx->dx0 = dx[0];
   return TD_OK;
 }
 

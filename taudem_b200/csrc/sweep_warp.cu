@@ -18,6 +18,7 @@
 //  * the kernel ends when no tile is queued or running.
 // Flow that crosses the strip boundary (one strip per GPU) is recorded in `halo` for the exchange rounds of the
 // row-strip driver (src/aread8.cpp:282-297, linearpart::addBorders).
+#include <stddef.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,32 +34,44 @@ namespace {
 constexpr int TS = 32;                                // tile edge (cells)
 constexpr int TC = TS * TS;                           // cells per tile
 constexpr int RH = TS + 2;                            // ring rows
-constexpr int RS = TS + 8;                            // ring row stride: columns c0-4 .. c0+35 (16-byte aligned rows), cell lx at lx + 4
+constexpr int RS = TS + 4;                            // ring row stride: cell lx of a tile row at lx + 4, its west neighbour at 3, its east neighbour at
+                                                      // 36 = slot 0 of the next row (slots 0..2 of a row are otherwise unused): rows stay 16-byte aligned
+constexpr int RN = RH * RS + 4;                       // ring array length (the east neighbour of the last ring row lives at RH * RS)
 #ifndef TD_WSTK
 #define TD_WSTK 128
 #endif
-constexpr int STKCAP = TD_WSTK;                       // fork stack entries per worker
-constexpr int EXTCAP = 256;                           // crossings of one visit: <= 124 perimeter cells x 2 receivers
+constexpr int STKCAP = TD_WSTK;                       // fork stack entries per worker (D-infinity)
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int C_HEAD = 0, C_TAIL = 16, C_PEND = 32;   // indices into WArgs::ctr (8-byte words): head ticket, tail ticket, queued + running tiles
 
+// neighbour offsets as 2-bit fields (value + 1) indexed by the direction k = 1..8
+constexpr unsigned pack_dir(bool row) {
+  unsigned v = 0;
+  for (int k = 1; k <= 8; ++k) v |= (unsigned)((row ? drow(k) : dcol(k)) + 1) << (2 * k);
+  return v;
+}
+constexpr unsigned DROW_LUT = pack_dir(true), DCOL_LUT = pack_dir(false);
+__device__ __forceinline__ int lut_drow(int k) { return (int)((DROW_LUT >> (2 * k)) & 3u) - 1; }
+__device__ __forceinline__ int lut_dcol(int k) { return (int)((DCOL_LUT >> (2 * k)) & 3u) - 1; }
+
 // one worker's shared memory: everything a visit touches while it runs the wavefront
 template <bool DINF>
 struct __align__(16) WarpMem {
-  float area[RH * RS];                    // areas of the tile and its ring (-1 = nodata / not final)
-  float ang[DINF ? RH * RS : 4];          // D-infinity: angles of the same cells
-  unsigned short node[RH * RS];           // node words of the same cells (D8 uses the interior only)
-  unsigned cnt[TC / 4];                   // dependency counts, four cells per word: 0..8, 0xFE = evaluated, 0xFF = not a node
-  double theta[DINF ? RH + 2 : 2];        // D-infinity: prop()'s row angle for every ring row
-  double dxr[DINF ? TS : 2];              // D-infinity: cell size of every tile row
-  unsigned short stk[DINF ? STKCAP : TC]; // D-infinity: second receivers that became ready (what does not fit is found again by a rescan of
-                                          // the counts); D8: the queue of the cells that are ready when the visit starts (any lane takes any)
-  unsigned short ext[EXTCAP];             // receivers outside the tile (ring index)
+  float area[RN];                         // areas of the tile and its ring (-1 = nodata / not final)
+  float ang[DINF ? RN : 4];               // D-infinity: angles of the same cells
+  unsigned short node[RN];                // node words of the same cells
+  alignas(16) unsigned cnt[TC / 4];       // dependency counts, four cells per word: 0..8 (0 = ready or evaluated by this visit), 0xFE = evaluated
+                                          // by an earlier visit, 0xFF = not a node
+  unsigned short stk[DINF ? STKCAP : 2];  // D-infinity: second receivers that became ready (what does not fit is found again by a rescan of the counts)
+  unsigned short ext[DINF ? 256 : 128];   // flow that leaves the tile: source cell | (direction - 1) << 10  (<= 124 perimeter cells x receivers)
   unsigned evmask[TS];                    // per tile row: cells evaluated by this visit
   int sp, next, dirty, pad;
 };
-template <bool DINF> constexpr int workers_per_cta() { return DINF ? 14 : 18; }
+template <bool DINF> constexpr int workers_per_cta() { return DINF ? 16 : 26; }
+static_assert(sizeof(WarpMem<false>) * workers_per_cta<false>() <= 227 * 1024 && sizeof(WarpMem<true>) * workers_per_cta<true>() + 512 <= 227 * 1024,
+              "the workers of a CTA must fit the shared memory of an SM");
+static_assert(offsetof(WarpMem<true>, ang) % 16 == 0 && offsetof(WarpMem<true>, node) % 8 == 0 && offsetof(WarpMem<false>, node) % 8 == 0, "cp.async alignment");
 
 // what a neighbouring strip exposes to this GPU (device pointers into the peer's memory)
 struct PeerStrip {
@@ -83,9 +96,10 @@ struct WArgs {
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;
   PropRow prop;            // D-infinity: the strip's prop() table (prop.uniform) — else per-row angles from `theta`
+  double dx0;              // D-infinity, uniform strips: the cell size every row adds (src/areadinf.cpp:216)
   unsigned long long* ctr; // scheduler words, one 128-byte line each (C_HEAD ...): every worker hammers them
-  unsigned long long* stat;// [3] visits, [4..7] cycle statistics (TAUDEM_B200_TIMING)
-  int stats;
+  unsigned long long* stat;// [1] cells, [2] wavefront iterations, [3] visits, [4..7] cycle statistics (TAUDEM_B200_TIMING)
+  int stats, poll;
   // peer mode (one strip per GPU, the neighbours' buffers mapped over NVLink with CUDA IPC): no exchange rounds — a tile
   // delivers into the neighbour GPU exactly as it delivers into a neighbour tile.  Every GPU only WRITES remote memory
   // (the neighbour's halo-area buffer, counts, tile states, queue); everything it reads is its own.
@@ -104,14 +118,17 @@ template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((c
 #ifndef TD_EMU
 __device__ __forceinline__ void cp16(void* smem, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
 __device__ __forceinline__ void cp8(void* smem, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp4(void* smem, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
 __device__ __forceinline__ void cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #else
-__device__ __forceinline__ void cp16(void* smem, const void* g) { emu::yield(); memcpy(smem, g, 16); }
-__device__ __forceinline__ void cp8(void* smem, const void* g) { memcpy(smem, g, 8); }
+__device__ __forceinline__ void cp_check(const void* smem, const void* g, size_t n) { if ((size_t)smem % n || (size_t)g % n) { fprintf(stderr, "emu: misaligned %zu-byte cp.async\n", n); abort(); } }
+__device__ __forceinline__ void cp16(void* smem, const void* g) { emu::yield(); cp_check(smem, g, 16); memcpy(smem, g, 16); }
+__device__ __forceinline__ void cp8(void* smem, const void* g) { cp_check(smem, g, 8); memcpy(smem, g, 8); }
+__device__ __forceinline__ void cp4(void* smem, const void* g) { cp_check(smem, g, 4); memcpy(smem, g, 4); }
 __device__ __forceinline__ void cp_wait_all() {}
 #endif
 
-// ---- scheduler (the protocol of the first-generation tile kernel, one lane per worker)
+// ---- scheduler (one lane per worker)
 // In peer mode a neighbour GPU operates on this strip's scheduler words and on the counts of its edge rows with
 // system-scope atomics over NVLink; the owner then uses system scope on the same words (atomics of different scopes on one
 // address are not guaranteed to be atomic with respect to each other).
@@ -179,9 +196,11 @@ __device__ __forceinline__ long long ld_relaxed(const unsigned long long* p) {
   long long v; asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 #endif
 }
-// waits about `cycles` SM cycles without touching memory (nanosleep alone returns after a few tens of nanoseconds
-// whatever it is asked for: measured 68 ns per poll with requests of 2 us — thousands of idle workers then hammer the L2)
-__device__ __forceinline__ void idle_wait(unsigned cycles) {
+// waits about `cycles` SM cycles without touching memory
+__device__ __forceinline__ void idle_wait(unsigned cycles, int plain) {
+#ifndef TD_EMU
+  if (plain) { __nanosleep(cycles >> 1); return; }
+#endif
 #ifdef TD_EMU
   (void)cycles; emu::yield();
 #else
@@ -205,7 +224,7 @@ __device__ int sched_pop(const WArgs& a) {
       return v - 1;
     }
     if ((++n & 7u) == 0u && ld_relaxed(a.peer ? a.G : a.ctr + C_PEND) <= 0) return -1;
-    idle_wait(wait);
+    idle_wait(wait, a.poll);
     if (wait < 4096) wait <<= 1;
   }
 }
@@ -221,8 +240,7 @@ __global__ void k_wsched_init(int* state, int* tq, unsigned qcap, int ntiles, un
   if ((int)i < ntiles) state[i] = 1;
   if (i == 0) {
     ctr[C_HEAD] = 0; ctr[C_TAIL] = (unsigned long long)ntiles; ctr[C_PEND] = (unsigned long long)ntiles;
-    stat[3] = stat[4] = stat[5] = stat[6] = stat[7] = 0;
-    for (int j = 40; j < 60; ++j) ctr[j] = 0;
+    for (int j = 1; j < 8; ++j) stat[j] = 0;
   }
 }
 
@@ -234,19 +252,19 @@ __device__ __noinline__ double wshare_full(float ang, double t, int kk) {
 
 // The share prop(av, kk) of a contributor (angle av, node word nn) for its receiver in direction kk, from the strip's
 // table.  The contributor's first receiver k1 (node word) is the sector j of its angle or the sector after it — one
-// comparison; kk is then j (share (ar[j+1] - a) / den[j] above the sector's lower edge, (a - ar[j-1]) / den[j-1] on it) or
-// j + 1 (share (a - ar[j]) / den[j]): prop()'s / dinf_outflow's expressions with the division by a table constant
-// (div_const).  Direction 1 reached through the end of the table (the float-rounded a - 2 PI of src/commonLib.cpp:82)
-// and angles outside [0, 2 PI) go through the interval search (rare, out of line).
+// comparison; kk is then j (share (ar[j+1] - a) / den[j]; for a == ar[j] numerator and denominator are the same double, the
+// share is 1 exactly as prop()'s (a - ar[j-1]) / (ar[j] - ar[j-1]) is) or j + 1 (share (a - ar[j]) / den[j]): prop()'s /
+// dinf_outflow's expressions with the division by a table constant (div_const).  Direction 1 reached through the end of the
+// table (the float-rounded a - 2 PI of src/commonLib.cpp:82) and angles outside [0, 2 PI) go through the interval search
+// (rare, out of line).
 __device__ __forceinline__ double wshare_tab(const PropRow& P, float av, unsigned nn, int kk) {
   const int k1 = (int)((nn >> 8) & 0xfu);
   const double a = (double)av;
   const int j = k1 - 1 + (a >= P.ar[k1 & 7 ? k1 : 8] ? 1 : 0);
   if ((k1 == 1 && a >= P.ar[8]) || (j == 8 && kk == 1) || av < 0.f || k1 < 1 || k1 > 8) return wshare_full(av, P.ar[2], kk);
-  const bool isA = kk == j, up = a > P.ar[j];
-  const int d = (isA && !up) ? j - 1 : j;
-  const double num = (isA && up) ? P.ar[j + 1] - a : a - P.ar[d];
-  return P.safe ? div_const(num, P.den[d], P.rden[d]) : num / P.den[d];
+  const bool isA = kk == j;
+  const double num = isA ? P.ar[j + 1] - a : a - P.ar[j];
+  return P.safe ? div_const(num, P.den[j], P.rden[j]) : num / P.den[j];
 }
 
 // bit 7 of every byte of the result is set exactly where that byte of w is zero (no borrow between bytes)
@@ -257,7 +275,7 @@ __device__ __forceinline__ unsigned zero_nibble(unsigned w) {
   return ((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u);
 }
 
-template <bool DINF>
+template <bool DINF, bool USEW>
 __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(const WArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   using Mem = WarpMem<DINF>;
@@ -297,16 +315,16 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
     if (lane == 0) { M.sp = 0; M.next = 0; M.dirty = 0; }
     __threadfence();          // the counts first, then the areas they announce (loaded by other lanes: barrier in between)
     __syncwarp();
-    // ---- 2. areas (+ node words, angles) of the tile and its ring: asynchronous 16-byte copies straight into shared memory,
-    //         all in flight at once (one round trip); what lies off the strip is filled in directly
+    // ---- 2. areas, node words (and angles) of the tile and its ring: asynchronous copies straight into shared memory, all in
+    //         flight at once (one round trip); what lies below the strip is filled in directly
 #pragma unroll
-    for (int j = 0; j < (RH * (RS / 4) + 31) / 32; ++j) {
+    for (int j = 0; j < (RH * 8 + 31) / 32; ++j) {
       const int i = lane + 32 * j;
-      if (i < RH * (RS / 4)) {
-        const int rr = i / (RS / 4), q = i - rr * (RS / 4);
-        const int r = r0 - 1 + rr, c = c0 - 4 + 4 * q;
-        const int so = rr * RS + 4 * q;
-        if (r >= 0 && r <= s.ny + 1 && c >= 0 && c < s.pitch) {
+      if (i < RH * 8) {
+        const int rr = i >> 3, q = i & 7;
+        const int r = r0 - 1 + rr, c = c0 + 4 * q;
+        const int so = rr * RS + 4 + 4 * q;
+        if (r <= s.ny + 1) {
           const long long g = s.idx(r, c);
           if (a.peer && (r == 0 || r == s.ny + 1)) cp16(M.area + so, a.halo_in + (r == 0 ? 0 : s.pitch) + c);
           else cp16(M.area + so, a.area + g);
@@ -319,27 +337,40 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
         }
       }
     }
-    if (DINF) {
-      // prop()'s row angle of every ring row (clamped to the strip's rows like the dependency stencil does), cell sizes of the tile rows
-      for (int i = lane; i < RH; i += 32) M.theta[i] = a.theta[min(max(r0 - 2 + i, 0), s.ny - 1)];
-      M.dxr[lane] = a.dxc[min(r0 + lane, s.ny) - 1];
+    // the ring columns: the west neighbours at slot 3 of their row (node words: two cells, slots 2 and 3), the east
+    // neighbours at slot 36 (node words: slots 36 and 37)
+#pragma unroll
+    for (int rr = lane; rr < RH; rr += 32) {
+      const int r = r0 - 1 + rr;
+      const bool rowok = r <= s.ny + 1;
+      const bool halo_row = a.peer && (r == 0 || r == s.ny + 1);
+      const float* hrow = a.halo_in + (r == 0 ? 0 : s.pitch);
+      const int sw = rr * RS + 3, se = rr * RS + RS;
+      if (rowok && c0 > 0) {
+        const long long g = s.idx(r, c0 - 1);
+        cp4(M.area + sw, halo_row ? hrow + (c0 - 1) : a.area + g);
+        if (DINF) cp4(M.ang + sw, a.ang + g);
+        cp4(M.node + sw - 1, a.node + g - 1);
+      } else {
+        M.area[sw] = -1.f;
+        if (DINF) M.ang[sw] = 0.f;
+        M.node[sw - 1] = 0; M.node[sw] = 0;
+      }
+      if (rowok && c0 + TS < s.pitch) {
+        const long long g = s.idx(r, c0 + TS);
+        cp4(M.area + se, halo_row ? hrow + (c0 + TS) : a.area + g);
+        if (DINF) cp4(M.ang + se, a.ang + g);
+        cp4(M.node + se, a.node + g);
+      } else {
+        M.area[se] = -1.f;
+        if (DINF) M.ang[se] = 0.f;
+        M.node[se] = 0; M.node[se + 1] = 0;
+      }
     }
     // ---- 3. cells that are ready (count 0): every lane keeps the ready cells of its own tile row as a bit mask
     unsigned rdy = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) rdy |= zero_nibble(g0[j]) << (4 * j);
-    int qn = 0;                    // D8: length of the ready queue (warp-uniform)
-    if (!DINF) {
-      // chains never fork: every ready cell of the visit is known now; a shared queue keeps all lanes busy
-      const int n = __popc(rdy);
-      int incl = n;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-      int pos = incl - n;
-      for (unsigned m = rdy; m; m &= m - 1u) M.stk[pos++] = (unsigned short)(lane * TS + __ffs(m) - 1);
-      qn = __shfl_sync(FULL, incl, 31);
-      rdy = 0;
-    }
     cp_wait_all();
     __syncwarp();
     if (a.stats && lane == 0) tk2 = clock64();
@@ -347,20 +378,9 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
     // ---- 4. the wavefront inside the tile: one chain per lane; an idle lane goes on with the next ready cell of its own
     //         row, then (D-infinity) with a cell from the warp's fork stack
     int cur = -1;
-    int iters = 0, qh = 0;
+    int iters = 0;
     for (;;) {
-      ++iters;
-
       if (cur < 0 && rdy) { const int b = __ffs(rdy) - 1; rdy &= rdy - 1; cur = lane * TS + b; }
-      if (!DINF) {
-        const unsigned idle = __ballot_sync(FULL, cur < 0);
-        if (idle && qh < qn) {
-          const int take = min(__popc(idle), qn - qh);
-          const int rank = __popc(idle & lt);
-          if (cur < 0 && rank < take) cur = M.stk[qh + rank];
-          qh += take;
-        }
-      }
       if (DINF) {
         const unsigned idle = __ballot_sync(FULL, cur < 0);
         if (idle) {
@@ -376,16 +396,21 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       }
       if (__ballot_sync(FULL, cur >= 0) == 0u) {
         if (!DINF) break;
-        // forks that did not fit the stack are still ready (count 0) in shared memory: look once more
+        // forks that did not fit the stack are ready (count 0) and not evaluated: look once more
+        const unsigned ev = M.evmask[lane];
 #pragma unroll
         for (int j = 0; j < 8; ++j) rdy |= zero_nibble(M.cnt[lane * 8 + j]) << (4 * j);
+        rdy &= ~ev;
         if (__ballot_sync(FULL, rdy != 0u) == 0u) break;
         continue;
       }
+      ++iters;
       if (cur >= 0) {
         const int l = cur;
         const int lr = l >> 5, lx = l & 31;
         const int ri = (lr + 1) * RS + lx + 4;
+        float wv = 0.f;
+        if (USEW) wv = a.w[s.idx(r0 + lr, c0 + lx)];
         const unsigned nd = M.node[ri];
         const unsigned msk = nd & 0xffu;
         bool con = (nd & NODE_CON) != 0;
@@ -393,14 +418,28 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
         int cont = -1;
         if (!DINF) {
           // src/aread8.cpp:228-257
-          if (a.usew) { const float wv = a.w[s.idx(r0 + lr, c0 + lx)]; val = nd_f(wv, a.w_nodata) ? -1.0f : wv; }
-          else val = 1.0f;
+          if (USEW) {
+            val = nd_f(wv, a.w_nodata) ? -1.0f : wv;
 #pragma unroll
-          for (int k = 1; k <= 8; ++k)
-            if (msk & (1u << (k - 1))) {
-              const float an = M.area[ri + drow(k) * RS + dcol(k)];
-              if (nd_f(an, -1.0f)) con = true; else val = val + an;
-            }
+            for (int k = 1; k <= 8; ++k)
+              if (msk & (1u << (k - 1))) {
+                const float an = M.area[ri + drow(k) * RS + dcol(k)];
+                if (nd_f(an, -1.0f)) con = true; else val = val + an;
+              }
+          } else {
+            // no weights: an area is -1 (nodata: contaminated) or a positive count, and a contaminated contributor
+            // contaminates the cell — its value does not matter then
+            val = 1.0f;
+            float mn = 0.f;
+#pragma unroll
+            for (int k = 1; k <= 8; ++k)
+              if (msk & (1u << (k - 1))) {
+                const float an = M.area[ri + drow(k) * RS + dcol(k)];
+                val = val + an;
+                mn = fminf(mn, an);
+              }
+            if (mn < 0.f) con = true;          // (with -nc no area is ever -1 when it is gathered)
+          }
         } else {
           // src/areadinf.cpp:187-218.  The share a contributor sends here is prop(its angle, direction to me): for a
           // contributor with two receivers in one of the sectors 1..7 its node word says which sector (k1, k1 + 1), so
@@ -412,7 +451,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
 #pragma unroll 1
           for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
             const int k = __ffs(m);
-            const int dr = drow(k), dc = dcol(k);
+            const int dr = lut_drow(k), dc = lut_dcol(k);
             const int ni = ri + dr * RS + dc;
             const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
             const int rn = r + dr;
@@ -422,7 +461,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
             double p;
             if (sprop.uniform && rn >= 1 && rn <= s.ny) p = wshare_tab(sprop, av, nn, kk);
             else {
-              const double th = M.theta[lr + 1 + dr];
+              const double th = a.theta[min(max(rn - 1, 0), s.ny - 1)];
               const int k1n = (nn >> 8) & 0xf;
               if ((nn & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
                 const double mid = aref(k1n, th), hi = aref(k1n + 1, th);
@@ -431,23 +470,23 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
             }
             if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
           }
-          if (a.usew) val = val + a.w[s.idx(r, c0 + lx)];
-          else val = (float)((double)val + M.dxr[lr]);
+          if (USEW) val = val + wv;
+          else val = (float)((double)val + (sprop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]));
         }
         if (con && a.contcheck) val = -1.0f;
         M.area[ri] = val;
-        atomicAdd(&M.cnt[l >> 2], 0xfeu << ((unsigned)(l & 3) * 8u));     // 0 -> 0xFE (evaluated)
         atomicOr(&M.evmask[lr], 1u << lx);
-        __threadfence_block();     // the area is in shared memory before any count says so
+        // (the areas are in shared memory before the counts that announce them are read: every lane that continues with a
+        //  receiver does so after the __syncwarp() that ends this iteration)
         // ---- the receivers: src/aread8.cpp:261-272, src/areadinf.cpp:221-239
 #pragma unroll
         for (int j = 0; j < (DINF ? 2 : 1); ++j) {
           int k;
           if (!DINF) k = (int)((nd >> 8) & 0xfu);
-          else { const int k1 = (int)((nd >> 8) & 0xfu); k = j == 0 ? k1 : ((nd & 0x2000u) ? k1 % 8 + 1 : 0); }
+          else { const int k1 = (int)((nd >> 8) & 0xfu); k = j == 0 ? k1 : ((nd & 0x2000u) ? (k1 & 7) + 1 : 0); }
           if (k < 1 || k > 8) continue;
-          const int nlr = lr + drow(k), nlx = lx + dcol(k);
-          if (nlr >= 0 && nlr < TS && nlx >= 0 && nlx < TS && r0 + nlr <= s.ny) {       // a cell of this tile
+          const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
+          if ((unsigned)nlr < (unsigned)TS && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {       // a cell of this tile
             const int l2 = nlr * TS + nlx;
             const unsigned sh = (unsigned)(l2 & 3) * 8u;
             const unsigned old = atomicSub(&M.cnt[l2 >> 2], 1u << sh);
@@ -456,45 +495,47 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
               else { const int slot = atomicAdd(&M.sp, 1); if (slot < STKCAP) M.stk[slot] = (unsigned short)l2; }   // a second ready receiver: an idle lane takes it
             }
           } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
-            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)(((nlr + 1) * RS + nlx + 4) | (lx << 11));   // receiver (ring index) | source column
+            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)(l | ((k - 1) << 10));
           }
         }
         cur = cont;
       }
-      __syncwarp();              // counts first, then the areas they announce (next iteration)
+      __syncwarp();              // areas and counts of this iteration are visible to every lane in the next one
     }
 
     if (a.stats && lane == 0) tk3 = clock64();
 
-    // ---- 5. write back what this visit evaluated, then publish counts and deliver the crossings
-#pragma unroll
-    for (int lr = 0; lr < TS; ++lr)
-      if ((M.evmask[lr] >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RS + lane + 4];
-    __threadfence();
+    // ---- 5. write back what this visit evaluated (row by row, only rows with evaluated cells), then publish counts and
+    //         deliver the crossings
+    const unsigned ev = M.evmask[lane];
+    for (unsigned rows = __ballot_sync(FULL, ev != 0u); rows; rows &= rows - 1u) {
+      const int lr = __ffs(rows) - 1;
+      const unsigned evr = __shfl_sync(FULL, ev, lr);
+      if ((evr >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RS + lane + 4];
+    }
     __syncwarp();
-    __threadfence();          // release by the lanes that publish: the other lanes' area stores are ordered before their atomics
+    __threadfence();          // release by the lanes that publish: every lane's area stores (ordered by the barrier) before their atomics
     {
+      // The shared-memory count of a cell this visit evaluated is 0, of any other cell its count at the start minus the
+      // arrivals from inside the tile; bytes >= 0x80 (not a node / evaluated before: flow into a cell without a direction
+      // still decrements them in shared memory) keep their value.  One 32-bit add per changed word carries all four cells
+      // (every byte of the sum stays within 0..0xFE, so nothing carries between bytes): evaluated -> 0xFE, others minus the
+      // local arrivals.  A zero byte in the result is a cell that became ready through arrivals from outside meanwhile.
       const int r = r0 + lane;
       bool dirty = false;
       if (r <= s.ny) {
         unsigned* gw = a.cntw + (s.idx(r, c0) >> 2);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const unsigned was = g0[j], now = M.cnt[lane * 8 + j];
-          if (was == now) continue;
-          unsigned delta = 0; int dec[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int b = (int)((was >> (8 * i)) & 0xffu), n = (int)((now >> (8 * i)) & 0xffu);
-            const int ci = b <= 8 ? n - b : 0;                  // evaluated: 0xFE - b; else minus the local arrivals
-            dec[i] = ci;
-            delta += (unsigned)ci << (8 * i);
-          }
-          if (delta != 0) {
+          const unsigned was = g0[j];
+          unsigned now = M.cnt[lane * 8 + j];
+          const unsigned keep = ((was >> 7) & 0x01010101u) * 0xffu;
+          now = (now & ~keep) | (was & keep);
+          const unsigned e4 = (ev >> (4 * j)) & 0xfu;
+          const unsigned delta = now - was + ((e4 * 0x00204081u) & 0x01010101u) * 0xfeu;
+          if (delta != 0u) {
             const unsigned old = W_ADD(gw + j, delta);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (dec[i] < 0 && (int)((old >> (8 * i)) & 0xffu) + dec[i] == 0) dirty = true;   // became ready meanwhile
+            if (zero_bytes(old + delta)) dirty = true;
           }
         }
       }
@@ -503,19 +544,18 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
     __syncwarp();
     const int ne = M.next;
     for (int e = lane; e < ne; e += 32) {
-      const int code = M.ext[e] & 0x7ff, lxs = M.ext[e] >> 11;
-      const int rr = code / RS, rc = code - rr * RS;
-      const int r = r0 - 1 + rr, c = c0 - 4 + rc;
+      const int l = M.ext[e] & 0x3ff, k = (M.ext[e] >> 10) + 1;
+      const int lr = l >> 5, lx = l & 31;
+      const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
+      const int r = r0 + nlr, c = c0 + nlx;
       if (r == 0 || r == s.ny + 1) {
-        if (a.peer) {      // the source is a cell of my first / last row: its area is still in shared memory
-          const int lrs = r == 0 ? 0 : s.ny - r0;
-          deliver_peer(a, r == 0, c0 + lxs, M.area[(lrs + 1) * RS + lxs + 4], c);
-        } else atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1);
+        if (a.peer) deliver_peer(a, r == 0, c0 + lx, M.area[(lr + 1) * RS + lx + 4], c);   // the source's area is still in shared memory
+        else atomicAdd(a.halo + (r == 0 ? 0 : s.pitch) + c, 1);
         continue;
       }
-      const long long ci = s.idx(r, c);
-      const unsigned ndr = (unsigned)M.node[code];
+      const unsigned ndr = (unsigned)M.node[(nlr + 1) * RS + nlx + 4];
       if (!(ndr & NODE_VALID)) continue;
+      const long long ci = s.idx(r, c);
       const unsigned sh = (unsigned)(ci & 3) * 8u;
       const unsigned old = W_ADD(a.cntw + (ci >> 2), 0u - (1u << sh));
       if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
@@ -524,20 +564,21 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
     if (lane == 0) {
       if (M.dirty) sched_activate(a, t);
       sched_finish(a, t);
-      if (a.stats) {
+    }
+    if (a.stats) {
+      const int ncell = __popc(ev);
+      int tot = ncell;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
+      if (lane == 0) {
         const long long tk4 = clock64();
         atomicAdd(a.stat + 3, 1ull);
         atomicAdd(a.stat + 4, (unsigned long long)(tk1 - tk0));
         atomicAdd(a.stat + 5, (unsigned long long)(tk2 - tk1));
         atomicAdd(a.stat + 6, (unsigned long long)(tk3 - tk2));
         atomicAdd(a.stat + 7, (unsigned long long)(tk4 - tk3));
-        // by size of the visit (cells evaluated: < 8, < 32, < 128, more): visits, cells, wavefront iterations, wavefront cycles
-        int ncell = 0;
-        for (int i = 0; i < TS; ++i) ncell += __popc(M.evmask[i]);
-        const int bin = ncell < 8 ? 0 : ncell < 32 ? 1 : ncell < 128 ? 2 : 3;
-        unsigned long long* h = a.ctr + 40 + 4 * bin;
-        atomicAdd(h, 1ull); atomicAdd(h + 1, (unsigned long long)ncell); atomicAdd(h + 2, (unsigned long long)iters);
-        atomicAdd(h + 3, (unsigned long long)(tk3 - tk2));
+        atomicAdd(a.stat + 1, (unsigned long long)tot);
+        atomicAdd(a.stat + 2, (unsigned long long)iters);
       }
     }
     __syncwarp();
@@ -569,9 +610,9 @@ __global__ void k_wsched_reset(unsigned long long* ctr) { if (threadIdx.x == 0) 
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
-  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
+  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
   a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + TS - 1) / TS;
-  a.stats = 0;
+  a.stats = 0; a.poll = 0;
   a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
   const long long nt = (long long)a.ntx * a.nty;
   if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
@@ -637,11 +678,16 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   }
   const char* te = getenv("TAUDEM_B200_TIMING");
   a.stats = (te && atoi(te) > 0) ? 1 : 0;
-  const int warps = dinf ? workers_per_cta<true>() : workers_per_cta<false>();
+  const char* pe = getenv("TAUDEM_B200_POLL");
+  a.poll = (pe && atoi(pe) > 0) ? 1 : 0;
+  a.dx0 = ctx->dx0;
+  int warps = dinf ? workers_per_cta<true>() : workers_per_cta<false>();
+  if (const char* we = getenv("TAUDEM_B200_WORKERS")) { const int v = atoi(we); if (v >= 1 && v < warps) warps = v; }   // experiments: fewer workers per SM
   const size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
-  const void* kern = dinf ? (const void*)k_sweep_warp<true> : (const void*)k_sweep_warp<false>;
-  int& per_dev = dinf ? ctx->wgrid_dinf : ctx->wgrid_d8;
-  if (!per_dev) {
+  const void* kern = dinf ? (usew ? (const void*)k_sweep_warp<true, true> : (const void*)k_sweep_warp<true, false>)
+                          : (usew ? (const void*)k_sweep_warp<false, true> : (const void*)k_sweep_warp<false, false>);
+  int& per_dev = ctx->wgrid[(dinf ? 2 : 0) + (usew ? 1 : 0)];
+  if (!per_dev || getenv("TAUDEM_B200_WORKERS")) {
     int dev = 0, sms = 0, occ = 0;
     TD_CUDA(cudaGetDevice(&dev));
     TD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -652,8 +698,8 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   }
   const long long nt = (long long)a.ntx * a.nty;
   const int g = (int)std::min<long long>(per_dev, (nt + warps - 1) / warps);
-  if (dinf) k_sweep_warp<true><<<g, warps * 32, smem, st>>>(a);
-  else k_sweep_warp<false><<<g, warps * 32, smem, st>>>(a);
+  if (dinf) { if (usew) k_sweep_warp<true, true><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false><<<g, warps * 32, smem, st>>>(a); }
+  else { if (usew) k_sweep_warp<false, true><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<false, false><<<g, warps * 32, smem, st>>>(a); }
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;

@@ -155,7 +155,7 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   }
   bool first = true;
   int rounds = 0;
-  for (auto& T : S) td::make_prop_row(T.theta[0], true, &T.ctx.prop);
+  for (auto& T : S) { td::make_prop_row(T.theta[0], true, &T.ctx.prop); T.ctx.dx0 = dx; }
   for (;;) {
     for (auto& T : S) {
       std::fill(T.halo.begin(), T.halo.end(), 0);

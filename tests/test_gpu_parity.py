@@ -275,9 +275,6 @@ def test_d8_stencil_ties_and_near_ties():
             assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TAUDEM_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="-o outlets were built after the round's GPU budget was spent (checked on the CPU emulation): "
-                           "set TAUDEM_B200_TEST_EXPERIMENTAL=1; scripts/gpu_validate_new.sh runs it")
 def test_outlets_grid_and_file_level(refrun, tmp_path):
     """aread8 / areadinf -o: the cells upstream of the outlets only.  Grid level against the C restatement (which the
     CPU suite pins on the reference tools), file level (our executables with a point shapefile) against the reference
