@@ -228,8 +228,8 @@ int td_area_sweep_run_dev(td_ctx*, const float* ang, const float* w, float* sca,
  * then td_sweep_peer_begin_dev + a barrier + ONE td_*_sweep_run_dev per rank complete the whole sweep:
  * tiles deliver into the neighbour GPU over NVLink (remote store + system-scope atomics) and queue its
  * tiles directly.  td_sweep_peer_off_dev returns to the round-based mode.                                */
-int td_sweep_peer_export_dev(td_ctx*, td_strip s, int dinf, unsigned char* handles_5x64, int* meta_5, void* stream);
-int td_sweep_peer_connect_dev(td_ctx*, int which, const unsigned char* handles_5x64, const int* meta_5);
+int td_sweep_peer_export_dev(td_ctx*, td_strip s, int dinf, unsigned char* handles_5x64, int* meta_8, void* stream);
+int td_sweep_peer_connect_dev(td_ctx*, int which, const unsigned char* handles_5x64, const int* meta_8);
 int td_sweep_peer_begin_dev(td_ctx*, td_strip s, void* stream);
 void td_sweep_peer_off_dev(td_ctx*);
 

@@ -297,12 +297,12 @@ int td_area_sweep_run_dev(td_ctx* ctx, const float* ang, const float* w, float* 
 
 // ---- peer mode of the partitioned sweeps: neighbours' counts / tile queues / halo buffers mapped over
 // NVLink with CUDA IPC; the sweep kernel then delivers across GPUs itself and no exchange rounds exist.
-int td_sweep_peer_export_dev(td_ctx* ctx, td_strip s, int dinf, unsigned char* handles_5x64, int* meta_5, void* stream) {
+int td_sweep_peer_export_dev(td_ctx* ctx, td_strip s, int dinf, unsigned char* handles_5x64, int* meta_8, void* stream) {
   if (int rc = check_strip(s)) return rc;
-  return td::sweep_peer_export(ctx, Strip(s), dinf, handles_5x64, meta_5, (cudaStream_t)stream);
+  return td::sweep_peer_export(ctx, Strip(s), dinf, handles_5x64, meta_8, (cudaStream_t)stream);
 }
-int td_sweep_peer_connect_dev(td_ctx* ctx, int which, const unsigned char* handles_5x64, const int* meta_5) {
-  return td::sweep_peer_connect(ctx, which, handles_5x64, meta_5);
+int td_sweep_peer_connect_dev(td_ctx* ctx, int which, const unsigned char* handles_5x64, const int* meta_8) {
+  return td::sweep_peer_connect(ctx, which, handles_5x64, meta_8);
 }
 int td_sweep_peer_begin_dev(td_ctx* ctx, td_strip s, void* stream) {
   if (int rc = check_strip(s)) return rc;

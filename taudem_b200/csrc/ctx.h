@@ -38,7 +38,7 @@ struct td_ctx {
   Buf rowfact;   // per-row constants of the flow-direction stencils (rowfact.cuh)
   Buf io[4];     // raster strips of host-grid level calls
   // peer mode of the sweeps (neighbour strips' buffers opened through CUDA IPC, see sweep_warp.cu)
-  struct PeerInfo { void *cntw = nullptr, *tileflags = nullptr, *dctr = nullptr, *halo_in = nullptr; int qmask = 0, ntx = 0, ny = 0, th = 0, nt = 0, valid = 0; };
+  struct PeerInfo { void *cntw = nullptr, *tileflags = nullptr, *dctr = nullptr, *halo_in = nullptr; int qmask = 0, ntx = 0, ny = 0, th = 0, nt = 0, valid = 0, nsh = 1, qshift = 0; };
   PeerInfo peer_up, peer_down;
   void* peer_G = nullptr;                // global pending counter (rank 0's gbuf)
   bool peer_G_opened = false;

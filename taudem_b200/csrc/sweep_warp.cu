@@ -43,7 +43,15 @@ constexpr int RN = RH * RS + 4;                       // ring array length (the 
 constexpr int STKCAP = TD_WSTK;                       // fork stack entries per worker (D-infinity)
 constexpr unsigned NODE_VALID = 0x8000u, NODE_CON = 0x1000u;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int C_HEAD = 0, C_TAIL = 16, C_PEND = 32;   // indices into WArgs::ctr (8-byte words): head ticket, tail ticket, queued + running tiles
+// The scheduler's words (WArgs::ctr, 8-byte words, one 128-byte line each).  The ticket queue is cut into up to MAXSH
+// independent shards (tile t belongs to shard t & (nsh - 1), worker w pops from shard w & (nsh - 1)): one queue's head /
+// tail / finished counters were the throughput limit of the whole sweep (three hot addresses, ~7 ns per atomic each).
+#ifdef TD_EMU
+constexpr int MAXSH = 8;     // the CPU emulation runs the CTAs one after the other: the first one alone must serve every shard
+#else
+constexpr int MAXSH = 64;
+#endif
+constexpr int C_TERM = 3 * MAXSH * 16, C_ACTIVE = (3 * MAXSH + 1) * 16, C_WORDS = (3 * MAXSH + 2) * 16;
 
 // neighbour offsets as 2-bit fields (value + 1) indexed by the direction k = 1..8
 constexpr unsigned pack_dir(bool row) {
@@ -76,7 +84,7 @@ static_assert(offsetof(WarpMem<true>, ang) % 16 == 0 && offsetof(WarpMem<true>, 
 // what a neighbouring strip exposes to this GPU (device pointers into the peer's memory)
 struct PeerStrip {
   unsigned* cntw = nullptr; int* state = nullptr; int* tq = nullptr; unsigned long long* ctr = nullptr; float* halo_in = nullptr;
-  unsigned qmask = 0; int ntx = 0, ny = 0, valid = 0;
+  unsigned qmask = 0; int ntx = 0, ny = 0, valid = 0, nsh = 1, qshift = 0;
 };
 
 struct WArgs {
@@ -94,10 +102,11 @@ struct WArgs {
   int ntx, nty;
   int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
   int* tq;                 // ring of tile ids + 1
-  unsigned qmask;
+  unsigned qmask;          // slots of one shard's ring - 1
+  int nsh, qshift;         // queue shards (a power of two), log2 of a shard's ring size
   PropRow prop;            // D-infinity: the strip's prop() table (prop.uniform) — else per-row angles from `theta`
   double dx0;              // D-infinity, uniform strips: the cell size every row adds (src/areadinf.cpp:216)
-  unsigned long long* ctr; // scheduler words, one 128-byte line each (C_HEAD ...): every worker hammers them
+  unsigned long long* ctr; // scheduler words (see MAXSH)
   unsigned long long* stat;// [1] cells, [2] wavefront iterations, [3] visits, [4..7] cycle statistics (TAUDEM_B200_TIMING)
   int stats, poll;
   // peer mode (one strip per GPU, the neighbours' buffers mapped over NVLink with CUDA IPC): no exchange rounds — a tile
@@ -105,7 +114,7 @@ struct WArgs {
   // (the neighbour's halo-area buffer, counts, tile states, queue); everything it reads is its own.
   int peer;
   PeerStrip up, down;      // the strip above (rank - 1) / below (rank + 1)
-  unsigned long long* G;   // queued + running tiles of ALL strips (lives on rank 0)
+  unsigned long long* G;   // strips that still have queued / running tiles + activations in flight between strips (lives on rank 0)
   const float* halo_in;    // areas of the neighbours' edge cells: [0, pitch) row above, [pitch, 2 pitch) row below
 };
 
@@ -135,33 +144,48 @@ __device__ __forceinline__ void cp_wait_all() {}
 #define W_ADD(ptr, v) (a.peer ? atomicAdd_system((ptr), (v)) : atomicAdd((ptr), (v)))
 #define W_CAS(ptr, c, v) (a.peer ? atomicCAS_system((ptr), (c), (v)) : atomicCAS((ptr), (c), (v)))
 #define W_EXCH(ptr, v) (a.peer ? atomicExch_system((ptr), (v)) : atomicExch((ptr), (v)))
+// the words a neighbour GPU can touch: counts of the strip's first / last row, states of the tiles that hold them
+#define W_ADD_IF(sys, ptr, v) ((sys) ? atomicAdd_system((ptr), (v)) : atomicAdd((ptr), (v)))
+#define W_CAS_IF(sys, ptr, c, v) ((sys) ? atomicCAS_system((ptr), (c), (v)) : atomicCAS((ptr), (c), (v)))
+#define W_EXCH_IF(sys, ptr, v) ((sys) ? atomicExch_system((ptr), (v)) : atomicExch((ptr), (v)))
 
-__device__ __forceinline__ void pending_add(const WArgs& a, unsigned long long v) {
-  if (a.peer) atomicAdd_system(a.G, v); else atomicAdd(a.ctr + C_PEND, v);
-}
+__device__ __forceinline__ unsigned long long* w_head(unsigned long long* ctr, int q) { return ctr + (3 * q) * 16; }
+__device__ __forceinline__ unsigned long long* w_tail(unsigned long long* ctr, int q) { return ctr + (3 * q + 1) * 16; }
+__device__ __forceinline__ unsigned long long* w_done(unsigned long long* ctr, int q) { return ctr + (3 * q + 2) * 16; }
+
+// A tile is pushed at most once between two visits (its state word says so), so a shard's ring never holds more entries
+// than the shard has tiles; tickets beyond the tail belong to waiting workers.
 __device__ void sched_push(const WArgs& a, int t) {
-  pending_add(a, 1ull);
-  const unsigned long long slot = W_ADD(a.ctr + C_TAIL, 1ull);
-  int* q = a.tq + (slot & a.qmask);
-  while (W_CAS(q, 0, t + 1) != 0) {}
+  const int q = t & (a.nsh - 1);
+  const unsigned long long slot = W_ADD(w_tail(a.ctr, q), 1ull);
+  int* ring = a.tq + ((size_t)q << a.qshift) + (slot & a.qmask);
+  while (W_CAS(ring, 0, t + 1) != 0) {}
 }
+__device__ __forceinline__ bool edge_tile(const WArgs& a, int t) { return a.peer && (t < a.ntx || t >= (a.nty - 1) * a.ntx); }
 __device__ void sched_activate(const WArgs& a, int t) {
+  const bool sys = edge_tile(a, t);
   for (;;) {
-    const int st = W_CAS(a.state + t, 0, 1);                // idle -> queued (the common case: one round trip)
+    const int st = W_CAS_IF(sys, a.state + t, 0, 1);        // idle -> queued (the common case: one round trip)
     if (st == 0) { sched_push(a, t); return; }
     if (st == 1 || st == 3) return;
-    if (W_CAS(a.state + t, 2, 3) == 2) return;             // running -> running + re-activated
+    if (W_CAS_IF(sys, a.state + t, 2, 3) == 2) return;     // running -> running + re-activated
   }
 }
-// the same protocol on a neighbour GPU's scheduler (system-scope atomics over NVLink)
+// The same protocol on a neighbour GPU's scheduler (system-scope atomics over NVLink).  Termination across GPUs: G counts
+// the strips that are ACTIVE (some tile queued or running) plus the activations in flight between strips.  Whoever
+// activates a tile of another strip first takes a token (G += 1), pushes, fences, and then marks the strip active: if it
+// was active already the token is returned, otherwise the token becomes that strip's own count.
 __device__ void sched_activate_peer(const WArgs& a, const PeerStrip& P, int t) {
   for (;;) {
     const int st = atomicCAS_system(P.state + t, 0, 1);
     if (st == 0) {
       atomicAdd_system(a.G, 1ull);
-      const unsigned long long slot = atomicAdd_system(P.ctr + C_TAIL, 1ull);
-      int* q = P.tq + (slot & P.qmask);
-      while (atomicCAS_system(q, 0, t + 1) != 0) {}
+      const int q = t & (P.nsh - 1);
+      const unsigned long long slot = atomicAdd_system(w_tail(P.ctr, q), 1ull);
+      int* ring = P.tq + ((size_t)q << P.qshift) + (slot & P.qmask);
+      while (atomicCAS_system(ring, 0, t + 1) != 0) {}
+      __threadfence_system();                                // the push is visible before the strip is (re)marked active
+      if (atomicExch_system(P.ctr + C_ACTIVE, 1ull) == 1ull) atomicAdd_system(a.G, ~0ull);
       return;
     }
     if (st == 1 || st == 3) return;
@@ -208,38 +232,77 @@ __device__ __forceinline__ void idle_wait(unsigned cycles, int plain) {
   do { __nanosleep(cycles >> 1); } while (clock64() - t0 < (long long)cycles);
 #endif
 }
-// Ticket h is served by the h-th push; a worker whose ticket is never served leaves when no tile is queued or running.
-// A waiting worker polls its own slot (a word nobody else polls) with an exponential back-off of 0.25 .. 2 us; the shared
-// "pending" word only every 8th time.
-__device__ int sched_pop(const WArgs& a) {
-  const unsigned long long h = atomicAdd(a.ctr + C_HEAD, 1ull);
-  int* q = a.tq + (h & a.qmask);
+// acquire load (orders the loads that follow after it)
+__device__ __forceinline__ long long ld_acquire(const unsigned long long* p) {
+#ifdef TD_EMU
+  emu::yield(); return (long long)*((const volatile unsigned long long*)p);
+#else
+  long long v; asm volatile("ld.acquire.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+#endif
+}
+// No tile of this strip is queued or running: every push (tail) has been matched by a finished visit (done).  The counters
+// only grow, a tile's own pushes precede its done, and all done counters are read BEFORE all tails: if the sums are equal,
+// they were equal at the moment the last done was read — nothing was running then, so nothing can be pushed any more
+// (except, in peer mode, by a neighbour strip).
+__device__ bool sched_balanced(const WArgs& a) {
+  long long d = 0, t = 0;
+  for (int q = 0; q < a.nsh; ++q) d += ld_acquire(w_done(a.ctr, q));
+  for (int q = 0; q < a.nsh; ++q) t += ld_relaxed(w_tail(a.ctr, q));
+  return d == t;
+}
+// Ticket h of a shard is served by the shard's h-th push.  A waiting worker polls its own slot (a word nobody else polls)
+// with an exponential back-off of 0.25 .. 2 us and the strip's "terminated" word every 8th time; the first warp of every
+// CTA also looks for termination itself (every 64th poll): all shards balanced — and in peer mode: this strip goes
+// passive (returning its count to G unless a neighbour re-activated it meanwhile) and the sweep ends when G is zero.
+__device__ int sched_pop(const WArgs& a, int q, bool scanner) {
+  const unsigned long long h = atomicAdd(w_head(a.ctr, q), 1ull);
+  int* slot = a.tq + ((size_t)q << a.qshift) + (h & a.qmask);
   unsigned wait = 512, n = 0;
   for (;;) {
-    const int v = ld_relaxed(q);
+    const int v = ld_relaxed(slot);
     if (v != 0) {
-      W_EXCH(q, 0);
-      W_EXCH(a.state + (v - 1), 2);
+      W_EXCH(slot, 0);
+      W_EXCH_IF(edge_tile(a, v - 1), a.state + (v - 1), 2);
       __threadfence();
       return v - 1;
     }
-    if ((++n & 7u) == 0u && ld_relaxed(a.peer ? a.G : a.ctr + C_PEND) <= 0) return -1;
+    if ((++n & 7u) == 0u) {
+      if (ld_relaxed(a.ctr + C_TERM) != 0) return -1;
+      if (scanner && (n & 63u) == 0u && sched_balanced(a)) {
+        bool over = true;
+        if (a.peer) {
+          if (atomicExch_system(a.ctr + C_ACTIVE, 0ull) == 1ull) {
+            __threadfence_system();
+            if (sched_balanced(a)) atomicAdd_system(a.G, ~0ull);                                   // passive: my count goes back
+            else if (atomicExch_system(a.ctr + C_ACTIVE, 1ull) == 1ull) atomicAdd_system(a.G, ~0ull);   // work arrived; the pusher's token counts for me
+          }
+          over = ldv(a.G) == 0ull;
+        }
+        if (over) { atomicExch(a.ctr + C_TERM, 1ull); return -1; }
+      }
+    }
     idle_wait(wait, a.poll);
     if (wait < 4096) wait <<= 1;
   }
 }
 __device__ void sched_finish(const WArgs& a, int t) {
   __threadfence();
-  if (W_CAS(a.state + t, 2, 0) != 2) { W_EXCH(a.state + t, 1); sched_push(a, t); }
-  pending_add(a, ~0ull);   // pending -= 1
+  const bool sys = edge_tile(a, t);
+  if (W_CAS_IF(sys, a.state + t, 2, 0) != 2) { W_EXCH_IF(sys, a.state + t, 1); sched_push(a, t); }
+  atomicAdd(w_done(a.ctr, t & (a.nsh - 1)), 1ull);
 }
 
-__global__ void k_wsched_init(int* state, int* tq, unsigned qcap, int ntiles, unsigned long long* ctr, unsigned long long* stat) {
+// start of a sweep: every tile queued (the rings and the scheduler words were zeroed before)
+__global__ void k_wsched_init(int* state, int* tq, int ntiles, unsigned long long* ctr, unsigned long long* stat, int nsh, int qshift, unsigned qmask) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < qcap) tq[i] = (int)i < ntiles ? (int)i + 1 : 0;
-  if ((int)i < ntiles) state[i] = 1;
+  if ((int)i < ntiles) {
+    state[i] = 1;
+    const int q = (int)i & (nsh - 1);
+    const unsigned long long slot = atomicAdd(w_tail(ctr, q), 1ull);
+    tq[((size_t)q << qshift) + (slot & qmask)] = (int)i + 1;
+  }
   if (i == 0) {
-    ctr[C_HEAD] = 0; ctr[C_TAIL] = (unsigned long long)ntiles; ctr[C_PEND] = (unsigned long long)ntiles;
+    ctr[C_ACTIVE] = 1ull;
     for (int j = 1; j < 8; ++j) stat[j] = 0;
   }
 }
@@ -283,6 +346,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
   const int lane = (int)(threadIdx.x & 31u), wid = (int)(threadIdx.x >> 5);
   const unsigned lt = (1u << lane) - 1u;
   Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
+  const int myq = (int)((blockIdx.x * (blockDim.x >> 5) + (unsigned)wid) & (unsigned)(a.nsh - 1));   // this worker's queue shard
   __shared__ PropRow sprop;
   if (DINF) {
     if (threadIdx.x == 0) sprop = a.prop;
@@ -292,7 +356,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
   for (;;) {
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
     int t = -1;
-    if (lane == 0) { if (a.stats) tk0 = clock64(); t = sched_pop(a); if (a.stats) tk1 = clock64(); }
+    if (lane == 0) { if (a.stats) tk0 = clock64(); t = sched_pop(a, myq, wid == 0); if (a.stats) tk1 = clock64(); }
     t = __shfl_sync(FULL, t, 0);
     if (t < 0) return;
     const int ty = t / a.ntx, tx = t - ty * a.ntx;
@@ -338,7 +402,8 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       }
     }
     // the ring columns: the west neighbours at slot 3 of their row (node words: two cells, slots 2 and 3), the east
-    // neighbours at slot 36 (node words: slots 36 and 37)
+    // neighbours at slot 36 (node words: slots 36 and 37).  Areas and angles change during the sweep: they are read past
+    // the L1 (4-byte cp.async exists only in the L1-allocating flavour), node words never change.
 #pragma unroll
     for (int rr = lane; rr < RH; rr += 32) {
       const int r = r0 - 1 + rr;
@@ -346,26 +411,15 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       const bool halo_row = a.peer && (r == 0 || r == s.ny + 1);
       const float* hrow = a.halo_in + (r == 0 ? 0 : s.pitch);
       const int sw = rr * RS + 3, se = rr * RS + RS;
-      if (rowok && c0 > 0) {
-        const long long g = s.idx(r, c0 - 1);
-        cp4(M.area + sw, halo_row ? hrow + (c0 - 1) : a.area + g);
-        if (DINF) cp4(M.ang + sw, a.ang + g);
-        cp4(M.node + sw - 1, a.node + g - 1);
-      } else {
-        M.area[sw] = -1.f;
-        if (DINF) M.ang[sw] = 0.f;
-        M.node[sw - 1] = 0; M.node[sw] = 0;
-      }
-      if (rowok && c0 + TS < s.pitch) {
-        const long long g = s.idx(r, c0 + TS);
-        cp4(M.area + se, halo_row ? hrow + (c0 + TS) : a.area + g);
-        if (DINF) cp4(M.ang + se, a.ang + g);
-        cp4(M.node + se, a.node + g);
-      } else {
-        M.area[se] = -1.f;
-        if (DINF) M.ang[se] = 0.f;
-        M.node[se] = 0; M.node[se + 1] = 0;
-      }
+      const bool west = rowok && c0 > 0, east = rowok && c0 + TS < s.pitch;
+      const long long gw_ = s.idx(r, c0 - 1), ge_ = s.idx(r, c0 + TS);
+      float aw = -1.f, ae = -1.f, gwn = 0.f, gen = 0.f;
+      if (west) { aw = __ldcg(halo_row ? hrow + (c0 - 1) : a.area + gw_); if (DINF) gwn = __ldcg(a.ang + gw_); cp4(M.node + sw - 1, a.node + gw_ - 1); }
+      else { M.node[sw - 1] = 0; M.node[sw] = 0; }
+      if (east) { ae = __ldcg(halo_row ? hrow + (c0 + TS) : a.area + ge_); if (DINF) gen = __ldcg(a.ang + ge_); cp4(M.node + se, a.node + ge_); }
+      else { M.node[se] = 0; M.node[se + 1] = 0; }
+      M.area[sw] = aw; M.area[se] = ae;
+      if (DINF) { M.ang[sw] = gwn; M.ang[se] = gen; }
     }
     // ---- 3. cells that are ready (count 0): every lane keeps the ready cells of its own tile row as a bit mask
     unsigned rdy = 0;
@@ -534,7 +588,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
           const unsigned e4 = (ev >> (4 * j)) & 0xfu;
           const unsigned delta = now - was + ((e4 * 0x00204081u) & 0x01010101u) * 0xfeu;
           if (delta != 0u) {
-            const unsigned old = W_ADD(gw + j, delta);
+            const unsigned old = W_ADD_IF(a.peer && (r == 1 || r == s.ny), gw + j, delta);
             if (zero_bytes(old + delta)) dirty = true;
           }
         }
@@ -557,7 +611,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       if (!(ndr & NODE_VALID)) continue;
       const long long ci = s.idx(r, c);
       const unsigned sh = (unsigned)(ci & 3) * 8u;
-      const unsigned old = W_ADD(a.cntw + (ci >> 2), 0u - (1u << sh));
+      const unsigned old = W_ADD_IF(a.peer && (r == 1 || r == s.ny), a.cntw + (ci >> 2), 0u - (1u << sh));
       if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
     }
     __syncwarp();
@@ -606,7 +660,8 @@ __global__ void k_wapply_halo(WArgs a, const int* __restrict__ dec_top, const in
   }
 }
 
-__global__ void k_wsched_reset(unsigned long long* ctr) { if (threadIdx.x == 0) ctr[C_HEAD] = ctr[C_TAIL] = ctr[C_PEND] = 0; }
+// between two runs of the round-based exchange: tickets abandoned at the end of the previous run are void (every ring slot is empty then)
+__global__ void k_wsched_reset(unsigned long long* ctr) { for (int i = threadIdx.x; i < C_WORDS; i += blockDim.x) ctr[i] = (i == C_ACTIVE) ? 1ull : 0ull; }
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
@@ -616,13 +671,18 @@ int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
   const long long nt = (long long)a.ntx * a.nty;
   if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
-  unsigned qcap = 1u << 14;   // always far more slots than workers holding tickets
-  while (qcap < (unsigned long long)nt) qcap <<= 1;
-  TD_CUDA(ctx->tileflags.ensure((size_t)nt * 4 + (size_t)qcap * 4));
+  // queue shards: a power of two, at most MAXSH and never more than the workers a launch has (>= min(tiles, one CTA per SM))
+  int nsh = 1;
+  while (nsh * 2 <= MAXSH && nsh * 2 <= nt) nsh *= 2;
+  // a shard's ring: its tiles (each queued at most once) + the tickets of waiting workers (< 2^13 workers per device)
+  const unsigned long long need = (unsigned long long)((nt + nsh - 1) / nsh) + (1u << 13);
+  int qshift = 14;
+  while ((1ull << qshift) < need) ++qshift;
+  a.nsh = nsh; a.qshift = qshift; a.qmask = (1u << qshift) - 1u;
+  TD_CUDA(ctx->tileflags.ensure((size_t)nt * 4 + ((size_t)nsh << qshift) * 4));
   a.state = ctx->tileflags.as<int>();
   a.tq = a.state + nt;
-  a.qmask = qcap - 1;
-  TD_CUDA(ctx->wsched.ensure(64 * sizeof(unsigned long long)));
+  TD_CUDA(ctx->wsched.ensure(C_WORDS * sizeof(unsigned long long)));
   a.ctr = ctx->wsched.as<unsigned long long>();
   a.stat = ctx->d_ctr + 24;
   a.node = ctx->node.as<unsigned short>();
@@ -636,7 +696,9 @@ int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   const int nt = a.ntx * a.nty;
-  k_wsched_init<<<(a.qmask + 1 + 255) / 256, 256, 0, st>>>(a.state, a.tq, a.qmask + 1, nt, a.ctr, a.stat);
+  TD_CUDA(cudaMemsetAsync(a.ctr, 0, C_WORDS * sizeof(unsigned long long), st));
+  TD_CUDA(cudaMemsetAsync(a.tq, 0, ((size_t)a.nsh << a.qshift) * sizeof(int), st));
+  k_wsched_init<<<(nt + 255) / 256, 256, 0, st>>>(a.state, a.tq, nt, a.ctr, a.stat, a.nsh, a.qshift, a.qmask);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;
@@ -647,7 +709,7 @@ int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
 int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
-  k_wsched_reset<<<1, 32, 0, st>>>(a.ctr);   // tickets abandoned at the end of the previous run are void
+  k_wsched_reset<<<1, 256, 0, st>>>(a.ctr);
   TD_LAUNCHED();
   k_wapply_halo<<<(s.nx + 255) / 256, 256, 0, st>>>(a, dec_top, dec_bot);
   TD_LAUNCHED();
@@ -669,7 +731,7 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
     auto fill = [](const td_ctx::PeerInfo& pi, PeerStrip& P) {
       P.valid = pi.valid;
       P.cntw = (unsigned*)pi.cntw; P.state = (int*)pi.tileflags; P.tq = P.state + pi.nt; P.ctr = (unsigned long long*)pi.dctr;
-      P.halo_in = (float*)pi.halo_in; P.qmask = (unsigned)pi.qmask; P.ntx = pi.ntx; P.ny = pi.ny;
+      P.halo_in = (float*)pi.halo_in; P.qmask = (unsigned)pi.qmask; P.ntx = pi.ntx; P.ny = pi.ny; P.nsh = pi.nsh; P.qshift = pi.qshift;
     };
     fill(ctx->peer_up, a.up); fill(ctx->peer_down, a.down);
     a.G = (unsigned long long*)ctx->peer_G;
@@ -735,7 +797,7 @@ int sweep_peer_export(td_ctx* ctx, const Strip& s, int dinf, unsigned char* hand
     TD_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
     memcpy(handles + 64 * i, &h, 64);
   }
-  meta[0] = (int)a.qmask; meta[1] = a.ntx; meta[2] = s.ny; meta[3] = TS; meta[4] = a.ntx * a.nty;
+  meta[0] = (int)a.qmask; meta[1] = a.ntx; meta[2] = s.ny; meta[3] = TS; meta[4] = a.ntx * a.nty; meta[5] = a.nsh; meta[6] = a.qshift; meta[7] = 0;
   return TD_OK;
 }
 
@@ -755,7 +817,7 @@ int sweep_peer_connect(td_ctx* ctx, int which, const unsigned char* handles, con
   }
   td_ctx::PeerInfo& pi = which == 0 ? ctx->peer_up : ctx->peer_down;
   if (!handles && meta && pi.valid) {       // same buffers, new geometry
-    pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4];
+    pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4]; pi.nsh = meta[5]; pi.qshift = meta[6];
     return TD_OK;
   }
   close_peer(pi);
@@ -764,11 +826,11 @@ int sweep_peer_connect(td_ctx* ctx, int which, const unsigned char* handles, con
   TD_CUDA(open(handles + 64, &pi.tileflags));
   TD_CUDA(open(handles + 128, &pi.dctr));
   TD_CUDA(open(handles + 192, &pi.halo_in));
-  pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4]; pi.valid = 1;
+  pi.qmask = meta[0]; pi.ntx = meta[1]; pi.ny = meta[2]; pi.th = meta[3]; pi.nt = meta[4]; pi.nsh = meta[5]; pi.qshift = meta[6]; pi.valid = 1;
   return TD_OK;
 }
 
-// start of a peer-mode sweep: queue all tiles, announce them in the global counter.  The caller must put a barrier
+// start of a peer-mode sweep: queue all tiles, count this strip as active in the global counter.  The caller must put a barrier
 // between this call and wsweep_run on every rank (nobody may see G == 0 before everybody announced).
 int sweep_peer_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
   ctx->peer_on = 1;
@@ -776,7 +838,7 @@ int sweep_peer_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   TD_CUDA(cudaMemsetAsync(ctx->peer_halo.p, 0, sizeof(float) * 2 * (size_t)s.pitch, st));
-  k_add_G<<<1, 32, 0, st>>>((unsigned long long*)ctx->peer_G, (unsigned long long)a.ntx * a.nty);
+  k_add_G<<<1, 32, 0, st>>>((unsigned long long*)ctx->peer_G, 1ull);     // this strip is active
   TD_LAUNCHED();
   TD_CUDA(cudaStreamSynchronize(st));
   return TD_OK;

@@ -120,7 +120,7 @@ class DistTools:
         """Exports this rank's IPC handles, gathers everybody's, opens the neighbours' (cached while unchanged)."""
         import numpy as np
         s = self.s
-        handles = np.zeros(320, np.uint8); meta = np.zeros(5, np.int32)
+        handles = np.zeros(320, np.uint8); meta = np.zeros(8, np.int32)
         check(self.l.td_sweep_peer_export_dev(self.T.ctx, s.c, int(dinf), handles.ctypes.data_as(C.c_void_p), meta.ctypes.data_as(C.c_void_p), self._stream()))
         mine = torch.from_numpy(np.concatenate([handles, meta.view(np.uint8)])).to(s.device)
         allp = [torch.empty_like(mine) for _ in range(self.world)]
