@@ -184,6 +184,48 @@ inline void make_prop_row(double t, bool uniform, PropRow* P) {
   }
 }
 
+
+// RN(x / d) for a divisor whose correctly rounded reciprocal y = RN(1 / d) is known (see rowfact.cuh's div_const: Markstein's
+// two corrections with exact residuals; PropRow::safe / RowFact::safe state the precondition)
+__device__ __forceinline__ double div_recip(double x, double d, double y) {
+  const double q0 = x * y;
+  const double q1 = fma(fma(-d, q0, x), y, q0);
+  return fma(fma(-d, q1, x), y, q1);
+}
+
+// dinf_outflow with the row's table: every divisor of prop() is a sector width den[i] = ar[i + 1] - ar[i] (the same double
+// the reference forms inline), so each share is one division by a table constant.
+__device__ __forceinline__ Outflow dinf_outflow_tab(float a, const PropRow& P) {
+  Outflow o; o.k1 = o.k2 = 0; o.p1 = o.p2 = 0.;
+  const double* ar = P.ar;
+  auto dv = [&](double num, int i) { return P.safe ? div_recip(num, P.den[i], P.rden[i]) : num / P.den[i]; };
+  auto wrapped = [&](float af) {
+    const float a1 = (float)(af - 2.0 * TD_PI);
+    double p = 0.;
+    if (a1 > ar[0] && a1 < ar[2]) p = (a1 > ar[1]) ? dv(ar[2] - a1, 1) : dv(a1 - ar[0], 0);
+    return p;
+  };
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i <= 9; ++i) j += (a >= ar[i]) ? 1 : 0;
+  double pA = 0., pB = 0.; int kA = 0, kB = 0;
+  if (j >= 1 && j <= 8) {
+    const double lo = ar[j - 1], mid = ar[j], hi = ar[j + 1];
+    kA = j;
+    pA = (a > mid) ? dv(hi - a, j) : dv(a - lo, j - 1);
+    if (j < 8) { kB = j + 1; if (a > mid) pB = dv(a - mid, j); }
+    else { kB = 1; pB = wrapped(a); }
+  } else if (j == 9) {
+    kA = 1; pA = wrapped(a);
+  } else {
+    kA = 1;
+    if (a > ar[0]) pA = (a > ar[1]) ? dv(ar[2] - a, 1) : dv(a - ar[0], 0);
+  }
+  if (!(pA < 1e-5)) { o.k1 = kA; o.p1 = pA; }
+  if (!(pB < 1e-5)) { if (o.k1 == 0) { o.k1 = kB; o.p1 = pB; } else { o.k2 = kB; o.p2 = pB; } }
+  return o;
+}
+
 __device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) { return dinf_outflow_t(a, ar); }
 __device__ __forceinline__ Outflow dinf_outflow(float a, double t) { return dinf_outflow_t(a, ArefRow{t}); }
 

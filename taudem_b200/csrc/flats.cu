@@ -62,7 +62,7 @@ __device__ __forceinline__ void append(long long* list, unsigned long long* ctr,
   unsigned long long base = 0;
   if (lane == leader) base = atomicAdd(ctr, (unsigned long long)__popc(m));
   base = __shfl_sync(m, base, leader);
-  list[base + __popc(m & ((1u << lane) - 1u))] = v;
+  if (list) list[base + __popc(m & ((1u << lane) - 1u))] = v;     // list == NULL: counting pass
 }
 
 template <class P>
@@ -397,15 +397,19 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
     return TD_OK;
   };
   // --- collect the flat cells (first call of the reference: src/d8.cpp:492-503)
-  // worst case every cell is flat; size lists by a counting pass
-  TD_CUDA(cudaMemsetAsync(dc, 0, 4 * sizeof(unsigned long long), st));
-  TD_CUDA(ctx->listA.ensure(sizeof(long long) * (size_t)s.nx * s.ny));
+  // a counting pass sizes the lists (8 bytes per FLAT cell, not per cell of the strip)
+  unsigned long long n = 0, ntot = 0;      // flat cells of this strip / of the whole grid
   {
     dim3 grid(s.ny, (s.nx + 255) / 256);
+    TD_CUDA(cudaMemsetAsync(dc, 0, 4 * sizeof(unsigned long long), st));
+    k_collect<P><<<grid, 256, 0, st>>>(dir, s, nullptr, dc);
+    TD_LAUNCHED();
+    TD_CUDA(read_ctr(0, &n));
+    TD_CUDA(ctx->listA.ensure(sizeof(long long) * (n + 1)));
+    TD_CUDA(cudaMemsetAsync(dc, 0, 4 * sizeof(unsigned long long), st));
     k_collect<P><<<grid, 256, 0, st>>>(dir, s, ctx->listA.as<long long>(), dc);
     TD_LAUNCHED();
   }
-  unsigned long long n = 0, ntot = 0;      // flat cells of this strip / of the whole grid
   TD_CUDA(read_ctr(0, &n));
   if (int rc = gsum(n, &ntot)) return rc;
   *nleft = (long long)ntot;
@@ -562,15 +566,26 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
 }
 }  // namespace
 
+// the level rasters (8 B per cell) and the flat-cell lists are only needed while the flats are resolved: the contributing-area
+// tools that follow need the memory (16 B per cell of D-infinity shares)
+static void release_flat_scratch(td_ctx* ctx, cudaStream_t st) {
+  cudaStreamSynchronize(st);
+  ctx->lev.release(); ctx->mk.release(); ctx->listA.release(); ctx->listB.release(); ctx->listC.release();
+}
+
 int resolve_flats_d8(td_ctx* ctx, float* elev, short* dir, const Strip& s, const double* dxc, const double* dyc, long long* nleft,
                      const td_strip_comm* comm, cudaStream_t st) {
   Geo g{dxc, dyc, nullptr, nullptr};
-  return resolve_flats<D8Pol>(ctx, elev, dir, s, g, nleft, comm, st);
+  const int rc = resolve_flats<D8Pol>(ctx, elev, dir, s, g, nleft, comm, st);
+  release_flat_scratch(ctx, st);
+  return rc;
 }
 int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, const double* dxc, const double* dyc, const double* thA,
                        const double* thB, long long* nleft, const td_strip_comm* comm, cudaStream_t st) {
   Geo g{dxc, dyc, thA, thB};
-  return resolve_flats<DinfPol>(ctx, elev, ang, s, g, nleft, comm, st);
+  const int rc = resolve_flats<DinfPol>(ctx, elev, ang, s, g, nleft, comm, st);
+  release_flat_scratch(ctx, st);
+  return rc;
 }
 
 }  // namespace td

@@ -67,7 +67,7 @@ __device__ __forceinline__ int lut_dcol(int k) { return (int)((DCOL_LUT >> (2 * 
 template <bool DINF>
 struct __align__(16) WarpMem {
   float area[RN];                         // areas of the tile and its ring (-1 = nodata / not final)
-  float ang[DINF ? RN : 4];               // D-infinity: angles of the same cells
+  double2 sh[DINF ? RN : 1];              // D-infinity: the shares prop() gives the two receivers of the same cells (k_deps_dinf)
   unsigned short node[RN];                // node words of the same cells
   alignas(16) unsigned cnt[TC / 4];       // dependency counts, four cells per word: 0..8 (0 = ready or evaluated by this visit), 0xFE = evaluated
                                           // by an earlier visit, 0xFF = not a node
@@ -76,10 +76,10 @@ struct __align__(16) WarpMem {
   unsigned evmask[TS];                    // per tile row: cells evaluated by this visit
   int sp, next, dirty, pad;
 };
-template <bool DINF> constexpr int workers_per_cta() { return DINF ? 16 : 26; }
-static_assert(sizeof(WarpMem<false>) * workers_per_cta<false>() <= 227 * 1024 && sizeof(WarpMem<true>) * workers_per_cta<true>() + 512 <= 227 * 1024,
+template <bool DINF> constexpr int workers_per_cta() { return DINF ? 8 : 26; }
+static_assert(sizeof(WarpMem<false>) * workers_per_cta<false>() <= 227 * 1024 && sizeof(WarpMem<true>) * workers_per_cta<true>() <= 227 * 1024,
               "the workers of a CTA must fit the shared memory of an SM");
-static_assert(offsetof(WarpMem<true>, ang) % 16 == 0 && offsetof(WarpMem<true>, node) % 8 == 0 && offsetof(WarpMem<false>, node) % 8 == 0, "cp.async alignment");
+static_assert(offsetof(WarpMem<true>, sh) % 16 == 0 && offsetof(WarpMem<true>, node) % 8 == 0 && offsetof(WarpMem<false>, node) % 8 == 0, "cp.async alignment");
 
 // what a neighbouring strip exposes to this GPU (device pointers into the peer's memory)
 struct PeerStrip {
@@ -92,11 +92,10 @@ struct WArgs {
   unsigned* cntw;
   float* area;
   const float* w;
-  const float* ang;
+  const double2* share;    // D-infinity: shares of every strip cell (k_deps_dinf)
   Strip s;
   int usew, contcheck;
   float w_nodata;
-  const double* theta;
   const double* dxc;
   int* halo;
   int ntx, nty;
@@ -104,11 +103,11 @@ struct WArgs {
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;          // slots of one shard's ring - 1
   int nsh, qshift;         // queue shards (a power of two), log2 of a shard's ring size
-  PropRow prop;            // D-infinity: the strip's prop() table (prop.uniform) — else per-row angles from `theta`
-  double dx0;              // D-infinity, uniform strips: the cell size every row adds (src/areadinf.cpp:216)
+  int dx_uniform;          // D-infinity: every row of the strip has the cell size dx0
+  double dx0;              // the cell size a cell's own area adds (src/areadinf.cpp:216)
   unsigned long long* ctr; // scheduler words (see MAXSH)
   unsigned long long* stat;// [1] cells, [2] wavefront iterations, [3] visits, [4..7] cycle statistics (TAUDEM_B200_TIMING)
-  int stats, poll;
+  int stats, poll, exp;    // exp: experiment switches (TAUDEM_B200_EXP)
   // peer mode (one strip per GPU, the neighbours' buffers mapped over NVLink with CUDA IPC): no exchange rounds — a tile
   // delivers into the neighbour GPU exactly as it delivers into a neighbour tile.  Every GPU only WRITES remote memory
   // (the neighbour's halo-area buffer, counts, tile states, queue); everything it reads is its own.
@@ -136,6 +135,14 @@ __device__ __forceinline__ void cp8(void* smem, const void* g) { cp_check(smem, 
 __device__ __forceinline__ void cp4(void* smem, const void* g) { cp_check(smem, g, 4); memcpy(smem, g, 4); }
 __device__ __forceinline__ void cp_wait_all() {}
 #endif
+
+__device__ __forceinline__ void fence_acq_rel() {
+#ifdef TD_EMU
+  emu::yield();
+#else
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
+}
 
 // ---- scheduler (one lane per worker)
 // In peer mode a neighbour GPU operates on this strip's scheduler words and on the counts of its edge rows with
@@ -263,7 +270,7 @@ __device__ int sched_pop(const WArgs& a, int q, bool scanner) {
     if (v != 0) {
       W_EXCH(slot, 0);
       W_EXCH_IF(edge_tile(a, v - 1), a.state + (v - 1), 2);
-      __threadfence();
+      if (!(a.exp & 1)) __threadfence();
       return v - 1;
     }
     if ((++n & 7u) == 0u) {
@@ -286,7 +293,7 @@ __device__ int sched_pop(const WArgs& a, int q, bool scanner) {
   }
 }
 __device__ void sched_finish(const WArgs& a, int t) {
-  __threadfence();
+  if (!(a.exp & 4)) __threadfence();
   const bool sys = edge_tile(a, t);
   if (W_CAS_IF(sys, a.state + t, 2, 0) != 2) { W_EXCH_IF(sys, a.state + t, 1); sched_push(a, t); }
   atomicAdd(w_done(a.ctr, t & (a.nsh - 1)), 1ull);
@@ -307,29 +314,6 @@ __global__ void k_wsched_init(int* state, int* tq, int ntiles, unsigned long lon
   }
 }
 
-// prop(angle, kk) through the full interval search (the rare path of the D-infinity gather)
-__device__ __noinline__ double wshare_full(float ang, double t, int kk) {
-  const Outflow o = dinf_outflow(ang, t);
-  return o.k1 == kk ? o.p1 : o.p2;
-}
-
-// The share prop(av, kk) of a contributor (angle av, node word nn) for its receiver in direction kk, from the strip's
-// table.  The contributor's first receiver k1 (node word) is the sector j of its angle or the sector after it — one
-// comparison; kk is then j (share (ar[j+1] - a) / den[j]; for a == ar[j] numerator and denominator are the same double, the
-// share is 1 exactly as prop()'s (a - ar[j-1]) / (ar[j] - ar[j-1]) is) or j + 1 (share (a - ar[j]) / den[j]): prop()'s /
-// dinf_outflow's expressions with the division by a table constant (div_const).  Direction 1 reached through the end of the
-// table (the float-rounded a - 2 PI of src/commonLib.cpp:82) and angles outside [0, 2 PI) go through the interval search
-// (rare, out of line).
-__device__ __forceinline__ double wshare_tab(const PropRow& P, float av, unsigned nn, int kk) {
-  const int k1 = (int)((nn >> 8) & 0xfu);
-  const double a = (double)av;
-  const int j = k1 - 1 + (a >= P.ar[k1 & 7 ? k1 : 8] ? 1 : 0);
-  if ((k1 == 1 && a >= P.ar[8]) || (j == 8 && kk == 1) || av < 0.f || k1 < 1 || k1 > 8) return wshare_full(av, P.ar[2], kk);
-  const bool isA = kk == j;
-  const double num = isA ? P.ar[j + 1] - a : a - P.ar[j];
-  return P.safe ? div_const(num, P.den[j], P.rden[j]) : num / P.den[j];
-}
-
 // bit 7 of every byte of the result is set exactly where that byte of w is zero (no borrow between bytes)
 __device__ __forceinline__ unsigned zero_bytes(unsigned w) { return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; }
 // bit i of the result: byte i of w is zero
@@ -339,7 +323,7 @@ __device__ __forceinline__ unsigned zero_nibble(unsigned w) {
 }
 
 template <bool DINF, bool USEW>
-__global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(const WArgs a) {
+__global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(const WArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   using Mem = WarpMem<DINF>;
   const Strip& s = a.s;
@@ -347,11 +331,6 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
   const unsigned lt = (1u << lane) - 1u;
   Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
   const int myq = (int)((blockIdx.x * (blockDim.x >> 5) + (unsigned)wid) & (unsigned)(a.nsh - 1));   // this worker's queue shard
-  __shared__ PropRow sprop;
-  if (DINF) {
-    if (threadIdx.x == 0) sprop = a.prop;
-    __syncthreads();
-  }
 
   for (;;) {
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
@@ -377,7 +356,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       M.evmask[lane] = 0u;
     }
     if (lane == 0) { M.sp = 0; M.next = 0; M.dirty = 0; }
-    __threadfence();          // the counts first, then the areas they announce (loaded by other lanes: barrier in between)
+    if (!(a.exp & 2)) __threadfence();          // the counts first, then the areas they announce (loaded by other lanes: barrier in between)
     __syncwarp();
     // ---- 2. areas, node words (and angles) of the tile and its ring: asynchronous copies straight into shared memory, all in
     //         flight at once (one round trip); what lies below the strip is filled in directly
@@ -392,11 +371,13 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
           const long long g = s.idx(r, c);
           if (a.peer && (r == 0 || r == s.ny + 1)) cp16(M.area + so, a.halo_in + (r == 0 ? 0 : s.pitch) + c);
           else cp16(M.area + so, a.area + g);
-          if (DINF) cp16(M.ang + so, a.ang + g);
+          if (DINF) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) cp16(M.sh + so + x, a.share + g + x);
+          }
           cp8(M.node + so, a.node + g);
         } else {
           *reinterpret_cast<float4*>(M.area + so) = make_float4(-1.f, -1.f, -1.f, -1.f);
-          if (DINF) *reinterpret_cast<float4*>(M.ang + so) = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<uint2*>(M.node + so) = make_uint2(0u, 0u);
         }
       }
@@ -413,13 +394,12 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       const int sw = rr * RS + 3, se = rr * RS + RS;
       const bool west = rowok && c0 > 0, east = rowok && c0 + TS < s.pitch;
       const long long gw_ = s.idx(r, c0 - 1), ge_ = s.idx(r, c0 + TS);
-      float aw = -1.f, ae = -1.f, gwn = 0.f, gen = 0.f;
-      if (west) { aw = __ldcg(halo_row ? hrow + (c0 - 1) : a.area + gw_); if (DINF) gwn = __ldcg(a.ang + gw_); cp4(M.node + sw - 1, a.node + gw_ - 1); }
+      float aw = -1.f, ae = -1.f;
+      if (west) { aw = __ldcg(halo_row ? hrow + (c0 - 1) : a.area + gw_); if (DINF) cp16(M.sh + sw, a.share + gw_); cp4(M.node + sw - 1, a.node + gw_ - 1); }
       else { M.node[sw - 1] = 0; M.node[sw] = 0; }
-      if (east) { ae = __ldcg(halo_row ? hrow + (c0 + TS) : a.area + ge_); if (DINF) gen = __ldcg(a.ang + ge_); cp4(M.node + se, a.node + ge_); }
+      if (east) { ae = __ldcg(halo_row ? hrow + (c0 + TS) : a.area + ge_); if (DINF) cp16(M.sh + se, a.share + ge_); cp4(M.node + se, a.node + ge_); }
       else { M.node[se] = 0; M.node[se + 1] = 0; }
       M.area[sw] = aw; M.area[se] = ae;
-      if (DINF) { M.ang[sw] = gwn; M.ang[se] = gen; }
     }
     // ---- 3. cells that are ready (count 0): every lane keeps the ready cells of its own tile row as a bit mask
     unsigned rdy = 0;
@@ -495,37 +475,22 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
             if (mn < 0.f) con = true;          // (with -nc no area is ever -1 when it is gathered)
           }
         } else {
-          // src/areadinf.cpp:187-218.  The share a contributor sends here is prop(its angle, direction to me): for a
-          // contributor with two receivers in one of the sectors 1..7 its node word says which sector (k1, k1 + 1), so
-          // the share is one division — exactly the expressions dinf_outflow evaluates; everything else (single
-          // receiver, the wrap sector, contributors in a halo row, whose node words belong to the neighbour strip)
-          // takes the full interval search.
-          const int r = r0 + lr;
+          // src/areadinf.cpp:187-218: the share a contributor sends here is prop(its angle, direction to me) — the first or
+          // the second of the two shares k_deps_dinf stored for it, depending on which of its receivers this cell is
           val = 0.f;
 #pragma unroll 1
           for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
             const int k = __ffs(m);
-            const int dr = lut_drow(k), dc = lut_dcol(k);
-            const int ni = ri + dr * RS + dc;
+            const int ni = ri + lut_drow(k) * RS + lut_dcol(k);
             const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
-            const int rn = r + dr;
             const unsigned nn = M.node[ni];
-            const float av = M.ang[ni];
             const float an = M.area[ni];
-            double p;
-            if (sprop.uniform && rn >= 1 && rn <= s.ny) p = wshare_tab(sprop, av, nn, kk);
-            else {
-              const double th = a.theta[min(max(rn - 1, 0), s.ny - 1)];
-              const int k1n = (nn >> 8) & 0xf;
-              if ((nn & 0x2000u) && k1n <= 7 && rn >= 1 && rn <= s.ny) {
-                const double mid = aref(k1n, th), hi = aref(k1n + 1, th);
-                p = (kk == k1n) ? (hi - av) / (hi - mid) : (av - mid) / (hi - mid);
-              } else p = wshare_full(av, th, kk);
-            }
+            const double* shp = reinterpret_cast<const double*>(M.sh + ni);
+            const double p = shp[(int)((nn >> 8) & 0xfu) == kk ? 0 : 1];
             if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
           }
           if (USEW) val = val + wv;
-          else val = (float)((double)val + (sprop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]));
+          else val = (float)((double)val + (a.dx_uniform ? a.dx0 : a.dxc[min(r0 + lr, s.ny) - 1]));
         }
         if (con && a.contcheck) val = -1.0f;
         M.area[ri] = val;
@@ -568,7 +533,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32) k_sweep_warp(con
       if ((evr >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RS + lane + 4];
     }
     __syncwarp();
-    __threadfence();          // release by the lanes that publish: every lane's area stores (ordered by the barrier) before their atomics
+    if (a.exp & 8) fence_acq_rel(); else __threadfence();          // release by the lanes that publish: every lane's area stores (ordered by the barrier) before their atomics
     {
       // The shared-memory count of a cell this visit evaluated is 0, of any other cell its count at the start minus the
       // arrivals from inside the tile; bytes >= 0x80 (not a node / evaluated before: flow into a cell without a direction
@@ -665,9 +630,9 @@ __global__ void k_wsched_reset(unsigned long long* ctr) { for (int i = threadIdx
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
-  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
+  a.area = nullptr; a.w = nullptr; a.share = nullptr; a.dx0 = 0.; a.dx_uniform = 0; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.dxc = nullptr; a.halo = nullptr;
   a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + TS - 1) / TS;
-  a.stats = 0; a.poll = 0;
+  a.stats = 0; a.poll = 0; a.exp = 0;
   a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
   const long long nt = (long long)a.ntx * a.nty;
   if (nt > (1ll << 30)) { set_error("strip has too many tiles"); return TD_ERR_ARG; }
@@ -722,10 +687,10 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
                int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
-  a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
-  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
-  a.prop = ctx->prop;
-  if (!dinf) a.prop.uniform = 0;
+  a.area = area; a.w = w; a.share = ctx->share.as<double2>(); a.usew = usew; a.contcheck = contcheck;
+  a.w_nodata = w_nodata; a.dxc = dxc; a.halo = halo;
+  a.dx_uniform = dinf ? ctx->prop.uniform : 0;
+  (void)ang; (void)theta;
   a.peer = ctx->peer_on;
   if (a.peer) {
     auto fill = [](const td_ctx::PeerInfo& pi, PeerStrip& P) {
@@ -740,9 +705,11 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   }
   const char* te = getenv("TAUDEM_B200_TIMING");
   a.stats = (te && atoi(te) > 0) ? 1 : 0;
+  if (const char* xe = getenv("TAUDEM_B200_EXP")) a.exp = atoi(xe);
   const char* pe = getenv("TAUDEM_B200_POLL");
   a.poll = (pe && atoi(pe) > 0) ? 1 : 0;
   a.dx0 = ctx->dx0;
+  if (dinf && !a.share) { set_error("areadinf sweep: the dependency stencil has not run"); return TD_ERR_ARG; }
   int warps = dinf ? workers_per_cta<true>() : workers_per_cta<false>();
   if (const char* we = getenv("TAUDEM_B200_WORKERS")) { const int v = atoi(we); if (v >= 1 && v < warps) warps = v; }   // experiments: fewer workers per SM
   const size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;

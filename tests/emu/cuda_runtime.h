@@ -43,6 +43,8 @@ inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return
 inline ushort4 make_ushort4(unsigned short a, unsigned short b, unsigned short c, unsigned short d) { return {a, b, c, d}; }
 inline uchar4 make_uchar4(unsigned char a, unsigned char b, unsigned char c, unsigned char d) { return {a, b, c, d}; }
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double a, double b) { return {a, b}; }
 inline short4 make_short4(short a, short b, short c, short d) { return {a, b, c, d}; }
 
 // ---- host runtime

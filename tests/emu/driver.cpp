@@ -19,7 +19,7 @@ int cuda_fail(cudaError_t, const char* what) { g_err = what; return 90; }
 td_ctx::td_ctx() { d_ctr = (unsigned long long*)calloc(32, 8); h_ctr = (unsigned long long*)calloc(32, 8); }
 td_ctx::~td_ctx() {
   free(d_ctr); free(h_ctr);
-  node.p = cnt.p = nullptr;       // owned by the caller below
+  node.p = cnt.p = share.p = nullptr;       // owned by the caller below
   listA.release(); listB.release(); listC.release(); lev.release(); mk.release(); halo.release(); tileflags.release(); wsched.release(); rowfact.release();
 }
 
@@ -35,6 +35,7 @@ struct StripState {
   std::vector<unsigned short> node;
   std::vector<unsigned char> cnt;
   std::vector<float> area, w, ang;
+  std::vector<double2> share;
   std::vector<short> p;
   std::vector<double> theta, dxc;
   std::vector<int> halo;
@@ -84,6 +85,7 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
       }
   } else {
     std::vector<unsigned char> code(n, 0);
+    S.share.assign(n, make_double2(0., 0.));
     for (int r = 0; r <= ny + 1; ++r)
       for (int c = 0; c < nx; ++c) {
         if (!s.on_grid(r, c)) continue;
@@ -91,6 +93,8 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
         if (fabsf(av - dir_nodata) < 1e-5f) continue;
         const td::Outflow o = td::dinf_outflow(av, S.theta[std::min(std::max(r - 1, 0), ny - 1)]);
         code[s.idx(r, c)] = (unsigned char)(o.k1 | (o.k2 << 4));
+        S.share[s.idx(r, c)] = make_double2(o.p1, o.p2);           // what k_deps_dinf stores for the sweep's gather
+        if (r == 0 || r == ny + 1) S.node[s.idx(r, c)] = (unsigned short)(((unsigned)o.k1 << 8) | (o.k2 ? 0x2000u : 0u));   // halo rows: receivers only
       }
     for (int r = 1; r <= ny; ++r)
       for (int c = 0; c < nx; ++c) {
@@ -111,6 +115,7 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
   }
   S.ctx.node.p = S.node.data(); S.ctx.node.cap = S.node.size() * 2;
   S.ctx.cnt.p = S.cnt.data(); S.ctx.cnt.cap = S.cnt.size();
+  if (dinf) { S.ctx.share.p = S.share.data(); S.ctx.share.cap = S.share.size() * sizeof(double2); }
 }
 }  // namespace
 
