@@ -5,10 +5,10 @@
 //            area() main loop    src/areadinf.cpp:173-265 (k-ordered gather
 //                                areares = (float)(areares + p*area_n), + weight or dxc[row],
 //                                then decrement every neighbour that receives flow).
-// shares: for every cell the two doubles prop() gives its first / second receiver (0 where there is none), 16 B per cell —
-// computed here once, in parallel, so that the sweep's gather is a multiply-add per contributor.
-// node word of a D-infinity cell: bits 0-7 = which neighbours drain into it, bits 8-11 = its first receiving
-// direction k1 (0 = none), 0x2000 = it has a second receiver (always k1 % 8 + 1), 0x1000 = contaminated, 0x8000 = valid.
+// node word of a D-infinity cell: bits 0-7 = which neighbours drain into it, bits 8-11 = its receiver field (dinf_field,
+// dinf_common.cuh: the first receiving direction k1 and how its shares are obtained), 0x2000 = it has a second receiver
+// (always k1 % 8 + 1), 0x1000 = contaminated, 0x8000 = valid.  Halo rows get the receiver bits alone (no VALID): the sweep's
+// gather needs them for contributors that belong to the neighbour strip.
 // prop's table aref[] = {-t,0,t,PI/2,PI-t,PI,PI+t,3PI/2,2PI-t,2PI} with t = atan2(dy,dx)
 // is rebuilt on the device from t (host glibc atan2, per row) using only +,-: the same
 // doubles as the reference.  The per-cell value is a deterministic gather, so any
@@ -24,47 +24,31 @@ constexpr int TW = 128, TH = 32;
 __device__ __forceinline__ unsigned eq_bytes7(unsigned w, unsigned t) { return ~((w ^ t) + 0x7f7f7f7fu) & 0x80808080u; }
 
 __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang, unsigned short* __restrict__ node,
-                                                   unsigned char* __restrict__ cnt, float* __restrict__ area, double2* __restrict__ share,
-                                                   Strip s, float nodata, const double* __restrict__ theta, const PropRow prop) {
+                                                   unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,
+                                                   float nodata, const double* __restrict__ theta) {
   using G = TileGeom<float, TW, TH>;
   __shared__ __align__(128) float tile[G::ELEMS];
   __shared__ __align__(8) uint64_t bar;
   const int c0 = blockIdx.x * TW, r0 = 1 + blockIdx.y * TH;
   load_tile_tma<float, TW, TH>(tile, &bar, ang, s, r0, c0);
-  // one byte per staged cell: k1 | 0x10 if there is a second receiver (always the next direction, k1 % 8 + 1) |
-  // 0x20 if the cell is off the grid or nodata; one prop() interval search each
+  // one byte per staged cell (dinf_node_code): k1 | 0x10 if there is a second receiver (always the next direction, k1 % 8 + 1) |
+  // 0x40 / 0x80 how the shares are obtained | 0x20 if the cell is off the grid or nodata; one prop() interval search each
   __shared__ double saref[(TH + 2) * 10];
   __shared__ __align__(16) unsigned char sout[G::ELEMS];
-  __shared__ PropRow sp;
-  if (threadIdx.x == 0) sp = prop;
   for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) saref[i] = aref(i % 10, theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]);
   __syncthreads();
-  // The outflow of every staged cell: its receivers (for the in-degrees below) and the shares prop() gives them — the
-  // sweep's gather reads the shares of the tile's own cells (and of the halo rows next to the first / last tile row)
-  // from `share` instead of evaluating prop() on its critical path (src/areadinf.cpp:196-207 calls prop per contributor).
-  const bool last_ty = r0 + TH > s.ny;
   for (int i = threadIdx.x; i < G::ELEMS; i += 256) {
     const int t = i / G::SW, sc = i - t * G::SW;
     const int gr = r0 - 1 + t, gc = c0 - G::HP + sc;
     unsigned char code = 0x20;
-    double2 sh = make_double2(0., 0.);
     if (s.on_grid(gr, gc)) {
       const float av = tile[i];
-      if (!nd_f(av, nodata)) {
-        const Outflow o = sp.uniform ? dinf_outflow_tab(av, sp) : dinf_outflow_t(av, saref + t * 10);
-        code = (unsigned char)((unsigned)o.k1 | (o.k2 ? 0x10u : 0u));
-        sh = make_double2(o.p1, o.p2);
-      }
+      if (!nd_f(av, nodata)) code = (unsigned char)dinf_node_code(av, saref + t * 10);
     }
     sout[i] = code;
-    const bool mine = sc >= G::HP && sc < G::HP + TW && gc < s.pitch &&
-                      ((t >= 1 && t <= TH && gr <= s.ny) || (t == 0 && gr == 0) || (last_ty && gr == s.ny + 1));
-    if (mine) {
-      share[s.idx(gr, gc)] = sh;
-      // halo rows: the neighbour strip's cells are no nodes here, but the gather must know which of a contributor's two
-      // shares is meant — its receivers (k1, "has a second one") in the node word's usual bits, without VALID
-      if (gr == 0 || gr == s.ny + 1) node[s.idx(gr, gc)] = (code & 0x20u) ? (unsigned short)0 : (unsigned short)(((code & 0xfu) << 8) | ((code & 0x10u) ? 0x2000u : 0u));
-    }
+    // halo rows of the strip (cells of the neighbour strips): receiver bits only, written by the tiles next to them
+    if ((gr == 0 || gr == s.ny + 1) && sc >= G::HP && sc < G::HP + TW && gc < s.pitch && (t == 0 || t == s.ny + 2 - r0))
+      node[s.idx(gr, gc)] = (code & 0x20u) ? (unsigned short)0 : (unsigned short)((dinf_field(code) << 8) | ((code & 0x10u) ? 0x2000u : 0u));
   }
   __syncthreads();
   // four adjacent cells per thread with byte-parallel arithmetic: neighbour k drains into me when one of its
@@ -102,7 +86,9 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     x = (x + (x >> 4)) & 0x0f0f0f0fu;
     const unsigned cw = (x & vm) | ~vm;                                   // count, or 0xff outside the field
     // VALID | CON (a neighbour off the grid or nodata) | the cell's own receivers: k1 in bits 8-11, 0x2000 = a second one (k1 % 8 + 1)
-    const unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1) | (wc & 0x0f0f0f0fu) | ((wc & 0x10101010u) << 1)) & vm;
+    const unsigned k4 = wc & 0x0f0f0f0fu;
+    const unsigned plus8 = ((wc >> 6) | ((wc >> 7) & (eq_bytes7(k4, 0x01010101u) >> 7))) & 0x01010101u;       // upper, or irregular with k1 = 1
+    const unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1) | (k4 + (plus8 << 3)) | ((wc & 0x10101010u) << 1)) & vm;
     const unsigned mw = mb & vm;
     unsigned short on4[4]; unsigned char oc4[4];
 #pragma unroll
@@ -119,10 +105,10 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
 
 }  // namespace
 
-cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, double2* share, const Strip& s,
-                             float nodata, const double* theta, const PropRow& prop, cudaStream_t st) {
+cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
+                             float nodata, const double* theta, cudaStream_t st) {
   dim3 grid((s.pitch + TW - 1) / TW, (s.ny + TH - 1) / TH);
-  k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, share, s, nodata, theta, prop);
+  k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, s, nodata, theta);
   TD_LAUNCHED();
   return cudaGetLastError();
 }

@@ -34,7 +34,7 @@ td_ctx::td_ctx() {
   if (d_ctr) cudaMemset(d_ctr, 0, 32 * sizeof(unsigned long long));
 }
 td_ctx::~td_ctx() {
-  node.release(); cnt.release(); share.release(); lev.release(); mk.release(); listA.release(); listB.release(); listC.release();
+  node.release(); cnt.release(); lev.release(); mk.release(); listA.release(); listB.release(); listC.release();
   tileflags.release(); wsched.release(); rowfact.release(); halo.release();
   if (d_ctr) cudaFree(d_ctr);
   if (h_ctr) cudaFreeHost(h_ctr);
@@ -241,9 +241,8 @@ int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, floa
   if (int rc = ensure_dep_state(ctx, Strip(s), st)) return rc;
   if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
   ctx->sweep_dinf = 1;
-  TD_CUDA(ctx->share.ensure((size_t)Strip(s).cells() * sizeof(double2)));
-  TD_CUDA(td::launch_deps_dinf(ang, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), sca, ctx->share.as<double2>(), Strip(s), ang_nodata,
-                               ctx->theta.as<double>(), ctx->prop, st));
+  TD_CUDA(td::launch_deps_dinf(ang, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), sca, Strip(s), ang_nodata,
+                               ctx->theta.as<double>(), st));
   return TD_OK;
 }
 int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca, td_strip s, int usew, int contcheck,

@@ -28,7 +28,6 @@ struct td_ctx {
   };
   Buf node;      // u16 per strip cell: static dependency node (inflow mask, dir, flags)
   Buf cnt;       // u8 per strip cell (addressed as u32 words): remaining inflow count
-  Buf share;     // D-infinity: two doubles per strip cell, the shares prop() gives the cell's first / second receiver
   Buf lev, mk;   // i32 per strip cell: Garbrecht-Martz levels / rise marks
   Buf listA, listB, listC;   // int64 cell-index lists (flat cells, BFS frontiers, ready queues)
   Buf tileflags; // fill: active-tile flags (2 x ntiles bytes)

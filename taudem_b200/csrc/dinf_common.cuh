@@ -185,45 +185,43 @@ inline void make_prop_row(double t, bool uniform, PropRow* P) {
 }
 
 
+// The receivers of a cell as the byte the dependency stencils work with: bits 0-3 = first receiver k1 (0 = none), 0x10 = there
+// is a second one (always k1 % 8 + 1), 0x40 = "upper": the angle lies in sector k1 - 1 and the sector's lower direction
+// got a share below 1e-5 (dropped), so the only receiver is the sector's upper direction, 0x80 = irregular: the wrap
+// sector, angles outside [0, 2 PI) or an upper cell with k1 = 8 — shares of such cells come from the interval search.
+// Regular cells (neither 0x80) get their shares from the sector table alone (SectorTab below):
+//   sector j = k1 (not upper) or k1 - 1 (upper);  first receiver of a non-upper cell: (ar[j+1] - a) / den[j];
+//   otherwise (second receiver, or the only receiver of an upper cell): (a - ar[j]) / den[j].
+template <typename AR>
+__device__ __forceinline__ unsigned dinf_node_code(float a, const AR& ar) {
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i <= 9; ++i) j += (a >= ar[i]) ? 1 : 0;
+  if (j >= 1 && j <= 7) {
+    const double lo = ar[j - 1], mid = ar[j], hi = ar[j + 1];
+    const bool up = a > mid;
+    const bool cA = up ? share_counts(hi - a, hi - mid) : share_counts(a - lo, mid - lo);     // pA >= 1e-5
+    const bool cB = up && share_counts(a - mid, hi - mid);                                      // pB >= 1e-5 (pB = 0 unless a > mid)
+    if (cA) return (unsigned)j | (cB ? 0x10u : 0u);
+    if (!cB) return 0u;
+    return j < 7 ? ((unsigned)(j + 1) | 0x40u) : (8u | 0x80u);
+  }
+  const Outflow o = dinf_outflow_t(a, ar);
+  return o.k1 ? ((unsigned)o.k1 | (o.k2 ? 0x10u : 0u) | 0x80u) : 0u;
+}
+// the 4-bit receiver field of a D-infinity node word: 0 none, 1..7 regular k1, 8 irregular k1 = 8, 9 irregular k1 = 1, 10..15 upper k1 = f - 8
+__host__ __device__ __forceinline__ unsigned dinf_field(unsigned code) {
+  const unsigned k = code & 0xfu;
+  return k + (((code & 0x40u) || ((code & 0x80u) && k == 1u)) ? 8u : 0u);
+}
+__host__ __device__ __forceinline__ int dinf_field_k1(unsigned f) { return (int)(f > 8u ? f - 8u : f); }
+
 // RN(x / d) for a divisor whose correctly rounded reciprocal y = RN(1 / d) is known (see rowfact.cuh's div_const: Markstein's
 // two corrections with exact residuals; PropRow::safe / RowFact::safe state the precondition)
 __device__ __forceinline__ double div_recip(double x, double d, double y) {
   const double q0 = x * y;
   const double q1 = fma(fma(-d, q0, x), y, q0);
   return fma(fma(-d, q1, x), y, q1);
-}
-
-// dinf_outflow with the row's table: every divisor of prop() is a sector width den[i] = ar[i + 1] - ar[i] (the same double
-// the reference forms inline), so each share is one division by a table constant.
-__device__ __forceinline__ Outflow dinf_outflow_tab(float a, const PropRow& P) {
-  Outflow o; o.k1 = o.k2 = 0; o.p1 = o.p2 = 0.;
-  const double* ar = P.ar;
-  auto dv = [&](double num, int i) { return P.safe ? div_recip(num, P.den[i], P.rden[i]) : num / P.den[i]; };
-  auto wrapped = [&](float af) {
-    const float a1 = (float)(af - 2.0 * TD_PI);
-    double p = 0.;
-    if (a1 > ar[0] && a1 < ar[2]) p = (a1 > ar[1]) ? dv(ar[2] - a1, 1) : dv(a1 - ar[0], 0);
-    return p;
-  };
-  int j = 0;
-#pragma unroll
-  for (int i = 1; i <= 9; ++i) j += (a >= ar[i]) ? 1 : 0;
-  double pA = 0., pB = 0.; int kA = 0, kB = 0;
-  if (j >= 1 && j <= 8) {
-    const double lo = ar[j - 1], mid = ar[j], hi = ar[j + 1];
-    kA = j;
-    pA = (a > mid) ? dv(hi - a, j) : dv(a - lo, j - 1);
-    if (j < 8) { kB = j + 1; if (a > mid) pB = dv(a - mid, j); }
-    else { kB = 1; pB = wrapped(a); }
-  } else if (j == 9) {
-    kA = 1; pA = wrapped(a);
-  } else {
-    kA = 1;
-    if (a > ar[0]) pA = (a > ar[1]) ? dv(ar[2] - a, 1) : dv(a - ar[0], 0);
-  }
-  if (!(pA < 1e-5)) { o.k1 = kA; o.p1 = pA; }
-  if (!(pB < 1e-5)) { if (o.k1 == 0) { o.k1 = kB; o.p1 = pB; } else { o.k2 = kB; o.p2 = pB; } }
-  return o;
 }
 
 __device__ __forceinline__ Outflow dinf_outflow(float a, const double* ar) { return dinf_outflow_t(a, ar); }

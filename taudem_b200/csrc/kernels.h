@@ -14,8 +14,8 @@ int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, con
                        const double* thA, const double* thB, long long* nleft, const td_strip_comm* comm, cudaStream_t st);
 cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
                            short nodata, cudaStream_t st);
-cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, double2* share, const Strip& s,
-                             float nodata, const double* theta, const PropRow& prop, cudaStream_t st);
+cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
+                             float nodata, const double* theta, cudaStream_t st);
 int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
 int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,

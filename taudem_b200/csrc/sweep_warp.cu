@@ -67,7 +67,7 @@ __device__ __forceinline__ int lut_dcol(int k) { return (int)((DCOL_LUT >> (2 * 
 template <bool DINF>
 struct __align__(16) WarpMem {
   float area[RN];                         // areas of the tile and its ring (-1 = nodata / not final)
-  double2 sh[DINF ? RN : 1];              // D-infinity: the shares prop() gives the two receivers of the same cells (k_deps_dinf)
+  float ang[DINF ? RN : 4];               // D-infinity: angles of the same cells
   unsigned short node[RN];                // node words of the same cells
   alignas(16) unsigned cnt[TC / 4];       // dependency counts, four cells per word: 0..8 (0 = ready or evaluated by this visit), 0xFE = evaluated
                                           // by an earlier visit, 0xFF = not a node
@@ -76,10 +76,10 @@ struct __align__(16) WarpMem {
   unsigned evmask[TS];                    // per tile row: cells evaluated by this visit
   int sp, next, dirty, pad;
 };
-template <bool DINF> constexpr int workers_per_cta() { return DINF ? 8 : 26; }
-static_assert(sizeof(WarpMem<false>) * workers_per_cta<false>() <= 227 * 1024 && sizeof(WarpMem<true>) * workers_per_cta<true>() <= 227 * 1024,
+template <bool DINF> constexpr int workers_per_cta() { return DINF ? 16 : 26; }
+static_assert(sizeof(WarpMem<false>) * workers_per_cta<false>() <= 227 * 1024 && sizeof(WarpMem<true>) * workers_per_cta<true>() + 1024 <= 227 * 1024,
               "the workers of a CTA must fit the shared memory of an SM");
-static_assert(offsetof(WarpMem<true>, sh) % 16 == 0 && offsetof(WarpMem<true>, node) % 8 == 0 && offsetof(WarpMem<false>, node) % 8 == 0, "cp.async alignment");
+static_assert(offsetof(WarpMem<true>, ang) % 16 == 0 && offsetof(WarpMem<true>, node) % 8 == 0 && offsetof(WarpMem<false>, node) % 8 == 0, "cp.async alignment");
 
 // what a neighbouring strip exposes to this GPU (device pointers into the peer's memory)
 struct PeerStrip {
@@ -92,10 +92,11 @@ struct WArgs {
   unsigned* cntw;
   float* area;
   const float* w;
-  const double2* share;    // D-infinity: shares of every strip cell (k_deps_dinf)
+  const float* ang;
   Strip s;
   int usew, contcheck;
   float w_nodata;
+  const double* theta;
   const double* dxc;
   int* halo;
   int ntx, nty;
@@ -103,7 +104,7 @@ struct WArgs {
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;          // slots of one shard's ring - 1
   int nsh, qshift;         // queue shards (a power of two), log2 of a shard's ring size
-  int dx_uniform;          // D-infinity: every row of the strip has the cell size dx0
+  PropRow prop;            // D-infinity: the strip's prop() table (prop.uniform: every row has the same cell size dx0) — else per-row angles from `theta`
   double dx0;              // the cell size a cell's own area adds (src/areadinf.cpp:216)
   unsigned long long* ctr; // scheduler words (see MAXSH)
   unsigned long long* stat;// [1] cells, [2] wavefront iterations, [3] visits, [4..7] cycle statistics (TAUDEM_B200_TIMING)
@@ -269,9 +270,10 @@ __device__ int sched_pop(const WArgs& a, int q, bool scanner) {
     const int v = ld_relaxed(slot);
     if (v != 0) {
       W_EXCH(slot, 0);
-      W_EXCH_IF(edge_tile(a, v - 1), a.state + (v - 1), 2);
-      if (!(a.exp & 1)) __threadfence();
-      return v - 1;
+      // the tile is marked running BEFORE its counts are read (whoever delivers into it after that re-activates it): the
+      // exchange's result is consumed, so the count loads that follow cannot be issued before the exchange was performed
+      const int prev = W_EXCH_IF(edge_tile(a, v - 1), a.state + (v - 1), 2);
+      return prev == 0x7ffffff0 ? -1 : v - 1;
     }
     if ((++n & 7u) == 0u) {
       if (ld_relaxed(a.ctr + C_TERM) != 0) return -1;
@@ -292,8 +294,9 @@ __device__ int sched_pop(const WArgs& a, int q, bool scanner) {
     if (wait < 4096) wait <<= 1;
   }
 }
+// (every atomic of the visit has returned its result by now — the counts, the deliveries, the activations — and the plain
+//  stores were fenced before them: nothing of the visit is still in flight when the tile is released)
 __device__ void sched_finish(const WArgs& a, int t) {
-  if (!(a.exp & 4)) __threadfence();
   const bool sys = edge_tile(a, t);
   if (W_CAS_IF(sys, a.state + t, 2, 0) != 2) { W_EXCH_IF(sys, a.state + t, 1); sched_push(a, t); }
   atomicAdd(w_done(a.ctr, t & (a.nsh - 1)), 1ull);
@@ -314,6 +317,14 @@ __global__ void k_wsched_init(int* state, int* tq, int ntiles, unsigned long lon
   }
 }
 
+// prop(angle, kk) through the full interval search (irregular cells, strips whose rows have different cell sizes)
+__device__ __noinline__ double wshare_full(float ang, double t, int kk) {
+  const Outflow o = dinf_outflow(ang, t);
+  return o.k1 == kk ? o.p1 : o.p2;
+}
+// one sector of prop()'s table: its two directions' angles, its width and the width's reciprocal
+struct __align__(16) Sector { double lo, hi, den, rden; };
+
 // bit 7 of every byte of the result is set exactly where that byte of w is zero (no borrow between bytes)
 __device__ __forceinline__ unsigned zero_bytes(unsigned w) { return ~(((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u; }
 // bit i of the result: byte i of w is zero
@@ -331,6 +342,11 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
   const unsigned lt = (1u << lane) - 1u;
   Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
   const int myq = (int)((blockIdx.x * (blockDim.x >> 5) + (unsigned)wid) & (unsigned)(a.nsh - 1));   // this worker's queue shard
+  __shared__ Sector sect[9];
+  if (DINF) {
+    if (threadIdx.x < 9) { const int j = (int)threadIdx.x; sect[j].lo = a.prop.ar[j]; sect[j].hi = a.prop.ar[j + 1]; sect[j].den = a.prop.den[j]; sect[j].rden = a.prop.rden[j]; }
+    __syncthreads();
+  }
 
   for (;;) {
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
@@ -371,13 +387,11 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           const long long g = s.idx(r, c);
           if (a.peer && (r == 0 || r == s.ny + 1)) cp16(M.area + so, a.halo_in + (r == 0 ? 0 : s.pitch) + c);
           else cp16(M.area + so, a.area + g);
-          if (DINF) {
-#pragma unroll
-            for (int x = 0; x < 4; ++x) cp16(M.sh + so + x, a.share + g + x);
-          }
+          if (DINF) cp16(M.ang + so, a.ang + g);
           cp8(M.node + so, a.node + g);
         } else {
           *reinterpret_cast<float4*>(M.area + so) = make_float4(-1.f, -1.f, -1.f, -1.f);
+          if (DINF) *reinterpret_cast<float4*>(M.ang + so) = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<uint2*>(M.node + so) = make_uint2(0u, 0u);
         }
       }
@@ -395,9 +409,9 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
       const bool west = rowok && c0 > 0, east = rowok && c0 + TS < s.pitch;
       const long long gw_ = s.idx(r, c0 - 1), ge_ = s.idx(r, c0 + TS);
       float aw = -1.f, ae = -1.f;
-      if (west) { aw = __ldcg(halo_row ? hrow + (c0 - 1) : a.area + gw_); if (DINF) cp16(M.sh + sw, a.share + gw_); cp4(M.node + sw - 1, a.node + gw_ - 1); }
+      if (west) { aw = __ldcg(halo_row ? hrow + (c0 - 1) : a.area + gw_); if (DINF) cp4(M.ang + sw, a.ang + gw_); cp4(M.node + sw - 1, a.node + gw_ - 1); }
       else { M.node[sw - 1] = 0; M.node[sw] = 0; }
-      if (east) { ae = __ldcg(halo_row ? hrow + (c0 + TS) : a.area + ge_); if (DINF) cp16(M.sh + se, a.share + ge_); cp4(M.node + se, a.node + ge_); }
+      if (east) { ae = __ldcg(halo_row ? hrow + (c0 + TS) : a.area + ge_); if (DINF) cp4(M.ang + se, a.ang + ge_); cp4(M.node + se, a.node + ge_); }
       else { M.node[se] = 0; M.node[se + 1] = 0; }
       M.area[sw] = aw; M.area[se] = ae;
     }
@@ -475,22 +489,37 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
             if (mn < 0.f) con = true;          // (with -nc no area is ever -1 when it is gathered)
           }
         } else {
-          // src/areadinf.cpp:187-218: the share a contributor sends here is prop(its angle, direction to me) — the first or
-          // the second of the two shares k_deps_dinf stored for it, depending on which of its receivers this cell is
+          // src/areadinf.cpp:187-218: the share a contributor sends here is prop(its angle, direction to me).  The
+          // contributor's node word says how it is obtained (dinf_field): for a regular cell one subtraction from a sector
+          // edge and one division by the sector's width (a table constant: div_recip) — the same doubles prop() /
+          // dinf_outflow form; irregular cells and strips without a common table take the interval search.
+          const int r = r0 + lr;
           val = 0.f;
 #pragma unroll 1
           for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
             const int k = __ffs(m);
-            const int ni = ri + lut_drow(k) * RS + lut_dcol(k);
+            const int dr = lut_drow(k);
+            const int ni = ri + dr * RS + lut_dcol(k);
             const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to this cell
-            const unsigned nn = M.node[ni];
+            const unsigned f = ((unsigned)M.node[ni] >> 8) & 0xfu;
+            const float av = M.ang[ni];
             const float an = M.area[ni];
-            const double* shp = reinterpret_cast<const double*>(M.sh + ni);
-            const double p = shp[(int)((nn >> 8) & 0xfu) == kk ? 0 : 1];
+            double p;
+            if (a.prop.uniform && f != 8u && f != 9u) {
+              const bool upper = f >= 10u;
+              const int k1 = (int)(upper ? f - 8u : f);
+              const Sector S = sect[upper ? k1 - 1 : k1];
+              const double ad = (double)av;
+              const double num = (kk == k1 && !upper) ? S.hi - ad : ad - S.lo;
+              p = a.prop.safe ? div_recip(num, S.den, S.rden) : num / S.den;
+            } else {
+              const int rn = r + dr;
+              p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : a.theta[min(max(rn - 1, 0), s.ny - 1)], kk);
+            }
             if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
           }
           if (USEW) val = val + wv;
-          else val = (float)((double)val + (a.dx_uniform ? a.dx0 : a.dxc[min(r0 + lr, s.ny) - 1]));
+          else val = (float)((double)val + (a.prop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]));
         }
         if (con && a.contcheck) val = -1.0f;
         M.area[ri] = val;
@@ -502,7 +531,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
         for (int j = 0; j < (DINF ? 2 : 1); ++j) {
           int k;
           if (!DINF) k = (int)((nd >> 8) & 0xfu);
-          else { const int k1 = (int)((nd >> 8) & 0xfu); k = j == 0 ? k1 : ((nd & 0x2000u) ? (k1 & 7) + 1 : 0); }
+          else { const int k1 = dinf_field_k1((nd >> 8) & 0xfu); k = j == 0 ? k1 : ((nd & 0x2000u) ? (k1 & 7) + 1 : 0); }
           if (k < 1 || k > 8) continue;
           const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
           if ((unsigned)nlr < (unsigned)TS && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {       // a cell of this tile
@@ -532,35 +561,32 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
       const unsigned evr = __shfl_sync(FULL, ev, lr);
       if ((evr >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RS + lane + 4];
     }
-    __syncwarp();
-    if (a.exp & 8) fence_acq_rel(); else __threadfence();          // release by the lanes that publish: every lane's area stores (ordered by the barrier) before their atomics
+    // The counts.  The shared-memory count of a cell this visit evaluated is 0, of any other cell its count at the start
+    // minus the arrivals from inside the tile; bytes >= 0x80 (not a node / evaluated before: flow into a cell without a
+    // direction still decrements them in shared memory) keep their value.  One 32-bit delta per word carries all four cells
+    // (every byte of the sum stays within 0..0xFE, so nothing carries between bytes): evaluated -> 0xFE, others minus the
+    // local arrivals.  Words without a cell of the tile's rim (or of the strip's last row, which a neighbour strip feeds)
+    // are touched by nobody else while the tile runs: plain stores, before the fence, like the areas.  The others are
+    // added atomically after it; a zero byte in the result is a cell that became ready through arrivals from outside meanwhile.
+    const int myr = r0 + lane;
+    const bool rimrow = lane == 0 || lane == TS - 1 || myr >= s.ny;
+    unsigned dl[8];
     {
-      // The shared-memory count of a cell this visit evaluated is 0, of any other cell its count at the start minus the
-      // arrivals from inside the tile; bytes >= 0x80 (not a node / evaluated before: flow into a cell without a direction
-      // still decrements them in shared memory) keep their value.  One 32-bit add per changed word carries all four cells
-      // (every byte of the sum stays within 0..0xFE, so nothing carries between bytes): evaluated -> 0xFE, others minus the
-      // local arrivals.  A zero byte in the result is a cell that became ready through arrivals from outside meanwhile.
-      const int r = r0 + lane;
-      bool dirty = false;
-      if (r <= s.ny) {
-        unsigned* gw = a.cntw + (s.idx(r, c0) >> 2);
+      unsigned* gw = a.cntw + (s.idx(min(myr, s.ny), c0) >> 2);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const unsigned was = g0[j];
-          unsigned now = M.cnt[lane * 8 + j];
-          const unsigned keep = ((was >> 7) & 0x01010101u) * 0xffu;
-          now = (now & ~keep) | (was & keep);
-          const unsigned e4 = (ev >> (4 * j)) & 0xfu;
-          const unsigned delta = now - was + ((e4 * 0x00204081u) & 0x01010101u) * 0xfeu;
-          if (delta != 0u) {
-            const unsigned old = W_ADD_IF(a.peer && (r == 1 || r == s.ny), gw + j, delta);
-            if (zero_bytes(old + delta)) dirty = true;
-          }
-        }
+      for (int j = 0; j < 8; ++j) {
+        const unsigned was = g0[j];
+        unsigned now = M.cnt[lane * 8 + j];
+        const unsigned keep = ((was >> 7) & 0x01010101u) * 0xffu;
+        now = (now & ~keep) | (was & keep);
+        const unsigned e4 = (ev >> (4 * j)) & 0xfu;
+        dl[j] = now - was + ((e4 * 0x00204081u) & 0x01010101u) * 0xfeu;
+        if (j >= 1 && j <= 6 && !rimrow && dl[j] != 0u) { gw[j] = was + dl[j]; dl[j] = 0u; }
       }
-      if (dirty) M.dirty = 1;
     }
     __syncwarp();
+    if (a.exp & 8) fence_acq_rel(); else __threadfence();          // release by the lanes that publish: every lane's stores (ordered by the barrier) before their atomics
+    // flow that leaves the tile first (the neighbours wait for it), then the rim's counts
     const int ne = M.next;
     for (int e = lane; e < ne; e += 32) {
       const int l = M.ext[e] & 0x3ff, k = (M.ext[e] >> 10) + 1;
@@ -578,6 +604,17 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
       const unsigned sh = (unsigned)(ci & 3) * 8u;
       const unsigned old = W_ADD_IF(a.peer && (r == 1 || r == s.ny), a.cntw + (ci >> 2), 0u - (1u << sh));
       if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
+    }
+    if (myr <= s.ny) {
+      unsigned* gw = a.cntw + (s.idx(myr, c0) >> 2);
+      bool dirty = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (dl[j] != 0u) {
+          const unsigned old = W_ADD_IF(a.peer && (myr == 1 || myr == s.ny), gw + j, dl[j]);
+          if (zero_bytes(old + dl[j])) dirty = true;
+        }
+      if (dirty) M.dirty = 1;
     }
     __syncwarp();
     if (lane == 0) {
@@ -630,7 +667,7 @@ __global__ void k_wsched_reset(unsigned long long* ctr) { for (int i = threadIdx
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
-  a.area = nullptr; a.w = nullptr; a.share = nullptr; a.dx0 = 0.; a.dx_uniform = 0; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.dxc = nullptr; a.halo = nullptr;
+  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
   a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + TS - 1) / TS;
   a.stats = 0; a.poll = 0; a.exp = 0;
   a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
@@ -687,10 +724,10 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
                int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
-  a.area = area; a.w = w; a.share = ctx->share.as<double2>(); a.usew = usew; a.contcheck = contcheck;
-  a.w_nodata = w_nodata; a.dxc = dxc; a.halo = halo;
-  a.dx_uniform = dinf ? ctx->prop.uniform : 0;
-  (void)ang; (void)theta;
+  a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
+  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+  a.prop = ctx->prop;
+  if (!dinf) a.prop.uniform = 0;
   a.peer = ctx->peer_on;
   if (a.peer) {
     auto fill = [](const td_ctx::PeerInfo& pi, PeerStrip& P) {
@@ -709,10 +746,10 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   const char* pe = getenv("TAUDEM_B200_POLL");
   a.poll = (pe && atoi(pe) > 0) ? 1 : 0;
   a.dx0 = ctx->dx0;
-  if (dinf && !a.share) { set_error("areadinf sweep: the dependency stencil has not run"); return TD_ERR_ARG; }
   int warps = dinf ? workers_per_cta<true>() : workers_per_cta<false>();
   if (const char* we = getenv("TAUDEM_B200_WORKERS")) { const int v = atoi(we); if (v >= 1 && v < warps) warps = v; }   // experiments: fewer workers per SM
-  const size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
+  size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
+  if (const char* pe2 = getenv("TAUDEM_B200_SMEMPAD")) smem = std::max(smem, (size_t)atoi(pe2));                  // experiments: one CTA per SM whatever its size
   const void* kern = dinf ? (usew ? (const void*)k_sweep_warp<true, true> : (const void*)k_sweep_warp<true, false>)
                           : (usew ? (const void*)k_sweep_warp<false, true> : (const void*)k_sweep_warp<false, false>);
   int& per_dev = ctx->wgrid[(dinf ? 2 : 0) + (usew ? 1 : 0)];

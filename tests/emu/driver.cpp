@@ -19,7 +19,7 @@ int cuda_fail(cudaError_t, const char* what) { g_err = what; return 90; }
 td_ctx::td_ctx() { d_ctr = (unsigned long long*)calloc(32, 8); h_ctr = (unsigned long long*)calloc(32, 8); }
 td_ctx::~td_ctx() {
   free(d_ctr); free(h_ctr);
-  node.p = cnt.p = share.p = nullptr;       // owned by the caller below
+  node.p = cnt.p = nullptr;       // owned by the caller below
   listA.release(); listB.release(); listC.release(); lev.release(); mk.release(); halo.release(); tileflags.release(); wsched.release(); rowfact.release();
 }
 
@@ -35,7 +35,6 @@ struct StripState {
   std::vector<unsigned short> node;
   std::vector<unsigned char> cnt;
   std::vector<float> area, w, ang;
-  std::vector<double2> share;
   std::vector<short> p;
   std::vector<double> theta, dxc;
   std::vector<int> halo;
@@ -84,17 +83,18 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
         S.cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
       }
   } else {
-    std::vector<unsigned char> code(n, 0);
-    S.share.assign(n, make_double2(0., 0.));
+    std::vector<unsigned char> code(n, 0), field(n, 0);
     for (int r = 0; r <= ny + 1; ++r)
       for (int c = 0; c < nx; ++c) {
         if (!s.on_grid(r, c)) continue;
         const float av = S.ang[s.idx(r, c)];
         if (fabsf(av - dir_nodata) < 1e-5f) continue;
-        const td::Outflow o = td::dinf_outflow(av, S.theta[std::min(std::max(r - 1, 0), ny - 1)]);
+        const double th = S.theta[std::min(std::max(r - 1, 0), ny - 1)];
+        const td::Outflow o = td::dinf_outflow(av, th);
         code[s.idx(r, c)] = (unsigned char)(o.k1 | (o.k2 << 4));
-        S.share[s.idx(r, c)] = make_double2(o.p1, o.p2);           // what k_deps_dinf stores for the sweep's gather
-        if (r == 0 || r == ny + 1) S.node[s.idx(r, c)] = (unsigned short)(((unsigned)o.k1 << 8) | (o.k2 ? 0x2000u : 0u));   // halo rows: receivers only
+        field[s.idx(r, c)] = (unsigned char)td::dinf_field(td::dinf_node_code(av, td::ArefRow{th}));      // how the sweep obtains the shares
+        if ((td::dinf_node_code(av, td::ArefRow{th}) & 0x1fu) != (unsigned)(o.k1 | (o.k2 ? 0x10 : 0))) abort();
+        if (r == 0 || r == ny + 1) S.node[s.idx(r, c)] = (unsigned short)(((unsigned)field[s.idx(r, c)] << 8) | (o.k2 ? 0x2000u : 0u));   // halo rows: receivers only
       }
     for (int r = 1; r <= ny; ++r)
       for (int c = 0; c < nx; ++c) {
@@ -108,14 +108,13 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
           if ((int)(cd & 15u) == kk || (int)(cd >> 4) == kk) mask |= 1u << (k - 1);
         }
         const unsigned own = code[s.idx(r, c)];                        // receivers of the cell itself: k1, and whether there is a second one
-        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask | ((own & 15u) << 8) | ((own >> 4) ? 0x2000u : 0u));
+        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask | ((unsigned)field[s.idx(r, c)] << 8) | ((own >> 4) ? 0x2000u : 0u));
         S.cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
         if ((own >> 4) && (own >> 4) != (own & 15u) % 8 + 1) abort();  // the second receiver is always the next direction
       }
   }
   S.ctx.node.p = S.node.data(); S.ctx.node.cap = S.node.size() * 2;
   S.ctx.cnt.p = S.cnt.data(); S.ctx.cnt.cap = S.cnt.size();
-  if (dinf) { S.ctx.share.p = S.share.data(); S.ctx.share.cap = S.share.size() * sizeof(double2); }
 }
 }  // namespace
 
@@ -192,9 +191,9 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
     if (rounds > 10000) return 2;
   }
   if (rounds_out) *rounds_out = rounds;
-  for (auto& T : S)       // every cell of the flow field must have been evaluated (count byte 0xFE) or removed (0xFF)
+  for (auto& T : S)       // no cell may be left ready but not evaluated (cells of a cycle keep a count > 0, like in the reference)
     for (int r = 1; r <= T.s.ny; ++r)
-      for (int c = 0; c < nx; ++c) if (T.cnt[T.s.idx(r, c)] <= 8) return 77;
+      for (int c = 0; c < nx; ++c) if (T.cnt[T.s.idx(r, c)] == 0) return 77;
   for (auto& T : S)
     for (int r = 1; r <= T.s.ny; ++r)
       for (int c = 0; c < nx; ++c) out[(size_t)(T.row0 + r - 1) * nx + c] = T.area[T.s.idx(r, c)];

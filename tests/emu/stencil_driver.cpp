@@ -74,9 +74,7 @@ extern "C" int emu_deps_dinf(const float* ang, unsigned short* node, unsigned ch
   Grid g(nx, ny, dx, dy);
   auto a = g.in(ang);
   std::vector<unsigned short> nd((size_t)g.s.cells(), 0); std::vector<unsigned char> cn((size_t)g.s.cells() + 4, 0); std::vector<float> ar((size_t)g.s.cells(), 0.f);
-  std::vector<double2> sh((size_t)g.s.cells());
-  td::PropRow P; td::make_prop_row(g.th[0], true, &P);       // (the emulated grids have one cell size)
-  td::launch_deps_dinf(a.data(), nd.data(), cn.data(), ar.data(), sh.data(), g.s, nodata, g.th.data(), P, nullptr);
+  td::launch_deps_dinf(a.data(), nd.data(), cn.data(), ar.data(), g.s, nodata, g.th.data(), nullptr);
   g.out(nd, node); g.out(cn, cnt); g.out(ar, area);
   return 0;
 }

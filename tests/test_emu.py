@@ -118,6 +118,19 @@ def test_emulated_dinf_sweep_matches_the_oracle(emu, fields):
     assert_bits(_run(emu, True, 0, 0, ang, w, False, 4), port.areadinf(ang, weights=w, contcheck=False), "sca -wg -nc")
 
 
+def test_emulated_dinf_angle_torture(emu):
+    """areadinf on angles at and next to every place where prop() changes its mind (sector edges, the 1e-5 share threshold,
+    the wrap sector, angles beyond 2 PI): the receiver field of the node words and the sector-table shares against the oracle."""
+    from oracle import port
+    from util import angle_torture
+    for dx, dy in ((30.0, 30.0), (12.5, 40.0)):
+        ang = angle_torture(dx=dx, dy=dy)
+        ref = port.areadinf(ang, dx=dx, dy=dy)
+        assert (ref >= 0).sum() > ang.size // 20
+        assert_bits(_run(emu, True, 0, 0, ang, None, True, 21, dx=dx, dy=dy), ref, f"sca angle torture {dx}x{dy}")
+        assert_bits(_run(emu, True, 0, 0, ang, None, False, 22, 3, dx=dx, dy=dy), port.areadinf(ang, dx=dx, dy=dy, contcheck=False), f"sca angle torture -nc, 3 strips {dx}x{dy}")
+
+
 def test_emulated_small_stacks_spill(fields):
     """A two-entry fork stack drops nearly every second receiver (the rescan of the shared-memory counts must find them);
     the outlet flood with a four-entry stack per warp spills nearly every discovered contributor to the host-drained list."""

@@ -275,6 +275,17 @@ def test_d8_stencil_ties_and_near_ties():
             assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
 
 
+def test_dinf_angle_torture():
+    """areadinf on angles at and next to every place where prop() changes its mind (sector edges, the 1e-5 share threshold, the
+    wrap sector, angles beyond 2 PI), bit for bit against the C restatement (pinned on the reference tools by the CPU suite)."""
+    from oracle import port
+    from util import angle_torture
+    for dx, dy in ((30.0, 30.0), (12.5, 40.0)):
+        ang = angle_torture(ny=200, nx=330, dx=dx, dy=dy)
+        assert_bits(td.areadinf_grid(ang, dx=dx, dy=dy), port.areadinf(ang, dx=dx, dy=dy), f"sca angle torture {dx}x{dy}")
+        assert_bits(td.areadinf_grid(ang, dx=dx, dy=dy, contcheck=False), port.areadinf(ang, dx=dx, dy=dy, contcheck=False), f"sca angle torture -nc {dx}x{dy}")
+
+
 def test_outlets_grid_and_file_level(refrun, tmp_path):
     """aread8 / areadinf -o: the cells upstream of the outlets only.  Grid level against the C restatement (which the
     CPU suite pins on the reference tools), file level (our executables with a point shapefile) against the reference

@@ -77,3 +77,28 @@ def write_point_geojson(path, xs, ys):
     import json
     feats = [{"type": "Feature", "properties": {"id": i + 1}, "geometry": {"type": "Point", "coordinates": [float(x), float(y)]}} for i, (x, y) in enumerate(zip(xs, ys))]
     json.dump({"type": "FeatureCollection", "features": feats}, open(path, "w"))
+
+
+def angle_torture(ny=96, nx=120, dx=30.0, dy=30.0, seed=5):
+    """A D-infinity angle grid made of the values where prop() changes its mind: the eight directions' angles and their float
+    neighbours, angles whose share for one direction lies within a few ulps of the 1e-5 threshold on either side (one of the
+    two receivers is dropped), the wrap sector below 2 PI, 0, 2 PI, angles beyond 2 PI, flats (-1) and nodata.  Mostly cyclic
+    nonsense as a flow field, which is fine: every tool leaves the cells of a cycle unevaluated."""
+    import numpy as np
+    PI = 3.14159265359
+    t = np.arctan2(dy, dx)
+    edges = [0.0, t, 0.5 * PI, PI - t, PI, PI + t, 1.5 * PI, 2 * PI - t, 2 * PI]
+    vals = []
+    for i, e in enumerate(edges):
+        f = np.float32(e)
+        vals += [f, np.nextafter(f, np.float32(10)), np.nextafter(f, np.float32(-10))]
+        if i + 1 < len(edges):
+            w = edges[i + 1] - e
+            for frac in (1e-5, 1e-5 * (1 + 2e-7), 1e-5 * (1 - 2e-7), 0.999e-5, 1.001e-5, 0.3, 0.5, 0.77):
+                vals += [np.float32(e + frac * w), np.float32(edges[i + 1] - frac * w)]
+    vals += [np.float32(2 * PI + 1e-4), np.float32(6.5), np.float32(1e-30), np.float32(-1.0)]
+    vals = np.array(vals, np.float32)
+    rng = np.random.default_rng(seed)
+    ang = vals[rng.integers(0, len(vals), size=(ny, nx))]
+    ang[rng.random((ny, nx)) < 0.02] = np.float32(-3.4028234663852886e38)
+    return np.ascontiguousarray(ang, np.float32)
