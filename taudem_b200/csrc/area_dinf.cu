@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     sout[i] = code;
     // halo rows of the strip (cells of the neighbour strips): receiver bits only, written by the tiles next to them
     if ((gr == 0 || gr == s.ny + 1) && sc >= G::HP && sc < G::HP + TW && gc < s.pitch && (t == 0 || t == s.ny + 2 - r0))
-      node[s.idx(gr, gc)] = (code & 0x20u) ? (unsigned short)0 : (unsigned short)((dinf_field(code) << 8) | ((code & 0x10u) ? 0x2000u : 0u));
+      node[s.idx(gr, gc)] = (code & 0x20u) ? (unsigned short)0 : (unsigned short)dinf_node_bits(code);
   }
   __syncthreads();
   // four adjacent cells per thread with byte-parallel arithmetic: neighbour k drains into me when one of its
@@ -86,9 +86,10 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     x = (x + (x >> 4)) & 0x0f0f0f0fu;
     const unsigned cw = (x & vm) | ~vm;                                   // count, or 0xff outside the field
     // VALID | CON (a neighbour off the grid or nodata) | the cell's own receivers: k1 in bits 8-11, 0x2000 = a second one (k1 % 8 + 1)
-    const unsigned k4 = wc & 0x0f0f0f0fu;
-    const unsigned plus8 = ((wc >> 6) | ((wc >> 7) & (eq_bytes7(k4, 0x01010101u) >> 7))) & 0x01010101u;       // upper, or irregular with k1 = 1
-    const unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1) | (k4 + (plus8 << 3)) | ((wc & 0x10101010u) << 1)) & vm;
+    // VALID | CON (a neighbour off the grid or nodata) | the cell's own receiver bits (dinf_node_bits: field in bits 8-11, 0x2000)
+    unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1)) & vm;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hb |= ((dinf_node_bits((wc >> (8 * i)) & 0xffu) >> 8) << (8 * i)) & vm;
     const unsigned mw = mb & vm;
     unsigned short on4[4]; unsigned char oc4[4];
 #pragma unroll

@@ -187,11 +187,12 @@ inline void make_prop_row(double t, bool uniform, PropRow* P) {
 
 // The receivers of a cell as the byte the dependency stencils work with: bits 0-3 = first receiver k1 (0 = none), 0x10 = there
 // is a second one (always k1 % 8 + 1), 0x40 = "upper": the angle lies in sector k1 - 1 and the sector's lower direction
-// got a share below 1e-5 (dropped), so the only receiver is the sector's upper direction, 0x80 = irregular: the wrap
-// sector, angles outside [0, 2 PI) or an upper cell with k1 = 8 — shares of such cells come from the interval search.
-// Regular cells (neither 0x80) get their shares from the sector table alone (SectorTab below):
+// got a share below 1e-5 (dropped), so the only receiver is the sector's upper direction, 0x80 = irregular: angles outside
+// [0, 2 PI), a wrap-sector cell whose only receiver is direction 1, an upper cell with k1 = 8 — the shares of such cells come
+// from the interval search.  Regular cells get their shares from the sector table alone:
 //   sector j = k1 (not upper) or k1 - 1 (upper);  first receiver of a non-upper cell: (ar[j+1] - a) / den[j];
-//   otherwise (second receiver, or the only receiver of an upper cell): (a - ar[j]) / den[j].
+//   second receiver, or the only receiver of an upper cell: (a - ar[j]) / den[j] — except in the wrap sector j = 8, whose
+//   second receiver is direction 1 reached through prop()'s float-rounded a - 2 PI: ((float)(a - 2 PI) - ar[0]) / den[0].
 template <typename AR>
 __device__ __forceinline__ unsigned dinf_node_code(float a, const AR& ar) {
   int j = 0;
@@ -207,14 +208,27 @@ __device__ __forceinline__ unsigned dinf_node_code(float a, const AR& ar) {
     return j < 7 ? ((unsigned)(j + 1) | 0x40u) : (8u | 0x80u);
   }
   const Outflow o = dinf_outflow_t(a, ar);
-  return o.k1 ? ((unsigned)o.k1 | (o.k2 ? 0x10u : 0u) | 0x80u) : 0u;
+  if (o.k1 == 0) return 0u;
+  if (j == 8 && o.k1 == 8) return 8u | (o.k2 ? 0x10u : 0u);      // wrap sector with direction 8 counted: regular
+  return (unsigned)o.k1 | (o.k2 ? 0x10u : 0u) | 0x80u;
 }
-// the 4-bit receiver field of a D-infinity node word: 0 none, 1..7 regular k1, 8 irregular k1 = 8, 9 irregular k1 = 1, 10..15 upper k1 = f - 8
-__host__ __device__ __forceinline__ unsigned dinf_field(unsigned code) {
+// The 4-bit receiver field of a D-infinity node word (bits 8-11) and what the word's 0x2000 bit means with it:
+//   0 none; 1..8 regular, k1 = f, 0x2000 = there is a second receiver; 10..15 upper, k1 = f - 8, single receiver;
+//   9 irregular, single receiver: k1 = 1, or k1 = 8 if 0x2000 is set (the bit has no other use there).
+__host__ __device__ __forceinline__ unsigned dinf_node_bits(unsigned code) {      // (field << 8) | 0x2000 flag, from dinf_node_code's byte
   const unsigned k = code & 0xfu;
-  return k + (((code & 0x40u) || ((code & 0x80u) && k == 1u)) ? 8u : 0u);
+  if (code & 0x80u) return (9u << 8) | (k == 8u ? 0x2000u : 0u);
+  if (code & 0x40u) return (k + 8u) << 8;
+  return (k << 8) | ((code & 0x10u) ? 0x2000u : 0u);
 }
-__host__ __device__ __forceinline__ int dinf_field_k1(unsigned f) { return (int)(f > 8u ? f - 8u : f); }
+__host__ __device__ __forceinline__ int dinf_node_k1(unsigned nd) {
+  const unsigned f = (nd >> 8) & 0xfu;
+  return (int)(f <= 8u ? f : (f == 9u ? ((nd & 0x2000u) ? 8u : 1u) : f - 8u));
+}
+__host__ __device__ __forceinline__ int dinf_node_k2(unsigned nd) {       // the second receiver, 0 = none
+  const unsigned f = (nd >> 8) & 0xfu;
+  return (f >= 1u && f <= 8u && (nd & 0x2000u)) ? (int)(f & 7u) + 1 : 0;
+}
 
 // RN(x / d) for a divisor whose correctly rounded reciprocal y = RN(1 / d) is known (see rowfact.cuh's div_const: Markstein's
 // two corrections with exact residuals; PropRow::safe / RowFact::safe state the precondition)

@@ -427,9 +427,9 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
   long long* fr = ctx->listC.as<long long>();
   const unsigned colblk = (unsigned)((s.nx + 255) / 256);
 
-  // TAUDEM_B200_FLATS_BATCH = K > 0 (single strip): K BFS levels per host round trip (k_bfs_level) instead of one
+  // single strip: 64 BFS levels per host round trip (k_bfs_level; TAUDEM_B200_FLATS_BATCH = K overrides, 0 = one launch + read-back per level)
   int batch = 0;
-  if (!multi) { const char* e = getenv("TAUDEM_B200_FLATS_BATCH"); batch = e ? std::max(0, std::min(atoi(e), 4096)) : 0; }
+  if (!multi) { const char* e = getenv("TAUDEM_B200_FLATS_BATCH"); batch = e ? std::max(0, std::min(atoi(e), 4096)) : 64; }
   constexpr unsigned long long MAXLEV = 1ull << 22;
   unsigned long long* bounds = nullptr; unsigned* blkdone = nullptr;
   int bgrid = 1;

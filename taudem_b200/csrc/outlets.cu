@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "dinf_common.cuh"
 #include "kernels.h"
 
 namespace td {
@@ -85,8 +86,7 @@ __global__ void __launch_bounds__(256) k_upstream(const UpArgs a) {
           if (s.on_grid(rn, cn) && rn >= 1 && rn <= s.ny) nn = a.node[s.idx(rn, cn)];
           if (!(nn & UP_VALID)) { con = 1; continue; }
           const int back = k > 4 ? k - 4 : k + 4;
-          const unsigned f = (nn >> 8) & 0xfu;                 // D8: the direction (0..8); D-infinity: the receiver field (dinf_field)
-          const int k1 = (int)(f > 8u ? f - 8u : f), k2 = (nn & 0x2000u) ? k1 % 8 + 1 : 0;
+          const int k1 = dinf_node_k1(nn), k2 = dinf_node_k2(nn);   // (D8 words: the direction 0..8, never a second receiver)
           if (k1 == back || k2 == back) mask |= 1u << (k - 1);
         }
         nd = UP_VALID | (con ? 0x1000u : 0u) | mask;            // receiver field 0: nothing downstream of it is decremented

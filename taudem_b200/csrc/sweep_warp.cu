@@ -505,12 +505,15 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
             const float av = M.ang[ni];
             const float an = M.area[ni];
             double p;
-            if (a.prop.uniform && f != 8u && f != 9u) {
+            if (a.prop.uniform && f != 9u) {
               const bool upper = f >= 10u;
               const int k1 = (int)(upper ? f - 8u : f);
-              const Sector S = sect[upper ? k1 - 1 : k1];
-              const double ad = (double)av;
-              const double num = (kk == k1 && !upper) ? S.hi - ad : ad - S.lo;
+              const bool first = kk == k1 && !upper;
+              const bool wrap = k1 == 8 && !first && !upper;                 // direction 1 from the wrap sector
+              const Sector S = sect[wrap ? 0 : (upper ? k1 - 1 : k1)];
+              double ad = (double)av;
+              if (wrap) ad = (double)(float)(ad - 2.0 * TD_PI);            // prop()'s float-rounded a - 2 PI (src/commonLib.cpp:82)
+              const double num = first ? S.hi - ad : ad - S.lo;
               p = a.prop.safe ? div_recip(num, S.den, S.rden) : num / S.den;
             } else {
               const int rn = r + dr;
@@ -531,7 +534,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
         for (int j = 0; j < (DINF ? 2 : 1); ++j) {
           int k;
           if (!DINF) k = (int)((nd >> 8) & 0xfu);
-          else { const int k1 = dinf_field_k1((nd >> 8) & 0xfu); k = j == 0 ? k1 : ((nd & 0x2000u) ? (k1 & 7) + 1 : 0); }
+          else k = j == 0 ? dinf_node_k1(nd) : dinf_node_k2(nd);
           if (k < 1 || k > 8) continue;
           const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
           if ((unsigned)nlr < (unsigned)TS && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {       // a cell of this tile

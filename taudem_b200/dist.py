@@ -242,11 +242,10 @@ class DistTools:
         self.share(fel)
         return self.T.dinf_slopes(self.s, fel, dxc, dyc, nodata)
 
-    # ---- flow directions incl. flats.  Default: the Garbrecht-Martz BFS runs REPLICATED — the strips of fel and of
-    # the positive-slope directions are all-gathered, every rank resolves the flats of the whole grid with the
-    # single-strip kernels and keeps its own rows (bit-identical by construction).  TAUDEM_B200_FLATS=strips
-    # selects the partitioned BFS (_flats_strips: one exchange per level; its protocol is checked against the
-    # oracle on the CPU emulation, tests/test_emu.py; it becomes the default once it has run on GPUs).
+    # ---- flow directions incl. flats.  The Garbrecht-Martz BFS runs on the row strips themselves (_flats_strips: one exchange
+    # per level like the reference's share() + MPI_Allreduce per pass; checked against the oracle on the CPU emulation and
+    # bit-identical to the single-strip run over NCCL on 2 GPUs, scripts/dist_check.py).  TAUDEM_B200_FLATS=replicated selects
+    # the first-generation fallback: all-gather fel + directions, every rank resolves the whole grid and keeps its rows.
     def gather_full(self, t):
         """All-gather of the owned rows of a strip tensor -> full-grid strip tensor (halo rows unused)."""
         from .device import DeviceStrip
@@ -342,7 +341,7 @@ class DistTools:
         total = all_reduce_scalar(int(nflat), device=self.s.device) if self.world > 1 else int(nflat)
         if total == 0:
             return 0
-        if os.environ.get("TAUDEM_B200_FLATS") == "strips":
+        if os.environ.get("TAUDEM_B200_FLATS") != "replicated":
             return self._flats_strips(fel, d, dxc, dyc, dinf)
         sf, fel_full = self.gather_full(fel)
         _, d_full = self.gather_full(d)

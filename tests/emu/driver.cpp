@@ -83,7 +83,8 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
         S.cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
       }
   } else {
-    std::vector<unsigned char> code(n, 0), field(n, 0);
+    std::vector<unsigned char> code(n, 0);
+    std::vector<unsigned short> bits(n, 0);
     for (int r = 0; r <= ny + 1; ++r)
       for (int c = 0; c < nx; ++c) {
         if (!s.on_grid(r, c)) continue;
@@ -92,9 +93,9 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
         const double th = S.theta[std::min(std::max(r - 1, 0), ny - 1)];
         const td::Outflow o = td::dinf_outflow(av, th);
         code[s.idx(r, c)] = (unsigned char)(o.k1 | (o.k2 << 4));
-        field[s.idx(r, c)] = (unsigned char)td::dinf_field(td::dinf_node_code(av, td::ArefRow{th}));      // how the sweep obtains the shares
-        if ((td::dinf_node_code(av, td::ArefRow{th}) & 0x1fu) != (unsigned)(o.k1 | (o.k2 ? 0x10 : 0))) abort();
-        if (r == 0 || r == ny + 1) S.node[s.idx(r, c)] = (unsigned short)(((unsigned)field[s.idx(r, c)] << 8) | (o.k2 ? 0x2000u : 0u));   // halo rows: receivers only
+        bits[s.idx(r, c)] = (unsigned short)td::dinf_node_bits(td::dinf_node_code(av, td::ArefRow{th}));      // how the sweep obtains the shares
+        if (td::dinf_node_k1(bits[s.idx(r, c)]) != o.k1 || td::dinf_node_k2(bits[s.idx(r, c)]) != o.k2) abort();
+        if (r == 0 || r == ny + 1) S.node[s.idx(r, c)] = bits[s.idx(r, c)];   // halo rows: receivers only
       }
     for (int r = 1; r <= ny; ++r)
       for (int c = 0; c < nx; ++c) {
@@ -108,7 +109,7 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
           if ((int)(cd & 15u) == kk || (int)(cd >> 4) == kk) mask |= 1u << (k - 1);
         }
         const unsigned own = code[s.idx(r, c)];                        // receivers of the cell itself: k1, and whether there is a second one
-        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask | ((unsigned)field[s.idx(r, c)] << 8) | ((own >> 4) ? 0x2000u : 0u));
+        S.node[s.idx(r, c)] = (unsigned short)(VALID | (con ? CON : 0u) | mask | bits[s.idx(r, c)]);
         S.cnt[s.idx(r, c)] = (unsigned char)__builtin_popcount(mask);
         if ((own >> 4) && (own >> 4) != (own & 15u) % 8 + 1) abort();  // the second receiver is always the next direction
       }
