@@ -27,7 +27,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 T0 = time.time()
 METRIC = "Mcells/s for aread8+areadinf on synthetic fractal DEM"
 HURST, TILT, SEED = 0.8, 1.0, 1234
-# dram__bytes_read + dram__bytes_write per cell from the ncu --set full captures at 8192^2 (profiles/r02_ncu_summary.md); None = not captured
+# dram__bytes_read + dram__bytes_write per cell from the ncu --set full captures (sweeps at 16384^2, dependency stencils at 8192^2: profiles/r02_ncu_summary.md); None = not captured
 NCU_TRAFFIC_PER_CELL = {"aread8_sweep": None, "areadinf_sweep": None, "aread8_deps": None, "areadinf_deps": None}
 try:
     with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as _f:
@@ -274,10 +274,10 @@ def ours(args):
             pipeline[k].update({"algorithmic_bytes_per_cell": b, "GB_per_s": round(gbs(b, pipe_ms[k]), 1), "frac_of_hbm_peak": round(gbs(b, pipe_ms[k]) / peak, 4)})
     roofline = {"bound": "hbm", "kernel": KERNEL[dom], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": round(traffic * cells) if traffic else None,
-                "traffic_source": "ncu --set full capture at 8192^2 scaled per cell (profiles/r02_ncu_summary.md)" if traffic else "not captured",
+                "traffic_source": "ncu --set full capture at 16384^2 (dram__bytes_read + write of one launch), scaled per cell to this size (profiles/r02_ncu_summary.md)" if traffic else "not captured",
                 "peak_source": peak_src, "sweep": sweep_name(), "sweep_stats": R["sweep_stats"],
                 "algorithmic_bytes_per_cell": ALG_BYTES[dom], "ms_per_launch": round(part_ms[dom], 3),
-                "note": "the contributing-area sweep is bound by the latency of dependent tile visits, not by bandwidth (DESIGN.md section 4)",
+                "note": "the contributing-area sweep is bound by instruction issue (aread8) / dependent-issue latency x tiles in flight (areadinf), not by bandwidth (DESIGN.md section 4.1)",
                 "per_kernel_ms": {KERNEL[k]: round(v, 3) for k, v in part_ms.items()},
                 "per_kernel_frac": {KERNEL[k]: round(ALG_BYTES[k] * cells / (v * 1e-3) / 1e9 / peak, 5) for k, v in part_ms.items()},
                 "pipeline": pipeline}

@@ -566,26 +566,15 @@ int resolve_flats(td_ctx* ctx, float* elev, typename P::DirT* dir, const Strip& 
 }
 }  // namespace
 
-// the level rasters (8 B per cell) and the flat-cell lists are only needed while the flats are resolved: the contributing-area
-// tools that follow need the memory (16 B per cell of D-infinity shares)
-static void release_flat_scratch(td_ctx* ctx, cudaStream_t st) {
-  cudaStreamSynchronize(st);
-  ctx->lev.release(); ctx->mk.release(); ctx->listA.release(); ctx->listB.release(); ctx->listC.release();
-}
-
 int resolve_flats_d8(td_ctx* ctx, float* elev, short* dir, const Strip& s, const double* dxc, const double* dyc, long long* nleft,
                      const td_strip_comm* comm, cudaStream_t st) {
   Geo g{dxc, dyc, nullptr, nullptr};
-  const int rc = resolve_flats<D8Pol>(ctx, elev, dir, s, g, nleft, comm, st);
-  release_flat_scratch(ctx, st);
-  return rc;
+  return resolve_flats<D8Pol>(ctx, elev, dir, s, g, nleft, comm, st);
 }
 int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, const double* dxc, const double* dyc, const double* thA,
                        const double* thB, long long* nleft, const td_strip_comm* comm, cudaStream_t st) {
   Geo g{dxc, dyc, thA, thB};
-  const int rc = resolve_flats<DinfPol>(ctx, elev, ang, s, g, nleft, comm, st);
-  release_flat_scratch(ctx, st);
-  return rc;
+  return resolve_flats<DinfPol>(ctx, elev, ang, s, g, nleft, comm, st);
 }
 
 }  // namespace td
