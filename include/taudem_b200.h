@@ -95,6 +95,13 @@ int td_aread8_host(const int16_t* p, const float* w /*NULL unless usew*/, float*
 int td_area_host(const float* ang, const float* w /*NULL unless usew*/, float* sca, int nx, int ny,
                  float ang_nodata, float w_nodata, const double* dxc, const double* dyc,
                  int contcheck);
+/* aread8 + areadinf of one DEM in one call (no weights, no outlets), the host<->device copies overlapped with the kernels
+ * on three streams: p in -> aread8 || ang in -> areadinf || ad8 out -> sca out.  Same results as the two calls above.
+ * Pinned host rasters make the copies asynchronous.  (No counterpart in the reference: its tools are one process each,
+ * src/aread8.cpp:56, src/areadinf.cpp:53; this is what a caller that wants both rasters of a DEM would bind.) */
+int td_contributing_areas_host(const int16_t* p, const float* ang, float* ad8, float* sca, int nx, int ny, int16_t p_nodata,
+                               float ang_nodata, const double* dxc, const double* dyc, int contcheck);
+
 /* The same with outlets (-o; the outlet branches of initNeighborD8up / initNeighborDinfup,
  * src/commonLib.cpp:285-385, 137-237): only the cells upstream of the outlet cells (column, row; points
  * off the grid are ignored) are evaluated, everything else keeps the nodata value -1.  nout < 0: no

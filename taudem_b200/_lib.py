@@ -48,6 +48,7 @@ SIGNATURES = {
     "td_setdir_host": (_I, [_P, _P, _P, _I, _I, _F, _P, _P]),
     "td_aread8_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _F, _I]),
     "td_area_host": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _I]),
+    "td_contributing_areas_host": (_I, [_P, _P, _P, _P, _I, _I, C.c_int16, _F, _P, _P, _I]),
     "td_aread8_outlets_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _F, _I, _P, _P, _I]),
     "td_area_outlets_host": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _I, _P, _P, _I]),
     "td_sweep_restrict_dev": (_I, [_P, Strip, _P, _P, _I, _P]),

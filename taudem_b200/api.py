@@ -153,6 +153,18 @@ def aread8_grid(p, nodata=int(MISSINGSHORT), weights=None, w_nodata=-9999.0, con
     return ad8
 
 
+def contributing_areas_grid(p, ang, p_nodata=int(MISSINGSHORT), ang_nodata=float(MISSINGFLOAT), dx=30.0, dy=30.0, contcheck=True, out_ad8=None, out_sca=None):
+    """aread8 + areadinf of one DEM in one call, copies overlapped with the kernels (td_contributing_areas_host)."""
+    p = _grid(p, np.int16); ang = _grid(ang, np.float32)
+    ny, nx = p.shape
+    assert ang.shape == p.shape
+    ad8 = out_ad8 if out_ad8 is not None else np.empty((ny, nx), np.float32)
+    sca = out_sca if out_sca is not None else np.empty((ny, nx), np.float32)
+    dxc, dyc = _rows(dx, ny), _rows(dy, ny)
+    check(lib().td_contributing_areas_host(_ptr(p), _ptr(ang), _ptr(ad8), _ptr(sca), nx, ny, int(p_nodata), np.float32(ang_nodata), _ptr(dxc), _ptr(dyc), int(contcheck)))
+    return ad8, sca
+
+
 def areadinf_grid(ang, nodata=float(MISSINGFLOAT), weights=None, w_nodata=-9999.0, dx=30.0, dy=30.0, contcheck=True, out=None, outlets=None):
     ang = _grid(ang, np.float32)
     ny, nx = ang.shape

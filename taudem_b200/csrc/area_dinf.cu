@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
   // 0x40 / 0x80 how the shares are obtained | 0x20 if the cell is off the grid or nodata; one prop() interval search each
   __shared__ double saref[(TH + 2) * 10];
   __shared__ __align__(16) unsigned char sout[G::ELEMS];
+  __shared__ __align__(16) unsigned char sbits[G::ELEMS];     // the receiver bits of the node word's high byte (dinf_node_bits >> 8)
   for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) saref[i] = aref(i % 10, theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]);
   __syncthreads();
   for (int i = threadIdx.x; i < G::ELEMS; i += 256) {
@@ -46,9 +47,11 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
       if (!nd_f(av, nodata)) code = (unsigned char)dinf_node_code(av, saref + t * 10);
     }
     sout[i] = code;
+    const unsigned nb = (code & 0x20u) ? 0u : dinf_node_bits(code);
+    sbits[i] = (unsigned char)(nb >> 8);
     // halo rows of the strip (cells of the neighbour strips): receiver bits only, written by the tiles next to them
     if ((gr == 0 || gr == s.ny + 1) && sc >= G::HP && sc < G::HP + TW && gc < s.pitch && (t == 0 || t == s.ny + 2 - r0))
-      node[s.idx(gr, gc)] = (code & 0x20u) ? (unsigned short)0 : (unsigned short)dinf_node_bits(code);
+      node[s.idx(gr, gc)] = (unsigned short)nb;
   }
   __syncthreads();
   // four adjacent cells per thread with byte-parallel arithmetic: neighbour k drains into me when one of its
@@ -87,9 +90,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     const unsigned cw = (x & vm) | ~vm;                                   // count, or 0xff outside the field
     // VALID | CON (a neighbour off the grid or nodata) | the cell's own receivers: k1 in bits 8-11, 0x2000 = a second one (k1 % 8 + 1)
     // VALID | CON (a neighbour off the grid or nodata) | the cell's own receiver bits (dinf_node_bits: field in bits 8-11, 0x2000)
-    unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1)) & vm;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) hb |= ((dinf_node_bits((wc >> (8 * i)) & 0xffu) >> 8) << (8 * i)) & vm;
+    const unsigned hb = (0x80808080u | ((all & 0x20202020u) >> 1) | reinterpret_cast<const unsigned*>(sbits)[(tr + 1) * QW + lane + 1]) & vm;
     const unsigned mw = mb & vm;
     unsigned short on4[4]; unsigned char oc4[4];
 #pragma unroll

@@ -440,6 +440,50 @@ int td_aread8_outlets_host(const int16_t* p, const float* w, float* ad8, int nx,
   return TD_OK;
 }
 
+// aread8 + areadinf of one DEM in ONE call with the copies overlapped with the kernels: three streams — host -> device (p, then
+// ang), compute (aread8 as soon as p has arrived, areadinf as soon as ang has and aread8 is done), device -> host (ad8 while
+// areadinf runs, then sca).  Same kernels, same results as td_aread8_host followed by td_area_host (no weights, no outlets).
+// Host rasters should be pinned (cudaHostAlloc / cudaHostRegister) — pageable memory makes the copies synchronous.
+int td_contributing_areas_host(const int16_t* p, const float* ang, float* ad8, float* sca, int nx, int ny, int16_t p_nodata, float ang_nodata,
+                               const double* dxc, const double* dyc, int contcheck) {
+  if (int rc = need_device()) return rc;
+  if (!p || !ang || !ad8 || !sca || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_contributing_areas_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  TD_CUDA(ctx->io[0].ensure(n * 2)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[2].ensure(n * 4)); TD_CUDA(ctx->io[3].ensure(n * 4));
+  int16_t* d_p = ctx->io[0].as<int16_t>(); float* d_ad8 = ctx->io[1].as<float>(); float* d_ang = ctx->io[2].as<float>(); float* d_sca = ctx->io[3].as<float>();
+  struct Streams {
+    cudaStream_t in = nullptr, run = nullptr, out = nullptr; cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Streams() { for (auto& x : e) if (x) cudaEventDestroy(x); if (in) cudaStreamDestroy(in); if (run) cudaStreamDestroy(run); if (out) cudaStreamDestroy(out); }
+  } S;
+  TD_CUDA(cudaDeviceSynchronize());          // earlier work of this context (legacy stream) is done before the private streams start
+  TD_CUDA(cudaStreamCreateWithFlags(&S.in, cudaStreamNonBlocking)); TD_CUDA(cudaStreamCreateWithFlags(&S.run, cudaStreamNonBlocking));
+  TD_CUDA(cudaStreamCreateWithFlags(&S.out, cudaStreamNonBlocking));
+  for (auto& x : S.e) TD_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+  const double *d_dx, *d_dy;
+  if (int rc = upload_rows(ctx, dxc, dyc, ny, &d_dx, &d_dy, S.run)) return rc;
+  TD_CUDA(h2d(d_p, p, s, S.in));     TD_CUDA(cudaEventRecord(S.e[0], S.in));
+  TD_CUDA(h2d(d_ang, ang, s, S.in)); TD_CUDA(cudaEventRecord(S.e[1], S.in));
+  Timer t; t.start(S.run);
+  TD_CUDA(cudaStreamWaitEvent(S.run, S.e[0], 0));
+  if (int rc = td_aread8_deps_dev(ctx, d_p, d_ad8, s, p_nodata, S.run)) return rc;
+  if (int rc = td_aread8_sweep_dev(ctx, nullptr, d_ad8, s, 0.f, 0, contcheck, S.run)) return rc;
+  TD_CUDA(cudaEventRecord(S.e[2], S.run));
+  TD_CUDA(cudaStreamWaitEvent(S.out, S.e[2], 0));
+  TD_CUDA(d2h(ad8, d_ad8, s, S.out));
+  TD_CUDA(cudaStreamWaitEvent(S.run, S.e[1], 0));
+  if (int rc = td_area_deps_dev(ctx, d_ang, d_sca, s, ang_nodata, d_dx, d_dy, S.run)) return rc;
+  if (int rc = td_area_sweep_dev(ctx, d_ang, nullptr, d_sca, s, 0, contcheck, d_dx, S.run)) return rc;
+  TD_CUDA(cudaEventRecord(S.e[3], S.run));
+  td::set_compute_seconds(t.stop(S.run));
+  TD_CUDA(cudaStreamWaitEvent(S.out, S.e[3], 0));
+  TD_CUDA(d2h(sca, d_sca, s, S.out));
+  TD_CUDA(cudaStreamSynchronize(S.out));
+  TD_CUDA(cudaStreamSynchronize(S.in));
+  return TD_OK;
+}
+
 int td_area_host(const float* ang, const float* w, float* sca, int nx, int ny, float ang_nodata, float w_nodata, const double* dxc,
                  const double* dyc, int contcheck) {
   return td_area_outlets_host(ang, w, sca, nx, ny, ang_nodata, w_nodata, dxc, dyc, contcheck, nullptr, nullptr, -1);

@@ -409,17 +409,29 @@ def bench_main(args, rank, world, local):
     D = DistTools(n, n, rank, world, device=dev)
     s = D.s
     dxc, dyc = s.rows(30.0), s.rows(30.0)
+    pipe_ms = {}
+
+    def timed(name, fn):
+        """one tool of the pipeline on all ranks: CUDA events per rank, max over ranks (BASELINE.json configs[3])"""
+        torch.cuda.synchronize(); dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(); r = fn(); a1.record(); torch.cuda.synchronize()
+        t = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pipe_ms[name] = round(float(t.item()), 3)
+        return r
+
     dem = D.T.gen_dem(s, seed=B.SEED, hurst=B.HURST, tilt=B.TILT)
-    fel = D.pitremove(dem)
+    fel = timed("pitremove", lambda: D.pitremove(dem))
     del dem
-    p, sd8 = D.d8flowdir(fel, dxc, dyc)
+    p, sd8 = timed("d8flowdir", lambda: D.d8flowdir(fel, dxc, dyc))
     del sd8
-    ang, slp = D.dinfflowdir(fel, dxc, dyc)
+    ang, slp = timed("dinfflowdir", lambda: D.dinfflowdir(fel, dxc, dyc))
     del slp, fel
     torch.cuda.synchronize(); torch.cuda.empty_cache()
     info = {"setup_s": round(time.time() - t_setup, 2)}
     ad8, sca = s.empty(torch.float32), s.empty(torch.float32)
-    log("inputs ready", info)
+    log("inputs ready", info, pipe_ms)
 
     def step():
         D.aread8(p, ad8)
@@ -442,6 +454,14 @@ def bench_main(args, rank, world, local):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = torch.tensor([td.launch_count()], device=dev, dtype=torch.int64)
     dist.all_reduce(launches)
+    # BASELINE.json configs[4]: areadinf with a weight grid (-wg), same strips
+    w = D.T.gen_weights(s)
+    scaw = s.empty(torch.float32)
+    D.areadinf(ang, dxc, dyc, scaw, w=w)
+    timed("areadinf_wg", lambda: D.areadinf(ang, dxc, dyc, scaw, w=w))
+    timed("aread8", lambda: D.aread8(p, ad8))
+    timed("areadinf", lambda: D.areadinf(ang, dxc, dyc, sca))
+    del w, scaw
     mx = torch.stack([s.owned(ad8).max(), s.owned(sca).max()]).double()
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     # 64-bit hashes of the raw bits of the whole rasters: the strips' position-weighted sums add up (mod 2^64)
@@ -484,9 +504,11 @@ def bench_main(args, rank, world, local):
                 "e2e": {"value": round(cells / 1e6 / float(te.item()), 2), "unit": "Mcells/s", "h2d_bytes_per_step": cells * 6, "d2h_bytes_per_step": cells * 8,
                         "steps": e2e_steps, "ms_per_step": round(float(te.item()) * 1e3, 2), "api": "per-rank pinned host strips -> device strips -> DistTools.aread8/areadinf -> pinned host strips"},
                 "gpu_launches": int(launches.item()),
-                "roofline": {"bound": "hbm", "kernel": "k_sweep_tiles<dinf>", "achieved": round(8 * cells / (ms_per_step * 1e-3) / 1e9 / world, 2), "peak": peak, "unit": "GB/s",
-                             "frac": round(8 * cells / (ms_per_step * 1e-3) / 1e9 / world / peak, 5), "traffic": None, "peak_source": peak_src,
-                             "note": "per GPU, whole step time attributed to the dominant kernel (upper bound on its duration)"},
+                "roofline": {"bound": "hbm", "kernel": "k_sweep_warp<dinf>", "achieved": round(8 * cells / (pipe_ms["areadinf"] * 1e-3) / 1e9 / world, 2), "peak": peak, "unit": "GB/s",
+                             "frac": round(8 * cells / (pipe_ms["areadinf"] * 1e-3) / 1e9 / world / peak, 5), "traffic": None, "peak_source": peak_src,
+                             "note": "per GPU: the strip's algorithmic bytes over the whole areadinf time (dependency stencil + sweep, max over ranks)",
+                             "per_tool_ms": pipe_ms,
+                             "per_tool_Mcells_per_s": {k: round(cells / 1e6 / (v * 1e-3), 1) for k, v in pipe_ms.items()}},
                 "cpu_baseline": None}
         print(json.dumps(line))
     dist.barrier()

@@ -275,6 +275,19 @@ def test_d8_stencil_ties_and_near_ties():
             assert_bits(p, p_ref, f"p ties {dx}x{dy}"); assert_bits(sd8, sd8_ref, f"sd8 ties {dx}x{dy}")
 
 
+def test_overlapped_two_tool_call_equals_the_two_calls():
+    """td_contributing_areas_host (aread8 + areadinf of one DEM, copies overlapped with the kernels on three streams) returns
+    exactly what td_aread8_host and td_area_host return."""
+    dem = synth.punch_holes(synth.gen_dem(700, 900, hurst=0.8, tilt=1.0, seed=23))
+    fel = td.pitremove_grid(dem); p, _ = td.d8flowdir_grid(fel, dx=25.0, dy=35.0); ang, _ = td.dinfflowdir_grid(fel, dx=25.0, dy=35.0)
+    ad8, sca = td.contributing_areas_grid(p, ang, dx=25.0, dy=35.0)
+    assert_bits(ad8, td.aread8_grid(p), "ad8 (overlapped call)")
+    assert_bits(sca, td.areadinf_grid(ang, dx=25.0, dy=35.0), "sca (overlapped call)")
+    ad8, sca = td.contributing_areas_grid(p, ang, dx=25.0, dy=35.0, contcheck=False)
+    assert_bits(ad8, td.aread8_grid(p, contcheck=False), "ad8 -nc (overlapped call)")
+    assert_bits(sca, td.areadinf_grid(ang, dx=25.0, dy=35.0, contcheck=False), "sca -nc (overlapped call)")
+
+
 def test_dinf_angle_torture():
     """areadinf on angles at and next to every place where prop() changes its mind (sector edges, the 1e-5 share threshold, the
     wrap sector, angles beyond 2 PI), bit for bit against the C restatement (pinned on the reference tools by the CPU suite)."""
