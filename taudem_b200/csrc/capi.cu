@@ -154,11 +154,8 @@ int td_d8_flats_strip_dev(td_ctx* ctx, float* fel, int16_t* p, td_strip s, const
 }
 
 // per-row atan2 tables are evaluated on the host (glibc), like the reference's prop()/VSLOPE do
-static int upload_theta(td_ctx* ctx, const double* d_dxc, const double* d_dyc, int ny, td_ctx::Buf& buf, cudaStream_t st) {
-  std::vector<double> dx(ny), dy(ny), th(2 * (size_t)ny);
-  TD_CUDA(cudaMemcpyAsync(dx.data(), d_dxc, sizeof(double) * ny, cudaMemcpyDeviceToHost, st));
-  TD_CUDA(cudaMemcpyAsync(dy.data(), d_dyc, sizeof(double) * ny, cudaMemcpyDeviceToHost, st));
-  TD_CUDA(cudaStreamSynchronize(st));
+static int upload_theta_from_host(td_ctx* ctx, const double* dx, const double* dy, int ny, td_ctx::Buf& buf, cudaStream_t st) {
+  std::vector<double> th(2 * (size_t)ny);
   for (int j = 0; j < ny; j++) { th[j] = atan2(dy[j], dx[j]); th[ny + j] = atan2(dx[j], dy[j]); }
   TD_CUDA(buf.ensure(sizeof(double) * 2 * (size_t)ny));
   TD_CUDA(cudaMemcpyAsync(buf.p, th.data(), sizeof(double) * 2 * (size_t)ny, cudaMemcpyHostToDevice, st));
@@ -169,6 +166,13 @@ static int upload_theta(td_ctx* ctx, const double* d_dxc, const double* d_dyc, i
   td::make_prop_row(th[0], uni, &ctx->prop);
   ctx->dx0 = dx[0];
   return TD_OK;
+}
+static int upload_theta(td_ctx* ctx, const double* d_dxc, const double* d_dyc, int ny, td_ctx::Buf& buf, cudaStream_t st) {
+  std::vector<double> dx(ny), dy(ny);
+  TD_CUDA(cudaMemcpyAsync(dx.data(), d_dxc, sizeof(double) * ny, cudaMemcpyDeviceToHost, st));
+  TD_CUDA(cudaMemcpyAsync(dy.data(), d_dyc, sizeof(double) * ny, cudaMemcpyDeviceToHost, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return upload_theta_from_host(ctx, dx.data(), dy.data(), ny, buf, st);
 }
 
 int td_dinf_slopes_dev(td_ctx* ctx, const float* fel, float* ang, float* slp, td_strip s, float fel_nodata, const double* dxc,
@@ -216,7 +220,7 @@ static int ensure_dep_state(td_ctx* ctx, const Strip& s, cudaStream_t st) {
   TD_CUDA(ctx->node.ensure(n * 2));
   TD_CUDA(ctx->cnt.ensure((n + 3) / 4 * 4));
   TD_CUDA(ctx->halo.ensure(sizeof(int) * 2 * (size_t)s.pitch));
-  TD_CUDA(cudaMemsetAsync(ctx->halo.p, 0, sizeof(int) * 2 * (size_t)s.pitch, st));
+  TD_CUDA(td::zero_words(ctx->halo.p, sizeof(int) * 2 * (size_t)s.pitch, st));
   return TD_OK;
 }
 
@@ -234,16 +238,22 @@ int td_aread8_sweep_dev(td_ctx* ctx, const float* w, float* ad8, td_strip s, flo
   return td::wsweep_run(ctx, false, ad8, w, nullptr, Strip(s), w_nodata, usew, contcheck, nullptr, nullptr, ctx->halo.as<int>(), (cudaStream_t)stream);
 }
 
-int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, float ang_nodata, const double* dxc, const double* dyc,
-                     void* stream) {
+// (theta_ready: the caller has uploaded the row tables of this strip already — upload_theta_from_host — so that no small copy
+//  of this call queues behind a raster that is travelling on another stream)
+static int area_deps(td_ctx* ctx, const float* ang, float* sca, td_strip s, float ang_nodata, const double* dxc, const double* dyc,
+                     bool theta_ready, void* stream) {
   if (int rc = check_strip(s)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = ensure_dep_state(ctx, Strip(s), st)) return rc;
-  if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc;
+  if (!theta_ready) { if (int rc = upload_theta(ctx, dxc, dyc, s.ny, ctx->theta, st)) return rc; }
   ctx->sweep_dinf = 1;
   TD_CUDA(td::launch_deps_dinf(ang, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), sca, Strip(s), ang_nodata,
                                ctx->theta.as<double>(), st));
   return TD_OK;
+}
+int td_area_deps_dev(td_ctx* ctx, const float* ang, float* sca, td_strip s, float ang_nodata, const double* dxc, const double* dyc,
+                     void* stream) {
+  return area_deps(ctx, ang, sca, s, ang_nodata, dxc, dyc, false, stream);
 }
 int td_area_sweep_dev(td_ctx* ctx, const float* ang, const float* w, float* sca, td_strip s, int usew, int contcheck,
                       const double* dxc, void* stream) {
@@ -323,10 +333,20 @@ struct Timer {
 };
 // host dense (nx) <-> device strip rows 1..ny (pitch)
 template <typename T> cudaError_t h2d(T* dst, const T* src, const td_strip& s, cudaStream_t st) {
+  if (s.pitch == s.nx) {
+    // one contiguous block, sent in 64 MiB pieces
+    const size_t total = (size_t)s.nx * s.ny * sizeof(T), piece = (size_t)64 << 20;
+    for (size_t off = 0; off < total; off += piece) {
+      const cudaError_t e = cudaMemcpyAsync((char*)(dst + s.pitch) + off, (const char*)src + off, std::min(piece, total - off), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   return cudaMemcpy2DAsync(dst + s.pitch, (size_t)s.pitch * sizeof(T), src, (size_t)s.nx * sizeof(T), (size_t)s.nx * sizeof(T), s.ny,
                            cudaMemcpyHostToDevice, st);
 }
 template <typename T> cudaError_t d2h(T* dst, const T* src, const td_strip& s, cudaStream_t st) {
+  if (s.pitch == s.nx) return cudaMemcpyAsync(dst, src + s.pitch, (size_t)s.nx * s.ny * sizeof(T), cudaMemcpyDeviceToHost, st);
   return cudaMemcpy2DAsync(dst, (size_t)s.nx * sizeof(T), src + s.pitch, (size_t)s.pitch * sizeof(T), (size_t)s.nx * sizeof(T), s.ny,
                            cudaMemcpyDeviceToHost, st);
 }
@@ -454,33 +474,56 @@ int td_contributing_areas_host(const int16_t* p, const float* ang, float* ad8, f
   TD_CUDA(ctx->io[0].ensure(n * 2)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[2].ensure(n * 4)); TD_CUDA(ctx->io[3].ensure(n * 4));
   int16_t* d_p = ctx->io[0].as<int16_t>(); float* d_ad8 = ctx->io[1].as<float>(); float* d_ang = ctx->io[2].as<float>(); float* d_sca = ctx->io[3].as<float>();
   struct Streams {
-    cudaStream_t in = nullptr, run = nullptr, out = nullptr; cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
-    ~Streams() { for (auto& x : e) if (x) cudaEventDestroy(x); if (in) cudaStreamDestroy(in); if (run) cudaStreamDestroy(run); if (out) cudaStreamDestroy(out); }
+    cudaStream_t in = nullptr, run = nullptr, out = nullptr; cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t t[12] = {};
+    ~Streams() { for (auto& x : e) if (x) cudaEventDestroy(x); for (auto& x : t) if (x) cudaEventDestroy(x); if (in) cudaStreamDestroy(in); if (run) cudaStreamDestroy(run); if (out) cudaStreamDestroy(out); }
   } S;
   TD_CUDA(cudaDeviceSynchronize());          // earlier work of this context (legacy stream) is done before the private streams start
   TD_CUDA(cudaStreamCreateWithFlags(&S.in, cudaStreamNonBlocking)); TD_CUDA(cudaStreamCreateWithFlags(&S.run, cudaStreamNonBlocking));
   TD_CUDA(cudaStreamCreateWithFlags(&S.out, cudaStreamNonBlocking));
   for (auto& x : S.e) TD_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+  const bool trace = getenv("TAUDEM_B200_TRACE") != nullptr;      // timestamps of every copy / tool on its stream
+  if (trace) for (auto& x : S.t) TD_CUDA(cudaEventCreate(&x));
+  auto mark = [&](int i, cudaStream_t st) { if (trace) cudaEventRecord(S.t[i], st); };
   const double *d_dx, *d_dy;
   if (int rc = upload_rows(ctx, dxc, dyc, ny, &d_dx, &d_dy, S.run)) return rc;
-  TD_CUDA(h2d(d_p, p, s, S.in));     TD_CUDA(cudaEventRecord(S.e[0], S.in));
-  TD_CUDA(h2d(d_ang, ang, s, S.in)); TD_CUDA(cudaEventRecord(S.e[1], S.in));
+  if (int rc = upload_theta_from_host(ctx, dxc, dyc, ny, ctx->theta, S.run)) return rc;     // every small copy before the rasters travel
+  mark(0, S.in);
+  TD_CUDA(h2d(d_p, p, s, S.in));     TD_CUDA(cudaEventRecord(S.e[0], S.in)); mark(1, S.in);
+  // The HOST waits for p: a stream that waits for an event of the upload stream is only released when that stream's LAST
+  // upload is done if more uploads were queued behind the event (measured, TAUDEM_B200_TRACE: aread8 began when ang had
+  // arrived) — so nothing is queued behind p until the kernels that need it are running.
+  TD_CUDA(cudaEventSynchronize(S.e[0]));
   Timer t; t.start(S.run);
   TD_CUDA(cudaStreamWaitEvent(S.run, S.e[0], 0));
+  mark(3, S.run);
   if (int rc = td_aread8_deps_dev(ctx, d_p, d_ad8, s, p_nodata, S.run)) return rc;
   if (int rc = td_aread8_sweep_dev(ctx, nullptr, d_ad8, s, 0.f, 0, contcheck, S.run)) return rc;
-  TD_CUDA(cudaEventRecord(S.e[2], S.run));
+  TD_CUDA(cudaEventRecord(S.e[2], S.run)); mark(4, S.run);
+  (void)cudaStreamQuery(S.run);                      // push the launches to the device now
+  const auto h0 = std::chrono::steady_clock::now();
+  TD_CUDA(h2d(d_ang, ang, s, S.in)); TD_CUDA(cudaEventRecord(S.e[1], S.in)); mark(2, S.in);
+  if (trace) fprintf(stderr, "[td trace] host spent %.2f ms enqueueing the ang upload\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
   TD_CUDA(cudaStreamWaitEvent(S.out, S.e[2], 0));
+  mark(5, S.out);
   TD_CUDA(d2h(ad8, d_ad8, s, S.out));
+  mark(6, S.out);
   TD_CUDA(cudaStreamWaitEvent(S.run, S.e[1], 0));
-  if (int rc = td_area_deps_dev(ctx, d_ang, d_sca, s, ang_nodata, d_dx, d_dy, S.run)) return rc;
+  mark(7, S.run);
+  if (int rc = area_deps(ctx, d_ang, d_sca, s, ang_nodata, d_dx, d_dy, true, S.run)) return rc;
   if (int rc = td_area_sweep_dev(ctx, d_ang, nullptr, d_sca, s, 0, contcheck, d_dx, S.run)) return rc;
-  TD_CUDA(cudaEventRecord(S.e[3], S.run));
+  TD_CUDA(cudaEventRecord(S.e[3], S.run)); mark(8, S.run);
   td::set_compute_seconds(t.stop(S.run));
   TD_CUDA(cudaStreamWaitEvent(S.out, S.e[3], 0));
+  mark(9, S.out);
   TD_CUDA(d2h(sca, d_sca, s, S.out));
+  mark(10, S.out);
   TD_CUDA(cudaStreamSynchronize(S.out));
   TD_CUDA(cudaStreamSynchronize(S.in));
+  if (trace) {
+    const char* what[11] = {"in: start", "in: p arrived", "in: ang arrived", "run: aread8 starts", "run: aread8 done", "out: ad8 copy starts", "out: ad8 copied",
+                            "run: areadinf starts", "run: areadinf done", "out: sca copy starts", "out: sca copied"};
+    for (int i = 1; i < 11; ++i) { float ms = 0; cudaEventElapsedTime(&ms, S.t[0], S.t[i]); fprintf(stderr, "[td trace] %8.2f ms  %s\n", ms, what[i]); }
+  }
   return TD_OK;
 }
 

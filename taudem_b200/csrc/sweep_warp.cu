@@ -302,6 +302,20 @@ __device__ void sched_finish(const WArgs& a, int t) {
   atomicAdd(w_done(a.ctr, t & (a.nsh - 1)), 1ull);
 }
 
+// Zeroing by a kernel, not cudaMemsetAsync: memsets are executed by the copy engines, where they queue behind whatever
+// host <-> device copy of another stream is in flight (a 17 GB raster: 0.3 s) and stall this stream's kernels with them.
+__global__ void k_zero_words(unsigned* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+}  // namespace
+cudaError_t zero_words(void* p, size_t bytes, cudaStream_t st) {
+  const size_t n = bytes / 4;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+  k_zero_words<<<grid ? grid : 1, 256, 0, st>>>((unsigned*)p, n);
+  TD_LAUNCHED();
+  return cudaGetLastError();
+}
+namespace {
 // start of a sweep: every tile queued (the rings and the scheduler words were zeroed before)
 __global__ void k_wsched_init(int* state, int* tq, int ntiles, unsigned long long* ctr, unsigned long long* stat, int nsh, int qshift, unsigned qmask) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -701,8 +715,8 @@ int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   const int nt = a.ntx * a.nty;
-  TD_CUDA(cudaMemsetAsync(a.ctr, 0, C_WORDS * sizeof(unsigned long long), st));
-  TD_CUDA(cudaMemsetAsync(a.tq, 0, ((size_t)a.nsh << a.qshift) * sizeof(int), st));
+  TD_CUDA(zero_words(a.ctr, C_WORDS * sizeof(unsigned long long), st));
+  TD_CUDA(zero_words(a.tq, ((size_t)a.nsh << a.qshift) * sizeof(int), st));
   k_wsched_init<<<(nt + 255) / 256, 256, 0, st>>>(a.state, a.tq, nt, a.ctr, a.stat, a.nsh, a.qshift, a.qmask);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
@@ -844,7 +858,7 @@ int sweep_peer_begin(td_ctx* ctx, const Strip& s, cudaStream_t st) {
   if (int rc = wsweep_begin(ctx, s, st)) return rc;
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
-  TD_CUDA(cudaMemsetAsync(ctx->peer_halo.p, 0, sizeof(float) * 2 * (size_t)s.pitch, st));
+  TD_CUDA(zero_words(ctx->peer_halo.p, sizeof(float) * 2 * (size_t)s.pitch, st));
   k_add_G<<<1, 32, 0, st>>>((unsigned long long*)ctx->peer_G, 1ull);     // this strip is active
   TD_LAUNCHED();
   TD_CUDA(cudaStreamSynchronize(st));

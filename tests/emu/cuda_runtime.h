@@ -123,6 +123,8 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline long long clock64() { return 0; }
 inline long long __double_as_longlong(double d) { long long v; memcpy(&v, &d, 8); return v; }
+inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) << (sh & 31) >> 32); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31)); }
 using std::max;
