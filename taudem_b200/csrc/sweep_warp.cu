@@ -456,7 +456,115 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           }
         }
       }
-      if (__ballot_sync(FULL, cur >= 0) == 0u) {
+      const unsigned act = __ballot_sync(FULL, cur >= 0);
+      if (act != 0u && (act & (act - 1u)) == 0u) {
+        // ---- one chain left (a river crossing the tile, the tail of every visit; the fork stack is empty, or idle lanes
+        // would have taken from it): the WHOLE warp follows it together.  Nothing diverges and nothing is contended: the cell
+        // is warp-uniform, lanes 0..7 evaluate one contributor link each (D-infinity), everybody folds the products in
+        // increasing k through shuffles, lane 0 alone touches the counts (plain loads and stores, no atomics, no ballots).
+        // A second receiver that becomes ready ends the mode (it goes to the stack: the other lanes are needed again).
+        int c = __shfl_sync(FULL, cur, __ffs(act) - 1);
+        bool forked = false;
+        do {
+          ++iters;
+          const int lr = c >> 5, lx = c & 31;
+          const int ri = (lr + 1) * RS + lx + 4;
+          float wv = 0.f;
+          if (USEW) wv = a.w[s.idx(r0 + lr, c0 + lx)];
+          const unsigned nd = M.node[ri];
+          const unsigned msk = nd & 0xffu;
+          bool con = (nd & NODE_CON) != 0;
+          float val;
+          if (!DINF) {
+            if (USEW) {
+              val = nd_f(wv, a.w_nodata) ? -1.0f : wv;
+#pragma unroll
+              for (int k = 1; k <= 8; ++k)
+                if (msk & (1u << (k - 1))) {
+                  const float an = M.area[ri + drow(k) * RS + dcol(k)];
+                  if (nd_f(an, -1.0f)) con = true; else val = val + an;
+                }
+            } else {
+              val = 1.0f;
+              float mn = 0.f;
+#pragma unroll
+              for (int k = 1; k <= 8; ++k)
+                if (msk & (1u << (k - 1))) {
+                  const float an = M.area[ri + drow(k) * RS + dcol(k)];
+                  val = val + an;
+                  mn = fminf(mn, an);
+                }
+              if (mn < 0.f) con = true;
+            }
+          } else {
+            double prod = 0.;
+            if (lane < 8 && ((msk >> lane) & 1u)) {
+              const int k = lane + 1;
+              const int dr = lut_drow(k);
+              const int ni = ri + dr * RS + lut_dcol(k);
+              const int kk = k > 4 ? k - 4 : k + 4;              // the direction from that neighbour to the cell
+              const unsigned f = ((unsigned)M.node[ni] >> 8) & 0xfu;
+              const float av = M.ang[ni];
+              const float an = M.area[ni];
+              double p;
+              if (a.prop.uniform && f != 9u) {
+                const bool upper = f >= 10u;
+                const int k1 = (int)(upper ? f - 8u : f);
+                const bool first = kk == k1 && !upper;
+                const bool wrap = k1 == 8 && !first && !upper;
+                const Sector S = sect[wrap ? 0 : (upper ? k1 - 1 : k1)];
+                double ad = (double)av;
+                if (wrap) ad = (double)(float)(ad - 2.0 * TD_PI);
+                const double num = first ? S.hi - ad : ad - S.lo;
+                p = a.prop.safe ? div_recip(num, S.den, S.rden) : num / S.den;
+              } else {
+                const int rn = r0 + lr + dr;
+                p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : a.theta[min(max(rn - 1, 0), s.ny - 1)], kk);
+              }
+              prod = nd_f(an, -1.0f) ? __longlong_as_double(0x7ff8dead00000000ll) : p * (double)an;   // NaN: a contaminated contributor
+            }
+            val = 0.f;
+            for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
+              const double pr = __shfl_sync(FULL, prod, __ffs(m) - 1);
+              if (pr != pr) con = true; else val = (float)((double)val + pr);
+            }
+            if (USEW) val = val + wv;
+            else val = (float)((double)val + (a.prop.uniform ? a.dx0 : a.dxc[min(r0 + lr, s.ny) - 1]));
+          }
+          if (con && a.contcheck) val = -1.0f;
+          if (lane == 0) { M.area[ri] = val; M.evmask[lr] |= 1u << lx; }
+          int next = -1;
+#pragma unroll
+          for (int j = 0; j < (DINF ? 2 : 1); ++j) {
+            int k;
+            if (!DINF) k = (int)((nd >> 8) & 0xfu);
+            else k = j == 0 ? dinf_node_k1(nd) : dinf_node_k2(nd);
+            if (k < 1 || k > 8) continue;
+            const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
+            if ((unsigned)nlr < (unsigned)TS && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {
+              const int l2 = nlr * TS + nlx;
+              const unsigned sh = (unsigned)(l2 & 3) * 8u;
+              unsigned w = 0;
+              if (lane == 0) { w = M.cnt[l2 >> 2]; M.cnt[l2 >> 2] = w - (1u << sh); }
+              w = __shfl_sync(FULL, w, 0);
+              if (((w >> sh) & 0xffu) == 1u) {
+                if (next < 0) next = l2;
+                else {
+                  forked = true;
+                  if (lane == 0) { const int slot = M.sp; if (slot < STKCAP) M.stk[slot] = (unsigned short)l2; M.sp = slot + 1; }
+                }
+              }
+            } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
+              if (lane == 0) { M.ext[M.next] = (unsigned short)(c | ((k - 1) << 10)); M.next = M.next + 1; }
+            }
+          }
+          c = next;
+          __syncwarp();            // lane 0's stores (area, counts) before the next cell's loads
+        } while (c >= 0 && !forked);
+        cur = lane == 0 ? c : -1;
+        continue;
+      }
+      if (act == 0u) {
         if (!DINF) break;
         // forks that did not fit the stack are ready (count 0) and not evaluated: look once more
         const unsigned ev = M.evmask[lane];
