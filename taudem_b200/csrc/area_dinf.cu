@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
   __shared__ double saref[(TH + 2) * 10];
   __shared__ __align__(16) unsigned char sout[G::ELEMS];
   __shared__ __align__(16) unsigned char sbits[G::ELEMS];     // the receiver bits of the node word's high byte (dinf_node_bits >> 8)
-  for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) saref[i] = aref(i % 10, theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]);
+  __shared__ float sarf[(TH + 2) * 10];                          // the same table rounded to float: the pre-screen below
+  for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) { const double v = aref(i % 10, theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]); saref[i] = v; sarf[i] = (float)v; }
   __syncthreads();
   for (int i = threadIdx.x; i < G::ELEMS; i += 256) {
     const int t = i / G::SW, sc = i - t * G::SW;
@@ -44,7 +45,20 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     unsigned char code = 0x20;
     if (s.on_grid(gr, gc)) {
       const float av = tile[i];
-      if (!nd_f(av, nodata)) code = (unsigned char)dinf_node_code(av, saref + t * 10);
+      if (!nd_f(av, nodata)) {
+        // Pre-screen in float: an angle well inside a sector (further than 4e-5 sector widths from both edges — float rounding
+        // of the table and of the differences is three orders of magnitude below that) has both shares far above prop()'s
+        // 1e-5 threshold: receivers j and j + 1, regular, nothing to decide in double.  Everything near or on an edge
+        // (flow exactly along a direction is common) takes the exact path.
+        const float* af = sarf + t * 10;
+        int j = 0;
+#pragma unroll
+        for (int e = 1; e <= 9; ++e) j += (av >= af[e]) ? 1 : 0;
+        const int jc = min(max(j, 1), 8);
+        const float lo = af[jc], hi = af[jc + 1], g = 4e-5f * (hi - lo);
+        if (j >= 1 && j <= 8 && av - lo > g && hi - av > g) code = (unsigned char)((unsigned)j | 0x10u);
+        else code = (unsigned char)dinf_node_code(av, saref + t * 10);
+      }
     }
     sout[i] = code;
     const unsigned nb = (code & 0x20u) ? 0u : dinf_node_bits(code);

@@ -70,9 +70,10 @@ int write_like(const char* name, const Input& like, tdio::DType t, double nodata
   if (fileGB > 4.0) printf("Setting BIGTIFF, File: %s, Anticipated size (GB):%.2f\n", path.c_str(), fileGB);
   tdio::Writer w;
   std::string err;
-  const char* comp_env = getenv("TAUDEM_B200_COMPRESS");   // "LZW" | "DEFLATE" | unset (= none)
-  int comp = 1;
-  if (comp_env && strcmp(comp_env, "LZW") == 0) comp = 5;
+  // LZW like the reference's GTiff creation options (src/tiffIO.cpp:316-318); TAUDEM_B200_COMPRESS = NONE | DEFLATE | LZW overrides
+  const char* comp_env = getenv("TAUDEM_B200_COMPRESS");
+  int comp = 5;
+  if (comp_env && strcmp(comp_env, "NONE") == 0) comp = 1;
   if (comp_env && strcmp(comp_env, "DEFLATE") == 0) comp = 8;
   if (!w.create(path, like.nx, like.ny, t, nodata, like.r.geo(), comp, &err) || !w.write_rows(0, like.ny, data.data(), &err) || !w.close(&err)) {
     printf("Error writing %s: %s\n", path.c_str(), err.c_str());
