@@ -319,6 +319,29 @@ def workload_name(n):
             "contamination check on, no weights")
 
 
+def host_cores():
+    """CPUs this process may really use: the affinity mask, capped by the cgroup CPU quota (a container can see 128 CPUs and own 8;
+    48 pinned ranks on 8 cores made the reference arm 12x slower on one of the pool's hosts)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0]); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def cpu_reference_sample(p_host, ang_host, sample, ranks):
     """Times the reference's own aread8 + areadinf (oracle/_ref, sources compiled unchanged) on a
     window of the same rasters, on this box's host cores."""
@@ -327,14 +350,14 @@ def cpu_reference_sample(p_host, ang_host, sample, ranks):
     if not refrun.available():
         return {"value": None, "unit": "Mcells/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
     m = min(sample, p_host.shape[0])
-    ranks = max(1, min(ranks, os.cpu_count() or 1))
+    ranks = max(1, min(ranks, host_cores()))
     os.environ["MINIMPI_PIN"] = "1"
     R = refrun.RefPipeline(np_ranks=ranks)
     pw = np.ascontiguousarray(p_host[:m, :m]); aw = np.ascontiguousarray(ang_host[:m, :m])
     R.aread8(pw); R.areadinf(aw)
     t = R.times["aread8"]["Compute time"] + R.times["areadinf"]["Compute time"]
     return {"value": round(m * m / 1e6 / t, 3), "unit": "Mcells/s", "cores": ranks, "kind": "reference",
-            "sample": f"top-left {m}x{m} window of the {p_host.shape[0]}^2 rasters; the reference tools' own 'Compute time' lines (aread8 {R.times['aread8']['Compute time']:.2f} s + areadinf {R.times['areadinf']['Compute time']:.2f} s), {ranks} ranks pinned one per core over the fork/socketpair MPI shim"}
+            "sample": f"top-left {m}x{m} window of the {p_host.shape[0]}^2 rasters; the reference tools' own 'Compute time' lines (aread8 {R.times['aread8']['Compute time']:.2f} s + areadinf {R.times['areadinf']['Compute time']:.2f} s), {ranks} ranks pinned one per core over the fork/socketpair MPI shim ({host_cores()} usable cores of {os.cpu_count()})"}
 
 
 def prep(args):
@@ -365,7 +388,7 @@ def reference(args):
     if not refrun.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built on this box"}))
         return
-    ranks = max(1, min(args.cpu_ranks, os.cpu_count() or 1))
+    ranks = max(1, min(args.cpu_ranks, host_cores()))
     os.environ["MINIMPI_PIN"] = "1"
     n = args.size or REF_SIZE
     work = tempfile.mkdtemp(prefix="tdbench_ref_")
@@ -391,7 +414,7 @@ def reference(args):
     times = times[-steps:]
     t = sum(a + b for a, b in times) / len(times)
     v = round(n * n / 1e6 / t, 3)
-    sample = f"{note}; the reference tools' own 'Compute time' lines (aread8 {times[-1][0]:.2f} s + areadinf {times[-1][1]:.2f} s), {ranks} ranks pinned one per core (fork/socketpair MPI shim)"
+    sample = f"{note}; the reference tools' own 'Compute time' lines (aread8 {times[-1][0]:.2f} s + areadinf {times[-1][1]:.2f} s), {ranks} ranks pinned one per core (fork/socketpair MPI shim; {host_cores()} usable cores of {os.cpu_count()})"
     import shutil
     shutil.rmtree(work, ignore_errors=True)
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mcells/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1 if args.warmup else 0,
