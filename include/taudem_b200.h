@@ -150,6 +150,9 @@ int td_flood_init_dev(td_ctx*, const float* dem, const int16_t* depmask, float* 
                       td_strip s, float dem_nodata, int is_4Point, void* stream);
 int td_flood_relax_dev(td_ctx*, const float* dem, float* planchon, td_strip s, int is_4Point,
                        int* changed_out, void* stream);
+/* the same after the neighbours' edge rows were copied into the halo rows again: starts from the tiles next to them only */
+int td_flood_relax_edges_dev(td_ctx*, const float* dem, float* planchon, td_strip s, int is_4Point,
+                             int* changed_out, void* stream);
 
 /* D8: setPosDir+calcSlope stencil (src/d8.cpp:359-409,153-177); dxc/dyc are DEVICE arrays
  * of ny doubles.  *nflat_out (host) = number of dir==0 cells in the strip.                */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "td_gen_weights_dev": (_I, [_P, Strip, _I, C.c_uint, _P]),
     "td_flood_init_dev": (_I, [_P, _P, _P, _P, Strip, _F, _I, _P]),
     "td_flood_relax_dev": (_I, [_P, _P, _P, Strip, _I, _P, _P]),
+    "td_flood_relax_edges_dev": (_I, [_P, _P, _P, Strip, _I, _P, _P]),
     "td_d8_slopes_dev": (_I, [_P, _P, _P, _P, Strip, _F, _P, _P, _P, _P]),
     "td_d8_flats_dev": (_I, [_P, _P, _P, Strip, _P, _P, _P, _P]),
     "td_d8_flats_strip_dev": (_I, [_P, _P, _P, Strip, _P, _P, _P, _P, _P]),

@@ -121,6 +121,15 @@ int td_flood_relax_dev(td_ctx* ctx, const float* dem, float* planchon, td_strip 
   return rc;
 }
 
+// after an exchange of the halo rows: only the tiles next to them are queued to start with
+int td_flood_relax_edges_dev(td_ctx* ctx, const float* dem, float* planchon, td_strip s, int is_4Point, int* changed_out, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  int ch = 0;
+  int rc = td::fill_relax(ctx, dem, planchon, Strip(s), is_4Point, &ch, (cudaStream_t)stream, true);
+  if (changed_out) *changed_out = ch;
+  return rc;
+}
+
 int td_d8_slopes_dev(td_ctx* ctx, const float* fel, int16_t* p, float* sd8, td_strip s, float fel_nodata, const double* dxc,
                      const double* dyc, long long* nflat_out, void* stream) {
   if (int rc = check_strip(s)) return rc;

@@ -142,6 +142,18 @@ __global__ void k_fill_all_tiles(int* list, int* flag, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) { list[t] = t; flag[t] = 1; }
 }
+// only the tiles that see a halo row (after an exchange with the neighbour strips nothing else can have changed)
+__global__ void k_fill_edge_tiles(int* list, int* flag, int ntx, int nty) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nedge = nty > 1 ? 2 * ntx : ntx;
+  if (i >= ntx * nty) return;
+  flag[i] = 0;
+  if (i < nedge) { const int t = i < ntx ? i : (nty - 1) * ntx + (i - ntx); list[i] = t; }
+}
+__global__ void k_fill_edge_flags(const int* list, int* flag, int nedge) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nedge) flag[list[i]] = 1;
+}
 }  // namespace
 
 int fill_init(const float* dem, const short* mask, float* W, const Strip& s, float nodata, int four, cudaStream_t st) {
@@ -153,16 +165,24 @@ int fill_init(const float* dem, const short* mask, float* W, const Strip& s, flo
 }
 
 // Relaxes until no tile of the strip changes.  *changed = whether any cell moved.
-int fill_relax(td_ctx* ctx, const float* dem, float* W, const Strip& s, int four, int* changed, cudaStream_t st) {
+int fill_relax(td_ctx* ctx, const float* dem, float* W, const Strip& s, int four, int* changed, cudaStream_t st, bool edges_only) {
   const int ntx = (s.nx + FW - 1) / FW, nty = (s.ny + FH - 1) / FH;
   const long long nt = (long long)ntx * nty;
   TD_CUDA(ctx->tileflags.ensure((size_t)nt * 4 * 3));
   int* flag = ctx->tileflags.as<int>();
   int* la = flag + nt;
   int* lb = la + nt;
-  k_fill_all_tiles<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(la, flag, (int)nt);
-  TD_LAUNCHED();
   unsigned long long n = (unsigned long long)nt;
+  if (edges_only) {
+    n = (unsigned long long)(nty > 1 ? 2 * ntx : ntx);
+    k_fill_edge_tiles<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(la, flag, ntx, nty);
+    TD_LAUNCHED();
+    k_fill_edge_flags<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(la, flag, (int)n);
+    TD_LAUNCHED();
+  } else {
+    k_fill_all_tiles<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(la, flag, (int)nt);
+    TD_LAUNCHED();
+  }
   int round = 1;
   *changed = 0;
   while (n > 0) {

@@ -80,9 +80,10 @@ class Tools:
         check(self.l.td_flood_init_dev(self.ctx, _p(dem), _p(depmask), _p(w), s.c, nodata, int(four_way), self._stream()))
         return w
 
-    def flood_relax(self, s, dem, w, four_way=False):
+    def flood_relax(self, s, dem, w, four_way=False, edges_only=False):
         ch = C.c_int(0)
-        check(self.l.td_flood_relax_dev(self.ctx, _p(dem), _p(w), s.c, int(four_way), C.byref(ch), self._stream()))
+        fn = self.l.td_flood_relax_edges_dev if edges_only else self.l.td_flood_relax_dev
+        check(fn(self.ctx, _p(dem), _p(w), s.c, int(four_way), C.byref(ch), self._stream()))
         return bool(ch.value)
 
     def pitremove(self, s, dem, nodata=-9999.0, four_way=False):

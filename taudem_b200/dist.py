@@ -380,9 +380,12 @@ class DistTools:
         s = self.s
         self.share(dem)
         w = self.T.flood_init(s, dem, nodata, four_way)
+        first = True
         while True:
             self.share(w)                                     # fresh halo rows from the neighbours
-            moved = int(self.T.flood_relax(s, dem, w, four_way))
+            # after the first pass only the tiles next to the halo rows can have something new to do
+            moved = int(self.T.flood_relax(s, dem, w, four_way, edges_only=not first))
+            first = False
             if self.world > 1:
                 moved = all_reduce_scalar(moved, device=s.device)   # ringTerm: did any strip move?
             if moved == 0:
