@@ -95,6 +95,15 @@ int td_aread8_host(const int16_t* p, const float* w /*NULL unless usew*/, float*
 int td_area_host(const float* ang, const float* w /*NULL unless usew*/, float* sca, int nx, int ny,
                  float ang_nodata, float w_nodata, const double* dxc, const double* dyc,
                  int contcheck);
+/* Point-wise consumers of the area rasters.  File level = the reference prototypes
+ * `int threshold(char* ssafile, char* srcfile, char* maskfile, float thresh, int usemask)` (src/Threshold.cpp:48) and
+ * `int twigrid(char* slopefile, char* areafile, char* twifile)` (src/TWI.cpp:47); host-grid and device-strip level like
+ * the other tools.  src: int16, nodata -32768; twi: float32, nodata -1 (within 1 float ulp of the reference's logf). */
+int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile, float thresh, int usemask);
+int td_twigrid(const char* slopefile, const char* areafile, const char* twifile);
+int td_threshold_host(const float* ssa, const float* mask /*NULL unless usemask*/, int16_t* src, int nx, int ny, float thresh, float ssa_nodata);
+int td_twi_host(const float* slp, const float* sca, float* twi, int nx, int ny, float slp_nodata, float sca_nodata);
+
 /* aread8 + areadinf of one DEM in one call (no weights, no outlets), the host<->device copies overlapped with the kernels
  * on three streams: p in -> aread8 || ang in -> areadinf || ad8 out -> sca out.  Same results as the two calls above.
  * Pinned host rasters make the copies asynchronous.  (No counterpart in the reference: its tools are one process each,
@@ -231,6 +240,10 @@ int td_aread8_sweep_run_dev(td_ctx*, const float* w, float* ad8, td_strip s, flo
                             int contcheck, int* halo_out, void* stream);
 int td_area_sweep_run_dev(td_ctx*, const float* ang, const float* w, float* sca, td_strip s, int usew,
                           int contcheck, const double* dxc, int* halo_out, void* stream);
+
+/* point-wise consumers on device strips (pointwise.cu) */
+int td_threshold_dev(td_ctx*, const float* ssa, const float* mask, int16_t* src, td_strip s, float thresh, float ssa_nodata, void* stream);
+int td_twi_dev(td_ctx*, const float* slp, const float* sca, float* twi, td_strip s, float slp_nodata, float sca_nodata, void* stream);
 
 /* Peer mode (one process per GPU on one NVSwitch box): every rank exports the IPC handles of the buffers
  * its neighbours write (counts, tile scheduler, halo areas, rank 0 also the global pending counter), opens

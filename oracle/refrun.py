@@ -102,3 +102,17 @@ class RefPipeline:
             args.append("-nc")
         _, self.times["areadinf"] = run_tool("areadinf", args, self.np_ranks)
         return self.get("sca.tif", np.float32)
+
+    def threshold(self, ssa, thresh, mask=None, nodata=-1.0):
+        self.put("ssa.tif", ssa, nodata)
+        args = ["-ssa", self.path("ssa.tif"), "-src", self.path("src.tif"), "-thresh", repr(float(thresh))]
+        if mask is not None:
+            self.put("mask.tif", mask, -9999.0)
+            args += ["-mask", self.path("mask.tif")]
+        _, self.times["threshold"] = run_tool("threshold", args, self.np_ranks)
+        return self.get("src.tif", np.int16)
+
+    def twi(self, slp, sca, nodata=-1.0):
+        self.put("slpin.tif", slp, nodata); self.put("scain.tif", sca, nodata)
+        _, self.times["twi"] = run_tool("twi", ["-slp", self.path("slpin.tif"), "-sca", self.path("scain.tif"), "-twi", self.path("twi.tif")], self.np_ranks)
+        return self.get("twi.tif", np.float32)

@@ -38,6 +38,12 @@ SIGNATURES = {
     "td_setdir": (_I, [_S, _S, _S, _S, _I]),
     "td_aread8": (_I, [_S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
     "td_area": (_I, [_S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
+    "td_threshold": (_I, [_S, _S, _S, _F, _I]),
+    "td_twigrid": (_I, [_S, _S, _S]),
+    "td_threshold_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),
+    "td_twi_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),
+    "td_threshold_dev": (_I, [_P, _P, _P, _P, Strip, _F, _F, _P]),
+    "td_twi_dev": (_I, [_P, _P, _P, _P, Strip, _F, _F, _P]),
     "td_nameadd": (_I, [_S, _S, _S]),
     "td_raster_info": (_I, [_S] + [_P] * 9),
     "td_raster_read": (_I, [_S, _I, _P, _I, _I]),

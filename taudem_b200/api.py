@@ -153,6 +153,26 @@ def aread8_grid(p, nodata=int(MISSINGSHORT), weights=None, w_nodata=-9999.0, con
     return ad8
 
 
+def threshold_grid(ssa, thresh=100.0, mask=None, nodata=-1.0):
+    """src = (ssa >= thresh [& mask >= 0]) ? 1 : 0, -32768 where ssa is nodata (td_threshold_host; src/Threshold.cpp:109-131)."""
+    ssa = _grid(ssa, np.float32)
+    ny, nx = ssa.shape
+    m = None if mask is None else _grid(mask, np.float32)
+    src = np.empty((ny, nx), np.int16)
+    check(lib().td_threshold_host(_ptr(ssa), _ptr(m), _ptr(src), nx, ny, np.float32(thresh), np.float32(nodata)))
+    return src
+
+
+def twi_grid(slp, sca, slp_nodata=-1.0, sca_nodata=-1.0):
+    """twi = ln(sca / slp) where both are data and positive, else -1 (td_twi_host; src/TWI.cpp:108-124)."""
+    slp = _grid(slp, np.float32); sca = _grid(sca, np.float32)
+    ny, nx = slp.shape
+    assert sca.shape == slp.shape
+    twi = np.empty((ny, nx), np.float32)
+    check(lib().td_twi_host(_ptr(slp), _ptr(sca), _ptr(twi), nx, ny, np.float32(slp_nodata), np.float32(sca_nodata)))
+    return twi
+
+
 def contributing_areas_grid(p, ang, p_nodata=int(MISSINGSHORT), ang_nodata=float(MISSINGFLOAT), dx=30.0, dy=30.0, contcheck=True, out_ad8=None, out_sca=None):
     """aread8 + areadinf of one DEM in one call, copies overlapped with the kernels (td_contributing_areas_host)."""
     p = _grid(p, np.int16); ang = _grid(ang, np.float32)

@@ -469,6 +469,51 @@ int td_aread8_outlets_host(const int16_t* p, const float* w, float* ad8, int nx,
   return TD_OK;
 }
 
+// ---- point-wise consumers (pointwise.cu): device-strip and host-grid level
+int td_threshold_dev(td_ctx*, const float* ssa, const float* mask, int16_t* src, td_strip s, float thresh, float ssa_nodata, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::launch_threshold(ssa, mask, src, Strip(s), thresh, ssa_nodata, (cudaStream_t)stream);
+}
+int td_twi_dev(td_ctx*, const float* slp, const float* sca, float* twi, td_strip s, float slp_nodata, float sca_nodata, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::launch_twi(slp, sca, twi, Strip(s), slp_nodata, sca_nodata, (cudaStream_t)stream);
+}
+int td_threshold_host(const float* ssa, const float* mask, int16_t* src, int nx, int ny, float thresh, float ssa_nodata) {
+  if (int rc = need_device()) return rc;
+  if (!ssa || !src || nx <= 0 || ny <= 0) { td::set_error("td_threshold_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 2));
+  float* d_ssa = ctx->io[0].as<float>(); int16_t* d_src = ctx->io[1].as<int16_t>(); float* d_mask = nullptr;
+  TD_CUDA(h2d(d_ssa, ssa, s, st));
+  if (mask) { TD_CUDA(ctx->io[2].ensure(n * 4)); d_mask = ctx->io[2].as<float>(); TD_CUDA(h2d(d_mask, mask, s, st)); }
+  Timer t; t.start(st);
+  if (int rc = td_threshold_dev(ctx, d_ssa, d_mask, d_src, s, thresh, ssa_nodata, st)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(src, d_src, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+int td_twi_host(const float* slp, const float* sca, float* twi, int nx, int ny, float slp_nodata, float sca_nodata) {
+  if (int rc = need_device()) return rc;
+  if (!slp || !sca || !twi || nx <= 0 || ny <= 0) { td::set_error("td_twi_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[2].ensure(n * 4));
+  float* d_slp = ctx->io[0].as<float>(); float* d_sca = ctx->io[1].as<float>(); float* d_twi = ctx->io[2].as<float>();
+  TD_CUDA(h2d(d_slp, slp, s, st)); TD_CUDA(h2d(d_sca, sca, s, st));
+  Timer t; t.start(st);
+  if (int rc = td_twi_dev(ctx, d_slp, d_sca, d_twi, s, slp_nodata, sca_nodata, st)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(twi, d_twi, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
 // aread8 + areadinf of one DEM in ONE call with the copies overlapped with the kernels: three streams — host -> device (p, then
 // ang), compute (aread8 as soon as p has arrived, areadinf as soon as ang has and aread8 is done), device -> host (ad8 while
 // areadinf runs, then sca).  Same kernels, same results as td_aread8_host followed by td_area_host (no weights, no outlets).

@@ -1,4 +1,4 @@
-// Command line front ends: pitremove, d8flowdir, dinfflowdir, aread8, areadinf.
+// Command line front ends: pitremove, d8flowdir, dinfflowdir, aread8, areadinf (+ the point-wise consumers threshold, twi).
 // Same flags, same two invocation styles and the same "print usage and exit(0)" error
 // behaviour as the reference mains (src/PitRemovemn.cpp:48-172, src/D8FlowDirmn.cpp:49-146,
 // src/DinfFlowDirmn.cpp:54-147, src/aread8mn.cpp:49-193, src/areadinfmn.cpp:49-178);
@@ -13,7 +13,7 @@
 
 struct Opt {
   const char* flag;
-  int kind;        // 0 = file name, 1 = switch, 2 = integer
+  int kind;        // 0 = file name, 1 = switch, 2 = integer, 3 = float (ival points to a float)
   char* sval;      // kind 0
   int* ival;       // kind 1 (set to `set`) / kind 2 (parsed) / kind 0 (set to `set` when given, may be NULL)
   int set;
@@ -38,6 +38,7 @@ static void parse(int argc, char** argv, Opt* opts, int nopts) {
     if (o->kind == 1) { *o->ival = o->set; continue; }
     if (argc <= i) usage(argv[0]);
     if (o->kind == 0) { strncpy(o->sval, argv[i], MAXLN - 1); o->sval[MAXLN - 1] = 0; if (o->ival) *o->ival = o->set; }
+    else if (o->kind == 3) sscanf(argv[i], "%f", (float*)o->ival);
     else sscanf(argv[i], "%d", o->ival);
     i++;
   }
@@ -162,6 +163,59 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(out, argv[1], OUT_SUFF); td_nameadd(in, argv[1], IN_SUFF); }
   int err = CALL(in, out, datasrc, lyrname, uselyrname, lyrno, wfile, useOutlets, usew, contcheck);
   if (err != 0) printf("area error %d\n", err);
+  return 0;
+}
+#elif defined(TOOL_threshold)
+// src/Thresholdmn.cpp:50-130 (its usage text names the flags wrongly; the flags themselves are -ssa -src -thresh -mask)
+static void usage(const char* prog) {
+  printf("Simple Use:\n %s <basefilename>\n", prog);
+  printf("Use with specific file names:\n %s -fel <ssafile>\n", prog);
+  printf("-ss <srcfile> [-thresh <thresholdvalue>] [-mask <maskfile>]\n");
+  printf("<basefilename> is the name of the base digital elevation model without suffixes for simple input. Suffixes 'ssa' and 'src' will be appended. \n");
+  printf("<ssafile> is the name of file to be thresholded.\n");
+  printf("<srcfile> is the name of file with the thresholded output.\n");
+  printf("<maskfile> is the name of a file that masks the domain.\n");
+  printf("<thresholdvalue> is the value of the threshold.\n");
+  printf("The threshold logic is src = ((ssa >= thresh) & (mask >=0)) ? 1:0.\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char ssa[MAXLN], src[MAXLN], mask[MAXLN];
+  int usemask = 0;
+  float thresh = 100.f;
+  if (argc < 2) usage(argv[0]);                 // (no "Error:" preamble in this tool)
+  Opt opts[] = {{"-ssa", 0, ssa, NULL, 0}, {"-src", 0, src, NULL, 0}, {"-mask", 0, mask, &usemask, 1}, {"-thresh", 3, NULL, (int*)&thresh, 0}};
+  parse(argc, argv, opts, 4);
+  if (argc == 2) { td_nameadd(ssa, argv[1], "ssa"); td_nameadd(src, argv[1], "src"); }
+  int err = td_threshold(ssa, src, mask, thresh, usemask);
+  if (err != 0) printf("Threshold Error %d\n", err);
+  return 0;
+}
+
+#elif defined(TOOL_twi)
+// src/TWImn.cpp:48-129
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s -sca <areafile>\n", prog);
+  printf("-slp <slopefile> -twi <twifile>\n");
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("<areafile> is the D-infinity specific catchment area input file.\n");
+  printf("<slopefile> is the D-infinity slope input file.\n");
+  printf("<twifile> is the topographic wetness index (ln(a/S) output file.\n");
+  printf("The following are appended to the file names\n");
+  printf("before the files are opened:\n");
+  printf("sca    D-infinity specific catchment area grid (input)\n");
+  printf("slp     D-infinity slope grid (input)\n");
+  printf("twi    output topographic wetness index grid grid\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char slp[MAXLN], sca[MAXLN], twi[MAXLN];
+  Opt opts[] = {{"-sca", 0, sca, NULL, 0}, {"-slp", 0, slp, NULL, 0}, {"-twi", 0, twi, NULL, 0}};
+  parse(argc, argv, opts, 3);
+  if (argc == 2) { td_nameadd(sca, argv[1], "sca"); td_nameadd(slp, argv[1], "slp"); td_nameadd(twi, argv[1], "twi"); }
+  int err = td_twigrid(slp, sca, twi);
+  if (err != 0) printf("TWI error %d\n", err);
   return 0;
 }
 #else

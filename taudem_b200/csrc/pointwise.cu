@@ -1,0 +1,61 @@
+// Point-wise consumers of the contributing-area rasters:
+//   threshold  src = (ssa >= thresh [& mask >= 0]) ? 1 : 0, nodata where ssa is nodata   (src/Threshold.cpp:109-131)
+//   twi        twi = ln(sca / slp) where both are data and positive, else nodata (-1)     (src/TWI.cpp:108-124)
+// One streaming kernel each, four cells per thread (16-byte loads, 8 / 16-byte stores): 6 B (10 with a mask) and 12 B of HBM
+// traffic per cell.  Device-strip level entry points take strips like every other kernel of the path; the host-grid level
+// copies dense arrays in and out.  isNodata is linearpart's |v - nodata| < 1e-5 (src/linearpart.h:471-483).
+#include "common.cuh"
+#include "ctx.h"
+#include "kernels.h"
+
+namespace td {
+namespace {
+__global__ void __launch_bounds__(256) k_threshold(const float* __restrict__ ssa, const float* __restrict__ mask, short* __restrict__ src, Strip s,
+                                                   float thresh, float ssa_nodata) {
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;      // rows on grid.x
+  if (c >= s.pitch) return;
+  const long long o = s.idx(r, c);
+  const float4 v = *reinterpret_cast<const float4*>(ssa + o);
+  float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mask) m = *reinterpret_cast<const float4*>(mask + o);
+  const float a[4] = {v.x, v.y, v.z, v.w}, mm[4] = {m.x, m.y, m.z, m.w};
+  short out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = nd_f(a[i], ssa_nodata) ? TD_MISSINGSHORT : (short)((a[i] >= thresh) & (mm[i] >= 0.f) ? 1 : 0);
+  *reinterpret_cast<short4*>(src + o) = make_short4(out[0], out[1], out[2], out[3]);
+}
+
+// ln of a float quotient: the reference's log(float) is glibc's logf (< 1 ulp); here the double logarithm rounded to float
+// (correctly rounded in all but ~1e-9 of the cases) — the two can differ in the last bit (tests: <= 1 ulp).
+__global__ void __launch_bounds__(256) k_twi(const float* __restrict__ slp, const float* __restrict__ sca, float* __restrict__ twi, Strip s,
+                                             float slp_nodata, float sca_nodata) {
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;
+  if (c >= s.pitch) return;
+  const long long o = s.idx(r, c);
+  const float4 sv = *reinterpret_cast<const float4*>(slp + o), av = *reinterpret_cast<const float4*>(sca + o);
+  const float sl[4] = {sv.x, sv.y, sv.z, sv.w}, ar[4] = {av.x, av.y, av.z, av.w};
+  float out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool ok = !nd_f(ar[i], sca_nodata) && !nd_f(sl[i], slp_nodata) && sl[i] > 0.0f && ar[i] > 0.0f;
+    out[i] = ok ? (float)log((double)(ar[i] / sl[i])) : -1.0f;
+  }
+  *reinterpret_cast<float4*>(twi + o) = make_float4(out[0], out[1], out[2], out[3]);
+}
+}  // namespace
+
+int launch_threshold(const float* ssa, const float* mask, short* src, const Strip& s, float thresh, float ssa_nodata, cudaStream_t st) {
+  const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
+  k_threshold<<<grid, 256, 0, st>>>(ssa, mask, src, s, thresh, ssa_nodata);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+int launch_twi(const float* slp, const float* sca, float* twi, const Strip& s, float slp_nodata, float sca_nodata, cudaStream_t st) {
+  const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
+  k_twi<<<grid, 256, 0, st>>>(slp, sca, twi, s, slp_nodata, sca_nodata);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+}  // namespace td

@@ -380,4 +380,69 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
   return TD_ERR_IO;
 }
 
+
+// src/Threshold.cpp:48-162
+int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile, float thresh, int usemask) try {
+  printf("Threshold version %s\n", td_version());
+  const double t0 = now();
+  Input a;
+  if (int rc = a.open(ssafile)) return rc;
+  std::vector<float> ssa;
+  nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
+  if (int rc = a.read(&ssa, tdio::DT_F32)) return rc;
+  Input m; std::vector<float> mask;
+  if (usemask == 1) {
+    if (int rc = m.open(maskfile)) return rc;
+    if (!tdio::compare_rasters(a.r, a.path, m.r, m.path)) { td::set_error("mask grid does not match"); return TD_ERR_ARG; }   // src/Threshold.cpp:89
+    nodata_msgs(m.r.nodata(), "float", (float)m.r.nodata());
+    if (int rc = m.read(&mask, tdio::DT_F32)) return rc;
+  }
+  const double t1 = now();
+  std::vector<int16_t> src((size_t)a.nx * a.ny);
+  if (int rc = td_threshold_host(ssa.data(), usemask == 1 ? mask.data() : nullptr, src.data(), a.nx, a.ny, thresh, (float)a.r.nodata())) {
+    printf("Threshold device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(srcfile, a, tdio::DT_I16, (double)(int16_t)-32768, src)) return rc;
+  const double t3 = now();
+  printf("Compute time: %f\n", t2 - t1);
+  printf("Read time: %f\nWrite time: %f\nTotal time: %f\nDevice compute time: %f\n", t1 - t0, t3 - t2, t3 - t0, td_last_compute_seconds());
+  return TD_OK;
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
+// src/TWI.cpp:47-155
+int td_twigrid(const char* slopefile, const char* areafile, const char* twifile) try {
+  printf("Topographic Wetness Index version %s\n", td_version());
+  const double t0 = now();
+  Input sl;
+  if (int rc = sl.open(slopefile)) return rc;
+  std::vector<float> slp;
+  nodata_msgs(sl.r.nodata(), "float", (float)sl.r.nodata());
+  if (int rc = sl.read(&slp, tdio::DT_F32)) return rc;
+  Input ar; std::vector<float> sca;
+  if (int rc = ar.open(areafile)) return rc;
+  if (!tdio::compare_rasters(sl.r, sl.path, ar.r, ar.path)) { td::set_error("area grid does not match"); return TD_ERR_ARG; }   // src/TWI.cpp:88
+  nodata_msgs(ar.r.nodata(), "float", (float)ar.r.nodata());
+  if (int rc = ar.read(&sca, tdio::DT_F32)) return rc;
+  const double t1 = now();
+  std::vector<float> twi((size_t)sl.nx * sl.ny);
+  if (int rc = td_twi_host(slp.data(), sca.data(), twi.data(), sl.nx, sl.ny, (float)sl.r.nodata(), (float)ar.r.nodata())) {
+    printf("TWI device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(twifile, sl, tdio::DT_F32, (double)-1.0f, twi)) return rc;
+  const double t3 = now();
+  printf("Compute time: %f\n", t2 - t1);
+  printf("Read time: %f\nWrite time: %f\nTotal time: %f\nDevice compute time: %f\n", t1 - t0, t3 - t2, t3 - t0, td_last_compute_seconds());
+  return TD_OK;
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
 }  // extern "C"

@@ -288,6 +288,41 @@ def test_overlapped_two_tool_call_equals_the_two_calls():
     assert_bits(sca, td.areadinf_grid(ang, dx=25.0, dy=35.0, contcheck=False), "sca -nc (overlapped call)")
 
 
+def test_pointwise_consumers_threshold_and_twi(refrun, tmp_path):
+    """threshold and twi on the rasters of the path: grid level and our executables against the
+    reference executables (oracle/_ref/threshold, oracle/_ref/twi: Threshold.cpp / TWI.cpp compiled unchanged).  src is
+    bit-exact; twi = ln(sca / slp) may differ from glibc's logf in the last bit (<= 1 ulp), with identical nodata masks."""
+    import os
+    import subprocess
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "twi"), os.X_OK):
+        pytest.skip("oracle/_ref/threshold and twi are not built")
+    dem = synth.punch_holes(synth.gen_dem(300, 380, hurst=0.8, tilt=1.0, seed=31))
+    fel = td.pitremove_grid(dem); p, _ = td.d8flowdir_grid(fel); ang, slp = td.dinfflowdir_grid(fel)
+    ad8 = td.aread8_grid(p); sca = td.areadinf_grid(ang)
+    mask = (synth.gen_weights(*dem.shape) - 0.3).astype(np.float32)          # negative on ~30 % of the cells
+    R = refrun.RefPipeline(workdir=str(tmp_path))
+    assert_bits(td.threshold_grid(ad8, 50.0), R.threshold(ad8, 50.0), "src")
+    assert_bits(td.threshold_grid(ad8, 7.5, mask=mask), R.threshold(ad8, 7.5, mask=mask), "src -mask")
+    twi, ref = td.twi_grid(slp, sca), R.twi(slp, sca)
+    assert np.array_equal(twi == -1.0, ref == -1.0), "twi nodata masks differ"
+    ok = ref != -1.0
+    ulp = np.abs(twi[ok].view(np.int32).astype(np.int64) - ref[ok].view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1, f"twi differs by {ulp.max()} ulp"
+    assert (ulp == 0).mean() > 0.9
+    # executables on the files the reference run left in tmp_path
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "ours_src.tif")
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "threshold"), "-ssa", str(tmp_path / "ssa.tif"), "-src", out, "-thresh", "7.5",
+                        "-mask", str(tmp_path / "mask.tif")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert_bits(td.read_raster(out, np.int16), R.get("src.tif", np.int16), "threshold (files)")
+    out = str(tmp_path / "ours_twi.tif")
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "twi"), "-slp", str(tmp_path / "slpin.tif"), "-sca", str(tmp_path / "scain.tif"), "-twi", out],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert_bits(td.read_raster(out), twi, "twi (files)")
+
+
 def test_dinf_angle_torture():
     """areadinf on angles at and next to every place where prop() changes its mind (sector edges, the 1e-5 share threshold, the
     wrap sector, angles beyond 2 PI), bit for bit against the C restatement (pinned on the reference tools by the CPU suite)."""
