@@ -99,6 +99,13 @@ int td_area_host(const float* ang, const float* w /*NULL unless usew*/, float* s
  * `int threshold(char* ssafile, char* srcfile, char* maskfile, float thresh, int usemask)` (src/Threshold.cpp:48) and
  * `int twigrid(char* slopefile, char* areafile, char* twifile)` (src/TWI.cpp:47); host-grid and device-strip level like
  * the other tools.  src: int16, nodata -32768; twi: float32, nodata -1 (within 1 float ulp of the reference's logf). */
+/* Sibling of aread8 on the same sweep: the largest / smallest value of a grid on the D8 flow paths above
+ * each cell.  File level = `int d8flowpathextremeup(char* pfile, char* safile, char* ssafile, int usemax, char* datasrc, char* lyrname,
+ * int uselyrname, int lyrno, int useOutlets, int contcheck)` (src/D8flowpathextremeup.cpp:58); ssa: float32, nodata -FLT_MAX. */
+int td_d8flowpathextremeup(const char* pfile, const char* safile, const char* ssafile, int usemax, const char* datasrc, const char* lyrname,
+                           int uselyrname, int lyrno, int useOutlets, int contcheck);
+int td_d8flowpathextremeup_host(const int16_t* p, const float* sa, float* ssa, int nx, int ny, int16_t p_nodata, int usemax, int contcheck,
+                                const int* outlet_cols, const int* outlet_rows, int nout /* < 0: no outlets */);
 int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile, float thresh, int usemask);
 int td_twigrid(const char* slopefile, const char* areafile, const char* twifile);
 int td_threshold_host(const float* ssa, const float* mask /*NULL unless usemask*/, int16_t* src, int nx, int ny, float thresh, float ssa_nodata);

@@ -103,6 +103,18 @@ class RefPipeline:
         _, self.times["areadinf"] = run_tool("areadinf", args, self.np_ranks)
         return self.get("sca.tif", np.float32)
 
+    def d8flowpathextremeup(self, p, sa, usemax=True, contcheck=True, outlets=None, nodata=-32768, sa_nodata=-9999.0):
+        self.put("pin.tif", p.astype(np.int16), nodata); self.put("sa.tif", sa, sa_nodata)
+        args = ["-p", self.path("pin.tif"), "-sa", self.path("sa.tif"), "-ssa", self.path("ssa_up.tif")]
+        if outlets is not None:
+            args += ["-o", outlets]
+        if not usemax:
+            args.append("-min")
+        if not contcheck:
+            args.append("-nc")
+        _, self.times["d8flowpathextremeup"] = run_tool("d8flowpathextremeup", args, self.np_ranks)
+        return self.get("ssa_up.tif", np.float32)
+
     def threshold(self, ssa, thresh, mask=None, nodata=-1.0):
         self.put("ssa.tif", ssa, nodata)
         args = ["-ssa", self.path("ssa.tif"), "-src", self.path("src.tif"), "-thresh", repr(float(thresh))]

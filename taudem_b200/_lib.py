@@ -38,6 +38,8 @@ SIGNATURES = {
     "td_setdir": (_I, [_S, _S, _S, _S, _I]),
     "td_aread8": (_I, [_S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
     "td_area": (_I, [_S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
+    "td_d8flowpathextremeup": (_I, [_S, _S, _S, _I, _S, _S, _I, _I, _I, _I]),
+    "td_d8flowpathextremeup_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _I, _I, _P, _P, _I]),
     "td_threshold": (_I, [_S, _S, _S, _F, _I]),
     "td_twigrid": (_I, [_S, _S, _S]),
     "td_threshold_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),

@@ -153,6 +153,18 @@ def aread8_grid(p, nodata=int(MISSINGSHORT), weights=None, w_nodata=-9999.0, con
     return ad8
 
 
+def d8flowpathextremeup_grid(p, sa, usemax=True, nodata=int(MISSINGSHORT), contcheck=True, outlets=None):
+    """The largest (smallest) value of `sa` on the D8 flow paths above each cell (td_d8flowpathextremeup_host;
+    src/D8flowpathextremeup.cpp:182-215).  nodata = -FLT_MAX."""
+    p = _grid(p, np.int16); sa = _grid(sa, np.float32)
+    ny, nx = p.shape
+    assert sa.shape == p.shape
+    ssa = np.empty((ny, nx), np.float32)
+    oc, orow, nout = _outlet_args(outlets)
+    check(lib().td_d8flowpathextremeup_host(_ptr(p), _ptr(sa), _ptr(ssa), nx, ny, int(nodata), int(usemax), int(contcheck), _ptr(oc), _ptr(orow), nout))
+    return ssa
+
+
 def threshold_grid(ssa, thresh=100.0, mask=None, nodata=-1.0):
     """src = (ssa >= thresh [& mask >= 0]) ? 1 : 0, -32768 where ssa is nodata (td_threshold_host; src/Threshold.cpp:109-131)."""
     ssa = _grid(ssa, np.float32)

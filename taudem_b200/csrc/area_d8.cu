@@ -62,7 +62,7 @@ __device__ __forceinline__ unsigned eq_bytes(unsigned w, unsigned t) { return ~(
 // (src/commonLib.cpp:262-264; code 0 counts for k = 4 exactly as the reference's "tempShort - k == -4" does).
 __global__ void __launch_bounds__(256) k_deps_d8(const short* __restrict__ p, unsigned short* __restrict__ node,
                                                  unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,
-                                                 short nodata) {
+                                                 short nodata, float area_init) {
   using G = TileGeom<short, TW, TH>;
   constexpr int QW = TW / 4 + 2;                       // words per row of q: columns c0-4 .. c0+TW+3
   __shared__ __align__(128) short tile[G::ELEMS];
@@ -147,16 +147,16 @@ __global__ void __launch_bounds__(256) k_deps_d8(const short* __restrict__ p, un
     *reinterpret_cast<ushort4*>(node + o) = make_ushort4(on4[0], on4[1], on4[2], on4[3]);
     *reinterpret_cast<uchar4*>(cnt + o) = make_uchar4(oc4[0], oc4[1], oc4[2], oc4[3]);
     // the area partition starts as nodata (-1) everywhere (src/aread8.cpp:193)
-    *reinterpret_cast<float4*>(area + o) = make_float4(-1.f, -1.f, -1.f, -1.f);
+    *reinterpret_cast<float4*>(area + o) = make_float4(area_init, area_init, area_init, area_init);
   }
 }
 
 }  // namespace
 
 cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s, short nodata,
-                           cudaStream_t st) {
+                           cudaStream_t st, float area_init) {
   dim3 grid((s.pitch + TW - 1) / TW, (s.ny + TH - 1) / TH);
-  k_deps_d8<<<grid, 256, 0, st>>>(p, node, cnt, area, s, nodata);
+  k_deps_d8<<<grid, 256, 0, st>>>(p, node, cnt, area, s, nodata, area_init);
   TD_LAUNCHED();
   return cudaGetLastError();
 }

@@ -469,6 +469,33 @@ int td_aread8_outlets_host(const int16_t* p, const float* w, float* ad8, int nx,
   return TD_OK;
 }
 
+// ---- d8flowpathextremeup (src/D8flowpathextremeup.cpp:58-285): the D8 dependency stencil and sweep with the extreme-value
+// algebra — each cell gets the largest (usemax) / smallest value of `sa` on the flow paths that end in it; nodata = MISSINGFLOAT.
+int td_d8flowpathextremeup_host(const int16_t* p, const float* sa, float* ssa, int nx, int ny, int16_t p_nodata, int usemax, int contcheck,
+                                const int* outlet_cols, const int* outlet_rows, int nout) {
+  if (int rc = need_device()) return rc;
+  if (!p || !sa || !ssa || nx <= 0 || ny <= 0) { td::set_error("td_d8flowpathextremeup_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 2)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[2].ensure(n * 4));
+  int16_t* d_p = ctx->io[0].as<int16_t>(); float* d_a = ctx->io[1].as<float>(); float* d_sa = ctx->io[2].as<float>();
+  TD_CUDA(h2d(d_p, p, s, st));
+  TD_CUDA(h2d(d_sa, sa, s, st));
+  Timer t; t.start(st);
+  if (int rc = ensure_dep_state(ctx, Strip(s), st)) return rc;
+  ctx->sweep_dinf = 0;
+  TD_CUDA(td::launch_deps_d8(d_p, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), d_a, Strip(s), p_nodata, st, TD_MISSINGFLOAT));
+  if (nout >= 0) { if (int rc = td_sweep_restrict_dev(ctx, s, outlet_cols, outlet_rows, nout, st)) return rc; }
+  if (int rc = td::wsweep_begin(ctx, Strip(s), st)) return rc;
+  if (int rc = td::wsweep_run(ctx, false, d_a, d_sa, nullptr, Strip(s), 0.f, 1, contcheck, nullptr, nullptr, ctx->halo.as<int>(), st, usemax ? 1 : 2)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(ssa, d_a, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
 // ---- point-wise consumers (pointwise.cu): device-strip and host-grid level
 int td_threshold_dev(td_ctx*, const float* ssa, const float* mask, int16_t* src, td_strip s, float thresh, float ssa_nodata, void* stream) {
   if (int rc = check_strip(s)) return rc;

@@ -165,6 +165,33 @@ int main(int argc, char** argv) {
   if (err != 0) printf("area error %d\n", err);
   return 0;
 }
+#elif defined(TOOL_d8flowpathextremeup)
+// src/D8FlowPathExtremeUpmn.cpp:57-174
+static void usage(const char* prog) {
+  printf("Simple Use:\n %s <basefilename>\n", prog);
+  printf("Use with specific file names:\n %s -p <pfile>\n", prog);
+  printf("-sa <safile> -ssa <ssafile> [-min] [-nc] [-o <outletsfile>]\n");
+  printf("<basefilename> is the name of the base digital elevation model without suffixes for simple input. Suffixes 'p', 'sa' and 'ssa' will be appended. \n");
+  printf("<pfile> is the name of D8 flow directions file.\n");
+  printf("<safile> is the name of input file with values from which extreme upslope is to be found.\n");
+  printf("<ssa> is the name of the output file with extreme upslope values.\n");
+  printf("-min indicates to search for a minimum (default is max)\n");
+  printf("-nc indicates to override edge contamination checking (checking is on by default)\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char pf[MAXLN], sa[MAXLN], ssa[MAXLN], datasrc[MAXLN], lyrname[MAXLN];
+  int useOutlets = 0, uselyrname = 0, usemax = 1, contcheck = 1, lyrno = 0;
+  if (argc < 2) usage(argv[0]);
+  Opt opts[] = {{"-p", 0, pf, NULL, 0}, {"-sa", 0, sa, NULL, 0}, {"-ssa", 0, ssa, NULL, 0}, {"-o", 0, datasrc, &useOutlets, 1},
+                {"-lyrno", 2, NULL, &lyrno, 0}, {"-lyrname", 0, lyrname, &uselyrname, 1}, {"-min", 1, NULL, &usemax, 0}, {"-nc", 1, NULL, &contcheck, 0}};
+  parse(argc, argv, opts, 8);
+  if (argc == 2) { td_nameadd(pf, argv[1], "p"); td_nameadd(sa, argv[1], "sa"); td_nameadd(ssa, argv[1], "ssa"); }
+  int err = td_d8flowpathextremeup(pf, sa, ssa, usemax, datasrc, lyrname, uselyrname, lyrno, useOutlets, contcheck);
+  if (err != 0) printf("Flow Path Extreme Up Error %d\n", err);
+  return 0;
+}
+
 #elif defined(TOOL_threshold)
 // src/Thresholdmn.cpp:50-130 (its usage text names the flags wrongly; the flags themselves are -ssa -src -thresh -mask)
 static void usage(const char* prog) {

@@ -347,7 +347,9 @@ __device__ __forceinline__ unsigned zero_nibble(unsigned w) {
   return ((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u);
 }
 
-template <bool DINF, bool USEW>
+// ALG (D8 with a value grid in `w` only): 0 = sum (aread8, src/aread8.cpp:228-257), 1 / 2 = the largest / smallest value of `w` on the
+// flow paths above each cell (d8flowpathextremeup, src/D8flowpathextremeup.cpp:182-215; results nodata = MISSINGFLOAT)
+template <bool DINF, bool USEW, int ALG>
 __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(const WArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   using Mem = WarpMem<DINF>;
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
   const unsigned lt = (1u << lane) - 1u;
   Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
   const int myq = (int)((blockIdx.x * (blockDim.x >> 5) + (unsigned)wid) & (unsigned)(a.nsh - 1));   // this worker's queue shard
+  const float NOD = ALG == 0 ? -1.0f : TD_MISSINGFLOAT;      // the result raster's nodata: not evaluated / contaminated
   __shared__ Sector sect[9];
   if (DINF) {
     if (threadIdx.x < 9) { const int j = (int)threadIdx.x; sect[j].lo = a.prop.ar[j]; sect[j].hi = a.prop.ar[j + 1]; sect[j].den = a.prop.den[j]; sect[j].rden = a.prop.rden[j]; }
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           if (DINF) cp16(M.ang + so, a.ang + g);
           cp8(M.node + so, a.node + g);
         } else {
-          *reinterpret_cast<float4*>(M.area + so) = make_float4(-1.f, -1.f, -1.f, -1.f);
+          *reinterpret_cast<float4*>(M.area + so) = make_float4(NOD, NOD, NOD, NOD);
           if (DINF) *reinterpret_cast<float4*>(M.ang + so) = make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<uint2*>(M.node + so) = make_uint2(0u, 0u);
         }
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
       const int sw = rr * RS + 3, se = rr * RS + RS;
       const bool west = rowok && c0 > 0, east = rowok && c0 + TS < s.pitch;
       const long long gw_ = s.idx(r, c0 - 1), ge_ = s.idx(r, c0 + TS);
-      float aw = -1.f, ae = -1.f;
+      float aw = NOD, ae = NOD;
       if (west) { aw = __ldcg(halo_row ? hrow + (c0 - 1) : a.area + gw_); if (DINF) cp4(M.ang + sw, a.ang + gw_); cp4(M.node + sw - 1, a.node + gw_ - 1); }
       else { M.node[sw - 1] = 0; M.node[sw] = 0; }
       if (east) { ae = __ldcg(halo_row ? hrow + (c0 + TS) : a.area + ge_); if (DINF) cp4(M.ang + se, a.ang + ge_); cp4(M.node + se, a.node + ge_); }
@@ -477,12 +480,13 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           float val;
           if (!DINF) {
             if (USEW) {
-              val = nd_f(wv, a.w_nodata) ? -1.0f : wv;
+              val = (ALG == 0 && nd_f(wv, a.w_nodata)) ? -1.0f : wv;
 #pragma unroll
               for (int k = 1; k <= 8; ++k)
                 if (msk & (1u << (k - 1))) {
                   const float an = M.area[ri + drow(k) * RS + dcol(k)];
-                  if (nd_f(an, -1.0f)) con = true; else val = val + an;
+                  if (nd_f(an, NOD)) con = true;
+                  else val = ALG == 0 ? val + an : ALG == 1 ? (an > val ? an : val) : (an < val ? an : val);
                 }
             } else {
               val = 1.0f;
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
             if (USEW) val = val + wv;
             else val = (float)((double)val + (a.prop.uniform ? a.dx0 : a.dxc[min(r0 + lr, s.ny) - 1]));
           }
-          if (con && a.contcheck) val = -1.0f;
+          if (con && a.contcheck) val = NOD;
           if (lane == 0) { M.area[ri] = val; M.evmask[lr] |= 1u << lx; }
           int next = -1;
 #pragma unroll
@@ -589,12 +593,13 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
         if (!DINF) {
           // src/aread8.cpp:228-257
           if (USEW) {
-            val = nd_f(wv, a.w_nodata) ? -1.0f : wv;
+            val = (ALG == 0 && nd_f(wv, a.w_nodata)) ? -1.0f : wv;
 #pragma unroll
             for (int k = 1; k <= 8; ++k)
               if (msk & (1u << (k - 1))) {
                 const float an = M.area[ri + drow(k) * RS + dcol(k)];
-                if (nd_f(an, -1.0f)) con = true; else val = val + an;
+                if (nd_f(an, NOD)) con = true;
+                else val = ALG == 0 ? val + an : ALG == 1 ? (an > val ? an : val) : (an < val ? an : val);
               }
           } else {
             // no weights: an area is -1 (nodata: contaminated) or a positive count, and a contaminated contributor
@@ -646,7 +651,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           if (USEW) val = val + wv;
           else val = (float)((double)val + (a.prop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]));
         }
-        if (con && a.contcheck) val = -1.0f;
+        if (con && a.contcheck) val = NOD;
         M.area[ri] = val;
         atomicOr(&M.evmask[lr], 1u << lx);
         // (the areas are in shared memory before the counts that announce them are read: every lane that continues with a
@@ -846,7 +851,8 @@ int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int
 
 // Runs the evaluation wavefront over the queued tiles until no tile of the strip has a ready cell left.
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
-               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st) {
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg) {
+  if (alg != 0 && (dinf || !usew || alg < 0 || alg > 2)) { set_error("wsweep_run: the extreme-value algebra is a D8 sweep over a value grid"); return TD_ERR_ARG; }
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
@@ -875,9 +881,10 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   if (const char* we = getenv("TAUDEM_B200_WORKERS")) { const int v = atoi(we); if (v >= 1 && v < warps) warps = v; }   // experiments: fewer workers per SM
   size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
   if (const char* pe2 = getenv("TAUDEM_B200_SMEMPAD")) smem = std::max(smem, (size_t)atoi(pe2));                  // experiments: one CTA per SM whatever its size
-  const void* kern = dinf ? (usew ? (const void*)k_sweep_warp<true, true> : (const void*)k_sweep_warp<true, false>)
-                          : (usew ? (const void*)k_sweep_warp<false, true> : (const void*)k_sweep_warp<false, false>);
-  int& per_dev = ctx->wgrid[(dinf ? 2 : 0) + (usew ? 1 : 0)];
+  const void* kern = dinf ? (usew ? (const void*)k_sweep_warp<true, true, 0> : (const void*)k_sweep_warp<true, false, 0>)
+                          : alg == 1 ? (const void*)k_sweep_warp<false, true, 1> : alg == 2 ? (const void*)k_sweep_warp<false, true, 2>
+                          : (usew ? (const void*)k_sweep_warp<false, true, 0> : (const void*)k_sweep_warp<false, false, 0>);
+  int& per_dev = ctx->wgrid[alg ? 3 + alg : (dinf ? 2 : 0) + (usew ? 1 : 0)];
   if (!per_dev || getenv("TAUDEM_B200_WORKERS")) {
     int dev = 0, sms = 0, occ = 0;
     TD_CUDA(cudaGetDevice(&dev));
@@ -889,8 +896,10 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   }
   const long long nt = (long long)a.ntx * a.nty;
   const int g = (int)std::min<long long>(per_dev, (nt + warps - 1) / warps);
-  if (dinf) { if (usew) k_sweep_warp<true, true><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false><<<g, warps * 32, smem, st>>>(a); }
-  else { if (usew) k_sweep_warp<false, true><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<false, false><<<g, warps * 32, smem, st>>>(a); }
+  if (dinf) { if (usew) k_sweep_warp<true, true, 0><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 0><<<g, warps * 32, smem, st>>>(a); }
+  else if (alg == 1) k_sweep_warp<false, true, 1><<<g, warps * 32, smem, st>>>(a);
+  else if (alg == 2) k_sweep_warp<false, true, 2><<<g, warps * 32, smem, st>>>(a);
+  else { if (usew) k_sweep_warp<false, true, 0><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<false, false, 0><<<g, warps * 32, smem, st>>>(a); }
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;

@@ -381,6 +381,41 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
 }
 
 
+// src/D8flowpathextremeup.cpp:58-285
+int td_d8flowpathextremeup(const char* pfile, const char* safile, const char* ssafile, int usemax, const char* datasrc, const char* lyrname,
+                           int uselyrname, int lyrno, int useOutlets, int contcheck) try {
+  printf("D8FlowPathExtremeUp version %s\n", td_version());
+  const double t0 = now();
+  Input p;
+  if (int rc = p.open(pfile)) return rc;
+  std::vector<int> ocols, orows;
+  if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, p, &ocols, &orows)) return rc; }
+  std::vector<int16_t> dir;
+  nodata_msgs(p.r.nodata(), "int16_t", (int16_t)p.r.nodata());
+  if (int rc = p.read(&dir, tdio::DT_I16)) return rc;
+  Input a; std::vector<float> sa;
+  if (int rc = a.open(safile)) return rc;
+  if (!tdio::compare_rasters(p.r, p.path, a.r, a.path)) { printf("File sizes do not match\n%s\n", safile); td::set_error("value grid does not match"); return TD_ERR_MISMATCH; }
+  nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
+  if (int rc = a.read(&sa, tdio::DT_F32)) return rc;
+  const double t1 = now();
+  std::vector<float> ssa((size_t)p.nx * p.ny);
+  if (int rc = td_d8flowpathextremeup_host(dir.data(), sa.data(), ssa.data(), p.nx, p.ny, (int16_t)p.r.nodata(), usemax, contcheck, ocols.data(),
+                                           orows.data(), useOutlets == 1 ? (int)ocols.size() : -1)) {
+    printf("D8FlowPathExtremeUp device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(ssafile, p, tdio::DT_F32, (double)-3.4028234663852886e38f, ssa)) return rc;
+  const double t3 = now();
+  printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
 // src/Threshold.cpp:48-162
 int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile, float thresh, int usemask) try {
   printf("Threshold version %s\n", td_version());

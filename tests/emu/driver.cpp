@@ -158,6 +158,10 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
     for (int i = 0; i < nstrips; ++i)
       if (int rc = td::sweep_restrict_round(&S[i].ctx, S[i].s, nullptr, nullptr, -1, nullptr, nullptr, req[i].data(), 1, nullptr)) return rc;
   }
+  // mode 10 / 11: the extreme-value algebra of d8flowpathextremeup (largest / smallest value of the `wgt` grid on the flow paths above a cell;
+  // single strip: the exchange of halo areas with the -FLT_MAX nodata is the row-strip driver's business)
+  const int alg = mode == 10 ? 1 : mode == 11 ? 2 : 0;
+  if (alg) for (auto& T : S) std::fill(T.area.begin(), T.area.end(), -3.4028234663852886e38f);
   bool first = true;
   int rounds = 0;
   for (auto& T : S) { td::make_prop_row(T.theta[0], true, &T.ctx.prop); T.ctx.dx0 = dx; }
@@ -167,7 +171,7 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
       int rc = first ? td::wsweep_begin(&T.ctx, T.s, nullptr) : 0;
       if (!rc)
         rc = td::wsweep_run(&T.ctx, dinf != 0, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew, contcheck,
-                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr);
+                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr, alg);
       if (rc) return rc;
     }
     first = false;

@@ -65,7 +65,7 @@ extern "C" int emu_deps_d8(const short* p, unsigned short* node, unsigned char* 
   Grid g(nx, ny, 30., 30.);
   auto d = g.in(p);
   std::vector<unsigned short> nd((size_t)g.s.cells(), 0); std::vector<unsigned char> cn((size_t)g.s.cells() + 4, 0); std::vector<float> ar((size_t)g.s.cells(), 0.f);
-  td::launch_deps_d8(d.data(), nd.data(), cn.data(), ar.data(), g.s, nodata, nullptr);
+  td::launch_deps_d8(d.data(), nd.data(), cn.data(), ar.data(), g.s, nodata, nullptr, -1.0f);
   g.out(nd, node); g.out(cn, cnt); g.out(ar, area);
   return 0;
 }

@@ -131,6 +131,19 @@ def test_emulated_dinf_angle_torture(emu):
         assert_bits(_run(emu, True, 0, 0, ang, None, False, 22, 3, dx=dx, dy=dy), port.areadinf(ang, dx=dx, dy=dy, contcheck=False), f"sca angle torture -nc, 3 strips {dx}x{dy}")
 
 
+def test_emulated_d8_flow_path_extreme_up(emu, fields):
+    """d8flowpathextremeup = the D8 sweep with the extreme-value algebra, against the reference executable
+    (oracle/_ref/d8flowpathextremeup: D8flowpathextremeup.cpp compiled unchanged)."""
+    import refrun
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "d8flowpathextremeup"), os.X_OK):
+        pytest.skip("oracle/_ref/d8flowpathextremeup is not built")
+    port, p, _, w = fields
+    sa = (w * 100.0 - 20.0).astype(np.float32)
+    R = refrun.RefPipeline()
+    assert_bits(_run(emu, False, 10, 0, p, sa, True, 31), R.d8flowpathextremeup(p, sa, usemax=True), "ssa max")
+    assert_bits(_run(emu, False, 11, 0, p, sa, False, 32), R.d8flowpathextremeup(p, sa, usemax=False, contcheck=False), "ssa min -nc")
+
+
 def test_emulated_small_stacks_spill(fields):
     """A two-entry fork stack drops nearly every second receiver (the rescan of the shared-memory counts must find them);
     the outlet flood with a four-entry stack per warp spills nearly every discovered contributor to the host-drained list."""

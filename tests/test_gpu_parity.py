@@ -288,6 +288,37 @@ def test_overlapped_two_tool_call_equals_the_two_calls():
     assert_bits(sca, td.areadinf_grid(ang, dx=25.0, dy=35.0, contcheck=False), "sca -nc (overlapped call)")
 
 
+def test_d8_flow_path_extreme_up(refrun, tmp_path):
+    """d8flowpathextremeup (a sibling of aread8 on the same sweep) against the reference executable
+    (oracle/_ref/d8flowpathextremeup): max, min, -nc, outlets; grid level and our executable, bit for bit."""
+    import os
+    import subprocess
+    from util import write_point_shapefile
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "d8flowpathextremeup"), os.X_OK):
+        pytest.skip("oracle/_ref/d8flowpathextremeup is not built")
+    dem = synth.punch_holes(synth.gen_dem(330, 410, hurst=0.8, tilt=1.0, seed=41))
+    fel = td.pitremove_grid(dem); p, sd8 = td.d8flowdir_grid(fel)
+    sa = np.where(sd8 < 0, np.float32(0.0), sd8).astype(np.float32)           # "largest slope upstream"
+    R = refrun.RefPipeline(workdir=str(tmp_path))
+    assert_bits(td.d8flowpathextremeup_grid(p, sa), R.d8flowpathextremeup(p, sa), "ssa max")
+    assert_bits(td.d8flowpathextremeup_grid(p, fel, usemax=False, contcheck=False), R.d8flowpathextremeup(p, fel, usemax=False, contcheck=False), "ssa min -nc")
+    ny, nx = p.shape
+    order = np.argsort(td.aread8_grid(p, contcheck=False).ravel())
+    cells = [int(order[-1]), int(order[-40]), int(order[-700])]
+    cols = [c % nx for c in cells]; rows = [c // nx for c in cells]
+    dx = dy = 30.0
+    shp = str(tmp_path / "outlets.shp")
+    write_point_shapefile(shp, [(c + 0.5) * dx for c in cols], [dy * ny - (r + 0.5) * dy for r in rows])
+    ref = R.d8flowpathextremeup(p, sa, outlets=shp)
+    assert_bits(td.d8flowpathextremeup_grid(p, sa, outlets=(cols, rows)), ref, "ssa max -o")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "ours_ssa.tif")
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "d8flowpathextremeup"), "-p", str(tmp_path / "pin.tif"), "-sa", str(tmp_path / "sa.tif"),
+                        "-ssa", out, "-o", shp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert_bits(td.read_raster(out), ref, "d8flowpathextremeup -o (files)")
+
+
 def test_pointwise_consumers_threshold_and_twi(refrun, tmp_path):
     """threshold and twi on the rasters of the path: grid level and our executables against the
     reference executables (oracle/_ref/threshold, oracle/_ref/twi: Threshold.cpp / TWI.cpp compiled unchanged).  src is
