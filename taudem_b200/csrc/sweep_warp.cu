@@ -31,12 +31,13 @@
 namespace td {
 namespace {
 
-constexpr int TS = 32;                                // tile edge (cells)
-constexpr int TC = TS * TS;                           // cells per tile
-constexpr int RH = TS + 2;                            // ring rows
+constexpr int TS = 32;                                // tile width (cells) = lanes of a warp
+// tile height (a multiple of 32: RPL = height / 32 rows per lane).  64-row D8 tiles (13 workers per SM instead of 26) were
+// measured: 330 ms instead of 288 ms at 65536^2 with identical results — the second set of warps hides more latency than the
+// taller tile saves instructions.
+template <bool DINF> constexpr int tile_h() { return 32; }
 constexpr int RS = TS + 4;                            // ring row stride: cell lx of a tile row at lx + 4, its west neighbour at 3, its east neighbour at
                                                       // 36 = slot 0 of the next row (slots 0..2 of a row are otherwise unused): rows stay 16-byte aligned
-constexpr int RN = RH * RS + 4;                       // ring array length (the east neighbour of the last ring row lives at RH * RS)
 #ifndef TD_WSTK
 #define TD_WSTK 128
 #endif
@@ -66,17 +67,21 @@ __device__ __forceinline__ int lut_dcol(int k) { return (int)((DCOL_LUT >> (2 * 
 // one worker's shared memory: everything a visit touches while it runs the wavefront
 template <bool DINF>
 struct __align__(16) WarpMem {
+  static constexpr int TH = tile_h<DINF>();      // tile rows
+  static constexpr int RH = TH + 2;              // ring rows
+  static constexpr int RN = RH * RS + 4;         // ring array length (the east neighbour of the last ring row lives at RH * RS)
+  static constexpr int TC = TS * TH;             // cells per tile
   float area[RN];                         // areas of the tile and its ring (-1 = nodata / not final)
   float ang[DINF ? RN : 4];               // D-infinity: angles of the same cells
   unsigned short node[RN];                // node words of the same cells
   alignas(16) unsigned cnt[TC / 4];       // dependency counts, four cells per word: 0..8 (0 = ready or evaluated by this visit), 0xFE = evaluated
                                           // by an earlier visit, 0xFF = not a node
   unsigned short stk[DINF ? STKCAP : 2];  // D-infinity: second receivers that became ready (what does not fit is found again by a rescan of the counts)
-  unsigned short ext[DINF ? 256 : 128];   // flow that leaves the tile: source cell | (direction - 1) << 10  (<= 124 perimeter cells x receivers)
-  unsigned evmask[TS];                    // per tile row: cells evaluated by this visit
+  unsigned short ext[DINF ? 256 : (TH > 32 ? 192 : 128)];   // flow that leaves the tile: source cell | (direction - 1) << 11  (<= 124 / 188 perimeter cells x receivers)
+  unsigned evmask[TH];                    // per tile row: cells evaluated by this visit
   int sp, next, dirty, pad;
 };
-template <bool DINF> constexpr int workers_per_cta() { return DINF ? 16 : 26; }
+template <bool DINF> constexpr int workers_per_cta() { return DINF ? 16 : (tile_h<false>() > 32 ? 13 : 26); }
 static_assert(sizeof(WarpMem<false>) * workers_per_cta<false>() <= 227 * 1024 && sizeof(WarpMem<true>) * workers_per_cta<true>() + 1024 <= 227 * 1024,
               "the workers of a CTA must fit the shared memory of an SM");
 static_assert(offsetof(WarpMem<true>, ang) % 16 == 0 && offsetof(WarpMem<true>, node) % 8 == 0 && offsetof(WarpMem<false>, node) % 8 == 0, "cp.async alignment");
@@ -99,7 +104,7 @@ struct WArgs {
   const double* theta;
   const double* dxc;
   int* halo;
-  int ntx, nty;
+  int ntx, nty, th;        // tiles of the strip, tile height
   int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;          // slots of one shard's ring - 1
@@ -211,7 +216,7 @@ __device__ void deliver_peer(const WArgs& a, bool up, int c_src, float val, int 
   const long long ci = (long long)r * pitch + c_dst;
   const unsigned sh = (unsigned)(ci & 3) * 8u;
   const unsigned old = atomicAdd_system(P.cntw + (ci >> 2), 0u - (1u << sh));
-  if (((old >> sh) & 0xffu) == 1u) sched_activate_peer(a, P, ((r - 1) / TS) * P.ntx + c_dst / TS);
+  if (((old >> sh) & 0xffu) == 1u) sched_activate_peer(a, P, ((r - 1) / a.th) * P.ntx + c_dst / TS);
 }
 // relaxed gpu-scope load of a scheduler word (a volatile load is a system-scope load: far more expensive to poll with)
 __device__ __forceinline__ int ld_relaxed(const int* p) {
@@ -353,6 +358,7 @@ template <bool DINF, bool USEW, int ALG>
 __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(const WArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
   using Mem = WarpMem<DINF>;
+  constexpr int TH = Mem::TH, RH = Mem::RH, RPL = TH / 32;      // tile rows, ring rows, tile rows per lane
   const Strip& s = a.s;
   const int lane = (int)(threadIdx.x & 31u), wid = (int)(threadIdx.x >> 5);
   const unsigned lt = (1u << lane) - 1u;
@@ -372,21 +378,23 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
     t = __shfl_sync(FULL, t, 0);
     if (t < 0) return;
     const int ty = t / a.ntx, tx = t - ty * a.ntx;
-    const int c0 = tx * TS, r0 = 1 + ty * TS;
+    const int c0 = tx * TS, r0 = 1 + ty * TH;
 
     // ---- 1. dependency counts: lane = tile row (32 bytes each), before anything else
-    unsigned g0[8];
-    {
-      const int r = r0 + lane;
+    unsigned g0[8 * RPL];
+#pragma unroll
+    for (int rp = 0; rp < RPL; ++rp) {
+      const int row = lane + 32 * rp, r = r0 + row;
       uint4 qa = make_uint4(FULL, FULL, FULL, FULL), qb = qa;
       if (r <= s.ny) {
         const uint4* src = reinterpret_cast<const uint4*>(a.cntw + (s.idx(r, c0) >> 2));
         qa = __ldcg(src); qb = __ldcg(src + 1);
       }
-      g0[0] = qa.x; g0[1] = qa.y; g0[2] = qa.z; g0[3] = qa.w; g0[4] = qb.x; g0[5] = qb.y; g0[6] = qb.z; g0[7] = qb.w;
-      uint4* dst = reinterpret_cast<uint4*>(M.cnt + lane * 8);
+      unsigned* g = g0 + 8 * rp;
+      g[0] = qa.x; g[1] = qa.y; g[2] = qa.z; g[3] = qa.w; g[4] = qb.x; g[5] = qb.y; g[6] = qb.z; g[7] = qb.w;
+      uint4* dst = reinterpret_cast<uint4*>(M.cnt + row * 8);
       dst[0] = qa; dst[1] = qb;
-      M.evmask[lane] = 0u;
+      M.evmask[row] = 0u;
     }
     if (lane == 0) { M.sp = 0; M.next = 0; M.dirty = 0; }
     if (!(a.exp & 2)) __threadfence();          // the counts first, then the areas they announce (loaded by other lanes: barrier in between)
@@ -433,9 +441,13 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
       M.area[sw] = aw; M.area[se] = ae;
     }
     // ---- 3. cells that are ready (count 0): every lane keeps the ready cells of its own tile row as a bit mask
-    unsigned rdy = 0;
+    unsigned rdy = 0, rdy2 = 0;             // ready cells of this lane's row(s): rdy = row `lane`, rdy2 = row `lane + 32` (tall tiles)
 #pragma unroll
     for (int j = 0; j < 8; ++j) rdy |= zero_nibble(g0[j]) << (4 * j);
+    if (RPL > 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rdy2 |= zero_nibble(g0[(RPL - 1) * 8 + j]) << (4 * j);
+    }
     cp_wait_all();
     __syncwarp();
     if (a.stats && lane == 0) tk2 = clock64();
@@ -446,6 +458,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
     int iters = 0;
     for (;;) {
       if (cur < 0 && rdy) { const int b = __ffs(rdy) - 1; rdy &= rdy - 1; cur = lane * TS + b; }
+      if (RPL > 1 && cur < 0 && rdy2) { const int b = __ffs(rdy2) - 1; rdy2 &= rdy2 - 1; cur = (lane + 32) * TS + b; }
       if (DINF) {
         const unsigned idle = __ballot_sync(FULL, cur < 0);
         if (idle) {
@@ -545,7 +558,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
             else k = j == 0 ? dinf_node_k1(nd) : dinf_node_k2(nd);
             if (k < 1 || k > 8) continue;
             const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
-            if ((unsigned)nlr < (unsigned)TS && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {
+            if ((unsigned)nlr < (unsigned)TH && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {
               const int l2 = nlr * TS + nlx;
               const unsigned sh = (unsigned)(l2 & 3) * 8u;
               unsigned w = 0;
@@ -559,7 +572,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
                 }
               }
             } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
-              if (lane == 0) { M.ext[M.next] = (unsigned short)(c | ((k - 1) << 10)); M.next = M.next + 1; }
+              if (lane == 0) { M.ext[M.next] = (unsigned short)(c | ((k - 1) << 11)); M.next = M.next + 1; }
             }
           }
           c = next;
@@ -664,7 +677,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           else k = j == 0 ? dinf_node_k1(nd) : dinf_node_k2(nd);
           if (k < 1 || k > 8) continue;
           const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
-          if ((unsigned)nlr < (unsigned)TS && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {       // a cell of this tile
+          if ((unsigned)nlr < (unsigned)TH && (unsigned)nlx < (unsigned)TS && r0 + nlr <= s.ny) {       // a cell of this tile
             const int l2 = nlr * TS + nlx;
             const unsigned sh = (unsigned)(l2 & 3) * 8u;
             const unsigned old = atomicSub(&M.cnt[l2 >> 2], 1u << sh);
@@ -673,7 +686,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
               else { const int slot = atomicAdd(&M.sp, 1); if (slot < STKCAP) M.stk[slot] = (unsigned short)l2; }   // a second ready receiver: an idle lane takes it
             }
           } else if (s.on_grid(r0 + nlr, c0 + nlx)) {
-            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)(l | ((k - 1) << 10));
+            M.ext[atomicAdd(&M.next, 1)] = (unsigned short)(l | ((k - 1) << 11));
           }
         }
         cur = cont;
@@ -685,11 +698,15 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
 
     // ---- 5. write back what this visit evaluated (row by row, only rows with evaluated cells), then publish counts and
     //         deliver the crossings
-    const unsigned ev = M.evmask[lane];
-    for (unsigned rows = __ballot_sync(FULL, ev != 0u); rows; rows &= rows - 1u) {
-      const int lr = __ffs(rows) - 1;
-      const unsigned evr = __shfl_sync(FULL, ev, lr);
-      if ((evr >> lane) & 1u) a.area[s.idx(r0 + lr, c0 + lane)] = M.area[(lr + 1) * RS + lane + 4];
+    unsigned evs[RPL];
+#pragma unroll
+    for (int rp = 0; rp < RPL; ++rp) {
+      evs[rp] = M.evmask[lane + 32 * rp];
+      for (unsigned rows = __ballot_sync(FULL, evs[rp] != 0u); rows; rows &= rows - 1u) {
+        const int lr = __ffs(rows) - 1;
+        const unsigned evr = __shfl_sync(FULL, evs[rp], lr);
+        if ((evr >> lane) & 1u) a.area[s.idx(r0 + lr + 32 * rp, c0 + lane)] = M.area[(lr + 32 * rp + 1) * RS + lane + 4];
+      }
     }
     // The counts.  The shared-memory count of a cell this visit evaluated is 0, of any other cell its count at the start
     // minus the arrivals from inside the tile; bytes >= 0x80 (not a node / evaluated before: flow into a cell without a
@@ -698,20 +715,21 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
     // local arrivals.  Words without a cell of the tile's rim (or of the strip's last row, which a neighbour strip feeds)
     // are touched by nobody else while the tile runs: plain stores, before the fence, like the areas.  The others are
     // added atomically after it; a zero byte in the result is a cell that became ready through arrivals from outside meanwhile.
-    const int myr = r0 + lane;
-    const bool rimrow = lane == 0 || lane == TS - 1 || myr >= s.ny;
-    unsigned dl[8];
-    {
+    unsigned dl[8 * RPL];
+#pragma unroll
+    for (int rp = 0; rp < RPL; ++rp) {
+      const int row = lane + 32 * rp, myr = r0 + row;
+      const bool rimrow = row == 0 || row == TH - 1 || myr >= s.ny;
       unsigned* gw = a.cntw + (s.idx(min(myr, s.ny), c0) >> 2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const unsigned was = g0[j];
-        unsigned now = M.cnt[lane * 8 + j];
+        const unsigned was = g0[8 * rp + j];
+        unsigned now = M.cnt[row * 8 + j];
         const unsigned keep = ((was >> 7) & 0x01010101u) * 0xffu;
         now = (now & ~keep) | (was & keep);
-        const unsigned e4 = (ev >> (4 * j)) & 0xfu;
-        dl[j] = now - was + ((e4 * 0x00204081u) & 0x01010101u) * 0xfeu;
-        if (j >= 1 && j <= 6 && !rimrow && dl[j] != 0u) { gw[j] = was + dl[j]; dl[j] = 0u; }
+        const unsigned e4 = (evs[rp] >> (4 * j)) & 0xfu;
+        dl[8 * rp + j] = now - was + ((e4 * 0x00204081u) & 0x01010101u) * 0xfeu;
+        if (j >= 1 && j <= 6 && !rimrow && dl[8 * rp + j] != 0u) { gw[j] = was + dl[8 * rp + j]; dl[8 * rp + j] = 0u; }
       }
     }
     __syncwarp();
@@ -719,7 +737,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
     // flow that leaves the tile first (the neighbours wait for it), then the rim's counts
     const int ne = M.next;
     for (int e = lane; e < ne; e += 32) {
-      const int l = M.ext[e] & 0x3ff, k = (M.ext[e] >> 10) + 1;
+      const int l = M.ext[e] & 0x7ff, k = (M.ext[e] >> 11) + 1;
       const int lr = l >> 5, lx = l & 31;
       const int nlr = lr + lut_drow(k), nlx = lx + lut_dcol(k);
       const int r = r0 + nlr, c = c0 + nlx;
@@ -733,16 +751,19 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
       const long long ci = s.idx(r, c);
       const unsigned sh = (unsigned)(ci & 3) * 8u;
       const unsigned old = W_ADD_IF(a.peer && (r == 1 || r == s.ny), a.cntw + (ci >> 2), 0u - (1u << sh));
-      if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
+      if (((old >> sh) & 0xffu) == 1u) sched_activate(a, ((r - 1) / TH) * a.ntx + c / TS);
     }
-    if (myr <= s.ny) {
+#pragma unroll
+    for (int rp = 0; rp < RPL; ++rp) {
+      const int myr = r0 + lane + 32 * rp;
+      if (myr > s.ny) continue;
       unsigned* gw = a.cntw + (s.idx(myr, c0) >> 2);
       bool dirty = false;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (dl[j] != 0u) {
-          const unsigned old = W_ADD_IF(a.peer && (myr == 1 || myr == s.ny), gw + j, dl[j]);
-          if (zero_bytes(old + dl[j])) dirty = true;
+        if (dl[8 * rp + j] != 0u) {
+          const unsigned old = W_ADD_IF(a.peer && (myr == 1 || myr == s.ny), gw + j, dl[8 * rp + j]);
+          if (zero_bytes(old + dl[8 * rp + j])) dirty = true;
         }
       if (dirty) M.dirty = 1;
     }
@@ -752,7 +773,9 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
       sched_finish(a, t);
     }
     if (a.stats) {
-      const int ncell = __popc(ev);
+      int ncell = 0;
+#pragma unroll
+      for (int rp = 0; rp < RPL; ++rp) ncell += __popc(evs[rp]);
       int tot = ncell;
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) tot += __shfl_xor_sync(FULL, tot, d);
@@ -788,7 +811,7 @@ __global__ void k_wapply_halo(WArgs a, const int* __restrict__ dec_top, const in
     if (!(a.node[ci] & NODE_VALID)) continue;
     const unsigned sh = (unsigned)(ci & 3) * 8u;
     const unsigned old = atomicAdd(a.cntw + (ci >> 2), 0u - ((unsigned)d << sh));
-    if ((int)((old >> sh) & 0xffu) == d) sched_activate(a, ((r - 1) / TS) * a.ntx + c / TS);
+    if ((int)((old >> sh) & 0xffu) == d) sched_activate(a, ((r - 1) / a.th) * a.ntx + c / TS);
   }
 }
 
@@ -798,7 +821,8 @@ __global__ void k_wsched_reset(unsigned long long* ctr) { for (int i = threadIdx
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
   a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
-  a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + TS - 1) / TS;
+  a.th = ctx->sweep_dinf ? tile_h<true>() : tile_h<false>();      // the tile height goes with the dependency state that is loaded
+  a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + a.th - 1) / a.th;
   a.stats = 0; a.poll = 0; a.exp = 0;
   a.peer = 0; a.G = nullptr; a.halo_in = nullptr; a.up = PeerStrip(); a.down = PeerStrip();
   const long long nt = (long long)a.ntx * a.nty;
@@ -935,7 +959,7 @@ int sweep_peer_export(td_ctx* ctx, const Strip& s, int dinf, unsigned char* hand
     TD_CUDA(cudaIpcGetMemHandle(&h, ptrs[i]));
     memcpy(handles + 64 * i, &h, 64);
   }
-  meta[0] = (int)a.qmask; meta[1] = a.ntx; meta[2] = s.ny; meta[3] = TS; meta[4] = a.ntx * a.nty; meta[5] = a.nsh; meta[6] = a.qshift; meta[7] = 0;
+  meta[0] = (int)a.qmask; meta[1] = a.ntx; meta[2] = s.ny; meta[3] = a.th; meta[4] = a.ntx * a.nty; meta[5] = a.nsh; meta[6] = a.qshift; meta[7] = 0;
   return TD_OK;
 }
 

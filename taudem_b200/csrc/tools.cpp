@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/taudem_b200.h"
+#include "mgpu.h"
 #include "tiff_io.h"
 
 namespace td { void set_error(const std::string& msg); }
@@ -56,7 +57,7 @@ struct Input {
 // tiffIO copy-constructor + write (src/tiffIO.cpp:187-243, 263-428): same size and
 // georeferencing as `like`, given type and nodata, name by the reference's extension rule.
 template <typename T>
-int write_like(const char* name, const Input& like, tdio::DType t, double nodata, const std::vector<T>& data) {
+int write_like(const char* name, const Input& like, tdio::DType t, double nodata, const T* data) {
   const std::string path = tdio::output_path_rule(name);
   const size_t dot = path.rfind('.');
   const std::string ext = dot == std::string::npos ? "" : path.substr(dot);
@@ -75,11 +76,40 @@ int write_like(const char* name, const Input& like, tdio::DType t, double nodata
   int comp = 5;
   if (comp_env && strcmp(comp_env, "NONE") == 0) comp = 1;
   if (comp_env && strcmp(comp_env, "DEFLATE") == 0) comp = 8;
-  if (!w.create(path, like.nx, like.ny, t, nodata, like.r.geo(), comp, &err) || !w.write_rows(0, like.ny, data.data(), &err) || !w.close(&err)) {
+  if (!w.create(path, like.nx, like.ny, t, nodata, like.r.geo(), comp, &err) || !w.write_rows(0, like.ny, data, &err) || !w.close(&err)) {
     printf("Error writing %s: %s\n", path.c_str(), err.c_str());
     td::set_error(err);
     return TD_ERR_IO;
   }
+  return TD_OK;
+}
+
+template <typename T>
+int write_like(const char* name, const Input& like, tdio::DType t, double nodata, const std::vector<T>& data) {
+  return write_like(name, like, t, nodata, data.data());
+}
+
+// TAUDEM_B200_GPUS=N (N > 1): the reference's `mpiexec -n N <tool>` — one forked process per GPU, each with its row strip
+// (mgpu.cu).  The ranks read their own rows; the parent writes the result.
+int area_multi_gpu(int dinf, int world, const Input& in, const char* infile, const char* wfile, int usew, int contcheck, const char* outfile,
+                   double t0, const char* nproc_label) {
+  const size_t bytes = (size_t)in.nx * in.ny * sizeof(float);
+  float* out = (float*)td::mgpu_alloc_shared(bytes);
+  if (!out) { td::set_error("cannot map the shared output raster"); return TD_ERR_IO; }
+  td::MgpuJob J;
+  J.dinf = dinf; J.dirfile = infile; J.wfile = wfile; J.usew = usew; J.contcheck = contcheck; J.nx = in.nx; J.ny = in.ny; J.out = out;
+  const double t1 = now();
+  double secs = 0.; int rounds = 0;
+  int rc = td::mgpu_area(J, world, &secs, &rounds);
+  const double t2 = now();
+  if (rc) printf("%s device error: %s\n", dinf ? "AreaDinf" : "AreaD8", td_last_error());
+  else rc = write_like(outfile, in, tdio::DT_F32, (double)-1.0f, (const float*)out);
+  const double t3 = now();
+  td::mgpu_free_shared(out, bytes);
+  if (rc) return rc;
+  // (the ranks read their rows inside what the reference calls compute time: Read time is the header pass)
+  printf("%s: %d\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", nproc_label, world, t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\nExchange rounds: %d\n", secs, rounds);
   return TD_OK;
 }
 
@@ -314,6 +344,15 @@ int td_aread8(const char* pfile, const char* afile, const char* datasrc, const c
   if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, p, &ocols, &orows)) return rc; }
   std::vector<int16_t> dir;
   nodata_msgs(p.r.nodata(), "int16_t", (int16_t)p.r.nodata());
+  if (td::mgpu_world() > 1 && useOutlets != 1 && p.ny >= td::mgpu_world()) {
+    Input w;
+    if (usew) {
+      if (int rc = w.open(wfile)) return rc;
+      if (!tdio::compare_rasters(p.r, p.path, w.r, w.path)) { printf("File sizes do not match\n%s\n", wfile); td::set_error("weight grid does not match"); return TD_ERR_MISMATCH; }
+      nodata_msgs(w.r.nodata(), "float", (float)w.r.nodata());
+    }
+    return area_multi_gpu(0, td::mgpu_world(), p, pfile, wfile, usew, contcheck, afile, t0, "Number of Processes");
+  }
   if (int rc = p.read(&dir, tdio::DT_I16)) return rc;
   Input w; std::vector<float> wg;
   if (usew) {
@@ -352,6 +391,15 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
   if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, a, &ocols, &orows)) return rc; }
   std::vector<float> ang;
   nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
+  if (td::mgpu_world() > 1 && useOutlets != 1 && a.ny >= td::mgpu_world()) {
+    Input w;
+    if (usew) {
+      if (int rc = w.open(wfile)) return rc;
+      if (!tdio::compare_rasters(a.r, a.path, w.r, w.path)) { td::set_error("weight grid does not match"); return TD_ERR_ARG; }
+      nodata_msgs(w.r.nodata(), "float", (float)w.r.nodata());
+    }
+    return area_multi_gpu(1, td::mgpu_world(), a, angfile, wfile, usew, contcheck, scafile, t0, "Processors");
+  }
   if (int rc = a.read(&ang, tdio::DT_F32)) return rc;
   Input w; std::vector<float> wg;
   if (usew) {

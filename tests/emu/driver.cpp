@@ -164,7 +164,7 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   if (alg) for (auto& T : S) std::fill(T.area.begin(), T.area.end(), -3.4028234663852886e38f);
   bool first = true;
   int rounds = 0;
-  for (auto& T : S) { td::make_prop_row(T.theta[0], true, &T.ctx.prop); T.ctx.dx0 = dx; }
+  for (auto& T : S) { td::make_prop_row(T.theta[0], true, &T.ctx.prop); T.ctx.dx0 = dx; T.ctx.sweep_dinf = dinf ? 1 : 0; }
   for (;;) {
     for (auto& T : S) {
       std::fill(T.halo.begin(), T.halo.end(), 0);

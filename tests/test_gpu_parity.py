@@ -98,6 +98,45 @@ def test_file_level_cli(refrun, tmp_path):
         assert np.float32(td.raster_info(str(d / f))["nodata"]) == np.float32(nd)
 
 
+def test_file_level_cli_multi_gpu(tmp_path):
+    """TAUDEM_B200_GPUS=N aread8 / areadinf (the reference's `mpiexec -n N`, src/aread8.cpp:57-100): one forked process per
+    GPU with its row strip; the files are bit-identical to the single-GPU run.  With fewer devices than ranks the ranks share
+    devices and exchange in rounds (the reference's scheme); with one device per rank the kernels deliver over NVLink."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "taudem_b200", "bin")
+    dem = synth.punch_holes(synth.gen_dem(520, 700, hurst=0.7, tilt=0.6, seed=33))
+    fel = td.pitremove_grid(dem, nodata=-9999.0)
+    p, _ = td.d8flowdir_grid(fel, dx=30.0, dy=30.0)
+    ang, _ = td.dinfflowdir_grid(fel, dx=30.0, dy=30.0)
+    rng = np.random.default_rng(5)
+    w = rng.uniform(0.0, 3.0, dem.shape).astype(np.float32)
+    d = tmp_path
+    td.write_raster(str(d / "p.tif"), p, -32768, dx=30.0, dy=30.0)
+    td.write_raster(str(d / "ang.tif"), ang, ANG_ND, dx=30.0, dy=30.0)
+    td.write_raster(str(d / "w.tif"), w, -9999.0, dx=30.0, dy=30.0)
+
+    def run(gpus, tool, *args):
+        env = dict(os.environ, TAUDEM_B200_GPUS=str(gpus))
+        r = subprocess.run([os.path.join(bindir, tool)] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
+                           timeout=300)
+        assert r.returncode == 0 and "error" not in r.stdout.lower(), r.stdout
+        return r.stdout
+
+    cases = [("aread8", "ad8", ("-p", d / "p.tif")), ("aread8", "ad8w", ("-p", d / "p.tif", "-wg", d / "w.tif", "-nc")),
+             ("areadinf", "sca", ("-ang", d / "ang.tif")), ("areadinf", "scaw", ("-ang", d / "ang.tif", "-wg", d / "w.tif"))]
+    for tool, name, args in cases:
+        outflag = "-ad8" if tool == "aread8" else "-sca"
+        run(1, tool, *args, outflag, d / f"{name}_1.tif")
+        one = td.read_raster(str(d / f"{name}_1.tif"))
+        for n in (2, 3):
+            out = run(n, tool, *args, outflag, d / f"{name}_{n}.tif")
+            assert (f"Number of Processes: {n}" if tool == "aread8" else f"Processors: {n}") in out, out
+            assert_bits(td.read_raster(str(d / f"{name}_{n}.tif")), one, f"{tool} {name} on {n} ranks")
+    assert_bits(td.read_raster(str(d / "ad8_1.tif")), td.aread8_grid(p), "ad8 file vs grid call")
+
+
 def test_properties_large():
     """Size-independent properties at a size the CPU reference cannot reach quickly (4096^2):
     fill is idempotent and never lowers a cell; every resolved D8 direction points to a cell that
