@@ -424,6 +424,53 @@ def reference(args):
                       "e2e": {"value": v, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def files_mode(args):
+    """File-level wall clock of the executables (not a bench line): `aread8` / `areadinf` on GeoTIFF files of the REF_SIZE
+    configuration, ours with TAUDEM_B200_GPUS = 1 .. --gpus (the reference's `mpiexec -n N`), the reference executables
+    (oracle/_ref, all host cores) beside them.  Wall time covers process start, reading, computing and writing (LZW)."""
+    import filecmp
+    import re
+    import subprocess
+    import tempfile
+    import time
+    n = args.size or REF_SIZE
+    work = tempfile.mkdtemp(prefix="tdbench_files_")
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--prep", work, "--size", str(n)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if r.returncode != 0:
+        print(json.dumps({"files": "unavailable", "why": r.stderr.strip()[-300:]}))
+        return
+    bindir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "taudem_b200", "bin")
+    rows = []
+    ns = [k for k in (1, 2, 4, 8) if k <= max(1, args.gpus)]
+    for tool, flag_in, fin, flag_out in (("aread8", "-p", "p.tif", "-ad8"), ("areadinf", "-ang", "ang.tif", "-sca")):
+        first = None
+        for k in ns:
+            out = os.path.join(work, f"{tool}_{k}.tif")
+            env = dict(os.environ, TAUDEM_B200_GPUS=str(k))
+            t0 = time.time()
+            rr = subprocess.run([os.path.join(bindir, tool), flag_in, os.path.join(work, fin), flag_out, out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+            wall = time.time() - t0
+            tm = {m.group(1).strip(): float(m.group(2)) for m in re.finditer(r"^([A-Za-z ]+time): ([0-9.eE+-]+)$", rr.stdout, re.M)}
+            same = None
+            if first is None:
+                first = out
+            else:
+                same = filecmp.cmp(first, out, shallow=False)
+            rows.append({"tool": tool, "impl": "ours", "ranks": k, "rc": rr.returncode, "wall_s": round(wall, 3), "tool_times_s": tm, "file_identical_to_1_rank": same})
+        if not args.no_cpu:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle"))
+            import refrun
+            if refrun.available():
+                ranks = max(1, min(args.cpu_ranks, host_cores()))
+                os.environ["MINIMPI_PIN"] = "1"
+                t0 = time.time()
+                _, tm = refrun.run_tool(tool, [flag_in, os.path.join(work, fin), flag_out, os.path.join(work, f"{tool}_ref.tif")], ranks)
+                rows.append({"tool": tool, "impl": "reference", "ranks": ranks, "rc": 0, "wall_s": round(time.time() - t0, 3), "tool_times_s": tm})
+    import shutil
+    shutil.rmtree(work, ignore_errors=True)
+    print(json.dumps({"files": f"{n}x{n}", "rows": rows}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -437,8 +484,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-same-config", action="store_true", help="skip the additional 16384^2 measurement (the reference arm's configuration)")
     ap.add_argument("--prep", default="", help="write the REF_SIZE direction rasters into this directory and exit (input preparation of the reference arm)")
+    ap.add_argument("--files", action="store_true", help="file-level wall clock of the executables at 1 .. --gpus ranks next to the reference executables")
     args = ap.parse_args()
-    if args.prep:
+    if args.files:
+        files_mode(args)
+    elif args.prep:
         prep(args)
     elif args.impl == "reference":
         reference(args)

@@ -48,6 +48,7 @@ extern "C" {
 const char* td_version(void);            /* "5.4.0-b200" (TDVERSION, src/commonLib.h:63)  */
 const char* td_last_error(void);         /* thread-local message for the last failure     */
 int td_device_count(void);               /* number of CUDA devices, 0 if none             */
+int td_warmup(void);                     /* creates the CUDA context now (callable from a helper thread while inputs are read) */
 int td_set_device(int dev);
 /* Kernels launched by this library since the last reset (bench `gpu_launches`). */
 unsigned long long td_launch_count(void);
@@ -106,6 +107,15 @@ int td_d8flowpathextremeup(const char* pfile, const char* safile, const char* ss
                            int uselyrname, int lyrno, int useOutlets, int contcheck);
 int td_d8flowpathextremeup_host(const int16_t* p, const float* sa, float* ssa, int nx, int ny, int16_t p_nodata, int usemax, int contcheck,
                                 const int* outlet_cols, const int* outlet_rows, int nout /* < 0: no outlets */);
+/* Sibling of areadinf on the same sweep: decaying accumulation.  File level = `int dmarea(char* angfile, char* adecfile, char* dmfile,
+ * char* datasrc, char* lyrname, int uselyrname, int lyrno, char* wfile, int useOutlets, int usew, int contcheck)`
+ * (src/dinfdecayaccum.cpp:61); dsca: float32, nodata -FLT_MAX.  A cell starts from its weight (or its cell size dx) and receives
+ * (float)(dm * area * p) from every contributor, dm = the contributor's decay multiplier (src/dinfdecayaccum.cpp:205-235). */
+int td_dmarea(const char* angfile, const char* adecfile, const char* dmfile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno,
+              const char* wfile, int useOutlets, int usew, int contcheck);
+int td_dinfdecayaccum_host(const float* ang, const float* dm, const float* w /*NULL unless usew*/, float* dsca, int nx, int ny, float ang_nodata,
+                           float dm_nodata, const double* dxc, const double* dyc, int contcheck, const int* outlet_cols, const int* outlet_rows,
+                           int nout /* < 0: no outlets */);
 int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile, float thresh, int usemask);
 int td_twigrid(const char* slopefile, const char* areafile, const char* twifile);
 int td_threshold_host(const float* ssa, const float* mask /*NULL unless usemask*/, int16_t* src, int nx, int ny, float thresh, float ssa_nodata);

@@ -115,6 +115,19 @@ class RefPipeline:
         _, self.times["d8flowpathextremeup"] = run_tool("d8flowpathextremeup", args, self.np_ranks)
         return self.get("ssa_up.tif", np.float32)
 
+    def dinfdecayaccum(self, ang, dm, weights=None, contcheck=True, outlets=None, nodata=-3.4028234663852886e38, dm_nodata=-9999.0, w_nodata=-9999.0):
+        self.put("angin.tif", ang, nodata); self.put("dm.tif", dm, dm_nodata)
+        args = ["-ang", self.path("angin.tif"), "-dm", self.path("dm.tif"), "-dsca", self.path("dsca.tif")]
+        if outlets is not None:
+            args += ["-o", outlets]
+        if weights is not None:
+            self.put("w.tif", weights, w_nodata)
+            args += ["-wg", self.path("w.tif")]
+        if not contcheck:
+            args.append("-nc")
+        _, self.times["dinfdecayaccum"] = run_tool("dinfdecayaccum", args, self.np_ranks)
+        return self.get("dsca.tif", np.float32)
+
     def threshold(self, ssa, thresh, mask=None, nodata=-1.0):
         self.put("ssa.tif", ssa, nodata)
         args = ["-ssa", self.path("ssa.tif"), "-src", self.path("src.tif"), "-thresh", repr(float(thresh))]

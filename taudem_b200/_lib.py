@@ -29,6 +29,7 @@ SIGNATURES = {
     "td_version": (_S, []),
     "td_last_error": (_S, []),
     "td_device_count": (_I, []),
+    "td_warmup": (_I, []),
     "td_set_device": (_I, [_I]),
     "td_launch_count": (C.c_ulonglong, []),
     "td_reset_launch_count": (None, []),
@@ -40,6 +41,8 @@ SIGNATURES = {
     "td_area": (_I, [_S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
     "td_d8flowpathextremeup": (_I, [_S, _S, _S, _I, _S, _S, _I, _I, _I, _I]),
     "td_d8flowpathextremeup_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _I, _I, _P, _P, _I]),
+    "td_dmarea": (_I, [_S, _S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
+    "td_dinfdecayaccum_host": (_I, [_P, _P, _P, _P, _I, _I, C.c_float, C.c_float, _P, _P, _I, _P, _P, _I]),
     "td_threshold": (_I, [_S, _S, _S, _F, _I]),
     "td_twigrid": (_I, [_S, _S, _S]),
     "td_threshold_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),

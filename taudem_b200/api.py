@@ -165,6 +165,23 @@ def d8flowpathextremeup_grid(p, sa, usemax=True, nodata=int(MISSINGSHORT), contc
     return ssa
 
 
+def dinfdecayaccum_grid(ang, dm, weights=None, dx=30.0, dy=30.0, nodata=float(MISSINGFLOAT), dm_nodata=-9999.0, contcheck=True, outlets=None,
+                        dxc=None, dyc=None):
+    """Decaying accumulation on the D-infinity flow field (td_dinfdecayaccum_host; src/dinfdecayaccum.cpp:205-235): a cell starts from
+    its weight (or dx) and receives (float)(dm * area * p) from every contributor.  nodata = -FLT_MAX."""
+    ang = _grid(ang, np.float32); dm = _grid(dm, np.float32)
+    ny, nx = ang.shape
+    assert dm.shape == ang.shape
+    w = None if weights is None else _grid(weights, np.float32)
+    dxc = _rows(dx, ny) if dxc is None else np.ascontiguousarray(dxc, np.float64)
+    dyc = _rows(dy, ny) if dyc is None else np.ascontiguousarray(dyc, np.float64)
+    out = np.empty((ny, nx), np.float32)
+    oc, orow, nout = _outlet_args(outlets)
+    check(lib().td_dinfdecayaccum_host(_ptr(ang), _ptr(dm), _ptr(w), _ptr(out), nx, ny, np.float32(nodata), np.float32(dm_nodata), _ptr(dxc), _ptr(dyc),
+                                       int(contcheck), _ptr(oc), _ptr(orow), nout))
+    return out
+
+
 def threshold_grid(ssa, thresh=100.0, mask=None, nodata=-1.0):
     """src = (ssa >= thresh [& mask >= 0]) ? 1 : 0, -32768 where ssa is nodata (td_threshold_host; src/Threshold.cpp:109-131)."""
     ssa = _grid(ssa, np.float32)

@@ -25,7 +25,7 @@ __device__ __forceinline__ unsigned eq_bytes7(unsigned w, unsigned t) { return ~
 
 __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang, unsigned short* __restrict__ node,
                                                    unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,
-                                                   float nodata, const double* __restrict__ theta) {
+                                                   float nodata, const double* __restrict__ theta, float area_init) {
   using G = TileGeom<float, TW, TH>;
   __shared__ __align__(128) float tile[G::ELEMS];
   __shared__ __align__(8) uint64_t bar;
@@ -115,16 +115,16 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
     const long long o = s.idx(r, c);
     *reinterpret_cast<ushort4*>(node + o) = make_ushort4(on4[0], on4[1], on4[2], on4[3]);
     *reinterpret_cast<uchar4*>(cnt + o) = make_uchar4(oc4[0], oc4[1], oc4[2], oc4[3]);
-    *reinterpret_cast<float4*>(area + o) = make_float4(-1.f, -1.f, -1.f, -1.f);   // src/areadinf.cpp:154
+    *reinterpret_cast<float4*>(area + o) = make_float4(area_init, area_init, area_init, area_init);   // nodata everywhere first (src/areadinf.cpp:154)
   }
 }
 
 }  // namespace
 
 cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
-                             float nodata, const double* theta, cudaStream_t st) {
+                             float nodata, const double* theta, cudaStream_t st, float area_init) {
   dim3 grid((s.pitch + TW - 1) / TW, (s.ny + TH - 1) / TH);
-  k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, s, nodata, theta);
+  k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, s, nodata, theta, area_init);
   TD_LAUNCHED();
   return cudaGetLastError();
 }

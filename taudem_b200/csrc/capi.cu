@@ -51,6 +51,13 @@ int need_device() {
   if (e != cudaSuccess || n == 0) { td::set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e)); return TD_ERR_CUDA; }
   return TD_OK;
 }
+// TAUDEM_B200_TRACE=1: wall-clock marks of the host-grid level calls on stderr (epoch seconds, comparable across processes)
+void trace_mark(const char* what) {
+  static const bool on = getenv("TAUDEM_B200_TRACE") != nullptr;
+  if (!on) return;
+  timespec ts; clock_gettime(CLOCK_REALTIME, &ts);
+  fprintf(stderr, "[td trace] %.3f %s\n", (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec, what);
+}
 td_ctx* default_ctx() {
   static td_ctx* c = nullptr;
   if (!c) c = new td_ctx();
@@ -62,6 +69,13 @@ extern "C" {
 
 const char* td_version(void) { return "5.4.0-b200"; }
 const char* td_last_error(void) { return td::g_err.c_str(); }
+// starts the CUDA context (file-level tools call it on a helper thread while they read their inputs)
+int td_warmup(void) {
+  trace_mark("warmup: start");
+  const cudaError_t e = cudaFree(0);
+  trace_mark("warmup: context ready");
+  return e == cudaSuccess ? TD_OK : TD_ERR_CUDA;
+}
 int td_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 int td_set_device(int dev) { TD_CUDA(cudaSetDevice(dev)); return TD_OK; }
 unsigned long long td_launch_count(void) { return td::g_launches; }
@@ -449,23 +463,29 @@ int td_aread8_host(const int16_t* p, const float* w, float* ad8, int nx, int ny,
 // nout < 0: no outlets (the whole grid); nout >= 0: only the cells upstream of the outlets (src/aread8.cpp -o)
 int td_aread8_outlets_host(const int16_t* p, const float* w, float* ad8, int nx, int ny, int16_t p_nodata, float w_nodata, int contcheck,
                            const int* outlet_cols, const int* outlet_rows, int nout) {
+  trace_mark("aread8_host: enter");
   if (int rc = need_device()) return rc;
   if (!p || !ad8 || nx <= 0 || ny <= 0) { td::set_error("td_aread8_host: bad arguments"); return TD_ERR_ARG; }
   td_ctx* ctx = default_ctx();
   const td_strip s = host_strip(nx, ny);
   const size_t n = (size_t)Strip(s).cells();
   cudaStream_t st = 0;
+  trace_mark("aread8_host: device ready");
   TD_CUDA(ctx->io[0].ensure(n * 2)); TD_CUDA(ctx->io[1].ensure(n * 4));
   int16_t* d_p = ctx->io[0].as<int16_t>(); float* d_a = ctx->io[1].as<float>(); float* d_w = nullptr;
+  trace_mark("aread8_host: buffers allocated");
   TD_CUDA(h2d(d_p, p, s, st));
   if (w) { TD_CUDA(ctx->io[2].ensure(n * 4)); d_w = ctx->io[2].as<float>(); TD_CUDA(h2d(d_w, w, s, st)); }
+  if (getenv("TAUDEM_B200_TRACE")) { cudaStreamSynchronize(st); trace_mark("aread8_host: inputs on the device"); }
   Timer t; t.start(st);
   if (int rc = td_aread8_deps_dev(ctx, d_p, d_a, s, p_nodata, st)) return rc;
   if (nout >= 0) { if (int rc = td_sweep_restrict_dev(ctx, s, outlet_cols, outlet_rows, nout, st)) return rc; }
   if (int rc = td_aread8_sweep_dev(ctx, d_w, d_a, s, w_nodata, w != nullptr, contcheck, st)) return rc;
   td::set_compute_seconds(t.stop(st));
+  trace_mark("aread8_host: computed");
   TD_CUDA(d2h(ad8, d_a, s, st));
   TD_CUDA(cudaStreamSynchronize(st));
+  trace_mark("aread8_host: result on the host");
   return TD_OK;
 }
 
@@ -492,6 +512,39 @@ int td_d8flowpathextremeup_host(const int16_t* p, const float* sa, float* ssa, i
   if (int rc = td::wsweep_run(ctx, false, d_a, d_sa, nullptr, Strip(s), 0.f, 1, contcheck, nullptr, nullptr, ctx->halo.as<int>(), st, usemax ? 1 : 2)) return rc;
   td::set_compute_seconds(t.stop(st));
   TD_CUDA(d2h(ssa, d_a, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
+// dinfdecayaccum (src/dinfdecayaccum.cpp:61): the D-infinity sweep with the decaying-accumulation algebra.  Single strip.
+int td_dinfdecayaccum_host(const float* ang, const float* dm, const float* w, float* dsca, int nx, int ny, float ang_nodata, float dm_nodata,
+                           const double* dxc, const double* dyc, int contcheck, const int* outlet_cols, const int* outlet_rows, int nout) {
+  if (int rc = need_device()) return rc;
+  if (!ang || !dm || !dsca || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_dinfdecayaccum_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[3].ensure(n * 4));
+  float* d_ang = ctx->io[0].as<float>(); float* d_a = ctx->io[1].as<float>(); float* d_dm = ctx->io[3].as<float>(); float* d_w = nullptr;
+  const double *d_dx, *d_dy;
+  if (int rc = upload_rows(ctx, dxc, dyc, ny, &d_dx, &d_dy, st)) return rc;
+  TD_CUDA(h2d(d_ang, ang, s, st));
+  TD_CUDA(h2d(d_dm, dm, s, st));
+  if (w) { TD_CUDA(ctx->io[2].ensure(n * 4)); d_w = ctx->io[2].as<float>(); TD_CUDA(h2d(d_w, w, s, st)); }
+  Timer t; t.start(st);
+  const Strip ss(s);
+  if (int rc = ensure_dep_state(ctx, ss, st)) return rc;
+  if (int rc = upload_theta(ctx, d_dx, d_dy, s.ny, ctx->theta, st)) return rc;
+  ctx->sweep_dinf = 1;
+  TD_CUDA(td::launch_deps_dinf(d_ang, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), d_a, ss, ang_nodata, ctx->theta.as<double>(), st,
+                               TD_MISSINGFLOAT));
+  if (nout >= 0) { if (int rc = td_sweep_restrict_dev(ctx, s, outlet_cols, outlet_rows, nout, st)) return rc; }
+  if (int rc = td::wsweep_begin(ctx, ss, st)) return rc;
+  if (int rc = td::wsweep_run(ctx, true, d_a, d_w, d_ang, ss, 0.f, w != nullptr, contcheck, ctx->theta.as<double>(), d_dx, ctx->halo.as<int>(), st, 3,
+                              d_dm, dm_nodata)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(dsca, d_a, s, st));
   TD_CUDA(cudaStreamSynchronize(st));
   return TD_OK;
 }

@@ -6,8 +6,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "../../../include/taudem_b200.h"
+
+// the outputs are on disk: leave without tearing the CUDA context down (hundreds of milliseconds with gigabytes allocated)
+static int done() { fflush(stdout); fflush(stderr); _exit(0); return 0; }
 
 #define MAXLN 4096
 
@@ -72,7 +76,7 @@ int main(int argc, char** argv) {
   }
   int err = td_flood(dem, fel, "", 0, verbose, four, use_mask, mask);
   if (err != 0) printf("PitRemove error %d\n", err);
-  return 0;
+  return done();
 }
 
 #elif defined(TOOL_d8flowdir)
@@ -96,7 +100,7 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(dem, argv[1], "fel"); td_nameadd(p, argv[1], "p"); td_nameadd(sd8, argv[1], "sd8"); }
   int err = td_setdird8(dem, p, sd8, flow, useflow);
   if (err != 0) printf("setdird8 error %d\n", err);
-  return 0;
+  return done();
 }
 
 #elif defined(TOOL_dinfflowdir)
@@ -120,7 +124,7 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(dem, argv[1], "fel"); td_nameadd(ang, argv[1], "ang"); td_nameadd(slp, argv[1], "slp"); }
   int err = td_setdir(dem, ang, slp, flow, useflow);
   if (err != 0) printf("Setdir error %d\n", err);
-  return 0;
+  return done();
 }
 
 #elif defined(TOOL_aread8) || defined(TOOL_areadinf)
@@ -163,7 +167,7 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(out, argv[1], OUT_SUFF); td_nameadd(in, argv[1], IN_SUFF); }
   int err = CALL(in, out, datasrc, lyrname, uselyrname, lyrno, wfile, useOutlets, usew, contcheck);
   if (err != 0) printf("area error %d\n", err);
-  return 0;
+  return done();
 }
 #elif defined(TOOL_d8flowpathextremeup)
 // src/D8FlowPathExtremeUpmn.cpp:57-174
@@ -189,7 +193,37 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(pf, argv[1], "p"); td_nameadd(sa, argv[1], "sa"); td_nameadd(ssa, argv[1], "ssa"); }
   int err = td_d8flowpathextremeup(pf, sa, ssa, usemax, datasrc, lyrname, uselyrname, lyrno, useOutlets, contcheck);
   if (err != 0) printf("Flow Path Extreme Up Error %d\n", err);
-  return 0;
+  return done();
+}
+
+#elif defined(TOOL_dinfdecayaccum)
+// src/DinfDecayAccummn.cpp:51-192
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s -ang <angfile>\n", prog);
+  printf("-dm <dmfile> -dsca <adecfile> [-o <outletshapefile>] [-wg <wfile>] [-nc]\n");
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("<angfile> is the D-infinity flow direction input file.\n");
+  printf("<dmfile> is the decay multiplier input grid file.\n");
+  printf("<adecfile> is the decayed specific catchment area output grid file.\n");
+  printf("[-o <outletshapefile>] is the optional outlet shape input file.\n");
+  printf("[-wg <wfile>] is the optional weight grid input file.\n");
+  printf("The flag -nc overrides edge contamination checking\n");
+  printf("The following are appended to the file names before the files are opened:\n");
+  printf("ang    D-infinity flow direction input file\ndm    decay multiplier input file\ndsca   decayed specific catchment area output file\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char ang[MAXLN], dm[MAXLN], dsca[MAXLN], wfile[MAXLN], datasrc[MAXLN], lyrname[MAXLN];
+  int useOutlets = 0, uselyrname = 0, usew = 0, contcheck = 1, lyrno = 0;
+  if (argc < 2) usage(argv[0]);
+  Opt opts[] = {{"-ang", 0, ang, NULL, 0}, {"-dm", 0, dm, NULL, 0}, {"-dsca", 0, dsca, NULL, 0}, {"-wg", 0, wfile, &usew, 1}, {"-o", 0, datasrc, &useOutlets, 1},
+                {"-lyrno", 2, NULL, &lyrno, 0}, {"-lyrname", 0, lyrname, &uselyrname, 1}, {"-nc", 1, NULL, &contcheck, 0}};
+  parse(argc, argv, opts, 8);
+  if (argc == 2) { td_nameadd(ang, argv[1], "ang"); td_nameadd(dm, argv[1], "dm"); td_nameadd(dsca, argv[1], "dsca"); }
+  int err = td_dmarea(ang, dsca, dm, datasrc, lyrname, uselyrname, lyrno, wfile, useOutlets, usew, contcheck);
+  if (err != 0) printf("area error %d\n", err);
+  return done();
 }
 
 #elif defined(TOOL_threshold)
@@ -216,7 +250,7 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(ssa, argv[1], "ssa"); td_nameadd(src, argv[1], "src"); }
   int err = td_threshold(ssa, src, mask, thresh, usemask);
   if (err != 0) printf("Threshold Error %d\n", err);
-  return 0;
+  return done();
 }
 
 #elif defined(TOOL_twi)
@@ -243,7 +277,7 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(sca, argv[1], "sca"); td_nameadd(slp, argv[1], "slp"); td_nameadd(twi, argv[1], "twi"); }
   int err = td_twigrid(slp, sca, twi);
   if (err != 0) printf("TWI error %d\n", err);
-  return 0;
+  return done();
 }
 #else
 #error "define TOOL_<name>"

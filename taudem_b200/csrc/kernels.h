@@ -15,12 +15,13 @@ int resolve_flats_dinf(td_ctx* ctx, float* elev, float* ang, const Strip& s, con
 cudaError_t launch_deps_d8(const short* p, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
                            short nodata, cudaStream_t st, float area_init = -1.0f);
 cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
-                             float nodata, const double* theta, cudaStream_t st);
+                             float nodata, const double* theta, cudaStream_t st, float area_init = -1.0f);
 cudaError_t zero_words(void* p, size_t bytes, cudaStream_t st);     // a multiple of 4 bytes, zeroed by a kernel (never by a copy engine)
 int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
 int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
-               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg = 0);
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg = 0, const float* dm = nullptr,
+               float dm_nodata = 0.f);
 int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, const int* in_top, const int* in_bot,
                          int* req_out, int finish, cudaStream_t st);
 int sweep_restrict_upstream(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, cudaStream_t st);

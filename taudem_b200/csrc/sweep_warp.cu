@@ -105,6 +105,7 @@ struct WArgs {
   const double* dxc;
   int* halo;
   int ntx, nty, th;        // tiles of the strip, tile height
+  const float* dm; float dm_nodata;   // ALG 3: the decay multiplier grid (strip layout) and its nodata
   int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;          // slots of one shard's ring - 1
@@ -352,8 +353,11 @@ __device__ __forceinline__ unsigned zero_nibble(unsigned w) {
   return ((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u);
 }
 
-// ALG (D8 with a value grid in `w` only): 0 = sum (aread8, src/aread8.cpp:228-257), 1 / 2 = the largest / smallest value of `w` on the
-// flow paths above each cell (d8flowpathextremeup, src/D8flowpathextremeup.cpp:182-215; results nodata = MISSINGFLOAT)
+// ALG: 0 = sum (aread8, src/aread8.cpp:228-257; areadinf, src/areadinf.cpp:187-218); D8 with a value grid in `w` only: 1 / 2 = the
+// largest / smallest value of `w` on the flow paths above each cell (d8flowpathextremeup, src/D8flowpathextremeup.cpp:182-215);
+// D-infinity only: 3 = decaying accumulation (dinfdecayaccum, src/dinfdecayaccum.cpp:205-235: the cell's own input first, then
+// per contributor  + (float)(dm * area * p)  with the contributor's decay multiplier dm; a nodata multiplier contaminates).
+// Results of ALG != 0 use MISSINGFLOAT as nodata.
 template <bool DINF, bool USEW, int ALG>
 __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(const WArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -538,14 +542,20 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
                 const int rn = r0 + lr + dr;
                 p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : a.theta[min(max(rn - 1, 0), s.ny - 1)], kk);
               }
-              prod = nd_f(an, -1.0f) ? __longlong_as_double(0x7ff8dead00000000ll) : p * (double)an;   // NaN: a contaminated contributor
+              if (ALG == 3) {
+                const float dmv = __ldg(a.dm + s.idx(r0 + lr + dr, c0 + lx + lut_dcol(k)));
+                prod = (nd_f(an, NOD) || nd_f(dmv, a.dm_nodata)) ? __longlong_as_double(0x7ff8dead00000000ll) : (double)(float)((double)(dmv * an) * p);
+              } else
+              prod = nd_f(an, NOD) ? __longlong_as_double(0x7ff8dead00000000ll) : p * (double)an;   // NaN: a contaminated contributor
             }
             val = 0.f;
+            if (ALG == 3) val = USEW ? wv : (float)(a.prop.uniform ? a.dx0 : a.dxc[min(r0 + lr, s.ny) - 1]);
             for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
               const double pr = __shfl_sync(FULL, prod, __ffs(m) - 1);
-              if (pr != pr) con = true; else val = (float)((double)val + pr);
+              if (pr != pr) con = true; else val = ALG == 3 ? val + (float)pr : (float)((double)val + pr);
             }
-            if (USEW) val = val + wv;
+            if (ALG == 3) {}
+            else if (USEW) val = val + wv;
             else val = (float)((double)val + (a.prop.uniform ? a.dx0 : a.dxc[min(r0 + lr, s.ny) - 1]));
           }
           if (con && a.contcheck) val = NOD;
@@ -635,6 +645,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           // dinf_outflow form; irregular cells and strips without a common table take the interval search.
           const int r = r0 + lr;
           val = 0.f;
+          if (ALG == 3) val = USEW ? wv : (float)(a.prop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]);
 #pragma unroll 1
           for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
             const int k = __ffs(m);
@@ -659,9 +670,14 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
               const int rn = r + dr;
               p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : a.theta[min(max(rn - 1, 0), s.ny - 1)], kk);
             }
-            if (nd_f(an, -1.0f)) con = true; else val = (float)((double)val + p * (double)an);
+            if (ALG == 3) {
+              const float dmv = __ldg(a.dm + s.idx(r + dr, c0 + lx + lut_dcol(k)));
+              if (nd_f(an, NOD) || nd_f(dmv, a.dm_nodata)) con = true;
+              else val = val + (float)((double)(dmv * an) * p);
+            } else if (nd_f(an, NOD)) con = true; else val = (float)((double)val + p * (double)an);
           }
-          if (USEW) val = val + wv;
+          if (ALG == 3) {}
+          else if (USEW) val = val + wv;
           else val = (float)((double)val + (a.prop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]));
         }
         if (con && a.contcheck) val = NOD;
@@ -820,7 +836,7 @@ __global__ void k_wsched_reset(unsigned long long* ctr) { for (int i = threadIdx
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
-  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr;
+  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr; a.dm = nullptr; a.dm_nodata = 0.f;
   a.th = ctx->sweep_dinf ? tile_h<true>() : tile_h<false>();      // the tile height goes with the dependency state that is loaded
   a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + a.th - 1) / a.th;
   a.stats = 0; a.poll = 0; a.exp = 0;
@@ -875,12 +891,15 @@ int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int
 
 // Runs the evaluation wavefront over the queued tiles until no tile of the strip has a ready cell left.
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
-               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg) {
-  if (alg != 0 && (dinf || !usew || alg < 0 || alg > 2)) { set_error("wsweep_run: the extreme-value algebra is a D8 sweep over a value grid"); return TD_ERR_ARG; }
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg, const float* dm, float dm_nodata) {
+  if (alg < 0 || alg > 3 || ((alg == 1 || alg == 2) && (dinf || !usew)) || (alg == 3 && (!dinf || !dm))) {
+    set_error("wsweep_run: the extreme-value algebra is a D8 sweep over a value grid, the decaying accumulation a D-infinity sweep with a multiplier grid");
+    return TD_ERR_ARG;
+  }
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
-  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo;
+  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo; a.dm = dm; a.dm_nodata = dm_nodata;
   a.prop = ctx->prop;
   if (!dinf) a.prop.uniform = 0;
   a.peer = ctx->peer_on;
@@ -905,10 +924,11 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   if (const char* we = getenv("TAUDEM_B200_WORKERS")) { const int v = atoi(we); if (v >= 1 && v < warps) warps = v; }   // experiments: fewer workers per SM
   size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
   if (const char* pe2 = getenv("TAUDEM_B200_SMEMPAD")) smem = std::max(smem, (size_t)atoi(pe2));                  // experiments: one CTA per SM whatever its size
-  const void* kern = dinf ? (usew ? (const void*)k_sweep_warp<true, true, 0> : (const void*)k_sweep_warp<true, false, 0>)
+  const void* kern = alg == 3 ? (usew ? (const void*)k_sweep_warp<true, true, 3> : (const void*)k_sweep_warp<true, false, 3>)
+                   : dinf ? (usew ? (const void*)k_sweep_warp<true, true, 0> : (const void*)k_sweep_warp<true, false, 0>)
                           : alg == 1 ? (const void*)k_sweep_warp<false, true, 1> : alg == 2 ? (const void*)k_sweep_warp<false, true, 2>
                           : (usew ? (const void*)k_sweep_warp<false, true, 0> : (const void*)k_sweep_warp<false, false, 0>);
-  int& per_dev = ctx->wgrid[alg ? 3 + alg : (dinf ? 2 : 0) + (usew ? 1 : 0)];
+  int& per_dev = ctx->wgrid[alg == 3 ? 6 + (usew ? 1 : 0) : alg ? 3 + alg : (dinf ? 2 : 0) + (usew ? 1 : 0)];
   if (!per_dev || getenv("TAUDEM_B200_WORKERS")) {
     int dev = 0, sms = 0, occ = 0;
     TD_CUDA(cudaGetDevice(&dev));
@@ -920,7 +940,8 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   }
   const long long nt = (long long)a.ntx * a.nty;
   const int g = (int)std::min<long long>(per_dev, (nt + warps - 1) / warps);
-  if (dinf) { if (usew) k_sweep_warp<true, true, 0><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 0><<<g, warps * 32, smem, st>>>(a); }
+  if (alg == 3) { if (usew) k_sweep_warp<true, true, 3><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 3><<<g, warps * 32, smem, st>>>(a); }
+  else if (dinf) { if (usew) k_sweep_warp<true, true, 0><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 0><<<g, warps * 32, smem, st>>>(a); }
   else if (alg == 1) k_sweep_warp<false, true, 1><<<g, warps * 32, smem, st>>>(a);
   else if (alg == 2) k_sweep_warp<false, true, 2><<<g, warps * 32, smem, st>>>(a);
   else { if (usew) k_sweep_warp<false, true, 0><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<false, false, 0><<<g, warps * 32, smem, st>>>(a); }

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/taudem_b200.h"
@@ -112,6 +113,14 @@ int area_multi_gpu(int dinf, int world, const Input& in, const char* infile, con
   printf("Device compute time: %f\nExchange rounds: %d\n", secs, rounds);
   return TD_OK;
 }
+
+// the CUDA context comes up on a helper thread while the tool opens and reads its rasters
+struct Warmup {
+  std::thread th;
+  Warmup() : th([] { td_warmup(); }) {}
+  void join() { if (th.joinable()) th.join(); }
+  ~Warmup() { join(); }
+};
 
 void nodata_msgs(double nd, const char* what, double cast) {
   // createpart.h:57-85 prints these two lines for every partition created from a file
@@ -353,6 +362,7 @@ int td_aread8(const char* pfile, const char* afile, const char* datasrc, const c
     }
     return area_multi_gpu(0, td::mgpu_world(), p, pfile, wfile, usew, contcheck, afile, t0, "Number of Processes");
   }
+  Warmup warm;
   if (int rc = p.read(&dir, tdio::DT_I16)) return rc;
   Input w; std::vector<float> wg;
   if (usew) {
@@ -363,6 +373,7 @@ int td_aread8(const char* pfile, const char* afile, const char* datasrc, const c
   }
   const double t1 = now();
   std::vector<float> ad8((size_t)p.nx * p.ny);
+  warm.join();
   if (int rc = td_aread8_outlets_host(dir.data(), usew ? wg.data() : nullptr, ad8.data(), p.nx, p.ny, (int16_t)p.r.nodata(),
                                       usew ? (float)w.r.nodata() : 0.f, contcheck, ocols.data(), orows.data(),
                                       useOutlets == 1 ? (int)ocols.size() : -1)) {
@@ -400,6 +411,7 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
     }
     return area_multi_gpu(1, td::mgpu_world(), a, angfile, wfile, usew, contcheck, scafile, t0, "Processors");
   }
+  Warmup warm;
   if (int rc = a.read(&ang, tdio::DT_F32)) return rc;
   Input w; std::vector<float> wg;
   if (usew) {
@@ -410,6 +422,7 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
   }
   const double t1 = now();
   std::vector<float> sca((size_t)a.nx * a.ny);
+  warm.join();
   if (int rc = td_area_outlets_host(ang.data(), usew ? wg.data() : nullptr, sca.data(), a.nx, a.ny, (float)a.r.nodata(),
                                     usew ? (float)w.r.nodata() : 0.f, a.dxc.data(), a.dyc.data(), contcheck, ocols.data(), orows.data(),
                                     useOutlets == 1 ? (int)ocols.size() : -1)) {
@@ -465,6 +478,48 @@ int td_d8flowpathextremeup(const char* pfile, const char* safile, const char* ss
 }
 
 // src/Threshold.cpp:48-162
+// dmarea (src/dinfdecayaccum.cpp:61-323)
+int td_dmarea(const char* angfile, const char* adecfile, const char* dmfile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno,
+              const char* wfile, int useOutlets, int usew, int contcheck) try {
+  printf("DinfDecayAccum version %s\n", td_version());
+  const double t0 = now();
+  Input a;
+  if (int rc = a.open(angfile)) return rc;
+  std::vector<int> ocols, orows;
+  if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, a, &ocols, &orows)) return rc; }
+  std::vector<float> ang, dm, wg;
+  nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
+  if (int rc = a.read(&ang, tdio::DT_F32)) return rc;
+  Input d;
+  if (int rc = d.open(dmfile)) return rc;
+  if (!tdio::compare_rasters(a.r, a.path, d.r, d.path)) { printf("File sizes do not match\n%s\n", dmfile); td::set_error("decay multiplier grid does not match"); return TD_ERR_MISMATCH; }
+  nodata_msgs(d.r.nodata(), "float", (float)d.r.nodata());
+  if (int rc = d.read(&dm, tdio::DT_F32)) return rc;
+  Input w;
+  if (usew) {
+    if (int rc = w.open(wfile)) return rc;
+    if (!tdio::compare_rasters(a.r, a.path, w.r, w.path)) { printf("File sizes do not match\n%s\n", wfile); td::set_error("weight grid does not match"); return TD_ERR_MISMATCH; }
+    nodata_msgs(w.r.nodata(), "float", (float)w.r.nodata());
+    if (int rc = w.read(&wg, tdio::DT_F32)) return rc;
+  }
+  const double t1 = now();
+  std::vector<float> out((size_t)a.nx * a.ny);
+  if (int rc = td_dinfdecayaccum_host(ang.data(), dm.data(), usew ? wg.data() : nullptr, out.data(), a.nx, a.ny, (float)a.r.nodata(), (float)d.r.nodata(),
+                                      a.dxc.data(), a.dyc.data(), contcheck, ocols.data(), orows.data(), useOutlets == 1 ? (int)ocols.size() : -1)) {
+    printf("DinfDecayAccum device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(adecfile, a, tdio::DT_F32, (double)-3.4028234663852886e38f, out)) return rc;
+  const double t3 = now();
+  printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
 int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile, float thresh, int usemask) try {
   printf("Threshold version %s\n", td_version());
   const double t0 = now();

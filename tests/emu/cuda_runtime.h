@@ -119,6 +119,7 @@ inline void __threadfence_block() {}
 inline void __threadfence_system() { emu::yield(); }
 inline void __nanosleep(unsigned) { emu::yield(); }
 template <typename T> inline T __ldcg(const T* p) { emu::yield(); return *p; }
+template <typename T> inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline long long clock64() { return 0; }

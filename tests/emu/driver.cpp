@@ -119,6 +119,10 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
 }
 }  // namespace
 
+static const float* g_dm = nullptr;
+static float g_dm_nodata = -9999.0f;
+extern "C" void emu_set_dm(const float* dm, float nodata) { g_dm = dm; g_dm_nodata = nodata; }
+
 // mode 0: k_ready + k_walk from the sources; mode 1: `passes` level passes first.  nstrips > 1 emulates the
 // exchange rounds of taudem_b200/dist.py::DistTools._sweep (linearpart partition, halo counts, area rows).
 extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float* out, const float* wgt, int nx, int ny, float dir_nodata,
@@ -160,8 +164,16 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   }
   // mode 10 / 11: the extreme-value algebra of d8flowpathextremeup (largest / smallest value of the `wgt` grid on the flow paths above a cell;
   // single strip: the exchange of halo areas with the -FLT_MAX nodata is the row-strip driver's business)
-  const int alg = mode == 10 ? 1 : mode == 11 ? 2 : 0;
+  // mode 12: the decaying accumulation of dinfdecayaccum (D-infinity, multiplier grid from emu_set_dm; single strip)
+  const int alg = mode == 10 ? 1 : mode == 11 ? 2 : mode == 12 ? 3 : 0;
   if (alg) for (auto& T : S) std::fill(T.area.begin(), T.area.end(), -3.4028234663852886e38f);
+  std::vector<float> dmstrip;
+  if (alg == 3) {
+    if (!g_dm || nstrips != 1 || !dinf) return 3;
+    const Strip& s = S[0].s;
+    dmstrip.assign((size_t)s.cells(), 0.f);
+    for (int r = 1; r <= s.ny; ++r) for (int c = 0; c < nx; ++c) dmstrip[s.idx(r, c)] = g_dm[(size_t)(r - 1) * nx + c];
+  }
   bool first = true;
   int rounds = 0;
   for (auto& T : S) { td::make_prop_row(T.theta[0], true, &T.ctx.prop); T.ctx.dx0 = dx; T.ctx.sweep_dinf = dinf ? 1 : 0; }
@@ -171,7 +183,7 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
       int rc = first ? td::wsweep_begin(&T.ctx, T.s, nullptr) : 0;
       if (!rc)
         rc = td::wsweep_run(&T.ctx, dinf != 0, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew, contcheck,
-                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr, alg);
+                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr, alg, alg == 3 ? dmstrip.data() : nullptr, g_dm_nodata);
       if (rc) return rc;
     }
     first = false;

@@ -74,7 +74,7 @@ extern "C" int emu_deps_dinf(const float* ang, unsigned short* node, unsigned ch
   Grid g(nx, ny, dx, dy);
   auto a = g.in(ang);
   std::vector<unsigned short> nd((size_t)g.s.cells(), 0); std::vector<unsigned char> cn((size_t)g.s.cells() + 4, 0); std::vector<float> ar((size_t)g.s.cells(), 0.f);
-  td::launch_deps_dinf(a.data(), nd.data(), cn.data(), ar.data(), g.s, nodata, g.th.data(), nullptr);
+  td::launch_deps_dinf(a.data(), nd.data(), cn.data(), ar.data(), g.s, nodata, g.th.data(), nullptr, -1.0f);
   g.out(nd, node); g.out(cn, cnt); g.out(ar, area);
   return 0;
 }

@@ -60,6 +60,8 @@ def _build(tag="", defines=()):
     lib.emu_sweep.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                               C.c_float, C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     P = C.c_void_p
+    lib.emu_set_dm.argtypes = [C.c_void_p, C.c_float]
+    lib.emu_set_dm.restype = None
     lib.emu_d8_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
     lib.emu_dinf_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
     lib.emu_deps_d8.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_short]
@@ -142,6 +144,23 @@ def test_emulated_d8_flow_path_extreme_up(emu, fields):
     R = refrun.RefPipeline()
     assert_bits(_run(emu, False, 10, 0, p, sa, True, 31), R.d8flowpathextremeup(p, sa, usemax=True), "ssa max")
     assert_bits(_run(emu, False, 11, 0, p, sa, False, 32), R.d8flowpathextremeup(p, sa, usemax=False, contcheck=False), "ssa min -nc")
+
+
+def test_emulated_dinf_decay_accumulation(emu, fields):
+    """dinfdecayaccum = the D-infinity sweep with the decaying-accumulation algebra, against the reference executable
+    (oracle/_ref/dinfdecayaccum: dinfdecayaccum.cpp compiled unchanged)."""
+    import refrun
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "dinfdecayaccum"), os.X_OK):
+        pytest.skip("oracle/_ref/dinfdecayaccum is not built")
+    port, _, ang, w = fields
+    rng = np.random.default_rng(17)
+    dm = rng.uniform(0.2, 1.0, ang.shape).astype(np.float32)
+    dm[rng.random(ang.shape) < 0.002] = -9999.0              # nodata multipliers contaminate what they feed
+    dmc = np.ascontiguousarray(dm)
+    emu.emu_set_dm(dmc.ctypes.data, C.c_float(-9999.0))
+    R = refrun.RefPipeline()
+    assert_bits(_run(emu, True, 12, 0, ang, None, True, 41), R.dinfdecayaccum(ang, dm), "dsca")
+    assert_bits(_run(emu, True, 12, 0, ang, w, False, 42), R.dinfdecayaccum(ang, dm, weights=w, contcheck=False), "dsca -wg -nc")
 
 
 def test_emulated_small_stacks_spill(fields):

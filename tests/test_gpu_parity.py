@@ -358,6 +358,40 @@ def test_d8_flow_path_extreme_up(refrun, tmp_path):
     assert_bits(td.read_raster(out), ref, "d8flowpathextremeup -o (files)")
 
 
+def test_dinf_decay_accumulation(refrun, tmp_path):
+    """dinfdecayaccum (a sibling of areadinf on the same sweep) against the reference executable
+    (oracle/_ref/dinfdecayaccum): plain, weights + -nc, nodata multipliers, outlets; grid level and our executable, bit for bit."""
+    import os
+    import subprocess
+    from util import write_point_shapefile
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "dinfdecayaccum"), os.X_OK):
+        pytest.skip("oracle/_ref/dinfdecayaccum is not built")
+    dem = synth.punch_holes(synth.gen_dem(330, 410, hurst=0.8, tilt=1.0, seed=43))
+    fel = td.pitremove_grid(dem); ang, slp = td.dinfflowdir_grid(fel)
+    rng = np.random.default_rng(9)
+    dm = rng.uniform(0.3, 1.0, ang.shape).astype(np.float32)
+    dm[rng.random(ang.shape) < 0.001] = -9999.0
+    w = rng.uniform(0.0, 2.0, ang.shape).astype(np.float32)
+    R = refrun.RefPipeline(workdir=str(tmp_path))
+    assert_bits(td.dinfdecayaccum_grid(ang, dm), R.dinfdecayaccum(ang, dm), "dsca")
+    assert_bits(td.dinfdecayaccum_grid(ang, dm, weights=w, contcheck=False), R.dinfdecayaccum(ang, dm, weights=w, contcheck=False), "dsca -wg -nc")
+    ny, nx = ang.shape
+    order = np.argsort(td.areadinf_grid(ang, contcheck=False).ravel())
+    cells = [int(order[-1]), int(order[-40]), int(order[-700])]
+    cols = [c % nx for c in cells]; rows = [c // nx for c in cells]
+    dx = dy = 30.0
+    shp = str(tmp_path / "outlets.shp")
+    write_point_shapefile(shp, [(c + 0.5) * dx for c in cols], [dy * ny - (r + 0.5) * dy for r in rows])
+    ref = R.dinfdecayaccum(ang, dm, outlets=shp)
+    assert_bits(td.dinfdecayaccum_grid(ang, dm, outlets=(cols, rows)), ref, "dsca -o")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "ours_dsca.tif")
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "dinfdecayaccum"), "-ang", str(tmp_path / "angin.tif"), "-dm", str(tmp_path / "dm.tif"),
+                        "-dsca", out, "-o", shp], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert_bits(td.read_raster(out), ref, "dinfdecayaccum -o (files)")
+
+
 def test_pointwise_consumers_threshold_and_twi(refrun, tmp_path):
     """threshold and twi on the rasters of the path: grid level and our executables against the
     reference executables (oracle/_ref/threshold, oracle/_ref/twi: Threshold.cpp / TWI.cpp compiled unchanged).  src is
