@@ -456,7 +456,11 @@ def files_mode(args):
                 first = out
             else:
                 same = filecmp.cmp(first, out, shallow=False)
-            rows.append({"tool": tool, "impl": "ours", "ranks": k, "rc": rr.returncode, "wall_s": round(wall, 3), "tool_times_s": tm, "file_identical_to_1_rank": same})
+            row = {"tool": tool, "impl": "ours", "ranks": k, "rc": rr.returncode, "wall_s": round(wall, 3), "tool_times_s": tm, "file_identical_to_1_rank": same}
+            trace = [(round(float(m.group(1)) - t0, 3), m.group(2)) for m in re.finditer(r"^\[td trace\] ([0-9.]+) (.*)$", rr.stdout, re.M)]
+            if trace:
+                row["trace_s_after_launch"] = trace
+            rows.append(row)
         if not args.no_cpu:
             sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle"))
             import refrun

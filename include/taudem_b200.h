@@ -116,6 +116,15 @@ int td_dmarea(const char* angfile, const char* adecfile, const char* dmfile, con
 int td_dinfdecayaccum_host(const float* ang, const float* dm, const float* w /*NULL unless usew*/, float* dsca, int nx, int ny, float ang_nodata,
                            float dm_nodata, const double* dxc, const double* dyc, int contcheck, const int* outlet_cols, const int* outlet_rows,
                            int nout /* < 0: no outlets */);
+/* Sibling of aread8 on the same sweep: gridnet.  File level = `int gridnet(char* pfile, char* plenfile, char* tlenfile, char* gordfile,
+ * char* maskfile, char* datasrc, char* lyrname, int uselyrname, int lyrno, int useMask, int useOutlets, int thresh)`
+ * (src/gridnet.cpp:55); plen / tlen: float32, nodata -1; gord: int16, nodata -1.  mask (int32, NULL = none): only cells with
+ * mask >= thresh are evaluated and contribute (src/gridnet.cpp:383-399).  Inputs are D8 rasters as d8flowdir writes them (no
+ * direction on the grid's edge cells: the reference reads stale temporaries for neighbours beyond the left / right edge). */
+int td_gridnet(const char* pfile, const char* plenfile, const char* tlenfile, const char* gordfile, const char* maskfile, const char* datasrc,
+               const char* lyrname, int uselyrname, int lyrno, int useMask, int useOutlets, int thresh);
+int td_gridnet_host(const int16_t* p, const int32_t* mask /*NULL unless useMask*/, int thresh, float* plen, float* tlen, int16_t* gord, int nx, int ny,
+                    int16_t p_nodata, const double* dxc, const double* dyc, const int* outlet_cols, const int* outlet_rows, int nout /* < 0: no outlets */);
 int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile, float thresh, int usemask);
 int td_twigrid(const char* slopefile, const char* areafile, const char* twifile);
 int td_threshold_host(const float* ssa, const float* mask /*NULL unless usemask*/, int16_t* src, int nx, int ny, float thresh, float ssa_nodata);

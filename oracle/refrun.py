@@ -115,6 +115,17 @@ class RefPipeline:
         _, self.times["d8flowpathextremeup"] = run_tool("d8flowpathextremeup", args, self.np_ranks)
         return self.get("ssa_up.tif", np.float32)
 
+    def gridnet(self, p, mask=None, thresh=0, outlets=None, nodata=-32768):
+        self.put("pin.tif", p.astype(np.int16), nodata)
+        args = ["-p", self.path("pin.tif"), "-plen", self.path("plen.tif"), "-tlen", self.path("tlen.tif"), "-gord", self.path("gord.tif")]
+        if outlets is not None:
+            args += ["-o", outlets]
+        if mask is not None:
+            self.put("mask.tif", mask.astype(np.int32), -1)
+            args += ["-mask", self.path("mask.tif"), "-thresh", str(int(thresh))]
+        _, self.times["gridnet"] = run_tool("gridnet", args, self.np_ranks)
+        return self.get("plen.tif", np.float32), self.get("tlen.tif", np.float32), self.get("gord.tif", np.int16)
+
     def dinfdecayaccum(self, ang, dm, weights=None, contcheck=True, outlets=None, nodata=-3.4028234663852886e38, dm_nodata=-9999.0, w_nodata=-9999.0):
         self.put("angin.tif", ang, nodata); self.put("dm.tif", dm, dm_nodata)
         args = ["-ang", self.path("angin.tif"), "-dm", self.path("dm.tif"), "-dsca", self.path("dsca.tif")]

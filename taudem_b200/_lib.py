@@ -41,6 +41,8 @@ SIGNATURES = {
     "td_area": (_I, [_S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
     "td_d8flowpathextremeup": (_I, [_S, _S, _S, _I, _S, _S, _I, _I, _I, _I]),
     "td_d8flowpathextremeup_host": (_I, [_P, _P, _P, _I, _I, C.c_int16, _I, _I, _P, _P, _I]),
+    "td_gridnet": (_I, [_S, _S, _S, _S, _S, _S, _S, _I, _I, _I, _I, _I]),
+    "td_gridnet_host": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, C.c_int16, _P, _P, _P, _P, _I]),
     "td_dmarea": (_I, [_S, _S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
     "td_dinfdecayaccum_host": (_I, [_P, _P, _P, _P, _I, _I, C.c_float, C.c_float, _P, _P, _I, _P, _P, _I]),
     "td_threshold": (_I, [_S, _S, _S, _F, _I]),

@@ -165,6 +165,21 @@ def d8flowpathextremeup_grid(p, sa, usemax=True, nodata=int(MISSINGSHORT), contc
     return ssa
 
 
+def gridnet_grid(p, mask=None, thresh=0, dx=30.0, dy=30.0, nodata=int(MISSINGSHORT), outlets=None, dxc=None, dyc=None):
+    """(plen, tlen, gord): longest and total upstream path length and Strahler order of the D8 flow field (td_gridnet_host;
+    src/gridnet.cpp:383-420).  mask (int32): only cells with mask >= thresh are evaluated and contribute.  nodata = -1."""
+    p = _grid(p, np.int16)
+    ny, nx = p.shape
+    m = None if mask is None else _grid(mask, np.int32)
+    dxc = _rows(dx, ny) if dxc is None else np.ascontiguousarray(dxc, np.float64)
+    dyc = _rows(dy, ny) if dyc is None else np.ascontiguousarray(dyc, np.float64)
+    plen = np.empty((ny, nx), np.float32); tlen = np.empty((ny, nx), np.float32); gord = np.empty((ny, nx), np.int16)
+    oc, orow, nout = _outlet_args(outlets)
+    check(lib().td_gridnet_host(_ptr(p), _ptr(m), int(thresh), _ptr(plen), _ptr(tlen), _ptr(gord), nx, ny, int(nodata), _ptr(dxc), _ptr(dyc),
+                                _ptr(oc), _ptr(orow), nout))
+    return plen, tlen, gord
+
+
 def dinfdecayaccum_grid(ang, dm, weights=None, dx=30.0, dy=30.0, nodata=float(MISSINGFLOAT), dm_nodata=-9999.0, contcheck=True, outlets=None,
                         dxc=None, dyc=None):
     """Decaying accumulation on the D-infinity flow field (td_dinfdecayaccum_host; src/dinfdecayaccum.cpp:205-235): a cell starts from

@@ -549,6 +549,60 @@ int td_dinfdecayaccum_host(const float* ang, const float* dm, const float* w, fl
   return TD_OK;
 }
 
+// gridnet (src/gridnet.cpp:55): longest upstream path length, total upstream path length and Strahler order of the D8 flow
+// field — three runs of the D8 sweep, one value per cell each (algebras 4, 5, 6).  Single strip.
+int td_gridnet_host(const int16_t* p, const int32_t* mask, int thresh, float* plen, float* tlen, int16_t* gord, int nx, int ny, int16_t p_nodata,
+                    const double* dxc, const double* dyc, const int* outlet_cols, const int* outlet_rows, int nout) {
+  if (int rc = need_device()) return rc;
+  if (!p || !plen || !tlen || !gord || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_gridnet_host: bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const Strip ss(s);
+  const size_t n = (size_t)ss.cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 2)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[3].ensure(n * 4));
+  int16_t* d_p = ctx->io[0].as<int16_t>(); float* d_a = ctx->io[1].as<float>(); float* d_ok = nullptr;
+  TD_CUDA(h2d(d_p, p, s, st));
+  if (mask) {
+    TD_CUDA(ctx->io[2].ensure(n * 4));
+    int* d_m = ctx->io[2].as<int>();
+    TD_CUDA(h2d(d_m, mask, s, st));
+    d_ok = ctx->io[3].as<float>();
+    if (int rc = td::launch_mask_ok(d_m, d_ok, ss, thresh, st)) return rc;
+  }
+  // dist[row][k] = sqrt(dxc^2 d1[k]^2 + dyc^2 d2[k]^2) as float (src/gridnet.cpp:190-200)
+  std::vector<float> dist((size_t)ny * 8);
+  static const int d1[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1}, d2[9] = {0, 0, -1, -1, -1, 0, 1, 1, 1};
+  for (int m = 0; m < ny; ++m)
+    for (int k = 1; k <= 8; ++k) dist[(size_t)m * 8 + k - 1] = (float)sqrt(dxc[m] * dxc[m] * d1[k] * d1[k] + dyc[m] * dyc[m] * d2[k] * d2[k]);
+  TD_CUDA(ctx->rows.ensure(sizeof(float) * dist.size()));
+  float* d_dist = ctx->rows.as<float>();
+  TD_CUDA(cudaMemcpyAsync(d_dist, dist.data(), sizeof(float) * dist.size(), cudaMemcpyHostToDevice, st));
+  Timer t; t.start(st);
+  if (int rc = ensure_dep_state(ctx, ss, st)) return rc;
+  ctx->sweep_dinf = 0;
+  for (int alg = 4; alg <= 6; ++alg) {
+    TD_CUDA(td::launch_deps_d8(d_p, ctx->node.as<unsigned short>(), ctx->cnt.as<unsigned char>(), d_a, ss, p_nodata, st, -1.0f));
+    if (nout >= 0) { if (int rc = td_sweep_restrict_dev(ctx, s, outlet_cols, outlet_rows, nout, st)) return rc; }
+    if (int rc = td::wsweep_begin(ctx, ss, st)) return rc;
+    // cells outside the mask: not evaluated — plen / tlen stay nodata; gord keeps what the start gave it: 1 if upstream of an outlet
+    // (src/gridnet.cpp:296), nodata otherwise
+    const float skip = (alg == 6 && nout >= 0) ? 1.0f : -1.0f;
+    if (int rc = td::wsweep_run(ctx, false, d_a, nullptr, nullptr, ss, skip, 0, 0, nullptr, nullptr, ctx->halo.as<int>(), st, alg, d_ok, 0.f, d_dist)) return rc;
+    if (alg == 4) TD_CUDA(d2h(plen, d_a, s, st));
+    else if (alg == 5) TD_CUDA(d2h(tlen, d_a, s, st));
+    else {
+      TD_CUDA(ctx->io[2].ensure(n * 2));
+      int16_t* d_g = ctx->io[2].as<int16_t>();
+      if (int rc = td::launch_gord_finish(d_a, d_p, d_g, ss, p_nodata, nout >= 0 ? 1 : 0, st)) return rc;
+      TD_CUDA(d2h(gord, d_g, s, st));
+    }
+  }
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
 // ---- point-wise consumers (pointwise.cu): device-strip and host-grid level
 int td_threshold_dev(td_ctx*, const float* ssa, const float* mask, int16_t* src, td_strip s, float thresh, float ssa_nodata, void* stream) {
   if (int rc = check_strip(s)) return rc;

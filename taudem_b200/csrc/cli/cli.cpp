@@ -196,6 +196,36 @@ int main(int argc, char** argv) {
   return done();
 }
 
+#elif defined(TOOL_gridnet)
+// src/gridnetmn.cpp:51-215
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("The following are appended to the file names\nbefore the files are opened:\n");
+  printf("p   D8 flow direction output file\nplen   the longest flow length upstream of each point output file.\n");
+  printf("tlen   the total path length upstream of each point output file.\ngord   the grid of strahler order output file.\n\n");
+  printf("Usage with specific file names:\n %s -p <pfile>\n", prog);
+  printf("-plen <plenfile> -tlen <tlenfile> -gord <gordfile> [-o <outletfine>] [-lyrname <layer name>] [-lyrno <layer number>] [-mask <maskfile> [-thresh <threshold>]]\n");
+  printf("<pfile> is the D8 flow direction input file.\n");
+  printf("[-mask <maskfile> [-thresh <threshold>]].  maskfile is an optional mask grid input file; the grid network is evaluated for\n");
+  printf("grid cells where values of the maskfile grid read as 4 byte integers are >= threshold.\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char pf[MAXLN], plen[MAXLN], tlen[MAXLN], gord[MAXLN], maskfile[MAXLN], datasrc[MAXLN], lyrname[MAXLN];
+  int useOutlets = 0, uselyrname = 0, useMask = 0, lyrno = 0, thresh = 0, havethresh = 0;
+  if (argc < 2) usage(argv[0]);
+  Opt opts[] = {{"-p", 0, pf, NULL, 0}, {"-plen", 0, plen, NULL, 0}, {"-tlen", 0, tlen, NULL, 0}, {"-gord", 0, gord, NULL, 0}, {"-o", 0, datasrc, &useOutlets, 1},
+                {"-lyrno", 2, NULL, &lyrno, 0}, {"-lyrname", 0, lyrname, &uselyrname, 1}, {"-mask", 0, maskfile, &useMask, 1}, {"-thresh", 2, NULL, &thresh, 0}};
+  parse(argc, argv, opts, 9);
+  for (int i = 1; i < argc; ++i) if (strcmp(argv[i], "-thresh") == 0) havethresh = 1;
+  if (useMask && !havethresh) usage(argv[0]);          // src/gridnetmn.cpp:160-166: -mask must be followed by -thresh
+  if (argc == 2) { td_nameadd(pf, argv[1], "p"); td_nameadd(plen, argv[1], "plen"); td_nameadd(tlen, argv[1], "tlen"); td_nameadd(gord, argv[1], "gord"); }
+  int err = td_gridnet(pf, plen, tlen, gord, maskfile, datasrc, lyrname, uselyrname, lyrno, useMask, useOutlets, thresh);
+  if (err != 0) printf("gridnet error %d\n", err);
+  return done();
+}
+
 #elif defined(TOOL_dinfdecayaccum)
 // src/DinfDecayAccummn.cpp:51-192
 static void usage(const char* prog) {

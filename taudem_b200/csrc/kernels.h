@@ -21,7 +21,7 @@ int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
 int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
                int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg = 0, const float* dm = nullptr,
-               float dm_nodata = 0.f);
+               float dm_nodata = 0.f, const float* dist = nullptr);
 int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, const int* in_top, const int* in_bot,
                          int* req_out, int finish, cudaStream_t st);
 int sweep_restrict_upstream(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, cudaStream_t st);
@@ -33,6 +33,8 @@ int fill_init(const float* dem, const short* mask, float* W, const Strip& s, flo
 int fill_relax(td_ctx* ctx, const float* dem, float* W, const Strip& s, int four, int* changed, cudaStream_t st, bool edges_only = false);
 int launch_threshold(const float* ssa, const float* mask, short* src, const Strip& s, float thresh, float ssa_nodata, cudaStream_t st);
 int launch_twi(const float* slp, const float* sca, float* twi, const Strip& s, float slp_nodata, float sca_nodata, cudaStream_t st);
+int launch_mask_ok(const int* mask, float* ok, const Strip& s, int thresh, cudaStream_t st);
+int launch_gord_finish(const float* g, const short* p, short* gord, const Strip& s, short p_nodata, int outlets, cudaStream_t st);
 cudaError_t launch_gen_dem(float* dem, const Strip& s, int row0, int total_ny, unsigned seed, float hurst, float tilt, cudaStream_t st);
 cudaError_t launch_gen_w(float* w, const Strip& s, int row0, unsigned seed, cudaStream_t st);
 }  // namespace td

@@ -42,7 +42,46 @@ __global__ void __launch_bounds__(256) k_twi(const float* __restrict__ slp, cons
   }
   *reinterpret_cast<float4*>(twi + o) = make_float4(out[0], out[1], out[2], out[3]);
 }
+// gridnet's mask rule (src/gridnet.cpp:383: maskData >= thresh, the mask read as 32-bit integers) as a 0 / 1 float grid
+__global__ void __launch_bounds__(256) k_mask_ok(const int* __restrict__ mask, float* __restrict__ ok, Strip s, int thresh) {
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;
+  if (c >= s.pitch) return;
+  const long long o = s.idx(r, c);
+  const int4 m = *reinterpret_cast<const int4*>(mask + o);
+  *reinterpret_cast<float4*>(ok + o) = make_float4(m.x >= thresh ? 1.f : 0.f, m.y >= thresh ? 1.f : 0.f, m.z >= thresh ? 1.f : 0.f, m.w >= thresh ? 1.f : 0.f);
+}
+// Strahler orders of the sweep (float, -1 = never evaluated) -> int16 like the reference's gord partition: with outlets every cell
+// with a flow direction starts at 0 (src/gridnet.cpp:262-267), without them cells outside the evaluation stay nodata (-1)
+__global__ void __launch_bounds__(256) k_gord_finish(const float* __restrict__ g, const short* __restrict__ p, short* __restrict__ gord, Strip s,
+                                                     short p_nodata, int outlets) {
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;
+  if (c >= s.pitch) return;
+  const long long o = s.idx(r, c);
+  const float4 v = *reinterpret_cast<const float4*>(g + o);
+  const short4 d = *reinterpret_cast<const short4*>(p + o);
+  const float a[4] = {v.x, v.y, v.z, v.w};
+  const short dd[4] = {d.x, d.y, d.z, d.w};
+  short out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = a[i] >= 0.f ? (short)a[i] : (short)((outlets && !nd_s(dd[i], p_nodata)) ? 0 : -1);
+  *reinterpret_cast<short4*>(gord + o) = make_short4(out[0], out[1], out[2], out[3]);
+}
 }  // namespace
+
+int launch_mask_ok(const int* mask, float* ok, const Strip& s, int thresh, cudaStream_t st) {
+  const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
+  k_mask_ok<<<grid, 256, 0, st>>>(mask, ok, s, thresh);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+int launch_gord_finish(const float* g, const short* p, short* gord, const Strip& s, short p_nodata, int outlets, cudaStream_t st) {
+  const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
+  k_gord_finish<<<grid, 256, 0, st>>>(g, p, gord, s, p_nodata, outlets);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
 
 int launch_threshold(const float* ssa, const float* mask, short* src, const Strip& s, float thresh, float ssa_nodata, cudaStream_t st) {
   const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));

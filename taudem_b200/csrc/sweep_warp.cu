@@ -105,7 +105,8 @@ struct WArgs {
   const double* dxc;
   int* halo;
   int ntx, nty, th;        // tiles of the strip, tile height
-  const float* dm; float dm_nodata;   // ALG 3: the decay multiplier grid (strip layout) and its nodata
+  const float* dm; float dm_nodata;   // ALG 3: the decay multiplier grid (strip layout) and its nodata; ALG 4-6: the mask grid (0 = outside) or NULL
+  const float* dist;                  // ALG 4-6: cell-to-cell distances, [row][direction - 1] (float, like src/gridnet.cpp:190-200)
   int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;          // slots of one shard's ring - 1
@@ -357,7 +358,33 @@ __device__ __forceinline__ unsigned zero_nibble(unsigned w) {
 // largest / smallest value of `w` on the flow paths above each cell (d8flowpathextremeup, src/D8flowpathextremeup.cpp:182-215);
 // D-infinity only: 3 = decaying accumulation (dinfdecayaccum, src/dinfdecayaccum.cpp:205-235: the cell's own input first, then
 // per contributor  + (float)(dm * area * p)  with the contributor's decay multiplier dm; a nodata multiplier contaminates).
-// Results of ALG != 0 use MISSINGFLOAT as nodata.
+// D8 only: 4 / 5 / 6 = gridnet's longest upstream path length, total upstream path length and Strahler order (src/gridnet.cpp:383-420;
+// three sweeps, one value each; `dm` = mask grid: cells outside are not evaluated (they get w_nodata) and contribute nothing).
+// Results of ALG 1-3 use MISSINGFLOAT as nodata, the others -1.
+// gridnet's cell evaluation (src/gridnet.cpp:383-420): contributors = the neighbours that drain into the cell (mask bits) with a
+// direction > 0 and inside the mask; all arithmetic in float like the reference's float dist table and float partitions.
+template <int ALG, typename Mem>
+__device__ __forceinline__ float gridnet_eval(const WArgs& a, const Mem& M, int ri, unsigned msk, int r, int c) {
+  const Strip& s = a.s;
+  if (a.dm && a.dm[s.idx(r, c)] == 0.f) return a.w_nodata;             // outside the mask: not evaluated
+  const float* drowp = a.dist + (size_t)(min(r, s.ny) - 1) * 8;
+  float val = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+  for (int k = 1; k <= 8; ++k) {
+    if (!(msk & (1u << (k - 1)))) continue;
+    const int ni = ri + drow(k) * RS + dcol(k);
+    if ((((unsigned)M.node[ni] >> 8) & 0xfu) == 0u) continue;           // sdir > 0 (a direction code 0 counts as a dependency only)
+    if (a.dm && a.dm[s.idx(r + drow(k), c + dcol(k))] == 0.f) continue;
+    const float an = M.area[ni];
+    const float d = drowp[k - 1];                                       // dist[j][sdir] = dist[j][k]: the same two cells
+    if (ALG == 4) { const float ld = an + d; if (ld > val) val = ld; }
+    else if (ALG == 5) val = val + (an + d);
+    else { if (an >= a1) { a2 = a1; a1 = an; } else if (an > a2) a2 = an; }
+  }
+  if (ALG == 6) val = (a2 + 1.f > a1) ? a2 + 1.f : a1;
+  return val;
+}
+
 template <bool DINF, bool USEW, int ALG>
 __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(const WArgs a) {
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -368,7 +395,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
   const unsigned lt = (1u << lane) - 1u;
   Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
   const int myq = (int)((blockIdx.x * (blockDim.x >> 5) + (unsigned)wid) & (unsigned)(a.nsh - 1));   // this worker's queue shard
-  const float NOD = ALG == 0 ? -1.0f : TD_MISSINGFLOAT;      // the result raster's nodata: not evaluated / contaminated
+  const float NOD = (ALG == 0 || ALG >= 4) ? -1.0f : TD_MISSINGFLOAT;      // the result raster's nodata: not evaluated / contaminated
   __shared__ Sector sect[9];
   if (DINF) {
     if (threadIdx.x < 9) { const int j = (int)threadIdx.x; sect[j].lo = a.prop.ar[j]; sect[j].hi = a.prop.ar[j + 1]; sect[j].den = a.prop.den[j]; sect[j].rden = a.prop.rden[j]; }
@@ -496,7 +523,8 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           bool con = (nd & NODE_CON) != 0;
           float val;
           if (!DINF) {
-            if (USEW) {
+            if (ALG >= 4) val = gridnet_eval<ALG>(a, M, ri, msk, r0 + lr, c0 + lx);
+            else if (USEW) {
               val = (ALG == 0 && nd_f(wv, a.w_nodata)) ? -1.0f : wv;
 #pragma unroll
               for (int k = 1; k <= 8; ++k)
@@ -615,7 +643,8 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
         int cont = -1;
         if (!DINF) {
           // src/aread8.cpp:228-257
-          if (USEW) {
+          if (ALG >= 4) val = gridnet_eval<ALG>(a, M, ri, msk, r0 + lr, c0 + lx);
+          else if (USEW) {
             val = (ALG == 0 && nd_f(wv, a.w_nodata)) ? -1.0f : wv;
 #pragma unroll
             for (int k = 1; k <= 8; ++k)
@@ -836,7 +865,7 @@ __global__ void k_wsched_reset(unsigned long long* ctr) { for (int i = threadIdx
 
 int wargs(td_ctx* ctx, WArgs& a, const Strip& s) {
   a.s = s;
-  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr; a.dm = nullptr; a.dm_nodata = 0.f;
+  a.area = nullptr; a.w = nullptr; a.ang = nullptr; a.dx0 = 0.; a.usew = 0; a.contcheck = 1; a.w_nodata = 0.f; a.theta = nullptr; a.dxc = nullptr; a.halo = nullptr; a.dm = nullptr; a.dm_nodata = 0.f; a.dist = nullptr;
   a.th = ctx->sweep_dinf ? tile_h<true>() : tile_h<false>();      // the tile height goes with the dependency state that is loaded
   a.ntx = (s.nx + TS - 1) / TS; a.nty = (s.ny + a.th - 1) / a.th;
   a.stats = 0; a.poll = 0; a.exp = 0;
@@ -891,15 +920,16 @@ int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int
 
 // Runs the evaluation wavefront over the queued tiles until no tile of the strip has a ready cell left.
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
-               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg, const float* dm, float dm_nodata) {
-  if (alg < 0 || alg > 3 || ((alg == 1 || alg == 2) && (dinf || !usew)) || (alg == 3 && (!dinf || !dm))) {
+               int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg, const float* dm, float dm_nodata,
+               const float* dist) {
+  if (alg < 0 || alg > 6 || ((alg == 1 || alg == 2) && (dinf || !usew)) || (alg == 3 && (!dinf || !dm)) || (alg >= 4 && (dinf || usew || !dist))) {
     set_error("wsweep_run: the extreme-value algebra is a D8 sweep over a value grid, the decaying accumulation a D-infinity sweep with a multiplier grid");
     return TD_ERR_ARG;
   }
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
-  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo; a.dm = dm; a.dm_nodata = dm_nodata;
+  a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo; a.dm = dm; a.dm_nodata = dm_nodata; a.dist = dist;
   a.prop = ctx->prop;
   if (!dinf) a.prop.uniform = 0;
   a.peer = ctx->peer_on;
@@ -924,11 +954,13 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   if (const char* we = getenv("TAUDEM_B200_WORKERS")) { const int v = atoi(we); if (v >= 1 && v < warps) warps = v; }   // experiments: fewer workers per SM
   size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
   if (const char* pe2 = getenv("TAUDEM_B200_SMEMPAD")) smem = std::max(smem, (size_t)atoi(pe2));                  // experiments: one CTA per SM whatever its size
-  const void* kern = alg == 3 ? (usew ? (const void*)k_sweep_warp<true, true, 3> : (const void*)k_sweep_warp<true, false, 3>)
+  const void* kern = alg == 4 ? (const void*)k_sweep_warp<false, false, 4> : alg == 5 ? (const void*)k_sweep_warp<false, false, 5>
+                   : alg == 6 ? (const void*)k_sweep_warp<false, false, 6>
+                   : alg == 3 ? (usew ? (const void*)k_sweep_warp<true, true, 3> : (const void*)k_sweep_warp<true, false, 3>)
                    : dinf ? (usew ? (const void*)k_sweep_warp<true, true, 0> : (const void*)k_sweep_warp<true, false, 0>)
                           : alg == 1 ? (const void*)k_sweep_warp<false, true, 1> : alg == 2 ? (const void*)k_sweep_warp<false, true, 2>
                           : (usew ? (const void*)k_sweep_warp<false, true, 0> : (const void*)k_sweep_warp<false, false, 0>);
-  int& per_dev = ctx->wgrid[alg == 3 ? 6 + (usew ? 1 : 0) : alg ? 3 + alg : (dinf ? 2 : 0) + (usew ? 1 : 0)];
+  int& per_dev = ctx->wgrid[alg >= 4 ? 4 + alg : alg == 3 ? 6 + (usew ? 1 : 0) : alg ? 3 + alg : (dinf ? 2 : 0) + (usew ? 1 : 0)];
   if (!per_dev || getenv("TAUDEM_B200_WORKERS")) {
     int dev = 0, sms = 0, occ = 0;
     TD_CUDA(cudaGetDevice(&dev));
@@ -940,7 +972,10 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   }
   const long long nt = (long long)a.ntx * a.nty;
   const int g = (int)std::min<long long>(per_dev, (nt + warps - 1) / warps);
-  if (alg == 3) { if (usew) k_sweep_warp<true, true, 3><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 3><<<g, warps * 32, smem, st>>>(a); }
+  if (alg == 4) k_sweep_warp<false, false, 4><<<g, warps * 32, smem, st>>>(a);
+  else if (alg == 5) k_sweep_warp<false, false, 5><<<g, warps * 32, smem, st>>>(a);
+  else if (alg == 6) k_sweep_warp<false, false, 6><<<g, warps * 32, smem, st>>>(a);
+  else if (alg == 3) { if (usew) k_sweep_warp<true, true, 3><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 3><<<g, warps * 32, smem, st>>>(a); }
   else if (dinf) { if (usew) k_sweep_warp<true, true, 0><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 0><<<g, warps * 32, smem, st>>>(a); }
   else if (alg == 1) k_sweep_warp<false, true, 1><<<g, warps * 32, smem, st>>>(a);
   else if (alg == 2) k_sweep_warp<false, true, 2><<<g, warps * 32, smem, st>>>(a);

@@ -372,16 +372,16 @@ int td_aread8(const char* pfile, const char* afile, const char* datasrc, const c
     if (int rc = w.read(&wg, tdio::DT_F32)) return rc;
   }
   const double t1 = now();
-  std::vector<float> ad8((size_t)p.nx * p.ny);
+  std::unique_ptr<float[]> ad8(new float[(size_t)p.nx * p.ny]);      // not zero-filled: every cell is written by the download
   warm.join();
-  if (int rc = td_aread8_outlets_host(dir.data(), usew ? wg.data() : nullptr, ad8.data(), p.nx, p.ny, (int16_t)p.r.nodata(),
+  if (int rc = td_aread8_outlets_host(dir.data(), usew ? wg.data() : nullptr, ad8.get(), p.nx, p.ny, (int16_t)p.r.nodata(),
                                       usew ? (float)w.r.nodata() : 0.f, contcheck, ocols.data(), orows.data(),
                                       useOutlets == 1 ? (int)ocols.size() : -1)) {
     printf("AreaD8 device error: %s\n", td_last_error());
     return rc;
   }
   const double t2 = now();
-  if (int rc = write_like(afile, p, tdio::DT_F32, (double)-1.0f, ad8)) return rc;
+  if (int rc = write_like(afile, p, tdio::DT_F32, (double)-1.0f, (const float*)ad8.get())) return rc;
   const double t3 = now();
   printf("Number of Processes: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());
@@ -421,16 +421,16 @@ int td_area(const char* angfile, const char* scafile, const char* datasrc, const
     if (int rc = w.read(&wg, tdio::DT_F32)) return rc;
   }
   const double t1 = now();
-  std::vector<float> sca((size_t)a.nx * a.ny);
+  std::unique_ptr<float[]> sca(new float[(size_t)a.nx * a.ny]);
   warm.join();
-  if (int rc = td_area_outlets_host(ang.data(), usew ? wg.data() : nullptr, sca.data(), a.nx, a.ny, (float)a.r.nodata(),
+  if (int rc = td_area_outlets_host(ang.data(), usew ? wg.data() : nullptr, sca.get(), a.nx, a.ny, (float)a.r.nodata(),
                                     usew ? (float)w.r.nodata() : 0.f, a.dxc.data(), a.dyc.data(), contcheck, ocols.data(), orows.data(),
                                     useOutlets == 1 ? (int)ocols.size() : -1)) {
     printf("AreaDinf device error: %s\n", td_last_error());
     return rc;
   }
   const double t2 = now();
-  if (int rc = write_like(scafile, a, tdio::DT_F32, (double)-1.0f, sca)) return rc;
+  if (int rc = write_like(scafile, a, tdio::DT_F32, (double)-1.0f, (const float*)sca.get())) return rc;
   const double t3 = now();
   printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());
@@ -478,6 +478,46 @@ int td_d8flowpathextremeup(const char* pfile, const char* safile, const char* ss
 }
 
 // src/Threshold.cpp:48-162
+// gridnet (src/gridnet.cpp:55-500)
+int td_gridnet(const char* pfile, const char* plenfile, const char* tlenfile, const char* gordfile, const char* maskfile, const char* datasrc,
+               const char* lyrname, int uselyrname, int lyrno, int useMask, int useOutlets, int thresh) try {
+  printf("GridNet version %s\n", td_version());
+  const double t0 = now();
+  Input p;
+  if (int rc = p.open(pfile)) return rc;
+  std::vector<int> ocols, orows;
+  if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, p, &ocols, &orows)) return rc; }
+  std::vector<int16_t> dir;
+  nodata_msgs(p.r.nodata(), "int16_t", (int16_t)p.r.nodata());
+  if (int rc = p.read(&dir, tdio::DT_I16)) return rc;
+  Input m; std::vector<int32_t> mask;
+  if (useMask == 1) {
+    if (int rc = m.open(maskfile)) return rc;
+    if (!tdio::compare_rasters(p.r, p.path, m.r, m.path)) { printf("File sizes do not match\n%s\n", maskfile); td::set_error("mask grid does not match"); return TD_ERR_MISMATCH; }
+    nodata_msgs(m.r.nodata(), "int32_t", (int32_t)m.r.nodata());
+    if (int rc = m.read(&mask, tdio::DT_I32)) return rc;
+  }
+  const double t1 = now();
+  const size_t n = (size_t)p.nx * p.ny;
+  std::vector<float> plen(n), tlen(n); std::vector<int16_t> gord(n);
+  if (int rc = td_gridnet_host(dir.data(), useMask == 1 ? mask.data() : nullptr, thresh, plen.data(), tlen.data(), gord.data(), p.nx, p.ny, (int16_t)p.r.nodata(),
+                               p.dxc.data(), p.dyc.data(), ocols.data(), orows.data(), useOutlets == 1 ? (int)ocols.size() : -1)) {
+    printf("GridNet device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(gordfile, p, tdio::DT_I16, -1.0, gord)) return rc;
+  if (int rc = write_like(plenfile, p, tdio::DT_F32, (double)-1.0f, plen)) return rc;
+  if (int rc = write_like(tlenfile, p, tdio::DT_F32, (double)-1.0f, tlen)) return rc;
+  const double t3 = now();
+  printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
 // dmarea (src/dinfdecayaccum.cpp:61-323)
 int td_dmarea(const char* angfile, const char* adecfile, const char* dmfile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno,
               const char* wfile, int useOutlets, int usew, int contcheck) try {

@@ -165,11 +165,19 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   // mode 10 / 11: the extreme-value algebra of d8flowpathextremeup (largest / smallest value of the `wgt` grid on the flow paths above a cell;
   // single strip: the exchange of halo areas with the -FLT_MAX nodata is the row-strip driver's business)
   // mode 12: the decaying accumulation of dinfdecayaccum (D-infinity, multiplier grid from emu_set_dm; single strip)
-  const int alg = mode == 10 ? 1 : mode == 11 ? 2 : mode == 12 ? 3 : 0;
-  if (alg) for (auto& T : S) std::fill(T.area.begin(), T.area.end(), -3.4028234663852886e38f);
+  // mode 13 / 14 / 15: gridnet's longest path, total path and Strahler order (D8; the emu_set_dm grid is the 0 / 1 mask, may be unset)
+  const int alg = mode == 10 ? 1 : mode == 11 ? 2 : mode == 12 ? 3 : mode >= 13 && mode <= 15 ? mode - 9 : 0;
+  if (alg >= 1 && alg <= 3) for (auto& T : S) std::fill(T.area.begin(), T.area.end(), -3.4028234663852886e38f);
   std::vector<float> dmstrip;
-  if (alg == 3) {
-    if (!g_dm || nstrips != 1 || !dinf) return 3;
+  std::vector<float> dist;
+  if (alg >= 4) {
+    if (nstrips != 1 || dinf) return 3;
+    static const int e1[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1}, e2[9] = {0, 0, -1, -1, -1, 0, 1, 1, 1};
+    dist.assign((size_t)ny * 8, 0.f);
+    for (int m = 0; m < ny; ++m) for (int k = 1; k <= 8; ++k) dist[(size_t)m * 8 + k - 1] = (float)sqrt(dx * dx * e1[k] * e1[k] + dy * dy * e2[k] * e2[k]);
+  }
+  if (alg == 3 || (alg >= 4 && g_dm)) {
+    if (!g_dm || nstrips != 1) return 3;
     const Strip& s = S[0].s;
     dmstrip.assign((size_t)s.cells(), 0.f);
     for (int r = 1; r <= s.ny; ++r) for (int c = 0; c < nx; ++c) dmstrip[s.idx(r, c)] = g_dm[(size_t)(r - 1) * nx + c];
@@ -183,7 +191,7 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
       int rc = first ? td::wsweep_begin(&T.ctx, T.s, nullptr) : 0;
       if (!rc)
         rc = td::wsweep_run(&T.ctx, dinf != 0, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew, contcheck,
-                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr, alg, alg == 3 ? dmstrip.data() : nullptr, g_dm_nodata);
+                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr, alg, dmstrip.empty() ? nullptr : dmstrip.data(), g_dm_nodata, dist.empty() ? nullptr : dist.data());
       if (rc) return rc;
     }
     first = false;

@@ -163,6 +163,41 @@ def test_emulated_dinf_decay_accumulation(emu, fields):
     assert_bits(_run(emu, True, 12, 0, ang, w, False, 42), R.dinfdecayaccum(ang, dm, weights=w, contcheck=False), "dsca -wg -nc")
 
 
+def test_emulated_gridnet(emu, fields):
+    """gridnet = three D8 sweeps (longest upstream path, total upstream path, Strahler order), against the reference executable
+    (oracle/_ref/gridnet: gridnet.cpp compiled unchanged); with and without a mask grid."""
+    import refrun
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "gridnet"), os.X_OK):
+        pytest.skip("oracle/_ref/gridnet is not built")
+    port, p, _, _ = fields
+    R = refrun.RefPipeline()
+
+    def ours(skip):
+        out = []
+        for mode in (13, 14, 15):
+            ny, nx = p.shape
+            res = np.empty((ny, nx), np.float32)
+            d = np.ascontiguousarray(p)
+            rc = emu.emu_sweep(0, mode, 0, d.ctypes.data, res.ctypes.data, None, nx, ny, -32768.0, 0, 0, skip, 30.0, 30.0, 50 + mode, 1, None, None, None, -1)
+            assert rc == 0
+            out.append(res)
+        return out[0], out[1], out[2].astype(np.int16)
+
+    emu.emu_set_dm(None, C.c_float(0.0))
+    plen, tlen, gord = ours(-1.0)
+    rp, rt, rg = R.gridnet(p)
+    assert_bits(plen, rp, "plen"); assert_bits(tlen, rt, "tlen"); assert_bits(gord, rg, "gord")
+    assert gord.max() >= 3
+    ad8 = port.aread8(p, contcheck=False)
+    mask = np.where(ad8 >= 0, ad8, 0).astype(np.int32)              # "streams": cells with at least 5 cells draining through them
+    ok = np.ascontiguousarray((mask >= 5).astype(np.float32))
+    emu.emu_set_dm(ok.ctypes.data, C.c_float(0.0))
+    plen, tlen, gord = ours(-1.0)
+    emu.emu_set_dm(None, C.c_float(0.0))
+    rp, rt, rg = R.gridnet(p, mask=mask, thresh=5)
+    assert_bits(plen, rp, "plen -mask"); assert_bits(tlen, rt, "tlen -mask"); assert_bits(gord, rg, "gord -mask")
+
+
 def test_emulated_small_stacks_spill(fields):
     """A two-entry fork stack drops nearly every second receiver (the rescan of the shared-memory counts must find them);
     the outlet flood with a four-entry stack per warp spills nearly every discovered contributor to the host-drained list."""

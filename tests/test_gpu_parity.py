@@ -358,6 +358,44 @@ def test_d8_flow_path_extreme_up(refrun, tmp_path):
     assert_bits(td.read_raster(out), ref, "d8flowpathextremeup -o (files)")
 
 
+def test_gridnet(refrun, tmp_path):
+    """gridnet (a sibling of aread8 on the same sweep) against the reference executable (oracle/_ref/gridnet):
+    plain, mask + threshold, outlets, outlets + mask; grid level and our executable, bit for bit."""
+    import os
+    import subprocess
+    from util import write_point_shapefile
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "gridnet"), os.X_OK):
+        pytest.skip("oracle/_ref/gridnet is not built")
+    dem = synth.punch_holes(synth.gen_dem(330, 410, hurst=0.8, tilt=1.0, seed=47))
+    fel = td.pitremove_grid(dem); p, _ = td.d8flowdir_grid(fel)
+    R = refrun.RefPipeline(workdir=str(tmp_path))
+
+    def same(ours, ref, what):
+        for a, b, n in zip(ours, ref, ("plen", "tlen", "gord")):
+            assert_bits(a, b, f"{n} {what}")
+
+    same(td.gridnet_grid(p), R.gridnet(p), "")
+    ad8 = td.aread8_grid(p, contcheck=False)
+    mask = np.where(ad8 >= 0, ad8, 0).astype(np.int32)
+    same(td.gridnet_grid(p, mask=mask, thresh=20), R.gridnet(p, mask=mask, thresh=20), "-mask -thresh 20")
+    ny, nx = p.shape
+    order = np.argsort(ad8.ravel())
+    cells = [int(order[-1]), int(order[-40]), int(order[-700])]
+    cols = [c % nx for c in cells]; rows = [c // nx for c in cells]
+    dx = dy = 30.0
+    shp = str(tmp_path / "outlets.shp")
+    write_point_shapefile(shp, [(c + 0.5) * dx for c in cols], [dy * ny - (r + 0.5) * dy for r in rows])
+    same(td.gridnet_grid(p, outlets=(cols, rows)), R.gridnet(p, outlets=shp), "-o")
+    ref = R.gridnet(p, mask=mask, thresh=20, outlets=shp)
+    same(td.gridnet_grid(p, mask=mask, thresh=20, outlets=(cols, rows)), ref, "-o -mask")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    o = {n: str(tmp_path / f"ours_{n}.tif") for n in ("plen", "tlen", "gord")}
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "gridnet"), "-p", str(tmp_path / "pin.tif"), "-plen", o["plen"], "-tlen", o["tlen"], "-gord", o["gord"],
+                        "-o", shp, "-mask", str(tmp_path / "mask.tif"), "-thresh", "20"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "error" not in r.stdout.lower(), r.stdout
+    same((td.read_raster(o["plen"]), td.read_raster(o["tlen"]), td.read_raster(o["gord"], np.int16)), ref, "-o -mask (files)")
+
+
 def test_dinf_decay_accumulation(refrun, tmp_path):
     """dinfdecayaccum (a sibling of areadinf on the same sweep) against the reference executable
     (oracle/_ref/dinfdecayaccum): plain, weights + -nc, nodata multipliers, outlets; grid level and our executable, bit for bit."""
