@@ -129,6 +129,14 @@ int td_threshold(const char* ssafile, const char* srcfile, const char* maskfile,
 int td_twigrid(const char* slopefile, const char* areafile, const char* twifile);
 int td_threshold_host(const float* ssa, const float* mask /*NULL unless usemask*/, int16_t* src, int nx, int ny, float thresh, float ssa_nodata);
 int td_twi_host(const float* slp, const float* sca, float* twi, int nx, int ny, float slp_nodata, float sca_nodata);
+/* The other two point-wise consumers of SURVEY.md 8(f) rank 4.  File level = `int slopearea(char* slopefile, char* scafile, char* safile,
+ * float* p)` (src/SlopeArea.cpp:52; p[0] = m, p[1] = n: sa = slp^m * sca^n where both are >= 0) and `int atanbgrid(char* slopefile,
+ * char* areafile, char* atanbfile)` (src/SlopeAreaRatio.cpp:49: sar = slp / sca where sca is data).  sa, sar: float32, nodata -1.
+ * sar is bit-exact; sa is within a few float ulps of the reference's powf * powf (nodata masks identical). */
+int td_slopearea(const char* slopefile, const char* scafile, const char* safile, const float* p /* m, n */);
+int td_atanbgrid(const char* slopefile, const char* areafile, const char* atanbfile);
+int td_slopearea_host(const float* slp, const float* sca, float* sa, int nx, int ny, float m, float n);
+int td_slopearearatio_host(const float* slp, const float* sca, float* sar, int nx, int ny, float sca_nodata);
 
 /* aread8 + areadinf of one DEM in one call (no weights, no outlets), the host<->device copies overlapped with the kernels
  * on three streams: p in -> aread8 || ang in -> areadinf || ad8 out -> sca out.  Same results as the two calls above.
@@ -270,6 +278,8 @@ int td_area_sweep_run_dev(td_ctx*, const float* ang, const float* w, float* sca,
 /* point-wise consumers on device strips (pointwise.cu) */
 int td_threshold_dev(td_ctx*, const float* ssa, const float* mask, int16_t* src, td_strip s, float thresh, float ssa_nodata, void* stream);
 int td_twi_dev(td_ctx*, const float* slp, const float* sca, float* twi, td_strip s, float slp_nodata, float sca_nodata, void* stream);
+int td_slopearea_dev(td_ctx*, const float* slp, const float* sca, float* sa, td_strip s, float m, float n, void* stream);
+int td_slopearearatio_dev(td_ctx*, const float* slp, const float* sca, float* sar, td_strip s, float sca_nodata, void* stream);
 
 /* Peer mode (one process per GPU on one NVSwitch box): every rank exports the IPC handles of the buffers
  * its neighbours write (counts, tile scheduler, halo areas, rank 0 also the global pending counter), opens

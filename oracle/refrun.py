@@ -148,6 +148,19 @@ class RefPipeline:
         _, self.times["threshold"] = run_tool("threshold", args, self.np_ranks)
         return self.get("src.tif", np.int16)
 
+    def slopearea(self, slp, sca, m=None, n=None, nodata=-1.0):
+        self.put("slpin.tif", slp, nodata); self.put("scain.tif", sca, nodata)
+        args = ["-slp", self.path("slpin.tif"), "-sca", self.path("scain.tif"), "-sa", self.path("sa.tif")]
+        if m is not None:
+            args += ["-par", repr(float(m)), repr(float(n))]
+        _, self.times["slopearea"] = run_tool("slopearea", args, self.np_ranks)
+        return self.get("sa.tif", np.float32)
+
+    def slopearearatio(self, slp, sca, nodata=-1.0):
+        self.put("slpin.tif", slp, nodata); self.put("scain.tif", sca, nodata)
+        _, self.times["slopearearatio"] = run_tool("slopearearatio", ["-slp", self.path("slpin.tif"), "-sca", self.path("scain.tif"), "-sar", self.path("sar.tif")], self.np_ranks)
+        return self.get("sar.tif", np.float32)
+
     def twi(self, slp, sca, nodata=-1.0):
         self.put("slpin.tif", slp, nodata); self.put("scain.tif", sca, nodata)
         _, self.times["twi"] = run_tool("twi", ["-slp", self.path("slpin.tif"), "-sca", self.path("scain.tif"), "-twi", self.path("twi.tif")], self.np_ranks)

@@ -49,6 +49,12 @@ SIGNATURES = {
     "td_twigrid": (_I, [_S, _S, _S]),
     "td_threshold_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),
     "td_twi_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),
+    "td_slopearea": (_I, [_S, _S, _S, _P]),
+    "td_atanbgrid": (_I, [_S, _S, _S]),
+    "td_slopearea_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),
+    "td_slopearearatio_host": (_I, [_P, _P, _P, _I, _I, _F]),
+    "td_slopearea_dev": (_I, [_P, _P, _P, _P, Strip, _F, _F, _P]),
+    "td_slopearearatio_dev": (_I, [_P, _P, _P, _P, Strip, _F, _P]),
     "td_threshold_dev": (_I, [_P, _P, _P, _P, Strip, _F, _F, _P]),
     "td_twi_dev": (_I, [_P, _P, _P, _P, Strip, _F, _F, _P]),
     "td_nameadd": (_I, [_S, _S, _S]),

@@ -217,6 +217,26 @@ def twi_grid(slp, sca, slp_nodata=-1.0, sca_nodata=-1.0):
     return twi
 
 
+def slopearea_grid(slp, sca, m=2.0, n=1.0):
+    """sa = slp^m * sca^n where slp >= 0 and sca >= 0, else -1 (td_slopearea_host; src/SlopeArea.cpp:114-125)."""
+    slp = _grid(slp, np.float32); sca = _grid(sca, np.float32)
+    ny, nx = slp.shape
+    assert sca.shape == slp.shape
+    sa = np.empty((ny, nx), np.float32)
+    check(lib().td_slopearea_host(_ptr(slp), _ptr(sca), _ptr(sa), nx, ny, np.float32(m), np.float32(n)))
+    return sa
+
+
+def slopearearatio_grid(slp, sca, sca_nodata=-1.0):
+    """sar = slp / sca where sca is data, else -1 (td_slopearearatio_host; src/SlopeAreaRatio.cpp:107-118)."""
+    slp = _grid(slp, np.float32); sca = _grid(sca, np.float32)
+    ny, nx = slp.shape
+    assert sca.shape == slp.shape
+    sar = np.empty((ny, nx), np.float32)
+    check(lib().td_slopearearatio_host(_ptr(slp), _ptr(sca), _ptr(sar), nx, ny, np.float32(sca_nodata)))
+    return sar
+
+
 def contributing_areas_grid(p, ang, p_nodata=int(MISSINGSHORT), ang_nodata=float(MISSINGFLOAT), dx=30.0, dy=30.0, contcheck=True, out_ad8=None, out_sca=None):
     """aread8 + areadinf of one DEM in one call, copies overlapped with the kernels (td_contributing_areas_host)."""
     p = _grid(p, np.int16); ang = _grid(ang, np.float32)

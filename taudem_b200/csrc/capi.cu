@@ -612,6 +612,38 @@ int td_twi_dev(td_ctx*, const float* slp, const float* sca, float* twi, td_strip
   if (int rc = check_strip(s)) return rc;
   return td::launch_twi(slp, sca, twi, Strip(s), slp_nodata, sca_nodata, (cudaStream_t)stream);
 }
+int td_slopearea_dev(td_ctx*, const float* slp, const float* sca, float* sa, td_strip s, float m, float n, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::launch_slopearea(slp, sca, sa, Strip(s), m, n, (cudaStream_t)stream);
+}
+int td_slopearearatio_dev(td_ctx*, const float* slp, const float* sca, float* sar, td_strip s, float sca_nodata, void* stream) {
+  if (int rc = check_strip(s)) return rc;
+  return td::launch_slopearearatio(slp, sca, sar, Strip(s), sca_nodata, (cudaStream_t)stream);
+}
+// the two-rasters-in, one-raster-out shape shared by slopearea and slopearearatio (which: 0 = slp^m * sca^n, 1 = slp / sca)
+static int two_in_one_out_host(const char* who, int which, const float* slp, const float* sca, float* out, int nx, int ny, float a, float b) {
+  if (int rc = need_device()) return rc;
+  if (!slp || !sca || !out || nx <= 0 || ny <= 0) { td::set_error(std::string(who) + ": bad arguments"); return TD_ERR_ARG; }
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[0].ensure(n * 4)); TD_CUDA(ctx->io[1].ensure(n * 4)); TD_CUDA(ctx->io[2].ensure(n * 4));
+  float* d_slp = ctx->io[0].as<float>(); float* d_sca = ctx->io[1].as<float>(); float* d_out = ctx->io[2].as<float>();
+  TD_CUDA(h2d(d_slp, slp, s, st)); TD_CUDA(h2d(d_sca, sca, s, st));
+  Timer t; t.start(st);
+  if (int rc = which == 0 ? td_slopearea_dev(ctx, d_slp, d_sca, d_out, s, a, b, st) : td_slopearearatio_dev(ctx, d_slp, d_sca, d_out, s, a, st)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(out, d_out, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+int td_slopearea_host(const float* slp, const float* sca, float* sa, int nx, int ny, float m, float n) {
+  return two_in_one_out_host("td_slopearea_host", 0, slp, sca, sa, nx, ny, m, n);
+}
+int td_slopearearatio_host(const float* slp, const float* sca, float* sar, int nx, int ny, float sca_nodata) {
+  return two_in_one_out_host("td_slopearearatio_host", 1, slp, sca, sar, nx, ny, sca_nodata, 0.f);
+}
 int td_threshold_host(const float* ssa, const float* mask, int16_t* src, int nx, int ny, float thresh, float ssa_nodata) {
   if (int rc = need_device()) return rc;
   if (!ssa || !src || nx <= 0 || ny <= 0) { td::set_error("td_threshold_host: bad arguments"); return TD_ERR_ARG; }

@@ -1,4 +1,4 @@
-// Command line front ends: pitremove, d8flowdir, dinfflowdir, aread8, areadinf (+ the point-wise consumers threshold, twi).
+// Command line front ends: pitremove, d8flowdir, dinfflowdir, aread8, areadinf (+ the point-wise consumers threshold, twi, slopearea, slopearearatio).
 // Same flags, same two invocation styles and the same "print usage and exit(0)" error
 // behaviour as the reference mains (src/PitRemovemn.cpp:48-172, src/D8FlowDirmn.cpp:49-146,
 // src/DinfFlowDirmn.cpp:54-147, src/aread8mn.cpp:49-193, src/areadinfmn.cpp:49-178);
@@ -17,7 +17,7 @@ static int done() { fflush(stdout); fflush(stderr); _exit(0); return 0; }
 
 struct Opt {
   const char* flag;
-  int kind;        // 0 = file name, 1 = switch, 2 = integer, 3 = float (ival points to a float)
+  int kind;        // 0 = file name, 1 = switch, 2 = integer, 3 = float (ival points to a float), 4 = two floats
   char* sval;      // kind 0
   int* ival;       // kind 1 (set to `set`) / kind 2 (parsed) / kind 0 (set to `set` when given, may be NULL)
   int set;
@@ -43,6 +43,7 @@ static void parse(int argc, char** argv, Opt* opts, int nopts) {
     if (argc <= i) usage(argv[0]);
     if (o->kind == 0) { strncpy(o->sval, argv[i], MAXLN - 1); o->sval[MAXLN - 1] = 0; if (o->ival) *o->ival = o->set; }
     else if (o->kind == 3) sscanf(argv[i], "%f", (float*)o->ival);
+    else if (o->kind == 4) { if (argc <= i + 1) usage(argv[0]); sscanf(argv[i], "%f", (float*)o->ival); i++; sscanf(argv[i], "%f", (float*)o->ival + 1); }
     else sscanf(argv[i], "%d", o->ival);
     i++;
   }
@@ -307,6 +308,58 @@ int main(int argc, char** argv) {
   if (argc == 2) { td_nameadd(sca, argv[1], "sca"); td_nameadd(slp, argv[1], "slp"); td_nameadd(twi, argv[1], "twi"); }
   int err = td_twigrid(slp, sca, twi);
   if (err != 0) printf("TWI error %d\n", err);
+  return done();
+}
+#elif defined(TOOL_slopearea)
+// src/SlopeAreamn.cpp:50-138 (no "Error:" preamble; -par takes two floats; errors leave through `return 0`)
+static void usage(const char* prog) {
+  printf("Simple Use:\n %s <basefilename>\n", prog);
+  printf("Use with specific file names:\n %s -slp <slopefile>\n", prog);
+  printf("-sca <scafile> -sa <safile> [-par <m> <n>] \n");
+  printf("<basefilename> is the name of the base digital elevation model without suffixes for simple input. Suffixes 'slp', 'sca' and 'sa' will be appended. \n");
+  printf("<slopefile> is the name of the input slope file.\n");
+  printf("<scafile> is the name of input contributing area file.\n");
+  printf("<safile> is the name of the output file with the result slope^m x (contributing area)^n.\n");
+  printf("<m> is the exponent on slope, default value 2 if not specified.\n");
+  printf("<n> is the exponent on contributing area, default value 1 if not specified.\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char slp[MAXLN], sca[MAXLN], sa[MAXLN];
+  float par[2] = {2.f, 1.f};
+  if (argc < 2) usage(argv[0]);
+  Opt opts[] = {{"-slp", 0, slp, NULL, 0}, {"-sca", 0, sca, NULL, 0}, {"-sa", 0, sa, NULL, 0}, {"-par", 4, NULL, (int*)par, 0}};
+  parse(argc, argv, opts, 4);
+  if (argc == 2) { td_nameadd(slp, argv[1], "slp"); td_nameadd(sca, argv[1], "sca"); td_nameadd(sa, argv[1], "sa"); }
+  int err = td_slopearea(slp, sca, sa, par);
+  if (err != 0) printf("SlopeArea Error %d\n", err);
+  return done();
+}
+
+#elif defined(TOOL_slopearearatio)
+// src/SlopeAreaRatiomn.cpp:48-136
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s -sca <areafile>\n", prog);
+  printf("-slp <slopefile> -sar <atanbfile>\n");
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("<areafile> is the D-infinity specific catchment area input file.\n");
+  printf("<slopefile> is the D-infinity slope input file.\n");
+  printf("<atanbfile> is the slope area ratio output file.\n");
+  printf("The following are appended to the file names\n");
+  printf("before the files are opened:\n");
+  printf("sca    D-infinity specific catchment area grid (input)\n");
+  printf("slp     D-infinity slope grid (input)\n");
+  printf("sar    output slope area ratio grid\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char slp[MAXLN], sca[MAXLN], sar[MAXLN];
+  Opt opts[] = {{"-sca", 0, sca, NULL, 0}, {"-slp", 0, slp, NULL, 0}, {"-sar", 0, sar, NULL, 0}};
+  parse(argc, argv, opts, 3);
+  if (argc == 2) { td_nameadd(sca, argv[1], "sca"); td_nameadd(slp, argv[1], "slp"); td_nameadd(sar, argv[1], "sar"); }
+  int err = td_atanbgrid(slp, sca, sar);
+  if (err != 0) printf("Slope area ratio error %d\n", err);
   return done();
 }
 #else

@@ -1,6 +1,8 @@
 // Point-wise consumers of the contributing-area rasters:
 //   threshold  src = (ssa >= thresh [& mask >= 0]) ? 1 : 0, nodata where ssa is nodata   (src/Threshold.cpp:109-131)
 //   twi        twi = ln(sca / slp) where both are data and positive, else nodata (-1)     (src/TWI.cpp:108-124)
+//   slopearea  sa = slp^m * sca^n where slp >= 0 and sca >= 0, else nodata (-1)            (src/SlopeArea.cpp:114-125)
+//   slopearearatio  sar = slp / sca where sca is data, else nodata (-1)                    (src/SlopeAreaRatio.cpp:107-118)
 // One streaming kernel each, four cells per thread (16-byte loads, 8 / 16-byte stores): 6 B (10 with a mask) and 12 B of HBM
 // traffic per cell.  Device-strip level entry points take strips like every other kernel of the path; the host-grid level
 // copies dense arrays in and out.  isNodata is linearpart's |v - nodata| < 1e-5 (src/linearpart.h:471-483).
@@ -41,6 +43,37 @@ __global__ void __launch_bounds__(256) k_twi(const float* __restrict__ slp, cons
     out[i] = ok ? (float)log((double)(ar[i] / sl[i])) : -1.0f;
   }
   *reinterpret_cast<float4*>(twi + o) = make_float4(out[0], out[1], out[2], out[3]);
+}
+// slp^m * sca^n: the reference multiplies two powf results as floats (std::pow(float, float), src/SlopeArea.cpp:119); here each power
+// is the double pow rounded to float (correctly rounded in all but ~1e-9 of the cases; glibc's powf is within 0.52 ulp), then the
+// same float product — results agree to a few ulps (tests: relative 1e-6), nodata masks are identical.
+__global__ void __launch_bounds__(256) k_slopearea(const float* __restrict__ slp, const float* __restrict__ sca, float* __restrict__ sa, Strip s,
+                                                   float m, float n) {
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;
+  if (c >= s.pitch) return;
+  const long long o = s.idx(r, c);
+  const float4 sv = *reinterpret_cast<const float4*>(slp + o), av = *reinterpret_cast<const float4*>(sca + o);
+  const float sl[4] = {sv.x, sv.y, sv.z, sv.w}, ar[4] = {av.x, av.y, av.z, av.w};
+  float out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool ok = sl[i] >= 0.0f && ar[i] >= 0.0f;
+    out[i] = ok ? (float)pow((double)sl[i], (double)m) * (float)pow((double)ar[i], (double)n) : -1.0f;
+  }
+  *reinterpret_cast<float4*>(sa + o) = make_float4(out[0], out[1], out[2], out[3]);
+}
+// slp / sca as one IEEE float division (-prec-div=true); only the area's nodata is looked at, like the reference
+__global__ void __launch_bounds__(256) k_slopearearatio(const float* __restrict__ slp, const float* __restrict__ sca, float* __restrict__ sar, Strip s,
+                                                        float sca_nodata) {
+  const int r = 1 + (int)blockIdx.x, c = ((int)blockIdx.y * 256 + (int)threadIdx.x) * 4;
+  if (c >= s.pitch) return;
+  const long long o = s.idx(r, c);
+  const float4 sv = *reinterpret_cast<const float4*>(slp + o), av = *reinterpret_cast<const float4*>(sca + o);
+  const float sl[4] = {sv.x, sv.y, sv.z, sv.w}, ar[4] = {av.x, av.y, av.z, av.w};
+  float out[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = nd_f(ar[i], sca_nodata) ? -1.0f : sl[i] / ar[i];
+  *reinterpret_cast<float4*>(sar + o) = make_float4(out[0], out[1], out[2], out[3]);
 }
 // gridnet's mask rule (src/gridnet.cpp:383: maskData >= thresh, the mask read as 32-bit integers) as a 0 / 1 float grid
 __global__ void __launch_bounds__(256) k_mask_ok(const int* __restrict__ mask, float* __restrict__ ok, Strip s, int thresh) {
@@ -86,6 +119,20 @@ int launch_gord_finish(const float* g, const short* p, short* gord, const Strip&
 int launch_threshold(const float* ssa, const float* mask, short* src, const Strip& s, float thresh, float ssa_nodata, cudaStream_t st) {
   const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
   k_threshold<<<grid, 256, 0, st>>>(ssa, mask, src, s, thresh, ssa_nodata);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+int launch_slopearea(const float* slp, const float* sca, float* sa, const Strip& s, float m, float n, cudaStream_t st) {
+  const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
+  k_slopearea<<<grid, 256, 0, st>>>(slp, sca, sa, s, m, n);
+  TD_LAUNCHED();
+  TD_CUDA(cudaGetLastError());
+  return TD_OK;
+}
+int launch_slopearearatio(const float* slp, const float* sca, float* sar, const Strip& s, float sca_nodata, cudaStream_t st) {
+  const dim3 grid((unsigned)s.ny, (unsigned)(((s.pitch >> 2) + 255) / 256));
+  k_slopearearatio<<<grid, 256, 0, st>>>(slp, sca, sar, s, sca_nodata);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;

@@ -623,4 +623,44 @@ int td_twigrid(const char* slopefile, const char* areafile, const char* twifile)
   return TD_ERR_IO;
 }
 
+// src/SlopeArea.cpp:52-156 and src/SlopeAreaRatio.cpp:49-150: two float rasters in, one out (nodata -1), same messages
+static int two_in_one_out(int which, const char* banner, const char* slopefile, const char* scafile, const char* outfile, const float* par) {
+  printf("%s version %s\n", banner, td_version());
+  const double t0 = now();
+  Input sl;
+  if (int rc = sl.open(slopefile)) return rc;
+  std::vector<float> slp;
+  nodata_msgs(sl.r.nodata(), "float", (float)sl.r.nodata());
+  if (int rc = sl.read(&slp, tdio::DT_F32)) return rc;
+  Input ar; std::vector<float> sca;
+  if (int rc = ar.open(scafile)) return rc;
+  if (!tdio::compare_rasters(sl.r, sl.path, ar.r, ar.path)) { td::set_error("area grid does not match"); return 1; }   // `return 1`, src/SlopeArea.cpp:89
+  nodata_msgs(ar.r.nodata(), "float", (float)ar.r.nodata());
+  if (int rc = ar.read(&sca, tdio::DT_F32)) return rc;
+  const double t1 = now();
+  std::vector<float> out((size_t)sl.nx * sl.ny);
+  const int rc = which == 0 ? td_slopearea_host(slp.data(), sca.data(), out.data(), sl.nx, sl.ny, par[0], par[1])
+                            : td_slopearearatio_host(slp.data(), sca.data(), out.data(), sl.nx, sl.ny, (float)ar.r.nodata());
+  if (rc) { printf("%s device error: %s\n", banner, td_last_error()); return rc; }
+  const double t2 = now();
+  if (int rc2 = write_like(outfile, sl, tdio::DT_F32, (double)-1.0f, out)) return rc2;
+  const double t3 = now();
+  printf("Compute time: %f\n", t2 - t1);
+  printf("Read time: %f\nWrite time: %f\nTotal time: %f\nDevice compute time: %f\n", t1 - t0, t3 - t2, t3 - t0, td_last_compute_seconds());
+  return TD_OK;
+}
+int td_slopearea(const char* slopefile, const char* scafile, const char* safile, const float* p) try {
+  if (!p) { td::set_error("td_slopearea: the exponents are missing"); return TD_ERR_ARG; }
+  return two_in_one_out(0, "SlopeArea", slopefile, scafile, safile, p);
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+int td_atanbgrid(const char* slopefile, const char* areafile, const char* atanbfile) try {
+  return two_in_one_out(1, "SlopeAreaRatio", slopefile, areafile, atanbfile, nullptr);
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
 }  // extern "C"

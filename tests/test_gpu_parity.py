@@ -465,6 +465,39 @@ def test_pointwise_consumers_threshold_and_twi(refrun, tmp_path):
     assert_bits(td.read_raster(out), twi, "twi (files)")
 
 
+def test_pointwise_consumers_slopearea_and_slopearearatio(refrun, tmp_path):
+    """slopearea and slopearearatio (the other two tools of SURVEY.md 8(f) rank 4): grid level and our executables against the
+    reference executables (SlopeArea.cpp / SlopeAreaRatio.cpp compiled unchanged).  sar = slp / sca is bit-exact; sa = slp^m * sca^n
+    is a product of two powf results in the reference (< 1 ulp each): relative 1e-6 with identical nodata masks."""
+    import os
+    import subprocess
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "slopearea"), os.X_OK):
+        pytest.skip("oracle/_ref/slopearea and slopearearatio are not built")
+    dem = synth.punch_holes(synth.gen_dem(260, 420, hurst=0.8, tilt=1.0, seed=37))
+    fel = td.pitremove_grid(dem); ang, slp = td.dinfflowdir_grid(fel); sca = td.areadinf_grid(ang)
+    R = refrun.RefPipeline(workdir=str(tmp_path))
+    with np.errstate(all="ignore"):
+        assert_bits(td.slopearearatio_grid(slp, sca), R.slopearearatio(slp, sca), "sar")
+    for m, n in ((None, None), (0.5, 1.75)):
+        ours = td.slopearea_grid(slp, sca) if m is None else td.slopearea_grid(slp, sca, m, n)
+        ref = R.slopearea(slp, sca, m, n)
+        assert np.array_equal(ours == -1.0, ref == -1.0), "sa nodata masks differ"
+        ok = ref != -1.0
+        np.testing.assert_allclose(ours[ok], ref[ok], rtol=1e-6, atol=0)
+        assert (ours[ok] == ref[ok]).mean() > 0.9
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "ours_sa.tif")
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "slopearea"), "-slp", str(tmp_path / "slpin.tif"), "-sca", str(tmp_path / "scain.tif"), "-sa", out,
+                        "-par", "0.5", "1.75"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "rror" not in r.stdout, r.stdout
+    assert_bits(td.read_raster(out), ours, "slopearea (files)")
+    out = str(tmp_path / "ours_sar.tif")
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "slopearearatio"), "-slp", str(tmp_path / "slpin.tif"), "-sca", str(tmp_path / "scain.tif"), "-sar", out],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "rror" not in r.stdout, r.stdout
+    assert_bits(td.read_raster(out), R.get("sar.tif", np.float32), "slopearearatio (files)")
+
+
 def test_dinf_angle_torture():
     """areadinf on angles at and next to every place where prop() changes its mind (sector edges, the 1e-5 share threshold, the
     wrap sector, angles beyond 2 PI), bit for bit against the C restatement (pinned on the reference tools by the CPU suite)."""
