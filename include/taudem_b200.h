@@ -116,6 +116,26 @@ int td_dmarea(const char* angfile, const char* adecfile, const char* dmfile, con
 int td_dinfdecayaccum_host(const float* ang, const float* dm, const float* w /*NULL unless usew*/, float* dsca, int nx, int ny, float ang_nodata,
                            float dm_nodata, const double* dxc, const double* dyc, int contcheck, const int* outlet_cols, const int* outlet_rows,
                            int nout /* < 0: no outlets */);
+/* Siblings of areadinf on the same sweep: the concentration- and the transport-limited accumulation.  File level =
+ * `int dsllArea(char* angfile, char* ctptfile, char* dmfile, char* datasrc, char* lyrname, int uselyrname, int lyrno, char* qfile, char* dgfile,
+ * int useOutlets, int contcheck, float cSol)` (src/DinfConcLimAccum.cpp:61) and `int tlaccum(char* angfile, char* tsupfile, char* tcfile,
+ * char* tlafile, char* depfile, char* cinfile, char* coutfile, char* datasrc, char* lyrname, int uselyrname, int lyrno, int useOutlets, int usec,
+ * int contcheck)` (src/DinfTransLimAccum.cpp:61).  All outputs float32 with nodata -FLT_MAX.
+ * ctpt: cells with q > 0 only; an indicator cell (dg > 0) has the concentration cSol, any other the float sum of p * ctpt * q * dm over its
+ * contributors divided by its own q (src/DinfConcLimAccum.cpp:242-270).  tla / tdep / ctpt: transport out = min(transport in + supply,
+ * capacity), deposition = the rest, concentration = load out / transport out (src/DinfTransLimAccum.cpp:237-302); cs and ctpt are
+ * both NULL or both given. */
+int td_dsllarea(const char* angfile, const char* ctptfile, const char* dmfile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno,
+                const char* qfile, const char* dgfile, int useOutlets, int contcheck, float cSol);
+int td_tlaccum(const char* angfile, const char* tsupfile, const char* tcfile, const char* tlafile, const char* depfile, const char* cinfile,
+               const char* coutfile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, int useOutlets, int usec, int contcheck);
+int td_dinfconclimaccum_host(const float* ang, const float* dm, const float* q, const int16_t* dg, float* ctpt, int nx, int ny, float ang_nodata,
+                             float dm_nodata, float q_nodata, float csol, const double* dxc, const double* dyc, int contcheck, const int* outlet_cols,
+                             const int* outlet_rows, int nout /* < 0: no outlets */);
+int td_dinftranslimaccum_host(const float* ang, const float* tsup, const float* tc, const float* cs /*NULL unless usec*/, float* tla, float* tdep,
+                              float* ctpt /*NULL unless usec*/, int nx, int ny, float ang_nodata, float tsup_nodata, float tc_nodata, float cs_nodata,
+                              const double* dxc, const double* dyc, int contcheck, const int* outlet_cols, const int* outlet_rows,
+                              int nout /* < 0: no outlets */);
 /* Sibling of aread8 on the same sweep: gridnet.  File level = `int gridnet(char* pfile, char* plenfile, char* tlenfile, char* gordfile,
  * char* maskfile, char* datasrc, char* lyrname, int uselyrname, int lyrno, int useMask, int useOutlets, int thresh)`
  * (src/gridnet.cpp:55); plen / tlen: float32, nodata -1; gord: int16, nodata -1.  mask (int32, NULL = none): only cells with

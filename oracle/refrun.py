@@ -139,6 +139,32 @@ class RefPipeline:
         _, self.times["dinfdecayaccum"] = run_tool("dinfdecayaccum", args, self.np_ranks)
         return self.get("dsca.tif", np.float32)
 
+    def dinfconclimaccum(self, ang, dm, q, dg, csol=1.0, contcheck=True, outlets=None, nodata=-9999.0):
+        self.put("angin.tif", ang, -3.4028234663852886e38); self.put("dm.tif", dm, nodata); self.put("q.tif", q, nodata)
+        self.put("dg.tif", np.asarray(dg, np.int16), -32768)
+        args = ["-ang", self.path("angin.tif"), "-dm", self.path("dm.tif"), "-q", self.path("q.tif"), "-dg", self.path("dg.tif"),
+                "-ctpt", self.path("ctpt.tif"), "-csol", repr(float(csol))]
+        if outlets is not None:
+            args += ["-o", outlets]
+        if not contcheck:
+            args.append("-nc")
+        _, self.times["dinfconclimaccum"] = run_tool("dinfconclimaccum", args, self.np_ranks)
+        return self.get("ctpt.tif", np.float32)
+
+    def dinftranslimaccum(self, ang, tsup, tc, cs=None, contcheck=True, outlets=None, nodata=-9999.0):
+        self.put("angin.tif", ang, -3.4028234663852886e38); self.put("tsup.tif", tsup, nodata); self.put("tc.tif", tc, nodata)
+        args = ["-ang", self.path("angin.tif"), "-tsup", self.path("tsup.tif"), "-tc", self.path("tc.tif"), "-tla", self.path("tla.tif"),
+                "-tdep", self.path("tdep.tif")]
+        if cs is not None:
+            self.put("cs.tif", cs, nodata)
+            args += ["-cs", self.path("cs.tif"), "-ctpt", self.path("ctptout.tif")]
+        if outlets is not None:
+            args += ["-o", outlets]
+        if not contcheck:
+            args.append("-nc")
+        _, self.times["dinftranslimaccum"] = run_tool("dinftranslimaccum", args, self.np_ranks)
+        return (self.get("tla.tif", np.float32), self.get("tdep.tif", np.float32), self.get("ctptout.tif", np.float32) if cs is not None else None)
+
     def threshold(self, ssa, thresh, mask=None, nodata=-1.0):
         self.put("ssa.tif", ssa, nodata)
         args = ["-ssa", self.path("ssa.tif"), "-src", self.path("src.tif"), "-thresh", repr(float(thresh))]

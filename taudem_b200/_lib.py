@@ -45,6 +45,10 @@ SIGNATURES = {
     "td_gridnet_host": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, C.c_int16, _P, _P, _P, _P, _I]),
     "td_dmarea": (_I, [_S, _S, _S, _S, _S, _I, _I, _S, _I, _I, _I]),
     "td_dinfdecayaccum_host": (_I, [_P, _P, _P, _P, _I, _I, C.c_float, C.c_float, _P, _P, _I, _P, _P, _I]),
+    "td_dsllarea": (_I, [_S, _S, _S, _S, _S, _I, _I, _S, _S, _I, _I, _F]),
+    "td_tlaccum": (_I, [_S, _S, _S, _S, _S, _S, _S, _S, _S, _I, _I, _I, _I, _I]),
+    "td_dinfconclimaccum_host": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _P, _P, _I, _P, _P, _I]),
+    "td_dinftranslimaccum_host": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _P, _P, _I, _P, _P, _I]),
     "td_threshold": (_I, [_S, _S, _S, _F, _I]),
     "td_twigrid": (_I, [_S, _S, _S]),
     "td_threshold_host": (_I, [_P, _P, _P, _I, _I, _F, _F]),

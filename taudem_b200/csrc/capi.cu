@@ -549,6 +549,89 @@ int td_dinfdecayaccum_host(const float* ang, const float* dm, const float* w, fl
   return TD_OK;
 }
 
+// DinfConcLimAccum (src/DinfConcLimAccum.cpp:61) and DinfTransLimAccum (src/DinfTransLimAccum.cpp:61): the D-infinity sweep with the
+// concentration- and transport-limited algebras (7; 8 / 9).  Single strip.
+namespace {
+struct DinfSweepSetup { td_ctx* ctx; td_strip s; cudaStream_t st; const double *d_dx, *d_dy; float* d_ang; float* d_a; };
+// uploads the angles, builds the dependency state with MISSINGFLOAT as the result's nodata, restricts it to the outlets' upstream cells
+int dinf_sibling_setup(DinfSweepSetup& S, const float* ang, int nx, int ny, float ang_nodata, const double* dxc, const double* dyc,
+                       const int* outlet_cols, const int* outlet_rows, int nout) {
+  S.ctx = default_ctx();
+  S.s = host_strip(nx, ny);
+  S.st = 0;
+  const size_t n = (size_t)Strip(S.s).cells();
+  TD_CUDA(S.ctx->io[0].ensure(n * 4)); TD_CUDA(S.ctx->io[1].ensure(n * 4));
+  S.d_ang = S.ctx->io[0].as<float>(); S.d_a = S.ctx->io[1].as<float>();
+  if (int rc = upload_rows(S.ctx, dxc, dyc, ny, &S.d_dx, &S.d_dy, S.st)) return rc;
+  TD_CUDA(h2d(S.d_ang, ang, S.s, S.st));
+  const Strip ss(S.s);
+  if (int rc = ensure_dep_state(S.ctx, ss, S.st)) return rc;
+  if (int rc = upload_theta(S.ctx, S.d_dx, S.d_dy, S.s.ny, S.ctx->theta, S.st)) return rc;
+  S.ctx->sweep_dinf = 1;
+  TD_CUDA(td::launch_deps_dinf(S.d_ang, S.ctx->node.as<unsigned short>(), S.ctx->cnt.as<unsigned char>(), S.d_a, ss, ang_nodata, S.ctx->theta.as<double>(), S.st,
+                               TD_MISSINGFLOAT));
+  if (nout >= 0) { if (int rc = td_sweep_restrict_dev(S.ctx, S.s, outlet_cols, outlet_rows, nout, S.st)) return rc; }
+  return td::wsweep_begin(S.ctx, ss, S.st);
+}
+}  // namespace
+int td_dinfconclimaccum_host(const float* ang, const float* dm, const float* q, const int16_t* dg, float* ctpt, int nx, int ny, float ang_nodata, float dm_nodata,
+                             float q_nodata, float csol, const double* dxc, const double* dyc, int contcheck, const int* outlet_cols, const int* outlet_rows, int nout) {
+  if (int rc = need_device()) return rc;
+  if (!ang || !dm || !q || !dg || !ctpt || !dxc || !dyc || nx <= 0 || ny <= 0) { td::set_error("td_dinfconclimaccum_host: bad arguments"); return TD_ERR_ARG; }
+  DinfSweepSetup S;
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const size_t n = (size_t)Strip(s).cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[2].ensure(n * 4)); TD_CUDA(ctx->io[3].ensure(n * 4)); TD_CUDA(ctx->io[4].ensure(n * 2));
+  float* d_q = ctx->io[2].as<float>(); float* d_dm = ctx->io[3].as<float>(); int16_t* d_dg = ctx->io[4].as<int16_t>();
+  TD_CUDA(h2d(d_q, q, s, st)); TD_CUDA(h2d(d_dm, dm, s, st)); TD_CUDA(h2d(d_dg, dg, s, st));
+  Timer t; t.start(st);
+  if (int rc = dinf_sibling_setup(S, ang, nx, ny, ang_nodata, dxc, dyc, outlet_cols, outlet_rows, nout)) return rc;
+  td::SweepExtra x; x.dg = d_dg; x.csol = csol;
+  if (int rc = td::wsweep_run(ctx, true, S.d_a, d_q, S.d_ang, Strip(s), q_nodata, 1, contcheck, ctx->theta.as<double>(), S.d_dx, ctx->halo.as<int>(), st, 7,
+                              d_dm, dm_nodata, nullptr, &x)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(ctpt, S.d_a, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+int td_dinftranslimaccum_host(const float* ang, const float* tsup, const float* tc, const float* cs, float* tla, float* tdep, float* ctpt, int nx, int ny,
+                              float ang_nodata, float tsup_nodata, float tc_nodata, float cs_nodata, const double* dxc, const double* dyc, int contcheck,
+                              const int* outlet_cols, const int* outlet_rows, int nout) {
+  if (int rc = need_device()) return rc;
+  if (!ang || !tsup || !tc || !tla || !tdep || (cs != nullptr) != (ctpt != nullptr) || !dxc || !dyc || nx <= 0 || ny <= 0) {
+    td::set_error("td_dinftranslimaccum_host: bad arguments (the concentration input and output come together)");
+    return TD_ERR_ARG;
+  }
+  DinfSweepSetup S;
+  td_ctx* ctx = default_ctx();
+  const td_strip s = host_strip(nx, ny);
+  const Strip ss(s);
+  const size_t n = (size_t)ss.cells();
+  cudaStream_t st = 0;
+  TD_CUDA(ctx->io[2].ensure(n * 4)); TD_CUDA(ctx->io[3].ensure(n * 4)); TD_CUDA(ctx->io[4].ensure(n * 4));
+  float* d_ts = ctx->io[2].as<float>(); float* d_tc = ctx->io[3].as<float>(); float* d_dep = ctx->io[4].as<float>(); float *d_cs = nullptr, *d_co = nullptr;
+  TD_CUDA(h2d(d_ts, tsup, s, st)); TD_CUDA(h2d(d_tc, tc, s, st));
+  if (cs) {
+    TD_CUDA(ctx->io[5].ensure(n * 4)); TD_CUDA(ctx->io[6].ensure(n * 4));
+    d_cs = ctx->io[5].as<float>(); d_co = ctx->io[6].as<float>();
+    TD_CUDA(h2d(d_cs, cs, s, st));
+  }
+  Timer t; t.start(st);
+  if (int rc = dinf_sibling_setup(S, ang, nx, ny, ang_nodata, dxc, dyc, outlet_cols, outlet_rows, nout)) return rc;
+  TD_CUDA(td::fill_floats(d_dep, ss, TD_MISSINGFLOAT, st));                 // cells that are never evaluated stay nodata (src/DinfTransLimAccum.cpp:198-204)
+  if (cs) TD_CUDA(td::fill_floats(d_co, ss, TD_MISSINGFLOAT, st));
+  td::SweepExtra x; x.cin = d_cs; x.cin_nodata = cs_nodata; x.out2 = d_dep; x.out3 = d_co;
+  if (int rc = td::wsweep_run(ctx, true, S.d_a, d_ts, S.d_ang, ss, tsup_nodata, 1, contcheck, ctx->theta.as<double>(), S.d_dx, ctx->halo.as<int>(), st, cs ? 9 : 8,
+                              d_tc, tc_nodata, nullptr, &x)) return rc;
+  td::set_compute_seconds(t.stop(st));
+  TD_CUDA(d2h(tla, S.d_a, s, st)); TD_CUDA(d2h(tdep, d_dep, s, st));
+  if (cs) TD_CUDA(d2h(ctpt, d_co, s, st));
+  TD_CUDA(cudaStreamSynchronize(st));
+  return TD_OK;
+}
+
 // gridnet (src/gridnet.cpp:55): longest upstream path length, total upstream path length and Strahler order of the D8 flow
 // field — three runs of the D8 sweep, one value per cell each (algebras 4, 5, 6).  Single strip.
 int td_gridnet_host(const int16_t* p, const int32_t* mask, int thresh, float* plen, float* tlen, int16_t* gord, int nx, int ny, int16_t p_nodata,

@@ -257,6 +257,77 @@ int main(int argc, char** argv) {
   return done();
 }
 
+#elif defined(TOOL_dinfconclimaccum)
+// src/DinfConcLimAccummn.cpp:50-221
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s -ang <angfile>\n", prog);
+  printf("-dg <indicatorFile> -dm <dmfile> -ctpt <afile>\n");
+  printf("-q <qfile> [-o <outletshapefile>] [-csol <cSol>] [<-nc>]\n");
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("<angfile> is the D-infinity flow direction input file.\n");
+  printf("<indicatorFile> is the disturbance indicator input grid file.\n");
+  printf("<dmfile> is the decay multiplier input grid file.\n");
+  printf("<ctptfile> is the concentration output grid file.\n");
+  printf("<qfile> is the specific discharge input grid file.\n");
+  printf("<outletshapefile> is the optional outlet shape input file.\n");
+  printf("<cSol> is the optional concentration threshold.\n");
+  printf("The flag -nc overrides edge contamination checking\n");
+  printf("The following are appended to the file names\nbefore the files are opened:\n");
+  printf("ang    D-infinity flow direction input file\ndg     Disturbance indicator input file\ndm     Decay multiplier grid (input)\n");
+  printf("q      Specific discharge grid (input)\nctpt   Concentration grid (output)\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char ang[MAXLN], ctpt[MAXLN], dm[MAXLN], q[MAXLN], dg[MAXLN], datasrc[MAXLN], lyrname[MAXLN];
+  int useOutlets = 0, uselyrname = 0, lyrno = 0, contcheck = 1;
+  float csol = 1.f;
+  Opt opts[] = {{"-ang", 0, ang, NULL, 0}, {"-dg", 0, dg, NULL, 0}, {"-dm", 0, dm, NULL, 0}, {"-ctpt", 0, ctpt, NULL, 0}, {"-q", 0, q, NULL, 0},
+                {"-csol", 3, NULL, (int*)&csol, 0}, {"-o", 0, datasrc, &useOutlets, 1}, {"-lyrno", 2, NULL, &lyrno, 0},
+                {"-lyrname", 0, lyrname, &uselyrname, 1}, {"-nc", 1, NULL, &contcheck, 0}};
+  parse(argc, argv, opts, 10);
+  if (argc == 2) { td_nameadd(ang, argv[1], "ang"); td_nameadd(dg, argv[1], "dg"); td_nameadd(dm, argv[1], "dm"); td_nameadd(q, argv[1], "q"); td_nameadd(ctpt, argv[1], "ctpt"); }
+  int err = td_dsllarea(ang, ctpt, dm, datasrc, lyrname, uselyrname, lyrno, q, dg, useOutlets, contcheck, csol);
+  if (err != 0) printf("area error %d\n", err);
+  return done();
+}
+
+#elif defined(TOOL_dinftranslimaccum)
+// src/DinfTransLimAccummn.cpp:51-234
+static void usage(const char* prog) {
+  printf("Simple Usage:\n %s <basefilename>\n", prog);
+  printf("Usage with specific file names:\n %s -ang <pfile>\n", prog);
+  printf("-tsup <wfile> -tc <tcfile> [-cs <cfile> -ctpt <coutfile>]\n");
+  printf("-tla <tlafile> -tdep <depfile> [-o <shfile>] [<-nc>]\n");
+  printf("<basefilename> is the name of the raw digital elevation model\n");
+  printf("<angfile> is the D-infinity flow direction input file.\n");
+  printf("<wfile> is the input transport supply grid file.\n");
+  printf("<tcfile> is the input transport capacity grid file.\n");
+  printf("<cfile> is the optional input concentration grid file.\n");
+  printf("<coutfile> is the optional output concentration grid file.\n");
+  printf("<tlafile> is the output transport limitted accumulation grid file.\n");
+  printf("<depfile> is the output deposition grid file.\n");
+  printf("<shfile> is the optional outlet shapefile.\n");
+  printf("The flag -nc overrides edge contamination checking\n");
+  printf("The following are appended to the file names\nbefore the files are opened:\n");
+  printf("ang    D-infinity flow direction input file\ntsup   Input transport supply grid\ntc     Input transport capacity grid\n");
+  printf("tla    Output transport limitted accumulation grid\ntdep   output deposition grid\n");
+  exit(0);
+}
+int main(int argc, char** argv) {
+  static char ang[MAXLN], tsup[MAXLN], tc[MAXLN], tla[MAXLN], dep[MAXLN], cin[MAXLN], cout[MAXLN], datasrc[MAXLN], lyrname[MAXLN];
+  int useOutlets = 0, usec = 0, compctpt = 0, uselyrname = 0, lyrno = 0, contcheck = 1;
+  Opt opts[] = {{"-ang", 0, ang, NULL, 0}, {"-tsup", 0, tsup, NULL, 0}, {"-tc", 0, tc, NULL, 0}, {"-cs", 0, cin, &usec, 1}, {"-ctpt", 0, cout, &compctpt, 1},
+                {"-tla", 0, tla, NULL, 0}, {"-tdep", 0, dep, NULL, 0}, {"-o", 0, datasrc, &useOutlets, 1}, {"-lyrno", 2, NULL, &lyrno, 0},
+                {"-lyrname", 0, lyrname, &uselyrname, 1}, {"-nc", 1, NULL, &contcheck, 0}};
+  parse(argc, argv, opts, 11);
+  if (argc == 2) { td_nameadd(ang, argv[1], "ang"); td_nameadd(tsup, argv[1], "tsup"); td_nameadd(tc, argv[1], "tc"); td_nameadd(tla, argv[1], "tla"); td_nameadd(dep, argv[1], "tdep"); }
+  usec = usec * compctpt;            // both -cs and -ctpt, or no concentration at all (src/DinfTransLimAccummn.cpp:202)
+  int err = td_tlaccum(ang, tsup, tc, tla, dep, cin, cout, datasrc, lyrname, uselyrname, lyrno, useOutlets, usec, contcheck);
+  if (err != 0) printf("tlaccum error %d\n", err);
+  return done();
+}
+
 #elif defined(TOOL_threshold)
 // src/Thresholdmn.cpp:50-130 (its usage text names the flags wrongly; the flags themselves are -ssa -src -thresh -mask)
 static void usage(const char* prog) {

@@ -36,7 +36,7 @@ struct td_ctx {
   Buf theta;     // per-row atan2(dy,dx) | atan2(dx,dy) tables (doubles)
   Buf rows;      // per-row dxc | dyc (host-grid level calls)
   Buf rowfact;   // per-row constants of the flow-direction stencils (rowfact.cuh)
-  Buf io[4];     // raster strips of host-grid level calls
+  Buf io[7];     // raster strips of host-grid level calls
   // peer mode of the sweeps (neighbour strips' buffers opened through CUDA IPC, see sweep_warp.cu)
   struct PeerInfo { void *cntw = nullptr, *tileflags = nullptr, *dctr = nullptr, *halo_in = nullptr; int qmask = 0, ntx = 0, ny = 0, th = 0, nt = 0, valid = 0, nsh = 1, qshift = 0; };
   PeerInfo peer_up, peer_down;
@@ -47,7 +47,7 @@ struct td_ctx {
   int sweep_dinf = 0;                    // which dependency state node/cnt hold (tile height of the sweep)
   td::PropRow prop;                      // prop() table of the strip whose theta table is loaded (uniform = 0: rows differ)
   double dx0 = 0.;                       // cell size of the strip's rows when they all have the same (prop.uniform)
-  int wgrid[12] = {0};           // persistent grid of the four warp-per-tile sweep kernels (D8 / D-infinity x weights) on this context's device
+  int wgrid[16] = {0};           // persistent grid of the four warp-per-tile sweep kernels (D8 / D-infinity x weights) on this context's device
   unsigned long long* d_ctr = nullptr;   // 32 device counters
   unsigned long long* h_ctr = nullptr;   // pinned host mirror
   td_ctx();

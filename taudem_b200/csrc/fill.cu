@@ -14,6 +14,7 @@
 // back and, if anything changed, queues the 3x3 tile neighbourhood for the next
 // round.  Rounds end when no tile changes.
 #include "ctx.h"
+#include "tile_pipe.cuh"
 
 namespace td {
 namespace {
@@ -23,59 +24,65 @@ constexpr int SW = FW + 2;                 // shared W row stride (with ring)
 
 // Initialisation (src/flood.cpp:243-271): nodata stays nodata, cells of the depression mask, cells on the edge of the
 // grid and cells with a nodata neighbour (8 or 4 neighbours) keep their elevation, everything else starts "under water"
-// (FLT_MAX).  A 3x3 stencil in the style of the flow-direction stencils: TMA-staged 32 x 128 tile, four cells per thread,
-// nodata through fmin chains over |z - nodata|, one float4 store.  8 B/cell (+2 with a mask).
-constexpr int IW = 128, IH = 32;
-__global__ void __launch_bounds__(256) k_fill_init(const float* __restrict__ dem, const short* __restrict__ mask,
+// (FLT_MAX).  A 3x3 stencil on the persistent tile pipeline of the flow-direction stencils (tile_pipe.cuh: three stages of
+// 2-D TMA tiles per CTA), four cells per thread, one float4 store.  The nodata test is a minimum of |z - nodata| over the
+// window, folded column-wise first (three cells of a column are shared by three windows).  Neighbours outside the grid
+// need no test: only edge cells have them and edge cells keep their elevation whatever their window holds (what the TMA
+// unit zero-fills there is never used for a decision; fminf drops NaNs).  8 B/cell (+2 with a mask).
+constexpr int IW = 128, IH = 32, ISTAGES = 3;
+using InitRing = TileRing<float, IW, IH, ISTAGES>;
+__global__ void __launch_bounds__(256) k_fill_init(const TD_GRID_CONSTANT TileMap tm, const short* __restrict__ mask,
                                                    float* __restrict__ W, Strip s, float nodata, int step) {
-  using G = TileGeom<float, IW, IH>;
-  __shared__ __align__(128) float tile[G::ELEMS];
-  __shared__ __align__(8) uint64_t bar;
-  const int c0 = blockIdx.x * IW, r0 = 1 + blockIdx.y * IH;
-  load_tile_tma<float, IW, IH>(tile, &bar, dem, s, r0, c0);
+  extern __shared__ __align__(128) unsigned char dsm128[];
+  using G = InitRing::G;
+  InitRing ring;
+  ring.init(dsm128, &tm, s);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long t = blockIdx.x; t < ring.ntiles; t += gridDim.x) {
+    int r0, c0;
+    const float* tile = ring.acquire(t, r0, c0);
 #pragma unroll 1
-  for (int pass = 0; pass < IH / 8; ++pass) {
-    const int tr = warp + 8 * pass;
-    const int r = r0 + tr, c = c0 + lane * 4;
-    if (r > s.ny || c >= s.pitch) continue;
-    const float* pm = tile + tr * G::SW + G::HP + lane * 4;   // row above, column c
-    float nb[3][6], a[3][6];
+    for (int pass = 0; pass < IH / 8; ++pass) {
+      const int tr = warp + 8 * pass;
+      const int r = r0 + tr, c = c0 + lane * 4;
+      if (r > s.ny || c >= s.pitch) continue;
+      const float* pm = tile + tr * G::SW + G::HP + lane * 4;   // row above, column c
+      float a[3][6], z[4];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const float* p = pm + j * G::SW;
-      const float4 v = *reinterpret_cast<const float4*>(p);
-      nb[j][0] = p[-1]; nb[j][1] = v.x; nb[j][2] = v.y; nb[j][3] = v.z; nb[j][4] = v.w; nb[j][5] = p[4];
+      for (int j = 0; j < 3; ++j) {
+        const float* p = pm + j * G::SW;
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        const float nb[6] = {p[-1], v.x, v.y, v.z, v.w, p[4]};
+        if (j == 1) { z[0] = v.x; z[1] = v.y; z[2] = v.z; z[3] = v.w; }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        // a neighbour off the grid does not count (the cell is an edge cell anyway): huge distance
-        const bool on = s.on_grid(r - 1 + j, c - 1 + i);
-        a[j][i] = on ? fabsf(nb[j][i] - nodata) : FLT_MAX;
+        for (int i = 0; i < 6; ++i) a[j][i] = fabsf(nb[i] - nodata);
       }
-    }
-    unsigned em = ((r == 1 && !s.has_top) || (r == s.ny && !s.has_bot)) ? 0xfu : 0u;     // cells on the edge of the whole grid
-    em |= (c == 0) ? 1u : 0u;
-    const int klast = s.nx - 1 - c;
-    if (klast < 4) em |= (0xfu << max(klast, 0)) & 0xfu;
-    short4 mk = make_short4(0, 0, 0, 0);
-    if (mask != nullptr) mk = *reinterpret_cast<const short4*>(mask + s.idx(r, c));
-    const short m4[4] = {mk.x, mk.y, mk.z, mk.w};
-    float out[4];
+      unsigned em = ((r == 1 && !s.has_top) || (r == s.ny && !s.has_bot)) ? 0xfu : 0u;     // cells on the edge of the whole grid
+      em |= (c == 0) ? 1u : 0u;
+      const int klast = s.nx - 1 - c;
+      if (klast < 4) em |= (0xfu << max(klast, 0)) & 0xfu;
+      short4 mk = make_short4(0, 0, 0, 0);
+      if (mask != nullptr) mk = *reinterpret_cast<const short4*>(mask + s.idx(r, c));
+      const short m4[4] = {mk.x, mk.y, mk.z, mk.w};
+      // 8 neighbours: the minimum over each window column (the centre's own distance may take part: a nodata centre becomes nodata below)
+      float col[6];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float z = nb[1][i + 1];
-      float dmin;
-      if (step == 1)
-        dmin = fminf(fminf(fminf(a[0][i], a[0][i + 1]), fminf(a[0][i + 2], a[1][i])), fminf(fminf(a[1][i + 2], a[2][i]), fminf(a[2][i + 1], a[2][i + 2])));
-      else
-        dmin = fminf(fminf(a[0][i + 1], a[2][i + 1]), fminf(a[1][i], a[1][i + 2]));
-      const bool keep = (m4[i] == 1) || ((em >> i) & 1u) || dmin < TD_MINEPS;
-      float v = keep ? z : FLT_MAX;
-      if (a[1][i + 1] < TD_MINEPS) v = TD_FELNODATA;
-      if (c + i >= s.nx) v = TD_FELNODATA;                       // padding columns
-      out[i] = v;
+      for (int i = 0; i < 6; ++i) col[i] = fminf(fminf(a[0][i], a[1][i]), a[2][i]);
+      float out[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float dmin;
+        if (step == 1) dmin = fminf(fminf(col[i], col[i + 1]), col[i + 2]);
+        else dmin = fminf(fminf(a[0][i + 1], a[2][i + 1]), fminf(a[1][i], a[1][i + 2]));
+        const bool keep = (m4[i] == 1) || ((em >> i) & 1u) || dmin < TD_MINEPS;
+        float v = keep ? z[i] : FLT_MAX;
+        if (a[1][i + 1] < TD_MINEPS) v = TD_FELNODATA;
+        if (c + i >= s.nx) v = TD_FELNODATA;                       // padding columns
+        out[i] = v;
+      }
+      *reinterpret_cast<float4*>(W + s.idx(r, c)) = make_float4(out[0], out[1], out[2], out[3]);
     }
-    *reinterpret_cast<float4*>(W + s.idx(r, c)) = make_float4(out[0], out[1], out[2], out[3]);
+    ring.release(&tm, t);
   }
 }
 
@@ -157,8 +164,12 @@ __global__ void k_fill_edge_flags(const int* list, int* flag, int nedge) {
 }  // namespace
 
 int fill_init(const float* dem, const short* mask, float* W, const Strip& s, float nodata, int four, cudaStream_t st) {
-  dim3 grid((s.pitch + IW - 1) / IW, (s.ny + IH - 1) / IH);
-  k_fill_init<<<grid, 256, 0, st>>>(dem, mask, W, s, nodata, four ? 2 : 1);
+  TileMap tm;
+  if (int rc = make_tile_map(&tm, dem, 4, s.pitch, s.ny + 2, InitRing::G::SW, InitRing::G::ROWS)) return rc;
+  const long long ntiles = (long long)((s.pitch + IW - 1) / IW) * ((s.ny + IH - 1) / IH);
+  int grid = 0;
+  if (int rc = stencil_grid((const void*)k_fill_init, 256, InitRing::SMEM, ntiles, &grid)) return rc;
+  k_fill_init<<<grid, 256, InitRing::SMEM, st>>>(tm, mask, W, s, nodata, four ? 2 : 1);
   TD_LAUNCHED();
   TD_CUDA(cudaGetLastError());
   return TD_OK;

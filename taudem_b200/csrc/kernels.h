@@ -19,9 +19,19 @@ cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned ch
 cudaError_t zero_words(void* p, size_t bytes, cudaStream_t st);     // a multiple of 4 bytes, zeroed by a kernel (never by a copy engine)
 int wsweep_begin(td_ctx* ctx, const Strip& s, cudaStream_t st);
 int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int* dec_bot, cudaStream_t st);
+// the extra grids of the concentration- and transport-limited accumulations (algebras 7-9 of the D-infinity sweep, sweep_warp.cu)
+struct SweepExtra {
+  const short* dg = nullptr;       // ALG 7: indicator grid (> 0: the cell is a source at the solubility threshold)
+  float csol = 0.f;                // ALG 7: the concentration of such a cell
+  const float* cin = nullptr;      // ALG 9: concentration of the supply
+  float cin_nodata = 0.f;
+  float* out2 = nullptr;           // ALG 8 / 9: deposition (written, never read; must start as nodata)
+  float* out3 = nullptr;           // ALG 9: concentration in the transported flux (written and read by receivers; must start as nodata)
+};
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
                int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg = 0, const float* dm = nullptr,
-               float dm_nodata = 0.f, const float* dist = nullptr);
+               float dm_nodata = 0.f, const float* dist = nullptr, const SweepExtra* extra = nullptr);
+cudaError_t fill_floats(float* p, const Strip& s, float v, cudaStream_t st);   // every cell of the strip := v
 int sweep_restrict_round(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, const int* in_top, const int* in_bot,
                          int* req_out, int finish, cudaStream_t st);
 int sweep_restrict_upstream(td_ctx* ctx, const Strip& s, const int* cols, const int* rows, int nout, cudaStream_t st);

@@ -107,6 +107,7 @@ struct WArgs {
   int ntx, nty, th;        // tiles of the strip, tile height
   const float* dm; float dm_nodata;   // ALG 3: the decay multiplier grid (strip layout) and its nodata; ALG 4-6: the mask grid (0 = outside) or NULL
   const float* dist;                  // ALG 4-6: cell-to-cell distances, [row][direction - 1] (float, like src/gridnet.cpp:190-200)
+  SweepExtra x;                       // ALG 7-9: indicator grid / solubility, supply concentration, deposition and concentration outputs
   int* state;              // per tile: 0 idle, 1 queued, 2 running, 3 running + re-activated
   int* tq;                 // ring of tile ids + 1
   unsigned qmask;          // slots of one shard's ring - 1
@@ -130,6 +131,7 @@ template <typename T> __device__ __forceinline__ T ldv(const T* p) { emu::yield(
 #else
 template <typename T> __device__ __forceinline__ T ldv(const T* p) { return *((const volatile T*)p); }
 #endif
+template <typename T> __device__ __forceinline__ void stv(T* p, T v) { *((volatile T*)p) = v; }
 
 #ifndef TD_EMU
 __device__ __forceinline__ void cp16(void* smem, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory"); }
@@ -314,7 +316,17 @@ __device__ void sched_finish(const WArgs& a, int t) {
 __global__ void k_zero_words(unsigned* p, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
 }
+__global__ void k_fill_floats(float* p, size_t n, float v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
 }  // namespace
+cudaError_t fill_floats(float* p, const Strip& s, float v, cudaStream_t st) {
+  const size_t n = (size_t)s.cells();
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
+  k_fill_floats<<<grid ? grid : 1, 256, 0, st>>>(p, n, v);
+  TD_LAUNCHED();
+  return cudaGetLastError();
+}
 cudaError_t zero_words(void* p, size_t bytes, cudaStream_t st) {
   const size_t n = bytes / 4;
   const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 16);
@@ -360,7 +372,13 @@ __device__ __forceinline__ unsigned zero_nibble(unsigned w) {
 // per contributor  + (float)(dm * area * p)  with the contributor's decay multiplier dm; a nodata multiplier contaminates).
 // D8 only: 4 / 5 / 6 = gridnet's longest upstream path length, total upstream path length and Strahler order (src/gridnet.cpp:383-420;
 // three sweeps, one value each; `dm` = mask grid: cells outside are not evaluated (they get w_nodata) and contribute nothing).
-// Results of ALG 1-3 use MISSINGFLOAT as nodata, the others -1.
+// D-infinity only, one chain per lane throughout (no warp-cooperative tail): 7 = concentration limited accumulation (DinfConcLimAccum,
+// src/DinfConcLimAccum.cpp:235-272; `w` = the specific discharge q, `dm` = the decay multiplier, x.dg = the indicator grid);
+// 8 / 9 = transport limited accumulation without / with a concentration (DinfTransLimAccum, src/DinfTransLimAccum.cpp:237-304;
+// `w` = supply, `dm` = transport capacity, the value that travels is the transport out of the cell; deposition goes straight to
+// x.out2; with a concentration (9) a second value travels: it lives in global memory (x.out3) — written before the receivers'
+// counts are touched, read past the L1 — because a worker's shared memory holds one value per cell).
+// Results of ALG 1-3 and 7-9 use MISSINGFLOAT as nodata, the others -1.
 // gridnet's cell evaluation (src/gridnet.cpp:383-420): contributors = the neighbours that drain into the cell (mask bits) with a
 // direction > 0 and inside the mask; all arithmetic in float like the reference's float dist table and float partitions.
 template <int ALG, typename Mem>
@@ -395,7 +413,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
   const unsigned lt = (1u << lane) - 1u;
   Mem& M = *reinterpret_cast<Mem*>(dsm + (size_t)wid * sizeof(Mem));
   const int myq = (int)((blockIdx.x * (blockDim.x >> 5) + (unsigned)wid) & (unsigned)(a.nsh - 1));   // this worker's queue shard
-  const float NOD = (ALG == 0 || ALG >= 4) ? -1.0f : TD_MISSINGFLOAT;      // the result raster's nodata: not evaluated / contaminated
+  const float NOD = (ALG == 0 || (ALG >= 4 && ALG <= 6)) ? -1.0f : TD_MISSINGFLOAT;      // the result raster's nodata: not evaluated / contaminated
   __shared__ Sector sect[9];
   if (DINF) {
     if (threadIdx.x < 9) { const int j = (int)threadIdx.x; sect[j].lo = a.prop.ar[j]; sect[j].hi = a.prop.ar[j + 1]; sect[j].den = a.prop.den[j]; sect[j].rden = a.prop.rden[j]; }
@@ -504,7 +522,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
         }
       }
       const unsigned act = __ballot_sync(FULL, cur >= 0);
-      if (act != 0u && (act & (act - 1u)) == 0u) {
+      if (ALG < 7 && act != 0u && (act & (act - 1u)) == 0u) {
         // ---- one chain left (a river crossing the tile, the tail of every visit; the fork stack is empty, or idle lanes
         // would have taken from it): the WHOLE warp follows it together.  Nothing diverges and nothing is contended: the cell
         // is warp-uniform, lanes 0..7 evaluate one contributor link each (D-infinity), everybody folds the products in
@@ -674,6 +692,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
           // dinf_outflow form; irregular cells and strips without a common table take the interval search.
           const int r = r0 + lr;
           val = 0.f;
+          float loadin = 0.f;                                    // ALG 9: the load of the second substance that arrives
           if (ALG == 3) val = USEW ? wv : (float)(a.prop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]);
 #pragma unroll 1
           for (unsigned m = msk; m; m &= m - 1u) {               // increasing k: the reference's order of additions
@@ -703,9 +722,56 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
               const float dmv = __ldg(a.dm + s.idx(r + dr, c0 + lx + lut_dcol(k)));
               if (nd_f(an, NOD) || nd_f(dmv, a.dm_nodata)) con = true;
               else val = val + (float)((double)(dmv * an) * p);
+            } else if (ALG == 7) {
+              // src/DinfConcLimAccum.cpp:252-262: Concentration += p * ctpt * q * dm of the contributor (double products, float sum)
+              const long long gi = s.idx(r + dr, c0 + lx + lut_dcol(k));
+              const float qq = __ldg(a.w + gi), dmm = __ldg(a.dm + gi);
+              if (nd_f(an, NOD) || nd_f(dmm, a.dm_nodata) || nd_f(qq, a.w_nodata)) con = true;
+              else val = (float)((double)val + ((p * (double)an) * (double)qq) * (double)dmm);
+            } else if (ALG == 8 || ALG == 9) {
+              // src/DinfTransLimAccum.cpp:252-266: transin += p * transport of the contributor; loadin += p * that transport * its concentration
+              float nt = 0.f;
+              if (nd_f(an, NOD)) con = true; else { val = (float)((double)val + p * (double)an); nt = an; }
+              if (ALG == 9) {
+                const float cn = ldv(a.x.out3 + s.idx(r + dr, c0 + lx + lut_dcol(k)));
+                if (nd_f(cn, NOD)) con = true; else loadin = (float)((double)loadin + (p * (double)nt) * (double)cn);
+              }
             } else if (nd_f(an, NOD)) con = true; else val = (float)((double)val + p * (double)an);
           }
           if (ALG == 3) {}
+          else if (ALG == 7) {
+            // src/DinfConcLimAccum.cpp:242-270: only cells with a positive discharge have a concentration; an indicator cell is a
+            // source at the solubility (its neighbours are not looked at: it cannot be contaminated)
+            const float dgv = (float)a.x.dg[s.idx(r, c0 + lx)];
+            if (!(wv > 0.f)) { val = NOD; con = false; }
+            else if (dgv > 0.f) { val = a.x.csol; con = false; }
+            else val = val / wv;
+          } else if (ALG == 8 || ALG == 9) {
+            // src/DinfTransLimAccum.cpp:237-238,268-302: cells whose supply, capacity (or supply concentration) is nodata are not evaluated
+            const long long gc = s.idx(r, c0 + lx);
+            const float tcc = __ldg(a.dm + gc);
+            float cinv = 0.f;
+            bool ev = !nd_f(wv, a.w_nodata) && !nd_f(tcc, a.dm_nodata);
+            if (ALG == 9) { cinv = __ldg(a.x.cin + gc); ev = ev && !nd_f(cinv, a.x.cin_nodata); }
+            if (!ev) { val = NOD; con = false; }
+            else {
+              const float transin = val;
+              float transout, depp;
+              if ((transin + wv) > tcc) { transout = tcc; depp = transin + wv - transout; }
+              else { transout = transin + wv; depp = 0.f; }
+              float cs = 0.f;
+              if (ALG == 9) {
+                float loadout;
+                if (transout < transin) loadout = transin > 0.f ? loadin * transout / transin : 0.f;      // no erosion from the cell
+                else loadout = loadin + cinv * (transout - transin);
+                cs = transout > 0.f ? loadout / transout : 0.f;
+              }
+              const bool bad = con && a.contcheck;
+              a.x.out2[gc] = bad ? NOD : depp;
+              if (ALG == 9) { stv(a.x.out3 + gc, bad ? NOD : cs); __threadfence_block(); }
+              val = transout;
+            }
+          }
           else if (USEW) val = val + wv;
           else val = (float)((double)val + (a.prop.uniform ? a.dx0 : a.dxc[min(r, s.ny) - 1]));
         }
@@ -921,15 +987,21 @@ int wsweep_apply_halo(td_ctx* ctx, const Strip& s, const int* dec_top, const int
 // Runs the evaluation wavefront over the queued tiles until no tile of the strip has a ready cell left.
 int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float* ang, const Strip& s, float w_nodata, int usew,
                int contcheck, const double* theta, const double* dxc, int* halo, cudaStream_t st, int alg, const float* dm, float dm_nodata,
-               const float* dist) {
-  if (alg < 0 || alg > 6 || ((alg == 1 || alg == 2) && (dinf || !usew)) || (alg == 3 && (!dinf || !dm)) || (alg >= 4 && (dinf || usew || !dist))) {
+               const float* dist, const SweepExtra* extra) {
+  if (alg < 0 || alg > 9 || ((alg == 1 || alg == 2) && (dinf || !usew)) || (alg == 3 && (!dinf || !dm)) || (alg >= 4 && alg <= 6 && (dinf || usew || !dist))) {
     set_error("wsweep_run: the extreme-value algebra is a D8 sweep over a value grid, the decaying accumulation a D-infinity sweep with a multiplier grid");
+    return TD_ERR_ARG;
+  }
+  if (alg >= 7 && (!dinf || !usew || !w || !dm || !extra || (alg == 7 && !extra->dg) || (alg >= 8 && !extra->out2) || (alg == 9 && (!extra->cin || !extra->out3)) ||
+                   ctx->peer_on || s.has_top || s.has_bot)) {
+    set_error("wsweep_run: the concentration / transport limited accumulations are single-strip D-infinity sweeps with all their grids");
     return TD_ERR_ARG;
   }
   WArgs a;
   if (int rc = wargs(ctx, a, s)) return rc;
   a.area = area; a.w = w; a.ang = ang; a.usew = usew; a.contcheck = contcheck;
   a.w_nodata = w_nodata; a.theta = theta; a.dxc = dxc; a.halo = halo; a.dm = dm; a.dm_nodata = dm_nodata; a.dist = dist;
+  if (extra) a.x = *extra;
   a.prop = ctx->prop;
   if (!dinf) a.prop.uniform = 0;
   a.peer = ctx->peer_on;
@@ -954,13 +1026,14 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   if (const char* we = getenv("TAUDEM_B200_WORKERS")) { const int v = atoi(we); if (v >= 1 && v < warps) warps = v; }   // experiments: fewer workers per SM
   size_t smem = (dinf ? sizeof(WarpMem<true>) : sizeof(WarpMem<false>)) * (size_t)warps;
   if (const char* pe2 = getenv("TAUDEM_B200_SMEMPAD")) smem = std::max(smem, (size_t)atoi(pe2));                  // experiments: one CTA per SM whatever its size
-  const void* kern = alg == 4 ? (const void*)k_sweep_warp<false, false, 4> : alg == 5 ? (const void*)k_sweep_warp<false, false, 5>
+  const void* kern = alg == 7 ? (const void*)k_sweep_warp<true, true, 7> : alg == 8 ? (const void*)k_sweep_warp<true, true, 8>
+                   : alg == 9 ? (const void*)k_sweep_warp<true, true, 9> : alg == 4 ? (const void*)k_sweep_warp<false, false, 4> : alg == 5 ? (const void*)k_sweep_warp<false, false, 5>
                    : alg == 6 ? (const void*)k_sweep_warp<false, false, 6>
                    : alg == 3 ? (usew ? (const void*)k_sweep_warp<true, true, 3> : (const void*)k_sweep_warp<true, false, 3>)
                    : dinf ? (usew ? (const void*)k_sweep_warp<true, true, 0> : (const void*)k_sweep_warp<true, false, 0>)
                           : alg == 1 ? (const void*)k_sweep_warp<false, true, 1> : alg == 2 ? (const void*)k_sweep_warp<false, true, 2>
                           : (usew ? (const void*)k_sweep_warp<false, true, 0> : (const void*)k_sweep_warp<false, false, 0>);
-  int& per_dev = ctx->wgrid[alg >= 4 ? 4 + alg : alg == 3 ? 6 + (usew ? 1 : 0) : alg ? 3 + alg : (dinf ? 2 : 0) + (usew ? 1 : 0)];
+  int& per_dev = ctx->wgrid[alg >= 7 ? 6 + alg : alg >= 4 ? 4 + alg : alg == 3 ? 6 + (usew ? 1 : 0) : alg ? 3 + alg : (dinf ? 2 : 0) + (usew ? 1 : 0)];
   if (!per_dev || getenv("TAUDEM_B200_WORKERS")) {
     int dev = 0, sms = 0, occ = 0;
     TD_CUDA(cudaGetDevice(&dev));
@@ -972,7 +1045,10 @@ int wsweep_run(td_ctx* ctx, bool dinf, float* area, const float* w, const float*
   }
   const long long nt = (long long)a.ntx * a.nty;
   const int g = (int)std::min<long long>(per_dev, (nt + warps - 1) / warps);
-  if (alg == 4) k_sweep_warp<false, false, 4><<<g, warps * 32, smem, st>>>(a);
+  if (alg == 7) k_sweep_warp<true, true, 7><<<g, warps * 32, smem, st>>>(a);
+  else if (alg == 8) k_sweep_warp<true, true, 8><<<g, warps * 32, smem, st>>>(a);
+  else if (alg == 9) k_sweep_warp<true, true, 9><<<g, warps * 32, smem, st>>>(a);
+  else if (alg == 4) k_sweep_warp<false, false, 4><<<g, warps * 32, smem, st>>>(a);
   else if (alg == 5) k_sweep_warp<false, false, 5><<<g, warps * 32, smem, st>>>(a);
   else if (alg == 6) k_sweep_warp<false, false, 6><<<g, warps * 32, smem, st>>>(a);
   else if (alg == 3) { if (usew) k_sweep_warp<true, true, 3><<<g, warps * 32, smem, st>>>(a); else k_sweep_warp<true, false, 3><<<g, warps * 32, smem, st>>>(a); }

@@ -127,6 +127,15 @@ void nodata_msgs(double nd, const char* what, double cast) {
   printf("Nodata value input to create partition from file: %lf\n", nd);
   printf("Nodata value recast to %s used in partition raster: %s\n", what, std::to_string(cast).c_str());
 }
+// one more float (or int16) grid of a sibling tool: open, compare with the angle grid, read
+template <typename T>
+int companion(Input& a, Input& g, const char* file, std::vector<T>* data, tdio::DType dt, const char* type) {
+  if (int rc = g.open(file)) return rc;
+  if (!tdio::compare_rasters(a.r, a.path, g.r, g.path)) { printf("File sizes do not match\n%s\n", file); td::set_error("companion grid does not match"); return TD_ERR_MISMATCH; }
+  if (dt == tdio::DT_F32) nodata_msgs(g.r.nodata(), type, (float)g.r.nodata()); else nodata_msgs(g.r.nodata(), type, (int16_t)g.r.nodata());
+  return g.read(data, dt);
+}
+
 }  // namespace
 
 extern "C" {
@@ -551,6 +560,81 @@ int td_dmarea(const char* angfile, const char* adecfile, const char* dmfile, con
   }
   const double t2 = now();
   if (int rc = write_like(adecfile, a, tdio::DT_F32, (double)-3.4028234663852886e38f, out)) return rc;
+  const double t3 = now();
+  printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
+// src/DinfConcLimAccum.cpp:61-347
+int td_dsllarea(const char* angfile, const char* ctptfile, const char* dmfile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno,
+                const char* qfile, const char* dgfile, int useOutlets, int contcheck, float cSol) try {
+  printf("DinfConcLimAccum version %s\n", td_version());
+  const double t0 = now();
+  Input a;
+  if (int rc = a.open(angfile)) return rc;
+  std::vector<int> ocols, orows;
+  if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, a, &ocols, &orows)) return rc; }
+  std::vector<float> ang, dm, q;
+  std::vector<int16_t> dg;
+  nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
+  if (int rc = a.read(&ang, tdio::DT_F32)) return rc;
+  Input d, g, qq;
+  if (int rc = companion(a, d, dmfile, &dm, tdio::DT_F32, "float")) return rc;
+  if (int rc = companion(a, g, dgfile, &dg, tdio::DT_I16, "int16_t")) return rc;
+  if (int rc = companion(a, qq, qfile, &q, tdio::DT_F32, "float")) return rc;
+  const double t1 = now();
+  std::vector<float> out((size_t)a.nx * a.ny);
+  if (int rc = td_dinfconclimaccum_host(ang.data(), dm.data(), q.data(), dg.data(), out.data(), a.nx, a.ny, (float)a.r.nodata(), (float)d.r.nodata(),
+                                        (float)qq.r.nodata(), cSol, a.dxc.data(), a.dyc.data(), contcheck, ocols.data(), orows.data(),
+                                        useOutlets == 1 ? (int)ocols.size() : -1)) {
+    printf("DinfConcLimAccum device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(ctptfile, a, tdio::DT_F32, (double)-3.4028234663852886e38f, out)) return rc;
+  const double t3 = now();
+  printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
+  printf("Device compute time: %f\n", td_last_compute_seconds());
+  return TD_OK;
+} catch (const std::exception& e) {
+  td::set_error(std::string("exception: ") + e.what());
+  return TD_ERR_IO;
+}
+
+// src/DinfTransLimAccum.cpp:61-394
+int td_tlaccum(const char* angfile, const char* tsupfile, const char* tcfile, const char* tlafile, const char* depfile, const char* cinfile,
+               const char* coutfile, const char* datasrc, const char* lyrname, int uselyrname, int lyrno, int useOutlets, int usec, int contcheck) try {
+  printf("DinfTransLimAccum version %s\n", td_version());
+  const double t0 = now();
+  Input a;
+  if (int rc = a.open(angfile)) return rc;
+  std::vector<int> ocols, orows;
+  if (useOutlets == 1) { if (int rc = outlet_cells(datasrc, lyrname, uselyrname, lyrno, a, &ocols, &orows)) return rc; }
+  std::vector<float> ang, tsup, tc, cin;
+  nodata_msgs(a.r.nodata(), "float", (float)a.r.nodata());
+  if (int rc = a.read(&ang, tdio::DT_F32)) return rc;
+  Input ts, tcc, ci;
+  if (int rc = companion(a, ts, tsupfile, &tsup, tdio::DT_F32, "float")) return rc;
+  if (int rc = companion(a, tcc, tcfile, &tc, tdio::DT_F32, "float")) return rc;
+  if (usec == 1) { if (int rc = companion(a, ci, cinfile, &cin, tdio::DT_F32, "float")) return rc; }
+  const double t1 = now();
+  const size_t n = (size_t)a.nx * a.ny;
+  std::vector<float> tla(n), dep(n), cout(usec == 1 ? n : 0);
+  if (int rc = td_dinftranslimaccum_host(ang.data(), tsup.data(), tc.data(), usec == 1 ? cin.data() : nullptr, tla.data(), dep.data(),
+                                         usec == 1 ? cout.data() : nullptr, a.nx, a.ny, (float)a.r.nodata(), (float)ts.r.nodata(), (float)tcc.r.nodata(),
+                                         usec == 1 ? (float)ci.r.nodata() : 0.f, a.dxc.data(), a.dyc.data(), contcheck, ocols.data(), orows.data(),
+                                         useOutlets == 1 ? (int)ocols.size() : -1)) {
+    printf("DinfTransLimAccum device error: %s\n", td_last_error());
+    return rc;
+  }
+  const double t2 = now();
+  if (int rc = write_like(tlafile, a, tdio::DT_F32, (double)-3.4028234663852886e38f, tla)) return rc;
+  if (int rc = write_like(depfile, a, tdio::DT_F32, (double)-3.4028234663852886e38f, dep)) return rc;
+  if (usec == 1) { if (int rc = write_like(coutfile, a, tdio::DT_F32, (double)-3.4028234663852886e38f, cout)) return rc; }
   const double t3 = now();
   printf("Processors: 1\nRead time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", t1 - t0, t2 - t1, t3 - t2, t3 - t0);
   printf("Device compute time: %f\n", td_last_compute_seconds());

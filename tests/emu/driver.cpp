@@ -122,6 +122,14 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
 static const float* g_dm = nullptr;
 static float g_dm_nodata = -9999.0f;
 extern "C" void emu_set_dm(const float* dm, float nodata) { g_dm = dm; g_dm_nodata = nodata; }
+// the extra grids of modes 16-18 (dense, ny x nx): indicator grid + solubility (16), supply concentration in / deposition out /
+// concentration out (17: deposition only)
+static const short* g_dg = nullptr; static float g_csol = 1.f;
+static const float* g_cin = nullptr; static float g_cin_nodata = -9999.0f;
+static float* g_out2 = nullptr; static float* g_out3 = nullptr;
+extern "C" void emu_set_extra(const short* dg, float csol, const float* cin, float cin_nodata, float* out2, float* out3) {
+  g_dg = dg; g_csol = csol; g_cin = cin; g_cin_nodata = cin_nodata; g_out2 = out2; g_out3 = out3;
+}
 
 // mode 0: k_ready + k_walk from the sources; mode 1: `passes` level passes first.  nstrips > 1 emulates the
 // exchange rounds of taudem_b200/dist.py::DistTools._sweep (linearpart partition, halo counts, area rows).
@@ -166,17 +174,41 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   // single strip: the exchange of halo areas with the -FLT_MAX nodata is the row-strip driver's business)
   // mode 12: the decaying accumulation of dinfdecayaccum (D-infinity, multiplier grid from emu_set_dm; single strip)
   // mode 13 / 14 / 15: gridnet's longest path, total path and Strahler order (D8; the emu_set_dm grid is the 0 / 1 mask, may be unset)
-  const int alg = mode == 10 ? 1 : mode == 11 ? 2 : mode == 12 ? 3 : mode >= 13 && mode <= 15 ? mode - 9 : 0;
-  if (alg >= 1 && alg <= 3) for (auto& T : S) std::fill(T.area.begin(), T.area.end(), -3.4028234663852886e38f);
+  // mode 16: DinfConcLimAccum (wgt = q, emu_set_dm = decay multiplier, emu_set_extra = indicator grid + solubility);
+  // mode 17 / 18: DinfTransLimAccum without / with a concentration (wgt = supply, emu_set_dm = capacity, emu_set_extra = the rest)
+  const int alg = mode == 10 ? 1 : mode == 11 ? 2 : mode == 12 ? 3 : mode >= 13 && mode <= 15 ? mode - 9 : mode >= 16 && mode <= 18 ? mode - 9 : 0;
+  td::SweepExtra X;
+  std::vector<short> dgstrip; std::vector<float> cinstrip, out2strip, out3strip;
+  if (alg >= 7) {
+    if (nstrips != 1 || !dinf || !usew || !g_dm) return 3;
+    const Strip& s = S[0].s;
+    const float MISS = -3.4028234663852886e38f;
+    if (alg == 7) {
+      if (!g_dg) return 3;
+      dgstrip.assign((size_t)s.cells(), 0);
+      for (int r = 1; r <= s.ny; ++r) for (int c = 0; c < nx; ++c) dgstrip[s.idx(r, c)] = g_dg[(size_t)(r - 1) * nx + c];
+      X.dg = dgstrip.data(); X.csol = g_csol;
+    } else {
+      if (!g_out2 || (alg == 9 && (!g_cin || !g_out3))) return 3;
+      out2strip.assign((size_t)s.cells(), MISS); X.out2 = out2strip.data();
+      if (alg == 9) {
+        out3strip.assign((size_t)s.cells(), MISS); X.out3 = out3strip.data();
+        cinstrip.assign((size_t)s.cells(), 0.f);
+        for (int r = 1; r <= s.ny; ++r) for (int c = 0; c < nx; ++c) cinstrip[s.idx(r, c)] = g_cin[(size_t)(r - 1) * nx + c];
+        X.cin = cinstrip.data(); X.cin_nodata = g_cin_nodata;
+      }
+    }
+  }
+  if ((alg >= 1 && alg <= 3) || alg >= 7) for (auto& T : S) std::fill(T.area.begin(), T.area.end(), -3.4028234663852886e38f);
   std::vector<float> dmstrip;
   std::vector<float> dist;
-  if (alg >= 4) {
+  if (alg >= 4 && alg <= 6) {
     if (nstrips != 1 || dinf) return 3;
     static const int e1[9] = {0, 1, 1, 0, -1, -1, -1, 0, 1}, e2[9] = {0, 0, -1, -1, -1, 0, 1, 1, 1};
     dist.assign((size_t)ny * 8, 0.f);
     for (int m = 0; m < ny; ++m) for (int k = 1; k <= 8; ++k) dist[(size_t)m * 8 + k - 1] = (float)sqrt(dx * dx * e1[k] * e1[k] + dy * dy * e2[k] * e2[k]);
   }
-  if (alg == 3 || (alg >= 4 && g_dm)) {
+  if (alg == 3 || alg >= 7 || (alg >= 4 && g_dm)) {
     if (!g_dm || nstrips != 1) return 3;
     const Strip& s = S[0].s;
     dmstrip.assign((size_t)s.cells(), 0.f);
@@ -191,7 +223,7 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
       int rc = first ? td::wsweep_begin(&T.ctx, T.s, nullptr) : 0;
       if (!rc)
         rc = td::wsweep_run(&T.ctx, dinf != 0, T.area.data(), usew ? T.w.data() : nullptr, T.ang.data(), T.s, w_nodata, usew, contcheck,
-                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr, alg, dmstrip.empty() ? nullptr : dmstrip.data(), g_dm_nodata, dist.empty() ? nullptr : dist.data());
+                            T.theta.data(), T.dxc.data(), T.halo.data(), nullptr, alg, dmstrip.empty() ? nullptr : dmstrip.data(), g_dm_nodata, dist.empty() ? nullptr : dist.data(), alg >= 7 ? &X : nullptr);
       if (rc) return rc;
     }
     first = false;
@@ -222,6 +254,14 @@ extern "C" int emu_sweep(int dinf, int mode, int passes, const void* dir, float*
   for (auto& T : S)
     for (int r = 1; r <= T.s.ny; ++r)
       for (int c = 0; c < nx; ++c) out[(size_t)(T.row0 + r - 1) * nx + c] = T.area[T.s.idx(r, c)];
+  if (alg >= 8) {
+    const Strip& s = S[0].s;
+    for (int r = 1; r <= s.ny; ++r)
+      for (int c = 0; c < nx; ++c) {
+        g_out2[(size_t)(r - 1) * nx + c] = out2strip[s.idx(r, c)];
+        if (alg == 9) g_out3[(size_t)(r - 1) * nx + c] = out3strip[s.idx(r, c)];
+      }
+  }
   return 0;
 }
 

@@ -62,6 +62,8 @@ def _build(tag="", defines=()):
     P = C.c_void_p
     lib.emu_set_dm.argtypes = [C.c_void_p, C.c_float]
     lib.emu_set_dm.restype = None
+    lib.emu_set_extra.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    lib.emu_set_extra.restype = None
     lib.emu_d8_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
     lib.emu_dinf_stencil.argtypes = [P, P, P, C.c_int, C.c_int, C.c_float, C.c_double, C.c_double, P]
     lib.emu_deps_d8.argtypes = [P, P, P, P, C.c_int, C.c_int, C.c_short]
@@ -161,6 +163,63 @@ def test_emulated_dinf_decay_accumulation(emu, fields):
     R = refrun.RefPipeline()
     assert_bits(_run(emu, True, 12, 0, ang, None, True, 41), R.dinfdecayaccum(ang, dm), "dsca")
     assert_bits(_run(emu, True, 12, 0, ang, w, False, 42), R.dinfdecayaccum(ang, dm, weights=w, contcheck=False), "dsca -wg -nc")
+
+
+def _sibling_grids(shape, seed):
+    """q / supply-like positive grids with a few nodata and non-positive cells, an indicator grid, a capacity grid"""
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(0.5, 3.0, shape).astype(np.float32)
+    q[rng.random(shape) < 0.003] = -9999.0
+    q[rng.random(shape) < 0.003] = 0.0
+    dm = rng.uniform(0.2, 1.0, shape).astype(np.float32)
+    dm[rng.random(shape) < 0.002] = -9999.0
+    dg = (rng.random(shape) < 0.02).astype(np.int16)
+    tc = rng.uniform(0.0, 8.0, shape).astype(np.float32)
+    tc[rng.random(shape) < 0.002] = -9999.0
+    cs = rng.uniform(0.0, 2.0, shape).astype(np.float32)
+    cs[rng.random(shape) < 0.002] = -9999.0
+    return q, dm, dg, tc, cs
+
+
+def test_emulated_dinf_conc_lim_accumulation(emu, fields):
+    """DinfConcLimAccum = the D-infinity sweep with the concentration-limited algebra (7), against the reference executable
+    (oracle/_ref/dinfconclimaccum: DinfConcLimAccum.cpp compiled unchanged); with and without contamination checking."""
+    import refrun
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "dinfconclimaccum"), os.X_OK):
+        pytest.skip("oracle/_ref/dinfconclimaccum is not built")
+    port, _, ang, _ = fields
+    q, dm, dg, _, _ = _sibling_grids(ang.shape, 23)
+    dmc, dgc = np.ascontiguousarray(dm), np.ascontiguousarray(dg)
+    emu.emu_set_dm(dmc.ctypes.data, C.c_float(-9999.0))
+    emu.emu_set_extra(dgc.ctypes.data, C.c_float(2.5), None, C.c_float(0.0), None, None)
+    R = refrun.RefPipeline()
+    assert_bits(_run(emu, True, 16, 0, ang, q, True, 61), R.dinfconclimaccum(ang, dm, q, dg, csol=2.5), "ctpt")
+    assert_bits(_run(emu, True, 16, 0, ang, q, False, 62), R.dinfconclimaccum(ang, dm, q, dg, csol=2.5, contcheck=False), "ctpt -nc")
+    emu.emu_set_dm(None, C.c_float(0.0))
+
+
+def test_emulated_dinf_trans_lim_accumulation(emu, fields):
+    """DinfTransLimAccum = the D-infinity sweep with the transport-limited algebra (8; 9 with a concentration that travels in global
+    memory), against the reference executable (oracle/_ref/dinftranslimaccum: DinfTransLimAccum.cpp compiled unchanged)."""
+    import refrun
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "dinftranslimaccum"), os.X_OK):
+        pytest.skip("oracle/_ref/dinftranslimaccum is not built")
+    port, _, ang, _ = fields
+    tsup, _, _, tc, cs = _sibling_grids(ang.shape, 29)
+    tcc, csc = np.ascontiguousarray(tc), np.ascontiguousarray(cs)
+    dep, cout = np.empty(ang.shape, np.float32), np.empty(ang.shape, np.float32)
+    emu.emu_set_dm(tcc.ctypes.data, C.c_float(-9999.0))
+    R = refrun.RefPipeline()
+    emu.emu_set_extra(None, C.c_float(0.0), None, C.c_float(0.0), dep.ctypes.data, None)
+    tla = _run(emu, True, 17, 0, ang, tsup, True, 71)
+    rt, rd, _ = R.dinftranslimaccum(ang, tsup, tc)
+    assert_bits(tla, rt, "tla"); assert_bits(dep, rd, "tdep")
+    for contcheck, seed in ((True, 72), (False, 73)):
+        emu.emu_set_extra(None, C.c_float(0.0), csc.ctypes.data, C.c_float(-9999.0), dep.ctypes.data, cout.ctypes.data)
+        tla = _run(emu, True, 18, 0, ang, tsup, contcheck, seed)
+        rt, rd, rc = R.dinftranslimaccum(ang, tsup, tc, cs=cs, contcheck=contcheck)
+        assert_bits(tla, rt, "tla (cs)"); assert_bits(dep, rd, "tdep (cs)"); assert_bits(cout, rc, "ctpt")
+    emu.emu_set_dm(None, C.c_float(0.0))
 
 
 def test_emulated_gridnet(emu, fields):

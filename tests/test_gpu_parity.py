@@ -430,6 +430,77 @@ def test_dinf_decay_accumulation(refrun, tmp_path):
     assert_bits(td.read_raster(out), ref, "dinfdecayaccum -o (files)")
 
 
+def _sibling_inputs(shape, seed):
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(0.5, 3.0, shape).astype(np.float32)
+    q[rng.random(shape) < 0.001] = -9999.0
+    q[rng.random(shape) < 0.001] = 0.0
+    dm = rng.uniform(0.2, 1.0, shape).astype(np.float32)
+    dm[rng.random(shape) < 0.0005] = -9999.0
+    dg = (rng.random(shape) < 0.02).astype(np.int16)
+    tc = rng.uniform(0.0, 8.0, shape).astype(np.float32)
+    tc[rng.random(shape) < 0.0005] = -9999.0
+    cs = rng.uniform(0.0, 2.0, shape).astype(np.float32)
+    cs[rng.random(shape) < 0.0005] = -9999.0
+    return q, dm, dg, tc, cs
+
+
+def test_dinf_conc_lim_and_trans_lim_accumulation(refrun, tmp_path):
+    """DinfConcLimAccum and DinfTransLimAccum (the last two siblings of areadinf on the same sweep) against the
+    reference executables (oracle/_ref/dinfconclimaccum, dinftranslimaccum): with and without contamination checking, with and without
+    the concentration that travels with the transport, outlets; grid level and our executables, bit for bit."""
+    import os
+    import subprocess
+    from util import write_point_shapefile
+    if not os.access(os.path.join(os.path.dirname(refrun.__file__), "_ref", "dinftranslimaccum"), os.X_OK):
+        pytest.skip("oracle/_ref/dinfconclimaccum and dinftranslimaccum are not built")
+    dem = synth.punch_holes(synth.gen_dem(340, 430, hurst=0.8, tilt=1.0, seed=47))
+    fel = td.pitremove_grid(dem); ang, _ = td.dinfflowdir_grid(fel)
+    q, dm, dg, tc, cs = _sibling_inputs(ang.shape, 11)
+    R = refrun.RefPipeline(workdir=str(tmp_path))
+    ny, nx = ang.shape
+    order = np.argsort(td.areadinf_grid(ang, contcheck=False).ravel())
+    cells = [int(order[-1]), int(order[-40]), int(order[-700])]
+    cols = [c % nx for c in cells]; rows = [c // nx for c in cells]
+    dx = dy = 30.0
+    shp = str(tmp_path / "outlets.shp")
+    write_point_shapefile(shp, [(c + 0.5) * dx for c in cols], [dy * ny - (r + 0.5) * dy for r in rows])
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # concentration limited
+    assert_bits(td.dinfconclimaccum_grid(ang, dm, q, dg, csol=2.5), R.dinfconclimaccum(ang, dm, q, dg, csol=2.5), "ctpt")
+    assert_bits(td.dinfconclimaccum_grid(ang, dm, q, dg, contcheck=False), R.dinfconclimaccum(ang, dm, q, dg, contcheck=False), "ctpt -nc")
+    ref = R.dinfconclimaccum(ang, dm, q, dg, csol=0.75, contcheck=False, outlets=shp)
+    assert_bits(td.dinfconclimaccum_grid(ang, dm, q, dg, csol=0.75, contcheck=False, outlets=(cols, rows)), ref, "ctpt -o")
+    out = str(tmp_path / "ours_ctpt.tif")
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "dinfconclimaccum"), "-ang", str(tmp_path / "angin.tif"), "-dm", str(tmp_path / "dm.tif"),
+                        "-q", str(tmp_path / "q.tif"), "-dg", str(tmp_path / "dg.tif"), "-ctpt", out, "-csol", "0.75", "-nc", "-o", shp],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "rror" not in r.stdout, r.stdout
+    assert_bits(td.read_raster(out), ref, "dinfconclimaccum -o (files)")
+    MISSINGFLOAT = np.float32(-3.4028234663852886e38)
+    assert (ref != MISSINGFLOAT).mean() > 0.02
+    # transport limited
+    tsup = q
+    for kw in ({}, {"contcheck": False}, {"cs": cs}, {"cs": cs, "contcheck": False}):
+        ours = td.dinftranslimaccum_grid(ang, tsup, tc, **kw)
+        refs = R.dinftranslimaccum(ang, tsup, tc, **kw)
+        for o, f, name in zip(ours, refs, ("tla", "tdep", "ctpt")):
+            if f is not None:
+                assert_bits(o, f, f"{name} {kw.keys()}")
+    assert (refs[0] != MISSINGFLOAT).mean() > 0.5 and (refs[1] > 0).mean() > 0.1
+    refs = R.dinftranslimaccum(ang, tsup, tc, cs=cs, contcheck=False, outlets=shp)
+    ours = td.dinftranslimaccum_grid(ang, tsup, tc, cs=cs, contcheck=False, outlets=(cols, rows))
+    for o, f, name in zip(ours, refs, ("tla", "tdep", "ctpt")):
+        assert_bits(o, f, name + " -o")
+    outs = [str(tmp_path / f"ours_{n}.tif") for n in ("tla", "tdep", "ctptout")]
+    r = subprocess.run([os.path.join(root, "taudem_b200", "bin", "dinftranslimaccum"), "-ang", str(tmp_path / "angin.tif"), "-tsup", str(tmp_path / "tsup.tif"),
+                        "-tc", str(tmp_path / "tc.tif"), "-cs", str(tmp_path / "cs.tif"), "-ctpt", outs[2], "-tla", outs[0], "-tdep", outs[1], "-nc", "-o", shp],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "rror" not in r.stdout, r.stdout
+    for o, f, name in zip(outs, refs, ("tla", "tdep", "ctpt")):
+        assert_bits(td.read_raster(o), f, name + " -o (files)")
+
+
 def test_pointwise_consumers_threshold_and_twi(refrun, tmp_path):
     """threshold and twi on the rasters of the path: grid level and our executables against the
     reference executables (oracle/_ref/threshold, oracle/_ref/twi: Threshold.cpp / TWI.cpp compiled unchanged).  src is
