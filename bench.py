@@ -110,6 +110,7 @@ def build_inputs(T, n, torch):
         return r
 
     dem = T.gen_dem(s, seed=SEED, hurst=HURST, tilt=TILT)
+    T.flood_init(s, dem)              # first launch of the kernel: module load, tensor map, occupancy query (like the stencils below)
     fel = timed("pitremove_init", lambda: T.flood_init(s, dem))
     timed("pitremove_relax", lambda: T.flood_relax(s, dem, fel))
     del dem

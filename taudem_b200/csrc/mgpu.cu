@@ -41,6 +41,8 @@ struct Shared {
   std::atomic<long long> handed[2];            // rounds mode: decrements handed over in this round (by round parity)
   double secs[MAXR];
   int rounds;
+  long long flats_left;
+  unsigned long long red[MAXR][8];             // allreduce_sum staging
   unsigned char handles[MAXR][320];
   int meta[MAXR][8];
   int device[MAXR], can_peer[MAXR];
@@ -221,6 +223,140 @@ void worker(const MgpuJob& J, Shared* S, char* extra, int rank, int world) {
   td_ctx_destroy(ctx);
   cudaFree(d_dir); cudaFree(d_out); cudaFree(d_halo); cudaFree(d_w); cudaFree(d_dx);
 }
+
+// ---- pitremove / d8flowdir / dinfflowdir on row strips.  What the reference does with linearpart::share() and MPI_Allreduce
+// (src/flood.cpp:344,401,468; src/d8.cpp:549-668) goes through the shared mapping: every rank has four row slots of 8 bytes per
+// cell (its first / last owned row, its two halo rows) and a line of eight words for the sums.
+struct RowSlots {
+  static size_t bytes(int pitch) { return (size_t)pitch * 8 * 4; }
+  char* base; int pitch;
+  char* slot(int rank, int which) const { return base + bytes(pitch) * rank + (size_t)which * pitch * 8; }
+};
+struct StripComm {
+  Shared* S; RowSlots R; int rank, world; td_strip s; cudaStream_t st;
+  bool bar() const { return barrier(S, world); }
+  // first / last owned row -> the halo rows of the strips above / below
+  int share(void* arr, int eb) const {
+    if (eb > 8) return 1;
+    const size_t rb = (size_t)s.pitch * eb;
+    char* a = (char*)arr;
+    if (cudaMemcpyAsync(R.slot(rank, 0), a + rb, rb, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaMemcpyAsync(R.slot(rank, 1), a + rb * (size_t)s.ny, rb, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    if (!bar()) return 1;
+    if (rank > 0 && cudaMemcpyAsync(a, R.slot(rank - 1, 1), rb, cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
+    if (rank < world - 1 && cudaMemcpyAsync(a + rb * (size_t)(s.ny + 1), R.slot(rank + 1, 0), rb, cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    return bar() ? 0 : 1;
+  }
+  // the reverse: what the neighbours hold in their halo rows for my first / last row
+  int collect(const void* arr, int eb, void* recv_top, void* recv_bot) const {
+    if (eb > 8) return 1;
+    const size_t rb = (size_t)s.pitch * eb;
+    const char* a = (const char*)arr;
+    if (cudaMemcpyAsync(R.slot(rank, 2), a, rb, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaMemcpyAsync(R.slot(rank, 3), a + rb * (size_t)(s.ny + 1), rb, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    if (!bar()) return 1;
+    if (rank > 0 && recv_top && cudaMemcpyAsync(recv_top, R.slot(rank - 1, 3), rb, cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
+    if (rank < world - 1 && recv_bot && cudaMemcpyAsync(recv_bot, R.slot(rank + 1, 2), rb, cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
+    return bar() ? 0 : 1;
+  }
+  int allreduce_sum(unsigned long long* v, int n) const {
+    if (n > 8) return 1;
+    for (int i = 0; i < n; ++i) S->red[rank][i] = v[i];
+    if (!bar()) return 1;
+    for (int i = 0; i < n; ++i) { unsigned long long t = 0; for (int r = 0; r < world; ++r) t += S->red[r][i]; v[i] = t; }
+    return bar() ? 0 : 1;
+  }
+};
+int cb_share(void* u, void* arr, int eb) { return ((const StripComm*)u)->share(arr, eb); }
+int cb_collect(void* u, const void* arr, int eb, void* rt, void* rb) { return ((const StripComm*)u)->collect(arr, eb, rt, rb); }
+int cb_allreduce(void* u, unsigned long long* v, int n) { return ((const StripComm*)u)->allreduce_sum(v, n); }
+
+void flow_worker(const MgpuFlowJob& J, Shared* S, char* extra, int rank, int world) {
+  int ndev = 0;
+  MG_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) throw Fail{"no CUDA device"};
+  MG_CUDA(cudaSetDevice(rank % ndev));
+  cudaStream_t st;
+  MG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  tdio::Raster in, mk;
+  std::string err;
+  if (!in.open(J.demfile, &err)) throw Fail{"open " + std::string(J.demfile) + ": " + err};
+  const int nx = (int)in.width(), total_ny = (int)in.height();
+  if (J.tool == 0 && J.use_mask && !mk.open(J.maskfile, &err)) throw Fail{"open " + std::string(J.maskfile) + ": " + err};
+  int row0, ny;
+  partition(total_ny, world, rank, &row0, &ny);
+  td_strip s;
+  s.nx = nx; s.ny = ny; s.pitch = td_pitch_for(nx); s.has_top = rank > 0; s.has_bot = rank < world - 1;
+  const size_t cells = (size_t)(ny + 2) * s.pitch;
+  float *d_z = nullptr, *d_f = nullptr, *d_slp = nullptr; void* d_dir = nullptr; int16_t* d_mask = nullptr; double* d_dx = nullptr;
+  MG_CUDA(cudaMalloc(&d_z, cells * 4));
+  load_strip(in, tdio::DT_F32, d_z, nx, s.pitch, row0, ny, total_ny, st);
+  td_ctx* ctx = td_ctx_create();
+  if (!ctx) throw Fail{"td_ctx_create failed"};
+  const StripComm C{S, RowSlots{extra, s.pitch}, rank, world, s, st};
+  td_strip_comm comm;
+  comm.user = (void*)&C; comm.share = cb_share; comm.collect = cb_collect; comm.allreduce_sum = cb_allreduce;
+  MG_BAR();
+  const double t0 = now();
+  int rounds = 0;
+  long long left = 0;
+  if (J.tool == 0) {
+    // flood(): local relaxation to convergence, fresh halo rows, repeat until no strip moved (src/flood.cpp:344-479)
+    if (J.use_mask) { MG_CUDA(cudaMalloc(&d_mask, cells * 2)); load_strip(mk, tdio::DT_I16, d_mask, nx, s.pitch, row0, ny, total_ny, st); }
+    MG_CUDA(cudaMalloc(&d_f, cells * 4));
+    MG_CUDA(cudaMemsetAsync(d_f, 0, cells * 4, st));
+    MG_TD(td_flood_init_dev(ctx, d_z, d_mask, d_f, s, (float)in.nodata(), J.four, st));
+    for (bool first = true;; first = false) {
+      MG_CUDA(cudaStreamSynchronize(st));
+      if (C.share(d_f, 4)) throw Fail{"row exchange failed"};
+      int moved = 0;
+      if (first) MG_TD(td_flood_relax_dev(ctx, d_z, d_f, s, J.four, &moved, st));
+      else MG_TD(td_flood_relax_edges_dev(ctx, d_z, d_f, s, J.four, &moved, st));
+      ++rounds;
+      unsigned long long any = moved ? 1ull : 0ull;
+      if (C.allreduce_sum(&any, 1)) throw Fail{"all-reduce failed"};
+      if (any == 0) break;
+    }
+    MG_CUDA(cudaMemcpy2D((float*)J.out0 + (size_t)row0 * nx, (size_t)nx * 4, d_f + s.pitch, (size_t)s.pitch * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost));
+  } else {
+    const bool dinf = J.tool == 2;
+    std::vector<double> dxc, dyc;
+    in.cell_sizes(&dxc, &dyc);
+    MG_CUDA(cudaMalloc(&d_dx, sizeof(double) * 2 * (size_t)ny));
+    MG_CUDA(cudaMemcpyAsync(d_dx, dxc.data() + row0, sizeof(double) * ny, cudaMemcpyHostToDevice, st));
+    MG_CUDA(cudaMemcpyAsync(d_dx + ny, dyc.data() + row0, sizeof(double) * ny, cudaMemcpyHostToDevice, st));
+    const size_t eb = dinf ? 4 : 2;
+    MG_CUDA(cudaMalloc(&d_dir, cells * eb));
+    MG_CUDA(cudaMalloc(&d_slp, cells * 4));
+    MG_CUDA(cudaMemsetAsync(d_dir, 0, cells * eb, st));
+    MG_CUDA(cudaMemsetAsync(d_slp, 0, cells * 4, st));
+    MG_CUDA(cudaStreamSynchronize(st));
+    long long nflat = 0;
+    if (dinf) MG_TD(td_dinf_slopes_dev(ctx, d_z, (float*)d_dir, d_slp, s, (float)in.nodata(), d_dx, d_dx + ny, &nflat, st));
+    else MG_TD(td_d8_slopes_dev(ctx, d_z, (int16_t*)d_dir, d_slp, s, (float)in.nodata(), d_dx, d_dx + ny, &nflat, st));
+    MG_CUDA(cudaStreamSynchronize(st));
+    unsigned long long total = (unsigned long long)nflat;
+    if (C.allreduce_sum(&total, 1)) throw Fail{"all-reduce failed"};
+    if (total) {
+      // Garbrecht-Martz on the strips: the halo rows of the directions first, then the BFS passes with their exchanges
+      if (C.share(d_dir, (int)eb)) throw Fail{"row exchange failed"};
+      if (dinf) MG_TD(td_dinf_flats_strip_dev(ctx, d_z, (float*)d_dir, s, d_dx, d_dx + ny, &left, &comm, st));
+      else MG_TD(td_d8_flats_strip_dev(ctx, d_z, (int16_t*)d_dir, s, d_dx, d_dx + ny, &left, &comm, st));
+      MG_CUDA(cudaStreamSynchronize(st));
+    }
+    MG_CUDA(cudaMemcpy2D((char*)J.out0 + (size_t)row0 * nx * eb, (size_t)nx * eb, (char*)d_dir + (size_t)s.pitch * eb, (size_t)s.pitch * eb, (size_t)nx * eb, (size_t)ny,
+                         cudaMemcpyDeviceToHost));
+    MG_CUDA(cudaMemcpy2D(J.out1 + (size_t)row0 * nx, (size_t)nx * 4, d_slp + s.pitch, (size_t)s.pitch * 4, (size_t)nx * 4, (size_t)ny, cudaMemcpyDeviceToHost));
+  }
+  S->secs[rank] = now() - t0;
+  if (rank == 0) { S->rounds = rounds; S->flats_left = left; }
+  td_ctx_destroy(ctx);
+  cudaFree(d_z); cudaFree(d_f); cudaFree(d_slp); cudaFree(d_dir); cudaFree(d_mask); cudaFree(d_dx);
+}
 }  // namespace
 
 void* mgpu_alloc_shared(size_t bytes) {
@@ -235,13 +371,13 @@ int mgpu_world() {
   return n < 1 ? 1 : (n > MAXR ? MAXR : n);
 }
 
-int mgpu_area(const MgpuJob& J, int world, double* compute_seconds, int* rounds) {
-  if (world < 2 || world > MAXR) { set_error("mgpu_area: between 2 and 64 ranks"); return TD_ERR_ARG; }
-  if (J.ny < world) { set_error("mgpu_area: fewer rows than ranks"); return TD_ERR_ARG; }
-  const int pitch = td_pitch_for(J.nx);
-  const size_t bytes = sizeof(Shared) + RoundBuf::bytes(pitch) * (size_t)world;
+namespace {
+// forks `world` ranks over a shared control block (+ extra bytes), waits for them, collects the timings
+template <class Fn>
+int run_ranks(const char* who, int world, size_t extra_bytes, Fn&& rank_fn, double* compute_seconds, int* rounds, long long* flats_left) {
+  const size_t bytes = sizeof(Shared) + extra_bytes;
   char* mem = (char*)mgpu_alloc_shared(bytes);
-  if (!mem) { set_error("mgpu_area: cannot map the shared control block"); return TD_ERR_IO; }
+  if (!mem) { set_error(std::string(who) + ": cannot map the shared control block"); return TD_ERR_IO; }
   Shared* S = new (mem) Shared();
   S->err.store(0); S->bar_count.store(0); S->bar_gen.store(0); S->handed[0].store(0); S->handed[1].store(0);
   fflush(stdout); fflush(stderr);
@@ -251,7 +387,7 @@ int mgpu_area(const MgpuJob& J, int world, double* compute_seconds, int* rounds)
     if (pid < 0) { S->err.store(1); break; }
     if (pid == 0) {
       int code = 0;
-      try { worker(J, S, mem + sizeof(Shared), r, world); }
+      try { rank_fn(S, mem + sizeof(Shared), r); }
       catch (const Fail& f) { snprintf(S->msg[r], sizeof(S->msg[r]), "%s", f.what.c_str()); code = 1; }
       catch (const std::exception& e) { snprintf(S->msg[r], sizeof(S->msg[r]), "exception: %s", e.what()); code = 1; }
       if (code) S->err.store(1);
@@ -296,9 +432,28 @@ int mgpu_area(const MgpuJob& J, int world, double* compute_seconds, int* rounds)
     for (int r = 0; r < world; ++r) mx = std::max(mx, S->secs[r]);
     if (compute_seconds) *compute_seconds = mx;
     if (rounds) *rounds = S->rounds;
+    if (flats_left) *flats_left = S->flats_left;
   }
   mgpu_free_shared(mem, bytes);
   return rc;
+}
+}  // namespace
+
+int mgpu_area(const MgpuJob& J, int world, double* compute_seconds, int* rounds) {
+  if (world < 2 || world > MAXR) { set_error("mgpu_area: between 2 and 64 ranks"); return TD_ERR_ARG; }
+  if (J.ny < world) { set_error("mgpu_area: fewer rows than ranks"); return TD_ERR_ARG; }
+  const int pitch = td_pitch_for(J.nx);
+  return run_ranks("mgpu_area", world, RoundBuf::bytes(pitch) * (size_t)world,
+                   [&](Shared* S, char* extra, int r) { worker(J, S, extra, r, world); }, compute_seconds, rounds, nullptr);
+}
+
+int mgpu_flow(const MgpuFlowJob& J, int world, double* compute_seconds, int* rounds, long long* flats_left) {
+  if (world < 2 || world > MAXR) { set_error("mgpu_flow: between 2 and 64 ranks"); return TD_ERR_ARG; }
+  if (J.ny < world) { set_error("mgpu_flow: fewer rows than ranks"); return TD_ERR_ARG; }
+  if (J.tool < 0 || J.tool > 2 || !J.out0 || (J.tool > 0 && !J.out1)) { set_error("mgpu_flow: bad job"); return TD_ERR_ARG; }
+  const int pitch = td_pitch_for(J.nx);
+  return run_ranks("mgpu_flow", world, RowSlots::bytes(pitch) * (size_t)world,
+                   [&](Shared* S, char* extra, int r) { flow_worker(J, S, extra, r, world); }, compute_seconds, rounds, flats_left);
 }
 
 }  // namespace td

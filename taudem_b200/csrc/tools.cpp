@@ -114,6 +114,42 @@ int area_multi_gpu(int dinf, int world, const Input& in, const char* infile, con
   return TD_OK;
 }
 
+// the same for pitremove / d8flowdir / dinfflowdir (mgpu_flow): the ranks read their rows of the DEM, the parent writes the rasters
+int flow_multi_gpu(int tool, int world, const Input& dem, const char* demfile, const char* maskfile, int use_mask, int four, const char* out0file,
+                   const char* out1file, double t0, double t1) {
+  const size_t n = (size_t)dem.nx * dem.ny;
+  const size_t b0 = n * (tool == 1 ? 2 : 4), b1 = tool == 0 ? 0 : n * 4;
+  void* out0 = td::mgpu_alloc_shared(b0);
+  float* out1 = b1 ? (float*)td::mgpu_alloc_shared(b1) : nullptr;
+  if (!out0 || (b1 && !out1)) { td::mgpu_free_shared(out0, b0); td::mgpu_free_shared(out1, b1); td::set_error("cannot map the shared output rasters"); return TD_ERR_IO; }
+  td::MgpuFlowJob J;
+  J.tool = tool; J.demfile = demfile; J.maskfile = maskfile; J.use_mask = use_mask; J.four = four; J.nx = dem.nx; J.ny = dem.ny; J.out0 = out0; J.out1 = out1;
+  double secs = 0.; int rounds = 0; long long left = 0;
+  int rc = td::mgpu_flow(J, world, &secs, &rounds, &left);
+  const double t2 = now();
+  const char* name = tool == 0 ? "PitRemove" : tool == 1 ? "D8FlowDir" : "DinfFlowDir";
+  double t3 = t2, t4 = t2;
+  if (rc) printf("%s device error: %s\n", name, td_last_error());
+  else if (tool == 0) { rc = write_like(out0file, dem, tdio::DT_F32, (double)-3.0e38f, (const float*)out0); t3 = t4 = now(); }
+  else {
+    rc = write_like(out1file, dem, tdio::DT_F32, (double)-1.0f, (const float*)out1);            // slope first, like the reference
+    t3 = now();
+    if (!rc) rc = tool == 1 ? write_like(out0file, dem, tdio::DT_I16, (double)(short)-32768, (const int16_t*)out0)
+                            : write_like(out0file, dem, tdio::DT_F32, (double)-3.402823466e+38F, (const float*)out0);
+    t4 = now();
+  }
+  td::mgpu_free_shared(out0, b0); td::mgpu_free_shared(out1, b1);
+  if (rc) return rc;
+  // (the ranks read their rows inside what is reported as compute time; the header pass is the read time)
+  if (tool == 0)
+    printf("Processes: %d\nHeader read time: %f\nData read time: %f\nCompute time: %f\nWrite time: %f\nTotal time: %f\n", world, t1 - t0, 0.0, t2 - t1, t3 - t2, t3 - t0);
+  else
+    printf("Processors: %d\nHeader read time: %f\nData read time: %f\nCompute Slope time: %f\nWrite Slope time: %f\nResolve Flat time: %f\nWrite Flat time: %f\nTotal time: %f\n",
+           world, t1 - t0, 0.0, t2 - t1, t3 - t2, 0.0, t4 - t3, t4 - t0);
+  printf("Device compute time: %f\nExchange rounds: %d\nFlat cells left: %lld\n", secs, rounds, left);
+  return TD_OK;
+}
+
 // the CUDA context comes up on a helper thread while the tool opens and reads its rasters
 struct Warmup {
   std::thread th;
@@ -238,6 +274,10 @@ int td_flood(const char* demfile, const char* felfile, const char* sfdrfile, int
   const double t1 = now();
   std::vector<float> z; std::vector<int16_t> m;
   nodata_msgs(dem.r.nodata(), "float", (float)dem.r.nodata());
+  if (td::mgpu_world() > 1 && dem.ny >= td::mgpu_world()) {
+    if (use_mask) nodata_msgs(mask.r.nodata(), "int16_t", (int16_t)mask.r.nodata());
+    return flow_multi_gpu(0, td::mgpu_world(), dem, demfile, maskfile, use_mask, is_4Point, felfile, nullptr, t0, t1);
+  }
   if (int rc = dem.read(&z, tdio::DT_F32)) return rc;
   if (use_mask) { nodata_msgs(mask.r.nodata(), "int16_t", (int16_t)mask.r.nodata()); if (int rc = mask.read(&m, tdio::DT_I16)) return rc; }
   const double t2 = now();
@@ -274,6 +314,7 @@ int td_setdird8(const char* demfile, const char* pointfile, const char* slopefil
   const double t1 = now();
   std::vector<float> z;
   nodata_msgs(dem.r.nodata(), "float", (float)dem.r.nodata());
+  if (td::mgpu_world() > 1 && dem.ny >= td::mgpu_world()) return flow_multi_gpu(1, td::mgpu_world(), dem, demfile, nullptr, 0, 0, pointfile, slopefile, t0, t1);
   if (int rc = dem.read(&z, tdio::DT_F32)) return rc;
   const double t2 = now();
   std::vector<int16_t> p((size_t)dem.nx * dem.ny);
@@ -307,6 +348,7 @@ int td_setdir(const char* demfile, const char* angfile, const char* slopefile, c
   const double t1 = now();
   std::vector<float> z;
   nodata_msgs(dem.r.nodata(), "float", (float)dem.r.nodata());
+  if (td::mgpu_world() > 1 && dem.ny >= td::mgpu_world()) return flow_multi_gpu(2, td::mgpu_world(), dem, demfile, nullptr, 0, 0, angfile, slopefile, t0, t1);
   if (int rc = dem.read(&z, tdio::DT_F32)) return rc;
   const double t2 = now();
   std::vector<float> ang((size_t)dem.nx * dem.ny), slp((size_t)dem.nx * dem.ny);
