@@ -56,8 +56,27 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
         for (int e = 1; e <= 9; ++e) j += (av >= af[e]) ? 1 : 0;
         const int jc = min(max(j, 1), 8);
         const float lo = af[jc], hi = af[jc + 1], g = 4e-5f * (hi - lo);
-        if (j >= 1 && j <= 8 && av - lo > g && hi - av > g) code = (unsigned char)((unsigned)j | 0x10u);
-        else code = (unsigned char)dinf_node_code(av, saref + t * 10);
+        const float dlo = av - lo, dhi = hi - av;
+        if (j >= 1 && j <= 8 && dlo > g && dhi > g) code = (unsigned char)((unsigned)j | 0x10u);
+        else {
+          // On or next to a direction's own angle (every cell of a resolved flat, every clipped facet: a quarter of a real DEM):
+          // closer to the edge e than half of prop()'s 1e-5 band (minus the float error of the table) the share of the sector's
+          // other direction is dropped for certain, and which side of the edge the angle lies on — one exact comparison — says
+          // how the single receiver e is coded: on or above the edge it is the sector's first direction (e; the wrap sector's
+          // direction 8 likewise), below it the upper direction of the sector underneath (e | 0x40; 8 | 0x80 below direction 8).
+          // dinf_node_code returns exactly that (its j = 1..7 branch with one share ~1 and one < 1e-5).  Anything else near an
+          // edge takes the interval search.
+          const bool low = fabsf(dlo) <= fabsf(dhi);
+          const int e = low ? jc : jc + 1;
+          const float ge = 0.5e-5f * fminf(af[e] - af[e - 1], af[min(e + 1, 9)] - af[e]) - 4e-7f;
+          unsigned fast = 0xffu;
+          if (j >= 1 && j <= 8 && e <= 8 && fabsf(low ? dlo : dhi) < ge) {
+            const bool above = (double)av >= saref[t * 10 + e];
+            if (above) fast = (unsigned)e;
+            else if (e >= 2) fast = e <= 7 ? ((unsigned)e | 0x40u) : (8u | 0x80u);
+          }
+          code = fast != 0xffu ? (unsigned char)fast : (unsigned char)dinf_node_code(av, saref + t * 10);
+        }
       }
     }
     sout[i] = code;

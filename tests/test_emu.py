@@ -353,15 +353,31 @@ def test_emulated_dependency_stencils(emu, fields):
     podd = p.copy()                                       # direction codes outside 0..8 (the generic path of k_deps_d8) and zeros
     idx = rng.integers(0, p.size, 400)
     podd.ravel()[idx] = rng.choice(np.array([0, 0, 9, 10, 12, -1, -3, 100, -32768], np.int16), 400)
-    for dinf, d, nd in ((0, np.ascontiguousarray(p), -32768.0), (0, np.ascontiguousarray(podd), -32768.0),
-                        (1, np.ascontiguousarray(ang), -3.4028234663852886e38)):
+    from util import angle_torture
+    MISS = -3.4028234663852886e38
+    cases = [(0, np.ascontiguousarray(p), -32768.0, 30.0, 30.0), (0, np.ascontiguousarray(podd), -32768.0, 30.0, 30.0),
+             (1, np.ascontiguousarray(ang), MISS, 30.0, 30.0)]
+    # angles on, next to and around every sector edge and every threshold of the float pre-screens (square and oblong cells)
+    cases += [(1, angle_torture(ny=ny, nx=nx, dx=dx, dy=dy, seed=7 + i), MISS, dx, dy) for i, (dx, dy) in enumerate(((30.0, 30.0), (30.0, 20.0), (10.0, 45.0)))]
+    for dx, dy in ((30.0, 30.0), (30.0, 12.0)):           # random angles within +-1.2e-5 sector widths of the edges, and float neighbours of the edges
+        t = np.arctan2(dy, dx); PI = 3.14159265359
+        edges = np.array([0.0, t, 0.5 * PI, PI - t, PI, PI + t, 1.5 * PI, 2 * PI - t, 2 * PI])
+        e = rng.integers(0, 9, (ny, nx))
+        w = np.minimum(np.diff(edges, append=edges[-1] + t)[e], np.diff(edges, prepend=-t)[e])
+        near = (edges[e] + rng.uniform(-1.2e-5, 1.2e-5, (ny, nx)) * w).astype(np.float32)
+        ulps = rng.integers(-3, 4, (ny, nx))
+        snap = rng.random((ny, nx)) < 0.3
+        near[snap] = (np.ascontiguousarray(edges[e].astype(np.float32)).view(np.int32) + ulps.astype(np.int32))[snap].view(np.float32)
+        near[near < 0] = 0.0
+        cases.append((1, np.ascontiguousarray(near, np.float32), MISS, dx, dy))
+    for dinf, d, nd, dx, dy in cases:
         node = np.empty((ny, nx), np.uint16); cnt = np.empty((ny, nx), np.uint8); area = np.empty((ny, nx), np.float32)
         rn = np.empty((ny, nx), np.uint16); rc = np.empty((ny, nx), np.uint8)
         if dinf:
-            assert emu.emu_deps_dinf(d.ctypes.data, node.ctypes.data, cnt.ctypes.data, area.ctypes.data, nx, ny, nd, 30.0, 30.0) == 0
+            assert emu.emu_deps_dinf(d.ctypes.data, node.ctypes.data, cnt.ctypes.data, area.ctypes.data, nx, ny, nd, dx, dy) == 0
         else:
             assert emu.emu_deps_d8(d.ctypes.data, node.ctypes.data, cnt.ctypes.data, area.ctypes.data, nx, ny, int(nd)) == 0
-        assert emu.emu_ref_deps(dinf, d.ctypes.data, rn.ctypes.data, rc.ctypes.data, nx, ny, nd, 30.0, 30.0) == 0
+        assert emu.emu_ref_deps(dinf, d.ctypes.data, rn.ctypes.data, rc.ctypes.data, nx, ny, nd, dx, dy) == 0
         assert np.array_equal(cnt, rc), f"counts dinf={dinf}: {int((cnt != rc).sum())} differ"
         assert np.array_equal(node, rn), f"node words dinf={dinf}: {int((node != rn).sum())} differ"
         assert np.all(area == -1.0)

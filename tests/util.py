@@ -94,7 +94,7 @@ def angle_torture(ny=96, nx=120, dx=30.0, dy=30.0, seed=5):
         vals += [f, np.nextafter(f, np.float32(10)), np.nextafter(f, np.float32(-10))]
         if i + 1 < len(edges):
             w = edges[i + 1] - e
-            for frac in (1e-5, 1e-5 * (1 + 2e-7), 1e-5 * (1 - 2e-7), 0.999e-5, 1.001e-5, 0.3, 0.5, 0.77):
+            for frac in (1e-5, 1e-5 * (1 + 2e-7), 1e-5 * (1 - 2e-7), 0.999e-5, 1.001e-5, 0.3, 0.5, 0.77, 1e-7, 1e-6, 0.4e-5, 0.449e-5, 0.45e-5, 0.5e-5, 0.6e-5, 2e-5, 3.9e-5, 4.1e-5):
                 vals += [np.float32(e + frac * w), np.float32(edges[i + 1] - frac * w)]
     vals += [np.float32(2 * PI + 1e-4), np.float32(6.5), np.float32(1e-30), np.float32(-1.0)]
     vals = np.array(vals, np.float32)
