@@ -256,6 +256,12 @@ int td_dinf_slopes_dev(td_ctx*, const float* fel, float* ang, float* slp, td_str
 int td_dinf_flats_dev(td_ctx*, float* fel, float* ang, td_strip s, const double* dxc,
                       const double* dyc, long long* nflat_left, void* stream);
 
+/* Row strips of a raster whose rows have different cell sizes (geographic rasters): the cell sizes of the rows just above / below
+ * the strip (the neighbour strips' edge rows; <= 0 = none).  The D-infinity dependency stencil and sweep evaluate a contributor in a
+ * halo row with ITS row's cell sizes like the reference (getdxdyc(jn), src/areadinf.cpp:199-201).  Call before td_area_deps_dev;
+ * stays in effect for the context until changed. */
+void td_set_halo_cell_sizes_dev(td_ctx*, double dx_top, double dy_top, double dx_bot, double dy_bot);
+
 /* -o: restricts the dependency state built by *_deps_dev to the cells upstream of the outlets (host
  * arrays of grid coordinates, row 0 = first owned row); call between *_deps_dev and *_sweep_dev.       */
 int td_sweep_restrict_dev(td_ctx*, td_strip s, const int* cols, const int* rows, int nout, void* stream);

@@ -104,6 +104,7 @@ SIGNATURES = {
     "td_sweep_peer_connect_dev": (_I, [_P, _I, _P, _P]),
     "td_sweep_peer_begin_dev": (_I, [_P, Strip, _P]),
     "td_sweep_peer_off_dev": (None, [_P]),
+    "td_set_halo_cell_sizes_dev": (None, [_P, _D, _D, _D, _D]),
     "td_area_sweep_run_dev": (_I, [_P, _P, _P, _P, Strip, _I, _I, _P, _P, _P]),
 }
 

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
   __shared__ __align__(16) unsigned char sout[G::ELEMS];
   __shared__ __align__(16) unsigned char sbits[G::ELEMS];     // the receiver bits of the node word's high byte (dinf_node_bits >> 8)
   __shared__ float sarf[(TH + 2) * 10];                          // the same table rounded to float: the pre-screen below
-  for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) { const double v = aref(i % 10, theta[min(max(r0 - 2 + i / 10, 0), s.ny - 1)]); saref[i] = v; sarf[i] = (float)v; }
+  for (int i = threadIdx.x; i < (TH + 2) * 10; i += 256) { const double v = aref(i % 10, theta_of_row(theta, s.ny, min(r0 - 1 + i / 10, s.ny + 1))); saref[i] = v; sarf[i] = (float)v; }
   __syncthreads();
   for (int i = threadIdx.x; i < G::ELEMS; i += 256) {
     const int t = i / G::SW, sc = i - t * G::SW;

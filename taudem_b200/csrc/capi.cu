@@ -178,13 +178,16 @@ int td_d8_flats_strip_dev(td_ctx* ctx, float* fel, int16_t* p, td_strip s, const
 
 // per-row atan2 tables are evaluated on the host (glibc), like the reference's prop()/VSLOPE do
 static int upload_theta_from_host(td_ctx* ctx, const double* dx, const double* dy, int ny, td_ctx::Buf& buf, cudaStream_t st) {
-  std::vector<double> th(2 * (size_t)ny);
+  // [0, ny) atan2(dy, dx), [ny, 2 ny) atan2(dx, dy), then the angle of the row above and of the row below the strip (theta_of_row)
+  std::vector<double> th(2 * (size_t)ny + 2);
   for (int j = 0; j < ny; j++) { th[j] = atan2(dy[j], dx[j]); th[ny + j] = atan2(dx[j], dy[j]); }
-  TD_CUDA(buf.ensure(sizeof(double) * 2 * (size_t)ny));
-  TD_CUDA(cudaMemcpyAsync(buf.p, th.data(), sizeof(double) * 2 * (size_t)ny, cudaMemcpyHostToDevice, st));
+  th[2 * (size_t)ny] = ctx->halo_dx[0] > 0. && ctx->halo_dy[0] > 0. ? atan2(ctx->halo_dy[0], ctx->halo_dx[0]) : th[0];
+  th[2 * (size_t)ny + 1] = ctx->halo_dx[1] > 0. && ctx->halo_dy[1] > 0. ? atan2(ctx->halo_dy[1], ctx->halo_dx[1]) : th[ny - 1];
+  TD_CUDA(buf.ensure(sizeof(double) * th.size()));
+  TD_CUDA(cudaMemcpyAsync(buf.p, th.data(), sizeof(double) * th.size(), cudaMemcpyHostToDevice, st));
   TD_CUDA(cudaStreamSynchronize(st));
-  // one prop() table for the whole strip when every row has the same angle (projected rasters)
-  bool uni = true;
+  // one prop() table for the whole strip when every row (the neighbours' edge rows included) has the same angle (projected rasters)
+  bool uni = th[2 * (size_t)ny] == th[0] && th[2 * (size_t)ny + 1] == th[0];
   for (int j = 1; j < ny && uni; j++) uni = th[j] == th[0] && dx[j] == dx[0];
   td::make_prop_row(th[0], uni, &ctx->prop);
   ctx->dx0 = dx[0];
@@ -198,6 +201,10 @@ static int upload_theta(td_ctx* ctx, const double* d_dxc, const double* d_dyc, i
   return upload_theta_from_host(ctx, dx.data(), dy.data(), ny, buf, st);
 }
 
+void td_set_halo_cell_sizes_dev(td_ctx* ctx, double dx_top, double dy_top, double dx_bot, double dy_bot) {
+  if (!ctx) return;
+  ctx->halo_dx[0] = dx_top; ctx->halo_dy[0] = dy_top; ctx->halo_dx[1] = dx_bot; ctx->halo_dy[1] = dy_bot;
+}
 int td_dinf_slopes_dev(td_ctx* ctx, const float* fel, float* ang, float* slp, td_strip s, float fel_nodata, const double* dxc,
                        const double* dyc, long long* nflat_out, void* stream) {
   if (int rc = check_strip(s)) return rc;

@@ -170,6 +170,13 @@ struct PropRow {
 };
 
 // host: the table for row angle t = atan2(dy, dx) (src/commonLib.cpp:78 builds aref[] with these expressions)
+// The per-row angle table of a strip: theta[0 .. ny) = atan2(dy, dx) of the owned rows, [ny .. 2 ny) = atan2(dx, dy),
+// theta[2 ny] / theta[2 ny + 1] = atan2(dy, dx) of the rows above / below the strip (the neighbour strips' edge rows: the
+// reference evaluates a contributor with ITS row's cell sizes, getdxdyc(jn), src/areadinf.cpp:199-201).  row = strip row 0 .. ny + 1.
+__host__ __device__ __forceinline__ double theta_of_row(const double* theta, int ny, int row) {
+  return row < 1 ? theta[2 * ny] : (row > ny ? theta[2 * ny + 1] : theta[row - 1]);
+}
+
 inline void make_prop_row(double t, bool uniform, PropRow* P) {
   const double PI = TD_PI;
   const double ar[10] = {-t, 0., t, (double)(0.5 * PI), PI - t, (double)PI, PI + t, (double)(1.5 * PI), 2. * PI - t, (double)(2. * PI)};

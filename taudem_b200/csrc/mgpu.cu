@@ -165,7 +165,14 @@ void worker(const MgpuJob& J, Shared* S, char* extra, int rank, int world) {
     if (rank < world - 1) MG_TD(td_sweep_peer_connect_dev(ctx, 1, S->handles[rank + 1], S->meta[rank + 1]));
     MG_TD(td_sweep_peer_connect_dev(ctx, 2, rank == 0 ? nullptr : S->handles[0], nullptr));
   }
-  if (J.dinf) MG_TD(td_area_deps_dev(ctx, (const float*)d_dir, d_out, s, (float)in.nodata(), d_dx, d_dx + ny, st));
+  if (J.dinf) {
+    // the neighbour strips' edge rows keep their own cell sizes (geographic rasters: src/areadinf.cpp:199-201 getdxdyc(jn))
+    std::vector<double> dxc, dyc;
+    in.cell_sizes(&dxc, &dyc);
+    td_set_halo_cell_sizes_dev(ctx, row0 > 0 ? dxc[row0 - 1] : 0., row0 > 0 ? dyc[row0 - 1] : 0., row0 + ny < total_ny ? dxc[row0 + ny] : 0.,
+                               row0 + ny < total_ny ? dyc[row0 + ny] : 0.);
+    MG_TD(td_area_deps_dev(ctx, (const float*)d_dir, d_out, s, (float)in.nodata(), d_dx, d_dx + ny, st));
+  }
   else MG_TD(td_aread8_deps_dev(ctx, (const int16_t*)d_dir, d_out, s, (int16_t)in.nodata(), st));
   auto run = [&]() {
     MG_CUDA(cudaMemsetAsync(d_halo, 0, sizeof(int) * 2 * (size_t)s.pitch, st));

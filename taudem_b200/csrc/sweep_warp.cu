@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
                 p = a.prop.safe ? div_recip(num, S.den, S.rden) : num / S.den;
               } else {
                 const int rn = r0 + lr + dr;
-                p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : a.theta[min(max(rn - 1, 0), s.ny - 1)], kk);
+                p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : theta_of_row(a.theta, s.ny, min(max(rn, 0), s.ny + 1)), kk);
               }
               if (ALG == 3) {
                 const float dmv = __ldg(a.dm + s.idx(r0 + lr + dr, c0 + lx + lut_dcol(k)));
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(workers_per_cta<DINF>() * 32, 1) k_sweep_warp(
               p = a.prop.safe ? div_recip(num, S.den, S.rden) : num / S.den;
             } else {
               const int rn = r + dr;
-              p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : a.theta[min(max(rn - 1, 0), s.ny - 1)], kk);
+              p = wshare_full(av, a.prop.uniform ? a.prop.ar[2] : theta_of_row(a.theta, s.ny, min(max(rn, 0), s.ny + 1)), kk);
             }
             if (ALG == 3) {
               const float dmv = __ldg(a.dm + s.idx(r + dr, c0 + lx + lut_dcol(k)));

@@ -226,6 +226,13 @@ class DistTools:
             self.share(ang)
         if self.peer:
             self._peer_setup(True)
+        if self.world > 1:
+            # the neighbour strips' edge rows keep their own cell sizes (geographic rasters: getdxdyc(jn), src/areadinf.cpp:199-201)
+            cs = torch.zeros((self.ny + 2, 2), dtype=torch.float64, device=dxc.device)
+            cs[1:self.ny + 1, 0] = dxc; cs[1:self.ny + 1, 1] = dyc
+            exchange_rows(cs, self.ny, self.rank, self.world)
+            top, bot = cs[0].tolist(), cs[self.ny + 1].tolist()
+            self.l.td_set_halo_cell_sizes_dev(self.T.ctx, top[0], top[1], bot[0], bot[1])
         self.T.areadinf_deps(s, ang, sca, dxc, dyc, nodata)
         if outlets is not None:
             self._restrict(outlets)

@@ -50,7 +50,7 @@ void build_strip(StripState& S, int dinf, const void* dir, const float* wgt, int
   const size_t n = (size_t)s.cells();
   S.node.assign(n, 0); S.cnt.assign((n + 3) / 4 * 4, 0xff);
   S.area.assign(n, -1.0f); S.w.assign(n, 0.f); S.ang.assign(n, 0.f); S.p.assign(n, 0);
-  S.theta.assign(2 * (size_t)ny, 0.); S.dxc.assign(ny, dx); S.halo.assign(2 * (size_t)s.pitch, 0);
+  S.theta.assign(2 * (size_t)ny + 2, atan2(dy, dx)); S.dxc.assign(ny, dx); S.halo.assign(2 * (size_t)s.pitch, 0);
   for (int j = 0; j < ny; ++j) { S.theta[j] = atan2(dy, dx); S.theta[ny + j] = atan2(dx, dy); }
   for (int r = 0; r <= ny + 1; ++r) {               // halo rows hold the neighbours' directions (DistTools.share)
     const int gr = row0 + r - 1;

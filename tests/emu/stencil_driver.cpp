@@ -22,7 +22,7 @@ struct Grid {
   Grid(int nx, int ny, double dx, double dy) {
     td_strip ts; ts.nx = nx; ts.ny = ny; ts.pitch = (nx + 31) / 32 * 32; ts.has_top = 0; ts.has_bot = 0;
     s = Strip(ts);
-    dxc.assign(ny, dx); dyc.assign(ny, dy); th.assign(2 * (size_t)ny, 0.);
+    dxc.assign(ny, dx); dyc.assign(ny, dy); th.assign(2 * (size_t)ny + 2, atan2(dy, dx));     // + the rows above / below the strip (theta_of_row)
     for (int j = 0; j < ny; ++j) { th[j] = atan2(dy, dx); th[ny + j] = atan2(dx, dy); }
   }
   template <typename T> std::vector<T> in(const T* src) const {

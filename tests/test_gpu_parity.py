@@ -329,6 +329,20 @@ def test_geographic_dem_file_level(refrun, tmp_path):
         a, b = td.read_raster(q(n + ".tif"), dt), td.read_raster(q("ref/" + n + ".tif"), dt)
         (assert_bits if exact else assert_float_parity)(a, b, n + " (geographic)")
     assert td.raster_info(q("sca.tif"))["is_geographic"]        # GeoTIFF keys pass through to the outputs
+    # the same on row strips (TAUDEM_B200_GPUS=N behind the executables): rows of different cell sizes on both sides of a strip
+    # boundary — the halo row of a strip is evaluated with the neighbour row's cell sizes like the reference does (getdxdyc(jn))
+    import subprocess
+    bindir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "taudem_b200", "bin")
+    for n in (2, 3):
+        env = dict(os.environ, TAUDEM_B200_GPUS=str(n))
+        for tool, args in (("pitremove", ["-z", q("geo.tif"), "-fel", q(f"fel_{n}.tif")]),
+                           ("d8flowdir", ["-fel", q("fel.tif"), "-p", q(f"p_{n}.tif"), "-sd8", q(f"sd8_{n}.tif")]),
+                           ("dinfflowdir", ["-fel", q("fel.tif"), "-ang", q(f"ang_{n}.tif"), "-slp", q(f"slp_{n}.tif")]),
+                           ("aread8", ["-p", q("p.tif"), "-ad8", q(f"ad8_{n}.tif")]), ("areadinf", ["-ang", q("ang.tif"), "-sca", q(f"sca_{n}.tif")])):
+            r = subprocess.run([os.path.join(bindir, tool)] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=300)
+            assert r.returncode == 0 and "error" not in r.stdout.lower(), r.stdout
+        for name, dt in (("fel", np.float32), ("p", np.int16), ("sd8", np.float32), ("ang", np.float32), ("slp", np.float32), ("ad8", np.float32), ("sca", np.float32)):
+            assert_bits(td.read_raster(q(f"{name}_{n}.tif"), dt), td.read_raster(q(name + ".tif"), dt), f"{name} (geographic) on {n} ranks")
 
 
 def test_d8_stencil_ties_and_near_ties():
