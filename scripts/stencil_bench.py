@@ -16,6 +16,7 @@ from taudem_b200.device import DeviceStrip, Tools, _p  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 7
+    only = set(sys.argv[3].split(",")) if len(sys.argv) > 3 else None        # e.g. k_deps_dinf,k_deps_d8
     try:
         peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
@@ -25,6 +26,8 @@ def main():
     out = {}
 
     def run(name, bytes_per_cell, fn):
+        if only is not None and name.split(" ")[0] not in only:
+            return
         ts = []
         for _ in range(reps + 1):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -53,6 +56,9 @@ def main():
     sca = s.empty(torch.float32)
     run("k_deps_dinf", 4, lambda: T.areadinf_deps(s, ang, sca, dxc, dyc))
     run("k_deps_dinf (+7 scratch)", 11, lambda: T.areadinf_deps(s, ang, sca, dxc, dyc))
+    if only is not None and not (only & {"k_threshold", "k_twi", "k_slopearea", "k_slopearearatio"}):
+        print(json.dumps({"n": n, "hbm_peak_gbs": peak, "kernels": out}))
+        return
     # point-wise consumers on the rasters of the path
     T.aread8_sweep(s, ad8); T.areadinf_deps(s, ang, sca, dxc, dyc); T.areadinf_sweep(s, ang, sca, dxc)
     src = s.empty(torch.int16); o = s.empty(torch.float32)

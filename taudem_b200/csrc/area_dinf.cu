@@ -13,6 +13,8 @@
 // is rebuilt on the device from t (host glibc atan2, per row) using only +,-: the same
 // doubles as the reference.  The per-cell value is a deterministic gather, so any
 // topological schedule reproduces it.
+#include <stdlib.h>
+
 #include "ctx.h"
 #include "dinf_common.cuh"
 
@@ -25,7 +27,7 @@ __device__ __forceinline__ unsigned eq_bytes7(unsigned w, unsigned t) { return ~
 
 __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang, unsigned short* __restrict__ node,
                                                    unsigned char* __restrict__ cnt, float* __restrict__ area, Strip s,
-                                                   float nodata, const double* __restrict__ theta, float area_init) {
+                                                   float nodata, const double* __restrict__ theta, float area_init, int edge_fast) {
   using G = TileGeom<float, TW, TH>;
   __shared__ __align__(128) float tile[G::ELEMS];
   __shared__ __align__(8) uint64_t bar;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
           const int e = low ? jc : jc + 1;
           const float ge = 0.5e-5f * fminf(af[e] - af[e - 1], af[min(e + 1, 9)] - af[e]) - 4e-7f;
           unsigned fast = 0xffu;
-          if (j >= 1 && j <= 8 && e <= 8 && fabsf(low ? dlo : dhi) < ge) {
+          if (edge_fast && j >= 1 && j <= 8 && e <= 8 && fabsf(low ? dlo : dhi) < ge) {
             const bool above = (double)av >= saref[t * 10 + e];
             if (above) fast = (unsigned)e;
             else if (e >= 2) fast = e <= 7 ? ((unsigned)e | 0x40u) : (8u | 0x80u);
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
 cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
                              float nodata, const double* theta, cudaStream_t st, float area_init) {
   dim3 grid((s.pitch + TW - 1) / TW, (s.ny + TH - 1) / TH);
-  k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, s, nodata, theta, area_init);
+  static const int edge_fast = [] { const char* e = getenv("TAUDEM_B200_DEPS_EDGE"); return e ? atoi(e) : 1; }();   // 0: every near-edge angle takes the interval search
+  k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, s, nodata, theta, area_init, edge_fast);
   TD_LAUNCHED();
   return cudaGetLastError();
 }
