@@ -27,6 +27,8 @@ def main():
 
     def run(name, bytes_per_cell, fn):
         if only is not None and name.split(" ")[0] not in only:
+            fn()                                 # later kernels need its outputs
+            torch.cuda.synchronize()
             return
         ts = []
         for _ in range(reps + 1):
