@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) k_deps_dinf(const float* __restrict__ ang
 cudaError_t launch_deps_dinf(const float* ang, unsigned short* node, unsigned char* cnt, float* area, const Strip& s,
                              float nodata, const double* theta, cudaStream_t st, float area_init) {
   dim3 grid((s.pitch + TW - 1) / TW, (s.ny + TH - 1) / TH);
-  static const int edge_fast = [] { const char* e = getenv("TAUDEM_B200_DEPS_EDGE"); return e ? atoi(e) : 0; }();   // 1: angles on or next to a direction decided by one exact comparison (faster at 16384^2, slower in the 65536^2 bench: off)
+  static const int edge_fast = [] { const char* e = getenv("TAUDEM_B200_DEPS_EDGE"); return e ? atoi(e) : 1; }();   // 0: every near-edge angle takes the interval search
   k_deps_dinf<<<grid, 256, 0, st>>>(ang, node, cnt, area, s, nodata, theta, area_init, edge_fast);
   TD_LAUNCHED();
   return cudaGetLastError();

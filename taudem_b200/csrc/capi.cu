@@ -180,7 +180,11 @@ int td_d8_flats_strip_dev(td_ctx* ctx, float* fel, int16_t* p, td_strip s, const
 static int upload_theta_from_host(td_ctx* ctx, const double* dx, const double* dy, int ny, td_ctx::Buf& buf, cudaStream_t st) {
   // [0, ny) atan2(dy, dx), [ny, 2 ny) atan2(dx, dy), then the angle of the row above and of the row below the strip (theta_of_row)
   std::vector<double> th(2 * (size_t)ny + 2);
-  for (int j = 0; j < ny; j++) { th[j] = atan2(dy[j], dx[j]); th[ny + j] = atan2(dx[j], dy[j]); }
+  for (int j = 0; j < ny; j++) {
+    // (projected rasters: every row has the same cell size — two atan2 calls instead of 2 ny on the critical path of every call)
+    if (j > 0 && dx[j] == dx[j - 1] && dy[j] == dy[j - 1]) { th[j] = th[j - 1]; th[ny + j] = th[ny + j - 1]; }
+    else { th[j] = atan2(dy[j], dx[j]); th[ny + j] = atan2(dx[j], dy[j]); }
+  }
   th[2 * (size_t)ny] = ctx->halo_dx[0] > 0. && ctx->halo_dy[0] > 0. ? atan2(ctx->halo_dy[0], ctx->halo_dx[0]) : th[0];
   th[2 * (size_t)ny + 1] = ctx->halo_dx[1] > 0. && ctx->halo_dy[1] > 0. ? atan2(ctx->halo_dy[1], ctx->halo_dx[1]) : th[ny - 1];
   TD_CUDA(buf.ensure(sizeof(double) * th.size()));
