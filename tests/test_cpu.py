@@ -140,6 +140,25 @@ def test_cli_usage_and_simple_mode_errors():
     assert r.returncode == 0 and "does not exist" in r.stderr and "area error" in r.stdout
 
 
+def test_cli_of_the_sibling_and_pointwise_tools():
+    """The nine tools of SURVEY.md 8(f) ranks 3 and 4: usage + exit 0 without arguments, on an unknown flag and on a flag without its
+    value (src/*mn.cpp: `goto errexit` / `exit(0)`); a missing input file is reported like the reference reports it."""
+    bindir = os.path.join(ROOT, "taudem_b200", "bin")
+    tools = {"d8flowpathextremeup": "-p", "gridnet": "-p", "dinfdecayaccum": "-ang", "dinfconclimaccum": "-ang", "dinftranslimaccum": "-ang", "threshold": "-ssa",
+             "twi": "-sca", "slopearea": "-slp", "slopearearatio": "-sca"}
+    for tool, flag in tools.items():
+        exe = os.path.join(bindir, tool)
+        for args in ([], ["-bogus", "x"], [flag, "a.tif", flag]):            # (one argument alone is the simple-usage base name)
+            r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            assert r.returncode == 0 and ("Usage" in r.stdout or "Use" in r.stdout), (tool, args, r.stdout)
+        r = subprocess.run([exe, flag, "/nonexistent/in.tif"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0 and "rror" in r.stdout, (tool, r.stdout)
+    r = subprocess.run([os.path.join(bindir, "slopearea"), "-slp", "a.tif", "-par", "1.5"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "Use" in r.stdout                 # -par needs both exponents (src/SlopeAreamn.cpp:103-114)
+    r = subprocess.run([os.path.join(bindir, "gridnet"), "-p", "a.tif", "-mask", "m.tif"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "Usage" in r.stdout               # -mask without -thresh (src/gridnetmn.cpp:160-166)
+
+
 def test_synth_families():
     d = synth.gen_dem(64, 96, family="tilted")
     assert d.shape == (64, 96) and d.dtype == np.float32 and np.isfinite(d).all()
