@@ -181,6 +181,18 @@ def _sibling_grids(shape, seed):
     return q, dm, dg, tc, cs
 
 
+def _outlet_points(port, ang, R):
+    """three outlet cells (nested and disjoint basins) as grid coordinates and as a point shapefile in the reference's work directory"""
+    from util import write_point_shapefile
+    ny, nx = ang.shape
+    order = np.argsort(port.areadinf(ang, contcheck=False).ravel())
+    cells = [int(order[-1]), int(order[-40]), int(order[-300])]
+    cols = [c % nx for c in cells]; rows = [c // nx for c in cells]
+    shp = R.path("outlets.shp")
+    write_point_shapefile(shp, [(c + 0.5) * 30.0 for c in cols], [30.0 * ny - (r + 0.5) * 30.0 for r in rows])
+    return (cols, rows), shp
+
+
 def test_emulated_dinf_conc_lim_accumulation(emu, fields):
     """DinfConcLimAccum = the D-infinity sweep with the concentration-limited algebra (7), against the reference executable
     (oracle/_ref/dinfconclimaccum: DinfConcLimAccum.cpp compiled unchanged); with and without contamination checking."""
@@ -195,6 +207,8 @@ def test_emulated_dinf_conc_lim_accumulation(emu, fields):
     R = refrun.RefPipeline()
     assert_bits(_run(emu, True, 16, 0, ang, q, True, 61), R.dinfconclimaccum(ang, dm, q, dg, csol=2.5), "ctpt")
     assert_bits(_run(emu, True, 16, 0, ang, q, False, 62), R.dinfconclimaccum(ang, dm, q, dg, csol=2.5, contcheck=False), "ctpt -nc")
+    outs, shp = _outlet_points(port, ang, R)
+    assert_bits(_run(emu, True, 16, 0, ang, q, False, 63, outlets=outs), R.dinfconclimaccum(ang, dm, q, dg, csol=2.5, contcheck=False, outlets=shp), "ctpt -nc -o")
     emu.emu_set_dm(None, C.c_float(0.0))
 
 
@@ -219,6 +233,11 @@ def test_emulated_dinf_trans_lim_accumulation(emu, fields):
         tla = _run(emu, True, 18, 0, ang, tsup, contcheck, seed)
         rt, rd, rc = R.dinftranslimaccum(ang, tsup, tc, cs=cs, contcheck=contcheck)
         assert_bits(tla, rt, "tla (cs)"); assert_bits(dep, rd, "tdep (cs)"); assert_bits(cout, rc, "ctpt")
+    outs, shp = _outlet_points(port, ang, R)
+    tla = _run(emu, True, 18, 0, ang, tsup, False, 74, outlets=outs)
+    rt, rd, rc = R.dinftranslimaccum(ang, tsup, tc, cs=cs, contcheck=False, outlets=shp)
+    assert_bits(tla, rt, "tla -o"); assert_bits(dep, rd, "tdep -o"); assert_bits(cout, rc, "ctpt -o")
+    assert 100 < int((rt > -1e38).sum()) < rt.size
     emu.emu_set_dm(None, C.c_float(0.0))
 
 
