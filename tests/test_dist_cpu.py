@@ -47,6 +47,13 @@ def _worker(rank, world, port, total_ny, nx):
         assert (top == 100 * (rank - 1) + 2).all()
     if bot is not None:
         assert (bot == 100 * (rank + 1) + 1).all()
+    # the cell sizes of the neighbour strips' edge rows (DistTools.areadinf on geographic rasters): a (ny + 2) x 2 float64 strip
+    dxf = 30.0 + 0.001 * torch.arange(total_ny, dtype=torch.float64); dyf = 25.0 - 0.002 * torch.arange(total_ny, dtype=torch.float64)
+    cs = torch.zeros((ny + 2, 2), dtype=torch.float64)
+    cs[1:ny + 1, 0] = dxf[row0:row0 + ny]; cs[1:ny + 1, 1] = dyf[row0:row0 + ny]
+    exchange_rows(cs, ny, rank, world)
+    assert cs[0].tolist() == ([float(dxf[row0 - 1]), float(dyf[row0 - 1])] if rank > 0 else [0.0, 0.0])            # 0 = none: the grid ends here
+    assert cs[ny + 1].tolist() == ([float(dxf[row0 + ny]), float(dyf[row0 + ny])] if rank < world - 1 else [0.0, 0.0])
     total = torch.tensor([int(halo.sum())]); dist.all_reduce(total)
     assert int(total) == sum(nx * (200 * r + 3) for r in range(world))
     dist.destroy_process_group()
