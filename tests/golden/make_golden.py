@@ -53,5 +53,51 @@ def main():
         print(f"{name}: {dem.shape} filled {(fel != dem).sum()} flats {flats} ad8 max {out['ad8'].max()} sca nodata {(out['sca'] == -1).sum()}")
 
 
+def sibling_inputs(shape, seed=77):
+    """the extra grids of the sibling sweep tools and the point-wise consumers"""
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(0.5, 3.0, shape).astype(np.float32)
+    q[rng.random(shape) < 0.004] = -9999.0
+    q[rng.random(shape) < 0.004] = 0.0
+    dm = rng.uniform(0.2, 1.0, shape).astype(np.float32)
+    dm[rng.random(shape) < 0.003] = -9999.0
+    dg = (rng.random(shape) < 0.02).astype(np.int16)
+    tc = rng.uniform(0.0, 8.0, shape).astype(np.float32)
+    tc[rng.random(shape) < 0.003] = -9999.0
+    cs = rng.uniform(0.0, 2.0, shape).astype(np.float32)
+    cs[rng.random(shape) < 0.003] = -9999.0
+    sa = (rng.random(shape) * 100.0 - 20.0).astype(np.float32)
+    return dict(q=q, dm=dm, dg=dg, tc=tc, cs=cs, sa=sa)
+
+
+def siblings():
+    """tests/golden/siblings.npz: the nine tools of SURVEY.md 8(f) ranks 3 and 4 on the rasters of the hills_holes case"""
+    g = np.load(os.path.join(HERE, "hills_holes.npz"))
+    dx, dy = float(g["dx"]), float(g["dy"])
+    p, ang, slp, ad8, sca = g["p"], g["ang"], g["slp"], g["ad8"], g["sca"]
+    x = sibling_inputs(p.shape)
+    R = refrun.RefPipeline(dx=dx, dy=dy)
+    out = dict(x)
+    out["ssa_max"] = R.d8flowpathextremeup(p, x["sa"], usemax=True)
+    out["ssa_min_nc"] = R.d8flowpathextremeup(p, x["sa"], usemax=False, contcheck=False)
+    out["plen"], out["tlen"], out["gord"] = R.gridnet(p)
+    mask = np.where(ad8 >= 0, ad8, 0).astype(np.int32)
+    out["gn_mask"] = mask
+    out["plen_m"], out["tlen_m"], out["gord_m"] = R.gridnet(p, mask=mask, thresh=5)
+    out["dsca"] = R.dinfdecayaccum(ang, x["dm"])
+    out["dsca_w_nc"] = R.dinfdecayaccum(ang, x["dm"], weights=g["w"], contcheck=False)
+    out["ctpt"] = R.dinfconclimaccum(ang, x["dm"], x["q"], x["dg"], csol=2.5)
+    out["ctpt_nc"] = R.dinfconclimaccum(ang, x["dm"], x["q"], x["dg"], csol=2.5, contcheck=False)
+    out["tla"], out["tdep"], _ = R.dinftranslimaccum(ang, x["q"], x["tc"])
+    out["tla_c"], out["tdep_c"], out["ctpt_c"] = R.dinftranslimaccum(ang, x["q"], x["tc"], cs=x["cs"], contcheck=False)
+    out["src"] = R.threshold(ad8, 50.0)
+    out["twi"] = R.twi(slp, sca)
+    out["sa_default"] = R.slopearea(slp, sca)
+    out["sar"] = R.slopearearatio(slp, sca)
+    np.savez_compressed(os.path.join(HERE, "siblings.npz"), **out)
+    print("siblings:", {k: (v.dtype.name, int((v > -1e38).sum()) if v.dtype.kind == "f" else int(v.max())) for k, v in out.items() if k not in x})
+
+
 if __name__ == "__main__":
     main()
+    siblings()

@@ -584,3 +584,46 @@ def test_emulated_random_configurations(emu):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "emu_stress.py"), "777", "14", "120"], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and " bad 0 " in r.stdout, r.stdout[-2000:]
+
+
+def test_emulated_sibling_tools_on_the_golden_vectors(emu):
+    """The sibling sweep tools (algebras 1-9 of sweep_warp.cu) on the emulated thread model against tests/golden/siblings.npz — outputs of
+    the reference executables (tests/golden/make_golden.py::siblings) on the hills_holes case, whose cells are 30 x 20 m (oblong: the
+    prop() table is not the square one)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hills_holes.npz"))
+    x = np.load(os.path.join(ROOT, "tests", "golden", "siblings.npz"))
+    dx, dy = float(g["dx"]), float(g["dy"])
+    p, ang, w = g["p"], g["ang"], g["w"]
+    ny, nx = p.shape
+    kw = dict(dx=dx, dy=dy)
+    assert_bits(_run(emu, False, 10, 0, p, x["sa"], True, 81, **kw), x["ssa_max"], "ssa max")
+    assert_bits(_run(emu, False, 11, 0, p, x["sa"], False, 82, **kw), x["ssa_min_nc"], "ssa min -nc")
+
+    def gridnet(okgrid):
+        out = []
+        for mode in (13, 14, 15):
+            res = np.empty((ny, nx), np.float32)
+            d = np.ascontiguousarray(p)
+            emu.emu_set_dm(None if okgrid is None else okgrid.ctypes.data, C.c_float(0.0))
+            assert emu.emu_sweep(0, mode, 0, d.ctypes.data, res.ctypes.data, None, nx, ny, -32768.0, 0, 0, -1.0, dx, dy, 90 + mode, 1, None, None, None, -1) == 0
+            out.append(res)
+        emu.emu_set_dm(None, C.c_float(0.0))
+        return out[0], out[1], out[2].astype(np.int16)
+
+    for suffix, ok in (("", None), ("_m", np.ascontiguousarray((x["gn_mask"] >= 5).astype(np.float32)))):
+        plen, tlen, gord = gridnet(ok)
+        assert_bits(plen, x["plen" + suffix], "plen" + suffix); assert_bits(tlen, x["tlen" + suffix], "tlen" + suffix); assert_bits(gord, x["gord" + suffix], "gord" + suffix)
+    dm, q, dg, tc, cs = (np.ascontiguousarray(x[k]) for k in ("dm", "q", "dg", "tc", "cs"))
+    emu.emu_set_dm(dm.ctypes.data, C.c_float(-9999.0))
+    assert_bits(_run(emu, True, 12, 0, ang, None, True, 83, **kw), x["dsca"], "dsca")
+    assert_bits(_run(emu, True, 12, 0, ang, w, False, 84, **kw), x["dsca_w_nc"], "dsca -wg -nc")
+    emu.emu_set_extra(dg.ctypes.data, C.c_float(2.5), None, C.c_float(0.0), None, None)
+    assert_bits(_run(emu, True, 16, 0, ang, q, True, 85, **kw), x["ctpt"], "ctpt")
+    assert_bits(_run(emu, True, 16, 0, ang, q, False, 86, **kw), x["ctpt_nc"], "ctpt -nc")
+    dep, cout = np.empty((ny, nx), np.float32), np.empty((ny, nx), np.float32)
+    emu.emu_set_dm(tc.ctypes.data, C.c_float(-9999.0))
+    emu.emu_set_extra(None, C.c_float(0.0), None, C.c_float(0.0), dep.ctypes.data, None)
+    assert_bits(_run(emu, True, 17, 0, ang, q, True, 87, **kw), x["tla"], "tla"); assert_bits(dep, x["tdep"], "tdep")
+    emu.emu_set_extra(None, C.c_float(0.0), cs.ctypes.data, C.c_float(-9999.0), dep.ctypes.data, cout.ctypes.data)
+    assert_bits(_run(emu, True, 18, 0, ang, q, False, 88, **kw), x["tla_c"], "tla -cs -nc"); assert_bits(dep, x["tdep_c"], "tdep -cs -nc"); assert_bits(cout, x["ctpt_c"], "ctpt -cs -nc")
+    emu.emu_set_dm(None, C.c_float(0.0))

@@ -9,7 +9,8 @@ ANG_ND = -3.4028234663852886e38
 
 
 def golden_cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+    # (siblings.npz holds the outputs of the nine tools of SURVEY.md 8(f) on the hills_holes case: not a pipeline case of its own)
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))) if n != "siblings")
 
 
 def load_golden(name):
