@@ -627,3 +627,36 @@ def test_emulated_sibling_tools_on_the_golden_vectors(emu):
     emu.emu_set_extra(None, C.c_float(0.0), cs.ctypes.data, C.c_float(-9999.0), dep.ctypes.data, cout.ctypes.data)
     assert_bits(_run(emu, True, 18, 0, ang, q, False, 88, **kw), x["tla_c"], "tla -cs -nc"); assert_bits(dep, x["tdep_c"], "tdep -cs -nc"); assert_bits(cout, x["ctpt_c"], "ctpt -cs -nc")
     emu.emu_set_dm(None, C.c_float(0.0))
+
+
+def test_emulated_stencils_on_odd_shapes(emu):
+    """The tile-ring kernels (k_fill_init, k_deps_d8) and k_deps_dinf on grids narrower / shorter than a tile, one cell wide, a few columns
+    past a tile edge: the rim logic of the staged tiles (columns off the grid, partial words, halo rows that do not exist)."""
+    from oracle import port
+    rng = np.random.default_rng(11)
+    MISS = -3.4028234663852886e38
+    for ny, nx in ((1, 1), (1, 7), (5, 3), (2, 260), (33, 129), (65, 132), (7, 127), (130, 5)):
+        p = rng.integers(1, 9, (ny, nx)).astype(np.int16)
+        p[rng.random((ny, nx)) < 0.1] = -32768
+        p[rng.random((ny, nx)) < 0.05] = rng.choice(np.array([0, 9, -3, 100], np.int16))
+        a = (rng.random((ny, nx)) * 6.4).astype(np.float32)
+        k = rng.random((ny, nx)) < 0.4
+        a[k] = (np.float32(np.pi / 4) * rng.integers(0, 9, (ny, nx)).astype(np.float32))[k]
+        a[rng.random((ny, nx)) < 0.1] = np.float32(MISS)
+        node = np.empty((ny, nx), np.uint16); cnt = np.empty((ny, nx), np.uint8); area = np.empty((ny, nx), np.float32)
+        rn = np.empty((ny, nx), np.uint16); rc = np.empty((ny, nx), np.uint8)
+        d = np.ascontiguousarray(p)
+        assert emu.emu_deps_d8(d.ctypes.data, node.ctypes.data, cnt.ctypes.data, area.ctypes.data, nx, ny, -32768) == 0
+        assert emu.emu_ref_deps(0, d.ctypes.data, rn.ctypes.data, rc.ctypes.data, nx, ny, -32768.0, 30.0, 30.0) == 0
+        assert np.array_equal(node, rn) and np.array_equal(cnt, rc) and np.all(area == -1.0), f"k_deps_d8 on {ny} x {nx}"
+        d = np.ascontiguousarray(a)
+        assert emu.emu_deps_dinf(d.ctypes.data, node.ctypes.data, cnt.ctypes.data, area.ctypes.data, nx, ny, MISS, 10.0, 25.0) == 0
+        assert emu.emu_ref_deps(1, d.ctypes.data, rn.ctypes.data, rc.ctypes.data, nx, ny, MISS, 10.0, 25.0) == 0
+        assert np.array_equal(node, rn) and np.array_equal(cnt, rc), f"k_deps_dinf on {ny} x {nx}"
+        dem = np.ascontiguousarray(synth.gen_dem(max(ny, 4), max(nx, 4), seed=ny * 31 + nx, hurst=0.7, tilt=0.3)[:ny, :nx])
+        dem[rng.random((ny, nx)) < 0.08] = -9999.0
+        mask = np.ascontiguousarray((rng.random((ny, nx)) < 0.05).astype(np.int16))
+        for four in (0, 1):
+            out = np.empty((ny, nx), np.float32)
+            assert emu.emu_fill(dem.ctypes.data, out.ctypes.data, mask.ctypes.data, nx, ny, -9999.0, four, 5) == 0
+            assert_bits(out, port.pitremove(dem, four_way=bool(four), depmask=mask), f"fel on {ny} x {nx}, 4-way {four}")
